@@ -1,0 +1,340 @@
+"""ctypes / numpy view of include/bpt/bpt.h.
+
+The same POD layouts are used by the CUDA library (`libbpt.so`, prefix ``bpt_``) and, in the
+tests only, by the CPU oracle (`liboracle.so`, prefix ``obpt_``) — that is what makes the parity
+tests read "same calls, same inputs, two implementations".
+
+Nothing here computes: it marshals host buffers across the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+# ---------------------------------------------------------------------------------------------
+# POD layouts (numpy dtypes, byte-identical to the C structs; sizes asserted below)
+# ---------------------------------------------------------------------------------------------
+f32, u32, i32, u64 = np.float32, np.uint32, np.int32, np.uint64
+
+DRAWABLE_SBT = np.dtype([(n, u32) for n in (
+    "drawable_index", "position_offset", "normal_offset", "tangent_offset", "color_offset",
+    "texcoord_offset", "texcoord2_offset", "index_offset", "material_offset")])
+BLAS_DESC = np.dtype([("position_offset", u32), ("index_offset", u32), ("num_triangles", u32), ("reserved", u32)])
+INSTANCE_DESC = np.dtype([("transform", f32, (3, 4)), ("instance_id_and_mask", u32),
+                          ("sbt_offset_and_flags", u32), ("blas", u64)])
+MATERIAL = np.dtype([("base_color", f32, 4), ("emission", f32, 3), ("roughness", f32), ("metallic", f32),
+                     ("normal_map_scale", f32), ("occlusion_strength", f32), ("flags", u32),
+                     ("base_color_tex", i32), ("metallic_roughness_tex", i32), ("normal_map_tex", i32),
+                     ("occlusion_tex", i32)])
+DIR_LIGHT = np.dtype([("emission", f32, 3), ("sm_index", i32), ("direction", f32, 3), ("shadow_strength", f32),
+                      ("cascade_shadow_radius_sqr", f32, 4), ("shadow_depth_bias", f32),
+                      ("shadow_normal_bias", f32), ("_pad1", f32, 2)])
+POINT_LIGHT = np.dtype([("emission", f32, 3), ("range_sqr_inv", f32), ("position", f32, 3), ("cos_inner", f32),
+                        ("direction", f32, 3), ("cos_outer", f32), ("sm_index", i32), ("shadow_strength", f32),
+                        ("shadow_depth_bias", f32), ("shadow_normal_bias", f32)])
+RECT_LIGHT = np.dtype([("emission", f32, 3), ("texture_index", i32), ("center_position", f32, 3), ("two_sided", u32),
+                       ("position0", f32, 3), ("inv_width_sqr", f32), ("position1", f32, 3), ("inv_height_sqr", f32),
+                       ("position2", f32, 3), ("inv_texel_size", f32), ("position3", f32, 3), ("_pad1", f32),
+                       ("normal", f32, 3), ("_pad2", f32)])
+BVH_NODE = np.dtype([(n, f32) for n in (
+    "c0_lo_x", "c0_hi_x", "c0_lo_y", "c0_hi_y", "c1_lo_x", "c1_hi_x", "c1_lo_y", "c1_hi_y",
+    "c0_lo_z", "c0_hi_z", "c1_lo_z", "c1_hi_z")] + [("child0", i32), ("child1", i32), ("parent", i32), ("reserved", u32)])
+RAY = np.dtype([("origin", f32, 3), ("tmin", f32), ("direction", f32, 3), ("tmax", f32)])
+HIT = np.dtype([("t", f32), ("u", f32), ("v", f32), ("instance", u32), ("primitive", u32)])
+
+assert DRAWABLE_SBT.itemsize == 36 and BLAS_DESC.itemsize == 16 and INSTANCE_DESC.itemsize == 64
+assert MATERIAL.itemsize == 64 and DIR_LIGHT.itemsize == 64 and POINT_LIGHT.itemsize == 64
+assert RECT_LIGHT.itemsize == 112 and BVH_NODE.itemsize == 64 and RAY.itemsize == 32 and HIT.itemsize == 20
+
+# enums
+VA_POSITION, VA_NORMAL, VA_TANGENT, VA_COLOR, VA_TEXCOORD, VA_TEXCOORD2 = 1, 2, 4, 8, 16, 32
+INSTANCE_FORCE_OPAQUE, INSTANCE_FORCE_NON_OPAQUE = 4, 8
+MATERIAL_KIND_GLTF_PBR, MATERIAL_KIND_ASSIMP_DIFFUSE, MATERIAL_KIND_DEFAULT = 0, 1, 2
+SURFACE_MODEL_UNLIT, SURFACE_MODEL_LIT = 0, 1
+BLEND_OPAQUE, BLEND_ALPHA_TEST, BLEND_TRANSLUCENT = 0, 1, 2
+MATERIAL_FLAG_TWO_SIDED = 1
+TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32_FLOAT = 0, 1
+ADDRESS_REPEAT, ADDRESS_CLAMP = 0, 1
+ACCEL_TWO_LEVEL, ACCEL_MERGED = 0, 1
+NEE_SHADOW_RAY, NEE_NONE = 0, 1
+BVH_TLAS = 0xFFFFFFFF
+
+STATUS_NAMES = {0: "BPT_OK", 1: "BPT_ERR_INVALID", 2: "BPT_ERR_CUDA", 3: "BPT_ERR_OOM", 4: "BPT_ERR_STATE",
+                5: "BPT_ERR_NO_DEVICE", 6: "BPT_ERR_UNSUPPORTED"}
+
+
+def material_flags(kind=MATERIAL_KIND_GLTF_PBR, blend=BLEND_OPAQUE, model=SURFACE_MODEL_LIT, two_sided=False) -> int:
+    return (1 if two_sided else 0) | (kind << 8) | (blend << 16) | (model << 24)
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32), ("max_lights_per_vertex", C.c_uint32)]
+
+
+class GeometryStreams(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("num_position_floats", C.c_uint64),
+                ("normals", C.c_void_p), ("num_normal_floats", C.c_uint64),
+                ("tangents", C.c_void_p), ("num_tangent_floats", C.c_uint64),
+                ("colors", C.c_void_p), ("num_color_floats", C.c_uint64),
+                ("texcoords", C.c_void_p), ("num_texcoord_floats", C.c_uint64),
+                ("texcoords2", C.c_void_p), ("num_texcoord2_floats", C.c_uint64),
+                ("indices", C.c_void_p), ("num_indices", C.c_uint64)]
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32),
+                ("address_mode_u", C.c_uint32), ("address_mode_v", C.c_uint32), ("filter_linear", C.c_uint32)]
+
+
+class LtcLuts(C.Structure):
+    _fields_ = [("matrix_lut0", C.c_void_p), ("matrix_lut1", C.c_void_p), ("matrix_lut2", C.c_void_p), ("norm_lut", C.c_void_p)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("matrix_inv_view", C.c_float * 16), ("matrix_inv_proj", C.c_float * 16), ("matrix_proj_view", C.c_float * 16)]
+
+
+class Settings(C.Structure):
+    _fields_ = [("ray_length", C.c_float), ("max_bounces", C.c_uint32), ("accumulate", C.c_uint32), ("nee_mode", C.c_uint32),
+                ("rect_shadow", C.c_uint32), ("russian_roulette", C.c_uint32), ("pixel_jitter", C.c_uint32),
+                ("state_precision", C.c_uint32)]
+
+    def __init__(self, ray_length=100.0, max_bounces=3, accumulate=1, nee_mode=NEE_SHADOW_RAY, **kw):
+        super().__init__(ray_length=ray_length, max_bounces=max_bounces, accumulate=accumulate, nee_mode=nee_mode, **kw)
+
+
+class Counters(C.Structure):
+    _fields_ = [("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("extend_rays_per_bounce", C.c_uint64 * 16), ("shadow_rays_per_bounce", C.c_uint64 * 16)]
+
+
+class ProbeVolume(C.Structure):
+    _fields_ = [("base_position", C.c_float * 3), ("_pad0", C.c_float), ("frame_x", C.c_float * 3), ("_pad1", C.c_float),
+                ("frame_y", C.c_float * 3), ("_pad2", C.c_float), ("frame_z", C.c_float * 3), ("_pad3", C.c_float),
+                ("extent", C.c_float * 3), ("ray_length", C.c_float), ("probe_counts", C.c_uint32 * 3), ("rays_per_probe", C.c_uint32)]
+
+
+class BptError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str):
+        super().__init__(f"{where}: {STATUS_NAMES.get(status, status)} — {detail}")
+        self.status = status
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# Entry points every implementation of the boundary exports: name → (argtypes). restype is int
+# (bpt_status) unless listed in _SPECIAL.
+_VP, _U32, _U64, _PU32, _PU64 = C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+COMMON_API = {
+    "create": [C.POINTER(Config), C.POINTER(_VP)],
+    "destroy": [_VP],
+    "resize": [_VP, _U32, _U32],
+    "scene_upload_geometry": [_VP, C.POINTER(GeometryStreams), _VP, _VP, _U32, _VP, _U32],
+    "scene_upload_instances": [_VP, _VP, _U32],
+    "scene_upload_materials": [_VP, _VP, _U32, C.POINTER(TextureDesc), _U32],
+    "scene_upload_lights": [_VP, _VP, _U32, _VP, _U32, _VP, _U32, C.POINTER(LtcLuts)],
+    "scene_upload_sky": [_VP, _VP, _U32, _VP, _VP],
+    "build_accel": [_VP, _U32],
+    "update_tlas": [_VP],
+    "debug_read_bvh": [_VP, _U32, _PU32, _VP, _VP, _VP, _U32, C.POINTER(C.c_int32)],
+    "clear_accum": [_VP],
+    "render": [_VP, C.POINTER(Camera), _U32, _U32, C.POINTER(Settings)],
+    "resolve": [_VP, _U32, _VP],
+    "get_counters": [_VP, C.POINTER(Counters)],
+    "reset_counters": [_VP],
+    "trace_rays": [_VP, _VP, _U64, _U32, _VP],
+    "trace_shadow_rays": [_VP, _VP, _U64, _U32, _VP],
+    "debug_capture": [_VP, _U32],
+    "debug_read_queue": [_VP, _U32, _U32, _VP, _VP, _VP, _U64, _PU64],
+    "trace_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _VP],
+}
+# Exported by the CUDA library only.
+BPT_ONLY_API = {
+    "set_stream": [_VP, _VP],
+    "sync": [_VP],
+    "resolve_device": [_VP, _U32, _VP],
+    "accum_device_ptr": [_VP, C.POINTER(_VP)],
+    "upload_accum": [_VP, _VP],
+}
+BPT_EXPORTS = sorted(["bpt_" + n for n in list(COMMON_API) + list(BPT_ONLY_API)] + ["bpt_last_error", "bpt_version"])
+
+
+class Library:
+    """A loaded implementation of the boundary: (shared object, symbol prefix)."""
+
+    def __init__(self, path: str, prefix: str, extra_api: dict | None = None):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing — build it first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "There is no fallback implementation.")
+        self.path, self.prefix = path, prefix
+        self.lib = C.CDLL(path)
+        api = dict(COMMON_API)
+        if extra_api:
+            api.update(extra_api)
+        for name, argtypes in api.items():
+            fn = getattr(self.lib, prefix + name)
+            fn.argtypes, fn.restype = argtypes, C.c_int
+        le = getattr(self.lib, prefix + "last_error")
+        le.argtypes, le.restype = [_VP], C.c_char_p
+
+    def fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+
+class Context:
+    """One bpt_context (or obpt_context): thin, explicit wrapper over the C entry points."""
+
+    def __init__(self, library: Library, width: int, height: int, device: int = 0):
+        self.L = library
+        self.width, self.height = int(width), int(height)
+        self._h = _VP()
+        cfg = Config(device=device, width=width, height=height, max_lights_per_vertex=0)
+        st = self.L.fn("create")(C.byref(cfg), C.byref(self._h))
+        if st != 0:
+            raise BptError(st, self.L.prefix + "create", "context creation failed (no CUDA device?)" if st == 5 else "")
+        self._keep = []
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _call(self, name, *args):
+        st = self.L.fn(name)(self._h, *args)
+        if st != 0:
+            detail = self.L.fn("last_error")(self._h)
+            raise BptError(st, self.L.prefix + name, detail.decode() if detail else "")
+
+    def close(self):
+        if self._h:
+            self.L.fn("destroy")(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scene ----------------------------------------------------------------------------------
+    def upload_scene(self, scene, accel_mode: int = ACCEL_TWO_LEVEL):
+        """`scene` is a scenes.SceneData. Uploads everything and builds the acceleration structure."""
+        g = GeometryStreams()
+        for name, arr in (("positions", scene.positions), ("normals", scene.normals), ("tangents", scene.tangents),
+                          ("colors", None), ("texcoords", scene.texcoords), ("texcoords2", None)):
+            setattr(g, name, _ptr(arr))
+            field = {"positions": "num_position_floats", "normals": "num_normal_floats", "tangents": "num_tangent_floats",
+                     "colors": "num_color_floats", "texcoords": "num_texcoord_floats", "texcoords2": "num_texcoord2_floats"}[name]
+            setattr(g, field, 0 if arr is None else arr.size)
+        g.indices, g.num_indices = _ptr(scene.indices), scene.indices.size
+        self._call("scene_upload_geometry", C.byref(g), _ptr(scene.drawables), _ptr(scene.drawable_va),
+                   len(scene.drawables), _ptr(scene.blas), len(scene.blas))
+        texs = (TextureDesc * max(1, len(scene.textures)))()
+        for i, t in enumerate(scene.textures):
+            texs[i] = TextureDesc(texels=_ptr(t["texels"]), width=t["width"], height=t["height"], format=t["format"],
+                                  address_mode_u=t.get("address_u", ADDRESS_REPEAT), address_mode_v=t.get("address_v", ADDRESS_REPEAT),
+                                  filter_linear=t.get("linear", 1))
+        self._call("scene_upload_materials", _ptr(scene.materials), len(scene.materials), texs, len(scene.textures))
+        self.upload_instances(scene.instances)
+        self.upload_lights(scene)
+        self.upload_sky(scene)
+        self._call("build_accel", accel_mode)
+
+    def upload_instances(self, instances):
+        self._call("scene_upload_instances", _ptr(instances), len(instances))
+
+    def upload_lights(self, scene):
+        luts = LtcLuts()
+        if scene.ltc_luts is not None:
+            luts.matrix_lut0, luts.matrix_lut1, luts.matrix_lut2, luts.norm_lut = (_ptr(a) for a in scene.ltc_luts)
+        self._call("scene_upload_lights", _ptr(scene.dir_lights), len(scene.dir_lights), _ptr(scene.point_lights),
+                   len(scene.point_lights), _ptr(scene.rect_lights), len(scene.rect_lights), C.byref(luts))
+
+    def upload_sky(self, scene):
+        xf = np.ascontiguousarray(scene.sky_transform, dtype=f32)
+        col = np.ascontiguousarray(scene.sky_color, dtype=f32)
+        size = 0 if scene.sky_faces is None else scene.sky_faces.shape[1]
+        self._call("scene_upload_sky", _ptr(scene.sky_faces), size, _ptr(xf), _ptr(col))
+
+    def build_accel(self, mode=ACCEL_TWO_LEVEL):
+        self._call("build_accel", mode)
+
+    def update_tlas(self):
+        self._call("update_tlas")
+
+    def read_bvh(self, which: int):
+        n, root = C.c_uint32(), C.c_int32()
+        self._call("debug_read_bvh", which, C.byref(n), None, None, None, 0, C.byref(root))
+        morton = np.zeros(n.value, dtype=u64)
+        prims = np.zeros(n.value, dtype=u32)
+        nodes = np.zeros(max(n.value - 1, 0), dtype=BVH_NODE)
+        self._call("debug_read_bvh", which, C.byref(n), _ptr(morton), _ptr(prims), _ptr(nodes) if len(nodes) else None,
+                   n.value, C.byref(root))
+        return {"n": n.value, "root": root.value, "morton": morton, "prims": prims, "nodes": nodes}
+
+    # -- render ---------------------------------------------------------------------------------
+    def clear_accum(self):
+        self._call("clear_accum")
+
+    def render(self, camera: Camera, frame_index_first: int, num_samples: int, settings: Settings):
+        self._call("render", C.byref(camera), frame_index_first, num_samples, C.byref(settings))
+
+    def resolve(self, total_samples: int) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), dtype=f32)
+        self._call("resolve", total_samples, _ptr(out))
+        return out
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self._call("get_counters", C.byref(c))
+        return c
+
+    def reset_counters(self):
+        self._call("reset_counters")
+
+    def trace_rays(self, rays: np.ndarray, frame_index: int = 0) -> np.ndarray:
+        assert rays.dtype == RAY
+        hits = np.zeros(len(rays), dtype=HIT)
+        self._call("trace_rays", _ptr(rays), len(rays), frame_index, _ptr(hits))
+        return hits
+
+    def trace_shadow_rays(self, rays: np.ndarray, frame_index: int = 0) -> np.ndarray:
+        assert rays.dtype == RAY
+        vis = np.zeros(len(rays), dtype=np.uint8)
+        self._call("trace_shadow_rays", _ptr(rays), len(rays), frame_index, _ptr(vis))
+        return vis
+
+    def debug_capture(self, enable: bool):
+        self._call("debug_capture", 1 if enable else 0)
+
+    def read_queue(self, bounce: int, kind: int):
+        n = C.c_uint64()
+        self._call("debug_read_queue", bounce, kind, None, None, None, 0, C.byref(n))
+        pixels = np.zeros(n.value, dtype=u32)
+        lights = np.zeros(n.value, dtype=u32) if kind == 1 else None
+        hits = np.zeros(n.value, dtype=HIT) if kind == 0 else None
+        if n.value:
+            self._call("debug_read_queue", bounce, kind, _ptr(pixels), _ptr(lights), _ptr(hits), n.value, C.byref(n))
+        return {"pixels": pixels, "lights": lights, "hits": hits}
+
+    # -- CUDA-library-only -----------------------------------------------------------------------
+    def set_stream(self, cuda_stream_handle: int):
+        self._call("set_stream", _VP(cuda_stream_handle))
+
+    def sync(self):
+        self._call("sync")
+
+    def accum_device_ptr(self) -> int:
+        p = _VP()
+        self._call("accum_device_ptr", C.byref(p))
+        return p.value
+
+    def resolve_device(self, total_samples: int, device_ptr: int):
+        self._call("resolve_device", total_samples, _VP(device_ptr))
+
+    def upload_accum(self, sums: np.ndarray):
+        self._call("upload_accum", _ptr(np.ascontiguousarray(sums, dtype=f32)))

@@ -1,0 +1,435 @@
+"""Seeded procedural scenes of the shapes BASELINE.json names (synthetic input only — no compute).
+
+Every generator returns a `SceneData` whose arrays are laid out exactly as the C ABI wants them
+(flat float/uint streams + DrawableSbtData / BLAS / instance records, include/bpt/bpt.h), i.e. the
+form the reference's GpuSceneSystem hands to its ray-tracing shaders
+(bisemutum/src/graphics/gpu_scene_data.hpp:10-24, drawable_stb_data.hpp:7-17).
+
+Importer semantics that the generators follow so the data looks like an imported glTF
+(bisemutum/src/scene_basic/menu_actions/import_model.cpp:27-430): POSITION/NORMAL/TEXCOORD_0 +
+per-vertex tangents with handedness in w, one drawable per (node, primitive), materials from the
+fixed metallic-roughness template (:208-230).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+f32, u32 = np.float32, np.uint32
+
+
+@dataclass
+class SceneData:
+    name: str
+    positions: np.ndarray
+    normals: np.ndarray
+    tangents: np.ndarray
+    texcoords: np.ndarray
+    indices: np.ndarray
+    drawables: np.ndarray
+    drawable_va: np.ndarray
+    blas: np.ndarray
+    instances: np.ndarray
+    materials: np.ndarray
+    textures: list = field(default_factory=list)
+    dir_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.DIR_LIGHT))
+    point_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.POINT_LIGHT))
+    rect_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.RECT_LIGHT))
+    ltc_luts: tuple | None = None
+    sky_faces: np.ndarray | None = None
+    sky_transform: np.ndarray = field(default_factory=lambda: np.eye(3, dtype=f32).reshape(9))
+    sky_color: np.ndarray = field(default_factory=lambda: np.ones(3, f32))
+    camera: dict = field(default_factory=dict)
+    bounds: tuple | None = None  # (lo, hi) world bounds, for light/probe placement
+
+    @property
+    def num_triangles(self) -> int:
+        """Instanced triangle count (what a ray can hit)."""
+        return int(sum(int(self.blas["num_triangles"][int(b)]) for b in self.instances["blas"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# mesh helpers
+# ---------------------------------------------------------------------------------------------
+def _normalize(v):
+    n = np.linalg.norm(v, axis=-1, keepdims=True)
+    n[n == 0] = 1.0
+    return v / n
+
+
+def grid_patch(nu, nv, pos_fn):
+    """(nu x nv) quad grid; pos_fn(u, v) -> (..., 3) with u, v in [0, 1]. Normals/tangents from
+    central differences of pos_fn (tangent = dP/du, handedness w from the uv orientation)."""
+    u = np.linspace(0.0, 1.0, nu + 1)
+    v = np.linspace(0.0, 1.0, nv + 1)
+    uu, vv = np.meshgrid(u, v, indexing="xy")           # (nv+1, nu+1)
+    P = pos_fn(uu, vv).astype(np.float64)
+    e = 1e-4
+    dPu = (pos_fn(uu + e, vv) - pos_fn(uu - e, vv)) / (2 * e)
+    dPv = (pos_fn(uu, vv + e) - pos_fn(uu, vv - e)) / (2 * e)
+    N = _normalize(np.cross(dPu, dPv))
+    T = _normalize(dPu - N * np.sum(N * dPu, -1, keepdims=True))
+    w = np.sign(np.sum(np.cross(N, T) * dPv, -1, keepdims=True))
+    w[w == 0] = 1.0
+    tang = np.concatenate([T, w], -1)
+    uv = np.stack([uu, vv], -1)
+    i0 = (np.arange(nv)[:, None] * (nu + 1) + np.arange(nu)[None, :]).reshape(-1)
+    tri = np.stack([np.stack([i0, i0 + 1, i0 + nu + 2], -1), np.stack([i0, i0 + nu + 2, i0 + nu + 1], -1)], 1).reshape(-1, 3)
+    return (P.reshape(-1, 3).astype(f32), N.reshape(-1, 3).astype(f32), tang.reshape(-1, 4).astype(f32),
+            uv.reshape(-1, 2).astype(f32), tri.astype(u32))
+
+
+def merge_meshes(meshes):
+    P, N, T, UV, I = [], [], [], [], []
+    base = 0
+    for (p, n, t, uv, i) in meshes:
+        P.append(p); N.append(n); T.append(t); UV.append(uv); I.append(i + base)
+        base += len(p)
+    return (np.concatenate(P), np.concatenate(N), np.concatenate(T), np.concatenate(UV), np.concatenate(I).astype(u32))
+
+
+def box_mesh(lo, hi, n=4):
+    """Axis-aligned box, outward normals, each face an n x n grid."""
+    lo, hi = np.asarray(lo, np.float64), np.asarray(hi, np.float64)
+    faces = []
+    for axis in range(3):
+        a1, a2 = (axis + 1) % 3, (axis + 2) % 3
+        for side in (0, 1):
+            def fn(u, v, axis=axis, a1=a1, a2=a2, side=side):
+                p = np.zeros(u.shape + (3,))
+                p[..., axis] = hi[axis] if side else lo[axis]
+                uu = u if side else 1.0 - u     # keep outward orientation
+                p[..., a1] = lo[a1] + (hi[a1] - lo[a1]) * uu
+                p[..., a2] = lo[a2] + (hi[a2] - lo[a2]) * v
+                return p
+            faces.append(grid_patch(n, n, fn))
+    return merge_meshes(faces)
+
+
+def cylinder_mesh(radius, height, nseg, nring, bulge=0.0):
+    def fn(u, v):
+        ang = 2 * np.pi * u
+        r = radius * (1.0 + bulge * np.sin(np.pi * v) ** 2 + 0.03 * np.cos(8 * ang) * 1.0)
+        return np.stack([r * np.cos(ang), height * v, -r * np.sin(ang)], -1)
+    return grid_patch(nseg, nring, fn)
+
+
+def sphere_mesh(radius, nseg, nring, bumps=0.0, seed=0):
+    rng = np.random.default_rng(seed)
+    ph = rng.uniform(0, 2 * np.pi, 4)
+
+    def fn(u, v):
+        th = np.pi * (0.02 + 0.96 * v)
+        ang = 2 * np.pi * u
+        r = radius * (1.0 + bumps * (np.sin(5 * ang + ph[0]) * np.sin(4 * th + ph[1]) + 0.5 * np.sin(9 * ang + ph[2]) * np.sin(7 * th + ph[3])))
+        return np.stack([r * np.sin(th) * np.cos(ang), -r * np.cos(th), -r * np.sin(th) * np.sin(ang)], -1)
+    return grid_patch(nseg, nring, fn)
+
+
+class SceneBuilder:
+    """Collects meshes (→ flat streams + one BLAS each), materials and drawables (→ instances)."""
+
+    def __init__(self, name):
+        self.name = name
+        self.P, self.N, self.T, self.UV, self.I = [], [], [], [], []
+        self.nverts = 0
+        self.nidx = 0
+        self.meshes = []      # (vertex_base, index_offset, num_tris)
+        self.materials = []
+        self.drawables = []   # (mesh, material, transform 3x4, opaque)
+        self.textures = []
+
+    def add_mesh(self, mesh):
+        p, n, t, uv, idx = mesh
+        self.P.append(p); self.N.append(n); self.T.append(t); self.UV.append(uv); self.I.append(idx.reshape(-1))
+        self.meshes.append((self.nverts, self.nidx, len(idx)))
+        self.nverts += len(p)
+        self.nidx += idx.size
+        return len(self.meshes) - 1
+
+    def add_material(self, base_color=(0.5, 0.5, 0.5, 1.0), roughness=0.5, metallic=0.0, two_sided=False,
+                     blend=capi.BLEND_OPAQUE, kind=capi.MATERIAL_KIND_GLTF_PBR, model=capi.SURFACE_MODEL_LIT,
+                     normal_map_scale=1.0, occlusion_strength=1.0, base_color_tex=-1, metallic_roughness_tex=-1,
+                     normal_map_tex=-1, occlusion_tex=-1):
+        m = np.zeros((), capi.MATERIAL)
+        bc = list(base_color) + [1.0] * (4 - len(base_color))
+        m["base_color"] = bc
+        m["roughness"], m["metallic"] = roughness, metallic
+        m["normal_map_scale"], m["occlusion_strength"] = normal_map_scale, occlusion_strength
+        m["flags"] = capi.material_flags(kind, blend, model, two_sided)
+        m["base_color_tex"], m["metallic_roughness_tex"] = base_color_tex, metallic_roughness_tex
+        m["normal_map_tex"], m["occlusion_tex"] = normal_map_tex, occlusion_tex
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def add_texture(self, texels, fmt=capi.TEXTURE_RGBA8_UNORM, address=capi.ADDRESS_REPEAT, linear=1):
+        texels = np.ascontiguousarray(texels)
+        self.textures.append({"texels": texels, "width": texels.shape[1], "height": texels.shape[0], "format": fmt,
+                              "address_u": address, "address_v": address, "linear": linear})
+        return len(self.textures) - 1
+
+    def add_drawable(self, mesh, material, transform=None):
+        xf = np.eye(4, dtype=np.float64)[:3] if transform is None else np.asarray(transform, np.float64)[:3]
+        self.drawables.append((mesh, material, xf.astype(f32)))
+        return len(self.drawables) - 1
+
+    def finish(self, **kw) -> SceneData:
+        nd = len(self.drawables)
+        drawables = np.zeros(nd, capi.DRAWABLE_SBT)
+        instances = np.zeros(nd, capi.INSTANCE_DESC)
+        blas = np.zeros(len(self.meshes), capi.BLAS_DESC)
+        for b, (vb, io, nt) in enumerate(self.meshes):
+            blas[b] = (vb * 3, io, nt, 0)
+        mats = np.array(self.materials, dtype=capi.MATERIAL)
+        for i, (mesh, mat, xf) in enumerate(self.drawables):
+            vb, io, nt = self.meshes[mesh]
+            drawables[i] = (i, vb * 3, vb * 3, vb * 4, 0, vb * 2, 0, io, mat * capi.MATERIAL.itemsize)
+            blend = (int(mats[mat]["flags"]) >> 16) & 0xff
+            flag = capi.INSTANCE_FORCE_OPAQUE if blend == capi.BLEND_OPAQUE else capi.INSTANCE_FORCE_NON_OPAQUE
+            instances[i]["transform"] = xf
+            instances[i]["instance_id_and_mask"] = i | (0xff << 24)
+            instances[i]["sbt_offset_and_flags"] = i | (flag << 24)
+            instances[i]["blas"] = mesh
+        va = np.full(nd, capi.VA_POSITION | capi.VA_NORMAL | capi.VA_TANGENT | capi.VA_TEXCOORD, u32)
+        return SceneData(
+            name=self.name,
+            positions=np.ascontiguousarray(np.concatenate(self.P).reshape(-1), f32),
+            normals=np.ascontiguousarray(np.concatenate(self.N).reshape(-1), f32),
+            tangents=np.ascontiguousarray(np.concatenate(self.T).reshape(-1), f32),
+            texcoords=np.ascontiguousarray(np.concatenate(self.UV).reshape(-1), f32),
+            indices=np.ascontiguousarray(np.concatenate(self.I), u32),
+            drawables=drawables, drawable_va=va, blas=blas, instances=instances, materials=mats,
+            textures=self.textures, **kw)
+
+
+def translate(x, y, z):
+    m = np.eye(4)
+    m[:3, 3] = (x, y, z)
+    return m
+
+
+def rotate_y(a):
+    c, s = np.cos(a), np.sin(a)
+    m = np.eye(4)
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, s, -s, c
+    return m
+
+
+def scale(sx, sy=None, sz=None):
+    sy = sx if sy is None else sy
+    sz = sx if sz is None else sz
+    return np.diag([sx, sy, sz, 1.0])
+
+
+def random_rotation(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    m = np.eye(4)
+    m[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                 [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                 [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+    return m
+
+
+def dir_light(direction_to_light, color=(1.0, 0.9, 0.8), strength=4.0):
+    """DirLightData as LightsContext::collect_all_lights packs it (lights.cpp:52-63) with
+    cast_shadow irrelevant (shadow rays replace shadow maps)."""
+    l = np.zeros(1, capi.DIR_LIGHT)
+    d = np.asarray(direction_to_light, np.float64)
+    l["emission"] = (np.asarray(color, f32) * f32(strength)).astype(f32)
+    l["direction"] = (d / np.linalg.norm(d)).astype(f32)
+    l["sm_index"] = -1
+    return l
+
+
+def procedural_sky(size=256, sun_dir=(0.3, 1.0, 0.2), seed=0):
+    """Gradient + sun-lobe cubemap, 6 x size x size x 4 float32, Vulkan face order."""
+    s = (np.arange(size) + 0.5) / size * 2.0 - 1.0
+    ux, uy = np.meshgrid(s, s, indexing="xy")       # uv.x along columns, uv.y along rows
+    one = np.ones_like(ux)
+    dirs = [np.stack([one, -uy, -ux], -1), np.stack([-one, -uy, ux], -1), np.stack([ux, one, uy], -1),
+            np.stack([ux, -one, -uy], -1), np.stack([ux, -uy, one], -1), np.stack([-ux, -uy, -one], -1)]
+    sd = np.asarray(sun_dir, np.float64)
+    sd /= np.linalg.norm(sd)
+    faces = np.zeros((6, size, size, 4), f32)
+    for f, d in enumerate(dirs):
+        d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+        t = np.clip(d[..., 1] * 0.5 + 0.5, 0, 1)[..., None]
+        horizon, zenith = np.array([0.85, 0.9, 1.0]), np.array([0.25, 0.45, 0.9])
+        col = horizon * (1 - t) + zenith * t
+        col = np.where(d[..., 1:2] < 0, np.array([0.18, 0.16, 0.14]) * (1 + d[..., 1:2] * 0.5), col)
+        lobe = np.clip(np.sum(d * sd, -1), 0, 1)[..., None]
+        col = col + np.array([1.0, 0.9, 0.7]) * (lobe ** 64) * 4.0
+        faces[f, ..., :3] = col
+        faces[f, ..., 3] = 1.0
+    return faces
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[0]: Cornell box, 512x512, 16 spp, max depth 5, one directional light
+# ---------------------------------------------------------------------------------------------
+def cornell_box(tess=16) -> SceneData:
+    b = SceneBuilder("cornell_box")
+    white = b.add_material((0.73, 0.73, 0.73), roughness=0.9)
+    red = b.add_material((0.65, 0.05, 0.05), roughness=0.9)
+    green = b.add_material((0.12, 0.45, 0.15), roughness=0.9)
+    metal = b.add_material((0.9, 0.85, 0.6), roughness=0.25, metallic=1.0)
+    glossy = b.add_material((0.2, 0.3, 0.8), roughness=0.35)
+
+    def quad(o, du, dv):
+        o, du, dv = (np.asarray(a, np.float64) for a in (o, du, dv))
+        return grid_patch(tess, tess, lambda u, v: o + u[..., None] * du + v[..., None] * dv)
+    # room x,z in [-1,1], y in [0,2], open towards +z; normals point inwards
+    b.add_drawable(b.add_mesh(quad((-1, 0, 1), (2, 0, 0), (0, 0, -2))), white)     # floor   (+y)
+    b.add_drawable(b.add_mesh(quad((-1, 2, -1), (2, 0, 0), (0, 0, 2))), white)     # ceiling (-y)
+    b.add_drawable(b.add_mesh(quad((-1, 0, -1), (2, 0, 0), (0, 2, 0))), white)     # back    (+z)
+    b.add_drawable(b.add_mesh(quad((-1, 0, 1), (0, 0, -2), (0, 2, 0))), red)       # left    (+x)
+    b.add_drawable(b.add_mesh(quad((1, 0, -1), (0, 0, 2), (0, 2, 0))), green)      # right   (-x)
+    box = b.add_mesh(box_mesh((-0.5, 0.0, -0.5), (0.5, 1.0, 0.5), n=max(2, tess // 4)))
+    b.add_drawable(box, metal, translate(-0.35, 0, -0.3) @ rotate_y(0.3) @ scale(0.6, 1.2, 0.6))
+    b.add_drawable(box, white, translate(0.4, 0, 0.3) @ rotate_y(-0.3) @ scale(0.6, 0.6, 0.6))
+    ball = b.add_mesh(sphere_mesh(0.25, 4 * tess // 2, 2 * tess // 2))
+    b.add_drawable(ball, glossy, translate(0.4, 0.6 + 0.25, 0.3))
+    cam = dict(position=(0.0, 1.0, 4.6), front_dir=(0.0, 0.0, -1.0), up_dir=(0.0, 1.0, 0.0), yfov=30.0, near_z=0.001, far_z=1e5)
+    return b.finish(dir_lights=dir_light((0.25, 0.55, 1.0), (1.0, 0.9, 0.8), 4.0), camera=cam,
+                    bounds=(np.array([-1, 0, -1.0]), np.array([1, 2, 1.0])))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[1]: procedural Sponza-scale atrium, ~262k triangles, 25 PBR materials,
+# directional light + skybox (README gallery set-up). Seed fixed by SURVEY §8d.
+# ---------------------------------------------------------------------------------------------
+ATRIUM_SEED = 0x5B0A2A1D
+ATRIUM_TRIANGLES = 262144
+
+
+def atrium(seed: int = ATRIUM_SEED, target_triangles: int = ATRIUM_TRIANGLES, sky_size: int = 256) -> SceneData:
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder("atrium")
+    mats = []
+    for _ in range(25):   # base U[0.05,0.9]^3, roughness U[0.1,1], metallic in {0,1} p=0.2
+        mats.append(b.add_material(tuple(rng.uniform(0.05, 0.9, 3)), roughness=float(rng.uniform(0.1, 1.0)),
+                                   metallic=1.0 if rng.uniform() < 0.2 else 0.0))
+    nxt = iter(range(10 ** 9))
+
+    def mat():
+        return mats[next(nxt) % 25]
+    LX, LY, LZ = 18.0, 12.0, 7.0     # half length, height, half width of the hall
+
+    def quad(o, du, dv, nu, nv, bump=0.0, freq=6.0):
+        o, du, dv = (np.asarray(a, np.float64) for a in (o, du, dv))
+        n = np.cross(du, dv)
+        n = n / np.linalg.norm(n)
+        ph = rng.uniform(0, 6.28, 2)
+
+        def fn(u, v):
+            p = o + u[..., None] * du + v[..., None] * dv
+            if bump:
+                p = p + n * (bump * np.sin(freq * 2 * np.pi * u + ph[0]) * np.sin(freq * 2 * np.pi * v + ph[1]))[..., None]
+            return p
+        return grid_patch(nu, nv, fn)
+    # columns: two rows of 8, shared mesh (instancing), 64 x 32 quads each
+    col = b.add_mesh(cylinder_mesh(0.45, 5.0, 64, 32, bulge=0.12))
+    col_up = b.add_mesh(cylinder_mesh(0.32, 4.0, 48, 24, bulge=0.08))
+    xs = np.linspace(-LX + 2.5, LX - 2.5, 8)
+    for x in xs:
+        for z in (-3.6, 3.6):
+            b.add_drawable(col, mat(), translate(x, 0.0, z))
+            b.add_drawable(col_up, mat(), translate(x, 5.6, z))
+    # arches between neighbouring columns (half torus), one mesh instanced 14 times
+    def arch_fn(u, v):
+        a = np.pi * u
+        R, r = (xs[1] - xs[0]) * 0.5, 0.28
+        ang = 2 * np.pi * v
+        cx = -R * np.cos(a)
+        cy = R * np.sin(a) * 0.6
+        rr = r * (1 + 0.15 * np.cos(6 * a))
+        return np.stack([cx + rr * np.cos(ang) * (-np.cos(a)), cy + rr * np.cos(ang) * np.sin(a) * 0.6, rr * np.sin(ang)], -1)
+    arch = b.add_mesh(grid_patch(48, 16, arch_fn))
+    for i in range(7):
+        for z in (-3.6, 3.6):
+            b.add_drawable(arch, mat(), translate((xs[i] + xs[i + 1]) * 0.5, 5.0, z))
+    # gallery slabs on both sides (boxes) and balustrade spheres
+    slab = b.add_mesh(box_mesh((-LX, 5.25, -0.5), (LX, 5.6, 0.5), n=24))
+    b.add_drawable(slab, mat(), translate(0, 0, -5.2) @ scale(1, 1, 3.4))
+    b.add_drawable(slab, mat(), translate(0, 0, 5.2) @ scale(1, 1, 3.4))
+    orb = b.add_mesh(sphere_mesh(0.35, 64, 32, bumps=0.05, seed=seed & 0xffff))
+    for x in xs:
+        for z in (-3.6, 3.6):
+            b.add_drawable(orb, mat(), translate(x, 9.95, z) @ random_rotation(rng))
+    # drapes: wavy two-sided cloth hanging between the upper columns
+    drape_two_sided = [b.add_material(tuple(rng.uniform(0.1, 0.9, 3)), roughness=float(rng.uniform(0.5, 1.0)), two_sided=True) for _ in range(3)]
+    for i in range(6):
+        x0 = xs[i] + 0.6
+        w = (xs[1] - xs[0]) - 1.2
+        z = -3.6 if i % 2 == 0 else 3.6
+        ph = rng.uniform(0, 6.28, 3)
+
+        def drape_fn(u, v, x0=x0, w=w, z=z, ph=ph):
+            sag = 0.35 * np.sin(np.pi * u)
+            fold = 0.18 * np.sin(10 * np.pi * u + ph[0]) * (0.3 + v) + 0.05 * np.sin(23 * u + 9 * v + ph[1])
+            return np.stack([x0 + w * u, 9.4 - sag * (1 - v) - 3.4 * v, z + fold], -1)
+        b.add_drawable(b.add_mesh(grid_patch(96, 64, drape_fn)), drape_two_sided[i % 3])
+    # vases / planters on the floor: displaced spheres, per-instance rotation + scale
+    vase = b.add_mesh(sphere_mesh(0.6, 96, 48, bumps=0.12, seed=(seed >> 8) & 0xffff))
+    for i in range(10):
+        x = rng.uniform(-LX + 2, LX - 2)
+        z = rng.choice([-1.0, 1.0]) * rng.uniform(0.5, 2.6)
+        s = rng.uniform(0.6, 1.3)
+        b.add_drawable(vase, mat(), translate(x, 0.6 * s, z) @ rotate_y(rng.uniform(0, 6.28)) @ scale(s))
+    # shell: walls, end walls, ceiling ring with a central opening (the sky + sun come through it)
+    b.add_drawable(b.add_mesh(quad((-LX, 0, -LZ), (0, LY, 0), (2 * LX, 0, 0), 48, 144, bump=0.03)), mat())   # -z wall (+z normal)
+    b.add_drawable(b.add_mesh(quad((-LX, 0, LZ), (2 * LX, 0, 0), (0, LY, 0), 144, 48, bump=0.03)), mat())    # +z wall (-z normal)
+    b.add_drawable(b.add_mesh(quad((-LX, 0, -LZ), (0, 0, 2 * LZ), (0, LY, 0), 56, 48, bump=0.02)), mat())    # -x end  (+x normal)
+    b.add_drawable(b.add_mesh(quad((LX, 0, -LZ), (0, LY, 0), (0, 0, 2 * LZ), 48, 56, bump=0.02)), mat())     # +x end  (-x normal)
+    ox, oz = 11.0, 2.6    # half extents of the roof opening
+    b.add_drawable(b.add_mesh(quad((-LX, LY, -LZ), (2 * LX, 0, 0), (0, 0, LZ - oz), 96, 16)), mat())         # ceiling strips (-y normal)
+    b.add_drawable(b.add_mesh(quad((-LX, LY, oz), (2 * LX, 0, 0), (0, 0, LZ - oz), 96, 16)), mat())
+    b.add_drawable(b.add_mesh(quad((-LX, LY, -oz), (LX - ox, 0, 0), (0, 0, 2 * oz), 24, 16)), mat())
+    b.add_drawable(b.add_mesh(quad((ox, LY, -oz), (LX - ox, 0, 0), (0, 0, 2 * oz), 24, 16)), mat())
+    # floor last: its tessellation absorbs the remainder so the scene has exactly `target_triangles`
+    used = sum(b.meshes[m][2] for (m, _, _) in b.drawables)
+    remaining = target_triangles - used
+    if remaining < 2 * 64:
+        raise ValueError("target_triangles too small for the atrium layout")
+    nu = 256
+    nv = remaining // (2 * nu)
+    b.add_drawable(b.add_mesh(quad((-LX, 0, LZ), (2 * LX, 0, 0), (0, 0, -2 * LZ), nu, nv, bump=0.015, freq=20.0)), mat())
+    rest = remaining - 2 * nu * nv        # < 512 triangles: a plinth strip under the -x end wall
+    if rest >= 2:
+        b.add_drawable(b.add_mesh(quad((-LX + 0.01, 0.0, -LZ), (0, 0, 2 * LZ), (0, 0.4, 0), rest // 2, 1)), mat())
+    sun = (0.3, 1.0, 0.2)
+    cam = dict(position=(-LX + 1.5, 3.2, 0.6), front_dir=(1.0, 0.12, -0.03), up_dir=(0.0, 1.0, 0.0), yfov=30.0, near_z=0.001, far_z=1e5)
+    return b.finish(dir_lights=dir_light(sun, (1.0, 0.9, 0.8), 4.0), sky_faces=procedural_sky(sky_size, sun) if sky_size else None,
+                    camera=cam, bounds=(np.array([-LX, 0, -LZ]), np.array([LX, LY, LZ])))
+
+
+def small_test_scene(seed=7, with_translucent=True) -> SceneData:
+    """A few hundred triangles exercising: instancing with rotation + non-uniform scale, two-sided,
+    alpha-test and stochastic-opacity (any-hit) drawables, a metallic and a rough material."""
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder("small_test")
+    ground = b.add_material((0.6, 0.6, 0.55), roughness=0.8)
+    shiny = b.add_material((0.9, 0.6, 0.3), roughness=0.2, metallic=1.0)
+    rough = b.add_material((0.2, 0.5, 0.8), roughness=0.7)
+    two = b.add_material((0.7, 0.2, 0.6), roughness=0.6, two_sided=True)
+    cut = b.add_material((0.9, 0.9, 0.2, 0.005), roughness=0.5, blend=capi.BLEND_ALPHA_TEST, two_sided=True)
+    glass = b.add_material((0.3, 0.9, 0.4, 0.45), roughness=0.4, blend=capi.BLEND_TRANSLUCENT, two_sided=True)
+    b.add_drawable(b.add_mesh(grid_patch(12, 12, lambda u, v: np.stack([8 * u - 4, 0.15 * np.sin(5 * u) * np.cos(4 * v), 4 - 8 * v], -1))), ground)
+    ball = b.add_mesh(sphere_mesh(0.5, 16, 8, bumps=0.1, seed=3))
+    box = b.add_mesh(box_mesh((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5), n=2))
+    for i in range(6):
+        m = [shiny, rough, two][i % 3]
+        xf = translate(rng.uniform(-2.5, 2.5), rng.uniform(0.6, 1.6), rng.uniform(-2.5, 2.5)) @ random_rotation(rng) @ scale(*rng.uniform(0.5, 1.4, 3))
+        b.add_drawable(ball if i % 2 == 0 else box, m, xf)
+    sheet = b.add_mesh(grid_patch(4, 4, lambda u, v: np.stack([3 * u - 1.5, 0.3 + 2.2 * v, 0 * u + 1.2], -1)))
+    if with_translucent:
+        b.add_drawable(sheet, glass)
+        b.add_drawable(sheet, cut, translate(0, 0, 0.6))
+    cam = dict(position=(0.3, 2.2, 6.5), front_dir=(-0.03, -0.22, -1.0), up_dir=(0.0, 1.0, 0.0), yfov=40.0, near_z=0.001, far_z=1e5)
+    return b.finish(dir_lights=dir_light((0.4, 1.0, 0.6), (1.0, 0.95, 0.9), 3.0), sky_faces=procedural_sky(16, (0.4, 1.0, 0.6)),
+                    camera=cam, bounds=(np.array([-4, 0, -4.0]), np.array([4, 3, 4.0])))

@@ -1,0 +1,373 @@
+/*
+ * bpt.h — C ABI of the B200-native wavefront path tracer ("bpt").
+ *
+ * This is the drop-in boundary for ONE hot path of PepcyCh/bisemutum-engine: the wavefront
+ * path-tracing pass (`PathTracingPass`, bisemutum/src/renderer/pass/path_tracing.{hpp,cpp}).
+ * A `CudaPathTracingPass` with the same two methods (`update_params`, `render`) calls only the
+ * functions below; see INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *  - Every function returns a bpt_status (0 = ok). No exceptions or longjmp cross this boundary.
+ *  - One bpt_context per GPU. A context is NOT thread-safe; all work is ordered on one CUDA
+ *    stream (bpt_set_stream) and is asynchronous until bpt_sync / a host-reading call.
+ *  - All pointers are HOST pointers unless the parameter name ends in `_device`.
+ *  - Matrices are column-major float[16] exactly as glm uploads them (reference:
+ *    bisemutum/src/graphics/camera.cpp:96-108). 3x4 instance transforms are row-major
+ *    (reference: bisemutum/include/bisemutum/rhi/accel.hpp:48-55).
+ *  - Struct byte layouts marked "REF layout" are byte-identical to the reference structs so
+ *    that the engine can hand over its CPU-side vectors without repacking.
+ *
+ * There is no CPU fallback: every entry point that computes needs a CUDA device and fails
+ * with BPT_ERR_NO_DEVICE / BPT_ERR_CUDA otherwise.
+ */
+#ifndef BPT_H_
+#define BPT_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define BPT_API __declspec(dllexport)
+#else
+#define BPT_API __attribute__((visibility("default")))
+#endif
+
+typedef struct bpt_context bpt_context;
+
+typedef enum bpt_status {
+    BPT_OK = 0,
+    BPT_ERR_INVALID = 1,   /* bad argument / inconsistent scene description            */
+    BPT_ERR_CUDA = 2,      /* a CUDA runtime call failed (see bpt_last_error)           */
+    BPT_ERR_OOM = 3,       /* device allocation failed                                  */
+    BPT_ERR_STATE = 4,     /* call order violated (e.g. render before build_accel)      */
+    BPT_ERR_NO_DEVICE = 5, /* no CUDA device visible — there is no CPU path             */
+    BPT_ERR_UNSUPPORTED = 6
+} bpt_status;
+
+/* ---------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_config {
+    int32_t device;      /* CUDA ordinal */
+    uint32_t width;      /* camera target extent; reference: path_tracing.cpp:228-229 */
+    uint32_t height;
+    uint32_t max_lights_per_vertex; /* sizing hint for the shadow-ray queue; 0 = derive at upload_lights */
+} bpt_config;
+
+BPT_API bpt_status bpt_create(const bpt_config* cfg, bpt_context** out_ctx);
+BPT_API bpt_status bpt_destroy(bpt_context* ctx);
+BPT_API const char* bpt_last_error(const bpt_context* ctx);
+BPT_API const char* bpt_version(void);
+/* All later work is enqueued on `cuda_stream` (a cudaStream_t; NULL = legacy default stream). */
+BPT_API bpt_status bpt_set_stream(bpt_context* ctx, void* cuda_stream);
+BPT_API bpt_status bpt_sync(bpt_context* ctx);
+/* Re-allocates the per-path wavefront state for a new target extent (history is dropped,
+ * as the reference does when width/height change: path_tracing.cpp:231-246). */
+BPT_API bpt_status bpt_resize(bpt_context* ctx, uint32_t width, uint32_t height);
+
+/* ---------------------------------------------------------------------------------------
+ * Scene: geometry.  Replaces GpuSceneSystem / mesh upload / SBT fill:
+ *   bisemutum/src/graphics/gpu_scene_data.hpp:10-24 (flat float/uint streams)
+ *   bisemutum/src/graphics/drawable_stb_data.hpp:7-17 (DrawableSbtData, 36 B)
+ *   bisemutum/src/graphics/graphics_manager.cpp:1314-1330 (offsets are ELEMENT offsets into
+ *   the streams; material_offset is a BYTE offset into the material-params buffer)
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_geometry_streams {
+    const float* positions;   uint64_t num_position_floats;   /* 3 per vertex */
+    const float* normals;     uint64_t num_normal_floats;     /* 3 per vertex */
+    const float* tangents;    uint64_t num_tangent_floats;    /* 4 per vertex */
+    const float* colors;      uint64_t num_color_floats;      /* 3 per vertex, may be NULL */
+    const float* texcoords;   uint64_t num_texcoord_floats;   /* 2 per vertex */
+    const float* texcoords2;  uint64_t num_texcoord2_floats;  /* 2 per vertex, may be NULL */
+    const uint32_t* indices;  uint64_t num_indices;
+} bpt_geometry_streams;
+
+/* REF layout: DrawableSbtData, bisemutum/shaders/core/raytracing/hit.hlsl:7-17. */
+typedef struct bpt_drawable_sbt_data {
+    uint32_t drawable_index;
+    uint32_t position_offset;
+    uint32_t normal_offset;
+    uint32_t tangent_offset;
+    uint32_t color_offset;
+    uint32_t texcoord_offset;
+    uint32_t texcoord2_offset;
+    uint32_t index_offset;
+    uint32_t material_offset; /* bytes; multiple of sizeof(bpt_material) */
+} bpt_drawable_sbt_data;
+
+/* Vertex-attribute presence mask of a drawable (VERTEX_ATTRIBUTES_IN, hit.hlsl:35-149). */
+enum {
+    BPT_VA_POSITION = 1, BPT_VA_NORMAL = 2, BPT_VA_TANGENT = 4,
+    BPT_VA_COLOR = 8, BPT_VA_TEXCOORD = 16, BPT_VA_TEXCOORD2 = 32
+};
+
+/* One bottom-level structure per (mesh id, submesh): graphics_manager.cpp:616-654.
+ * Offsets are element offsets into the positions (floats) / indices streams. */
+typedef struct bpt_blas_desc {
+    uint32_t position_offset; /* floats; = mesh positions offset + base_vertex*3 */
+    uint32_t index_offset;    /* uints  */
+    uint32_t num_triangles;   /* min(submesh.num_indices, mesh.num_indices)/3 */
+    uint32_t reserved;
+} bpt_blas_desc;
+
+BPT_API bpt_status bpt_scene_upload_geometry(
+    bpt_context* ctx, const bpt_geometry_streams* streams,
+    const bpt_drawable_sbt_data* drawables, const uint32_t* drawable_vertex_attributes /* may be NULL = pos|normal|tangent|texcoord */,
+    uint32_t num_drawables,
+    const bpt_blas_desc* blas, uint32_t num_blas);
+
+/* REF layout (64 B): AccelerationStructureInstanceDesc, rhi/accel.hpp:48-55, filled as
+ * bisemutum/src/graphics/accel.cpp:104-132: instance_id = sbt_offset = continuous drawable
+ * index, mask 0xff, flags = force_opaque (4) iff blend_mode == opaque else force_non_opaque (8).
+ * `blas` holds the index into the bpt_blas_desc array instead of a GPU address. */
+typedef struct bpt_instance_desc {
+    float transform[3][4];
+    uint32_t instance_id_and_mask;   /* instance_id : 24 | mask : 8  */
+    uint32_t sbt_offset_and_flags;   /* sbt_offset  : 24 | flags : 8 */
+    uint64_t blas;
+} bpt_instance_desc;
+enum { BPT_INSTANCE_FORCE_OPAQUE = 4, BPT_INSTANCE_FORCE_NON_OPAQUE = 8 };
+
+BPT_API bpt_status bpt_scene_upload_instances(bpt_context* ctx, const bpt_instance_desc* instances, uint32_t num_instances);
+
+/* ---------------------------------------------------------------------------------------
+ * Scene: materials.  The reference's materials are HLSL snippets spliced at $MATERIAL_FUNCTION
+ * (hit.hlsl:166-173).  CUDA cannot run them, so a closed set of "material kinds" is offered,
+ * each the restatement of one snippet the reference ships.
+ * ------------------------------------------------------------------------------------- */
+enum {
+    BPT_MATERIAL_KIND_GLTF_PBR = 0,        /* import_model.cpp:208-230 */
+    BPT_MATERIAL_KIND_ASSIMP_DIFFUSE = 1,  /* import_model.cpp:490-493 (base_color, roughness) */
+    BPT_MATERIAL_KIND_DEFAULT = 2          /* surface_data_default, material/utils.hlsl:18-31 */
+};
+enum { BPT_SURFACE_MODEL_UNLIT = 0, BPT_SURFACE_MODEL_LIT = 1 };         /* material.hlsl:3-5 */
+enum { BPT_BLEND_OPAQUE = 0, BPT_BLEND_ALPHA_TEST = 1, BPT_BLEND_TRANSLUCENT = 2 };
+
+#define BPT_MATERIAL_FLAG_TWO_SIDED 1u
+#define BPT_MATERIAL_KIND_SHIFT 8
+#define BPT_MATERIAL_BLEND_SHIFT 16
+#define BPT_MATERIAL_MODEL_SHIFT 24
+
+/* 64-byte, 16-byte-aligned parameter record (the reference aligns records to 16 B in a byte
+ * buffer: graphics_manager.cpp:221-256). Texture indices: -1 = the importer's 1x1 default
+ * (white1x1 / normal1x1, import_model.cpp:186-203). */
+typedef struct bpt_material {
+    float base_color[4];
+    float emission[3];   /* carried for API fidelity; the PT G-buffer drops it (gbuffer.hlsl:18-33) */
+    float roughness;
+    float metallic;
+    float normal_map_scale;
+    float occlusion_strength;
+    uint32_t flags;      /* two_sided | kind<<8 | blend_mode<<16 | surface_model<<24 */
+    int32_t base_color_tex;
+    int32_t metallic_roughness_tex;
+    int32_t normal_map_tex;
+    int32_t occlusion_tex;
+} bpt_material;
+
+enum { BPT_TEXTURE_RGBA8_UNORM = 0, BPT_TEXTURE_RGBA32_FLOAT = 1 };
+enum { BPT_ADDRESS_REPEAT = 0, BPT_ADDRESS_CLAMP = 1 };
+typedef struct bpt_texture_desc {
+    const void* texels;   /* level 0 only (hit shaders have no derivatives → level 0) */
+    uint32_t width, height;
+    uint32_t format;
+    uint32_t address_mode_u, address_mode_v;
+    uint32_t filter_linear; /* 0 = nearest, 1 = bilinear (explicit FP32 lerp, no HW filtering) */
+} bpt_texture_desc;
+
+BPT_API bpt_status bpt_scene_upload_materials(
+    bpt_context* ctx, const bpt_material* materials, uint32_t num_materials,
+    const bpt_texture_desc* textures, uint32_t num_textures);
+
+/* ---------------------------------------------------------------------------------------
+ * Scene: lights.  REF layouts of bisemutum/src/renderer/context/lights.hpp:12-53
+ * (= shaders/renderer/lights_struct.hlsl:3-53), as packed by LightsContext::collect_all_lights
+ * (lights.cpp:48-244).
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_dir_light_data {      /* 64 B */
+    float emission[3]; int32_t sm_index;
+    float direction[3]; float shadow_strength;   /* direction points TO the light */
+    float cascade_shadow_radius_sqr[4];
+    float shadow_depth_bias; float shadow_normal_bias; float _pad1[2];
+} bpt_dir_light_data;
+
+typedef struct bpt_point_light_data {    /* 64 B */
+    float emission[3]; float range_sqr_inv;
+    float position[3]; float cos_inner;
+    float direction[3]; float cos_outer;
+    int32_t sm_index; float shadow_strength; float shadow_depth_bias; float shadow_normal_bias;
+} bpt_point_light_data;
+
+typedef struct bpt_rect_light_data {     /* 112 B */
+    float emission[3]; int32_t texture_index;
+    float center_position[3]; uint32_t two_sided;
+    float position0[3]; float inv_width_sqr;
+    float position1[3]; float inv_height_sqr;
+    float position2[3]; float inv_texel_size;
+    float position3[3]; float _pad1;
+    float normal[3]; float _pad2;
+} bpt_rect_light_data;
+
+/* LTC look-up tables, bisemutum/assets/textures/ltc_*.biasset: 8x8x64 texels each,
+ * matrix luts rgba32f (65536 B each), norm lut rg32f (32768 B). May be NULL iff num_rect == 0. */
+typedef struct bpt_ltc_luts {
+    const float* matrix_lut0; const float* matrix_lut1; const float* matrix_lut2; /* 8*8*64*4 floats */
+    const float* norm_lut;                                                          /* 8*8*64*2 floats */
+} bpt_ltc_luts;
+
+BPT_API bpt_status bpt_scene_upload_lights(
+    bpt_context* ctx,
+    const bpt_dir_light_data* dir_lights, uint32_t num_dir_lights,
+    const bpt_point_light_data* point_lights, uint32_t num_point_lights,
+    const bpt_rect_light_data* rect_lights, uint32_t num_rect_lights,
+    const bpt_ltc_luts* ltc_luts);
+
+/* Sky: six square rgba32f faces in Vulkan cube order (+X,-X,+Y,-Y,+Z,-Z), skybox_transform is
+ * the upper-left 3x3 (row-major here) applied to the miss direction, skybox_color multiplies the
+ * lookup (deferred_lighting_secondary.hlsl:24-29; skybox.hpp:9-17). faces == NULL → black 1x1. */
+BPT_API bpt_status bpt_scene_upload_sky(
+    bpt_context* ctx, const float* faces_rgba32f, uint32_t face_size,
+    const float skybox_transform[9], const float skybox_color[3]);
+
+/* ---------------------------------------------------------------------------------------
+ * Acceleration structure (replaces AccelerationStructure ctor, accel.cpp:11-159; rebuilt when
+ * instances change).  LBVH: 63-bit Morton of AABB centroids in scene bounds → stable LSD radix
+ * sort (code, primitive) → Karras-2012 hierarchy → bottom-up refit.
+ * ------------------------------------------------------------------------------------- */
+enum {
+    BPT_ACCEL_TWO_LEVEL = 0, /* one BLAS per bpt_blas_desc (object space) + TLAS over instances */
+    BPT_ACCEL_MERGED = 1     /* instances pre-transformed into one world-space BLAS              */
+};
+BPT_API bpt_status bpt_build_accel(bpt_context* ctx, uint32_t mode);
+/* Rebuilds only the TLAS after bpt_scene_upload_instances (the reference rebuilds its TLAS
+ * every frame: render_graph.cpp:818-825). Two-level mode only. */
+BPT_API bpt_status bpt_update_tlas(bpt_context* ctx);
+
+/* 64-byte node: both children's boxes live in the parent so one node fetch = four 16-B loads.
+ * child >= 0: internal node index; child < 0: leaf, ~child = sorted primitive slot. */
+typedef struct bpt_bvh_node {
+    float c0_lo_x, c0_hi_x, c0_lo_y, c0_hi_y;
+    float c1_lo_x, c1_hi_x, c1_lo_y, c1_hi_y;
+    float c0_lo_z, c0_hi_z, c1_lo_z, c1_hi_z;
+    int32_t child0, child1;
+    int32_t parent;     /* -1 for the root */
+    uint32_t reserved;
+} bpt_bvh_node;
+
+/* which: 0..num_blas-1 = that BLAS (in merged mode only 0 exists), 0xffffffff = the TLAS.
+ * Any out pointer may be NULL. `num_prims` receives the leaf count N; arrays need N
+ * (morton/prims) and max(N-1,0) (nodes) entries. */
+#define BPT_BVH_TLAS 0xffffffffu
+BPT_API bpt_status bpt_debug_read_bvh(
+    bpt_context* ctx, uint32_t which, uint32_t* num_prims,
+    uint64_t* sorted_morton, uint32_t* sorted_prims, bpt_bvh_node* nodes, uint32_t capacity,
+    int32_t* root);
+
+/* ---------------------------------------------------------------------------------------
+ * Render (replaces the GPU work recorded by PathTracingPass::render, path_tracing.cpp:224-488)
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_camera {
+    float matrix_inv_view[16];
+    float matrix_inv_proj[16];
+    float matrix_proj_view[16]; /* only compared by the host pass for history validity */
+} bpt_camera;
+
+enum { BPT_NEE_SHADOW_RAY = 0, BPT_NEE_NONE = 1 };
+enum { BPT_RECT_SHADOW_OFF = 0, BPT_RECT_SHADOW_MRP_RAY = 1 };
+enum { BPT_STATE_FP32 = 0, BPT_STATE_REFERENCE_FP16 = 1 };
+
+/* BasicRenderer::PathTracingSettings (renderer/basic.hpp:76-81) + the mode switches of
+ * SURVEY.md §0. Defaults (all-zero switches) are the parity configuration. */
+typedef struct bpt_settings {
+    float ray_length;        /* 100 */
+    uint32_t max_bounces;    /* clamped to [2,16] as path_tracing.cpp:187,290 */
+    uint32_t accumulate;     /* honoured by the host pass (history reset); kept for fidelity */
+    uint32_t nee_mode;
+    uint32_t rect_shadow;
+    uint32_t russian_roulette;
+    uint32_t pixel_jitter;
+    uint32_t state_precision;
+} bpt_settings;
+
+/* Zeroes the FP32 accumulation buffer (history invalid). */
+BPT_API bpt_status bpt_clear_accum(bpt_context* ctx);
+/* Adds `num_samples` samples (frame_index = frame_index_first + s, one reference "frame" each)
+ * for every pixel to the FP32 sum buffer. Asynchronous. */
+BPT_API bpt_status bpt_render(
+    bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index_first, uint32_t num_samples,
+    const bpt_settings* settings);
+/* out[p] = (sum[p].rgb * (1/total_samples), 1). Host destination (synchronises). */
+BPT_API bpt_status bpt_resolve(bpt_context* ctx, uint32_t total_samples, float* out_rgba32f);
+/* Same, written to device memory (no synchronisation). */
+BPT_API bpt_status bpt_resolve_device(bpt_context* ctx, uint32_t total_samples, float* out_rgba32f_device);
+/* Raw FP32 sum buffer (device pointer, W*H float4) for the multi-GPU reduce. */
+BPT_API bpt_status bpt_accum_device_ptr(bpt_context* ctx, float** out_device_ptr);
+/* Replaces the sum buffer contents from the host (checkpoint/resume of the history). */
+BPT_API bpt_status bpt_upload_accum(bpt_context* ctx, const float* sum_rgba32f);
+
+typedef struct bpt_counters {
+    uint64_t extend_rays;        /* rays actually traversed by the extend kernel          */
+    uint64_t shadow_rays;        /* rays actually traversed by the connect kernel         */
+    uint64_t samples;            /* pixel-samples started                                  */
+    uint64_t kernel_launches;    /* kernels launched by this library since last reset      */
+    uint64_t extend_rays_per_bounce[16];
+    uint64_t shadow_rays_per_bounce[16];
+} bpt_counters;
+BPT_API bpt_status bpt_get_counters(bpt_context* ctx, bpt_counters* out);   /* synchronises */
+BPT_API bpt_status bpt_reset_counters(bpt_context* ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * Debug / parity hooks
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_ray {       /* 32 B */
+    float origin[3]; float tmin;
+    float direction[3]; float tmax;
+} bpt_ray;
+typedef struct bpt_hit {       /* 16 B + ids */
+    float t;                   /* < 0 → miss */
+    float u, v;                /* barycentrics of vertex 1 and 2 */
+    uint32_t instance;         /* instance_id (continuous drawable index) */
+    uint32_t primitive;        /* triangle index inside its BLAS          */
+} bpt_hit;
+/* Closest-hit trace of an arbitrary host ray batch through the extend kernel
+ * (rt_gbuffer.hlsl:17-25 semantics; opacity rule of hits/rt_gbuffer_hit.hlsl:20-35 with
+ * `frame_index` as the opacity seed). */
+BPT_API bpt_status bpt_trace_rays(bpt_context* ctx, const bpt_ray* rays, uint64_t num_rays, uint32_t frame_index, bpt_hit* out_hits);
+/* Any-hit (occlusion) trace through the connect kernel; out_visible[i] = 1 if unoccluded. */
+BPT_API bpt_status bpt_trace_shadow_rays(bpt_context* ctx, const bpt_ray* rays, uint64_t num_rays, uint32_t frame_index, uint8_t* out_visible);
+
+/* When enabled, bpt_render(num_samples == 1) keeps, per bounce, the extend queue (pixel index
+ * per live path), the hit records and the shadow-ray queue (pixel, light) for read-back. */
+BPT_API bpt_status bpt_debug_capture(bpt_context* ctx, uint32_t enable);
+/* kind 0: extend queue → pixels[i], hits[i] (hits may be NULL).
+ * kind 1: shadow queue → pixels[i], lights[i] (index: dir lights first, then point lights). */
+BPT_API bpt_status bpt_debug_read_queue(
+    bpt_context* ctx, uint32_t bounce /* 1..max_bounces-1 */, uint32_t kind,
+    uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t capacity, uint64_t* count);
+
+/* ---------------------------------------------------------------------------------------
+ * DDGI-style probe tracing through the same extend/shade kernels
+ * (shaders/renderer/ddgi/trace_gbuffer.hlsl:10-51, ddgi/deferred_lighting.hlsl:12-118).
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_probe_volume {
+    float base_position[3]; float _pad0;
+    float frame_x[3]; float _pad1;
+    float frame_y[3]; float _pad2;
+    float frame_z[3]; float _pad3;
+    float extent[3]; float ray_length;
+    uint32_t probe_counts[3];
+    uint32_t rays_per_probe;
+} bpt_probe_volume;
+/* out_radiance_dist: num_probes*rays_per_probe float4 = (radiance rgb, hit distance or -1). */
+BPT_API bpt_status bpt_trace_probes(
+    bpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2 /* 8192 float2 */,
+    uint32_t frame_index, uint32_t num_bounces, float* out_radiance_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPT_H_ */

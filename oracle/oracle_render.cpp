@@ -1,0 +1,579 @@
+// oracle_render.cpp — TEST INFRASTRUCTURE ONLY (CPU oracle).
+//
+// Per-pixel restatement of the reference's wavefront path tracer:
+//   host loop        bisemutum/src/renderer/pass/path_tracing.cpp:224-488
+//   camera ray       shaders/renderer/raytracing/direction_sample/generate_camera_ray.hlsl:4-16
+//   trace            shaders/renderer/raytracing/rt_gbuffer.hlsl:7-36
+//   closest hit      shaders/renderer/raytracing/hits/rt_gbuffer_hit.hlsl:6-18
+//                    shaders/core/raytracing/hit.hlsl:27-173
+//   lighting         shaders/renderer/raytracing/deferred_lighting_secondary.hlsl:11-111
+//                    shaders/renderer/lights.hlsl:10-25
+//   next direction   shaders/renderer/raytracing/direction_sample/sample_secondary_ray.hlsl:11-69
+//   accumulate       shaders/renderer/raytracing/pt_accumulate.hlsl:3-11 (as FP32 sum / N)
+// with state_precision = fp32 (no fp16/unorm G-buffer quantisation) and NEE visibility by
+// shadow ray instead of the reference's rasterised shadow maps (NEW).
+#include <algorithm>
+#include <cfloat>
+#include <thread>
+#include "oracle_scene.hpp"
+#include "oracle_ltc.hpp"
+
+namespace orc {
+
+// ---- textures: explicit FP32 bilinear (no 8-bit HW filter weights; SURVEY §7 hard parts) -----
+static inline f4 fetch_texel(const Texture& t, int x, int y) {
+    size_t i = (size_t)y * t.w + x;
+    if (t.format == BPT_TEXTURE_RGBA8_UNORM) {
+        const uint8_t* p = &t.texels[i * 4];
+        return f4{(float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f, (float)p[3] / 255.0f};
+    }
+    const float* p = reinterpret_cast<const float*>(t.texels.data()) + i * 4;
+    return f4{p[0], p[1], p[2], p[3]};
+}
+static inline int wrap_coord(int c, int n, uint32_t mode) {
+    if (mode == BPT_ADDRESS_REPEAT) { int m = c % n; return m < 0 ? m + n : m; }
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+static inline f4 lerp4(f4 a, f4 b, float t) {
+    return f4{a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t};
+}
+static inline f4 sample_texture(const Texture& t, float u, float v) {
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    if (!t.linear) {
+        int xi = wrap_coord((int)floorf(u * (float)t.w), (int)t.w, t.addr_u);
+        int yi = wrap_coord((int)floorf(v * (float)t.h), (int)t.h, t.addr_v);
+        return fetch_texel(t, xi, yi);
+    }
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = wrap_coord((int)x0f, (int)t.w, t.addr_u), x1 = wrap_coord((int)x0f + 1, (int)t.w, t.addr_u);
+    int y0 = wrap_coord((int)y0f, (int)t.h, t.addr_v), y1 = wrap_coord((int)y0f + 1, (int)t.h, t.addr_v);
+    f4 top = lerp4(fetch_texel(t, x0, y0), fetch_texel(t, x1, y0), fx);
+    f4 bot = lerp4(fetch_texel(t, x0, y1), fetch_texel(t, x1, y1), fx);
+    return lerp4(top, bot, fy);
+}
+static inline f4 sample_or_default(const Scene& sc, int32_t tex, f2 uv, f4 dflt) {
+    if (tex < 0 || (size_t)tex >= sc.textures.size()) return dflt;
+    return sample_texture(sc.textures[tex], uv.x, uv.y);
+}
+
+// ---- sky: deferred_lighting_secondary.hlsl:24-29; face/uv selection is the Vulkan cube rule,
+//      the inverse of core/utils/cubemap.hlsl:3-21; bilinear inside the face, clamp to edge. ----
+static inline f3 sample_sky(const Scene& sc, f3 d) {
+    if (sc.sky_size == 0) return splat3(0.0f);
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int face; float sc_, tc, ma;
+    if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; ma = ax; sc_ = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; }
+    else if (ay >= az) { face = d.y >= 0.0f ? 2 : 3; ma = ay; sc_ = d.x; tc = d.y >= 0.0f ? d.z : -d.z; }
+    else { face = d.z >= 0.0f ? 4 : 5; ma = az; sc_ = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; }
+    if (!(ma > 0.0f)) return splat3(0.0f);
+    float u = 0.5f * (sc_ / ma + 1.0f), v = 0.5f * (tc / ma + 1.0f);
+    int n = (int)sc.sky_size;
+    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = wrap_coord((int)x0f, n, BPT_ADDRESS_CLAMP), x1 = wrap_coord((int)x0f + 1, n, BPT_ADDRESS_CLAMP);
+    int y0 = wrap_coord((int)y0f, n, BPT_ADDRESS_CLAMP), y1 = wrap_coord((int)y0f + 1, n, BPT_ADDRESS_CLAMP);
+    const float* base = &sc.sky_faces[(size_t)face * n * n * 4];
+    auto tx = [&](int xx, int yy) { const float* p = base + ((size_t)yy * n + xx) * 4; return mk3(p[0], p[1], p[2]); };
+    f3 top = lerp3(tx(x0, y0), tx(x1, y0), fx);
+    f3 bot = lerp3(tx(x0, y1), tx(x1, y1), fx);
+    return lerp3(top, bot, fy);
+}
+
+// ---- vertex fetch: core/raytracing/hit.hlsl:27-164 ---------------------------------------------
+struct Vertex { f3 normal_world, tangent_world, bitangent_world; f2 texcoord; };
+
+static inline void fetch_indices(const Scene& sc, const bpt_drawable_sbt_data& dr, uint32_t prim, uint32_t idx[3]) {
+    for (int c = 0; c < 3; c++) idx[c] = sc.indices[(size_t)dr.index_offset + 3ull * prim + c];   // hit.hlsl:28-32
+}
+static inline f2 fetch_texcoord(const Scene& sc, const bpt_drawable_sbt_data& dr, uint32_t va, const uint32_t idx[3], float bu, float bv) {
+    if (!(va & BPT_VA_TEXCOORD)) return f2{0.0f, 0.0f};                                            // hit.hlsl:117-132
+    const float* t0 = &sc.texcoords[(size_t)dr.texcoord_offset + 2ull * idx[0]];
+    const float* t1 = &sc.texcoords[(size_t)dr.texcoord_offset + 2ull * idx[1]];
+    const float* t2 = &sc.texcoords[(size_t)dr.texcoord_offset + 2ull * idx[2]];
+    return f2{(t0[0] + (t1[0] - t0[0]) * bu) + (t2[0] - t0[0]) * bv, (t0[1] + (t1[1] - t0[1]) * bu) + (t2[1] - t0[1]) * bv};
+}
+static inline f3 interp3(const float* a0, const float* a1, const float* a2, float bu, float bv) {
+    return mk3((a0[0] + (a1[0] - a0[0]) * bu) + (a2[0] - a0[0]) * bv,
+               (a0[1] + (a1[1] - a0[1]) * bu) + (a2[1] - a0[1]) * bv,
+               (a0[2] + (a1[2] - a0[2]) * bu) + (a2[2] - a0[2]) * bv);
+}
+static Vertex fetch_vertex_attributes(const Scene& sc, const InstanceXf& x, uint32_t prim, float bu, float bv) {
+    const bpt_drawable_sbt_data& dr = sc.drawables[x.instance_id];
+    uint32_t va = sc.drawable_va[x.instance_id];
+    uint32_t idx[3];
+    fetch_indices(sc, dr, prim, idx);
+    f3 normal = mk3(0.0f, 0.0f, 1.0f);                                                             // hit.hlsl:54-72
+    if (va & BPT_VA_NORMAL)
+        normal = interp3(&sc.normals[(size_t)dr.normal_offset + 3ull * idx[0]], &sc.normals[(size_t)dr.normal_offset + 3ull * idx[1]],
+                         &sc.normals[(size_t)dr.normal_offset + 3ull * idx[2]], bu, bv);
+    f3 tangent = mk3(1.0f, 0.0f, 0.0f); float tangent_w = 1.0f;                                    // hit.hlsl:74-95
+    if (va & BPT_VA_TANGENT) {
+        const float* t0 = &sc.tangents[(size_t)dr.tangent_offset + 4ull * idx[0]];
+        const float* t1 = &sc.tangents[(size_t)dr.tangent_offset + 4ull * idx[1]];
+        const float* t2 = &sc.tangents[(size_t)dr.tangent_offset + 4ull * idx[2]];
+        tangent = interp3(t0, t1, t2, bu, bv);
+        tangent_w = (t0[3] + (t1[3] - t0[3]) * bu) + (t2[3] - t0[3]) * bv;
+    }
+    Vertex vt;
+    vt.normal_world = normalize(xf_vector_transposed(x.w2o, normal));                              // hit.hlsl:157
+    vt.tangent_world = normalize(xf_vector(x.o2w, tangent));                                       // hit.hlsl:158
+    vt.bitangent_world = normalize(cross(vt.normal_world, vt.tangent_world)) * tangent_w;          // hit.hlsl:159
+    vt.texcoord = fetch_texcoord(sc, dr, va, idx, bu, bv);
+    return vt;
+}
+
+// ---- material_function: the closed set of snippets (hit.hlsl:166-173) --------------------------
+static SurfaceData material_function(const Scene& sc, const bpt_material& m, f2 uv) {
+    SurfaceData s = surface_data_default();
+    uint32_t kind = (m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu;
+    if (kind == BPT_MATERIAL_KIND_GLTF_PBR) {                    // import_model.cpp:208-230
+        f4 bt = sample_or_default(sc, m.base_color_tex, uv, f4{1, 1, 1, 1});
+        f4 base = f4{bt.x * m.base_color[0], bt.y * m.base_color[1], bt.z * m.base_color[2], bt.w * m.base_color[3]};
+        s.base_color = mk3(base.x, base.y, base.z);
+        s.opacity = base.w;
+        f4 nt = sample_or_default(sc, m.normal_map_tex, uv, f4{0.5f, 0.5f, 1.0f, 1.0f});
+        f3 nm = mk3(nt.x * 2.0f - 1.0f, nt.y * 2.0f - 1.0f, nt.z * 2.0f - 1.0f);
+        nm = normalize(nm * mk3(m.normal_map_scale, m.normal_map_scale, 1.0f));
+        s.normal_map_value = nm * 0.5f + splat3(0.5f);
+        f4 mr = sample_or_default(sc, m.metallic_roughness_tex, uv, f4{1, 1, 1, 1});
+        s.roughness = m.roughness * mr.y;
+        s.f0_color = lerp3(splat3(0.04f), s.base_color, m.metallic * mr.z);
+        float occlusion = sample_or_default(sc, m.occlusion_tex, uv, f4{1, 1, 1, 1}).x * m.occlusion_strength;
+        s.base_color = s.base_color * occlusion;
+        s.f0_color = s.f0_color * occlusion;
+        s.f90_color = s.f90_color * occlusion;
+        s.emission = mk3(m.emission[0], m.emission[1], m.emission[2]);
+        s.two_sided = (m.flags & BPT_MATERIAL_FLAG_TWO_SIDED) != 0;
+    } else if (kind == BPT_MATERIAL_KIND_ASSIMP_DIFFUSE) {       // import_model.cpp:490-493
+        s.base_color = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
+        s.roughness = m.roughness;
+    }
+    return s;
+}
+
+float eval_opacity(const Scene& sc, uint32_t instance_id, uint32_t prim, float u, float v) {
+    const bpt_drawable_sbt_data& dr = sc.drawables[instance_id];
+    const bpt_material& m = sc.materials[dr.material_offset / sizeof(bpt_material)];
+    uint32_t idx[3];
+    fetch_indices(sc, dr, prim, idx);
+    f2 uv = fetch_texcoord(sc, dr, sc.drawable_va[instance_id], idx, u, v);
+    return material_function(sc, m, uv).opacity;
+}
+
+// ---- lights: shaders/renderer/lights.hlsl:10-25 -------------------------------------------------
+static inline f3 point_light_eval(const bpt_point_light_data& l, f3 P, f3& light_dir, float& dist) {
+    f3 lv = mk3(l.position[0], l.position[1], l.position[2]) - P;
+    float d2 = dot(lv, lv);
+    dist = sqrtf(d2);
+    light_dir = lv / dist;
+    float att = saturate(1.0f - pow2(d2 * l.range_sqr_inv)) / fmax_(d2, 0.001f);
+    if (l.cos_inner > l.cos_outer) {
+        float ct = clampf(dot(light_dir, mk3(l.direction[0], l.direction[1], l.direction[2])), l.cos_outer, l.cos_inner);
+        att = att * ((ct - l.cos_outer) / fmax_(l.cos_inner - l.cos_outer, 0.001f));
+    }
+    return mk3(l.emission[0], l.emission[1], l.emission[2]) * att;
+}
+
+// ---- camera ray: generate_camera_ray.hlsl:4-16, camera.hlsl:7-9 (glm column-major storage) ----
+static inline void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t W, uint32_t H, f3& O, f3& D) {
+    const float* ip = cam.matrix_inv_proj;
+    const float* iv = cam.matrix_inv_view;
+    float uvx = ((float)px + 0.5f) / (float)W, uvy = ((float)py + 0.5f) / (float)H;
+    float nx = uvx * 2.0f - 1.0f, ny = 1.0f - uvy * 2.0f;
+    // mul(M, float4(nx, ny, 1, 1)).xyz, M column-major: M[c*4 + r]
+    f3 dl = mk3(((ip[0] * nx + ip[4] * ny) + ip[8]) + ip[12],
+                ((ip[1] * nx + ip[5] * ny) + ip[9]) + ip[13],
+                ((ip[2] * nx + ip[6] * ny) + ip[10]) + ip[14]);
+    dl = normalize(dl);
+    f3 dw = mk3((iv[0] * dl.x + iv[4] * dl.y) + iv[8] * dl.z,
+                (iv[1] * dl.x + iv[5] * dl.y) + iv[9] * dl.z,
+                (iv[2] * dl.x + iv[6] * dl.y) + iv[10] * dl.z);
+    D = normalize(dw);
+    O = mk3(iv[12], iv[13], iv[14]);
+}
+
+struct ThreadOut {
+    TraceStats ext, shd;
+    uint64_t ext_per_bounce[16] = {0}, shd_per_bounce[16] = {0};
+    uint64_t shaded = 0, missed = 0;
+    struct CapE { uint32_t bounce, pixel; bpt_hit hit; };
+    struct CapS { uint32_t bounce, pixel, light; };
+    std::vector<CapE> cap_e;
+    std::vector<f3> pending;
+    std::vector<CapS> cap_s;
+};
+
+template <class Acc>
+static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const bpt_settings& st, uint32_t frame_index,
+                         uint32_t px, uint32_t py, Acc* a, ThreadOut& out) {
+    const Scene& sc = ctx.scene;
+    const uint32_t W = ctx.width, H = ctx.height;
+    const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);               // path_tracing.cpp:290
+    const uint32_t pixel = py * W + px;
+    f3 O, D;
+    camera_ray(cam, px, py, W, H, O, D);
+    f3 Wt = splat3(1.0f);
+    auto add = [&](f3 c) { a[0] += c.x; a[1] += c.y; a[2] += c.z; };
+    for (uint32_t i = 1; i < B; i++) {
+        out.ext_per_bounce[i]++;
+        HitRec h = trace_closest(sc, O, D, 0.001f, st.ray_length, frame_index, out.ext);   // rt_gbuffer.hlsl:17-25
+        if (ctx.capture) out.cap_e.push_back({i, pixel, bpt_hit{h.t, h.u, h.v, h.hit ? h.instance_id : 0xffffffffu, h.hit ? h.prim : 0xffffffffu}});
+        if (!h.hit) {                                                                       // deferred_lighting_secondary.hlsl:24-29
+            const float* m = sc.sky_transform;
+            f3 dir = mk3((m[0] * D.x + m[1] * D.y) + m[2] * D.z, (m[3] * D.x + m[4] * D.y) + m[5] * D.z, (m[6] * D.x + m[7] * D.y) + m[8] * D.z);
+            f3 color = sample_sky(sc, dir) * mk3(sc.sky_color[0], sc.sky_color[1], sc.sky_color[2]);
+            add(color * Wt);
+            out.missed++;
+            return;
+        }
+        out.shaded++;
+        const InstanceXf& x = sc.xf[h.inst_slot];
+        const bpt_drawable_sbt_data& dr = sc.drawables[x.instance_id];
+        const bpt_material& mat = sc.materials[dr.material_offset / sizeof(bpt_material)];
+        const uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
+        f3 P = O + D * h.t;                                                                 // rt_gbuffer.hlsl:32
+        Vertex vt = fetch_vertex_attributes(sc, x, h.prim, h.u, h.v);
+        SurfaceData surf = material_function(sc, mat, vt.texcoord);
+        f3 nts = surf.normal_map_value * 2.0f - splat3(1.0f);                               // rt_gbuffer_hit.hlsl:10-14
+        f3 N = normalize((nts.x * vt.tangent_world + nts.y * vt.bitangent_world) + nts.z * vt.normal_world);
+        if (surf.two_sided && dot(D, N) > 0.0f) N = -N;
+        f3 T = gbuffer_roundtrip_tangent(N, vt.tangent_world);                              // gbuffer.hlsl:27,41
+        f3 Bv = cross(N, T);                                                                // deferred_lighting_secondary.hlsl:41
+        surf.opacity = 1.0f;                                                                // gbuffer.hlsl:44
+        f3 V = normalize(O - P);                                                            // deferred_lighting_secondary.hlsl:45
+
+        // Contributions of this vertex. The GPU adds the unshadowed (immediate) terms in the shade
+        // kernel and the shadow-ray terms in the connect kernel that follows it, so the oracle keeps
+        // that order: rect lights (LTC, unshadowed) first, then the NEE terms in light order.
+        out.pending.clear();
+        auto direct = [&](f3 le, f3 L, float tmax, uint32_t light_index) {
+            f3 c = (le * surface_eval(N, T, Bv, V, L, surf, surface_model)) * Wt;
+            if (!(fmax_(c.x, fmax_(c.y, c.z)) > 0.0f)) return;            // zero contribution: no ray
+            if (st.nee_mode == BPT_NEE_NONE) { out.pending.push_back(c); return; }
+            out.shd_per_bounce[i]++;
+            if (ctx.capture) out.cap_s.push_back({i, pixel, light_index});
+            if (!trace_any(sc, P, L, 0.001f, tmax, frame_index, out.shd)) out.pending.push_back(c);
+        };
+        for (size_t l = 0; l < sc.rect_lights.size(); l++)                                  // deferred_lighting_secondary.hlsl:72-96
+            add(ltc_rect_light(sc, sc.rect_lights[l], P, N, T, Bv, V, surf, surface_model) * Wt);
+        for (size_t l = 0; l < sc.dir_lights.size(); l++) {                                 // deferred_lighting_secondary.hlsl:51-60
+            const bpt_dir_light_data& li = sc.dir_lights[l];
+            direct(mk3(li.emission[0], li.emission[1], li.emission[2]), mk3(li.direction[0], li.direction[1], li.direction[2]), st.ray_length, (uint32_t)l);
+        }
+        for (size_t l = 0; l < sc.point_lights.size(); l++) {                               // deferred_lighting_secondary.hlsl:61-70
+            f3 L; float dist;
+            f3 le = point_light_eval(sc.point_lights[l], P, L, dist);
+            direct(le, L, dist * 0.999f, (uint32_t)(sc.dir_lights.size() + l));
+        }
+        for (const f3& c : out.pending) add(c);
+
+        // next direction: sample_secondary_ray.hlsl:11-69 (bounce_index = i)
+        if (i + 1 >= B) return;
+        if (fmax_(Wt.x, fmax_(Wt.y, Wt.z)) < 0.001f) return;                                // :23-28
+        Frame frame = create_frame(N, T);                                                   // :42
+        f3 V_local = frame_to_local(frame, V);
+        float rx, ry;
+        get_anisotropic_roughness(surf.roughness, surf.anisotropy, rx, ry);
+        uint32_t seed = rng_tea(py * W + px, frame_index + i * 3u);                         // :52
+        float u1 = rng_next(seed);
+        float u2 = rng_next(seed);
+        f3 half_dir = ggx_vndf_sample(V_local, rx, ry, u1, u2);
+        f3 out_local = reflect(-V_local, half_dir);
+        float pdf_wh = ggx_vndf_sample_pdf(half_dir, V_local, rx, ry);
+        float pdf = pdf_wh / (4.0f * fabsf(dot(half_dir, V_local)));
+        f3 out_dir = frame_to_world(frame, out_local);
+        f3 bsdf = surface_eval(N, T, Bv, V, out_dir, surf, surface_model);
+        f3 weight = bsdf / pdf;
+        if (!finite3(weight)) weight = splat3(0.0f);                                        // :62-64
+        f3 newW = weight * Wt;
+        // A zero-weight path can never contribute again (deferred_lighting_secondary.hlsl:17-21
+        // writes 0 and the next sample pass kills it), so it is dropped here instead of traced.
+        if (newW.x == 0.0f && newW.y == 0.0f && newW.z == 0.0f) return;
+        O = P; D = out_dir; Wt = newW;
+    }
+}
+
+template <class Acc>
+static void render_impl(obpt_context& ctx, const bpt_camera& cam, uint32_t first, uint32_t ns, const bpt_settings& st, Acc* accum, bool count) {
+    const uint32_t W = ctx.width, H = ctx.height;
+    uint32_t nt = ctx.threads ? ctx.threads : std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t TILE = 16;
+    const uint32_t tx = (W + TILE - 1) / TILE, ty = (H + TILE - 1) / TILE;
+    std::atomic<uint32_t> next{0};
+    std::vector<ThreadOut> outs(nt);
+    auto work = [&](uint32_t tid) {
+        ThreadOut& out = outs[tid];
+        for (;;) {
+            uint32_t t = next.fetch_add(1);
+            if (t >= tx * ty) break;
+            uint32_t x0 = (t % tx) * TILE, y0 = (t / tx) * TILE;
+            for (uint32_t y = y0; y < std::min(y0 + TILE, H); y++)
+                for (uint32_t x = x0; x < std::min(x0 + TILE, W); x++)
+                    for (uint32_t s = 0; s < ns; s++)
+                        render_pixel(ctx, cam, st, first + s, x, y, accum + 4ull * (y * W + x), out);
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    if (!count) return;
+    TraceStats ext, shd;
+    for (auto& o : outs) {
+        ext.add(o.ext); shd.add(o.shd);
+        for (int b = 0; b < 16; b++) {
+            ctx.counters.extend_rays_per_bounce[b] += o.ext_per_bounce[b];
+            ctx.counters.shadow_rays_per_bounce[b] += o.shd_per_bounce[b];
+        }
+        ctx.stats.shaded_vertices += o.shaded;
+        ctx.stats.miss_vertices += o.missed;
+    }
+    ctx.counters.extend_rays += ext.rays; ctx.counters.shadow_rays += shd.rays;
+    ctx.counters.samples += (uint64_t)W * H * ns;
+    ctx.stats.extend_rays += ext.rays; ctx.stats.extend_nodes += ext.nodes; ctx.stats.extend_tris += ext.tris; ctx.stats.extend_instances += ext.instances;
+    ctx.stats.shadow_rays += shd.rays; ctx.stats.shadow_nodes += shd.nodes; ctx.stats.shadow_tris += shd.tris; ctx.stats.shadow_instances += shd.instances;
+    ctx.stats.samples += (uint64_t)W * H * ns;
+    if (ctx.capture) {
+        uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);
+        ctx.cap_extend_pixels.assign(B, {}); ctx.cap_extend_hits.assign(B, {});
+        ctx.cap_shadow_pixels.assign(B, {}); ctx.cap_shadow_lights.assign(B, {});
+        std::vector<ThreadOut::CapE> e; std::vector<ThreadOut::CapS> s;
+        for (auto& o : outs) { e.insert(e.end(), o.cap_e.begin(), o.cap_e.end()); s.insert(s.end(), o.cap_s.begin(), o.cap_s.end()); }
+        std::sort(e.begin(), e.end(), [](auto& a, auto& b) { return a.bounce != b.bounce ? a.bounce < b.bounce : a.pixel < b.pixel; });
+        std::sort(s.begin(), s.end(), [](auto& a, auto& b) { return a.bounce != b.bounce ? a.bounce < b.bounce : (a.pixel != b.pixel ? a.pixel < b.pixel : a.light < b.light); });
+        for (auto& r : e) { ctx.cap_extend_pixels[r.bounce].push_back(r.pixel); ctx.cap_extend_hits[r.bounce].push_back(r.hit); }
+        for (auto& r : s) { ctx.cap_shadow_pixels[r.bounce].push_back(r.pixel); ctx.cap_shadow_lights[r.bounce].push_back(r.light); }
+    }
+}
+
+} // namespace orc
+
+using namespace orc;
+
+#define CHECK_CTX(c) do { if (!(c)) return BPT_ERR_INVALID; } while (0)
+static bpt_status fail(obpt_context* c, bpt_status s, const char* msg) { c->err = msg; return s; }
+
+extern "C" {
+
+bpt_status obpt_create(const bpt_config* cfg, obpt_context** out) {
+    if (!cfg || !out || cfg->width == 0 || cfg->height == 0) return BPT_ERR_INVALID;
+    auto* c = new obpt_context();
+    c->width = cfg->width; c->height = cfg->height;
+    c->accum.assign((size_t)cfg->width * cfg->height * 4, 0.0f);
+    *out = c;
+    return BPT_OK;
+}
+bpt_status obpt_destroy(obpt_context* c) { delete c; return BPT_OK; }
+const char* obpt_last_error(const obpt_context* c) { return c ? c->err.c_str() : "null context"; }
+bpt_status obpt_set_threads(obpt_context* c, uint32_t n) { CHECK_CTX(c); c->threads = n; return BPT_OK; }
+uint32_t obpt_get_threads(const obpt_context* c) { return c->threads ? c->threads : std::max(1u, std::thread::hardware_concurrency()); }
+bpt_status obpt_resize(obpt_context* c, uint32_t w, uint32_t h) {
+    CHECK_CTX(c); if (!w || !h) return BPT_ERR_INVALID;
+    c->width = w; c->height = h; c->accum.assign((size_t)w * h * 4, 0.0f); return BPT_OK;
+}
+
+bpt_status obpt_scene_upload_geometry(obpt_context* c, const bpt_geometry_streams* s, const bpt_drawable_sbt_data* dr, const uint32_t* va,
+                                      uint32_t nd, const bpt_blas_desc* blas, uint32_t nb) {
+    CHECK_CTX(c);
+    if (!s || !dr || !blas || !s->positions || !s->indices) return fail(c, BPT_ERR_INVALID, "geometry: null stream");
+    Scene& sc = c->scene;
+    auto cp = [](std::vector<float>& v, const float* p, uint64_t n) { v.assign(p ? p : nullptr, p ? p + n : nullptr); };
+    cp(sc.positions, s->positions, s->num_position_floats); cp(sc.normals, s->normals, s->num_normal_floats);
+    cp(sc.tangents, s->tangents, s->num_tangent_floats); cp(sc.colors, s->colors, s->num_color_floats);
+    cp(sc.texcoords, s->texcoords, s->num_texcoord_floats); cp(sc.texcoords2, s->texcoords2, s->num_texcoord2_floats);
+    sc.indices.assign(s->indices, s->indices + s->num_indices);
+    sc.drawables.assign(dr, dr + nd);
+    sc.drawable_va.resize(nd);
+    for (uint32_t i = 0; i < nd; i++) {
+        uint32_t m = va ? va[i] : (BPT_VA_POSITION | BPT_VA_NORMAL | BPT_VA_TANGENT | BPT_VA_TEXCOORD);
+        if (!s->normals) m &= ~BPT_VA_NORMAL;
+        if (!s->tangents) m &= ~BPT_VA_TANGENT;
+        if (!s->texcoords) m &= ~BPT_VA_TEXCOORD;
+        sc.drawable_va[i] = m;
+    }
+    sc.blas_descs.assign(blas, blas + nb);
+    sc.accel_built = false;
+    return BPT_OK;
+}
+bpt_status obpt_scene_upload_instances(obpt_context* c, const bpt_instance_desc* inst, uint32_t n) {
+    CHECK_CTX(c); if (!inst && n) return BPT_ERR_INVALID;
+    c->scene.instances.assign(inst, inst + n);
+    return BPT_OK;
+}
+bpt_status obpt_scene_upload_materials(obpt_context* c, const bpt_material* m, uint32_t n, const bpt_texture_desc* t, uint32_t nt) {
+    CHECK_CTX(c); if (!m || !n) return fail(c, BPT_ERR_INVALID, "materials: empty");
+    c->scene.materials.assign(m, m + n);
+    c->scene.textures.clear();
+    for (uint32_t i = 0; i < nt; i++) {
+        Texture tx; tx.w = t[i].width; tx.h = t[i].height; tx.format = t[i].format; tx.addr_u = t[i].address_mode_u; tx.addr_v = t[i].address_mode_v; tx.linear = t[i].filter_linear;
+        size_t bytes = (size_t)tx.w * tx.h * (tx.format == BPT_TEXTURE_RGBA8_UNORM ? 4 : 16);
+        tx.texels.assign((const uint8_t*)t[i].texels, (const uint8_t*)t[i].texels + bytes);
+        c->scene.textures.push_back(std::move(tx));
+    }
+    return BPT_OK;
+}
+bpt_status obpt_scene_upload_lights(obpt_context* c, const bpt_dir_light_data* d, uint32_t nd, const bpt_point_light_data* p, uint32_t np,
+                                    const bpt_rect_light_data* r, uint32_t nr, const bpt_ltc_luts* luts) {
+    CHECK_CTX(c);
+    Scene& sc = c->scene;
+    sc.dir_lights.assign(d, d + nd); sc.point_lights.assign(p, p + np); sc.rect_lights.assign(r, r + nr);
+    if (nr) {
+        if (!luts || !luts->matrix_lut0 || !luts->matrix_lut1 || !luts->matrix_lut2 || !luts->norm_lut) return fail(c, BPT_ERR_INVALID, "rect lights need the LTC LUTs");
+        sc.ltc_m0.assign(luts->matrix_lut0, luts->matrix_lut0 + 8 * 8 * 64 * 4);
+        sc.ltc_m1.assign(luts->matrix_lut1, luts->matrix_lut1 + 8 * 8 * 64 * 4);
+        sc.ltc_m2.assign(luts->matrix_lut2, luts->matrix_lut2 + 8 * 8 * 64 * 4);
+        sc.ltc_norm.assign(luts->norm_lut, luts->norm_lut + 8 * 8 * 64 * 2);
+    }
+    return BPT_OK;
+}
+bpt_status obpt_scene_upload_sky(obpt_context* c, const float* faces, uint32_t size, const float xf[9], const float col[3]) {
+    CHECK_CTX(c);
+    Scene& sc = c->scene;
+    if (faces && size) { sc.sky_faces.assign(faces, faces + (size_t)6 * size * size * 4); sc.sky_size = size; }
+    else { sc.sky_faces.clear(); sc.sky_size = 0; }
+    if (xf) std::memcpy(sc.sky_transform, xf, sizeof(float) * 9);
+    if (col) std::memcpy(sc.sky_color, col, sizeof(float) * 3);
+    return BPT_OK;
+}
+
+bpt_status obpt_build_accel(obpt_context* c, uint32_t mode) {
+    CHECK_CTX(c);
+    if (c->scene.materials.empty()) return fail(c, BPT_ERR_STATE, "upload materials before build_accel");
+    for (auto& d : c->scene.drawables)
+        if (d.material_offset % sizeof(bpt_material) || d.material_offset / sizeof(bpt_material) >= c->scene.materials.size())
+            return fail(c, BPT_ERR_INVALID, "drawable material_offset out of range");
+    std::string err;
+    if (!build_accel(c->scene, mode, err)) { c->err = err; return BPT_ERR_INVALID; }
+    return BPT_OK;
+}
+bpt_status obpt_update_tlas(obpt_context* c) {
+    CHECK_CTX(c);
+    if (!c->scene.accel_built || c->scene.accel_mode != BPT_ACCEL_TWO_LEVEL) return fail(c, BPT_ERR_STATE, "update_tlas needs a built two-level accel");
+    std::string err;
+    if (!build_tlas(c->scene, err)) { c->err = err; return BPT_ERR_INVALID; }
+    return BPT_OK;
+}
+bpt_status obpt_debug_read_bvh(obpt_context* c, uint32_t which, uint32_t* np, uint64_t* morton, uint32_t* prims, bpt_bvh_node* nodes, uint32_t cap, int32_t* root) {
+    CHECK_CTX(c);
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "accel not built");
+    const Bvh* b;
+    if (which == BPT_BVH_TLAS) { if (c->scene.accel_mode != BPT_ACCEL_TWO_LEVEL) return fail(c, BPT_ERR_INVALID, "no TLAS in merged mode"); b = &c->scene.tlas; }
+    else { if (which >= c->scene.blas.size()) return fail(c, BPT_ERR_INVALID, "blas index out of range"); b = &c->scene.blas[which]; }
+    if (np) *np = b->n;
+    if (root) *root = b->root;
+    if ((morton || prims || nodes) && cap < b->n) return fail(c, BPT_ERR_INVALID, "capacity too small");
+    if (morton) std::copy(b->morton.begin(), b->morton.end(), morton);
+    if (prims) std::copy(b->prims.begin(), b->prims.end(), prims);
+    if (nodes) std::copy(b->nodes.begin(), b->nodes.end(), nodes);
+    return BPT_OK;
+}
+
+bpt_status obpt_clear_accum(obpt_context* c) { CHECK_CTX(c); std::fill(c->accum.begin(), c->accum.end(), 0.0f); return BPT_OK; }
+bpt_status obpt_render(obpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t ns, const bpt_settings* st) {
+    CHECK_CTX(c); if (!cam || !st) return BPT_ERR_INVALID;
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
+    if (st->state_precision != BPT_STATE_FP32 || st->russian_roulette || st->pixel_jitter || st->rect_shadow) return fail(c, BPT_ERR_UNSUPPORTED, "mode switch not implemented");
+    render_impl<float>(*c, *cam, first, ns, *st, c->accum.data(), true);
+    return BPT_OK;
+}
+bpt_status obpt_render_converged(obpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t ns, const bpt_settings* st, float* out) {
+    CHECK_CTX(c); if (!cam || !st || !out || !ns) return BPT_ERR_INVALID;
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
+    std::vector<double> acc((size_t)c->width * c->height * 4, 0.0);
+    bool cap = c->capture; c->capture = false;
+    render_impl<double>(*c, *cam, first, ns, *st, acc.data(), false);
+    c->capture = cap;
+    for (size_t p = 0; p < (size_t)c->width * c->height; p++) {
+        for (int k = 0; k < 3; k++) out[p * 4 + k] = (float)(acc[p * 4 + k] / (double)ns);
+        out[p * 4 + 3] = 1.0f;
+    }
+    return BPT_OK;
+}
+bpt_status obpt_resolve(obpt_context* c, uint32_t total, float* out) {
+    CHECK_CTX(c); if (!out || !total) return BPT_ERR_INVALID;
+    float inv = 1.0f / (float)total;
+    for (size_t p = 0; p < (size_t)c->width * c->height; p++) {
+        for (int k = 0; k < 3; k++) out[p * 4 + k] = c->accum[p * 4 + k] * inv;
+        out[p * 4 + 3] = 1.0f;
+    }
+    return BPT_OK;
+}
+bpt_status obpt_get_counters(obpt_context* c, bpt_counters* o) { CHECK_CTX(c); *o = c->counters; return BPT_OK; }
+bpt_status obpt_reset_counters(obpt_context* c) { CHECK_CTX(c); c->counters = bpt_counters{}; c->stats = obpt_stats{}; return BPT_OK; }
+bpt_status obpt_get_stats(obpt_context* c, obpt_stats* o) { CHECK_CTX(c); *o = c->stats; return BPT_OK; }
+
+bpt_status obpt_trace_rays(obpt_context* c, const bpt_ray* rays, uint64_t n, uint32_t frame, bpt_hit* out) {
+    CHECK_CTX(c); if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "accel not built");
+    uint32_t nt = obpt_get_threads(c);
+    std::vector<std::thread> th; std::vector<TraceStats> sts(nt);
+    auto work = [&](uint32_t tid) {
+        for (uint64_t i = tid; i < n; i += nt) {
+            const bpt_ray& r = rays[i];
+            HitRec h = trace_closest(c->scene, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, frame, sts[tid]);
+            out[i] = bpt_hit{h.t, h.u, h.v, h.hit ? h.instance_id : 0xffffffffu, h.hit ? h.prim : 0xffffffffu};
+        }
+    };
+    for (uint32_t i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    for (auto& s : sts) { c->stats.extend_rays += s.rays; c->stats.extend_nodes += s.nodes; c->stats.extend_tris += s.tris; c->stats.extend_instances += s.instances; }
+    return BPT_OK;
+}
+bpt_status obpt_trace_shadow_rays(obpt_context* c, const bpt_ray* rays, uint64_t n, uint32_t frame, uint8_t* vis) {
+    CHECK_CTX(c); if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "accel not built");
+    uint32_t nt = obpt_get_threads(c);
+    std::vector<std::thread> th; std::vector<TraceStats> sts(nt);
+    auto work = [&](uint32_t tid) {
+        for (uint64_t i = tid; i < n; i += nt) {
+            const bpt_ray& r = rays[i];
+            vis[i] = trace_any(c->scene, mk3(r.origin[0], r.origin[1], r.origin[2]), mk3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, frame, sts[tid]) ? 0 : 1;
+        }
+    };
+    for (uint32_t i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    for (auto& s : sts) { c->stats.shadow_rays += s.rays; c->stats.shadow_nodes += s.nodes; c->stats.shadow_tris += s.tris; c->stats.shadow_instances += s.instances; }
+    return BPT_OK;
+}
+bpt_status obpt_debug_capture(obpt_context* c, uint32_t en) { CHECK_CTX(c); c->capture = en != 0; return BPT_OK; }
+bpt_status obpt_debug_read_queue(obpt_context* c, uint32_t bounce, uint32_t kind, uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t cap, uint64_t* count) {
+    CHECK_CTX(c);
+    auto& px = kind == 0 ? c->cap_extend_pixels : c->cap_shadow_pixels;
+    if (bounce >= px.size()) { if (count) *count = 0; return BPT_OK; }
+    uint64_t n = px[bounce].size();
+    if (count) *count = n;
+    if (!pixels && !lights && !hits) return BPT_OK;
+    if (cap < n) return fail(c, BPT_ERR_INVALID, "capacity too small");
+    if (pixels) std::copy(px[bounce].begin(), px[bounce].end(), pixels);
+    if (kind == 0 && hits) std::copy(c->cap_extend_hits[bounce].begin(), c->cap_extend_hits[bounce].end(), hits);
+    if (kind == 1 && lights) std::copy(c->cap_shadow_lights[bounce].begin(), c->cap_shadow_lights[bounce].end(), lights);
+    return BPT_OK;
+}
+bpt_status obpt_trace_probes(obpt_context* c, const bpt_probe_volume*, const float*, uint32_t, uint32_t, float*) {
+    return fail(c, BPT_ERR_UNSUPPORTED, "probe tracing not implemented yet");
+}
+
+uint32_t obpt_rng_tea(uint32_t a, uint32_t b) { return rng_tea(a, b); }
+uint32_t obpt_rng_lcg(uint32_t* s) { return rng_lcg(*s); }
+void obpt_sincos_2pi(float u, float* s, float* c) { sincos_2pi(u, *s, *c); }
+float obpt_atan2(float y, float x) { return atan2_(y, x); }
+float obpt_acos(float x) { return acos_(x); }
+void obpt_ggx_vndf_sample(const float v[3], float rx, float ry, float u1, float u2, float o[3]) {
+    f3 h = ggx_vndf_sample(mk3(v[0], v[1], v[2]), rx, ry, u1, u2); o[0] = h.x; o[1] = h.y; o[2] = h.z;
+}
+void obpt_surface_eval_lit(const float N[3], const float T[3], const float V[3], const float L[3], const float base[3], const float f0[3], const float f90[3],
+                           float roughness, float anisotropy, float out[3]) {
+    SurfaceData s = surface_data_default();
+    s.base_color = mk3(base[0], base[1], base[2]); s.f0_color = mk3(f0[0], f0[1], f0[2]); s.f90_color = mk3(f90[0], f90[1], f90[2]);
+    s.roughness = roughness; s.anisotropy = anisotropy;
+    f3 n = mk3(N[0], N[1], N[2]), t = mk3(T[0], T[1], T[2]);
+    f3 r = surface_eval(n, t, cross(n, t), mk3(V[0], V[1], V[2]), mk3(L[0], L[1], L[2]), s, 1u);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+uint64_t obpt_morton63(const float c[3], const float lo[3], const float hi[3]) {
+    return morton63(mk3(c[0], c[1], c[2]), mk3(lo[0], lo[1], lo[2]), mk3(hi[0], hi[1], hi[2]));
+}
+
+} // extern "C"
