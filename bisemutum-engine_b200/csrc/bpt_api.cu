@@ -1,0 +1,377 @@
+// bpt_api.cu — the C ABI of include/bpt/bpt.h: context, scene upload, accel build, render, debug.
+// Each entry point cites the reference interface it replaces in the header.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include "bpt_internal.cuh"
+
+using namespace bptd;
+
+bpt_status dev_alloc(bpt_context* ctx, DevBuf& b, size_t bytes) {
+    b.p = nullptr; b.bytes = 0;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
+        b.p = nullptr;
+        return e == cudaErrorMemoryAllocation ? BPT_ERR_OOM : BPT_ERR_CUDA;
+    }
+    b.bytes = bytes;
+    return BPT_OK;
+}
+void dev_free(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.bytes = 0;
+}
+bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes) {
+    dev_free(b);
+    bpt_status s = dev_alloc(ctx, b, bytes);
+    if (s) return s;
+    if (bytes && src) BPT_CUDA_TRY(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return BPT_OK;
+}
+
+DScene bpt_context::scene_view() const {
+    DScene s{};
+    s.positions = d_positions.as<float>(); s.normals = d_normals.as<float>(); s.tangents = d_tangents.as<float>();
+    s.texcoords = d_texcoords.as<float>(); s.indices = d_indices.as<uint32_t>();
+    s.drawables = d_drawables.as<bpt_drawable_sbt_data>(); s.drawable_va = d_drawable_va.as<uint32_t>();
+    s.materials = d_materials.as<bpt_material>();
+    s.textures = d_textures.as<DTexture>(); s.num_textures = (uint32_t)d_texels.size();
+    s.instances = d_instances.as<DInstance>(); s.num_instances = (uint32_t)h_instances.size();
+    s.accel_mode = accel_mode;
+    s.tlas_nodes = tlas.nodes.as<float4>(); s.tlas_prims = tlas.prims.as<uint32_t>(); s.tlas_root = tlas.root; s.tlas_n = tlas.n;
+    s.blas = d_blas_table.as<DBlas>();
+    s.dir_lights = d_dir.as<bpt_dir_light_data>(); s.num_dir = num_dir;
+    s.point_lights = d_point.as<bpt_point_light_data>(); s.num_point = num_point;
+    s.rect_lights = d_rect.as<bpt_rect_light_data>(); s.num_rect = num_rect;
+    s.ltc_m0 = d_ltc[0].as<float>(); s.ltc_m1 = d_ltc[1].as<float>(); s.ltc_m2 = d_ltc[2].as<float>(); s.ltc_norm = d_ltc[3].as<float>();
+    s.sky_faces = d_sky.as<float4>(); s.sky_size = sky_size;
+    memcpy(s.sky_transform, sky_transform, sizeof(sky_transform));
+    memcpy(s.sky_color, sky_color, sizeof(sky_color));
+    return s;
+}
+
+static bpt_status fail(bpt_context* c, bpt_status s, const char* msg) { c->err = msg; return s; }
+#define NEED(c) do { if (!(c)) return BPT_ERR_INVALID; cudaSetDevice((c)->device); } while (0)
+
+extern "C" {
+
+const char* bpt_version(void) { return "bpt 0.1 (sm_100a)"; }
+
+bpt_status bpt_create(const bpt_config* cfg, bpt_context** out) {
+    if (!cfg || !out || cfg->width == 0 || cfg->height == 0) return BPT_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return BPT_ERR_NO_DEVICE;   // no CPU path exists
+    if (cfg->device < 0 || cfg->device >= count) return BPT_ERR_INVALID;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return BPT_ERR_CUDA;
+    bpt_context* c = new (std::nothrow) bpt_context();
+    if (!c) return BPT_ERR_OOM;
+    c->device = cfg->device; c->width = cfg->width; c->height = cfg->height;
+    bpt_status s = wavefront_alloc(c);
+    if (s) { delete c; return s; }
+    *out = c;
+    return BPT_OK;
+}
+
+bpt_status bpt_destroy(bpt_context* c) {
+    if (!c) return BPT_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
+                      &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
+                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
+                      &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims};
+    for (DevBuf* b : bufs) dev_free(*b);
+    for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
+    for (auto& t : c->d_texels) dev_free(t);
+    for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); }
+    delete c;
+    return BPT_OK;
+}
+
+const char* bpt_last_error(const bpt_context* c) { return c ? c->err.c_str() : "null context"; }
+
+bpt_status bpt_set_stream(bpt_context* c, void* stream) { NEED(c); c->stream = (cudaStream_t)stream; return BPT_OK; }
+bpt_status bpt_sync(bpt_context* c) { NEED(c); BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return BPT_OK; }
+
+bpt_status bpt_resize(bpt_context* c, uint32_t w, uint32_t h) {
+    NEED(c);
+    if (!w || !h) return BPT_ERR_INVALID;
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->width = w; c->height = h;
+    return wavefront_alloc(c);
+}
+
+bpt_status bpt_scene_upload_geometry(bpt_context* c, const bpt_geometry_streams* g, const bpt_drawable_sbt_data* dr, const uint32_t* va,
+                                     uint32_t nd, const bpt_blas_desc* blas, uint32_t nb) {
+    NEED(c);
+    if (!g || !dr || !blas || !nd || !nb || !g->positions || !g->indices) return fail(c, BPT_ERR_INVALID, "geometry: null stream or empty scene");
+    bpt_status s;
+    if ((s = dev_upload(c, c->d_positions, g->positions, g->num_position_floats * 4))) return s;
+    if ((s = dev_upload(c, c->d_normals, g->normals, g->normals ? g->num_normal_floats * 4 : 0))) return s;
+    if ((s = dev_upload(c, c->d_tangents, g->tangents, g->tangents ? g->num_tangent_floats * 4 : 0))) return s;
+    if ((s = dev_upload(c, c->d_texcoords, g->texcoords, g->texcoords ? g->num_texcoord_floats * 4 : 0))) return s;
+    if ((s = dev_upload(c, c->d_indices, g->indices, g->num_indices * 4))) return s;
+    c->has_normals = g->normals != nullptr; c->has_tangents = g->tangents != nullptr; c->has_texcoords = g->texcoords != nullptr;
+    c->num_position_floats = g->num_position_floats; c->num_indices = g->num_indices;
+    c->h_drawables.assign(dr, dr + nd);
+    std::vector<uint32_t> vam(nd);
+    for (uint32_t i = 0; i < nd; i++) {
+        uint32_t m = va ? va[i] : (BPT_VA_POSITION | BPT_VA_NORMAL | BPT_VA_TANGENT | BPT_VA_TEXCOORD);
+        if (!c->has_normals) m &= ~BPT_VA_NORMAL;
+        if (!c->has_tangents) m &= ~BPT_VA_TANGENT;
+        if (!c->has_texcoords) m &= ~BPT_VA_TEXCOORD;
+        vam[i] = m;
+    }
+    if ((s = dev_upload(c, c->d_drawables, dr, (size_t)nd * sizeof(bpt_drawable_sbt_data)))) return s;
+    if ((s = dev_upload(c, c->d_drawable_va, vam.data(), (size_t)nd * 4))) return s;
+    c->h_blas_desc.assign(blas, blas + nb);
+    for (auto& bd : c->h_blas_desc)
+        if (bd.num_triangles == 0 || (uint64_t)bd.index_offset + 3ull * bd.num_triangles > g->num_indices)
+            return fail(c, BPT_ERR_INVALID, "BLAS index range out of bounds or empty");
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));   // host buffers may be released by the caller
+    c->accel_built = false;
+    return BPT_OK;
+}
+
+bpt_status bpt_scene_upload_instances(bpt_context* c, const bpt_instance_desc* inst, uint32_t n) {
+    NEED(c);
+    if (!inst || !n) return fail(c, BPT_ERR_INVALID, "instances: empty");
+    c->h_instances.assign(inst, inst + n);
+    return BPT_OK;
+}
+
+bpt_status bpt_scene_upload_materials(bpt_context* c, const bpt_material* m, uint32_t n, const bpt_texture_desc* t, uint32_t nt) {
+    NEED(c);
+    if (!m || !n) return fail(c, BPT_ERR_INVALID, "materials: empty");
+    c->h_materials.assign(m, m + n);
+    bpt_status s;
+    if ((s = dev_upload(c, c->d_materials, m, (size_t)n * sizeof(bpt_material)))) return s;
+    for (auto& b : c->d_texels) dev_free(b);
+    c->d_texels.assign(nt, DevBuf{});
+    std::vector<DTexture> table(std::max(nt, 1u));
+    for (uint32_t i = 0; i < nt; i++) {
+        if (!t[i].texels || !t[i].width || !t[i].height || t[i].format > BPT_TEXTURE_RGBA32_FLOAT) return fail(c, BPT_ERR_INVALID, "bad texture desc");
+        size_t bytes = (size_t)t[i].width * t[i].height * (t[i].format == BPT_TEXTURE_RGBA8_UNORM ? 4 : 16);
+        if ((s = dev_upload(c, c->d_texels[i], t[i].texels, bytes))) return s;
+        table[i] = DTexture{c->d_texels[i].p, t[i].width, t[i].height, t[i].format, t[i].address_mode_u, t[i].address_mode_v, t[i].filter_linear};
+    }
+    if ((s = dev_upload(c, c->d_textures, table.data(), table.size() * sizeof(DTexture)))) return s;
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
+}
+
+bpt_status bpt_scene_upload_lights(bpt_context* c, const bpt_dir_light_data* d, uint32_t nd, const bpt_point_light_data* p, uint32_t np,
+                                   const bpt_rect_light_data* r, uint32_t nr, const bpt_ltc_luts* luts) {
+    NEED(c);
+    if ((nd && !d) || (np && !p) || (nr && !r)) return fail(c, BPT_ERR_INVALID, "lights: null array");
+    bpt_status s;
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if ((s = dev_upload(c, c->d_dir, d, (size_t)nd * sizeof(*d)))) return s;
+    if ((s = dev_upload(c, c->d_point, p, (size_t)np * sizeof(*p)))) return s;
+    if ((s = dev_upload(c, c->d_rect, r, (size_t)nr * sizeof(*r)))) return s;
+    if (nr) {
+        if (!luts || !luts->matrix_lut0 || !luts->matrix_lut1 || !luts->matrix_lut2 || !luts->norm_lut) return fail(c, BPT_ERR_INVALID, "rect lights need the LTC LUTs");
+        const float* src[4] = {luts->matrix_lut0, luts->matrix_lut1, luts->matrix_lut2, luts->norm_lut};
+        for (int k = 0; k < 4; k++)
+            if ((s = dev_upload(c, c->d_ltc[k], src[k], (size_t)8 * 8 * 64 * (k < 3 ? 4 : 2) * 4))) return s;
+    }
+    c->num_dir = nd; c->num_point = np; c->num_rect = nr;
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return wavefront_alloc(c);
+}
+
+bpt_status bpt_scene_upload_sky(bpt_context* c, const float* faces, uint32_t size, const float xf[9], const float col[3]) {
+    NEED(c);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (faces && size) {
+        bpt_status s = dev_upload(c, c->d_sky, faces, (size_t)6 * size * size * 16);
+        if (s) return s;
+        c->sky_size = size;
+        BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    } else { dev_free(c->d_sky); c->sky_size = 0; }
+    if (xf) memcpy(c->sky_transform, xf, sizeof(float) * 9);
+    if (col) memcpy(c->sky_color, col, sizeof(float) * 3);
+    return BPT_OK;
+}
+
+static bpt_status validate_scene(bpt_context* c) {
+    if (c->h_blas_desc.empty() || c->h_instances.empty()) return fail(c, BPT_ERR_STATE, "build_accel: upload geometry and instances first");
+    if (c->h_materials.empty()) return fail(c, BPT_ERR_STATE, "build_accel: upload materials first");
+    for (auto& d : c->h_drawables)
+        if (d.material_offset % sizeof(bpt_material) || d.material_offset / sizeof(bpt_material) >= c->h_materials.size())
+            return fail(c, BPT_ERR_INVALID, "drawable material_offset out of range");
+    for (auto& in : c->h_instances) {
+        if (in.blas >= c->h_blas_desc.size()) return fail(c, BPT_ERR_INVALID, "instance references a BLAS out of range");
+        if ((in.instance_id_and_mask & 0xffffffu) >= c->h_drawables.size()) return fail(c, BPT_ERR_INVALID, "instance_id out of drawable range");
+    }
+    return BPT_OK;
+}
+
+static bpt_status upload_blas_table(bpt_context* c) {
+    std::vector<DBlas> t(c->blas.size());
+    for (size_t i = 0; i < c->blas.size(); i++) t[i] = DBlas{c->blas[i].nodes.as<float4>(), c->blas[i].tris.as<float4>(), c->blas[i].root, c->blas[i].n};
+    bpt_status s = dev_upload(c, c->d_blas_table, t.data(), t.size() * sizeof(DBlas));
+    if (s) return s;
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
+}
+
+bpt_status bpt_build_accel(bpt_context* c, uint32_t mode) {
+    NEED(c);
+    bpt_status s;
+    if ((s = validate_scene(c))) return s;
+    if (mode != BPT_ACCEL_TWO_LEVEL && mode != BPT_ACCEL_MERGED) return fail(c, BPT_ERR_INVALID, "unknown accel mode");
+    c->accel_built = false;
+    c->accel_mode = mode;
+    if ((s = upload_instance_table(c))) return s;
+    for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); }
+    if (mode == BPT_ACCEL_TWO_LEVEL) {
+        c->blas.assign(c->h_blas_desc.size(), DevBvh{});
+        for (uint32_t b = 0; b < c->blas.size(); b++)
+            if ((s = build_blas_two_level(c, b))) return s;
+        if ((s = build_tlas(c))) return s;
+    } else {
+        c->blas.assign(1, DevBvh{});
+        if ((s = build_blas_merged(c))) return s;
+        dev_free(c->tlas.nodes); dev_free(c->tlas.morton); dev_free(c->tlas.prims);
+        c->tlas = DevBvh{};
+    }
+    if ((s = upload_blas_table(c))) return s;
+    c->accel_built = true;
+    return BPT_OK;
+}
+
+bpt_status bpt_update_tlas(bpt_context* c) {
+    NEED(c);
+    if (!c->accel_built || c->accel_mode != BPT_ACCEL_TWO_LEVEL) return fail(c, BPT_ERR_STATE, "update_tlas needs a built two-level accel");
+    bpt_status s;
+    if ((s = validate_scene(c))) return s;
+    if ((s = upload_instance_table(c))) return s;
+    return build_tlas(c);
+}
+
+bpt_status bpt_debug_read_bvh(bpt_context* c, uint32_t which, uint32_t* np, uint64_t* morton, uint32_t* prims, bpt_bvh_node* nodes, uint32_t cap, int32_t* root) {
+    NEED(c);
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "accel not built");
+    const DevBvh* b;
+    if (which == BPT_BVH_TLAS) { if (c->accel_mode != BPT_ACCEL_TWO_LEVEL) return fail(c, BPT_ERR_INVALID, "no TLAS in merged mode"); b = &c->tlas; }
+    else { if (which >= c->blas.size()) return fail(c, BPT_ERR_INVALID, "blas index out of range"); b = &c->blas[which]; }
+    if (np) *np = b->n;
+    if (root) *root = b->root;
+    if ((morton || prims || nodes) && cap < b->n) return fail(c, BPT_ERR_INVALID, "capacity too small");
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (morton) BPT_CUDA_TRY(c, cudaMemcpy(morton, b->morton.p, (size_t)b->n * 8, cudaMemcpyDeviceToHost));
+    if (prims) BPT_CUDA_TRY(c, cudaMemcpy(prims, b->prims.p, (size_t)b->n * 4, cudaMemcpyDeviceToHost));
+    if (nodes && b->n >= 2) BPT_CUDA_TRY(c, cudaMemcpy(nodes, b->nodes.p, (size_t)(b->n - 1) * 64, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+
+bpt_status bpt_clear_accum(bpt_context* c) {
+    NEED(c);
+    BPT_CUDA_TRY(c, cudaMemsetAsync(c->wf.accum.p, 0, (size_t)c->width * c->height * 16, c->stream));
+    return BPT_OK;
+}
+
+bpt_status bpt_render(bpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t ns, const bpt_settings* st) {
+    NEED(c);
+    if (!cam || !st) return BPT_ERR_INVALID;
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
+    if (st->state_precision != BPT_STATE_FP32 || st->russian_roulette || st->pixel_jitter || st->rect_shadow)
+        return fail(c, BPT_ERR_UNSUPPORTED, "mode switch not implemented");
+    return wavefront_render(c, *cam, first, ns, *st);
+}
+
+bpt_status bpt_resolve_device(bpt_context* c, uint32_t total, float* d_out) {
+    NEED(c);
+    if (!total || !d_out) return BPT_ERR_INVALID;
+    return launch_resolve(c, total, d_out);
+}
+
+bpt_status bpt_resolve(bpt_context* c, uint32_t total, float* out) {
+    NEED(c);
+    if (!total || !out) return BPT_ERR_INVALID;
+    DevBuf tmp;
+    size_t bytes = (size_t)c->width * c->height * 16;
+    bpt_status s = dev_alloc(c, tmp, bytes);
+    if (s) return s;
+    s = launch_resolve(c, total, tmp.as<float>());
+    cudaError_t e = cudaSuccess;
+    if (!s) e = cudaMemcpyAsync(out, tmp.p, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (!s && e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    dev_free(tmp);
+    if (s) return s;
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}
+
+bpt_status bpt_accum_device_ptr(bpt_context* c, float** out) { NEED(c); if (!out) return BPT_ERR_INVALID; *out = c->wf.accum.as<float>(); return BPT_OK; }
+
+bpt_status bpt_upload_accum(bpt_context* c, const float* sums) {
+    NEED(c);
+    if (!sums) return BPT_ERR_INVALID;
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->wf.accum.p, sums, (size_t)c->width * c->height * 16, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
+}
+
+bpt_status bpt_get_counters(bpt_context* c, bpt_counters* out) {
+    NEED(c);
+    if (!out) return BPT_ERR_INVALID;
+    uint64_t t[40];
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(t, c->wf.totals.p, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof(*out));
+    for (int b = 0; b < 16; b++) {
+        out->extend_rays_per_bounce[b] = t[b]; out->shadow_rays_per_bounce[b] = t[16 + b];
+        out->extend_rays += t[b]; out->shadow_rays += t[16 + b];
+    }
+    out->samples = t[32];
+    out->kernel_launches = c->launches;
+    return BPT_OK;
+}
+
+bpt_status bpt_reset_counters(bpt_context* c) {
+    NEED(c);
+    BPT_CUDA_TRY(c, cudaMemsetAsync(c->wf.totals.p, 0, 40 * sizeof(uint64_t), c->stream));
+    c->launches = 0;
+    return BPT_OK;
+}
+
+bpt_status bpt_trace_rays(bpt_context* c, const bpt_ray* rays, uint64_t n, uint32_t frame, bpt_hit* out) {
+    NEED(c);
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "accel not built");
+    if (n && (!rays || !out)) return BPT_ERR_INVALID;
+    return launch_trace_batch(c, rays, n, frame, out, nullptr);
+}
+bpt_status bpt_trace_shadow_rays(bpt_context* c, const bpt_ray* rays, uint64_t n, uint32_t frame, uint8_t* vis) {
+    NEED(c);
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "accel not built");
+    if (n && (!rays || !vis)) return BPT_ERR_INVALID;
+    return launch_trace_batch(c, rays, n, frame, nullptr, vis);
+}
+
+bpt_status bpt_debug_capture(bpt_context* c, uint32_t en) { NEED(c); c->capture = en != 0; return BPT_OK; }
+
+bpt_status bpt_debug_read_queue(bpt_context* c, uint32_t bounce, uint32_t kind, uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t cap, uint64_t* count) {
+    NEED(c);
+    auto& px = kind == 0 ? c->cap_extend_pixels : c->cap_shadow_pixels;
+    if (bounce >= px.size()) { if (count) *count = 0; return BPT_OK; }
+    uint64_t n = px[bounce].size();
+    if (count) *count = n;
+    if (!pixels && !lights && !hits) return BPT_OK;
+    if (cap < n) return fail(c, BPT_ERR_INVALID, "capacity too small");
+    if (pixels) std::copy(px[bounce].begin(), px[bounce].end(), pixels);
+    if (kind == 0 && hits) std::copy(c->cap_extend_hits[bounce].begin(), c->cap_extend_hits[bounce].end(), hits);
+    if (kind == 1 && lights) std::copy(c->cap_shadow_lights[bounce].begin(), c->cap_shadow_lights[bounce].end(), lights);
+    return BPT_OK;
+}
+
+bpt_status bpt_trace_probes(bpt_context* c, const bpt_probe_volume*, const float*, uint32_t, uint32_t, float*) {
+    NEED(c);
+    return fail(c, BPT_ERR_UNSUPPORTED, "probe tracing not implemented yet");
+}
+
+} // extern "C"

@@ -1,0 +1,104 @@
+// bpt_internal.cuh — host-side context of libbpt.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "bpt_scene.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// One built BVH (BLAS or TLAS) in device memory.
+struct DevBvh {
+    uint32_t n = 0;
+    int32_t root = 0;
+    DevBuf nodes;      // float4[4*(n-1)]
+    DevBuf tris;       // float4[3*n] (BLAS only)
+    DevBuf morton;     // uint64[n] sorted
+    DevBuf prims;      // uint32[n] sorted primitive ids
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+};
+
+struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through compaction)
+    uint32_t capacity = 0;  // = width*height
+    DevBuf ray_o[2], ray_d[2], ray_w[2];   // float4 each: (O|pixel), (D|-), (W|-)
+    DevBuf hit;             // float4 (t,u,v,prim)
+    DevBuf hit_slot;        // uint32
+    uint64_t shadow_capacity = 0;
+    DevBuf sh_o, sh_d, sh_c; // float4 each: (P|pixel), (L|tmax), (c|light)
+    DevBuf accum;           // float4 per pixel: FP32 sums
+    DevBuf qcount;          // uint32[2*32]: [0..16] extend queue sizes per bounce, [32..48] shadow queue sizes
+    DevBuf totals;          // uint64[40]: extend per bounce [0..15], shadow per bounce [16..31], samples [32]
+};
+
+struct bpt_context {
+    int device = 0;
+    uint32_t width = 0, height = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // host copies needed for validation / rebuilds
+    std::vector<bpt_drawable_sbt_data> h_drawables;
+    std::vector<bpt_blas_desc> h_blas_desc;
+    std::vector<bpt_instance_desc> h_instances;
+    std::vector<bpt_material> h_materials;
+    uint64_t num_position_floats = 0, num_indices = 0;
+    uint32_t num_dir = 0, num_point = 0, num_rect = 0;
+    bool has_normals = false, has_tangents = false, has_texcoords = false;
+
+    // device scene
+    DevBuf d_positions, d_normals, d_tangents, d_texcoords, d_indices, d_drawables, d_drawable_va, d_materials;
+    DevBuf d_textures; std::vector<DevBuf> d_texels;
+    DevBuf d_instances;          // DInstance[]
+    DevBuf d_dir, d_point, d_rect, d_ltc[4];
+    DevBuf d_sky; uint32_t sky_size = 0;
+    float sky_transform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float sky_color[3] = {1, 1, 1};
+
+    // accel
+    bool accel_built = false;
+    uint32_t accel_mode = 0;
+    std::vector<DevBvh> blas;
+    DevBvh tlas;
+    DevBuf d_blas_table;         // DBlas[]
+    DevBuf d_inst_aabb;          // scratch for TLAS build
+
+    WavefrontState wf;
+    bool capture = false;
+    uint32_t cap_bounces = 0;
+    std::vector<std::vector<uint32_t>> cap_extend_pixels, cap_shadow_pixels, cap_shadow_lights;
+    std::vector<std::vector<bpt_hit>> cap_extend_hits;
+
+    bptd::DScene scene_view() const;
+};
+
+#define BPT_CUDA_TRY(ctx, expr)                                                                      \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                        \
+            return e__ == cudaErrorMemoryAllocation ? BPT_ERR_OOM : BPT_ERR_CUDA;                    \
+        }                                                                                            \
+    } while (0)
+
+bpt_status dev_alloc(bpt_context* ctx, DevBuf& b, size_t bytes);
+void dev_free(DevBuf& b);
+bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes);
+
+// bvh_build.cu
+// Builds an LBVH over `n` primitives whose AABBs are in d_lo/d_hi (float4 each, device).
+bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi);
+bpt_status build_blas_two_level(bpt_context* ctx, uint32_t blas_index);
+bpt_status build_blas_merged(bpt_context* ctx);
+bpt_status build_tlas(bpt_context* ctx);
+bpt_status upload_instance_table(bpt_context* ctx);
+
+// render.cu
+bpt_status wavefront_alloc(bpt_context* ctx);
+bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st);
+bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out);
+bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t n, uint32_t frame_index, bpt_hit* h_hits, uint8_t* h_visible);

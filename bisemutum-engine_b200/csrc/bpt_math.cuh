@@ -1,0 +1,260 @@
+// bpt_math.cuh — device math of the wavefront path tracer (sm_100a).
+//
+// FP32 shading math that the kernels share: RNG, frames, GGX/VNDF, Schlick, the lit BSDF.
+// Reference formulas (paths under bisemutum/shaders/):
+//   core/utils/random.hlsl:3-26, core/utils/frame.hlsl:9-34, core/utils/pack.hlsl:112-129,
+//   core/material/utils.hlsl:18-129, core/material/lit.hlsl:5-58, core/utils/sampling.hlsl:14-19
+//
+// Numeric contract (DESIGN.md "Numerics"): compiled with -fmad=false so a*b+c is never fused
+// implicitly; fmaf() appears only where the contract calls for a fused op (ray/box slabs).
+// dot(a,b) = (ax*bx + ay*by) + az*bz; normalize(v) = v * (1/sqrt(dot(v,v))); trigonometry is the
+// fixed-order polynomial below, not libdevice, so results do not depend on the math library.
+//
+// Everything is BPT_HD so the same source can be compiled for the host by tests/hostcheck
+// (a test-only harness; libbpt.so itself contains no host execution path).
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#if defined(__CUDACC__)
+#define BPT_HD __host__ __device__ __forceinline__
+#else
+#define BPT_HD inline
+#endif
+
+namespace bptd {
+
+#if defined(__CUDA_ARCH__)
+BPT_HD uint32_t f2u(float f) { return __float_as_uint(f); }
+BPT_HD float u2f(uint32_t u) { return __uint_as_float(u); }
+#else
+BPT_HD uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+BPT_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#endif
+
+BPT_HD float3 v3(float x, float y, float z) { return make_float3(x, y, z); }
+BPT_HD float3 v3s(float s) { return make_float3(s, s, s); }
+BPT_HD float3 operator+(float3 a, float3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+BPT_HD float3 operator-(float3 a, float3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+BPT_HD float3 operator*(float3 a, float3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+BPT_HD float3 operator*(float3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+BPT_HD float3 operator*(float s, float3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+BPT_HD float3 operator/(float3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+BPT_HD float3 operator/(float3 a, float3 b) { return v3(a.x / b.x, a.y / b.y, a.z / b.z); }
+BPT_HD float3 operator-(float3 a) { return v3(-a.x, -a.y, -a.z); }
+// ternary min/max: identical semantics on host and device (no NaN/-0 library differences)
+BPT_HD float tmin_(float a, float b) { return a < b ? a : b; }
+BPT_HD float tmax_(float a, float b) { return a > b ? a : b; }
+BPT_HD float3 vmin(float3 a, float3 b) { return v3(tmin_(a.x, b.x), tmin_(a.y, b.y), tmin_(a.z, b.z)); }
+BPT_HD float3 vmax(float3 a, float3 b) { return v3(tmax_(a.x, b.x), tmax_(a.y, b.y), tmax_(a.z, b.z)); }
+BPT_HD float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+BPT_HD float3 cross3(float3 a, float3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+BPT_HD float3 normalize3(float3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
+BPT_HD float sat(float x) { return tmin_(tmax_(x, 0.0f), 1.0f); }
+BPT_HD float clampf_(float x, float lo, float hi) { return tmin_(tmax_(x, lo), hi); }
+BPT_HD float mix1(float a, float b, float t) { return a + (b - a) * t; }
+BPT_HD float3 mix3(float3 a, float3 b, float t) { return a + (b - a) * t; }
+BPT_HD float3 reflect3(float3 i, float3 n) { return i - n * (2.0f * dot3(n, i)); }   // HLSL reflect
+BPT_HD float max3c(float3 c) { return tmax_(c.x, tmax_(c.y, c.z)); }
+BPT_HD bool is_finite1(float x) { return (f2u(x) & 0x7f800000u) != 0x7f800000u; }
+BPT_HD bool is_finite3(float3 v) { return is_finite1(v.x) && is_finite1(v.y) && is_finite1(v.z); }
+
+constexpr float kPi = 3.14159265359f;           // core/utils/math.hlsl:3
+constexpr float kInvPi = 1.0f / 3.14159265359f;
+constexpr float kHalfPi = 1.57079632679f;
+
+BPT_HD float sq(float x) { return x * x; }
+BPT_HD float pow5f(float x) { float x2 = x * x; return (x2 * x2) * x; }     // math.hlsl:12-23
+
+// ---- RNG (random.hlsl:3-26) ---------------------------------------------------------------
+BPT_HD uint32_t rng_tea(uint32_t val0, uint32_t val1) {
+    uint32_t v0 = val0, v1 = val1, s0 = 0;
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v0;
+}
+BPT_HD float rng_next(uint32_t& state) {
+    state = 1664525u * state + 1013904223u;
+    return (float)(state & 0x00ffffffu) / 16777216.0f;
+}
+
+// ---- fixed-order trigonometry ---------------------------------------------------------------
+BPT_HD void sincos_2pi(float u, float& s, float& c) {
+    float x = u * 4.0f;
+    float q = floorf(x + 0.5f);
+    float r = x - q;
+    float a = r * 1.57079637f;
+    float a2 = a * a;
+    float sp = -1.98412698e-4f + a2 * 2.75573192e-6f;
+    sp = 8.33333333e-3f + a2 * sp;
+    sp = -1.66666667e-1f + a2 * sp;
+    float sr = a + (a * a2) * sp;
+    float cp = 2.48015873e-5f + a2 * -2.75573192e-7f;
+    cp = -1.38888889e-3f + a2 * cp;
+    cp = 4.16666667e-2f + a2 * cp;
+    cp = -0.5f + a2 * cp;
+    float cr = 1.0f + a2 * cp;
+    int qi = ((int)q) & 3;
+    s = qi == 0 ? sr : (qi == 1 ? cr : (qi == 2 ? -sr : -cr));
+    c = qi == 0 ? cr : (qi == 1 ? -sr : (qi == 2 ? -cr : sr));
+}
+BPT_HD float atan_unit(float z) {
+    float z2 = z * z;
+    float p = 0.00282363896f;
+    p = -0.0159569028f + z2 * p;
+    p = 0.0425049886f + z2 * p;
+    p = -0.0748900772f + z2 * p;
+    p = 0.106347933f + z2 * p;
+    p = -0.142027363f + z2 * p;
+    p = 0.199926957f + z2 * p;
+    p = -0.333331018f + z2 * p;
+    return z + (z * z2) * p;
+}
+BPT_HD float atan2_(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = tmax_(ax, ay), mn = tmin_(ax, ay);
+    if (mx == 0.0f) return 0.0f;
+    float a = atan_unit(mn / mx);
+    if (ay > ax) a = kHalfPi - a;
+    if (x < 0.0f) a = kPi - a;
+    return y < 0.0f ? -a : a;
+}
+BPT_HD float acos_(float x) {
+    x = clampf_(x, -1.0f, 1.0f);
+    return 2.0f * atan2_(sqrtf(1.0f - x), sqrtf(1.0f + x));
+}
+
+// ---- frames (frame.hlsl) -----------------------------------------------------------------
+struct Frame3 { float3 x, y, z; };
+BPT_HD Frame3 frame_from_normal(float3 n) {                       // frame.hlsl:9-18
+    Frame3 f; f.z = n;
+    float sign = n.z > 0.0f ? 1.0f : -1.0f;
+    float a = -1.0f / (sign + n.z);
+    float b = n.x * n.y * a;
+    f.x = v3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
+    f.y = v3(b, sign + n.y * n.y * a, -n.y);
+    return f;
+}
+BPT_HD Frame3 frame_from_nt(float3 n, float3 t) {                 // frame.hlsl:20-26
+    Frame3 f; f.z = n;
+    f.y = normalize3(cross3(n, t));
+    f.x = cross3(f.y, n);
+    return f;
+}
+BPT_HD float3 to_local(const Frame3& f, float3 v) { return v3(dot3(v, f.x), dot3(v, f.y), dot3(v, f.z)); }
+BPT_HD float3 to_world(const Frame3& f, float3 v) { return v.x * f.x + v.y * f.y + v.z * f.z; }
+
+// T after the G-buffer pack/unpack round trip (pack.hlsl:112-129) without the storage quantisation.
+BPT_HD float3 tangent_after_gbuffer(float3 N, float3 T) {
+    Frame3 fr = frame_from_normal(N);
+    float px = dot3(T, fr.x), py = dot3(T, fr.y);
+    float lnorm = fabsf(px) + fabsf(py);
+    px = px / lnorm; py = py / lnorm;
+    float packed_z = px * 0.5f + 0.5f;
+    float sign = py < 0.0f ? -1.0f : 1.0f;
+    float projected_x = packed_z * 2.0f - 1.0f;
+    float projected_y = sign * (1.0f - fabsf(projected_x));
+    return normalize3(fr.x * projected_x + fr.y * projected_y);
+}
+
+// ---- surface / BSDF (material/utils.hlsl, material/lit.hlsl) ----------------------------------
+struct Surface {
+    float3 base_color, f0_color, f90_color, normal_map_value;
+    float roughness, anisotropy, ior, opacity;
+    bool two_sided;
+};
+BPT_HD Surface surface_default() {                               // utils.hlsl:18-31
+    Surface s;
+    s.base_color = v3s(0.5f); s.f0_color = v3s(0.04f); s.f90_color = v3s(1.0f);
+    s.normal_map_value = v3(0.5f, 0.5f, 1.0f);
+    s.roughness = 0.5f; s.anisotropy = 0.0f; s.ior = 1.5f; s.opacity = 1.0f; s.two_sided = false;
+    return s;
+}
+BPT_HD float3 schlick_fresnel(float3 f0, float3 f90, float cos_theta, float ior) {   // utils.hlsl:40-51
+    if (cos_theta < 0.0f) {
+        float eta = 1.0f / ior;
+        float sin_theta_sqr = eta * eta * (1.0f - cos_theta * cos_theta);
+        cos_theta = sqrtf(tmax_(1.0f - sin_theta_sqr, 0.0f));
+    }
+    return mix3(f0, f90, pow5f(1.0f - cos_theta));
+}
+BPT_HD void aniso_roughness(float roughness, float anisotropy, float& rx, float& ry) {   // utils.hlsl:54-59
+    float aniso = sqrtf(1.0f - anisotropy * 0.9f);
+    float r2 = roughness * roughness;
+    rx = tmax_(r2 / aniso, 0.001f);
+    ry = tmax_(r2 * aniso, 0.001f);
+}
+BPT_HD float ggx_ndf(float3 h, float rx, float ry) {                                      // utils.hlsl:62-65
+    float a = (sq(h.x / rx) + sq(h.y / ry)) + sq(h.z);
+    return kInvPi / (rx * ry * a * a);
+}
+BPT_HD float ggx_g1(float3 v, float rx, float ry) {                                       // utils.hlsl:67-70
+    float a = (sq(rx * v.x) + sq(ry * v.y)) / tmax_(v.z * v.z, 0.0001f);
+    return 2.0f / (1.0f + sqrtf(1.0f + a));
+}
+BPT_HD float ggx_visible_hc(float3 v, float3 l, float rx, float ry) {                     // utils.hlsl:92-96
+    float vv = l.z * sqrtf((sq(rx * v.x) + sq(ry * v.y)) + sq(v.z));
+    float ll = v.z * sqrtf((sq(rx * l.x) + sq(ry * l.y)) + sq(l.z));
+    return 0.5f / tmax_(vv + ll, 0.0001f);
+}
+BPT_HD float3 ggx_vndf_sample(float3 v, float rx, float ry, float rand_x, float rand_y) { // utils.hlsl:98-116
+    if (v.z < 0.0f) v = -v;
+    float3 vh = normalize3(v3(rx * v.x, ry * v.y, v.z));
+    float len_sqr = vh.x * vh.x + vh.y * vh.y;
+    float3 t1v = len_sqr > 0.0f ? v3(-vh.y, vh.x, 0.0f) / sqrtf(len_sqr) : v3(1.0f, 0.0f, 0.0f);
+    float3 t2v = cross3(vh, t1v);
+    float r = sqrtf(rand_x);
+    float sn, cs;
+    sincos_2pi(rand_y, sn, cs);
+    float t1 = r * cs;
+    float t2 = r * sn;
+    float s = 0.5f * (1.0f + vh.z);
+    t2 = (1.0f - s) * sqrtf(1.0f - t1 * t1) + s * t2;
+    float3 nh = (t1 * t1v + t2 * t2v) + sqrtf(tmax_((1.0f - t1 * t1) - t2 * t2, 0.0f)) * vh;
+    return normalize3(v3(rx * nh.x, ry * nh.y, tmax_(nh.z, 0.0f)));
+}
+BPT_HD float ggx_vndf_pdf(float3 h, float3 v, float rx, float ry) {                        // utils.hlsl:118-121
+    return ggx_g1(v, rx, ry) * ggx_ndf(h, rx, ry) * tmax_(dot3(h, v), 0.0f) / tmax_(v.z, 0.0001f);
+}
+// surface_eval (material.hlsl:81-118 → lit.hlsl:5-35): diffuse + specular; unlit/none → 0
+BPT_HD float3 bsdf_eval(float3 N, float3 T, float3 B, float3 V, float3 L, const Surface& s, uint32_t surface_model) {
+    if (surface_model != 1u) return v3s(0.0f);
+    float3 H = normalize3(V + L);
+    float3 lh = v3(dot3(H, T), dot3(H, B), dot3(H, N));
+    float3 lv = v3(dot3(V, T), dot3(V, B), dot3(V, N));
+    float3 ll = v3(dot3(L, T), dot3(L, B), dot3(L, N));
+    if (lv.z <= 0.0f || ll.z <= 0.0f) return v3s(0.0f);
+    float3 fr = schlick_fresnel(s.f0_color, s.f90_color, tmax_(dot3(V, H), 0.0f), s.ior);
+    float3 diffuse = (v3s(1.0f) - fr) * s.base_color * kInvPi * tmax_(ll.z, 0.0f);
+    float rx, ry;
+    aniso_roughness(s.roughness, s.anisotropy, rx, ry);
+    float ndf = ggx_ndf(lh, rx, ry);
+    float vis = ggx_visible_hc(lv, ll, rx, ry);
+    float3 specular = fr * ndf * vis * tmax_(ll.z, 0.0f);
+    return diffuse + specular;
+}
+// surface_eval_lut (lit.hlsl:37-58)
+BPT_HD float3 bsdf_eval_lut(float3 N, float3 V, const Surface& s, float3 int_diffuse, float3 int_specular, float2 int_brdf, uint32_t surface_model) {
+    if (surface_model != 1u) return v3s(0.0f);
+    float ndotv = dot3(N, V);
+    if (ndotv <= 0.0f) return v3s(0.0f);
+    float3 fr = schlick_fresnel(s.f0_color, s.f90_color, ndotv, s.ior);
+    float3 diffuse = (v3s(1.0f) - fr) * s.base_color * kInvPi;
+    float3 specular = s.f0_color * int_brdf.x + s.f90_color * int_brdf.y;
+    return diffuse * int_diffuse + specular * int_specular;
+}
+BPT_HD float3 uniform_sphere_sample(float rand_x, float rand_y) {                           // sampling.hlsl:14-19
+    float sn, cs;
+    sincos_2pi(rand_x, sn, cs);
+    float z = rand_y * 2.0f - 1.0f;
+    float r = sqrtf(tmax_(1.0f - z * z, 0.0f));
+    return v3(cs * r, sn * r, z);
+}
+
+} // namespace bptd

@@ -1,0 +1,258 @@
+// bpt_scene.cuh — device-side scene description, vertex fetch, material function, sky and light
+// evaluation. Layout in HBM (DESIGN.md "Data layout"):
+//   * geometry streams exactly as the reference's GpuSceneData (flat float / uint arrays,
+//     bisemutum/src/graphics/gpu_scene_data.hpp:10-24) + 36-B DrawableSbtData records
+//   * BVH nodes: 64 B = 4 x float4 (both child boxes + child ids) → four 16-B vector loads
+//   * triangles: 48 B = 3 x float4 (v0|prim, e1|instance slot, e2|-) in BVH leaf order
+//   * instances: 128-B records (object→world 3x4, world→object 3x4, ids) as float4[8]
+#pragma once
+#include "../../include/bpt/bpt.h"
+#include "bpt_math.cuh"
+
+#if defined(__CUDA_ARCH__)
+#define BPT_LDG(p) __ldg(p)
+#else
+#define BPT_LDG(p) (*(p))
+#endif
+
+namespace bptd {
+
+struct DBlas {
+    const float4* nodes;   // 4 per node
+    const float4* tris;    // 3 per triangle, leaf order
+    int32_t root;
+    uint32_t n;
+};
+
+struct DTexture {
+    const void* texels;
+    uint32_t w, h, format, addr_u, addr_v, linear;
+};
+
+struct DInstance {           // 128 B
+    float o2w[12];
+    float w2o[12];
+    uint32_t instance_id, flags, blas, pad[5];
+};
+
+struct DScene {
+    const float* positions; const float* normals; const float* tangents; const float* texcoords;
+    const uint32_t* indices;
+    const bpt_drawable_sbt_data* drawables;
+    const uint32_t* drawable_va;
+    const bpt_material* materials;
+    const DTexture* textures; uint32_t num_textures;
+    const DInstance* instances; uint32_t num_instances;
+    // accel
+    uint32_t accel_mode;
+    const float4* tlas_nodes; const uint32_t* tlas_prims; int32_t tlas_root; uint32_t tlas_n;
+    const DBlas* blas;
+    // lights
+    const bpt_dir_light_data* dir_lights; uint32_t num_dir;
+    const bpt_point_light_data* point_lights; uint32_t num_point;
+    const bpt_rect_light_data* rect_lights; uint32_t num_rect;
+    const float* ltc_m0; const float* ltc_m1; const float* ltc_m2; const float* ltc_norm;
+    // sky
+    const float4* sky_faces; uint32_t sky_size;
+    float sky_transform[9]; float sky_color[3];
+};
+
+BPT_HD float3 xf_point(const float* m, float3 p) {
+    return v3(((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7],
+              ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11]);
+}
+BPT_HD float3 xf_vector(const float* m, float3 v) {
+    return v3((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z, (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
+}
+BPT_HD float3 xf_vector_t(const float* m, float3 v) {   // transpose(upper 3x3) * v
+    return v3((m[0] * v.x + m[4] * v.y) + m[8] * v.z, (m[1] * v.x + m[5] * v.y) + m[9] * v.z, (m[2] * v.x + m[6] * v.y) + m[10] * v.z);
+}
+
+// Inverse of a row-major 3x4 affine matrix: adjugate / determinant, then t' = -(A^-1 t).
+BPT_HD void invert_3x4(const float* m, float* o) {
+    float a00 = m[0], a01 = m[1], a02 = m[2], a10 = m[4], a11 = m[5], a12 = m[6], a20 = m[8], a21 = m[9], a22 = m[10];
+    float c00 = a11 * a22 - a12 * a21;
+    float c01 = a12 * a20 - a10 * a22;
+    float c02 = a10 * a21 - a11 * a20;
+    float det = (a00 * c00 + a01 * c01) + a02 * c02;
+    float inv_det = 1.0f / det;
+    o[0] = c00 * inv_det; o[1] = (a02 * a21 - a01 * a22) * inv_det; o[2] = (a01 * a12 - a02 * a11) * inv_det;
+    o[4] = c01 * inv_det; o[5] = (a00 * a22 - a02 * a20) * inv_det; o[6] = (a02 * a10 - a00 * a12) * inv_det;
+    o[8] = c02 * inv_det; o[9] = (a01 * a20 - a00 * a21) * inv_det; o[10] = (a00 * a11 - a01 * a10) * inv_det;
+    float tx = m[3], ty = m[7], tz = m[11];
+    o[3] = -((o[0] * tx + o[1] * ty) + o[2] * tz);
+    o[7] = -((o[4] * tx + o[5] * ty) + o[6] * tz);
+    o[11] = -((o[8] * tx + o[9] * ty) + o[10] * tz);
+}
+
+// ---- textures: explicit FP32 bilinear (texture units filter with 8-bit weights → > 1e-4) --------
+BPT_HD int wrap_tc(int c, int n, uint32_t mode) {
+    if (mode == BPT_ADDRESS_REPEAT) { int m = c % n; return m < 0 ? m + n : m; }
+    return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+BPT_HD float4 texel_at(const DTexture& t, int x, int y) {
+    size_t i = (size_t)y * t.w + x;
+    if (t.format == BPT_TEXTURE_RGBA8_UNORM) {
+        uchar4 p = BPT_LDG(reinterpret_cast<const uchar4*>(t.texels) + i);
+        return make_float4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, (float)p.w / 255.0f);
+    }
+    return BPT_LDG(reinterpret_cast<const float4*>(t.texels) + i);
+}
+BPT_HD float4 mix4(float4 a, float4 b, float t) {
+    return make_float4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, a.w + (b.w - a.w) * t);
+}
+BPT_HD float4 sample_tex(const DTexture& t, float u, float v) {
+    if (!t.linear) {
+        int xi = wrap_tc((int)floorf(u * (float)t.w), (int)t.w, t.addr_u);
+        int yi = wrap_tc((int)floorf(v * (float)t.h), (int)t.h, t.addr_v);
+        return texel_at(t, xi, yi);
+    }
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = wrap_tc((int)x0f, (int)t.w, t.addr_u), x1 = wrap_tc((int)x0f + 1, (int)t.w, t.addr_u);
+    int y0 = wrap_tc((int)y0f, (int)t.h, t.addr_v), y1 = wrap_tc((int)y0f + 1, (int)t.h, t.addr_v);
+    float4 top = mix4(texel_at(t, x0, y0), texel_at(t, x1, y0), fx);
+    float4 bot = mix4(texel_at(t, x0, y1), texel_at(t, x1, y1), fx);
+    return mix4(top, bot, fy);
+}
+BPT_HD float4 sample_or(const DScene& sc, int32_t tex, float2 uv, float4 dflt) {
+    if (tex < 0 || (uint32_t)tex >= sc.num_textures) return dflt;
+    return sample_tex(sc.textures[tex], uv.x, uv.y);
+}
+
+// ---- sky (deferred_lighting_secondary.hlsl:24-29; Vulkan cube face rule = inverse of
+//      core/utils/cubemap.hlsl:3-21; bilinear inside the face, clamp to edge) --------------------
+BPT_HD float3 sample_sky(const DScene& sc, float3 d) {
+    if (sc.sky_size == 0) return v3s(0.0f);
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int face; float s_, t_, ma;
+    if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; ma = ax; s_ = d.x >= 0.0f ? -d.z : d.z; t_ = -d.y; }
+    else if (ay >= az) { face = d.y >= 0.0f ? 2 : 3; ma = ay; s_ = d.x; t_ = d.y >= 0.0f ? d.z : -d.z; }
+    else { face = d.z >= 0.0f ? 4 : 5; ma = az; s_ = d.z >= 0.0f ? d.x : -d.x; t_ = -d.y; }
+    if (!(ma > 0.0f)) return v3s(0.0f);
+    float u = 0.5f * (s_ / ma + 1.0f), v = 0.5f * (t_ / ma + 1.0f);
+    int n = (int)sc.sky_size;
+    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = wrap_tc((int)x0f, n, BPT_ADDRESS_CLAMP), x1 = wrap_tc((int)x0f + 1, n, BPT_ADDRESS_CLAMP);
+    int y0 = wrap_tc((int)y0f, n, BPT_ADDRESS_CLAMP), y1 = wrap_tc((int)y0f + 1, n, BPT_ADDRESS_CLAMP);
+    const float4* base = sc.sky_faces + (size_t)face * n * n;
+    float4 a = BPT_LDG(base + (size_t)y0 * n + x0), b = BPT_LDG(base + (size_t)y0 * n + x1);
+    float4 c = BPT_LDG(base + (size_t)y1 * n + x0), e = BPT_LDG(base + (size_t)y1 * n + x1);
+    float3 top = mix3(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), fx);
+    float3 bot = mix3(v3(c.x, c.y, c.z), v3(e.x, e.y, e.z), fx);
+    return mix3(top, bot, fy);
+}
+
+// ---- vertex fetch (core/raytracing/hit.hlsl:27-164) ---------------------------------------------
+struct HitVertex { float3 normal_world, tangent_world, bitangent_world; float2 texcoord; };
+
+BPT_HD void load_tri_indices(const DScene& sc, const bpt_drawable_sbt_data& dr, uint32_t prim, uint32_t idx[3]) {
+    const uint32_t* p = sc.indices + (size_t)dr.index_offset + 3ull * prim;
+    idx[0] = BPT_LDG(p); idx[1] = BPT_LDG(p + 1); idx[2] = BPT_LDG(p + 2);
+}
+BPT_HD float bary_mix(float a0, float a1, float a2, float bu, float bv) { return (a0 + (a1 - a0) * bu) + (a2 - a0) * bv; }
+BPT_HD float2 load_texcoord(const DScene& sc, const bpt_drawable_sbt_data& dr, uint32_t va, const uint32_t idx[3], float bu, float bv) {
+    if (!(va & BPT_VA_TEXCOORD)) return make_float2(0.0f, 0.0f);
+    const float* b = sc.texcoords + dr.texcoord_offset;
+    float2 t0 = BPT_LDG(reinterpret_cast<const float2*>(b + 2ull * idx[0]));
+    float2 t1 = BPT_LDG(reinterpret_cast<const float2*>(b + 2ull * idx[1]));
+    float2 t2 = BPT_LDG(reinterpret_cast<const float2*>(b + 2ull * idx[2]));
+    return make_float2(bary_mix(t0.x, t1.x, t2.x, bu, bv), bary_mix(t0.y, t1.y, t2.y, bu, bv));
+}
+BPT_HD float3 load3(const float* p) { return v3(BPT_LDG(p), BPT_LDG(p + 1), BPT_LDG(p + 2)); }
+BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_t prim, float bu, float bv) {
+    const bpt_drawable_sbt_data& dr = sc.drawables[in.instance_id];
+    uint32_t va = BPT_LDG(sc.drawable_va + in.instance_id);
+    uint32_t idx[3];
+    load_tri_indices(sc, dr, prim, idx);
+    float3 normal = v3(0.0f, 0.0f, 1.0f);
+    if (va & BPT_VA_NORMAL) {
+        const float* b = sc.normals + dr.normal_offset;
+        float3 n0 = load3(b + 3ull * idx[0]), n1 = load3(b + 3ull * idx[1]), n2 = load3(b + 3ull * idx[2]);
+        normal = v3(bary_mix(n0.x, n1.x, n2.x, bu, bv), bary_mix(n0.y, n1.y, n2.y, bu, bv), bary_mix(n0.z, n1.z, n2.z, bu, bv));
+    }
+    float3 tangent = v3(1.0f, 0.0f, 0.0f); float tangent_w = 1.0f;
+    if (va & BPT_VA_TANGENT) {
+        const float* b = sc.tangents + dr.tangent_offset;
+        float4 t0 = BPT_LDG(reinterpret_cast<const float4*>(b + 4ull * idx[0]));
+        float4 t1 = BPT_LDG(reinterpret_cast<const float4*>(b + 4ull * idx[1]));
+        float4 t2 = BPT_LDG(reinterpret_cast<const float4*>(b + 4ull * idx[2]));
+        tangent = v3(bary_mix(t0.x, t1.x, t2.x, bu, bv), bary_mix(t0.y, t1.y, t2.y, bu, bv), bary_mix(t0.z, t1.z, t2.z, bu, bv));
+        tangent_w = bary_mix(t0.w, t1.w, t2.w, bu, bv);
+    }
+    HitVertex hv;
+    hv.normal_world = normalize3(xf_vector_t(in.w2o, normal));                       // hit.hlsl:157
+    hv.tangent_world = normalize3(xf_vector(in.o2w, tangent));                       // hit.hlsl:158
+    hv.bitangent_world = normalize3(cross3(hv.normal_world, hv.tangent_world)) * tangent_w;   // hit.hlsl:159
+    hv.texcoord = load_texcoord(sc, dr, va, idx, bu, bv);
+    return hv;
+}
+
+// ---- material_function: closed set of the reference's HLSL snippets -----------------------------
+BPT_HD Surface eval_material(const DScene& sc, const bpt_material& m, float2 uv) {
+    Surface s = surface_default();
+    uint32_t kind = (m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu;
+    if (kind == BPT_MATERIAL_KIND_GLTF_PBR) {                                        // import_model.cpp:208-230
+        float4 bt = sample_or(sc, m.base_color_tex, uv, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+        s.base_color = v3(bt.x * m.base_color[0], bt.y * m.base_color[1], bt.z * m.base_color[2]);
+        s.opacity = bt.w * m.base_color[3];
+        float4 nt = sample_or(sc, m.normal_map_tex, uv, make_float4(0.5f, 0.5f, 1.0f, 1.0f));
+        float3 nm = v3(nt.x * 2.0f - 1.0f, nt.y * 2.0f - 1.0f, nt.z * 2.0f - 1.0f);
+        nm = normalize3(nm * v3(m.normal_map_scale, m.normal_map_scale, 1.0f));
+        s.normal_map_value = nm * 0.5f + v3s(0.5f);
+        float4 mr = sample_or(sc, m.metallic_roughness_tex, uv, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+        s.roughness = m.roughness * mr.y;
+        s.f0_color = mix3(v3s(0.04f), s.base_color, m.metallic * mr.z);
+        float occlusion = sample_or(sc, m.occlusion_tex, uv, make_float4(1.0f, 1.0f, 1.0f, 1.0f)).x * m.occlusion_strength;
+        s.base_color = s.base_color * occlusion;
+        s.f0_color = s.f0_color * occlusion;
+        s.f90_color = s.f90_color * occlusion;
+        s.two_sided = (m.flags & BPT_MATERIAL_FLAG_TWO_SIDED) != 0;
+    } else if (kind == BPT_MATERIAL_KIND_ASSIMP_DIFFUSE) {                           // import_model.cpp:490-493
+        s.base_color = v3(m.base_color[0], m.base_color[1], m.base_color[2]);
+        s.roughness = m.roughness;
+    }
+    return s;
+}
+BPT_HD float eval_hit_opacity(const DScene& sc, uint32_t instance_id, uint32_t prim, float bu, float bv) {
+    const bpt_drawable_sbt_data& dr = sc.drawables[instance_id];
+    const bpt_material& m = sc.materials[dr.material_offset / (uint32_t)sizeof(bpt_material)];
+    uint32_t idx[3];
+    load_tri_indices(sc, dr, prim, idx);
+    float2 uv = load_texcoord(sc, dr, BPT_LDG(sc.drawable_va + instance_id), idx, bu, bv);
+    return eval_material(sc, m, uv).opacity;
+}
+
+// ---- point / spot light (lights.hlsl:14-25) -----------------------------------------------------
+BPT_HD float3 eval_point_light(const bpt_point_light_data& l, float3 P, float3& light_dir, float& dist) {
+    float3 lv = v3(l.position[0], l.position[1], l.position[2]) - P;
+    float d2 = dot3(lv, lv);
+    dist = sqrtf(d2);
+    light_dir = lv / dist;
+    float att = sat(1.0f - sq(d2 * l.range_sqr_inv)) / tmax_(d2, 0.001f);
+    if (l.cos_inner > l.cos_outer) {
+        float ct = clampf_(dot3(light_dir, v3(l.direction[0], l.direction[1], l.direction[2])), l.cos_outer, l.cos_inner);
+        att = att * ((ct - l.cos_outer) / tmax_(l.cos_inner - l.cos_outer, 0.001f));
+    }
+    return v3(l.emission[0], l.emission[1], l.emission[2]) * att;
+}
+
+// ---- camera ray (generate_camera_ray.hlsl:4-16, camera.hlsl:7-9) --------------------------------
+BPT_HD void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t W, uint32_t H, float3& O, float3& D) {
+    const float* ip = cam.matrix_inv_proj;
+    const float* iv = cam.matrix_inv_view;
+    float uvx = ((float)px + 0.5f) / (float)W, uvy = ((float)py + 0.5f) / (float)H;
+    float nx = uvx * 2.0f - 1.0f, ny = 1.0f - uvy * 2.0f;
+    float3 dl = v3(((ip[0] * nx + ip[4] * ny) + ip[8]) + ip[12], ((ip[1] * nx + ip[5] * ny) + ip[9]) + ip[13],
+                   ((ip[2] * nx + ip[6] * ny) + ip[10]) + ip[14]);
+    dl = normalize3(dl);
+    float3 dw = v3((iv[0] * dl.x + iv[4] * dl.y) + iv[8] * dl.z, (iv[1] * dl.x + iv[5] * dl.y) + iv[9] * dl.z,
+                   (iv[2] * dl.x + iv[6] * dl.y) + iv[10] * dl.z);
+    D = normalize3(dw);
+    O = v3(iv[12], iv[13], iv[14]);
+}
+
+} // namespace bptd

@@ -1,0 +1,93 @@
+// bpt_shade.cuh — one path vertex: closest-hit material + direct lighting + next direction.
+//
+// This fuses what the reference runs as three full-screen passes per bounce
+//   closest hit      shaders/renderer/raytracing/hits/rt_gbuffer_hit.hlsl:6-18  (G-buffer write)
+//   lighting         shaders/renderer/raytracing/deferred_lighting_secondary.hlsl:11-111
+//   next direction   shaders/renderer/raytracing/direction_sample/sample_secondary_ray.hlsl:11-69
+// into one per-path function: the surface never leaves registers, so the 28 B/px G-buffer round
+// trip (and its fp16 / rg11b10 / unorm8 quantisation) disappears (state_precision = fp32).
+// Visibility of directional / point / spot lights is a shadow ray handed to `sink.shadow()` (NEW:
+// the reference samples rasterised shadow maps, lights.hlsl:27-159).
+#pragma once
+#include "bpt_ltc.cuh"
+#include "bpt_trace.cuh"
+
+namespace bptd {
+
+struct ShadeParams {
+    uint32_t width, height;
+    uint32_t max_bounces;      // clamped to [2,16] (path_tracing.cpp:290)
+    uint32_t nee_mode;
+    float ray_length;
+};
+
+// Sink concept:
+//   void add(float3 c)                                         — unshadowed radiance for this pixel
+//   void shadow(float3 P, float3 L, float tmax, float3 c, uint32_t light) — NEE candidate
+// Returns true when the path continues; (nO, nD, nW) is then the next extend ray.
+template <class Sink>
+BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame_index, uint32_t bounce, uint32_t pixel,
+                         float3 O, float3 D, float3 Wt, const TraceResult& hit, Sink& sink, float3& nO, float3& nD, float3& nW) {
+    if (!hit.hit) {                                                     // deferred_lighting_secondary.hlsl:24-29
+        const float* m = sc.sky_transform;
+        float3 dir = v3((m[0] * D.x + m[1] * D.y) + m[2] * D.z, (m[3] * D.x + m[4] * D.y) + m[5] * D.z, (m[6] * D.x + m[7] * D.y) + m[8] * D.z);
+        float3 color = sample_sky(sc, dir) * v3(sc.sky_color[0], sc.sky_color[1], sc.sky_color[2]);
+        sink.add(color * Wt);
+        return false;
+    }
+    const DInstance& in = sc.instances[hit.slot];
+    const bpt_drawable_sbt_data& dr = sc.drawables[in.instance_id];
+    const bpt_material& mat = sc.materials[dr.material_offset / (uint32_t)sizeof(bpt_material)];
+    const uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
+    float3 P = O + D * hit.t;                                           // rt_gbuffer.hlsl:32
+    HitVertex hv = fetch_hit_vertex(sc, in, hit.prim, hit.u, hit.v);
+    Surface surf = eval_material(sc, mat, hv.texcoord);
+    float3 nts = surf.normal_map_value * 2.0f - v3s(1.0f);              // rt_gbuffer_hit.hlsl:10-14
+    float3 N = normalize3((nts.x * hv.tangent_world + nts.y * hv.bitangent_world) + nts.z * hv.normal_world);
+    if (surf.two_sided && dot3(D, N) > 0.0f) N = -N;
+    float3 T = tangent_after_gbuffer(N, hv.tangent_world);              // gbuffer.hlsl:27,41
+    float3 B = cross3(N, T);
+    surf.opacity = 1.0f;                                                // gbuffer.hlsl:44
+    float3 V = normalize3(O - P);                                       // deferred_lighting_secondary.hlsl:45
+
+    for (uint32_t l = 0; l < sc.num_rect; l++)                          // :72-96 (unshadowed, as the reference)
+        sink.add(eval_rect_light(sc, sc.rect_lights[l], P, N, T, B, V, surf, surface_model) * Wt);
+    for (uint32_t l = 0; l < sc.num_dir; l++) {                         // :51-60
+        const bpt_dir_light_data& li = sc.dir_lights[l];
+        float3 L = v3(li.direction[0], li.direction[1], li.direction[2]);
+        float3 c = (v3(li.emission[0], li.emission[1], li.emission[2]) * bsdf_eval(N, T, B, V, L, surf, surface_model)) * Wt;
+        if (max3c(c) > 0.0f) sink.shadow(P, L, sp.ray_length, c, l);
+    }
+    for (uint32_t l = 0; l < sc.num_point; l++) {                       // :61-70
+        float3 L; float dist;
+        float3 le = eval_point_light(sc.point_lights[l], P, L, dist);
+        float3 c = (le * bsdf_eval(N, T, B, V, L, surf, surface_model)) * Wt;
+        if (max3c(c) > 0.0f) sink.shadow(P, L, dist * 0.999f, c, sc.num_dir + l);
+    }
+
+    // next direction — sample_secondary_ray.hlsl:11-69 with bounce_index = bounce
+    if (bounce + 1 >= sp.max_bounces) return false;
+    if (max3c(Wt) < 0.001f) return false;                               // :23-28
+    Frame3 frame = frame_from_nt(N, T);                                 // :42
+    float3 V_local = to_local(frame, V);
+    float rx, ry;
+    aniso_roughness(surf.roughness, surf.anisotropy, rx, ry);
+    uint32_t seed = rng_tea(pixel, frame_index + bounce * 3u);          // :52 (pixel = y * width + x)
+    float u1 = rng_next(seed);
+    float u2 = rng_next(seed);
+    float3 half_dir = ggx_vndf_sample(V_local, rx, ry, u1, u2);
+    float3 out_local = reflect3(-V_local, half_dir);
+    float pdf_wh = ggx_vndf_pdf(half_dir, V_local, rx, ry);
+    float pdf = pdf_wh / (4.0f * fabsf(dot3(half_dir, V_local)));
+    float3 out_dir = to_world(frame, out_local);
+    float3 bsdf = bsdf_eval(N, T, B, V, out_dir, surf, surface_model);
+    float3 weight = bsdf / pdf;
+    if (!is_finite3(weight)) weight = v3s(0.0f);                        // :62-64
+    float3 w2 = weight * Wt;
+    // a zero-weight path can never contribute again (deferred_lighting_secondary.hlsl:17-21): drop it
+    if (w2.x == 0.0f && w2.y == 0.0f && w2.z == 0.0f) return false;
+    nO = P; nD = out_dir; nW = w2;
+    return true;
+}
+
+} // namespace bptd

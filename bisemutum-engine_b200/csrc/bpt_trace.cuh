@@ -1,0 +1,174 @@
+// bpt_trace.cuh — stack-based software BVH traversal (B200 has no RT cores).
+//
+// Semantics kept from the reference's hardware path: closest hit in (TMin, TMax] with
+// RAY_FLAG_NONE and no face culling (shaders/renderer/raytracing/rt_gbuffer.hlsl:17-25), the
+// any-hit opacity rule for non-opaque instances (hits/rt_gbuffer_hit.hlsl:20-35) with ONE random
+// number per ray seeded from the ray's bit pattern (hits/rt_gbuffer.hlsl:14-19).
+//
+// Determinism: a hit replaces the current best iff t < best || (t == best && id < best_id) with
+// id = (instance slot << 32 | primitive), and boxes are culled with t_near <= best, so the result
+// does not depend on traversal order — the kernel is free to reorder work.
+//
+// Node fetch = four 16-B loads (64 B); triangle fetch = three 16-B loads (48 B).
+#pragma once
+#include "bpt_scene.cuh"
+
+namespace bptd {
+
+constexpr int kStackSize = 160;           // Karras depth bound: 63 code bits + 32 index bits per level
+constexpr int32_t kSentinel = (int32_t)0x80000000;
+
+struct TraceResult {
+    float t, u, v;
+    uint32_t slot, prim;
+    bool hit;
+};
+
+struct RayState {
+    float3 O, D;          // world-space ray (opacity seed)
+    float tmin, tbest;
+    uint32_t best_slot, best_prim;
+    float bu, bv;
+    uint32_t frame_index;
+    float opacity_u;
+    bool have_u, found;
+};
+
+BPT_HD float ray_opacity_random(RayState& rs) {                 // hits/rt_gbuffer.hlsl:14-19
+    if (!rs.have_u) {
+        uint32_t seed = f2u(rs.O.x) ^ f2u(rs.O.y) ^ f2u(rs.O.z) ^ f2u(rs.D.x) ^ f2u(rs.D.y) ^ f2u(rs.D.z);
+        uint32_t st = rng_tea(seed, rs.frame_index);
+        rs.opacity_u = rng_next(st);
+        rs.have_u = true;
+    }
+    return rs.opacity_u;
+}
+
+// true = keep the candidate (hits/rt_gbuffer_hit.hlsl:20-35)
+BPT_HD bool anyhit_keep(const DScene& sc, RayState& rs, uint32_t slot, uint32_t prim, float u, float v) {
+    const DInstance& in = sc.instances[slot];
+    if (!(in.flags & BPT_INSTANCE_FORCE_NON_OPAQUE)) return true;
+    const bpt_drawable_sbt_data& dr = sc.drawables[in.instance_id];
+    const bpt_material& m = sc.materials[dr.material_offset / (uint32_t)sizeof(bpt_material)];
+    uint32_t blend = (m.flags >> BPT_MATERIAL_BLEND_SHIFT) & 0xffu;
+    if (blend == BPT_BLEND_OPAQUE) return true;
+    float opacity = eval_hit_opacity(sc, in.instance_id, prim, u, v);
+    if (blend == BPT_BLEND_ALPHA_TEST) return !(opacity < 0.01f);
+    return !(ray_opacity_random(rs) < 1.0f - opacity);
+}
+
+// Möller–Trumbore on the (v0, e1, e2) record; unfused arithmetic (see bpt_math.cuh header).
+template <bool ANY>
+BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, float3 O, float3 D, uint32_t slot_or_none) {
+    float4 a = BPT_LDG(tri), b = BPT_LDG(tri + 1), c = BPT_LDG(tri + 2);
+    float3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
+    float3 pvec = cross3(D, e2);
+    float det = dot3(e1, pvec);
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    float3 tvec = O - v0;
+    float u = dot3(tvec, pvec) * inv;
+    if (u < 0.0f || u > 1.0f) return false;
+    float3 qvec = cross3(tvec, e1);
+    float v = dot3(D, qvec) * inv;
+    if (v < 0.0f || u + v > 1.0f) return false;
+    float t = dot3(e2, qvec) * inv;
+    if (!(t > rs.tmin)) return false;
+    uint32_t prim = f2u(a.w);
+    uint32_t slot = slot_or_none == 0xffffffffu ? f2u(b.w) : slot_or_none;
+    bool better = t < rs.tbest || (t == rs.tbest && (!rs.found || slot < rs.best_slot || (slot == rs.best_slot && prim < rs.best_prim)));
+    if (!better) return false;
+    if (!anyhit_keep(sc, rs, slot, prim, u, v)) return false;
+    rs.tbest = t; rs.bu = u; rs.bv = v; rs.best_slot = slot; rs.best_prim = prim; rs.found = true;
+    return true;
+}
+
+struct RaySpace { float3 O, D, idir, ood; };
+BPT_HD RaySpace make_space(float3 O, float3 D) {
+    const float ooeps = 8.27180613e-25f;   // 2^-80
+    RaySpace r; r.O = O; r.D = D;
+    r.idir.x = 1.0f / (fabsf(D.x) > ooeps ? D.x : copysignf(ooeps, D.x));
+    r.idir.y = 1.0f / (fabsf(D.y) > ooeps ? D.y : copysignf(ooeps, D.y));
+    r.idir.z = 1.0f / (fabsf(D.z) > ooeps ? D.z : copysignf(ooeps, D.z));
+    r.ood = O * r.idir;
+    return r;
+}
+
+// One node step: returns the next node to visit (or kSentinel+1 == "pop") and optionally pushes.
+#define BPT_POP ((int32_t)0x80000001)
+BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, float tmin, float tbest, int32_t* stack, int& sp) {
+    const float4* n = nodes + 4 * (size_t)cur;
+    float4 n0 = BPT_LDG(n), n1 = BPT_LDG(n + 1), n2 = BPT_LDG(n + 2), n3 = BPT_LDG(n + 3);
+    float c0lox = fmaf(n0.x, r.idir.x, -r.ood.x), c0hix = fmaf(n0.y, r.idir.x, -r.ood.x);
+    float c0loy = fmaf(n0.z, r.idir.y, -r.ood.y), c0hiy = fmaf(n0.w, r.idir.y, -r.ood.y);
+    float c1lox = fmaf(n1.x, r.idir.x, -r.ood.x), c1hix = fmaf(n1.y, r.idir.x, -r.ood.x);
+    float c1loy = fmaf(n1.z, r.idir.y, -r.ood.y), c1hiy = fmaf(n1.w, r.idir.y, -r.ood.y);
+    float c0loz = fmaf(n2.x, r.idir.z, -r.ood.z), c0hiz = fmaf(n2.y, r.idir.z, -r.ood.z);
+    float c1loz = fmaf(n2.z, r.idir.z, -r.ood.z), c1hiz = fmaf(n2.w, r.idir.z, -r.ood.z);
+    float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
+    float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tbest));
+    float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
+    float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tbest));
+    bool h0 = t0n <= t0f, h1 = t1n <= t1f;
+    int32_t ch0 = (int32_t)f2u(n3.x), ch1 = (int32_t)f2u(n3.y);
+    if (h0 && h1) {
+        bool c0_near = t0n <= t1n;
+        stack[sp++] = c0_near ? ch1 : ch0;
+        return c0_near ? ch0 : ch1;
+    }
+    if (h0) return ch0;
+    if (h1) return ch1;
+    return BPT_POP;
+}
+
+template <bool ANY>
+BPT_HD TraceResult trace_ray(const DScene& sc, float3 O, float3 D, float tmin, float tmax, uint32_t frame_index) {
+    RayState rs;
+    rs.O = O; rs.D = D; rs.tmin = tmin; rs.tbest = tmax; rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu;
+    rs.bu = 0.0f; rs.bv = 0.0f; rs.frame_index = frame_index; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
+    int32_t stack[kStackSize];
+    int sp = 0;
+    const bool two_level = sc.accel_mode == BPT_ACCEL_TWO_LEVEL;
+    RaySpace world = make_space(O, D);
+    RaySpace cur_space = world;
+    const float4* nodes = two_level ? sc.tlas_nodes : sc.blas[0].nodes;
+    const float4* tris = two_level ? nullptr : sc.blas[0].tris;
+    uint32_t slot = 0xffffffffu;           // 0xffffffff: take the slot from the triangle record (merged)
+    bool in_blas = !two_level;
+    int32_t cur = two_level ? sc.tlas_root : sc.blas[0].root;
+    uint32_t nprims = two_level ? sc.tlas_n : sc.blas[0].n;
+    if (nprims != 0) {
+        for (;;) {
+            if (cur >= 0) {
+                cur = node_step(nodes, cur, cur_space, rs.tmin, rs.tbest, stack, sp);
+                if (cur != BPT_POP) continue;
+            } else if (in_blas) {
+                bool accepted = test_triangle<ANY>(sc, rs, tris + 3 * (size_t)(uint32_t)~cur, cur_space.O, cur_space.D, slot);
+                if (ANY && accepted) break;
+            } else {
+                // TLAS leaf: enter the instance (object-space ray, direction NOT renormalised so t is shared)
+                slot = BPT_LDG(sc.tlas_prims + (uint32_t)~cur);
+                const DInstance& in = sc.instances[slot];
+                const DBlas& bl = sc.blas[in.blas];
+                cur_space = make_space(xf_point(in.w2o, O), xf_vector(in.w2o, D));
+                nodes = bl.nodes; tris = bl.tris; in_blas = true;
+                stack[sp++] = kSentinel;
+                cur = bl.root;
+                continue;
+            }
+            // pop
+            if (sp == 0) break;
+            cur = stack[--sp];
+            if (cur == kSentinel) {
+                cur_space = world; nodes = sc.tlas_nodes; tris = nullptr; in_blas = false;
+                if (sp == 0) break;
+                cur = stack[--sp];
+            }
+        }
+    }
+    TraceResult res;
+    res.hit = rs.found; res.t = rs.found ? rs.tbest : -1.0f; res.u = rs.bu; res.v = rs.bv; res.slot = rs.best_slot; res.prim = rs.best_prim;
+    return res;
+}
+
+} // namespace bptd

@@ -1,0 +1,427 @@
+// bvh_build.cu — LBVH construction on the GPU (sm_100a), all kernels hand-written.
+//
+// Replaces the driver-side BLAS/TLAS build of the reference (AccelerationStructure ctor,
+// bisemutum/src/graphics/accel.cpp:11-159; BLAS desc graphics_manager.cpp:616-654; instance
+// records accel.cpp:104-132). NEW algorithm, defined by DESIGN.md "LBVH" and checked bit-exactly
+// against oracle/oracle_bvh.cpp:
+//   primitive AABBs → bounds → 63-bit Morton of AABB centroids → stable LSD radix sort (8 x 8 bit)
+//   → Karras 2012 hierarchy (64-bit codes, index tie-break) → bottom-up refit (atomic arrival flags)
+//   → 64-B nodes (both child boxes in the parent) + 48-B triangle records in leaf order.
+// All passes are streaming and HBM-bound; build time is reported separately from render time.
+#include <cfloat>
+#include "bpt_internal.cuh"
+
+using namespace bptd;
+
+namespace {
+
+constexpr int kThreads = 256;
+inline unsigned grid_for(uint64_t n, int threads = kThreads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---- ordered-uint encoding of floats for atomic min/max ---------------------------------------
+__device__ __forceinline__ uint32_t f_key(float f) { uint32_t k = __float_as_uint(f); return (k & 0x80000000u) ? ~k : (k | 0x80000000u); }
+__device__ __forceinline__ float key_f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+__global__ void k_init_bounds(uint32_t* keys) {
+    if (threadIdx.x < 3) keys[threadIdx.x] = 0xffffffffu;       // min keys
+    else if (threadIdx.x < 6) keys[threadIdx.x] = 0u;           // max keys
+}
+
+// Triangle gather: object space (xf == nullptr) or world space (merged mode: o2w of one instance).
+// Writes unsorted 48-B records (v0|prim, v1|slot, v2|-) and the AABB.
+__global__ void k_gather_tris(const float* __restrict__ positions, const uint32_t* __restrict__ indices, bpt_blas_desc bd,
+                              const DInstance* __restrict__ inst, uint32_t slot, uint32_t out_base,
+                              float4* __restrict__ raw, float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= bd.num_triangles) return;
+    float3 v[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        uint32_t idx = indices[(size_t)bd.index_offset + 3ull * k + c];
+        const float* p = positions + (size_t)bd.position_offset + 3ull * idx;
+        v[c] = v3(p[0], p[1], p[2]);
+        if (inst) v[c] = xf_point(inst[slot].o2w, v[c]);
+    }
+    size_t g = (size_t)out_base + k;
+    raw[3 * g + 0] = make_float4(v[0].x, v[0].y, v[0].z, __uint_as_float(k));
+    raw[3 * g + 1] = make_float4(v[1].x, v[1].y, v[1].z, __uint_as_float(slot));
+    raw[3 * g + 2] = make_float4(v[2].x, v[2].y, v[2].z, 0.0f);
+    float3 l = vmin(vmin(v[0], v[1]), v[2]), h = vmax(vmax(v[0], v[1]), v[2]);
+    lo[g] = make_float4(l.x, l.y, l.z, 0.0f);
+    hi[g] = make_float4(h.x, h.y, h.z, 0.0f);
+}
+
+__global__ void k_reduce_bounds(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, uint32_t* keys) {
+    float3 l = v3s(FLT_MAX), h = v3s(-FLT_MAX);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = lo[i], b = hi[i];
+        l = vmin(l, v3(a.x, a.y, a.z)); h = vmax(h, v3(b.x, b.y, b.z));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l.x = fminf(l.x, __shfl_xor_sync(0xffffffffu, l.x, o)); l.y = fminf(l.y, __shfl_xor_sync(0xffffffffu, l.y, o)); l.z = fminf(l.z, __shfl_xor_sync(0xffffffffu, l.z, o));
+        h.x = fmaxf(h.x, __shfl_xor_sync(0xffffffffu, h.x, o)); h.y = fmaxf(h.y, __shfl_xor_sync(0xffffffffu, h.y, o)); h.z = fmaxf(h.z, __shfl_xor_sync(0xffffffffu, h.z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&keys[0], f_key(l.x)); atomicMin(&keys[1], f_key(l.y)); atomicMin(&keys[2], f_key(l.z));
+        atomicMax(&keys[3], f_key(h.x)); atomicMax(&keys[4], f_key(h.y)); atomicMax(&keys[5], f_key(h.z));
+    }
+}
+__global__ void k_decode_bounds(const uint32_t* keys, float* out6) {
+    if (threadIdx.x < 6) out6[threadIdx.x] = key_f(keys[threadIdx.x]);
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+__device__ __forceinline__ uint32_t quant21(float c, float lo, float hi) {
+    float ext = hi - lo;
+    float t = ext > 0.0f ? (c - lo) / ext : 0.0f;
+    float s = t * 2097152.0f;
+    s = tmax_(s, 0.0f);
+    s = tmin_(s, 2097151.0f);
+    return (uint32_t)s;
+}
+__global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, const float* __restrict__ b6,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = lo[i], b = hi[i];
+    float3 c = (v3(a.x, a.y, a.z) + v3(b.x, b.y, b.z)) * 0.5f;
+    keys[i] = (expand21(quant21(c.x, b6[0], b6[3])) << 2) | (expand21(quant21(c.y, b6[1], b6[4])) << 1) | expand21(quant21(c.z, b6[2], b6[5]));
+    vals[i] = i;
+}
+
+// ---- stable LSD radix sort, 8 bits per pass ---------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortItems; r++) {
+        uint32_t i = base + r * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];     // digit-major
+}
+// exclusive scan of `total` counters, single block
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, uint32_t total) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < total; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < total ? hist[i] : 0;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x], s = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (threadIdx.x >= o) s += y; }
+            warp_sums[threadIdx.x] = s - w;
+        }
+        __syncthreads();
+        uint32_t excl = x - v + warp_sums[threadIdx.x >> 5] + carry;
+        if (i < total) hist[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                               uint32_t n, int shift, const uint32_t* __restrict__ hist, uint32_t nblocks) {
+    __shared__ uint32_t digit_base[256];                       // global offset of this block's first key of each digit
+    __shared__ uint32_t warp_count[kSortThreads / 32][256];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    digit_base[threadIdx.x] = hist[threadIdx.x * nblocks + blockIdx.x];
+    uint32_t base = blockIdx.x * kSortTile;
+    for (int r = 0; r < kSortItems; r++) {
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; w++) warp_count[w][threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t i = base + r * kSortThreads + threadIdx.x;
+        bool valid = i < n;
+        uint64_t key = valid ? keys_in[i] : 0;
+        uint32_t d = valid ? ((uint32_t)(key >> shift) & 0xffu) : (0x100u + lane);
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) warp_count[warp][d] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            uint32_t off = digit_base[d] + rank;
+            for (uint32_t w = 0; w < warp; w++) off += warp_count[w][d];
+            keys_out[off] = key;
+            vals_out[off] = vals_in[i];
+        }
+        __syncthreads();
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; w++) tot += warp_count[w][threadIdx.x];
+        digit_base[threadIdx.x] += tot;
+        __syncthreads();
+    }
+}
+
+// ---- Karras 2012 -----------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ k, uint32_t n, int64_t i, int64_t j) {
+    if (j < 0 || j >= (int64_t)n) return -1;
+    uint64_t a = k[i], c = k[j];
+    return a != c ? __clzll((long long)(a ^ c)) : 64 + __clz((int)((uint32_t)i ^ (uint32_t)j));
+}
+__global__ void k_karras(const uint64_t* __restrict__ keys, uint32_t n, int32_t* __restrict__ child0, int32_t* __restrict__ child1,
+                         int32_t* __restrict__ node_parent, int32_t* __restrict__ leaf_parent) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n - 1) return;
+    if (i == 0) node_parent[0] = -1;
+    int d = delta(keys, n, i, i + 1) > delta(keys, n, i, i - 1) ? 1 : -1;
+    int dmin = delta(keys, n, i, i - d);
+    int64_t lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int64_t l = 0;
+    for (int64_t t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int64_t j = i + l * d;
+    int dnode = delta(keys, n, i, j);
+    int64_t s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int64_t gamma = i + s * d + (d < 0 ? d : 0);
+    int64_t lo_i = i < j ? i : j, hi_i = i < j ? j : i;
+    int32_t left = (lo_i == gamma) ? ~(int32_t)gamma : (int32_t)gamma;
+    int32_t right = (hi_i == gamma + 1) ? ~(int32_t)(gamma + 1) : (int32_t)(gamma + 1);
+    child0[i] = left; child1[i] = right;
+    if (left >= 0) node_parent[left] = (int32_t)i; else leaf_parent[~left] = (int32_t)i;
+    if (right >= 0) node_parent[right] = (int32_t)i; else leaf_parent[~right] = (int32_t)i;
+}
+
+// ---- bottom-up refit ---------------------------------------------------------------------------
+__global__ void k_refit(uint32_t n, const uint32_t* __restrict__ prims, const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                        const int32_t* __restrict__ child0, const int32_t* __restrict__ child1, const int32_t* __restrict__ node_parent,
+                        const int32_t* __restrict__ leaf_parent, float4* node_lo, float4* node_hi, uint32_t* flags, float4* __restrict__ nodes) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int32_t node = leaf_parent[j];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[node], 1u) == 0u) return;     // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        int32_t c0 = child0[node], c1 = child1[node];
+        float4 l0, h0, l1, h1;
+        if (c0 < 0) { uint32_t p = prims[~c0]; l0 = prim_lo[p]; h0 = prim_hi[p]; } else { l0 = __ldcg(&node_lo[c0]); h0 = __ldcg(&node_hi[c0]); }
+        if (c1 < 0) { uint32_t p = prims[~c1]; l1 = prim_lo[p]; h1 = prim_hi[p]; } else { l1 = __ldcg(&node_lo[c1]); h1 = __ldcg(&node_hi[c1]); }
+        float4* out = nodes + 4 * (size_t)node;
+        out[0] = make_float4(l0.x, h0.x, l0.y, h0.y);
+        out[1] = make_float4(l1.x, h1.x, l1.y, h1.y);
+        out[2] = make_float4(l0.z, h0.z, l1.z, h1.z);
+        out[3] = make_float4(__int_as_float(c0), __int_as_float(c1), __int_as_float(node_parent[node]), 0.0f);
+        float3 ul = vmin(v3(l0.x, l0.y, l0.z), v3(l1.x, l1.y, l1.z)), uh = vmax(v3(h0.x, h0.y, h0.z), v3(h1.x, h1.y, h1.z));
+        __stcg(&node_lo[node], make_float4(ul.x, ul.y, ul.z, 0.0f));
+        __stcg(&node_hi[node], make_float4(uh.x, uh.y, uh.z, 0.0f));
+        node = node_parent[node];
+    }
+}
+
+__global__ void k_emit_tris(uint32_t n, const uint32_t* __restrict__ prims, const float4* __restrict__ raw, float4* __restrict__ tris) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    size_t p = prims[j];
+    float4 a = raw[3 * p], b = raw[3 * p + 1], c = raw[3 * p + 2];
+    float3 v0 = v3(a.x, a.y, a.z);
+    float3 e1 = v3(b.x, b.y, b.z) - v0, e2 = v3(c.x, c.y, c.z) - v0;
+    tris[3 * (size_t)j + 0] = a;                                            // v0 | prim
+    tris[3 * (size_t)j + 1] = make_float4(e1.x, e1.y, e1.z, b.w);           // e1 | instance slot
+    tris[3 * (size_t)j + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+}
+
+// ---- instances ---------------------------------------------------------------------------------
+__global__ void k_make_instances(const bpt_instance_desc* __restrict__ desc, uint32_t n, DInstance* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DInstance d;
+    const float* t = &desc[i].transform[0][0];
+#pragma unroll
+    for (int k = 0; k < 12; k++) d.o2w[k] = t[k];
+    invert_3x4(d.o2w, d.w2o);
+    d.instance_id = desc[i].instance_id_and_mask & 0xffffffu;
+    d.flags = desc[i].sbt_offset_and_flags >> 24;
+    d.blas = (uint32_t)desc[i].blas;
+    for (int k = 0; k < 5; k++) d.pad[k] = 0;
+    out[i] = d;
+}
+// world AABB of an instance = min/max of the 8 transformed corners of its BLAS bounds
+// (Transform::transform_bounding_box, bisemutum/src/math/transform.cpp:59-78)
+__global__ void k_instance_bounds(const DInstance* __restrict__ inst, uint32_t n, const float* __restrict__ blas_bounds6, float4* __restrict__ lo, float4* __restrict__ hi) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* b = blas_bounds6 + 6 * (size_t)inst[i].blas;
+    float3 mn = v3s(FLT_MAX), mx = v3s(-FLT_MAX);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        float3 p = v3((c & 4) ? b[3] : b[0], (c & 2) ? b[4] : b[1], (c & 1) ? b[5] : b[2]);
+        float3 w = xf_point(inst[i].o2w, p);
+        mn = vmin(mn, w); mx = vmax(mx, w);
+    }
+    lo[i] = make_float4(mn.x, mn.y, mn.z, 0.0f);
+    hi[i] = make_float4(mx.x, mx.y, mx.z, 0.0f);
+}
+
+struct Scratch {
+    std::vector<DevBuf> bufs;
+    ~Scratch() { for (auto& b : bufs) dev_free(b); }
+    bpt_status get(bpt_context* ctx, DevBuf& out, size_t bytes) {
+        DevBuf b; bpt_status s = dev_alloc(ctx, b, bytes); if (s) return s;
+        bufs.push_back(b); out = b; return BPT_OK;
+    }
+};
+
+} // namespace
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                                   \
+    do {                                                                        \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);             \
+        (ctx)->launches++;                                                      \
+        BPT_CUDA_TRY(ctx, cudaGetLastError());                                  \
+    } while (0)
+
+bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi) {
+    out.n = n;
+    out.root = n == 1 ? ~0 : 0;
+    Scratch sc;
+    DevBuf bkeys, b6;
+    bpt_status s;
+    if ((s = sc.get(ctx, bkeys, 6 * sizeof(uint32_t)))) return s;
+    if ((s = sc.get(ctx, b6, 6 * sizeof(float)))) return s;
+    LAUNCH(ctx, k_init_bounds, 1, 32, bkeys.as<uint32_t>());
+    LAUNCH(ctx, k_reduce_bounds, std::min(grid_for(n), 1024u), kThreads, d_lo, d_hi, n, bkeys.as<uint32_t>());
+    LAUNCH(ctx, k_decode_bounds, 1, 32, bkeys.as<uint32_t>(), b6.as<float>());
+    float hb[6];
+    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(hb, b6.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
+    // sort
+    dev_free(out.morton); dev_free(out.prims); dev_free(out.nodes);
+    DevBuf keys2, vals2;
+    if ((s = dev_alloc(ctx, out.morton, (size_t)n * 8))) return s;
+    if ((s = dev_alloc(ctx, out.prims, (size_t)n * 4))) return s;
+    if ((s = sc.get(ctx, keys2, (size_t)n * 8))) return s;
+    if ((s = sc.get(ctx, vals2, (size_t)n * 4))) return s;
+    LAUNCH(ctx, k_morton, grid_for(n), kThreads, d_lo, d_hi, n, b6.as<float>(), out.morton.as<uint64_t>(), out.prims.as<uint32_t>());
+    uint32_t nblocks = (n + kSortTile - 1) / kSortTile;
+    DevBuf hist;
+    if ((s = sc.get(ctx, hist, (size_t)256 * nblocks * 4))) return s;
+    uint64_t* ka = out.morton.as<uint64_t>(); uint64_t* kb = keys2.as<uint64_t>();
+    uint32_t* va = out.prims.as<uint32_t>(); uint32_t* vb = vals2.as<uint32_t>();
+    for (int pass = 0; pass < 8; pass++) {       // 63-bit keys: all 8 bytes
+        int shift = pass * 8;
+        LAUNCH(ctx, k_sort_hist, nblocks, kSortThreads, ka, n, shift, hist.as<uint32_t>(), nblocks);
+        LAUNCH(ctx, k_sort_scan, 1, 1024, hist.as<uint32_t>(), 256u * nblocks);
+        LAUNCH(ctx, k_sort_scatter, nblocks, kSortThreads, ka, va, kb, vb, n, shift, hist.as<uint32_t>(), nblocks);
+        std::swap(ka, kb); std::swap(va, vb);
+    }   // even number of passes: result is back in out.morton / out.prims
+    if (n >= 2) {
+        if ((s = dev_alloc(ctx, out.nodes, (size_t)(n - 1) * 64))) return s;
+        DevBuf c0, c1, np, lp, nlo, nhi, flags;
+        if ((s = sc.get(ctx, c0, (size_t)(n - 1) * 4))) return s;
+        if ((s = sc.get(ctx, c1, (size_t)(n - 1) * 4))) return s;
+        if ((s = sc.get(ctx, np, (size_t)(n - 1) * 4))) return s;
+        if ((s = sc.get(ctx, lp, (size_t)n * 4))) return s;
+        if ((s = sc.get(ctx, nlo, (size_t)(n - 1) * 16))) return s;
+        if ((s = sc.get(ctx, nhi, (size_t)(n - 1) * 16))) return s;
+        if ((s = sc.get(ctx, flags, (size_t)(n - 1) * 4))) return s;
+        BPT_CUDA_TRY(ctx, cudaMemsetAsync(flags.p, 0, (size_t)(n - 1) * 4, ctx->stream));
+        LAUNCH(ctx, k_karras, grid_for(n - 1), kThreads, out.morton.as<uint64_t>(), n, c0.as<int32_t>(), c1.as<int32_t>(), np.as<int32_t>(), lp.as<int32_t>());
+        LAUNCH(ctx, k_refit, grid_for(n), kThreads, n, out.prims.as<uint32_t>(), d_lo, d_hi, c0.as<int32_t>(), c1.as<int32_t>(), np.as<int32_t>(),
+               lp.as<int32_t>(), nlo.as<float4>(), nhi.as<float4>(), flags.as<uint32_t>(), out.nodes.as<float4>());
+    }
+    BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // scratch is freed on return; bounds are read on the host
+    for (int k = 0; k < 3; k++) { out.lo[k] = hb[k]; out.hi[k] = hb[3 + k]; }
+    return BPT_OK;
+}
+
+bpt_status upload_instance_table(bpt_context* ctx) {
+    uint32_t n = (uint32_t)ctx->h_instances.size();
+    DevBuf desc;
+    bpt_status s;
+    if ((s = dev_upload(ctx, desc, ctx->h_instances.data(), (size_t)n * sizeof(bpt_instance_desc)))) return s;
+    dev_free(ctx->d_instances);
+    if ((s = dev_alloc(ctx, ctx->d_instances, (size_t)n * sizeof(DInstance)))) { dev_free(desc); return s; }
+    k_make_instances<<<grid_for(n), kThreads, 0, ctx->stream>>>(desc.as<bpt_instance_desc>(), n, ctx->d_instances.as<DInstance>());
+    ctx->launches++;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    dev_free(desc);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}
+
+static bpt_status emit_tris(bpt_context* ctx, DevBvh& b, const float4* raw) {
+    dev_free(b.tris);
+    bpt_status s;
+    if ((s = dev_alloc(ctx, b.tris, (size_t)b.n * 48))) return s;
+    LAUNCH(ctx, k_emit_tris, grid_for(b.n), kThreads, b.n, b.prims.as<uint32_t>(), raw, b.tris.as<float4>());
+    BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPT_OK;
+}
+
+bpt_status build_blas_two_level(bpt_context* ctx, uint32_t bi) {
+    const bpt_blas_desc& bd = ctx->h_blas_desc[bi];
+    uint32_t n = bd.num_triangles;
+    Scratch sc; DevBuf raw, lo, hi; bpt_status s;
+    if ((s = sc.get(ctx, raw, (size_t)n * 48))) return s;
+    if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
+    if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
+    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), bd, (const DInstance*)nullptr, 0u, 0u,
+           raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
+    if ((s = lbvh_build(ctx, ctx->blas[bi], n, lo.as<float4>(), hi.as<float4>()))) return s;
+    return emit_tris(ctx, ctx->blas[bi], raw.as<float4>());
+}
+
+bpt_status build_blas_merged(bpt_context* ctx) {
+    uint64_t total = 0;
+    for (auto& in : ctx->h_instances) total += ctx->h_blas_desc[(uint32_t)in.blas].num_triangles;
+    if (total == 0 || total > 0x7fffffffull) { ctx->err = "merged accel: triangle count out of range"; return BPT_ERR_INVALID; }
+    uint32_t n = (uint32_t)total;
+    Scratch sc; DevBuf raw, lo, hi; bpt_status s;
+    if ((s = sc.get(ctx, raw, (size_t)n * 48))) return s;
+    if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
+    if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
+    uint32_t base = 0;
+    for (uint32_t slot = 0; slot < ctx->h_instances.size(); slot++) {
+        const bpt_blas_desc& bd = ctx->h_blas_desc[(uint32_t)ctx->h_instances[slot].blas];
+        LAUNCH(ctx, k_gather_tris, grid_for(bd.num_triangles), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), bd,
+               ctx->d_instances.as<DInstance>(), slot, base, raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
+        base += bd.num_triangles;
+    }
+    if ((s = lbvh_build(ctx, ctx->blas[0], n, lo.as<float4>(), hi.as<float4>()))) return s;
+    return emit_tris(ctx, ctx->blas[0], raw.as<float4>());
+}
+
+bpt_status build_tlas(bpt_context* ctx) {
+    uint32_t n = (uint32_t)ctx->h_instances.size();
+    std::vector<float> bb(6 * ctx->blas.size());
+    for (size_t b = 0; b < ctx->blas.size(); b++)
+        for (int k = 0; k < 3; k++) { bb[6 * b + k] = ctx->blas[b].lo[k]; bb[6 * b + 3 + k] = ctx->blas[b].hi[k]; }
+    Scratch sc; DevBuf dbb, lo, hi; bpt_status s;
+    if ((s = sc.get(ctx, dbb, bb.size() * 4))) return s;
+    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(dbb.p, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
+    if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
+    LAUNCH(ctx, k_instance_bounds, grid_for(n), kThreads, ctx->d_instances.as<DInstance>(), n, dbb.as<float>(), lo.as<float4>(), hi.as<float4>());
+    return lbvh_build(ctx, ctx->tlas, n, lo.as<float4>(), hi.as<float4>());
+}

@@ -1,0 +1,311 @@
+// render.cu — the wavefront: raygen → (extend → shade → connect)^(B-1) per sample, FP32 accumulation.
+//
+// Replaces the per-frame GPU work recorded by PathTracingPass::render
+// (bisemutum/src/renderer/pass/path_tracing.cpp:290-480): the reference runs full-screen passes
+// over screen-sized textures (one texel = one path, dead paths keep their thread). Here paths live
+// in compacted queues: every kernel reads its queue length from device memory, so no host
+// synchronisation happens inside a sample, and dead paths cost nothing.
+//
+// Queue compaction: warp ballot + popc, one atomicAdd per warp. Queue ORDER is
+// therefore not deterministic, queue CONTENT is (every entry is keyed by its pixel index).
+#include <algorithm>
+#include "bpt_internal.cuh"
+#include "bpt_shade.cuh"
+
+using namespace bptd;
+
+namespace {
+
+constexpr int kBlock = 128;
+constexpr int QE = 0;      // qcount[QE + bounce]  : extend queue length of that bounce
+constexpr int QS = 32;     // qcount[QS + bounce]  : shadow queue length of that bounce
+
+struct RenderArgs {
+    DScene sc;
+    ShadeParams sp;
+    bpt_camera cam;
+    uint32_t frame_index;
+    float4 *ray_o_in, *ray_d_in, *ray_w_in;
+    float4 *ray_o_out, *ray_d_out, *ray_w_out;
+    float4* hit; uint32_t* hit_slot;
+    float4 *sh_o, *sh_d, *sh_c;
+    float4* accum;
+    uint32_t* qcount;
+    uint64_t shadow_capacity;
+};
+
+// warp-aggregated append: returns the slot for this lane (valid only if `emit`)
+__device__ __forceinline__ uint32_t queue_push(uint32_t* counter, bool emit) {
+    uint32_t active = __activemask();
+    uint32_t ballot = __ballot_sync(active, emit);
+    if (!emit) return 0;
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t leader = __ffs(ballot) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(ballot));
+    base = __shfl_sync(ballot, base, leader);
+    return base + __popc(ballot & ((1u << lane) - 1u));
+}
+
+// ---- raygen (generate_camera_ray.hlsl:4-16): one thread per pixel, weight = 1, no jitter ------
+__global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ RenderArgs a) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t npx = a.sp.width * a.sp.height;
+    if (p == 0) a.qcount[QE + 1] = npx;
+    if (p >= npx) return;
+    float3 O, D;
+    camera_ray(a.cam, p % a.sp.width, p / a.sp.width, a.sp.width, a.sp.height, O, D);
+    a.ray_o_out[p] = make_float4(O.x, O.y, O.z, __uint_as_float(p));
+    a.ray_d_out[p] = make_float4(D.x, D.y, D.z, 0.0f);
+    a.ray_w_out[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+}
+
+// ---- extend (rt_gbuffer.hlsl:7-36): closest hit of every live path -----------------------------
+__global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.qcount[QE + bounce]) return;
+    float4 o = a.ray_o_in[i], d = a.ray_d_in[i];
+    TraceResult r = trace_ray<false>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, a.sp.ray_length, a.frame_index);
+    a.hit[i] = make_float4(r.t, r.u, r.v, __uint_as_float(r.prim));
+    a.hit_slot[i] = r.slot;
+}
+
+// ---- shade: material + lighting + next direction, emits shadow rays and the next extend ray ---
+struct KernelSink {
+    const RenderArgs& a;
+    uint32_t bounce, pixel;
+    __device__ void add(float3 c) {
+        float4 v = a.accum[pixel];
+        v.x += c.x; v.y += c.y; v.z += c.z;
+        a.accum[pixel] = v;
+    }
+    __device__ void shadow(float3 P, float3 L, float tmax, float3 c, uint32_t light) {
+        if (a.sp.nee_mode == BPT_NEE_NONE) { add(c); return; }
+        uint32_t slot = queue_push(&a.qcount[QS + bounce], true);
+        if (slot < a.shadow_capacity) {
+            a.sh_o[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(pixel));
+            a.sh_d[slot] = make_float4(L.x, L.y, L.z, tmax);
+            a.sh_c[slot] = make_float4(c.x, c.y, c.z, __uint_as_float(light));
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < a.qcount[QE + bounce];
+    bool cont = false;
+    float3 nO = v3s(0.0f), nD = v3s(0.0f), nW = v3s(0.0f);
+    uint32_t pixel = 0;
+    if (live) {
+        float4 o = a.ray_o_in[i], d = a.ray_d_in[i], w = a.ray_w_in[i], h = a.hit[i];
+        pixel = __float_as_uint(o.w);
+        TraceResult r;
+        r.t = h.x; r.u = h.y; r.v = h.z; r.prim = __float_as_uint(h.w); r.slot = a.hit_slot[i]; r.hit = h.x >= 0.0f;
+        KernelSink sink{a, bounce, pixel};
+        cont = shade_vertex(a.sc, a.sp, a.frame_index, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
+    }
+    uint32_t slot = queue_push(&a.qcount[QE + bounce + 1], cont);
+    if (cont) {
+        a.ray_o_out[slot] = make_float4(nO.x, nO.y, nO.z, __uint_as_float(pixel));
+        a.ray_d_out[slot] = make_float4(nD.x, nD.y, nD.z, 0.0f);
+        a.ray_w_out[slot] = make_float4(nW.x, nW.y, nW.z, 0.0f);
+    }
+}
+
+// ---- connect: any-hit shadow rays; unoccluded contributions are added to the pixel -------------
+__global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = a.qcount[QS + bounce];
+    if (i >= n || i >= a.shadow_capacity) return;
+    float4 o = a.sh_o[i], d = a.sh_d[i];
+    TraceResult r = trace_ray<true>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, d.w, a.frame_index);
+    if (r.hit) return;
+    float4 c = a.sh_c[i];
+    float* px = reinterpret_cast<float*>(a.accum + __float_as_uint(o.w));
+    atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+}
+
+// ---- per-sample bookkeeping: queue lengths → 64-bit totals -------------------------------------
+__global__ void k_tally(const uint32_t* __restrict__ qcount, uint64_t* __restrict__ totals, uint32_t npx) {
+    uint32_t t = threadIdx.x;
+    if (t < 16) totals[t] += qcount[QE + t];
+    else if (t < 32) totals[t] += qcount[QS + (t - 16)];
+    else if (t == 32) totals[32] += npx;
+}
+
+__global__ void k_resolve(const float4* __restrict__ accum, float4* __restrict__ out, uint32_t npx, float inv) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    float4 v = accum[p];
+    out[p] = make_float4(v.x * inv, v.y * inv, v.z * inv, 1.0f);
+}
+
+// ---- arbitrary ray batches (bpt_trace_rays / bpt_trace_shadow_rays) ----------------------------
+__global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ DScene sc, const bpt_ray* __restrict__ rays, uint64_t n, uint32_t frame_index,
+                                                        bpt_hit* __restrict__ hits, uint8_t* __restrict__ visible, const DInstance* __restrict__ inst) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bpt_ray r = rays[i];
+    float3 O = v3(r.origin[0], r.origin[1], r.origin[2]), D = v3(r.direction[0], r.direction[1], r.direction[2]);
+    if (hits) {
+        TraceResult t = trace_ray<false>(sc, O, D, r.tmin, r.tmax, frame_index);
+        bpt_hit h;
+        h.t = t.t; h.u = t.u; h.v = t.v;
+        h.instance = t.hit ? inst[t.slot].instance_id : 0xffffffffu;
+        h.primitive = t.hit ? t.prim : 0xffffffffu;
+        hits[i] = h;
+    } else {
+        TraceResult t = trace_ray<true>(sc, O, D, r.tmin, r.tmax, frame_index);
+        visible[i] = t.hit ? 0 : 1;
+    }
+}
+
+} // namespace
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                                   \
+    do {                                                                        \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);             \
+        (ctx)->launches++;                                                      \
+        BPT_CUDA_TRY(ctx, cudaGetLastError());                                  \
+    } while (0)
+
+bpt_status wavefront_alloc(bpt_context* ctx) {
+    WavefrontState& wf = ctx->wf;
+    uint32_t npx = ctx->width * ctx->height;
+    bpt_status s;
+    if (wf.capacity != npx) {
+        for (int k = 0; k < 2; k++) {
+            dev_free(wf.ray_o[k]); dev_free(wf.ray_d[k]); dev_free(wf.ray_w[k]);
+            if ((s = dev_alloc(ctx, wf.ray_o[k], (size_t)npx * 16))) return s;
+            if ((s = dev_alloc(ctx, wf.ray_d[k], (size_t)npx * 16))) return s;
+            if ((s = dev_alloc(ctx, wf.ray_w[k], (size_t)npx * 16))) return s;
+        }
+        dev_free(wf.hit); dev_free(wf.hit_slot); dev_free(wf.accum);
+        if ((s = dev_alloc(ctx, wf.hit, (size_t)npx * 16))) return s;
+        if ((s = dev_alloc(ctx, wf.hit_slot, (size_t)npx * 4))) return s;
+        if ((s = dev_alloc(ctx, wf.accum, (size_t)npx * 16))) return s;
+        BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.accum.p, 0, (size_t)npx * 16, ctx->stream));
+        wf.capacity = npx;
+        wf.shadow_capacity = 0;
+    }
+    if (!wf.qcount.p) {
+        if ((s = dev_alloc(ctx, wf.qcount, 64 * sizeof(uint32_t)))) return s;
+        if ((s = dev_alloc(ctx, wf.totals, 40 * sizeof(uint64_t)))) return s;
+        BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.totals.p, 0, 40 * sizeof(uint64_t), ctx->stream));
+    }
+    uint64_t nl = (uint64_t)ctx->num_dir + ctx->num_point;
+    uint64_t need = (uint64_t)npx * std::max<uint64_t>(nl, 1);
+    if (wf.shadow_capacity < need) {
+        if (need * 48 > (64ull << 30)) { ctx->err = "shadow-ray queue would exceed 64 GiB; reduce lights or resolution"; return BPT_ERR_OOM; }
+        dev_free(wf.sh_o); dev_free(wf.sh_d); dev_free(wf.sh_c);
+        if ((s = dev_alloc(ctx, wf.sh_o, need * 16))) return s;
+        if ((s = dev_alloc(ctx, wf.sh_d, need * 16))) return s;
+        if ((s = dev_alloc(ctx, wf.sh_c, need * 16))) return s;
+        wf.shadow_capacity = need;
+    }
+    return BPT_OK;
+}
+
+static bpt_status capture_bounce(bpt_context* ctx, uint32_t bounce, int in_buf) {
+    WavefrontState& wf = ctx->wf;
+    uint32_t qc[64];
+    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(qc, wf.qcount.p, sizeof(qc), cudaMemcpyDeviceToHost, ctx->stream));
+    BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t ne = qc[QE + bounce], ns = qc[QS + bounce];
+    std::vector<float4> o(ne), h(ne); std::vector<uint32_t> slot(ne);
+    std::vector<DInstance> inst(ctx->h_instances.size());
+    BPT_CUDA_TRY(ctx, cudaMemcpy(o.data(), wf.ray_o[in_buf].p, (size_t)ne * 16, cudaMemcpyDeviceToHost));
+    BPT_CUDA_TRY(ctx, cudaMemcpy(h.data(), wf.hit.p, (size_t)ne * 16, cudaMemcpyDeviceToHost));
+    BPT_CUDA_TRY(ctx, cudaMemcpy(slot.data(), wf.hit_slot.p, (size_t)ne * 4, cudaMemcpyDeviceToHost));
+    BPT_CUDA_TRY(ctx, cudaMemcpy(inst.data(), ctx->d_instances.p, inst.size() * sizeof(DInstance), cudaMemcpyDeviceToHost));
+    auto& ep = ctx->cap_extend_pixels[bounce]; auto& eh = ctx->cap_extend_hits[bounce];
+    ep.resize(ne); eh.resize(ne);
+    for (uint32_t i = 0; i < ne; i++) {
+        uint32_t px, prim;
+        memcpy(&px, &o[i].w, 4); memcpy(&prim, &h[i].w, 4);
+        ep[i] = px;
+        bool hit = h[i].x >= 0.0f;
+        eh[i] = bpt_hit{h[i].x, h[i].y, h[i].z, hit ? inst[slot[i]].instance_id : 0xffffffffu, hit ? prim : 0xffffffffu};
+    }
+    std::vector<float4> so(ns), scv(ns);
+    BPT_CUDA_TRY(ctx, cudaMemcpy(so.data(), wf.sh_o.p, (size_t)ns * 16, cudaMemcpyDeviceToHost));
+    BPT_CUDA_TRY(ctx, cudaMemcpy(scv.data(), wf.sh_c.p, (size_t)ns * 16, cudaMemcpyDeviceToHost));
+    auto& spx = ctx->cap_shadow_pixels[bounce]; auto& sl = ctx->cap_shadow_lights[bounce];
+    spx.resize(ns); sl.resize(ns);
+    for (uint32_t i = 0; i < ns; i++) { memcpy(&spx[i], &so[i].w, 4); memcpy(&sl[i], &scv[i].w, 4); }
+    return BPT_OK;
+}
+
+bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st) {
+    bpt_status s;
+    if ((s = wavefront_alloc(ctx))) return s;
+    WavefrontState& wf = ctx->wf;
+    const uint32_t npx = ctx->width * ctx->height;
+    const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);           // path_tracing.cpp:187,290
+    RenderArgs a;
+    a.sc = ctx->scene_view();
+    a.sp.width = ctx->width; a.sp.height = ctx->height; a.sp.max_bounces = B; a.sp.nee_mode = st.nee_mode; a.sp.ray_length = st.ray_length;
+    a.cam = cam;
+    a.hit = wf.hit.as<float4>(); a.hit_slot = wf.hit_slot.as<uint32_t>();
+    a.sh_o = wf.sh_o.as<float4>(); a.sh_d = wf.sh_d.as<float4>(); a.sh_c = wf.sh_c.as<float4>();
+    a.accum = wf.accum.as<float4>(); a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
+    const unsigned grid_px = (npx + kBlock - 1) / kBlock;
+    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point, 1);
+    const bool capture = ctx->capture && nsamples == 1;
+    if (capture) {
+        ctx->cap_bounces = B;
+        ctx->cap_extend_pixels.assign(B, {}); ctx->cap_extend_hits.assign(B, {});
+        ctx->cap_shadow_pixels.assign(B, {}); ctx->cap_shadow_lights.assign(B, {});
+    }
+    for (uint32_t smp = 0; smp < nsamples; smp++) {
+        a.frame_index = frame_first + smp;
+        BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.qcount.p, 0, 64 * sizeof(uint32_t), ctx->stream));
+        int cur = 0;
+        auto bind = [&](int in, int out) {
+            a.ray_o_in = wf.ray_o[in].as<float4>(); a.ray_d_in = wf.ray_d[in].as<float4>(); a.ray_w_in = wf.ray_w[in].as<float4>();
+            a.ray_o_out = wf.ray_o[out].as<float4>(); a.ray_d_out = wf.ray_d[out].as<float4>(); a.ray_w_out = wf.ray_w[out].as<float4>();
+        };
+        bind(1, 0);
+        LAUNCH(ctx, k_raygen, grid_px, kBlock, a);
+        for (uint32_t i = 1; i < B; i++) {
+            bind(cur, cur ^ 1);
+            LAUNCH(ctx, k_extend, grid_px, kBlock, a, i);
+            LAUNCH(ctx, k_shade, grid_px, kBlock, a, i);
+            if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
+                // the shadow queue holds at most (live paths x lights) rays; the grid covers the bound
+                uint64_t bound = (uint64_t)npx * nl;
+                LAUNCH(ctx, k_connect, (unsigned)((bound + kBlock - 1) / kBlock), kBlock, a, i);
+            }
+            if (capture && (s = capture_bounce(ctx, i, cur))) return s;
+            cur ^= 1;
+        }
+        LAUNCH(ctx, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), npx);
+    }
+    return BPT_OK;
+}
+
+bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out) {
+    uint32_t npx = ctx->width * ctx->height;
+    float inv = 1.0f / (float)total_samples;
+    LAUNCH(ctx, k_resolve, (npx + 255) / 256, 256, ctx->wf.accum.as<float4>(), reinterpret_cast<float4*>(d_out), npx, inv);
+    return BPT_OK;
+}
+
+bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t n, uint32_t frame_index, bpt_hit* h_hits, uint8_t* h_visible) {
+    if (n == 0) return BPT_OK;
+    DevBuf rays, out;
+    bpt_status s;
+    if ((s = dev_upload(ctx, rays, h_rays, n * sizeof(bpt_ray)))) return s;
+    size_t out_bytes = h_hits ? n * sizeof(bpt_hit) : n;
+    if ((s = dev_alloc(ctx, out, out_bytes))) { dev_free(rays); return s; }
+    DScene sc = ctx->scene_view();
+    k_trace_batch<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(sc, rays.as<bpt_ray>(), n, frame_index,
+        h_hits ? out.as<bpt_hit>() : nullptr, h_hits ? nullptr : out.as<uint8_t>(), ctx->d_instances.as<DInstance>());
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hits ? (void*)h_hits : (void*)h_visible, out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(rays); dev_free(out);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}

@@ -1,0 +1,118 @@
+// host/c_exports.cpp — plain-C view of the host mirror for the Python harness (tests / bench).
+#include <cstring>
+#include "engine.hpp"
+
+using namespace bi;
+
+extern "C" {
+#define HOST_API __attribute__((visibility("default")))
+
+struct bpt_host_camera_desc {
+    float position[3]; float front_dir[3]; float up_dir[3];
+    float yfov; float near_z; float far_z;
+    uint32_t width; uint32_t height; uint32_t orthographic;
+};
+
+static gfx::Camera make_camera(const bpt_host_camera_desc* d) {
+    gfx::Camera c;
+    c.position = {d->position[0], d->position[1], d->position[2]};
+    c.front_dir = {d->front_dir[0], d->front_dir[1], d->front_dir[2]};
+    c.up_dir = {d->up_dir[0], d->up_dir[1], d->up_dir[2]};
+    c.yfov = d->yfov; c.near_z = d->near_z; c.far_z = d->far_z;
+    c.projection_type = d->orthographic ? gfx::ProjectionType::orthographic : gfx::ProjectionType::perspective;
+    c.set_target_extent(d->width, d->height);
+    return c;
+}
+
+HOST_API void bpt_host_camera_matrices(const bpt_host_camera_desc* d, bpt_camera* out, float view[16], float proj[16]) {
+    gfx::Camera c = make_camera(d);
+    c.update_shader_params(0);
+    std::memcpy(out->matrix_inv_view, c.matrix_inv_view().data(), 64);
+    std::memcpy(out->matrix_inv_proj, c.matrix_inv_proj().data(), 64);
+    std::memcpy(out->matrix_proj_view, c.matrix_proj_view().data(), 64);
+    if (view) std::memcpy(view, c.matrix_view().data(), 64);
+    if (proj) std::memcpy(proj, c.matrix_proj().data(), 64);
+}
+
+HOST_API void bpt_host_frustum_planes(const bpt_host_camera_desc* d, float planes[24]) {
+    gfx::Camera c = make_camera(d);
+    auto p = c.get_frustum_planes();
+    for (int i = 0; i < 6; i++) { planes[4 * i] = p[i].x; planes[4 * i + 1] = p[i].y; planes[4 * i + 2] = p[i].z; planes[4 * i + 3] = p[i].w; }
+}
+
+// The culling half of RenderGraph::add_rendered_object_list (render_graph.cpp:391-461): visibility of
+// each drawable's world AABB against the six planes. (The PT pass itself does not cull — SURVEY §0.)
+HOST_API void bpt_host_cull(const float planes[24], const float* aabb_min_max, uint32_t n, uint8_t* visible) {
+    float4 pl[6];
+    for (int i = 0; i < 6; i++) pl[i] = float4(planes[4 * i], planes[4 * i + 1], planes[4 * i + 2], planes[4 * i + 3]);
+    for (uint32_t i = 0; i < n; i++) {
+        BoundingBox b;
+        b.p_min = {aabb_min_max[6 * i], aabb_min_max[6 * i + 1], aabb_min_max[6 * i + 2]};
+        b.p_max = {aabb_min_max[6 * i + 3], aabb_min_max[6 * i + 4], aabb_min_max[6 * i + 5]};
+        visible[i] = b.test_with_planes(pl, 6) ? 1 : 0;
+    }
+}
+
+HOST_API void bpt_host_transform_aabb(const float m[12], const float in[6], float out[6]) {
+    BoundingBox b; b.p_min = {in[0], in[1], in[2]}; b.p_max = {in[3], in[4], in[5]};
+    BoundingBox r = transform_bounding_box(m, b);
+    out[0] = r.p_min.x; out[1] = r.p_min.y; out[2] = r.p_min.z; out[3] = r.p_max.x; out[4] = r.p_max.y; out[5] = r.p_max.z;
+}
+
+// LightsContext packing for the harness.
+HOST_API void bpt_host_pack_point_light(const float color[3], float strength, float range, int spot, float inner, float outer,
+                                        const float translation[3], const float rotation[9], bpt_point_light_data* out, int* emitted) {
+    LightsContext lc; PointLightComponent l; LightTransform t;
+    l.color = {color[0], color[1], color[2]}; l.strength = strength; l.range = range; l.spot = spot != 0; l.spot_inner_angle = inner; l.spot_outer_angle = outer;
+    t.translation = {translation[0], translation[1], translation[2]}; std::memcpy(t.rotation, rotation, 36);
+    lc.add(l, t);
+    *emitted = (int)lc.point_lights.size();
+    if (*emitted) *out = lc.point_lights[0];
+}
+HOST_API void bpt_host_pack_rect_light(const float color[3], float strength, float width, float height, int two_sided,
+                                       const float translation[3], const float rotation[9], bpt_rect_light_data* out, int* emitted) {
+    LightsContext lc; RectLightComponent l; LightTransform t;
+    l.color = {color[0], color[1], color[2]}; l.strength = strength; l.width = width; l.height = height; l.two_sided = two_sided != 0;
+    t.translation = {translation[0], translation[1], translation[2]}; std::memcpy(t.rotation, rotation, 36);
+    lc.add(l, t);
+    *emitted = (int)lc.rect_lights.size();
+    if (*emitted) *out = lc.rect_lights[0];
+}
+HOST_API void bpt_host_pack_dir_light(const float color[3], float strength, const float rotation[9], bpt_dir_light_data* out, int* emitted) {
+    LightsContext lc; DirectionalLightComponent l; LightTransform t;
+    l.color = {color[0], color[1], color[2]}; l.strength = strength; std::memcpy(t.rotation, rotation, 36);
+    lc.add(l, t);
+    *emitted = (int)lc.dir_lights.size();
+    if (*emitted) *out = lc.dir_lights[0];
+}
+
+// Drives N frames through PathTracingPass::{update_params, render} + RenderGraph::execute exactly as
+// BasicRenderer::render_camera would (basic.cpp:46-48,157-166): used by tests and bench e2e.
+struct bpt_host_pass { PathTracingPass* pass; gfx::Camera camera; uint64_t frame; };
+
+HOST_API bpt_host_pass* bpt_host_pass_create(bpt_context* ctx, const bpt_host_camera_desc* cam) {
+    auto* p = new bpt_host_pass{new PathTracingPass(ctx), make_camera(cam), 0};
+    return p;
+}
+HOST_API void bpt_host_pass_destroy(bpt_host_pass* p) { if (p) { delete p->pass; delete p; } }
+HOST_API void bpt_host_pass_set_camera(bpt_host_pass* p, const bpt_host_camera_desc* cam) {
+    gfx::Camera c = make_camera(cam);
+    p->camera.position = c.position; p->camera.front_dir = c.front_dir; p->camera.up_dir = c.up_dir;
+    p->camera.yfov = c.yfov; p->camera.near_z = c.near_z; p->camera.far_z = c.far_z; p->camera.projection_type = c.projection_type;
+    p->camera.set_target_extent(cam->width, cam->height);
+}
+HOST_API void bpt_host_pass_set_frame(bpt_host_pass* p, uint64_t frame) { p->frame = frame; }
+// One engine frame: camera.update_shader_params → pass.render (records) → rg.execute. Returns bpt_status.
+HOST_API int bpt_host_pass_frame(bpt_host_pass* p, float ray_length, uint32_t max_bounces, int accumulate, uint64_t* accumulated_frames) {
+    BasicRenderer::PathTracingSettings s; s.ray_length = ray_length; s.max_bounces = max_bounces; s.accumulate = accumulate != 0;
+    p->camera.update_shader_params(p->frame);
+    p->pass->set_frame_count(p->frame);
+    gfx::RenderGraph rg;
+    p->pass->render(p->camera, rg, {}, s);
+    rg.execute();
+    if (accumulated_frames) *accumulated_frames = p->pass->accumulated_frames(p->camera);
+    p->frame++;
+    return (int)p->pass->last_status();
+}
+
+} // extern "C"

@@ -1,0 +1,178 @@
+// host/engine.cpp — see engine.hpp for the reference citations of every function.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace bi {
+namespace gfx {
+
+auto Camera::update_shader_params(uint64_t frame_count) -> void {
+    frame_index_ = static_cast<uint32_t>(frame_count);                                       // camera.cpp:80
+    auto aspect = 1.0f;
+    if (width_ != 0 && height_ != 0) aspect = static_cast<float>(width_) / height_;          // camera.cpp:83-87
+    matrix_view_ = math::lookAt(position, position + front_dir, up_dir);                     // camera.cpp:96
+    if (projection_type == ProjectionType::perspective) {
+        matrix_proj_ = math::perspective_reverse_z(math::radians(yfov), aspect, near_z, far_z);
+    } else {
+        auto ortho_height = std::tan(math::radians(yfov * 0.5f));
+        auto ortho_width = ortho_height * aspect;
+        matrix_proj_ = math::ortho_reverse_z(-ortho_width, ortho_width, -ortho_height, ortho_height, near_z, far_z);
+    }
+    matrix_inv_view_ = math::inverse(matrix_view_);
+    matrix_inv_proj_ = math::inverse(matrix_proj_);
+    matrix_proj_view_ = matrix_proj_ * matrix_view_;
+}
+
+auto Camera::get_frustum_planes() const -> std::array<float4, 6> {
+    std::array<float4, 6> planes;
+    auto front = math::normalize(front_dir);
+    auto right = math::normalize(math::cross(front, up_dir));
+    auto up = math::cross(right, front);
+    auto aspect = 1.0f;
+    if (width_ != 0 && height_ != 0) aspect = static_cast<float>(width_) / height_;
+    auto xfov = yfov * aspect;                                                               // camera.cpp:138 (kept as is)
+    auto pos_dot_front = math::dot(position, front);
+    planes[0] = float4(front, -near_z - pos_dot_front);
+    planes[1] = float4(-front, pos_dot_front + far_z);
+    auto with_w = [&](float3 n) { return float4(n, -math::dot(position, n)); };
+    if (projection_type == ProjectionType::perspective) {
+        auto vert_angle = math::radians(90.0f - yfov * 0.5f);
+        planes[2] = with_w(math::rotate_direction(-vert_angle, right, front));
+        planes[3] = with_w(math::rotate_direction(vert_angle, right, front));
+        auto hori_angle = math::radians(90.0f - xfov * 0.5f);
+        planes[4] = with_w(math::rotate_direction(-hori_angle, up, front));
+        planes[5] = with_w(math::rotate_direction(hori_angle, up, front));
+    } else {
+        auto ortho_height = std::tan(math::radians(yfov * 0.5f));
+        auto ortho_width = ortho_height * aspect;
+        auto pos_dot_up = math::dot(position, up);
+        planes[2] = float4(-up, ortho_height + pos_dot_up);
+        planes[3] = float4(up, ortho_height - pos_dot_up);
+        planes[4] = float4(right, ortho_width - pos_dot_up);                                  // camera.cpp:169-170 (kept as is)
+        planes[5] = float4(-right, ortho_width + pos_dot_up);
+    }
+    return planes;
+}
+
+auto RenderGraph::add_texture(uint32_t, uint32_t, uint32_t) -> TextureHandle { return TextureHandle{next_texture_++}; }
+
+auto RenderGraph::execute() -> void {
+    ComputePassContext ctx{this};
+    for (auto& p : passes_) {
+        if (p->builder.execute_) p->builder.execute_(&p->data, ctx);
+        executed_.push_back(p->name);
+    }
+    passes_.clear();
+}
+
+} // namespace gfx
+
+auto LightsContext::add(DirectionalLightComponent const& light, LightTransform const& transform) -> void {
+    bpt_dir_light_data data{};
+    float3 emission = light.color * light.strength;
+    if (emission == float3(0.0f)) return;
+    data.emission[0] = emission.x; data.emission[1] = emission.y; data.emission[2] = emission.z;
+    float3 d = transform.transform_direction_without_scaling({0.0f, 1.0f, 0.0f});
+    data.direction[0] = d.x; data.direction[1] = d.y; data.direction[2] = d.z;
+    data.sm_index = -1;     // shadow maps are not produced: visibility is a shadow ray
+    dir_lights.push_back(data);
+}
+auto LightsContext::add(PointLightComponent const& light, LightTransform const& transform) -> void {
+    bpt_point_light_data data{};
+    float3 emission = light.color * light.strength;
+    if (emission == float3(0.0f)) return;
+    data.emission[0] = emission.x; data.emission[1] = emission.y; data.emission[2] = emission.z;
+    data.position[0] = transform.translation.x; data.position[1] = transform.translation.y; data.position[2] = transform.translation.z;
+    float3 d = transform.transform_direction_without_scaling({0.0f, 1.0f, 0.0f});
+    data.direction[0] = d.x; data.direction[1] = d.y; data.direction[2] = d.z;
+    if (light.spot) {
+        data.cos_outer = std::cos(math::radians(light.spot_outer_angle));
+        data.cos_inner = std::cos(math::radians(light.spot_inner_angle));
+    } else { data.cos_outer = 0.0f; data.cos_inner = 0.0f; }
+    data.range_sqr_inv = 1.0f / (light.range * light.range);
+    data.sm_index = -1;
+    point_lights.push_back(data);
+}
+auto LightsContext::add(RectLightComponent const& light, LightTransform const& transform) -> void {
+    bpt_rect_light_data data{};
+    float3 emission = light.color * light.strength;
+    if (emission == float3(0.0f)) return;
+    data.emission[0] = emission.x; data.emission[1] = emission.y; data.emission[2] = emission.z;
+    float3 c = transform.translation;
+    auto w = 0.5f * light.width, h = 0.5f * light.height;
+    auto put = [](float* dst, float3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; };
+    put(data.center_position, c);
+    put(data.position0, c + transform.transform_direction_without_scaling({w, h, 0.0f}));
+    put(data.position1, c + transform.transform_direction_without_scaling({-w, h, 0.0f}));
+    put(data.position2, c + transform.transform_direction_without_scaling({-w, -h, 0.0f}));
+    put(data.position3, c + transform.transform_direction_without_scaling({w, -h, 0.0f}));
+    put(data.normal, transform.transform_direction_without_scaling({0.0f, 0.0f, 1.0f}));
+    data.inv_width_sqr = 1.0f / (light.width * light.width);
+    data.inv_height_sqr = 1.0f / (light.height * light.height);
+    data.two_sided = light.two_sided;
+    data.texture_index = -1;
+    rect_lights.push_back(data);
+}
+
+auto PathTracingPass::update_params(LightsContext& lights_ctx, SkyboxContext& skybox_ctx, BasicRenderer::PathTracingSettings const&) -> void {
+    // The reference re-binds lights/sky into per-bounce parameter blocks here (path_tracing.cpp:183-222);
+    // the CUDA context keeps one copy, re-uploaded once per frame like the reference's uniform update.
+    status_ = bpt_scene_upload_lights(ctx_, lights_ctx.dir_lights.data(), (uint32_t)lights_ctx.dir_lights.size(),
+                                      lights_ctx.point_lights.data(), (uint32_t)lights_ctx.point_lights.size(),
+                                      lights_ctx.rect_lights.data(), (uint32_t)lights_ctx.rect_lights.size(), &lights_ctx.ltc_luts);
+    if (status_ != BPT_OK) return;
+    float col[3] = {skybox_ctx.color.x, skybox_ctx.color.y, skybox_ctx.color.z};
+    status_ = bpt_scene_upload_sky(ctx_, skybox_ctx.faces_rgba32f, skybox_ctx.face_size, skybox_ctx.skybox_transform, col);
+}
+
+auto PathTracingPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, InputData const&,
+                             BasicRenderer::PathTracingSettings const& settings) -> OutputData {
+    auto width = camera.target_width();
+    auto height = camera.target_height();
+    auto frame_count = frame_counter_;
+    // history validity: path_tracing.cpp:231-246
+    auto [hist_camera_it, is_new_camera] = camera_history_infos_.try_emplace(&camera);
+    auto has_history = !is_new_camera
+        && hist_camera_it->second.last_frame + 1 == frame_count
+        && hist_camera_it->second.width == width
+        && hist_camera_it->second.height == height
+        && hist_camera_it->second.proj_view == camera.matrix_proj_view();
+    hist_camera_it->second.last_frame = frame_count;
+    hist_camera_it->second.width = width;
+    hist_camera_it->second.height = height;
+    hist_camera_it->second.proj_view = camera.matrix_proj_view();
+    if (has_history && settings.accumulate) ++hist_camera_it->second.frame_count;
+    else hist_camera_it->second.frame_count = 1;
+    bool reset = hist_camera_it->second.frame_count == 1;
+
+    OutputData out;
+    out.color = rg.add_texture(width, height, 16);
+    out.depth = gfx::TextureHandle{};
+    out.velocity = gfx::TextureHandle{};
+
+    struct PassData { gfx::TextureHandle color; };
+    auto [builder, pass_data] = rg.add_compute_pass<PassData>("PT CUDA wavefront");
+    pass_data->color = builder.write(out.color);
+    builder.set_execution_function<PassData>(
+        [this, &camera, settings, reset](CRef<PassData>, gfx::ComputePassContext const&) {
+            bpt_camera cam;
+            std::memcpy(cam.matrix_inv_view, camera.matrix_inv_view().data(), 64);
+            std::memcpy(cam.matrix_inv_proj, camera.matrix_inv_proj().data(), 64);
+            std::memcpy(cam.matrix_proj_view, camera.matrix_proj_view().data(), 64);
+            bpt_settings st{};
+            st.ray_length = settings.ray_length;
+            st.max_bounces = settings.max_bounces;
+            st.accumulate = settings.accumulate;
+            if (reset) status_ = bpt_clear_accum(ctx_);
+            if (status_ == BPT_OK) status_ = bpt_render(ctx_, &cam, camera.frame_index(), 1, &st);
+        });
+    return out;
+}
+
+auto PathTracingPass::accumulated_frames(gfx::Camera const& camera) const -> uint64_t {
+    auto it = camera_history_infos_.find(&camera);
+    return it == camera_history_infos_.end() ? 0 : it->second.frame_count;
+}
+
+} // namespace bi

@@ -1,0 +1,185 @@
+// host/engine.hpp — host-side mirror of the reference interfaces that sit either side of the
+// path-tracing pass, so that `PathTracingPass` below reads like (and drops in for) the reference's
+// bisemutum/src/renderer/pass/path_tracing.{hpp,cpp}. Only what this path touches is mirrored:
+//   gfx::Camera            include/bisemutum/graphics/camera.hpp:30-75, src/graphics/camera.cpp:73-174
+//   gfx::RenderGraph       include/bisemutum/graphics/render_graph.hpp:22-123 (add_compute_pass /
+//                          builder.read/write / set_execution_function / execute) — a SHIM: passes run
+//                          in submission order, there is no resource aliasing or barrier logic because the
+//                          CUDA pass owns its device buffers (the reference's RHI exposes no CUDA interop,
+//                          include/bisemutum/graphics/resource.hpp:49-185)
+//   light components       include/bisemutum/scene_basic/light.hpp:9-95
+//   LightsContext          src/renderer/context/lights.{hpp,cpp} (collect_all_lights packing)
+//   SkyboxContext          src/renderer/context/skybox.hpp:9-35 + src/scene_basic/skybox.cpp:43-73
+//   BasicRenderer::PathTracingSettings   include/bisemutum/renderer/basic.hpp:76-81
+//   IRenderer              include/bisemutum/graphics/renderer.hpp:10-23 (as an abstract class; the
+//                          reference type-erases with AnyAny)
+#pragma once
+#include <any>
+#include <functional>
+#include <memory>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bpt/bpt.h"
+#include "math.hpp"
+
+namespace bi {
+
+template <typename T> using Ref = T*;
+template <typename T> using CRef = T const*;
+
+namespace gfx {
+
+enum class ProjectionType : uint8_t { perspective, orthographic };
+
+struct TextureHandle { uint32_t id = ~0u; bool valid() const { return id != ~0u; } };
+struct AccelerationStructureHandle { uint32_t id = ~0u; };
+
+struct Camera final {
+    auto update_shader_params(uint64_t frame_count) -> void;           // camera.cpp:73-118
+    auto matrix_proj() const -> float4x4 const& { return matrix_proj_; }
+    auto matrix_view() const -> float4x4 const& { return matrix_view_; }
+    auto matrix_proj_view() const -> float4x4 const& { return matrix_proj_view_; }
+    auto matrix_inv_view() const -> float4x4 const& { return matrix_inv_view_; }
+    auto matrix_inv_proj() const -> float4x4 const& { return matrix_inv_proj_; }
+    auto frame_index() const -> uint32_t { return frame_index_; }
+    // Order: front, back, top, down, left, right; normals point inwards (camera.cpp:126-174)
+    auto get_frustum_planes() const -> std::array<float4, 6>;
+    auto set_target_extent(uint32_t width, uint32_t height) -> void { width_ = width; height_ = height; }
+    auto target_width() const -> uint32_t { return width_; }
+    auto target_height() const -> uint32_t { return height_; }
+
+    float3 position = float3{0.0f, 0.0f, -1.0f};
+    float3 front_dir = float3{0.0f, 0.0f, 1.0f};
+    float3 up_dir = float3{0.0f, 1.0f, 0.0f};
+    float yfov = 30.0f;
+    float near_z = 0.01f;
+    float far_z = 10000.0f;
+    ProjectionType projection_type = ProjectionType::perspective;
+    bool enabled = true;
+
+private:
+    uint32_t width_ = 0, height_ = 0;
+    uint32_t frame_index_ = 0;
+    float4x4 matrix_view_{1.0f}, matrix_proj_{1.0f}, matrix_inv_view_{1.0f}, matrix_inv_proj_{1.0f}, matrix_proj_view_{1.0f};
+};
+
+struct RenderGraph;
+struct ComputePassContext final { RenderGraph* rg = nullptr; };
+
+struct ComputePassBuilder final {
+    auto read(TextureHandle h) -> TextureHandle { return h; }
+    auto write(TextureHandle h) -> TextureHandle { return h; }
+    template <typename PassData>
+    auto set_execution_function(std::function<auto(CRef<PassData>, ComputePassContext const&) -> void> func) -> void {
+        execute_ = [func = std::move(func)](std::any const* data, ComputePassContext const& ctx) { func(std::any_cast<PassData>(data), ctx); };
+    }
+    std::function<void(std::any const*, ComputePassContext const&)> execute_;
+};
+
+struct RenderGraph final {
+    auto add_texture(uint32_t width, uint32_t height, uint32_t bytes_per_texel) -> TextureHandle;
+    template <typename PassData>
+    auto add_compute_pass(std::string_view name) -> std::pair<ComputePassBuilder&, Ref<PassData>> {
+        passes_.push_back(std::make_unique<Pass>());
+        Pass& p = *passes_.back();
+        p.name = std::string(name);
+        p.data = PassData{};
+        return {p.builder, std::any_cast<PassData>(&p.data)};
+    }
+    auto execute() -> void;                                              // render_graph.cpp:567-587 (in order)
+    auto executed_pass_names() const -> std::vector<std::string> const& { return executed_; }
+
+private:
+    struct Pass { std::string name; std::any data; ComputePassBuilder builder; };
+    std::vector<std::unique_ptr<Pass>> passes_;
+    std::vector<std::string> executed_;
+    uint32_t next_texture_ = 0;
+};
+
+// IRenderer trait (include/bisemutum/graphics/renderer.hpp:10-23)
+struct IRenderer {
+    virtual ~IRenderer() = default;
+    virtual auto override_volume_component_name() const -> std::string_view = 0;
+    virtual auto prepare_renderer_per_frame_data() -> void = 0;
+    virtual auto prepare_renderer_per_camera_data(Camera const& camera) -> void = 0;
+    virtual auto render_camera(Camera const& camera, RenderGraph& rg) -> void = 0;
+};
+
+} // namespace gfx
+
+// ---- scene_basic light components (include/bisemutum/scene_basic/light.hpp) ---------------------
+struct LightTransform {                   // what collect_all_lights reads from object->world_transform()
+    float3 translation{0.0f, 0.0f, 0.0f};
+    float rotation[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};   // row-major 3x3, no scaling
+    auto transform_direction_without_scaling(float3 d) const -> float3 {
+        return {(rotation[0] * d.x + rotation[1] * d.y) + rotation[2] * d.z, (rotation[3] * d.x + rotation[4] * d.y) + rotation[5] * d.z,
+                (rotation[6] * d.x + rotation[7] * d.y) + rotation[8] * d.z};
+    }
+};
+struct DirectionalLightComponent final { float3 color = float3{1.0f}; float strength = 1.0f; bool cast_shadow = false; };
+struct PointLightComponent final {
+    float3 color = float3{1.0f}; float strength = 1.0f; float range = 30.0f;
+    bool spot = false; float spot_inner_angle = 30.0f; float spot_outer_angle = 60.0f; bool cast_shadow = false;
+};
+struct RectLightComponent final { float3 color = float3{1.0f}; float strength = 1.0f; float width = 1.0f; float height = 1.0f; bool two_sided = false; };
+
+// ---- LightsContext (src/renderer/context/lights.{hpp,cpp}) -------------------------------------
+struct LightsContext final {
+    auto clear() -> void { dir_lights.clear(); point_lights.clear(); rect_lights.clear(); }
+    auto add(DirectionalLightComponent const& light, LightTransform const& transform) -> void;   // lights.cpp:52-63
+    auto add(PointLightComponent const& light, LightTransform const& transform) -> void;         // lights.cpp:125-143
+    auto add(RectLightComponent const& light, LightTransform const& transform) -> void;          // lights.cpp:208-229
+    auto set_ltc_luts(bpt_ltc_luts const& luts) -> void { ltc_luts = luts; }
+    std::vector<bpt_dir_light_data> dir_lights;
+    std::vector<bpt_point_light_data> point_lights;
+    std::vector<bpt_rect_light_data> rect_lights;
+    bpt_ltc_luts ltc_luts{};
+};
+
+// ---- SkyboxContext + current skybox (src/renderer/context/skybox.hpp, src/scene_basic/skybox.cpp) --
+struct SkyboxContext final {
+    float skybox_transform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float3 color{1.0f, 1.0f, 1.0f};
+    float const* faces_rgba32f = nullptr;   // 6 faces, Vulkan order; nullptr = black 1x1 (skybox.cpp default)
+    uint32_t face_size = 0;
+};
+
+struct BasicRenderer {
+    struct PathTracingSettings final {     // include/bisemutum/renderer/basic.hpp:76-81
+        float ray_length = 100.0f;
+        uint32_t max_bounces = 3;
+        bool denoise = true;                // declared, never read
+        bool accumulate = true;
+    };
+};
+
+// ---- the pass ------------------------------------------------------------------------------------
+// Drop-in for bi::PathTracingPass (src/renderer/pass/path_tracing.hpp:12-69): same two methods.
+struct PathTracingPass final {
+    struct InputData final { gfx::AccelerationStructureHandle scene_accel; };
+    struct OutputData final { gfx::TextureHandle color; gfx::TextureHandle depth; gfx::TextureHandle velocity; };
+
+    explicit PathTracingPass(bpt_context* ctx) : ctx_(ctx) {}
+
+    auto update_params(LightsContext& lights_ctx, SkyboxContext& skybox_ctx, BasicRenderer::PathTracingSettings const& settings) -> void;
+    auto render(gfx::Camera const& camera, gfx::RenderGraph& rg, InputData const& input,
+                BasicRenderer::PathTracingSettings const& settings) -> OutputData;
+
+    // frames accumulated for `camera` so far (the `frame_count` of path_tracing.cpp:239-246,473)
+    auto accumulated_frames(gfx::Camera const& camera) const -> uint64_t;
+    auto last_status() const -> bpt_status { return status_; }
+
+private:
+    struct CameraHistoryInfo final { uint64_t last_frame; uint64_t frame_count; float4x4 proj_view; uint32_t width; uint32_t height; };
+    std::unordered_map<gfx::Camera const*, CameraHistoryInfo> camera_history_infos_;
+    bpt_context* ctx_;
+    bpt_status status_ = BPT_OK;
+    uint64_t frame_counter_ = 0;      // stands in for g_engine->window()->frame_count()
+public:
+    auto set_frame_count(uint64_t f) -> void { frame_counter_ = f; }
+};
+
+} // namespace bi

@@ -333,8 +333,8 @@ def atrium(seed: int = ATRIUM_SEED, target_triangles: int = ATRIUM_TRIANGLES, sk
             return p
         return grid_patch(nu, nv, fn)
     # columns: two rows of 8, shared mesh (instancing), 64 x 32 quads each
-    col = b.add_mesh(cylinder_mesh(0.45, 5.0, 64, 32, bulge=0.12))
-    col_up = b.add_mesh(cylinder_mesh(0.32, 4.0, 48, 24, bulge=0.08))
+    col = b.add_mesh(cylinder_mesh(0.45, 5.0, 48, 24, bulge=0.12))
+    col_up = b.add_mesh(cylinder_mesh(0.32, 4.0, 32, 16, bulge=0.08))
     xs = np.linspace(-LX + 2.5, LX - 2.5, 8)
     for x in xs:
         for z in (-3.6, 3.6):
@@ -349,15 +349,15 @@ def atrium(seed: int = ATRIUM_SEED, target_triangles: int = ATRIUM_TRIANGLES, sk
         cy = R * np.sin(a) * 0.6
         rr = r * (1 + 0.15 * np.cos(6 * a))
         return np.stack([cx + rr * np.cos(ang) * (-np.cos(a)), cy + rr * np.cos(ang) * np.sin(a) * 0.6, rr * np.sin(ang)], -1)
-    arch = b.add_mesh(grid_patch(48, 16, arch_fn))
+    arch = b.add_mesh(grid_patch(32, 12, arch_fn))
     for i in range(7):
         for z in (-3.6, 3.6):
             b.add_drawable(arch, mat(), translate((xs[i] + xs[i + 1]) * 0.5, 5.0, z))
     # gallery slabs on both sides (boxes) and balustrade spheres
-    slab = b.add_mesh(box_mesh((-LX, 5.25, -0.5), (LX, 5.6, 0.5), n=24))
+    slab = b.add_mesh(box_mesh((-LX, 5.25, -0.5), (LX, 5.6, 0.5), n=16))
     b.add_drawable(slab, mat(), translate(0, 0, -5.2) @ scale(1, 1, 3.4))
     b.add_drawable(slab, mat(), translate(0, 0, 5.2) @ scale(1, 1, 3.4))
-    orb = b.add_mesh(sphere_mesh(0.35, 64, 32, bumps=0.05, seed=seed & 0xffff))
+    orb = b.add_mesh(sphere_mesh(0.35, 32, 16, bumps=0.05, seed=seed & 0xffff))
     for x in xs:
         for z in (-3.6, 3.6):
             b.add_drawable(orb, mat(), translate(x, 9.95, z) @ random_rotation(rng))
@@ -373,24 +373,24 @@ def atrium(seed: int = ATRIUM_SEED, target_triangles: int = ATRIUM_TRIANGLES, sk
             sag = 0.35 * np.sin(np.pi * u)
             fold = 0.18 * np.sin(10 * np.pi * u + ph[0]) * (0.3 + v) + 0.05 * np.sin(23 * u + 9 * v + ph[1])
             return np.stack([x0 + w * u, 9.4 - sag * (1 - v) - 3.4 * v, z + fold], -1)
-        b.add_drawable(b.add_mesh(grid_patch(96, 64, drape_fn)), drape_two_sided[i % 3])
+        b.add_drawable(b.add_mesh(grid_patch(64, 48, drape_fn)), drape_two_sided[i % 3])
     # vases / planters on the floor: displaced spheres, per-instance rotation + scale
-    vase = b.add_mesh(sphere_mesh(0.6, 96, 48, bumps=0.12, seed=(seed >> 8) & 0xffff))
+    vase = b.add_mesh(sphere_mesh(0.6, 64, 32, bumps=0.12, seed=(seed >> 8) & 0xffff))
     for i in range(10):
         x = rng.uniform(-LX + 2, LX - 2)
         z = rng.choice([-1.0, 1.0]) * rng.uniform(0.5, 2.6)
         s = rng.uniform(0.6, 1.3)
         b.add_drawable(vase, mat(), translate(x, 0.6 * s, z) @ rotate_y(rng.uniform(0, 6.28)) @ scale(s))
     # shell: walls, end walls, ceiling ring with a central opening (the sky + sun come through it)
-    b.add_drawable(b.add_mesh(quad((-LX, 0, -LZ), (0, LY, 0), (2 * LX, 0, 0), 48, 144, bump=0.03)), mat())   # -z wall (+z normal)
-    b.add_drawable(b.add_mesh(quad((-LX, 0, LZ), (2 * LX, 0, 0), (0, LY, 0), 144, 48, bump=0.03)), mat())    # +z wall (-z normal)
-    b.add_drawable(b.add_mesh(quad((-LX, 0, -LZ), (0, 0, 2 * LZ), (0, LY, 0), 56, 48, bump=0.02)), mat())    # -x end  (+x normal)
-    b.add_drawable(b.add_mesh(quad((LX, 0, -LZ), (0, LY, 0), (0, 0, 2 * LZ), 48, 56, bump=0.02)), mat())     # +x end  (-x normal)
+    b.add_drawable(b.add_mesh(quad((-LX, 0, -LZ), (0, LY, 0), (2 * LX, 0, 0), 32, 96, bump=0.03)), mat())   # -z wall (+z normal)
+    b.add_drawable(b.add_mesh(quad((-LX, 0, LZ), (2 * LX, 0, 0), (0, LY, 0), 96, 32, bump=0.03)), mat())    # +z wall (-z normal)
+    b.add_drawable(b.add_mesh(quad((-LX, 0, -LZ), (0, 0, 2 * LZ), (0, LY, 0), 32, 32, bump=0.02)), mat())    # -x end  (+x normal)
+    b.add_drawable(b.add_mesh(quad((LX, 0, -LZ), (0, LY, 0), (0, 0, 2 * LZ), 32, 32, bump=0.02)), mat())     # +x end  (-x normal)
     ox, oz = 11.0, 2.6    # half extents of the roof opening
-    b.add_drawable(b.add_mesh(quad((-LX, LY, -LZ), (2 * LX, 0, 0), (0, 0, LZ - oz), 96, 16)), mat())         # ceiling strips (-y normal)
-    b.add_drawable(b.add_mesh(quad((-LX, LY, oz), (2 * LX, 0, 0), (0, 0, LZ - oz), 96, 16)), mat())
-    b.add_drawable(b.add_mesh(quad((-LX, LY, -oz), (LX - ox, 0, 0), (0, 0, 2 * oz), 24, 16)), mat())
-    b.add_drawable(b.add_mesh(quad((ox, LY, -oz), (LX - ox, 0, 0), (0, 0, 2 * oz), 24, 16)), mat())
+    b.add_drawable(b.add_mesh(quad((-LX, LY, -LZ), (2 * LX, 0, 0), (0, 0, LZ - oz), 64, 12)), mat())         # ceiling strips (-y normal)
+    b.add_drawable(b.add_mesh(quad((-LX, LY, oz), (2 * LX, 0, 0), (0, 0, LZ - oz), 64, 12)), mat())
+    b.add_drawable(b.add_mesh(quad((-LX, LY, -oz), (LX - ox, 0, 0), (0, 0, 2 * oz), 16, 12)), mat())
+    b.add_drawable(b.add_mesh(quad((ox, LY, -oz), (LX - ox, 0, 0), (0, 0, 2 * oz), 16, 12)), mat())
     # floor last: its tessellation absorbs the remainder so the scene has exactly `target_triangles`
     used = sum(b.meshes[m][2] for (m, _, _) in b.drawables)
     remaining = target_triangles - used

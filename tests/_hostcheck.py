@@ -1,0 +1,109 @@
+"""Test-only: host build of the CUDA device functions (tests/hostcheck/hostcheck.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from bisemutum_engine_b200 import capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostcheck", "hostcheck.cpp")
+OUT = os.path.join(HERE, "hostcheck", "_build_hostcheck.so")
+CSRC = os.path.join(os.path.dirname(HERE), "bisemutum-engine_b200", "csrc")
+
+
+class HcBvh(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("root", C.c_int32), ("nodes", C.c_void_p), ("prims", C.c_void_p)]
+
+
+class HcScene(C.Structure):
+    _fields_ = [("positions", C.c_void_p), ("normals", C.c_void_p), ("tangents", C.c_void_p), ("texcoords", C.c_void_p),
+                ("indices", C.c_void_p),
+                ("drawables", C.c_void_p), ("drawable_va", C.c_void_p), ("num_drawables", C.c_uint32),
+                ("blas_desc", C.c_void_p), ("num_blas", C.c_uint32),
+                ("instances", C.c_void_p), ("num_instances", C.c_uint32),
+                ("materials", C.c_void_p), ("num_materials", C.c_uint32),
+                ("dir", C.c_void_p), ("num_dir", C.c_uint32),
+                ("point", C.c_void_p), ("num_point", C.c_uint32),
+                ("rect", C.c_void_p), ("num_rect", C.c_uint32),
+                ("ltc_m0", C.c_void_p), ("ltc_m1", C.c_void_p), ("ltc_m2", C.c_void_p), ("ltc_norm", C.c_void_p),
+                ("sky_faces", C.c_void_p), ("sky_size", C.c_uint32), ("sky_transform", C.c_float * 9), ("sky_color", C.c_float * 3),
+                ("accel_mode", C.c_uint32),
+                ("blas_bvh", C.POINTER(HcBvh)), ("tlas", HcBvh)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+        if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-mavx2",
+                            "-fvisibility=hidden", "-I/usr/local/cuda/include", "-o", OUT, SRC], check=True)
+        _lib = C.CDLL(OUT)
+        _lib.hc_rng_tea.argtypes, _lib.hc_rng_tea.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+        _lib.hc_sincos_2pi.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        _lib.hc_atan2.argtypes, _lib.hc_atan2.restype = [C.c_float, C.c_float], C.c_float
+        _lib.hc_acos.argtypes, _lib.hc_acos.restype = [C.c_float], C.c_float
+        _lib.hc_ggx_vndf_sample.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        _lib.hc_surface_eval_lit.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p]
+        _lib.hc_render.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                   C.POINTER(capi.Settings), C.c_void_p]
+        _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None or a.size == 0 else a.ctypes.data_as(C.c_void_p)
+
+
+class HostScene:
+    """hc_scene built from a SceneData and the BVH arrays read back from an oracle context."""
+
+    def __init__(self, scene, oracle_ctx, accel_mode):
+        self.keep = []
+        h = HcScene()
+        h.positions, h.normals, h.tangents, h.texcoords = _p(scene.positions), _p(scene.normals), _p(scene.tangents), _p(scene.texcoords)
+        h.indices = _p(scene.indices)
+        h.drawables, h.drawable_va, h.num_drawables = _p(scene.drawables), _p(scene.drawable_va), len(scene.drawables)
+        h.blas_desc, h.num_blas = _p(scene.blas), len(scene.blas)
+        h.instances, h.num_instances = _p(scene.instances), len(scene.instances)
+        h.materials, h.num_materials = _p(scene.materials), len(scene.materials)
+        h.dir, h.num_dir = _p(scene.dir_lights), len(scene.dir_lights)
+        h.point, h.num_point = _p(scene.point_lights), len(scene.point_lights)
+        h.rect, h.num_rect = _p(scene.rect_lights), len(scene.rect_lights)
+        if scene.ltc_luts is not None:
+            h.ltc_m0, h.ltc_m1, h.ltc_m2, h.ltc_norm = (_p(a) for a in scene.ltc_luts)
+        if scene.sky_faces is not None:
+            h.sky_faces, h.sky_size = _p(scene.sky_faces), scene.sky_faces.shape[1]
+        h.sky_transform[:] = list(np.asarray(scene.sky_transform, np.float32))
+        h.sky_color[:] = list(np.asarray(scene.sky_color, np.float32))
+        h.accel_mode = accel_mode
+        nb = len(scene.blas) if accel_mode == capi.ACCEL_TWO_LEVEL else 1
+        arr = (HcBvh * nb)()
+        for b in range(nb):
+            bv = oracle_ctx.read_bvh(b)
+            self.keep.append(bv)
+            arr[b] = HcBvh(bv["n"], bv["root"], _p(bv["nodes"]), _p(bv["prims"]))
+        h.blas_bvh = arr
+        if accel_mode == capi.ACCEL_TWO_LEVEL:
+            tv = oracle_ctx.read_bvh(capi.BVH_TLAS)
+            self.keep.append(tv)
+            h.tlas = HcBvh(tv["n"], tv["root"], _p(tv["nodes"]), _p(tv["prims"]))
+        self.keep.append(arr)
+        self.scene = scene
+        self.h = h
+
+    def render(self, camera, width, height, frame_first, nsamples, settings):
+        accum = np.zeros((height, width, 4), np.float32)
+        lib().hc_render(C.byref(self.h), C.byref(camera), width, height, frame_first, nsamples, C.byref(settings), accum.ctypes.data_as(C.c_void_p))
+        return accum
+
+    def trace(self, rays, frame_index=0):
+        hits = np.zeros(len(rays), capi.HIT)
+        vis = np.zeros(len(rays), np.uint8)
+        lib().hc_trace(C.byref(self.h), rays.ctypes.data_as(C.c_void_p), len(rays), frame_index, hits.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p))
+        return hits, vis

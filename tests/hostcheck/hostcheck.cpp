@@ -1,0 +1,175 @@
+// tests/hostcheck/hostcheck.cpp — TEST HARNESS ONLY, never shipped, never linked into libbpt.so.
+//
+// Compiles the kernels' per-thread device functions (bpt_math/scene/trace/shade .cuh, all
+// BPT_HD) for the HOST with g++ -ffp-contract=off so that `pytest -m "not gpu"` can compare the
+// CUDA source's arithmetic against the oracle without a GPU: an expression-order mismatch shows
+// up here in seconds instead of after a GPU round trip. The BVH is NOT built here (the build is
+// __global__ kernels); the harness is handed the oracle's BVH arrays, which the GPU build must
+// match bit-exactly anyway (tests/test_gpu_parity.py checks that on the device).
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+#include "../../bisemutum-engine_b200/csrc/bpt_shade.cuh"
+
+using namespace bptd;
+
+struct hc_bvh {
+    uint32_t n; int32_t root;
+    const bpt_bvh_node* nodes;     // n-1
+    const uint32_t* prims;         // n sorted primitive ids
+};
+struct hc_scene {
+    const float *positions, *normals, *tangents, *texcoords;
+    const uint32_t* indices;
+    const bpt_drawable_sbt_data* drawables; const uint32_t* drawable_va; uint32_t num_drawables;
+    const bpt_blas_desc* blas_desc; uint32_t num_blas;
+    const bpt_instance_desc* instances; uint32_t num_instances;
+    const bpt_material* materials; uint32_t num_materials;
+    const bpt_dir_light_data* dir; uint32_t num_dir;
+    const bpt_point_light_data* point; uint32_t num_point;
+    const bpt_rect_light_data* rect; uint32_t num_rect;
+    const float *ltc_m0, *ltc_m1, *ltc_m2, *ltc_norm;
+    const float* sky_faces; uint32_t sky_size; float sky_transform[9]; float sky_color[3];
+    uint32_t accel_mode;
+    const hc_bvh* blas_bvh;        // num_blas entries (two-level) or 1 (merged)
+    hc_bvh tlas;
+};
+
+namespace {
+struct Built {
+    std::vector<DInstance> inst;
+    std::vector<std::vector<float4>> tris;
+    std::vector<DBlas> blas;
+    DScene sc{};
+};
+
+float4 f4(float x, float y, float z, uint32_t w) { return make_float4(x, y, z, u2f(w)); }
+
+void build(const hc_scene& h, Built& b) {
+    b.inst.resize(h.num_instances);
+    for (uint32_t i = 0; i < h.num_instances; i++) {
+        DInstance& d = b.inst[i];
+        memcpy(d.o2w, h.instances[i].transform, 48);
+        invert_3x4(d.o2w, d.w2o);
+        d.instance_id = h.instances[i].instance_id_and_mask & 0xffffffu;
+        d.flags = h.instances[i].sbt_offset_and_flags >> 24;
+        d.blas = (uint32_t)h.instances[i].blas;
+    }
+    auto vert = [&](const bpt_blas_desc& bd, uint32_t k, int c) {
+        uint32_t idx = h.indices[(size_t)bd.index_offset + 3ull * k + c];
+        const float* p = h.positions + (size_t)bd.position_offset + 3ull * idx;
+        return v3(p[0], p[1], p[2]);
+    };
+    uint32_t nb = h.accel_mode == BPT_ACCEL_TWO_LEVEL ? h.num_blas : 1;
+    b.tris.resize(nb); b.blas.resize(nb);
+    if (h.accel_mode == BPT_ACCEL_TWO_LEVEL) {
+        for (uint32_t bi = 0; bi < nb; bi++) {
+            const hc_bvh& hb = h.blas_bvh[bi];
+            b.tris[bi].resize(3ull * hb.n);
+            for (uint32_t j = 0; j < hb.n; j++) {
+                uint32_t k = hb.prims[j];
+                float3 v0 = vert(h.blas_desc[bi], k, 0), v1 = vert(h.blas_desc[bi], k, 1), v2 = vert(h.blas_desc[bi], k, 2);
+                float3 e1 = v1 - v0, e2 = v2 - v0;
+                b.tris[bi][3 * j] = f4(v0.x, v0.y, v0.z, k); b.tris[bi][3 * j + 1] = f4(e1.x, e1.y, e1.z, 0); b.tris[bi][3 * j + 2] = f4(e2.x, e2.y, e2.z, 0);
+            }
+        }
+    } else {
+        const hc_bvh& hb = h.blas_bvh[0];
+        std::vector<uint32_t> slot_of(hb.n), prim_of(hb.n);
+        uint32_t g = 0;
+        for (uint32_t s = 0; s < h.num_instances; s++)
+            for (uint32_t k = 0; k < h.blas_desc[b.inst[s].blas].num_triangles; k++, g++) { slot_of[g] = s; prim_of[g] = k; }
+        b.tris[0].resize(3ull * hb.n);
+        for (uint32_t j = 0; j < hb.n; j++) {
+            uint32_t p = hb.prims[j], s = slot_of[p], k = prim_of[p];
+            const bpt_blas_desc& bd = h.blas_desc[b.inst[s].blas];
+            float3 v0 = xf_point(b.inst[s].o2w, vert(bd, k, 0)), v1 = xf_point(b.inst[s].o2w, vert(bd, k, 1)), v2 = xf_point(b.inst[s].o2w, vert(bd, k, 2));
+            float3 e1 = v1 - v0, e2 = v2 - v0;
+            b.tris[0][3 * j] = f4(v0.x, v0.y, v0.z, k); b.tris[0][3 * j + 1] = f4(e1.x, e1.y, e1.z, s); b.tris[0][3 * j + 2] = f4(e2.x, e2.y, e2.z, 0);
+        }
+    }
+    for (uint32_t bi = 0; bi < nb; bi++)
+        b.blas[bi] = DBlas{reinterpret_cast<const float4*>(h.blas_bvh[bi].nodes), b.tris[bi].data(), h.blas_bvh[bi].root, h.blas_bvh[bi].n};
+    DScene& s = b.sc;
+    s.positions = h.positions; s.normals = h.normals; s.tangents = h.tangents; s.texcoords = h.texcoords; s.indices = h.indices;
+    s.drawables = h.drawables; s.drawable_va = h.drawable_va; s.materials = h.materials; s.textures = nullptr; s.num_textures = 0;
+    s.instances = b.inst.data(); s.num_instances = h.num_instances;
+    s.accel_mode = h.accel_mode;
+    s.tlas_nodes = reinterpret_cast<const float4*>(h.tlas.nodes); s.tlas_prims = h.tlas.prims; s.tlas_root = h.tlas.root; s.tlas_n = h.tlas.n;
+    s.blas = b.blas.data();
+    s.dir_lights = h.dir; s.num_dir = h.num_dir; s.point_lights = h.point; s.num_point = h.num_point; s.rect_lights = h.rect; s.num_rect = h.num_rect;
+    s.ltc_m0 = h.ltc_m0; s.ltc_m1 = h.ltc_m1; s.ltc_m2 = h.ltc_m2; s.ltc_norm = h.ltc_norm;
+    s.sky_faces = reinterpret_cast<const float4*>(h.sky_faces); s.sky_size = h.sky_size;
+    memcpy(s.sky_transform, h.sky_transform, 36); memcpy(s.sky_color, h.sky_color, 12);
+}
+
+struct HostSink {
+    const DScene& sc; uint32_t nee_mode; uint32_t frame_index; float* px;
+    std::vector<float3> pending;
+    void add(float3 c) { px[0] += c.x; px[1] += c.y; px[2] += c.z; }
+    void shadow(float3 P, float3 L, float tmax, float3 c, uint32_t) {
+        if (nee_mode == BPT_NEE_NONE) { add(c); return; }
+        // the connect kernel runs after the shade kernel: its contributions land after the immediate ones
+        TraceResult r = trace_ray<true>(sc, P, L, 0.001f, tmax, frame_index);
+        if (!r.hit) pending.push_back(c);
+    }
+};
+} // namespace
+
+extern "C" {
+
+// Runs the wavefront logic (raygen → extend → shade → connect) for every pixel, one path at a time.
+__attribute__((visibility("default")))
+int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t height, uint32_t frame_first, uint32_t nsamples,
+              const bpt_settings* st, float* accum_rgba) {
+    Built b; build(*h, b);
+    ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = std::min(std::max(st->max_bounces, 2u), 16u); sp.nee_mode = st->nee_mode; sp.ray_length = st->ray_length;
+    for (uint32_t s = 0; s < nsamples; s++)
+        for (uint32_t p = 0; p < width * height; p++) {
+            float3 O, D, W = v3s(1.0f);
+            camera_ray(*cam, p % width, p / width, width, height, O, D);
+            for (uint32_t i = 1; i < sp.max_bounces; i++) {
+                TraceResult r = trace_ray<false>(b.sc, O, D, 0.001f, sp.ray_length, frame_first + s);
+                HostSink sink{b.sc, st->nee_mode, frame_first + s, accum_rgba + 4ull * p, {}};
+                float3 nO, nD, nW;
+                bool cont = shade_vertex(b.sc, sp, frame_first + s, i, p, O, D, W, r, sink, nO, nD, nW);
+                for (auto& c : sink.pending) sink.add(c);
+                if (!cont) break;
+                O = nO; D = nD; W = nW;
+            }
+        }
+    return 0;
+}
+
+__attribute__((visibility("default")))
+int hc_trace(const hc_scene* h, const bpt_ray* rays, uint64_t n, uint32_t frame_index, bpt_hit* hits, uint8_t* visible) {
+    Built b; build(*h, b);
+    for (uint64_t i = 0; i < n; i++) {
+        float3 O = v3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), D = v3(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
+        if (hits) {
+            TraceResult t = trace_ray<false>(b.sc, O, D, rays[i].tmin, rays[i].tmax, frame_index);
+            hits[i] = bpt_hit{t.t, t.u, t.v, t.hit ? b.inst[t.slot].instance_id : 0xffffffffu, t.hit ? t.prim : 0xffffffffu};
+        }
+        if (visible) visible[i] = trace_ray<true>(b.sc, O, D, rays[i].tmin, rays[i].tmax, frame_index).hit ? 0 : 1;
+    }
+    return 0;
+}
+
+__attribute__((visibility("default"))) uint32_t hc_rng_tea(uint32_t a, uint32_t b) { return rng_tea(a, b); }
+__attribute__((visibility("default"))) void hc_sincos_2pi(float u, float* s, float* c) { sincos_2pi(u, *s, *c); }
+__attribute__((visibility("default"))) float hc_atan2(float y, float x) { return atan2_(y, x); }
+__attribute__((visibility("default"))) float hc_acos(float x) { return acos_(x); }
+__attribute__((visibility("default"))) void hc_ggx_vndf_sample(const float v[3], float rx, float ry, float u1, float u2, float o[3]) {
+    float3 h = ggx_vndf_sample(v3(v[0], v[1], v[2]), rx, ry, u1, u2); o[0] = h.x; o[1] = h.y; o[2] = h.z;
+}
+__attribute__((visibility("default"))) void hc_surface_eval_lit(const float N[3], const float T[3], const float V[3], const float L[3], const float base[3],
+                                                                 const float f0[3], const float f90[3], float roughness, float anisotropy, float out[3]) {
+    Surface s = surface_default();
+    s.base_color = v3(base[0], base[1], base[2]); s.f0_color = v3(f0[0], f0[1], f0[2]); s.f90_color = v3(f90[0], f90[1], f90[2]);
+    s.roughness = roughness; s.anisotropy = anisotropy;
+    float3 n = v3(N[0], N[1], N[2]), t = v3(T[0], T[1], T[2]);
+    float3 r = bsdf_eval(n, t, cross3(n, t), v3(V[0], V[1], V[2]), v3(L[0], L[1], L[2]), s, 1u);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+
+} // extern "C"
