@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric (Mrays/s, plus Mpix·spp/s) on BASELINE configs[1]:
+procedural Sponza-scale atrium, 262 144 triangles, 25 PBR materials, 1920x1080, max_bounces 8,
+directional light + sky.
+
+A "step" is one reference frame = one sample per pixel over the whole image (the reference renders
+1 spp per frame and accumulates, path_tracing.cpp:231-246,463-480); 256 steps = the 256-spp config.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU)
+  python bench.py --impl reference ...                     the CPU oracle port of the reference path
+
+Contract keys: value (device-resident whole-job throughput), e2e (through the public pass API with
+host buffers), roofline (dominant kernel vs measured HBM peak), cpu_baseline, clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT, BOUNCES, RAY_LENGTH = 1920, 1080, 8, 100.0
+WORKLOAD = "atrium_262144tri_25mat_1920x1080_depth8_dirlight_sky"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--bounces", type=int, default=BOUNCES)
+    ap.add_argument("--accel", default="merged", choices=["merged", "two_level"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-tile-stride", type=int, default=0, help="oracle sample: every n-th 16x16 tile (0 = auto)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_sample(scene, accel_mode, width, height, bounces, tile_stride, frames, threads=0):
+    """Times the CPU oracle (the port of the reference's path) on a bounded, spatially uniform sample of
+    the same workload. Returns (rays/s, stats, description, cores)."""
+    from bisemutum_engine_b200 import capi
+    from oracle import oracle_py
+    ctx = oracle_py.OracleContext(width, height, threads)
+    ctx.upload_scene(scene, accel_mode)
+    cam = oracle_py.camera_matrices(scene.camera, width, height)
+    st = capi.Settings(ray_length=RAY_LENGTH, max_bounces=bounces)
+    ctx.set_tile_sample(tile_stride, 0)
+    ctx.render(cam, 1000, 1, st)          # warm-up (page in, spawn threads)
+    ctx.reset_counters()
+    t0 = time.perf_counter()
+    ctx.render(cam, 0, frames, st)
+    dt = time.perf_counter() - t0
+    c, s = ctx.counters(), ctx.stats()
+    rays = c.extend_rays + c.shadow_rays
+    desc = f"every {tile_stride}th 16x16 tile of the {width}x{height} frame, {frames} spp, depth {bounces} ({c.samples} pixel-samples, {rays} rays)"
+    out = dict(rays_per_s=rays / dt, seconds=dt, rays=rays, pixel_samples=c.samples, cores=ctx.threads, desc=desc,
+               ext_nodes=s.extend_nodes / max(1, s.extend_rays), ext_tris=s.extend_tris / max(1, s.extend_rays),
+               shd_nodes=s.shadow_nodes / max(1, s.shadow_rays), shd_tris=s.shadow_tris / max(1, s.shadow_rays),
+               ext_inst=s.extend_instances / max(1, s.extend_rays))
+    ctx.close()
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path cannot be built here
+    (HLSL + Vulkan RT), so the arm times the oracle port with all host threads."""
+    if rank != 0:
+        return
+    from bisemutum_engine_b200 import capi, scenes
+    scene = scenes.atrium()
+    mode = capi.ACCEL_MERGED if args.accel == "merged" else capi.ACCEL_TWO_LEVEL
+    stride = args.cpu_tile_stride or 16
+    from oracle import oracle_py
+    ctx = oracle_py.OracleContext(args.width, args.height)
+    ctx.upload_scene(scene, mode)
+    cam = oracle_py.camera_matrices(scene.camera, args.width, args.height)
+    st = capi.Settings(ray_length=RAY_LENGTH, max_bounces=args.bounces)
+    ctx.set_tile_sample(stride, 0)
+    for w in range(args.warmup):
+        ctx.render(cam, 100000 + w, 1, st)
+    ctx.reset_counters()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ctx.render(cam, k, 1, st)
+    dt = time.perf_counter() - t0
+    c = ctx.counters()
+    rays = c.extend_rays + c.shadow_rays
+    value = rays / dt / 1e6
+    sample = f"each step = 1 spp over every {stride}th 16x16 tile of the {args.width}x{args.height} frame ({c.samples // max(1, args.steps)} pixel-samples/step)"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "accel": args.accel, "note": "CPU oracle port of the reference path; reference itself is not buildable (HLSL/DXC + Vulkan RT + window)"},
+        "mpix_spp_per_s": c.samples / dt / 1e6,
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": ctx.threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import bisemutum_engine_b200 as pkg
+    from bisemutum_engine_b200 import capi, engine, scenes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, H, B = args.width, args.height, args.bounces
+    mode = capi.ACCEL_MERGED if args.accel == "merged" else capi.ACCEL_TWO_LEVEL
+    scene = scenes.atrium()
+    lib = pkg.load_library()
+
+    # ---------------- device-resident arm: value -------------------------------------------------
+    ctx = capi.Context(lib, W, H, device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    ctx.upload_scene(scene, mode)
+    ctx.sync()
+    build_ms = (time.perf_counter() - t0) * 1e3
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(ray_length=RAY_LENGTH, max_bounces=B)
+    reduce_buf = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # sample s of the job ↔ frame_index = s; rank r renders s ≡ r (mod world)  
+    for w in range(args.warmup):
+        ctx.render(cam, 1_000_000 + w * world + rank, 1, st)
+    ctx.sync()
+    ctx.clear_accum()
+    ctx.reset_counters()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for k in range(args.steps):
+        ctx.render(cam, k * world + rank, 1, st)
+    if world > 1:   # the one exchange step: FP32 sum buffers → rank 0 (one NCCL reduce per batch of frames)
+        ctx.resolve_device(1, reduce_buf.data_ptr())
+        dist.reduce(reduce_buf, dst=0, op=dist.ReduceOp.SUM)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    c = ctx.counters()
+    launches = c.kernel_launches
+    stats = torch.tensor([ms, float(c.extend_rays), float(c.shadow_rays), float(c.samples)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms = float(mx[0]); ext, shd, samples = float(sm[1]), float(sm[2]), float(sm[3])
+    else:
+        ext, shd, samples = float(c.extend_rays), float(c.shadow_rays), float(c.samples)
+    value = (ext + shd) / (ms * 1e-3) / 1e6
+    mpix = samples / (ms * 1e-3) / 1e6
+
+    # ---------------- per-kernel timing of the dominant kernel (CUDA events inside libbpt) --------
+    prof_steps = min(8, max(1, args.steps))
+    ctx.profile_enable(True)
+    ctx.reset_counters()
+    for k in range(prof_steps):
+        ctx.render(cam, k * world + rank, 1, st)
+    kt = ctx.profile_read()
+    ctx.profile_enable(False)
+    pc = ctx.counters()
+
+    # ---------------- e2e arm: through PathTracingPass with host buffers ---------------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        r = engine.Renderer(W, H, device=local_rank)
+        r.ctx.set_stream(stream.cuda_stream)
+        r.set_scene(scene, mode)
+        host_img = torch.empty(H, W, 4, dtype=torch.float32).pin_memory()
+        dev_img = torch.empty(H, W, 4, dtype=torch.float32, device="cuda")
+        lights_bytes = scene.dir_lights.nbytes + scene.point_lights.nbytes + scene.rect_lights.nbytes
+        h2d = lights_bytes + 3 * 64 + 32            # lights (update_params) + camera matrices + settings
+        d2h = W * H * 16
+        e2e_steps = max(4, min(args.steps, 32))
+        for i in range(3):
+            r.ctx.upload_lights(scene); r.frame(RAY_LENGTH, B, True)
+        r.ctx.sync(); r.ctx.reset_counters()
+        barrier()
+        t0 = time.perf_counter()
+        n = 0
+        for i in range(e2e_steps):
+            r.ctx.upload_lights(scene)                      # PathTracingPass::update_params: per-frame H2D of the light arrays
+            n = r.frame(RAY_LENGTH, B, True)                # Camera::update_shader_params + PathTracingPass::render + RenderGraph::execute
+            r.ctx.resolve_device(n, dev_img.data_ptr())     # the frame's result ...
+            host_img.copy_(dev_img, non_blocking=True)      # ... read back to pinned host memory
+            stream.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        ec = r.ctx.counters()
+        erays = torch.tensor([float(ec.extend_rays + ec.shadow_rays), dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tot = erays.clone(); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            mxx = erays.clone(); dist.all_reduce(mxx, op=dist.ReduceOp.MAX)
+            e_rays, e_dt = float(tot[0]), float(mxx[1])
+        else:
+            e_rays, e_dt = float(erays[0]), dt
+        e2e = {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "ms_per_step": e_dt / e2e_steps * 1e3}
+        r.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline + algorithmic bytes (oracle counters on the bit-identical BVH) --
+    cpu = None
+    peak, peak_src = peaks()
+    roofline = None
+    ora = None
+    if not args.no_cpu_baseline:
+        stride = args.cpu_tile_stride or 8
+        ora = oracle_sample(scene, mode, W, H, B, stride, 1)
+        if ora["seconds"] < 5.0:        # aim for ~10-30 s of CPU work
+            frames = int(min(64, max(2, 12.0 / max(ora["seconds"], 1e-3))))
+            ora = oracle_sample(scene, mode, W, H, B, stride, frames)
+        cpu = {"value": ora["rays_per_s"] / 1e6, "unit": "Mrays/s", "cores": ora["cores"], "kind": "port",
+               "sample": ora["desc"], "seconds": ora["seconds"]}
+    if kt.extend_launches:
+        # extend ray = 32 B ray in + 16 B hit out + 64 B x nodes + 48 B x tris (oracle counters)
+        nodes, tris = (ora["ext_nodes"], ora["ext_tris"]) if ora else (None, None)
+        if nodes is not None:
+            per_ray = 32 + 16 + 64 * nodes + 48 * tris
+            rays_per_launch = pc.extend_rays / kt.extend_launches
+            avg_s = kt.extend_ms * 1e-3 / kt.extend_launches
+            achieved = per_ray * rays_per_launch / avg_s / 1e9
+            total_k = kt.raygen_ms + kt.extend_ms + kt.shade_ms + kt.connect_ms + kt.other_ms
+            roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "peak_source": peak_src, "bytes_per_ray": per_ray, "nodes_per_ray": nodes, "tris_per_ray": tris,
+                        "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_s * 1e3,
+                        "kernel_time_share": {"raygen": kt.raygen_ms / total_k, "extend": kt.extend_ms / total_k, "shade": kt.shade_ms / total_k,
+                                              "connect": kt.connect_ms / total_k, "other": kt.other_ms / total_k}}
+    out = {
+        "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "width": W, "height": H, "max_bounces": B, "accel": args.accel, "triangles": scene.num_triangles,
+                   "step": "1 spp over the full frame per GPU (frame_index = step*n_gpus + rank)",
+                   "l2_policy": "inputs larger than L2: ~%d MB of per-path wavefront state streams through HBM every step; the %.0f MB scene+BVH is the steady-state L2-resident working set"
+                   % (W * H * (6 * 16 + 20 + 16) // 1000000, (scene.num_triangles * (48 + 64)) / 1e6),
+                   "multi_gpu": "sample-index sharding, scene+BVH replicated, one NCCL reduce of the FP32 sum buffer per batch" if world > 1 else "single GPU"},
+        "mpix_spp_per_s": mpix, "extend_rays": ext, "shadow_rays": shd, "accel_build_ms": build_ms,
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,11 @@ class Counters(C.Structure):
                 ("extend_rays_per_bounce", C.c_uint64 * 16), ("shadow_rays_per_bounce", C.c_uint64 * 16)]
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("raygen_ms", "extend_ms", "shade_ms", "connect_ms", "other_ms")] + \
+               [(n, C.c_uint64) for n in ("raygen_launches", "extend_launches", "shade_launches", "connect_launches", "other_launches")]
+
+
 class ProbeVolume(C.Structure):
     _fields_ = [("base_position", C.c_float * 3), ("_pad0", C.c_float), ("frame_x", C.c_float * 3), ("_pad1", C.c_float),
                 ("frame_y", C.c_float * 3), ("_pad2", C.c_float), ("frame_z", C.c_float * 3), ("_pad3", C.c_float),
@@ -162,6 +167,8 @@ BPT_ONLY_API = {
     "resolve_device": [_VP, _U32, _VP],
     "accum_device_ptr": [_VP, C.POINTER(_VP)],
     "upload_accum": [_VP, _VP],
+    "profile_enable": [_VP, _U32],
+    "profile_read": [_VP, C.POINTER(KernelTimes)],
 }
 BPT_EXPORTS = sorted(["bpt_" + n for n in list(COMMON_API) + list(BPT_ONLY_API)] + ["bpt_last_error", "bpt_version"])
 
@@ -335,6 +342,14 @@ class Context:
 
     def resolve_device(self, total_samples: int, device_ptr: int):
         self._call("resolve_device", total_samples, _VP(device_ptr))
+
+    def profile_enable(self, enable: bool):
+        self._call("profile_enable", 1 if enable else 0)
+
+    def profile_read(self) -> KernelTimes:
+        t = KernelTimes()
+        self._call("profile_read", C.byref(t))
+        return t
 
     def upload_accum(self, sums: np.ndarray):
         self._call("upload_accum", _ptr(np.ascontiguousarray(sums, dtype=f32)))

@@ -340,6 +340,30 @@ bpt_status bpt_reset_counters(bpt_context* c) {
     return BPT_OK;
 }
 
+bpt_status bpt_profile_enable(bpt_context* c, uint32_t en) {
+    NEED(c);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto& e : c->prof_events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    c->prof_events.clear();
+    c->profile = en != 0;
+    return BPT_OK;
+}
+bpt_status bpt_profile_read(bpt_context* c, bpt_kernel_times* out) {
+    NEED(c);
+    if (!out) return BPT_ERR_INVALID;
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    double ms[5] = {0, 0, 0, 0, 0}; uint64_t n[5] = {0, 0, 0, 0, 0};
+    for (auto& e : c->prof_events) {
+        float t = 0.0f;
+        BPT_CUDA_TRY(c, cudaEventElapsedTime(&t, e.a, e.b));
+        ms[e.cls] += t; n[e.cls]++;
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    c->prof_events.clear();
+    *out = bpt_kernel_times{ms[0], ms[1], ms[2], ms[3], ms[4], n[0], n[1], n[2], n[3], n[4]};
+    return BPT_OK;
+}
+
 bpt_status bpt_trace_rays(bpt_context* c, const bpt_ray* rays, uint64_t n, uint32_t frame, bpt_hit* out) {
     NEED(c);
     if (!c->accel_built) return fail(c, BPT_ERR_STATE, "accel not built");

@@ -68,6 +68,9 @@ struct bpt_context {
     DevBuf d_inst_aabb;          // scratch for TLAS build
 
     WavefrontState wf;
+    bool profile = false;
+    struct ProfEvent { cudaEvent_t a, b; int cls; };
+    std::vector<ProfEvent> prof_events;
     bool capture = false;
     uint32_t cap_bounces = 0;
     std::vector<std::vector<uint32_t>> cap_extend_pixels, cap_shadow_pixels, cap_shadow_lights;

@@ -169,6 +169,18 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ 
         BPT_CUDA_TRY(ctx, cudaGetLastError());                                  \
     } while (0)
 
+// LAUNCH with optional event bracketing (bpt_profile_enable): class 0 raygen, 1 extend, 2 shade, 3 connect, 4 other
+#define LAUNCH_T(ctx, cls, kernel, grid, block, ...)                                              \
+    do {                                                                                          \
+        bpt_context::ProfEvent pe__{nullptr, nullptr, (cls)};                                     \
+        if ((ctx)->profile) {                                                                     \
+            BPT_CUDA_TRY(ctx, cudaEventCreate(&pe__.a)); BPT_CUDA_TRY(ctx, cudaEventCreate(&pe__.b)); \
+            BPT_CUDA_TRY(ctx, cudaEventRecord(pe__.a, (ctx)->stream));                            \
+        }                                                                                         \
+        LAUNCH(ctx, kernel, grid, block, __VA_ARGS__);                                            \
+        if ((ctx)->profile) { BPT_CUDA_TRY(ctx, cudaEventRecord(pe__.b, (ctx)->stream)); (ctx)->prof_events.push_back(pe__); } \
+    } while (0)
+
 bpt_status wavefront_alloc(bpt_context* ctx) {
     WavefrontState& wf = ctx->wf;
     uint32_t npx = ctx->width * ctx->height;
@@ -266,20 +278,20 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
             a.ray_o_out = wf.ray_o[out].as<float4>(); a.ray_d_out = wf.ray_d[out].as<float4>(); a.ray_w_out = wf.ray_w[out].as<float4>();
         };
         bind(1, 0);
-        LAUNCH(ctx, k_raygen, grid_px, kBlock, a);
+        LAUNCH_T(ctx, 0, k_raygen, grid_px, kBlock, a);
         for (uint32_t i = 1; i < B; i++) {
             bind(cur, cur ^ 1);
-            LAUNCH(ctx, k_extend, grid_px, kBlock, a, i);
-            LAUNCH(ctx, k_shade, grid_px, kBlock, a, i);
+            LAUNCH_T(ctx, 1, k_extend, grid_px, kBlock, a, i);
+            LAUNCH_T(ctx, 2, k_shade, grid_px, kBlock, a, i);
             if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
                 // the shadow queue holds at most (live paths x lights) rays; the grid covers the bound
                 uint64_t bound = (uint64_t)npx * nl;
-                LAUNCH(ctx, k_connect, (unsigned)((bound + kBlock - 1) / kBlock), kBlock, a, i);
+                LAUNCH_T(ctx, 3, k_connect, (unsigned)((bound + kBlock - 1) / kBlock), kBlock, a, i);
             }
             if (capture && (s = capture_bounce(ctx, i, cur))) return s;
             cur ^= 1;
         }
-        LAUNCH(ctx, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), npx);
+        LAUNCH_T(ctx, 4, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), npx);
     }
     return BPT_OK;
 }

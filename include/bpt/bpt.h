@@ -320,6 +320,15 @@ typedef struct bpt_counters {
 BPT_API bpt_status bpt_get_counters(bpt_context* ctx, bpt_counters* out);   /* synchronises */
 BPT_API bpt_status bpt_reset_counters(bpt_context* ctx);
 
+/* Per-kernel device timing (CUDA events on the launching stream around every kernel of bpt_render).
+ * Used by bench.py for the roofline of the dominant kernel; off by default (no events recorded). */
+typedef struct bpt_kernel_times {
+    double raygen_ms, extend_ms, shade_ms, connect_ms, other_ms;
+    uint64_t raygen_launches, extend_launches, shade_launches, connect_launches, other_launches;
+} bpt_kernel_times;
+BPT_API bpt_status bpt_profile_enable(bpt_context* ctx, uint32_t enable);
+BPT_API bpt_status bpt_profile_read(bpt_context* ctx, bpt_kernel_times* out); /* synchronises, then resets */
+
 /* ---------------------------------------------------------------------------------------
  * Debug / parity hooks
  * ------------------------------------------------------------------------------------- */

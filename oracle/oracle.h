@@ -85,6 +85,9 @@ typedef struct obpt_stats {
     uint64_t samples;
 } obpt_stats;
 BPT_API bpt_status obpt_get_stats(obpt_context* ctx, obpt_stats* out);
+/* Oracle-only: render only the 16x16 tiles t with t % stride == offset (a bounded, spatially uniform
+ * sample of the frame for the CPU-baseline timing). stride 1 = every tile (default). */
+BPT_API bpt_status obpt_set_tile_sample(obpt_context* ctx, uint32_t stride, uint32_t offset);
 
 /* Oracle-only: double-precision accumulation of a many-spp reference image (relMSE gate). */
 BPT_API bpt_status obpt_render_converged(

@@ -52,6 +52,7 @@ def library() -> capi.Library:
         _lib = capi.Library(LIB_PATH, "obpt_", {
             "set_threads": [C.c_void_p, C.c_uint32],
             "get_stats": [C.c_void_p, C.POINTER(Stats)],
+            "set_tile_sample": [C.c_void_p, C.c_uint32, C.c_uint32],
             "render_converged": [C.c_void_p, C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.POINTER(capi.Settings), C.c_void_p],
         })
         L = _lib.lib
@@ -81,6 +82,9 @@ class OracleContext(capi.Context):
     @property
     def threads(self) -> int:
         return self.L.lib.obpt_get_threads(self._h)
+
+    def set_tile_sample(self, stride: int, offset: int = 0):
+        self._call("set_tile_sample", stride, offset)
 
     def stats(self) -> Stats:
         s = Stats()

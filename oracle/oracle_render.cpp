@@ -197,7 +197,7 @@ static inline void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, u
 struct ThreadOut {
     TraceStats ext, shd;
     uint64_t ext_per_bounce[16] = {0}, shd_per_bounce[16] = {0};
-    uint64_t shaded = 0, missed = 0;
+    uint64_t shaded = 0, missed = 0, pixel_samples = 0;
     struct CapE { uint32_t bounce, pixel; bpt_hit hit; };
     struct CapS { uint32_t bounce, pixel, light; };
     std::vector<CapE> cap_e;
@@ -308,10 +308,11 @@ static void render_impl(obpt_context& ctx, const bpt_camera& cam, uint32_t first
         for (;;) {
             uint32_t t = next.fetch_add(1);
             if (t >= tx * ty) break;
+            if (t % ctx.tile_stride != ctx.tile_offset) continue;
             uint32_t x0 = (t % tx) * TILE, y0 = (t / tx) * TILE;
             for (uint32_t y = y0; y < std::min(y0 + TILE, H); y++)
                 for (uint32_t x = x0; x < std::min(x0 + TILE, W); x++)
-                    for (uint32_t s = 0; s < ns; s++)
+                    for (uint32_t s = 0; s < ns; s++, out.pixel_samples++)
                         render_pixel(ctx, cam, st, first + s, x, y, accum + 4ull * (y * W + x), out);
         }
     };
@@ -329,12 +330,12 @@ static void render_impl(obpt_context& ctx, const bpt_camera& cam, uint32_t first
         }
         ctx.stats.shaded_vertices += o.shaded;
         ctx.stats.miss_vertices += o.missed;
+        ctx.counters.samples += o.pixel_samples;
+        ctx.stats.samples += o.pixel_samples;
     }
     ctx.counters.extend_rays += ext.rays; ctx.counters.shadow_rays += shd.rays;
-    ctx.counters.samples += (uint64_t)W * H * ns;
     ctx.stats.extend_rays += ext.rays; ctx.stats.extend_nodes += ext.nodes; ctx.stats.extend_tris += ext.tris; ctx.stats.extend_instances += ext.instances;
     ctx.stats.shadow_rays += shd.rays; ctx.stats.shadow_nodes += shd.nodes; ctx.stats.shadow_tris += shd.tris; ctx.stats.shadow_instances += shd.instances;
-    ctx.stats.samples += (uint64_t)W * H * ns;
     if (ctx.capture) {
         uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);
         ctx.cap_extend_pixels.assign(B, {}); ctx.cap_extend_hits.assign(B, {});
@@ -503,6 +504,10 @@ bpt_status obpt_resolve(obpt_context* c, uint32_t total, float* out) {
 bpt_status obpt_get_counters(obpt_context* c, bpt_counters* o) { CHECK_CTX(c); *o = c->counters; return BPT_OK; }
 bpt_status obpt_reset_counters(obpt_context* c) { CHECK_CTX(c); c->counters = bpt_counters{}; c->stats = obpt_stats{}; return BPT_OK; }
 bpt_status obpt_get_stats(obpt_context* c, obpt_stats* o) { CHECK_CTX(c); *o = c->stats; return BPT_OK; }
+bpt_status obpt_set_tile_sample(obpt_context* c, uint32_t stride, uint32_t offset) {
+    CHECK_CTX(c); if (!stride || offset >= stride) return BPT_ERR_INVALID;
+    c->tile_stride = stride; c->tile_offset = offset; return BPT_OK;
+}
 
 bpt_status obpt_trace_rays(obpt_context* c, const bpt_ray* rays, uint64_t n, uint32_t frame, bpt_hit* out) {
     CHECK_CTX(c); if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "accel not built");

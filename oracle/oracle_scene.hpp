@@ -103,6 +103,7 @@ struct obpt_context {
     orc::Scene scene;
     uint32_t width = 0, height = 0;
     uint32_t threads = 0;
+    uint32_t tile_stride = 1, tile_offset = 0;
     std::string err;
     std::vector<float> accum;        // W*H*4 FP32 sums
     bpt_counters counters{};

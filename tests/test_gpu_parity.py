@@ -140,7 +140,8 @@ def test_atrium_full_size_bvh_and_render(lib, oracle):
     big.clear_accum(); big.render(cam, 1, 1, st); s1 = big.resolve(1)
     big.clear_accum(); big.render(cam, 0, 2, st); s01 = big.resolve(1)
     assert np.isfinite(s01).all() and s01[..., :3].mean() > 0
-    np.testing.assert_array_equal((s0 + s1)[..., :3], s01[..., :3])
+    # linearity of the FP32 sum buffer (exact up to the different association of the adds)
+    np.testing.assert_allclose((s0 + s1)[..., :3], s01[..., :3], rtol=1e-5, atol=1e-7)
     c = big.counters()
     assert c.samples == 4 * W * H and c.extend_rays_per_bounce[1] == 4 * W * H
     assert all(c.extend_rays_per_bounce[i] >= c.extend_rays_per_bounce[i + 1] for i in range(1, 8))
