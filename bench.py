@@ -32,7 +32,7 @@ WORKLOAD = "atrium_262144tri_25mat_1920x1080_depth8_dirlight_sky"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=WIDTH)
@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--bounces", type=int, default=BOUNCES)
     ap.add_argument("--accel", default="merged", choices=["merged", "two_level"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="only the device-resident timed loop (for ncu captures)")
     ap.add_argument("--cpu-tile-stride", type=int, default=0, help="oracle sample: every n-th 16x16 tile (0 = auto)")
     return ap.parse_args()
 
@@ -232,6 +233,11 @@ def main():
     value = (ext + shd) / (ms * 1e-3) / 1e6
     mpix = samples / (ms * 1e-3) / 1e6
 
+    if args.device_only:
+        if rank == 0:
+            print(json.dumps({"metric": "Mrays/s", "value": value, "ms_per_step": ms / max(1, args.steps), "device_only": True}))
+        return
+
     # ---------------- per-kernel timing of the dominant kernel (CUDA events inside libbpt) --------
     prof_steps = min(8, max(1, args.steps))
     ctx.profile_enable(True)
@@ -294,7 +300,7 @@ def main():
         stride = args.cpu_tile_stride or 8
         ora = oracle_sample(scene, mode, W, H, B, stride, 1)
         if ora["seconds"] < 5.0:        # aim for ~10-30 s of CPU work
-            frames = int(min(64, max(2, 12.0 / max(ora["seconds"], 1e-3))))
+            frames = int(min(1024, max(2, 15.0 / max(ora["seconds"], 1e-3))))
             ora = oracle_sample(scene, mode, W, H, B, stride, frames)
         cpu = {"value": ora["rays_per_s"] / 1e6, "unit": "Mrays/s", "cores": ora["cores"], "kind": "port",
                "sample": ora["desc"], "seconds": ora["seconds"]}
