@@ -172,7 +172,7 @@ def main():
     import torch
     import torch.distributed as dist
     import bisemutum_engine_b200 as pkg
-    from bisemutum_engine_b200 import capi, engine, scenes
+    from bisemutum_engine_b200 import capi, engine, scenes, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
@@ -213,10 +213,10 @@ def main():
     barrier()
     ev0.record(stream)
     for k in range(args.steps):
-        ctx.render(cam, k * world + rank, 1, st)
+        ctx.render(cam, sharding.frame_index(k, rank, world), 1, st)
     if world > 1:   # the one exchange step: FP32 sum buffers → rank 0 (one NCCL reduce per batch of frames)
         ctx.resolve_device(1, reduce_buf.data_ptr())
-        dist.reduce(reduce_buf, dst=0, op=dist.ReduceOp.SUM)
+        sharding.reduce_sums(reduce_buf, dst=0)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()

@@ -433,3 +433,64 @@ def small_test_scene(seed=7, with_translucent=True) -> SceneData:
     cam = dict(position=(0.3, 2.2, 6.5), front_dir=(-0.03, -0.22, -1.0), up_dir=(0.0, 1.0, 0.0), yfov=40.0, near_z=0.001, far_z=1e5)
     return b.finish(dir_lights=dir_light((0.4, 1.0, 0.6), (1.0, 0.95, 0.9), 3.0), sky_faces=procedural_sky(16, (0.4, 1.0, 0.6)),
                     camera=cam, bounds=(np.array([-4, 0, -4.0]), np.array([4, 3, 4.0])))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: mixed lights — point / spot / LTC rect lights packed exactly as
+# LightsContext::collect_all_lights does (bisemutum/src/renderer/context/lights.cpp:125-229).
+# ---------------------------------------------------------------------------------------------
+def _rotation_rows(rng):
+    return random_rotation(rng)[:3, :3]
+
+
+def add_mixed_lights(scene: SceneData, n_point: int, n_rect: int, ltc_luts, seed: int = 3, strength: float = 6.0,
+                     light_range: float = 30.0, keep_dir_lights: bool = False) -> SceneData:
+    """n_point point lights (every second one a spot, inner 30 / outer 60 degrees) at uniform positions
+    inside the scene bounds + n_rect one-sided, untextured 1x1 m rect lights."""
+    rng = np.random.default_rng(seed)
+    lo, hi = (np.asarray(b, np.float64) for b in scene.bounds)
+    pad = 0.08 * (hi - lo)
+    pl = np.zeros(n_point, capi.POINT_LIGHT)
+    for i in range(n_point):
+        R = _rotation_rows(rng)
+        color = rng.uniform(0.3, 1.0, 3)
+        pl[i]["emission"] = (color * strength).astype(f32)
+        pl[i]["position"] = rng.uniform(lo + pad, hi - pad).astype(f32)
+        pl[i]["direction"] = (R @ np.array([0.0, 1.0, 0.0])).astype(f32)          # lights point along local +Y
+        if i % 2 == 1:
+            pl[i]["cos_outer"] = np.cos(np.radians(f32(60.0)))
+            pl[i]["cos_inner"] = np.cos(np.radians(f32(30.0)))
+        pl[i]["range_sqr_inv"] = f32(1.0) / (f32(light_range) * f32(light_range))
+        pl[i]["sm_index"] = -1
+    rl = np.zeros(n_rect, capi.RECT_LIGHT)
+    for i in range(n_rect):
+        R = _rotation_rows(rng)
+        c = rng.uniform(lo + pad, hi - pad)
+        w = h = 0.5
+        rl[i]["emission"] = (rng.uniform(0.3, 1.0, 3) * strength).astype(f32)
+        rl[i]["texture_index"] = -1
+        rl[i]["center_position"] = c.astype(f32)
+        rl[i]["two_sided"] = 0
+        rl[i]["position0"] = (c + R @ np.array([w, h, 0.0])).astype(f32)
+        rl[i]["position1"] = (c + R @ np.array([-w, h, 0.0])).astype(f32)
+        rl[i]["position2"] = (c + R @ np.array([-w, -h, 0.0])).astype(f32)
+        rl[i]["position3"] = (c + R @ np.array([w, -h, 0.0])).astype(f32)
+        rl[i]["normal"] = (R @ np.array([0.0, 0.0, 1.0])).astype(f32)
+        rl[i]["inv_width_sqr"] = 1.0
+        rl[i]["inv_height_sqr"] = 1.0
+    scene.point_lights, scene.rect_lights = pl, rl
+    if not keep_dir_lights:
+        scene.dir_lights = np.zeros(0, capi.DIR_LIGHT)
+    scene.ltc_luts = tuple(np.ascontiguousarray(a, f32) for a in ltc_luts) if n_rect else None
+    scene.name += f"+{n_point}point+{n_rect}rect"
+    return scene
+
+
+def load_ltc_luts(npz_path: str):
+    z = np.load(npz_path)
+    return tuple(np.ascontiguousarray(z[k], f32) for k in ("matrix_lut0", "matrix_lut1", "matrix_lut2", "norm_lut"))
+
+
+def mixed_lights(ltc_luts, seed: int = ATRIUM_SEED) -> SceneData:
+    """configs[2]: the atrium with 64 point/spot lights + 16 LTC rect lights."""
+    return add_mixed_lights(atrium(seed), 64, 16, ltc_luts, seed=seed & 0xffff)

@@ -1,0 +1,34 @@
+"""Multi-GPU plumbing for the one place the path shards: samples are independent because
+all randomness is keyed by (pixel, frame_index, bounce) (sample_secondary_ray.hlsl:52), so GPU `rank`
+of `world` renders the samples s ≡ rank (mod world) of every pixel into its own FP32 sum buffer
+(scene + BVH replicated), and ONE reduce of the W x H x 4 sum buffers to rank 0 per batch of frames is
+the only exchange. torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def frame_index(step: int, rank: int, world: int, first: int = 0) -> int:
+    """frame_index of the `step`-th frame this rank renders."""
+    return first + step * world + rank
+
+
+def frames_of_rank(steps: int, rank: int, world: int, first: int = 0) -> list[int]:
+    return [frame_index(k, rank, world, first) for k in range(steps)]
+
+
+def reduce_sums(sum_buffer: torch.Tensor, dst: int = 0) -> torch.Tensor:
+    """In-place sum of every rank's FP32 accumulation buffer into rank `dst` (no-op for world 1)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(sum_buffer, dst=dst, op=dist.ReduceOp.SUM)
+    return sum_buffer
+
+
+def resolve(sum_buffer: torch.Tensor, total_samples: int) -> torch.Tensor:
+    """image = sum / N with alpha 1 (pt_accumulate.hlsl:3-11 restated as sum-then-divide so that the
+    result does not depend on how samples were distributed over GPUs)."""
+    out = sum_buffer * (1.0 / float(total_samples))
+    out[..., 3] = 1.0
+    return out

@@ -1,0 +1,77 @@
+"""Generates tests/golden/golden_v1.npz with the CPU oracle (the reference ships no golden vectors for
+this path — SURVEY §4/§8c "parity unpinned" — so these pin the ORACLE against drift and give the CUDA
+path a fixed, committed target in addition to the live oracle comparison).
+
+    python tests/golden/make_golden.py          (build container; needs oracle/_build/liboracle.so)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from bisemutum_engine_b200 import capi, scenes  # noqa: E402
+from oracle import oracle_py  # noqa: E402
+
+OUT = os.path.join(HERE, "golden_v1.npz")
+W, H = 48, 32
+
+
+def golden_rays(scene, n=512, seed=21):
+    rng = np.random.default_rng(seed)
+    lo, hi = scene.bounds
+    rays = np.zeros(n, capi.RAY)
+    rays["origin"] = rng.uniform(lo - 0.5, hi + 0.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tmin"], rays["tmax"] = 0.001, 100.0
+    return rays
+
+
+def cases():
+    luts = scenes.load_ltc_luts(os.path.join(HERE, "ltc_luts.npz"))
+    yield "small", scenes.small_test_scene(), 6
+    yield "cornell", scenes.cornell_box(tess=8), 5
+    yield "mixed", scenes.add_mixed_lights(scenes.small_test_scene(), 5, 3, luts, keep_dir_lights=True, light_range=12.0), 3
+
+
+def compute(name, scene, bounces, make_ctx):
+    out = {}
+    for mode, mname in ((capi.ACCEL_TWO_LEVEL, "two_level"), (capi.ACCEL_MERGED, "merged")):
+        ctx = make_ctx(W, H)
+        ctx.upload_scene(scene, mode)
+        k = f"{name}.{mname}"
+        b = ctx.read_bvh(0)
+        out[f"{k}.bvh0.morton"] = b["morton"]; out[f"{k}.bvh0.prims"] = b["prims"]
+        out[f"{k}.bvh0.child0"] = b["nodes"]["child0"]; out[f"{k}.bvh0.child1"] = b["nodes"]["child1"]
+        if mode == capi.ACCEL_TWO_LEVEL:
+            t = ctx.read_bvh(capi.BVH_TLAS)
+            out[f"{k}.tlas.prims"] = t["prims"]; out[f"{k}.tlas.child0"] = t["nodes"]["child0"]
+        hits = ctx.trace_rays(golden_rays(scene), 2)
+        for f in ("t", "u", "v", "instance", "primitive"):
+            out[f"{k}.hits.{f}"] = hits[f]
+        cam = oracle_py.camera_matrices(scene.camera, W, H)
+        st = capi.Settings(max_bounces=bounces)
+        for frame in (0, 9):
+            ctx.clear_accum()
+            ctx.render(cam, frame, 1, st)
+            out[f"{k}.image.f{frame}"] = ctx.resolve(1)[..., :3].copy()
+        c = ctx.counters()
+        out[f"{k}.extend_per_bounce"] = np.array(list(c.extend_rays_per_bounce), np.uint64)
+        out[f"{k}.shadow_per_bounce"] = np.array(list(c.shadow_rays_per_bounce), np.uint64)
+        ctx.close()
+    return out
+
+
+def main():
+    oracle_py.build()
+    out = {}
+    for name, scene, bounces in cases():
+        out.update(compute(name, scene, bounces, oracle_py.OracleContext))
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,254 @@
+"""CPU tests of the oracle itself: known-answer values, properties, and an independent numpy
+brute-force check of its BVH + traversal. (`-m "not gpu"`)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from bisemutum_engine_b200 import capi, scenes
+
+# SURVEY.md Appendix D — computed from shaders/core/utils/random.hlsl:3-26 (the only external pin)
+RNG_KATS = [
+    ((0, 0), 0x741C187D, (0xD2FFB8, 0x013FB7)),
+    ((1, 0), 0x8DA6B311, (0xE7D13C, 0x6E7B6B)),
+    ((0, 1), 0x70D3AEF1, (0x6BDB9C, 0xA5424B)),
+    ((1037220, 1), 0x10109D9D, (0x688258, 0x44A1D7)),
+    ((2073599, 276), 0x79330A80, (0xB57BDF, 0xC817B2)),
+    ((123456, 42), 0xBC8A51F3, (0xD6EEB6, 0x3B969D)),
+]
+
+
+def test_rng_known_answers(oracle):
+    L = oracle.library().lib
+    for (a, b), tea, lcgs in RNG_KATS:
+        assert L.obpt_rng_tea(a, b) == tea
+        st = C.c_uint32(tea)
+        assert L.obpt_rng_lcg(C.byref(st)) == lcgs[0]
+        assert L.obpt_rng_lcg(C.byref(st)) == lcgs[1]
+
+
+def test_rng_tea_matches_python_restatement(oracle):
+    def tea(v0, v1):
+        s0 = 0
+        for _ in range(16):
+            s0 = (s0 + 0x9E3779B9) & 0xFFFFFFFF
+            v0 = (v0 + ((((v1 << 4) + 0xA341316C) ^ (v1 + s0) ^ ((v1 >> 5) + 0xC8013EA4)) & 0xFFFFFFFF)) & 0xFFFFFFFF
+            v1 = (v1 + ((((v0 << 4) + 0xAD90777D) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7E95761E)) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        return v0
+    rng = np.random.default_rng(1)
+    L = oracle.library().lib
+    for a, b in rng.integers(0, 2 ** 32, (200, 2)):
+        assert L.obpt_rng_tea(int(a), int(b)) == tea(int(a), int(b))
+
+
+def test_trig_polynomials_accuracy(oracle):
+    L = oracle.library().lib
+    s, c = C.c_float(), C.c_float()
+    for u in np.linspace(0, 1, 4001).astype(np.float32):
+        L.obpt_sincos_2pi(float(u), C.byref(s), C.byref(c))
+        assert abs(s.value - np.sin(2 * np.pi * float(u))) < 3e-7 and abs(c.value - np.cos(2 * np.pi * float(u))) < 3e-7
+    for x in np.linspace(-1, 1, 2001).astype(np.float32):
+        assert abs(L.obpt_acos(float(x)) - np.arccos(float(x))) < 1e-6
+    rng = np.random.default_rng(0)
+    for y, x in rng.normal(size=(2000, 2)).astype(np.float32):
+        assert abs(L.obpt_atan2(float(y), float(x)) - np.arctan2(float(y), float(x))) < 1e-6
+
+
+def test_vndf_sample_properties(oracle):
+    L = oracle.library().lib
+    rng = np.random.default_rng(2)
+    out = np.zeros(3, np.float32)
+    for _ in range(500):
+        v = rng.normal(size=3); v[2] = abs(v[2]) + 0.05; v = (v / np.linalg.norm(v)).astype(np.float32)
+        rx, ry = rng.uniform(0.01, 1.0, 2)
+        L.obpt_ggx_vndf_sample(v.ctypes.data_as(C.c_void_p), rx, ry, rng.uniform(), rng.uniform(), out.ctypes.data_as(C.c_void_p))
+        assert abs(np.linalg.norm(out) - 1) < 1e-5 and out[2] >= 0
+        assert np.dot(out, v) > -1e-5          # visible normals face the viewer
+
+
+def test_bsdf_matches_float64_formula(oracle):
+    """surface_eval_lit against a float64 numpy restatement of lit.hlsl:5-35."""
+    L = oracle.library().lib
+    rng = np.random.default_rng(3)
+
+    def ref(N, T, V, Ld, base, f0, f90, rough, aniso):
+        B = np.cross(N, T); H = (V + Ld) / np.linalg.norm(V + Ld)
+        lh, lv, ll = (np.array([x @ T, x @ B, x @ N]) for x in (H, V, Ld))
+        if lv[2] <= 0 or ll[2] <= 0:
+            return np.zeros(3)
+        fr = f0 + (f90 - f0) * (1 - max(V @ H, 0)) ** 5
+        diff = (1 - fr) * base / np.pi * ll[2]
+        a = np.sqrt(1 - 0.9 * aniso); r2 = rough * rough
+        rx, ry = max(r2 / a, 1e-3), max(r2 * a, 1e-3)
+        ndf = 1 / (np.pi * rx * ry * ((lh[0] / rx) ** 2 + (lh[1] / ry) ** 2 + lh[2] ** 2) ** 2)
+        vv = ll[2] * np.sqrt((rx * lv[0]) ** 2 + (ry * lv[1]) ** 2 + lv[2] ** 2)
+        lll = lv[2] * np.sqrt((rx * ll[0]) ** 2 + (ry * ll[1]) ** 2 + ll[2] ** 2)
+        return diff + fr * ndf * (0.5 / max(vv + lll, 1e-4)) * ll[2]
+    out = np.zeros(3, np.float32)
+    for _ in range(300):
+        N = np.array([0, 0, 1.0]); T = np.array([1.0, 0, 0])
+        V = rng.normal(size=3); V[2] = abs(V[2]) + 0.1; V /= np.linalg.norm(V)
+        Ld = rng.normal(size=3); Ld[2] = abs(Ld[2]) + 0.1; Ld /= np.linalg.norm(Ld)
+        base, f0 = rng.uniform(0, 1, 3), rng.uniform(0, 1, 3); f90 = np.ones(3)
+        rough, aniso = rng.uniform(0.2, 1), rng.uniform(0, 0.8)
+        args = [np.asarray(a, np.float32) for a in (N, T, V, Ld, base, f0, f90)]
+        L.obpt_surface_eval_lit(*[a.ctypes.data_as(C.c_void_p) for a in args], rough, aniso, out.ctypes.data_as(C.c_void_p))
+        np.testing.assert_allclose(out, ref(*[a.astype(np.float64) for a in args], rough, aniso), rtol=2e-4, atol=1e-6)
+
+
+def check_bvh_structure(b, prim_lo, prim_hi):
+    n = b["n"]
+    assert sorted(b["prims"].tolist()) == list(range(n))                 # a permutation
+    assert (np.diff(b["morton"].astype(np.uint64)) >= 0).all() if n > 1 else True
+    same = b["morton"][1:] == b["morton"][:-1]
+    assert (b["prims"][1:][same] > b["prims"][:-1][same]).all()          # stable: ties keep ascending ids
+    if n < 2:
+        assert b["root"] == -1                                           # ~0: the single leaf
+        return
+    nodes = b["nodes"]
+    seen_leaf, seen_node = np.zeros(n, bool), np.zeros(n - 1, bool)
+    lo = np.zeros((n - 1, 3)); hi = np.zeros((n - 1, 3))
+
+    def visit(i, parent):
+        assert not seen_node[i]; seen_node[i] = True
+        assert nodes["parent"][i] == parent
+        boxes = []
+        for k, ch in enumerate((nodes["child0"][i], nodes["child1"][i])):
+            clo = np.array([nodes[f"c{k}_lo_{a}"][i] for a in "xyz"]); chi = np.array([nodes[f"c{k}_hi_{a}"][i] for a in "xyz"])
+            if ch < 0:
+                j = ~int(ch); assert not seen_leaf[j]; seen_leaf[j] = True
+                p = b["prims"][j]
+                np.testing.assert_array_equal(clo, prim_lo[p]); np.testing.assert_array_equal(chi, prim_hi[p])
+            else:
+                visit(int(ch), i)
+                np.testing.assert_array_equal(clo, lo[ch]); np.testing.assert_array_equal(chi, hi[ch])
+            boxes.append((clo, chi))
+        lo[i] = np.minimum(boxes[0][0], boxes[1][0]); hi[i] = np.maximum(boxes[0][1], boxes[1][1])
+    import sys
+    sys.setrecursionlimit(10000)
+    visit(0, -1)
+    assert seen_leaf.all() and seen_node.all()
+
+
+def world_triangles(scene):
+    tris = []
+    for inst in scene.instances:
+        b = scene.blas[int(inst["blas"])]
+        idx = scene.indices[int(b["index_offset"]): int(b["index_offset"]) + 3 * int(b["num_triangles"])]
+        p = scene.positions[int(b["position_offset"]):].reshape(-1, 3)[idx].astype(np.float64)
+        m = inst["transform"].astype(np.float64)
+        tris.append((p @ m[:, :3].T + m[:, 3]).reshape(-1, 3, 3))
+    return np.concatenate(tris)
+
+
+@pytest.mark.parametrize("mode", [capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED])
+def test_lbvh_structure_and_bruteforce_traversal(oracle, mode):
+    scene = scenes.small_test_scene(with_translucent=False)
+    ctx = oracle.OracleContext(8, 8)
+    ctx.upload_scene(scene, mode)
+    if mode == capi.ACCEL_MERGED:
+        b = ctx.read_bvh(0)
+        # float32 world-space boxes as the oracle builds them are value-identical to a float32 numpy transform only
+        # up to rounding order, so the structure check uses the boxes recorded in the leaves themselves
+        assert b["n"] == scene.num_triangles
+    else:
+        for bi, bd in enumerate(scene.blas):
+            b = ctx.read_bvh(bi)
+            idx = scene.indices[int(bd["index_offset"]): int(bd["index_offset"]) + 3 * int(bd["num_triangles"])]
+            p = scene.positions[int(bd["position_offset"]):].reshape(-1, 3)[idx].reshape(-1, 3, 3)
+            check_bvh_structure(b, p.min(1), p.max(1))
+        assert ctx.read_bvh(capi.BVH_TLAS)["n"] == len(scene.instances)
+    # brute force: float64 Moller-Trumbore over every world triangle
+    tris = world_triangles(scene)
+    rng = np.random.default_rng(5)
+    n = 400
+    rays = np.zeros(n, capi.RAY)
+    rays["origin"] = rng.uniform(-4, 4, (n, 3)) * [1, 0.3, 1] + [0, 2.0, 0]
+    d = rng.normal(size=(n, 3)); rays["direction"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays["tmin"], rays["tmax"] = 0.001, 100.0
+    hits = ctx.trace_rays(rays)
+    v0, e1, e2 = tris[:, 0], tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]
+    for i in range(n):
+        O, D = rays["origin"][i].astype(np.float64), rays["direction"][i].astype(np.float64)
+        pvec = np.cross(D, e2); det = np.einsum("ij,ij->i", e1, pvec)
+        ok = np.abs(det) > 1e-12
+        inv = np.where(ok, 1 / np.where(ok, det, 1), 0)
+        tvec = O - v0; u = np.einsum("ij,ij->i", tvec, pvec) * inv
+        qvec = np.cross(tvec, e1); v = (qvec @ D) * inv; t = np.einsum("ij,ij->i", e2, qvec) * inv
+        m = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 0.001) & (t <= 100)
+        tb = t[m].min() if m.any() else -1.0
+        if tb >= 0:   # (a float64 miss may be a float32 grazing hit on an edge: not asserted)
+            assert hits["t"][i] > 0 and abs(hits["t"][i] - tb) <= 1e-3 * max(1.0, tb)
+
+
+def test_morton_is_monotone_per_axis(oracle):
+    L = oracle.library().lib
+    lo, hi = np.zeros(3, np.float32), np.ones(3, np.float32)
+
+    def code(c):
+        c = np.asarray(c, np.float32)
+        return L.obpt_morton63(c.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p))
+    assert code([0, 0, 0]) == 0 and code([1, 1, 1]) == (1 << 63) - 1
+    assert code([1, 0, 0]) > code([0, 1, 0]) > code([0, 0, 1])                 # x is the most significant axis
+    xs = np.linspace(0, 1, 50)
+    for axis in range(3):
+        vals = [code(np.eye(3)[axis] * x) for x in xs]
+        assert all(a <= b for a, b in zip(vals, vals[1:]))
+    # degenerate extent → 0 on that axis
+    hi0 = np.array([1, 0, 1], np.float32)
+    c = np.array([0.5, 0.0, 0.5], np.float32)
+    assert L.obpt_morton63(c.ctypes.data_as(C.c_void_p), lo.ctypes.data_as(C.c_void_p), hi0.ctypes.data_as(C.c_void_p)) & 0x2492492492492492 == 0
+
+
+def test_render_invariants(oracle):
+    """Size-independent properties: determinism, sample-sum linearity, NEE on/off consistency, counters."""
+    scene = scenes.small_test_scene()
+    W, H = 40, 30
+    ctx = oracle.OracleContext(W, H)
+    ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    cam = oracle.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=5)
+    ctx.render(cam, 0, 2, st); a = ctx.resolve(1).copy()
+    ctx.clear_accum(); ctx.render(cam, 0, 2, st)
+    np.testing.assert_array_equal(a, ctx.resolve(1))                            # deterministic (threads do not matter)
+    one = oracle.OracleContext(W, H, threads=1); one.upload_scene(scene, capi.ACCEL_MERGED)
+    one.render(cam, 0, 2, st)
+    np.testing.assert_array_equal(a, one.resolve(1))
+    c = ctx.counters()
+    assert c.extend_rays_per_bounce[1] == 2 * 2 * W * H and c.samples == 2 * 2 * W * H
+    assert all(c.extend_rays_per_bounce[i] >= c.extend_rays_per_bounce[i + 1] for i in range(1, 5))
+    assert c.extend_rays_per_bounce[5] == 0                                    # max_bounces 5 → 4 extend passes
+    # unshadowed direct light is never darker than shadowed
+    none = oracle.OracleContext(W, H); none.upload_scene(scene, capi.ACCEL_MERGED)
+    none.render(cam, 0, 2, capi.Settings(max_bounces=2, nee_mode=capi.NEE_NONE))
+    shad = oracle.OracleContext(W, H); shad.upload_scene(scene, capi.ACCEL_MERGED)
+    shad.render(cam, 0, 2, capi.Settings(max_bounces=2))
+    assert (none.resolve(2)[..., :3] >= shad.resolve(2)[..., :3] - 1e-6).all()
+    assert none.counters().shadow_rays == 0 and shad.counters().shadow_rays > 0
+
+
+def test_empty_and_edge_inputs(oracle):
+    ctx = oracle.OracleContext(4, 4)
+    with pytest.raises(capi.BptError):
+        ctx.build_accel(capi.ACCEL_MERGED)                                      # nothing uploaded
+    with pytest.raises(capi.BptError):
+        ctx.render(capi.Camera(), 0, 1, capi.Settings())                        # render before build
+    # single triangle, single instance: root is a leaf
+    b = scenes.SceneBuilder("one_tri")
+    m = b.add_material((0.8, 0.8, 0.8))
+    P = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    N = np.tile(np.array([[0, 0, 1]], np.float32), (3, 1)); T = np.tile(np.array([[1, 0, 0, 1]], np.float32), (3, 1))
+    b.add_drawable(b.add_mesh((P, N, T, P[:, :2].copy(), np.array([[0, 1, 2]], np.uint32))), m)
+    sc = b.finish(dir_lights=scenes.dir_light((0, 0, 1)), camera=dict(position=(0.3, 0.3, 3), front_dir=(0, 0, -1), up_dir=(0, 1, 0), yfov=30, near_z=0.01, far_z=100))
+    for mode in (capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED):
+        ctx.upload_scene(sc, mode)
+        assert ctx.read_bvh(0)["root"] == -1 and ctx.read_bvh(0)["n"] == 1
+        rays = np.zeros(3, capi.RAY)
+        rays["origin"] = [(0.2, 0.2, 1), (2, 2, 1), (0.2, 0.2, 1)]; rays["direction"] = [(0, 0, -1)] * 3
+        rays["tmin"] = 0.001; rays["tmax"] = [10, 10, 0.5]
+        h = ctx.trace_rays(rays)
+        assert h["t"][0] == 1.0 and h["t"][1] < 0 and h["t"][2] < 0             # hit, miss, beyond tmax
+        assert h["primitive"][0] == 0 and h["instance"][0] == 0
+    # max_bounces is clamped to [2, 16] (path_tracing.cpp:290)
+    ctx.render(oracle.camera_matrices(sc.camera, 4, 4), 0, 1, capi.Settings(max_bounces=0))
+    assert ctx.counters().extend_rays_per_bounce[1] == 16 and ctx.counters().extend_rays_per_bounce[2] == 0
