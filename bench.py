@@ -201,9 +201,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # sample s of the job ↔ frame_index = s; rank r renders s ≡ r (mod world)  
-    for w in range(args.warmup):
-        ctx.render(cam, 1_000_000 + w * world + rank, 1, st)
+    # sample s of the job ↔ frame_index = s; rank r renders the block [r*steps, (r+1)*steps)  
+    ctx.render(cam, 1_000_000 + rank * args.warmup, args.warmup, st)
     ctx.sync()
     ctx.clear_accum()
     ctx.reset_counters()
@@ -212,8 +211,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for k in range(args.steps):
-        ctx.render(cam, sharding.frame_index(k, rank, world), 1, st)
+    ctx.render(cam, sharding.first_frame(args.steps, rank, world), args.steps, st)     # K steps = K frames of 1 spp
     if world > 1:   # the one exchange step: FP32 sum buffers → rank 0 (one NCCL reduce per batch of frames)
         ctx.resolve_device(1, reduce_buf.data_ptr())
         sharding.reduce_sums(reduce_buf, dst=0)
@@ -239,11 +237,10 @@ def main():
         return
 
     # ---------------- per-kernel timing of the dominant kernel (CUDA events inside libbpt) --------
-    prof_steps = min(8, max(1, args.steps))
+    prof_steps = min(16, max(1, args.steps))
     ctx.profile_enable(True)
     ctx.reset_counters()
-    for k in range(prof_steps):
-        ctx.render(cam, k * world + rank, 1, st)
+    ctx.render(cam, sharding.first_frame(args.steps, rank, world), prof_steps, st)
     kt = ctx.profile_read()
     ctx.profile_enable(False)
     pc = ctx.counters()
@@ -322,7 +319,7 @@ def main():
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": W, "height": H, "max_bounces": B, "accel": args.accel, "triangles": scene.num_triangles,
-                   "step": "1 spp over the full frame per GPU (frame_index = step*n_gpus + rank)",
+                   "step": "1 spp over the full frame per GPU (rank r renders frames [r*steps, (r+1)*steps)); samples_per_wave = min(steps, 2^24 / pixels)",
                    "l2_policy": "inputs larger than L2: ~%d MB of per-path wavefront state streams through HBM every step; the %.0f MB scene+BVH is the steady-state L2-resident working set"
                    % (W * H * (6 * 16 + 20 + 16) // 1000000, (scene.num_triangles * (48 + 64)) / 1e6),
                    "multi_gpu": "sample-index sharding, scene+BVH replicated, one NCCL reduce of the FP32 sum buffer per batch" if world > 1 else "single GPU"},

@@ -82,7 +82,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
                       &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
-                      &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims};
+                      &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims};
     for (DevBuf* b : bufs) dev_free(*b);
     for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
     for (auto& t : c->d_texels) dev_free(t);

@@ -23,7 +23,9 @@ struct DevBvh {
 };
 
 struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through compaction)
-    uint32_t capacity = 0;  // = width*height
+    uint64_t capacity = 0;  // paths in flight = slots * width * height
+    uint32_t npx = 0, slots = 1;
+    DevBuf color;           // float4 per path: per-sample colour C_s
     DevBuf ray_o[2], ray_d[2], ray_w[2];   // float4 each: (O|pixel), (D|-), (W|-)
     DevBuf hit;             // float4 (t,u,v,prim)
     DevBuf hit_slot;        // uint32

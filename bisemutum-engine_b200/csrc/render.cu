@@ -24,14 +24,16 @@ struct RenderArgs {
     DScene sc;
     ShadeParams sp;
     bpt_camera cam;
-    uint32_t frame_index;
     float4 *ray_o_in, *ray_d_in, *ray_w_in;
     float4 *ray_o_out, *ray_d_out, *ray_w_out;
     float4* hit; uint32_t* hit_slot;
     float4 *sh_o, *sh_d, *sh_c;
     float4* accum;
+    float4* color;            // per-sample colour, [slot][pixel]
     uint32_t* qcount;
     uint64_t shadow_capacity;
+    uint32_t npx, nslots;     // pixels, samples in this wave; a path's id is slot * npx + pixel
+    uint32_t frame_base;      // frame_index of slot 0
 };
 
 // warp-aggregated append: returns the slot for this lane (valid only if `emit`)
@@ -47,17 +49,20 @@ __device__ __forceinline__ uint32_t queue_push(uint32_t* counter, bool emit) {
     return base + __popc(ballot & ((1u << lane) - 1u));
 }
 
-// ---- raygen (generate_camera_ray.hlsl:4-16): one thread per pixel, weight = 1, no jitter ------
+// ---- raygen (generate_camera_ray.hlsl:4-16): one thread per (sample slot, pixel), weight = 1, no jitter;
+//      also zeroes the path's per-sample colour -----------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ RenderArgs a) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t npx = a.sp.width * a.sp.height;
-    if (p == 0) a.qcount[QE + 1] = npx;
-    if (p >= npx) return;
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total = a.npx * a.nslots;
+    if (id == 0) a.qcount[QE + 1] = total;
+    if (id >= total) return;
+    uint32_t p = id % a.npx;
     float3 O, D;
     camera_ray(a.cam, p % a.sp.width, p / a.sp.width, a.sp.width, a.sp.height, O, D);
-    a.ray_o_out[p] = make_float4(O.x, O.y, O.z, __uint_as_float(p));
-    a.ray_d_out[p] = make_float4(D.x, D.y, D.z, 0.0f);
-    a.ray_w_out[p] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    a.ray_o_out[id] = make_float4(O.x, O.y, O.z, __uint_as_float(id));
+    a.ray_d_out[id] = make_float4(D.x, D.y, D.z, 0.0f);
+    a.ray_w_out[id] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    a.color[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // ---- extend (rt_gbuffer.hlsl:7-36): closest hit of every live path -----------------------------
@@ -65,7 +70,8 @@ __global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ Rende
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.qcount[QE + bounce]) return;
     float4 o = a.ray_o_in[i], d = a.ray_d_in[i];
-    TraceResult r = trace_ray<false>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, a.sp.ray_length, a.frame_index);
+    uint32_t frame = a.frame_base + __float_as_uint(o.w) / a.npx;
+    TraceResult r = trace_ray<false>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, a.sp.ray_length, frame);
     a.hit[i] = make_float4(r.t, r.u, r.v, __uint_as_float(r.prim));
     a.hit_slot[i] = r.slot;
 }
@@ -73,17 +79,17 @@ __global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ Rende
 // ---- shade: material + lighting + next direction, emits shadow rays and the next extend ray ---
 struct KernelSink {
     const RenderArgs& a;
-    uint32_t bounce, pixel;
+    uint32_t bounce, path;      // path = slot * npx + pixel
     __device__ void add(float3 c) {
-        float4 v = a.accum[pixel];
+        float4 v = a.color[path];
         v.x += c.x; v.y += c.y; v.z += c.z;
-        a.accum[pixel] = v;
+        a.color[path] = v;
     }
     __device__ void shadow(float3 P, float3 L, float tmax, float3 c, uint32_t light) {
         if (a.sp.nee_mode == BPT_NEE_NONE) { add(c); return; }
         uint32_t slot = queue_push(&a.qcount[QS + bounce], true);
         if (slot < a.shadow_capacity) {
-            a.sh_o[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(pixel));
+            a.sh_o[slot] = make_float4(P.x, P.y, P.z, __uint_as_float(path));
             a.sh_d[slot] = make_float4(L.x, L.y, L.z, tmax);
             a.sh_c[slot] = make_float4(c.x, c.y, c.z, __uint_as_float(light));
         }
@@ -95,18 +101,19 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ Render
     bool live = i < a.qcount[QE + bounce];
     bool cont = false;
     float3 nO = v3s(0.0f), nD = v3s(0.0f), nW = v3s(0.0f);
-    uint32_t pixel = 0;
+    uint32_t path = 0;
     if (live) {
         float4 o = a.ray_o_in[i], d = a.ray_d_in[i], w = a.ray_w_in[i], h = a.hit[i];
-        pixel = __float_as_uint(o.w);
+        path = __float_as_uint(o.w);
+        uint32_t pixel = path % a.npx, frame = a.frame_base + path / a.npx;
         TraceResult r;
         r.t = h.x; r.u = h.y; r.v = h.z; r.prim = __float_as_uint(h.w); r.slot = a.hit_slot[i]; r.hit = h.x >= 0.0f;
-        KernelSink sink{a, bounce, pixel};
-        cont = shade_vertex(a.sc, a.sp, a.frame_index, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
+        KernelSink sink{a, bounce, path};
+        cont = shade_vertex(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
     }
     uint32_t slot = queue_push(&a.qcount[QE + bounce + 1], cont);
     if (cont) {
-        a.ray_o_out[slot] = make_float4(nO.x, nO.y, nO.z, __uint_as_float(pixel));
+        a.ray_o_out[slot] = make_float4(nO.x, nO.y, nO.z, __uint_as_float(path));
         a.ray_d_out[slot] = make_float4(nD.x, nD.y, nD.z, 0.0f);
         a.ray_w_out[slot] = make_float4(nW.x, nW.y, nW.z, 0.0f);
     }
@@ -118,10 +125,11 @@ __global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ Rend
     uint32_t n = a.qcount[QS + bounce];
     if (i >= n || i >= a.shadow_capacity) return;
     float4 o = a.sh_o[i], d = a.sh_d[i];
-    TraceResult r = trace_ray<true>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, d.w, a.frame_index);
+    uint32_t path = __float_as_uint(o.w);
+    TraceResult r = trace_ray<true>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, d.w, a.frame_base + path / a.npx);
     if (r.hit) return;
     float4 c = a.sh_c[i];
-    float* px = reinterpret_cast<float*>(a.accum + __float_as_uint(o.w));
+    float* px = reinterpret_cast<float*>(a.color + path);
     atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
 }
 
@@ -131,6 +139,18 @@ __global__ void k_tally(const uint32_t* __restrict__ qcount, uint64_t* __restric
     if (t < 16) totals[t] += qcount[QE + t];
     else if (t < 32) totals[t] += qcount[QS + (t - 16)];
     else if (t == 32) totals[32] += npx;
+}
+
+// ---- accumulate (pt_accumulate.hlsl:3-11 as FP32 sum): sum[p] += C_s[p], slots in ascending order ---
+__global__ void k_accumulate(const float4* __restrict__ color, float4* __restrict__ accum, uint32_t npx, uint32_t nslots) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    float4 v = accum[p];
+    for (uint32_t s = 0; s < nslots; s++) {
+        float4 c = color[(size_t)s * npx + p];
+        v.x += c.x; v.y += c.y; v.z += c.z;
+    }
+    accum[p] = v;
 }
 
 __global__ void k_resolve(const float4* __restrict__ accum, float4* __restrict__ out, uint32_t npx, float inv) {
@@ -181,23 +201,43 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ 
         if ((ctx)->profile) { BPT_CUDA_TRY(ctx, cudaEventRecord(pe__.b, (ctx)->stream)); (ctx)->prof_events.push_back(pe__); } \
     } while (0)
 
+// Samples per wave: several samples of every pixel are in flight together so that the late, nearly
+// empty bounces (each kernel has a ~100 us latency floor: one warp's longest traversal) are amortised
+// over more paths. Bounded by a path budget and by the shadow-queue footprint.
+static uint32_t wave_slots(const bpt_context* ctx) {
+    const uint64_t npx = (uint64_t)ctx->width * ctx->height;
+    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point, 1);
+    uint64_t by_paths = std::max<uint64_t>(1, (1ull << 24) / npx);                 // <= 16.7 M paths in flight
+    uint64_t by_shadow = std::max<uint64_t>(1, (8ull << 30) / (npx * nl * 48));    // <= 8 GiB of shadow-ray records
+    return (uint32_t)std::min<uint64_t>(std::min(by_paths, by_shadow), 64);
+}
+
 bpt_status wavefront_alloc(bpt_context* ctx) {
     WavefrontState& wf = ctx->wf;
-    uint32_t npx = ctx->width * ctx->height;
+    const uint32_t npx = ctx->width * ctx->height;
+    const uint32_t slots = wave_slots(ctx);
+    const uint64_t paths = (uint64_t)npx * slots;
     bpt_status s;
-    if (wf.capacity != npx) {
-        for (int k = 0; k < 2; k++) {
-            dev_free(wf.ray_o[k]); dev_free(wf.ray_d[k]); dev_free(wf.ray_w[k]);
-            if ((s = dev_alloc(ctx, wf.ray_o[k], (size_t)npx * 16))) return s;
-            if ((s = dev_alloc(ctx, wf.ray_d[k], (size_t)npx * 16))) return s;
-            if ((s = dev_alloc(ctx, wf.ray_w[k], (size_t)npx * 16))) return s;
-        }
-        dev_free(wf.hit); dev_free(wf.hit_slot); dev_free(wf.accum);
-        if ((s = dev_alloc(ctx, wf.hit, (size_t)npx * 16))) return s;
-        if ((s = dev_alloc(ctx, wf.hit_slot, (size_t)npx * 4))) return s;
+    if (wf.npx != npx) {
+        dev_free(wf.accum);
         if ((s = dev_alloc(ctx, wf.accum, (size_t)npx * 16))) return s;
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.accum.p, 0, (size_t)npx * 16, ctx->stream));
-        wf.capacity = npx;
+        wf.npx = npx;
+        wf.capacity = 0;
+    }
+    if (wf.capacity != paths) {
+        for (int k = 0; k < 2; k++) {
+            dev_free(wf.ray_o[k]); dev_free(wf.ray_d[k]); dev_free(wf.ray_w[k]);
+            if ((s = dev_alloc(ctx, wf.ray_o[k], paths * 16))) return s;
+            if ((s = dev_alloc(ctx, wf.ray_d[k], paths * 16))) return s;
+            if ((s = dev_alloc(ctx, wf.ray_w[k], paths * 16))) return s;
+        }
+        dev_free(wf.hit); dev_free(wf.hit_slot); dev_free(wf.color);
+        if ((s = dev_alloc(ctx, wf.hit, paths * 16))) return s;
+        if ((s = dev_alloc(ctx, wf.hit_slot, paths * 4))) return s;
+        if ((s = dev_alloc(ctx, wf.color, paths * 16))) return s;
+        wf.capacity = paths;
+        wf.slots = slots;
         wf.shadow_capacity = 0;
     }
     if (!wf.qcount.p) {
@@ -205,8 +245,8 @@ bpt_status wavefront_alloc(bpt_context* ctx) {
         if ((s = dev_alloc(ctx, wf.totals, 40 * sizeof(uint64_t)))) return s;
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.totals.p, 0, 40 * sizeof(uint64_t), ctx->stream));
     }
-    uint64_t nl = (uint64_t)ctx->num_dir + ctx->num_point;
-    uint64_t need = (uint64_t)npx * std::max<uint64_t>(nl, 1);
+    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point, 1);
+    const uint64_t need = paths * nl;
     if (wf.shadow_capacity < need) {
         if (need * 48 > (64ull << 30)) { ctx->err = "shadow-ray queue would exceed 64 GiB; reduce lights or resolution"; return BPT_ERR_OOM; }
         dev_free(wf.sh_o); dev_free(wf.sh_d); dev_free(wf.sh_c);
@@ -258,10 +298,11 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
     a.sc = ctx->scene_view();
     a.sp.width = ctx->width; a.sp.height = ctx->height; a.sp.max_bounces = B; a.sp.nee_mode = st.nee_mode; a.sp.ray_length = st.ray_length;
     a.cam = cam;
+    a.npx = npx;
     a.hit = wf.hit.as<float4>(); a.hit_slot = wf.hit_slot.as<uint32_t>();
     a.sh_o = wf.sh_o.as<float4>(); a.sh_d = wf.sh_d.as<float4>(); a.sh_c = wf.sh_c.as<float4>();
-    a.accum = wf.accum.as<float4>(); a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
-    const unsigned grid_px = (npx + kBlock - 1) / kBlock;
+    a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();
+    a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
     const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point, 1);
     const bool capture = ctx->capture && nsamples == 1;
     if (capture) {
@@ -269,8 +310,12 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         ctx->cap_extend_pixels.assign(B, {}); ctx->cap_extend_hits.assign(B, {});
         ctx->cap_shadow_pixels.assign(B, {}); ctx->cap_shadow_lights.assign(B, {});
     }
-    for (uint32_t smp = 0; smp < nsamples; smp++) {
-        a.frame_index = frame_first + smp;
+    for (uint32_t done = 0; done < nsamples;) {
+        const uint32_t slots = std::min(nsamples - done, wf.slots);
+        const uint64_t paths = (uint64_t)npx * slots;
+        const unsigned grid_paths = (unsigned)((paths + kBlock - 1) / kBlock);
+        a.nslots = slots;
+        a.frame_base = frame_first + done;
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.qcount.p, 0, 64 * sizeof(uint32_t), ctx->stream));
         int cur = 0;
         auto bind = [&](int in, int out) {
@@ -278,20 +323,22 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
             a.ray_o_out = wf.ray_o[out].as<float4>(); a.ray_d_out = wf.ray_d[out].as<float4>(); a.ray_w_out = wf.ray_w[out].as<float4>();
         };
         bind(1, 0);
-        LAUNCH_T(ctx, 0, k_raygen, grid_px, kBlock, a);
+        LAUNCH_T(ctx, 0, k_raygen, grid_paths, kBlock, a);
         for (uint32_t i = 1; i < B; i++) {
             bind(cur, cur ^ 1);
-            LAUNCH_T(ctx, 1, k_extend, grid_px, kBlock, a, i);
-            LAUNCH_T(ctx, 2, k_shade, grid_px, kBlock, a, i);
+            LAUNCH_T(ctx, 1, k_extend, grid_paths, kBlock, a, i);
+            LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
             if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
                 // the shadow queue holds at most (live paths x lights) rays; the grid covers the bound
-                uint64_t bound = (uint64_t)npx * nl;
+                uint64_t bound = paths * nl;
                 LAUNCH_T(ctx, 3, k_connect, (unsigned)((bound + kBlock - 1) / kBlock), kBlock, a, i);
             }
             if (capture && (s = capture_bounce(ctx, i, cur))) return s;
             cur ^= 1;
         }
-        LAUNCH_T(ctx, 4, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), npx);
+        LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, slots);
+        LAUNCH_T(ctx, 4, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), (uint32_t)paths);
+        done += slots;
     }
     return BPT_OK;
 }

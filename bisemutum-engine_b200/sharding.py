@@ -1,6 +1,6 @@
 """Multi-GPU plumbing for the one place the path shards: samples are independent because
 all randomness is keyed by (pixel, frame_index, bounce) (sample_secondary_ray.hlsl:52), so GPU `rank`
-of `world` renders the samples s ≡ rank (mod world) of every pixel into its own FP32 sum buffer
+of `world` renders a contiguous block of samples of every pixel into its own FP32 sum buffer
 (scene + BVH replicated), and ONE reduce of the W x H x 4 sum buffers to rank 0 per batch of frames is
 the only exchange. torch.distributed is plumbing here (NCCL on GPUs, gloo in the CPU tests).
 """
@@ -10,13 +10,19 @@ import torch
 import torch.distributed as dist
 
 
-def frame_index(step: int, rank: int, world: int, first: int = 0) -> int:
+def first_frame(steps: int, rank: int, world: int, first: int = 0) -> int:
+    """Rank `rank` renders the contiguous block of `steps` frames starting here (one bpt_render call,
+    so the library can keep several samples in flight per wave)."""
+    return first + rank * steps
+
+
+def frame_index(step: int, steps: int, rank: int, world: int, first: int = 0) -> int:
     """frame_index of the `step`-th frame this rank renders."""
-    return first + step * world + rank
+    return first_frame(steps, rank, world, first) + step
 
 
 def frames_of_rank(steps: int, rank: int, world: int, first: int = 0) -> list[int]:
-    return [frame_index(k, rank, world, first) for k in range(steps)]
+    return [frame_index(k, steps, rank, world, first) for k in range(steps)]
 
 
 def reduce_sums(sum_buffer: torch.Tensor, dst: int = 0) -> torch.Tensor:

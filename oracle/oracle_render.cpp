@@ -215,7 +215,12 @@ static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const b
     f3 O, D;
     camera_ray(cam, px, py, W, H, O, D);
     f3 Wt = splat3(1.0f);
-    auto add = [&](f3 c) { a[0] += c.x; a[1] += c.y; a[2] += c.z; };
+    // Per-sample colour C_s starts at 0, receives this sample's contributions in order, and is added to the
+    // FP32 sum buffer when the sample ends (the reference's color texture + accumulate pass,
+    // path_tracing.cpp:421-480): sum += C_s, samples in ascending frame order.
+    Acc C[3] = {0, 0, 0};
+    struct Flush { Acc* a; Acc* C; ~Flush() { a[0] += C[0]; a[1] += C[1]; a[2] += C[2]; } } flush{a, C};
+    auto add = [&](f3 c) { C[0] += c.x; C[1] += c.y; C[2] += c.z; };
     for (uint32_t i = 1; i < B; i++) {
         out.ext_per_bounce[i]++;
         HitRec h = trace_closest(sc, O, D, 0.001f, st.ray_length, frame_index, out.ext);   // rt_gbuffer.hlsl:17-25

@@ -127,16 +127,18 @@ int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t
     for (uint32_t s = 0; s < nsamples; s++)
         for (uint32_t p = 0; p < width * height; p++) {
             float3 O, D, W = v3s(1.0f);
+            float color[4] = {0, 0, 0, 0};           // per-sample colour, added to the sum when the sample ends
             camera_ray(*cam, p % width, p / width, width, height, O, D);
             for (uint32_t i = 1; i < sp.max_bounces; i++) {
                 TraceResult r = trace_ray<false>(b.sc, O, D, 0.001f, sp.ray_length, frame_first + s);
-                HostSink sink{b.sc, st->nee_mode, frame_first + s, accum_rgba + 4ull * p, {}};
+                HostSink sink{b.sc, st->nee_mode, frame_first + s, color, {}};
                 float3 nO, nD, nW;
                 bool cont = shade_vertex(b.sc, sp, frame_first + s, i, p, O, D, W, r, sink, nO, nD, nW);
                 for (auto& c : sink.pending) sink.add(c);
                 if (!cont) break;
                 O = nO; D = nD; W = nW;
             }
+            for (int k = 0; k < 3; k++) accum_rgba[4ull * p + k] += color[k];
         }
     return 0;
 }
