@@ -315,6 +315,8 @@ def main():
                         "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_s * 1e3,
                         "kernel_time_share": {"raygen": kt.raygen_ms / total_k, "extend": kt.extend_ms / total_k, "shade": kt.shade_ms / total_k,
                                               "connect": kt.connect_ms / total_k, "other": kt.other_ms / total_k}}
+    kernel_ms = {"steps": prof_steps, "raygen": kt.raygen_ms / prof_steps, "extend": kt.extend_ms / prof_steps, "shade": kt.shade_ms / prof_steps,
+                 "connect": kt.connect_ms / prof_steps, "other": kt.other_ms / prof_steps}
     out = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -324,7 +326,7 @@ def main():
                    % (W * H * (6 * 16 + 20 + 16) // 1000000, (scene.num_triangles * (48 + 64)) / 1e6),
                    "multi_gpu": "sample-index sharding, scene+BVH replicated, one NCCL reduce of the FP32 sum buffer per batch" if world > 1 else "single GPU"},
         "mpix_spp_per_s": mpix, "extend_rays": ext, "shadow_rays": shd, "accel_build_ms": build_ms,
-        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(out))
     if world > 1:

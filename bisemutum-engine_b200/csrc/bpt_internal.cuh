@@ -26,13 +26,14 @@ struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through 
     uint64_t capacity = 0;  // paths in flight = slots * width * height
     uint32_t npx = 0, slots = 1;
     DevBuf color;           // float4 per path: per-sample colour C_s
+    unsigned grid_extend = 0, grid_connect = 0, grid_extend_m = 0, grid_connect_m = 0;   // resident grid sizes of the persistent traversal kernels
     DevBuf ray_o[2], ray_d[2], ray_w[2];   // float4 each: (O|pixel), (D|-), (W|-)
     DevBuf hit;             // float4 (t,u,v,prim)
     DevBuf hit_slot;        // uint32
     uint64_t shadow_capacity = 0;
     DevBuf sh_o, sh_d, sh_c; // float4 each: (P|pixel), (L|tmax), (c|light)
     DevBuf accum;           // float4 per pixel: FP32 sums
-    DevBuf qcount;          // uint32[2*32]: [0..16] extend queue sizes per bounce, [32..48] shadow queue sizes
+    DevBuf qcount;          // uint32[128]: extend / shadow queue lengths per bounce + work cursors of the persistent kernels
     DevBuf totals;          // uint64[40]: extend per bounce [0..15], shadow per bounce [16..31], samples [32]
 };
 

@@ -32,7 +32,9 @@ struct DTexture {
 struct DInstance {           // 128 B
     float o2w[12];
     float w2o[12];
-    uint32_t instance_id, flags, blas, pad[5];
+    uint32_t instance_id, flags, blas;
+    uint32_t anyhit;         // 1 if candidates of this instance must run the any-hit opacity rule
+    uint32_t pad[4];
 };
 
 struct DScene {

@@ -6,8 +6,9 @@
 // number per ray seeded from the ray's bit pattern (hits/rt_gbuffer.hlsl:14-19).
 //
 // Determinism: a hit replaces the current best iff t < best || (t == best && id < best_id) with
-// id = (instance slot << 32 | primitive), and boxes are culled with t_near <= best, so the result
-// does not depend on traversal order — the kernel is free to reorder work.
+// id = (instance slot << 32 | primitive), and boxes are culled against tcull = best * (1 + 1e-5) (the slab
+// and triangle tests round differently by a few ulps; the margin guarantees that every candidate that can
+// still win is visited), so the result does not depend on traversal order — kernels may reorder work.
 //
 // Node fetch = four 16-B loads (64 B); triangle fetch = three 16-B loads (48 B).
 #pragma once
@@ -27,6 +28,7 @@ struct TraceResult {
 struct RayState {
     float3 O, D;          // world-space ray (opacity seed)
     float tmin, tbest;
+    float tcull;          // tbest * (1 + 1e-5): what boxes are culled against (order-independence, see header)
     uint32_t best_slot, best_prim;
     float bu, bv;
     uint32_t frame_index;
@@ -45,13 +47,12 @@ BPT_HD float ray_opacity_random(RayState& rs) {                 // hits/rt_gbuff
 }
 
 // true = keep the candidate (hits/rt_gbuffer_hit.hlsl:20-35)
+// Only reached for instances whose DInstance::anyhit flag is set (non-opaque instance AND non-opaque blend).
 BPT_HD bool anyhit_keep(const DScene& sc, RayState& rs, uint32_t slot, uint32_t prim, float u, float v) {
     const DInstance& in = sc.instances[slot];
-    if (!(in.flags & BPT_INSTANCE_FORCE_NON_OPAQUE)) return true;
     const bpt_drawable_sbt_data& dr = sc.drawables[in.instance_id];
     const bpt_material& m = sc.materials[dr.material_offset / (uint32_t)sizeof(bpt_material)];
     uint32_t blend = (m.flags >> BPT_MATERIAL_BLEND_SHIFT) & 0xffu;
-    if (blend == BPT_BLEND_OPAQUE) return true;
     float opacity = eval_hit_opacity(sc, in.instance_id, prim, u, v);
     if (blend == BPT_BLEND_ALPHA_TEST) return !(opacity < 0.01f);
     return !(ray_opacity_random(rs) < 1.0f - opacity);
@@ -59,7 +60,7 @@ BPT_HD bool anyhit_keep(const DScene& sc, RayState& rs, uint32_t slot, uint32_t 
 
 // Möller–Trumbore on the (v0, e1, e2) record; unfused arithmetic (see bpt_math.cuh header).
 template <bool ANY>
-BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, float3 O, float3 D, uint32_t slot_or_none) {
+BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, float3 O, float3 D, uint32_t slot_or_none, uint32_t instance_anyhit) {
     float4 a = BPT_LDG(tri), b = BPT_LDG(tri + 1), c = BPT_LDG(tri + 2);
     float3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
     float3 pvec = cross3(D, e2);
@@ -78,8 +79,10 @@ BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, flo
     uint32_t slot = slot_or_none == 0xffffffffu ? f2u(b.w) : slot_or_none;
     bool better = t < rs.tbest || (t == rs.tbest && (!rs.found || slot < rs.best_slot || (slot == rs.best_slot && prim < rs.best_prim)));
     if (!better) return false;
-    if (!anyhit_keep(sc, rs, slot, prim, u, v)) return false;
-    rs.tbest = t; rs.bu = u; rs.bv = v; rs.best_slot = slot; rs.best_prim = prim; rs.found = true;
+    // any-hit flag: per triangle (merged: e2.w) or per entered instance (two-level)
+    uint32_t need_anyhit = slot_or_none == 0xffffffffu ? f2u(c.w) : instance_anyhit;
+    if (need_anyhit && !anyhit_keep(sc, rs, slot, prim, u, v)) return false;
+    rs.tbest = t; rs.tcull = t * 1.00001f; rs.bu = u; rs.bv = v; rs.best_slot = slot; rs.best_prim = prim; rs.found = true;
     return true;
 }
 
@@ -96,7 +99,7 @@ BPT_HD RaySpace make_space(float3 O, float3 D) {
 
 // One node step: returns the next node to visit (or kSentinel+1 == "pop") and optionally pushes.
 #define BPT_POP ((int32_t)0x80000001)
-BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, float tmin, float tbest, int32_t* stack, int& sp) {
+BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, float tmin, float tcull, int32_t* stack, int& sp) {
     const float4* n = nodes + 4 * (size_t)cur;
     float4 n0 = BPT_LDG(n), n1 = BPT_LDG(n + 1), n2 = BPT_LDG(n + 2), n3 = BPT_LDG(n + 3);
     float c0lox = fmaf(n0.x, r.idir.x, -r.ood.x), c0hix = fmaf(n0.y, r.idir.x, -r.ood.x);
@@ -106,9 +109,9 @@ BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, fl
     float c0loz = fmaf(n2.x, r.idir.z, -r.ood.z), c0hiz = fmaf(n2.y, r.idir.z, -r.ood.z);
     float c1loz = fmaf(n2.z, r.idir.z, -r.ood.z), c1hiz = fmaf(n2.w, r.idir.z, -r.ood.z);
     float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-    float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tbest));
+    float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tcull));
     float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-    float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tbest));
+    float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tcull));
     bool h0 = t0n <= t0f, h1 = t1n <= t1f;
     int32_t ch0 = (int32_t)f2u(n3.x), ch1 = (int32_t)f2u(n3.y);
     if (h0 && h1) {
@@ -121,54 +124,84 @@ BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, fl
     return BPT_POP;
 }
 
+// ---- resumable traversal state -------------------------------------------------------------------
+// One ray's traversal as a small state machine so that the same steps serve (a) the simple
+// run-to-completion loop (trace_ray: ray batches, host-check) and (b) the persistent while-while
+// kernels of render.cu, which interleave steps of 32 rays per warp and refill finished lanes.
+struct Trav {
+    RayState rs;
+    RaySpace world, cur;
+    const float4* nodes;
+    const float4* tris;
+    uint32_t slot;          // instance slot of the BLAS being traversed; 0xffffffff = read it from the triangle (merged)
+    uint32_t inst_anyhit;   // DInstance::anyhit of that instance (two-level)
+    int32_t node;           // >= 0 internal node, < 0 leaf (~index)
+    int sp;
+    bool in_blas, done;
+};
+
+BPT_HD void trav_begin(const DScene& sc, Trav& t, float3 O, float3 D, float tmin, float tmax, uint32_t frame_index) {
+    t.rs.O = O; t.rs.D = D; t.rs.tmin = tmin; t.rs.tbest = tmax; t.rs.tcull = tmax * 1.00001f; t.rs.best_slot = 0xffffffffu; t.rs.best_prim = 0xffffffffu;
+    t.rs.bu = 0.0f; t.rs.bv = 0.0f; t.rs.frame_index = frame_index; t.rs.opacity_u = 0.0f; t.rs.have_u = false; t.rs.found = false;
+    const bool two_level = sc.accel_mode == BPT_ACCEL_TWO_LEVEL;
+    t.world = make_space(O, D);
+    t.cur = t.world;
+    t.nodes = two_level ? sc.tlas_nodes : sc.blas[0].nodes;
+    t.tris = two_level ? nullptr : sc.blas[0].tris;
+    t.slot = 0xffffffffu;
+    t.inst_anyhit = 0;
+    t.in_blas = !two_level;
+    t.node = two_level ? sc.tlas_root : sc.blas[0].root;
+    t.sp = 0;
+    t.done = (two_level ? sc.tlas_n : sc.blas[0].n) == 0;
+}
+BPT_HD void trav_pop(const DScene& sc, Trav& t, int32_t* stack) {
+    if (t.sp == 0) { t.done = true; return; }
+    t.node = stack[--t.sp];
+    if (t.node == kSentinel) {          // leaving an instance: back to the world-space ray and the TLAS
+        t.cur = t.world; t.nodes = sc.tlas_nodes; t.tris = nullptr; t.in_blas = false;
+        if (t.sp == 0) { t.done = true; return; }
+        t.node = stack[--t.sp];
+    }
+}
+BPT_HD void trav_node(const DScene& sc, Trav& t, int32_t* stack) {     // requires t.node >= 0
+    int32_t next = node_step(t.nodes, t.node, t.cur, t.rs.tmin, t.rs.tcull, stack, t.sp);
+    if (next != BPT_POP) t.node = next; else trav_pop(sc, t, stack);
+}
+template <bool ANY>
+BPT_HD void trav_leaf(const DScene& sc, Trav& t, int32_t* stack) {     // requires t.node < 0
+    if (t.in_blas) {
+        bool accepted = test_triangle<ANY>(sc, t.rs, t.tris + 3 * (size_t)(uint32_t)~t.node, t.cur.O, t.cur.D, t.slot, t.inst_anyhit);
+        if (ANY && accepted) { t.done = true; return; }
+        trav_pop(sc, t, stack);
+    } else {
+        // TLAS leaf: enter the instance (object-space ray, direction NOT renormalised so t is shared)
+        t.slot = BPT_LDG(sc.tlas_prims + (uint32_t)~t.node);
+        const DInstance& in = sc.instances[t.slot];
+        const DBlas& bl = sc.blas[in.blas];
+        t.inst_anyhit = in.anyhit;
+        t.cur = make_space(xf_point(in.w2o, t.rs.O), xf_vector(in.w2o, t.rs.D));
+        t.nodes = bl.nodes; t.tris = bl.tris; t.in_blas = true;
+        stack[t.sp++] = kSentinel;
+        t.node = bl.root;
+    }
+}
+BPT_HD TraceResult trav_result(const Trav& t) {
+    TraceResult res;
+    res.hit = t.rs.found; res.t = t.rs.found ? t.rs.tbest : -1.0f; res.u = t.rs.bu; res.v = t.rs.bv; res.slot = t.rs.best_slot; res.prim = t.rs.best_prim;
+    return res;
+}
+
 template <bool ANY>
 BPT_HD TraceResult trace_ray(const DScene& sc, float3 O, float3 D, float tmin, float tmax, uint32_t frame_index) {
-    RayState rs;
-    rs.O = O; rs.D = D; rs.tmin = tmin; rs.tbest = tmax; rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu;
-    rs.bu = 0.0f; rs.bv = 0.0f; rs.frame_index = frame_index; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
+    Trav t;
     int32_t stack[kStackSize];
-    int sp = 0;
-    const bool two_level = sc.accel_mode == BPT_ACCEL_TWO_LEVEL;
-    RaySpace world = make_space(O, D);
-    RaySpace cur_space = world;
-    const float4* nodes = two_level ? sc.tlas_nodes : sc.blas[0].nodes;
-    const float4* tris = two_level ? nullptr : sc.blas[0].tris;
-    uint32_t slot = 0xffffffffu;           // 0xffffffff: take the slot from the triangle record (merged)
-    bool in_blas = !two_level;
-    int32_t cur = two_level ? sc.tlas_root : sc.blas[0].root;
-    uint32_t nprims = two_level ? sc.tlas_n : sc.blas[0].n;
-    if (nprims != 0) {
-        for (;;) {
-            if (cur >= 0) {
-                cur = node_step(nodes, cur, cur_space, rs.tmin, rs.tbest, stack, sp);
-                if (cur != BPT_POP) continue;
-            } else if (in_blas) {
-                bool accepted = test_triangle<ANY>(sc, rs, tris + 3 * (size_t)(uint32_t)~cur, cur_space.O, cur_space.D, slot);
-                if (ANY && accepted) break;
-            } else {
-                // TLAS leaf: enter the instance (object-space ray, direction NOT renormalised so t is shared)
-                slot = BPT_LDG(sc.tlas_prims + (uint32_t)~cur);
-                const DInstance& in = sc.instances[slot];
-                const DBlas& bl = sc.blas[in.blas];
-                cur_space = make_space(xf_point(in.w2o, O), xf_vector(in.w2o, D));
-                nodes = bl.nodes; tris = bl.tris; in_blas = true;
-                stack[sp++] = kSentinel;
-                cur = bl.root;
-                continue;
-            }
-            // pop
-            if (sp == 0) break;
-            cur = stack[--sp];
-            if (cur == kSentinel) {
-                cur_space = world; nodes = sc.tlas_nodes; tris = nullptr; in_blas = false;
-                if (sp == 0) break;
-                cur = stack[--sp];
-            }
-        }
+    trav_begin(sc, t, O, D, tmin, tmax, frame_index);
+    while (!t.done) {
+        if (t.node >= 0) trav_node(sc, t, stack);
+        else trav_leaf<ANY>(sc, t, stack);
     }
-    TraceResult res;
-    res.hit = rs.found; res.t = rs.found ? rs.tbest : -1.0f; res.u = rs.bu; res.v = rs.bv; res.slot = rs.best_slot; res.prim = rs.best_prim;
-    return res;
+    return trav_result(t);
 }
 
 } // namespace bptd

@@ -45,7 +45,7 @@ __global__ void k_gather_tris(const float* __restrict__ positions, const uint32_
     size_t g = (size_t)out_base + k;
     raw[3 * g + 0] = make_float4(v[0].x, v[0].y, v[0].z, __uint_as_float(k));
     raw[3 * g + 1] = make_float4(v[1].x, v[1].y, v[1].z, __uint_as_float(slot));
-    raw[3 * g + 2] = make_float4(v[2].x, v[2].y, v[2].z, 0.0f);
+    raw[3 * g + 2] = make_float4(v[2].x, v[2].y, v[2].z, __uint_as_float(inst ? inst[slot].anyhit : 0u));
     float3 l = vmin(vmin(v[0], v[1]), v[2]), h = vmax(vmax(v[0], v[1]), v[2]);
     lo[g] = make_float4(l.x, l.y, l.z, 0.0f);
     hi[g] = make_float4(h.x, h.y, h.z, 0.0f);
@@ -249,11 +249,12 @@ __global__ void k_emit_tris(uint32_t n, const uint32_t* __restrict__ prims, cons
     float3 e1 = v3(b.x, b.y, b.z) - v0, e2 = v3(c.x, c.y, c.z) - v0;
     tris[3 * (size_t)j + 0] = a;                                            // v0 | prim
     tris[3 * (size_t)j + 1] = make_float4(e1.x, e1.y, e1.z, b.w);           // e1 | instance slot
-    tris[3 * (size_t)j + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+    tris[3 * (size_t)j + 2] = make_float4(e2.x, e2.y, e2.z, c.w);           // e2 | any-hit flag (merged mode)
 }
 
 // ---- instances ---------------------------------------------------------------------------------
-__global__ void k_make_instances(const bpt_instance_desc* __restrict__ desc, uint32_t n, DInstance* __restrict__ out) {
+__global__ void k_make_instances(const bpt_instance_desc* __restrict__ desc, uint32_t n, const bpt_drawable_sbt_data* __restrict__ drawables,
+                                 const bpt_material* __restrict__ materials, DInstance* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     DInstance d;
@@ -264,7 +265,10 @@ __global__ void k_make_instances(const bpt_instance_desc* __restrict__ desc, uin
     d.instance_id = desc[i].instance_id_and_mask & 0xffffffu;
     d.flags = desc[i].sbt_offset_and_flags >> 24;
     d.blas = (uint32_t)desc[i].blas;
-    for (int k = 0; k < 5; k++) d.pad[k] = 0;
+    for (int k = 0; k < 4; k++) d.pad[k] = 0;
+    // any-hit needed? (non-opaque instance AND a non-opaque blend mode: hits/rt_gbuffer_hit.hlsl:20-35, accel.cpp:112-116)
+    uint32_t blend = (materials[drawables[d.instance_id].material_offset / (uint32_t)sizeof(bpt_material)].flags >> BPT_MATERIAL_BLEND_SHIFT) & 0xffu;
+    d.anyhit = ((d.flags & BPT_INSTANCE_FORCE_NON_OPAQUE) && blend != BPT_BLEND_OPAQUE) ? 1u : 0u;
     out[i] = d;
 }
 // world AABB of an instance = min/max of the 8 transformed corners of its BLAS bounds
@@ -362,7 +366,8 @@ bpt_status upload_instance_table(bpt_context* ctx) {
     if ((s = dev_upload(ctx, desc, ctx->h_instances.data(), (size_t)n * sizeof(bpt_instance_desc)))) return s;
     dev_free(ctx->d_instances);
     if ((s = dev_alloc(ctx, ctx->d_instances, (size_t)n * sizeof(DInstance)))) { dev_free(desc); return s; }
-    k_make_instances<<<grid_for(n), kThreads, 0, ctx->stream>>>(desc.as<bpt_instance_desc>(), n, ctx->d_instances.as<DInstance>());
+    k_make_instances<<<grid_for(n), kThreads, 0, ctx->stream>>>(desc.as<bpt_instance_desc>(), n, ctx->d_drawables.as<bpt_drawable_sbt_data>(),
+                                                                 ctx->d_materials.as<bpt_material>(), ctx->d_instances.as<DInstance>());
     ctx->launches++;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     dev_free(desc);

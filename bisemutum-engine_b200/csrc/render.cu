@@ -19,6 +19,10 @@ namespace {
 constexpr int kBlock = 128;
 constexpr int QE = 0;      // qcount[QE + bounce]  : extend queue length of that bounce
 constexpr int QS = 32;     // qcount[QS + bounce]  : shadow queue length of that bounce
+constexpr int QWE = 64;    // qcount[QWE + bounce] : work-fetch cursor of the persistent extend kernel
+constexpr int QWS = 96;    // qcount[QWS + bounce] : work-fetch cursor of the persistent connect kernel
+constexpr int QN = 128;
+constexpr int kRefillThreshold = 20;   // refill a warp's finished lanes when fewer rays than this are still in flight
 
 struct RenderArgs {
     DScene sc;
@@ -34,6 +38,7 @@ struct RenderArgs {
     uint64_t shadow_capacity;
     uint32_t npx, nslots;     // pixels, samples in this wave; a path's id is slot * npx + pixel
     uint32_t frame_base;      // frame_index of slot 0
+    const float4* m_nodes; const float4* m_tris; int32_t m_root; uint32_t m_n;   // the single BVH of merged mode
 };
 
 // warp-aggregated append: returns the slot for this lane (valid only if `emit`)
@@ -65,15 +70,160 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
     a.color[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-// ---- extend (rt_gbuffer.hlsl:7-36): closest hit of every live path -----------------------------
-__global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ RenderArgs a, uint32_t bounce) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.qcount[QE + bounce]) return;
-    float4 o = a.ray_o_in[i], d = a.ray_d_in[i];
-    uint32_t frame = a.frame_base + __float_as_uint(o.w) / a.npx;
-    TraceResult r = trace_ray<false>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, a.sp.ray_length, frame);
-    a.hit[i] = make_float4(r.t, r.u, r.v, __uint_as_float(r.prim));
-    a.hit_slot[i] = r.slot;
+// ---- persistent while-while traversal (extend: rt_gbuffer.hlsl:7-36; connect: NEW shadow rays) ------
+// ncu on the one-thread-per-ray version showed 9.5/32 active lanes on incoherent bounces: rays of a warp
+// finish at very different times and node/leaf steps diverge. So: one resident grid, every warp keeps 32
+// traversal state machines and (a) runs all lanes through internal nodes until each holds a leaf
+// (while-while, leaf work is batched), (b) when fewer than kRefillThreshold rays are still in flight it
+// writes out the finished lanes and refills them from the queue (one atomicAdd per warp). Results do not
+// depend on the order (tie-break rule in bpt_trace.cuh).
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock) k_trace_persistent(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
+    uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
+    const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
+    const float4* __restrict__ qd = ANY ? a.sh_d : a.ray_d_in;
+    const uint32_t lane = threadIdx.x & 31;
+    int32_t stack[kStackSize];
+    Trav t;
+    t.done = true;
+    uint32_t ray = 0xffffffffu;       // queue index owned by this lane, or none
+    uint32_t path = 0;
+    bool exhausted = false;           // the queue has no more rays for this warp
+    for (;;) {
+        // ---- write out finished lanes, refill from the queue ----
+        if (ray != 0xffffffffu && t.done) {
+            if (ANY) {
+                if (!t.rs.found) {    // unoccluded: add the carried contribution to the path's per-sample colour
+                    float4 c = a.sh_c[ray];
+                    float* px = reinterpret_cast<float*>(a.color + path);
+                    atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+                }
+            } else {
+                a.hit[ray] = make_float4(t.rs.found ? t.rs.tbest : -1.0f, t.rs.bu, t.rs.bv, __uint_as_float(t.rs.best_prim));
+                a.hit_slot[ray] = t.rs.best_slot;
+            }
+            ray = 0xffffffffu;
+        }
+        if (!exhausted) {
+            bool want = ray == 0xffffffffu;
+            uint32_t mask = __ballot_sync(0xffffffffu, want);
+            if (mask) {
+                uint32_t base = 0;
+                if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(cursor, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+                if (want) {
+                    uint32_t idx = base + __popc(mask & ((1u << lane) - 1u));
+                    if (idx < n) {
+                        float4 o = qo[idx], d = qd[idx];
+                        ray = idx;
+                        path = __float_as_uint(o.w);
+                        trav_begin(a.sc, t, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, ANY ? d.w : a.sp.ray_length, a.frame_base + path / a.npx);
+                    }
+                }
+                if (base + (uint32_t)__popc(mask) >= n) exhausted = true;    // warp-uniform
+            }
+        }
+        if (__ballot_sync(0xffffffffu, ray != 0xffffffffu) == 0) break;
+        // ---- traverse ----
+        for (;;) {
+            while (!t.done && t.node >= 0) trav_node(a.sc, t, stack);
+            if (!t.done) trav_leaf<ANY>(a.sc, t, stack);
+            uint32_t alive = __ballot_sync(0xffffffffu, !t.done);
+            if (alive == 0) break;
+            if (!exhausted && __popc(alive) < kRefillThreshold) break;
+        }
+    }
+}
+
+// ---- merged-mode specialisation: speculative while-while (Aila & Laine 2009) -----------------------
+// One world-space BVH, no instance transitions, so the per-lane state is just (ray, node, postponed leaf,
+// stack). A lane that reaches a leaf POSTPONES it and keeps descending; the warp switches to the triangle
+// phase only when no lane is still searching, so both phases run with (nearly) all live lanes — the
+// one-step-at-a-time loop above measured 9.7/32 active lanes on incoherent bounces.
+constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this lane
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
+    uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
+    const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
+    const float4* __restrict__ qd = ANY ? a.sh_d : a.ray_d_in;
+    const float4* __restrict__ nodes = a.m_nodes;
+    const float4* __restrict__ tris = a.m_tris;
+    const uint32_t lane = threadIdx.x & 31;
+    int32_t stack[kStackSize];
+    RayState rs;
+    RaySpace sp_;
+    rs.found = false; rs.tbest = 0.0f; rs.tcull = 0.0f; rs.tmin = 0.001f;
+    int32_t node = kEmpty, leaf = 0;
+    int sp = 0;
+    uint32_t ray = 0xffffffffu, path = 0;
+    bool exhausted = false;
+    for (;;) {
+        if (ray != 0xffffffffu && node == kEmpty && leaf == 0) {          // finished: write out
+            if (ANY) {
+                if (!rs.found) {
+                    float4 c = a.sh_c[ray];
+                    float* px = reinterpret_cast<float*>(a.color + path);
+                    atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+                }
+            } else {
+                a.hit[ray] = make_float4(rs.found ? rs.tbest : -1.0f, rs.bu, rs.bv, __uint_as_float(rs.best_prim));
+                a.hit_slot[ray] = rs.best_slot;
+            }
+            ray = 0xffffffffu;
+        }
+        if (!exhausted) {                                                  // refill idle lanes, one atomic per warp
+            bool want = ray == 0xffffffffu;
+            uint32_t mask = __ballot_sync(0xffffffffu, want);
+            if (mask) {
+                uint32_t base = 0;
+                if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(cursor, (uint32_t)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+                if (want) {
+                    uint32_t idx = base + __popc(mask & ((1u << lane) - 1u));
+                    if (idx < n) {
+                        float4 o = qo[idx], d = qd[idx];
+                        ray = idx;
+                        path = __float_as_uint(o.w);
+                        rs.O = v3(o.x, o.y, o.z); rs.D = v3(d.x, d.y, d.z);
+                        rs.tmin = 0.001f; rs.tbest = ANY ? d.w : a.sp.ray_length; rs.tcull = rs.tbest * 1.00001f;
+                        rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu; rs.bu = 0.0f; rs.bv = 0.0f;
+                        rs.frame_index = a.frame_base + path / a.npx; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
+                        sp_ = make_space(rs.O, rs.D);
+                        sp = 0; leaf = 0;
+                        node = a.m_n == 0 ? kEmpty : a.m_root;
+                        if (node < 0) { leaf = node; node = kEmpty; }      // single-triangle BVH: the root is a leaf
+                    }
+                }
+                if (base + (uint32_t)__popc(mask) >= n) exhausted = true;  // warp-uniform
+            }
+        }
+        if (__ballot_sync(0xffffffffu, ray != 0xffffffffu) == 0) break;
+        for (;;) {
+            // ---- node phase: until no lane is still searching for its first leaf ----
+            for (;;) {
+                if (node >= 0 && node != kEmpty) {
+                    int32_t next = node_step(nodes, node, sp_, rs.tmin, rs.tcull, stack, sp);
+                    if (next == BPT_POP) next = sp ? stack[--sp] : kEmpty;
+                    node = next;
+                    if (node < 0 && leaf == 0) { leaf = node; node = sp ? stack[--sp] : kEmpty; }   // postpone, keep descending
+                }
+                bool searching = leaf == 0 && node >= 0 && node != kEmpty;
+                if (!__any_sync(0xffffffffu, searching)) break;
+            }
+            // ---- triangle phase ----
+            while (leaf != 0) {
+                bool accepted = test_triangle<ANY>(a.sc, rs, tris + 3 * (size_t)(uint32_t)~leaf, rs.O, rs.D, 0xffffffffu, 0u);
+                leaf = 0;
+                if (ANY && accepted) { node = kEmpty; sp = 0; break; }
+                if (node < 0) { leaf = node; node = sp ? stack[--sp] : kEmpty; }
+            }
+            uint32_t alive = __ballot_sync(0xffffffffu, node != kEmpty);
+            if (alive == 0) break;
+            if (!exhausted && __popc(alive) < kRefillThreshold) break;
+        }
+    }
 }
 
 // ---- shade: material + lighting + next direction, emits shadow rays and the next extend ray ---
@@ -96,7 +246,7 @@ struct KernelSink {
     }
 };
 
-__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+__global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < a.qcount[QE + bounce];
     bool cont = false;
@@ -117,20 +267,6 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ Render
         a.ray_d_out[slot] = make_float4(nD.x, nD.y, nD.z, 0.0f);
         a.ray_w_out[slot] = make_float4(nW.x, nW.y, nW.z, 0.0f);
     }
-}
-
-// ---- connect: any-hit shadow rays; unoccluded contributions are added to the pixel -------------
-__global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ RenderArgs a, uint32_t bounce) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n = a.qcount[QS + bounce];
-    if (i >= n || i >= a.shadow_capacity) return;
-    float4 o = a.sh_o[i], d = a.sh_d[i];
-    uint32_t path = __float_as_uint(o.w);
-    TraceResult r = trace_ray<true>(a.sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, d.w, a.frame_base + path / a.npx);
-    if (r.hit) return;
-    float4 c = a.sh_c[i];
-    float* px = reinterpret_cast<float*>(a.color + path);
-    atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
 }
 
 // ---- per-sample bookkeeping: queue lengths → 64-bit totals -------------------------------------
@@ -241,7 +377,7 @@ bpt_status wavefront_alloc(bpt_context* ctx) {
         wf.shadow_capacity = 0;
     }
     if (!wf.qcount.p) {
-        if ((s = dev_alloc(ctx, wf.qcount, 64 * sizeof(uint32_t)))) return s;
+        if ((s = dev_alloc(ctx, wf.qcount, QN * sizeof(uint32_t)))) return s;
         if ((s = dev_alloc(ctx, wf.totals, 40 * sizeof(uint64_t)))) return s;
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.totals.p, 0, 40 * sizeof(uint64_t), ctx->stream));
     }
@@ -260,7 +396,7 @@ bpt_status wavefront_alloc(bpt_context* ctx) {
 
 static bpt_status capture_bounce(bpt_context* ctx, uint32_t bounce, int in_buf) {
     WavefrontState& wf = ctx->wf;
-    uint32_t qc[64];
+    uint32_t qc[QN];
     BPT_CUDA_TRY(ctx, cudaMemcpyAsync(qc, wf.qcount.p, sizeof(qc), cudaMemcpyDeviceToHost, ctx->stream));
     BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     uint32_t ne = qc[QE + bounce], ns = qc[QS + bounce];
@@ -303,7 +439,22 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
     a.sh_o = wf.sh_o.as<float4>(); a.sh_d = wf.sh_d.as<float4>(); a.sh_c = wf.sh_c.as<float4>();
     a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();
     a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
-    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point, 1);
+    if (!wf.grid_extend) {      // resident grids of the persistent traversal kernels: SMs x blocks that fit per SM
+        int dev = 0, sms = 0, be = 0, ba = 0;
+        BPT_CUDA_TRY(ctx, cudaGetDevice(&dev));
+        BPT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_persistent<true>, kBlock, 0));
+        wf.grid_extend = (unsigned)(sms * std::max(be, 1)); wf.grid_connect = (unsigned)(sms * std::max(ba, 1));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_merged<false>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_merged<true>, kBlock, 0));
+        wf.grid_extend_m = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_m = (unsigned)(sms * std::max(ba, 1));
+    }
+    const bool merged = ctx->accel_mode == BPT_ACCEL_MERGED;
+    if (merged) {
+        a.m_nodes = ctx->blas[0].nodes.as<float4>(); a.m_tris = ctx->blas[0].tris.as<float4>(); a.m_root = ctx->blas[0].root; a.m_n = ctx->blas[0].n;
+    } else { a.m_nodes = nullptr; a.m_tris = nullptr; a.m_root = 0; a.m_n = 0; }
+    const unsigned persistent_grid = wf.grid_extend, persistent_grid_any = wf.grid_connect;
     const bool capture = ctx->capture && nsamples == 1;
     if (capture) {
         ctx->cap_bounces = B;
@@ -316,7 +467,7 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         const unsigned grid_paths = (unsigned)((paths + kBlock - 1) / kBlock);
         a.nslots = slots;
         a.frame_base = frame_first + done;
-        BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.qcount.p, 0, 64 * sizeof(uint32_t), ctx->stream));
+        BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream));
         int cur = 0;
         auto bind = [&](int in, int out) {
             a.ray_o_in = wf.ray_o[in].as<float4>(); a.ray_d_in = wf.ray_d[in].as<float4>(); a.ray_w_in = wf.ray_w[in].as<float4>();
@@ -326,12 +477,12 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         LAUNCH_T(ctx, 0, k_raygen, grid_paths, kBlock, a);
         for (uint32_t i = 1; i < B; i++) {
             bind(cur, cur ^ 1);
-            LAUNCH_T(ctx, 1, k_extend, grid_paths, kBlock, a, i);
+            if (merged) LAUNCH_T(ctx, 1, k_trace_merged<false>, wf.grid_extend_m, kBlock, a, i);
+            else LAUNCH_T(ctx, 1, k_trace_persistent<false>, persistent_grid, kBlock, a, i);
             LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
             if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
-                // the shadow queue holds at most (live paths x lights) rays; the grid covers the bound
-                uint64_t bound = paths * nl;
-                LAUNCH_T(ctx, 3, k_connect, (unsigned)((bound + kBlock - 1) / kBlock), kBlock, a, i);
+                if (merged) LAUNCH_T(ctx, 3, k_trace_merged<true>, wf.grid_connect_m, kBlock, a, i);
+                else LAUNCH_T(ctx, 3, k_trace_persistent<true>, persistent_grid_any, kBlock, a, i);
             }
             if (capture && (s = capture_bounce(ctx, i, cur))) return s;
             cur ^= 1;

@@ -262,11 +262,19 @@ bool build_accel(Scene& sc, uint32_t mode, std::string& err) {
 
 // ---------------------------------------------------------------------------------------------
 // Traversal
+//
+// Result rule (what makes the answer independent of traversal ORDER, so the GPU may reorder work):
+//   * a candidate replaces the best iff t < tbest || (t == tbest && id < best_id), id = (slot << 32 | prim);
+//   * a box is entered iff t_near <= min(t_far, tcull) with tcull = tbest * (1 + 1e-5). The slab test and the
+//     triangle test round differently (a few ulps), so culling against tbest itself could skip the box of an
+//     equal-t (shared edge) or few-ulp-closer candidate depending on which was found first; the 1e-5 margin
+//     (~84 ulps) guarantees every candidate that can still win is visited in any order.
 // ---------------------------------------------------------------------------------------------
 struct RayCtx {
     f3 O, D;             // world ray (opacity seed, rt_gbuffer.hlsl:24)
     float tmin;
     float tbest;
+    float tcull;         // tbest * (1 + 1e-5): boxes are culled against this, see trace rule below
     uint64_t best_id;    // (instance slot << 32 | prim), tie-break on equal t
     float bu, bv;
     uint32_t best_slot, best_prim;
@@ -315,7 +323,7 @@ static inline void tri_test(const Scene& sc, RayCtx& rc, const Tri& tr, f3 O, f3
     uint64_t id = ((uint64_t)slot << 32) | tr.prim;
     if (!(t < rc.tbest || (t == rc.tbest && id < rc.best_id))) return;
     if (!anyhit_accept(sc, rc, slot, tr.prim, u, v)) return;
-    rc.tbest = t; rc.best_id = id; rc.bu = u; rc.bv = v; rc.best_slot = slot; rc.best_prim = tr.prim;
+    rc.tbest = t; rc.tcull = t * 1.00001f; rc.best_id = id; rc.bu = u; rc.bv = v; rc.best_slot = slot; rc.best_prim = tr.prim;
     if (rc.any_mode) rc.terminated = true;
 }
 
@@ -346,9 +354,9 @@ static inline void traverse(const Bvh& b, f3 O, f3 D, RayCtx& rc, TraceStats& st
             float c1loy = fmaf(n.c1_lo_y, idir.y, -ood.y), c1hiy = fmaf(n.c1_hi_y, idir.y, -ood.y);
             float c1loz = fmaf(n.c1_lo_z, idir.z, -ood.z), c1hiz = fmaf(n.c1_hi_z, idir.z, -ood.z);
             float t0n = fmax_(fmax_(fmin_(c0lox, c0hix), fmin_(c0loy, c0hiy)), fmax_(fmin_(c0loz, c0hiz), rc.tmin));
-            float t0f = fmin_(fmin_(fmax_(c0lox, c0hix), fmax_(c0loy, c0hiy)), fmin_(fmax_(c0loz, c0hiz), rc.tbest));
+            float t0f = fmin_(fmin_(fmax_(c0lox, c0hix), fmax_(c0loy, c0hiy)), fmin_(fmax_(c0loz, c0hiz), rc.tcull));
             float t1n = fmax_(fmax_(fmin_(c1lox, c1hix), fmin_(c1loy, c1hiy)), fmax_(fmin_(c1loz, c1hiz), rc.tmin));
-            float t1f = fmin_(fmin_(fmax_(c1lox, c1hix), fmax_(c1loy, c1hiy)), fmin_(fmax_(c1loz, c1hiz), rc.tbest));
+            float t1f = fmin_(fmin_(fmax_(c1lox, c1hix), fmax_(c1loy, c1hiy)), fmin_(fmax_(c1loz, c1hiz), rc.tcull));
             bool h0 = t0n <= t0f, h1 = t1n <= t1f;
             if (h0 && h1) {
                 bool c0_near = t0n <= t1n;
@@ -388,7 +396,7 @@ static void trace_generic(const Scene& sc, RayCtx& rc, TraceStats& st) {
 
 HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st) {
     RayCtx rc{};
-    rc.O = O; rc.D = D; rc.tmin = tmin; rc.tbest = tmax; rc.best_id = ~0ull;
+    rc.O = O; rc.D = D; rc.tmin = tmin; rc.tbest = tmax; rc.tcull = tmax * 1.00001f; rc.best_id = ~0ull;
     rc.any_mode = false; rc.terminated = false; rc.frame_index = frame_index; rc.have_u = false;
     trace_generic(sc, rc, st);
     HitRec h{};
@@ -402,7 +410,7 @@ HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32
 
 bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st) {
     RayCtx rc{};
-    rc.O = O; rc.D = D; rc.tmin = tmin; rc.tbest = tmax; rc.best_id = ~0ull;
+    rc.O = O; rc.D = D; rc.tmin = tmin; rc.tbest = tmax; rc.tcull = tmax * 1.00001f; rc.best_id = ~0ull;
     rc.any_mode = true; rc.terminated = false; rc.frame_index = frame_index; rc.have_u = false;
     trace_generic(sc, rc, st);
     return rc.terminated;  // true = occluded

@@ -54,6 +54,8 @@ void build(const hc_scene& h, Built& b) {
         d.instance_id = h.instances[i].instance_id_and_mask & 0xffffffu;
         d.flags = h.instances[i].sbt_offset_and_flags >> 24;
         d.blas = (uint32_t)h.instances[i].blas;
+        uint32_t blend = (h.materials[h.drawables[d.instance_id].material_offset / sizeof(bpt_material)].flags >> BPT_MATERIAL_BLEND_SHIFT) & 0xffu;
+        d.anyhit = ((d.flags & BPT_INSTANCE_FORCE_NON_OPAQUE) && blend != BPT_BLEND_OPAQUE) ? 1u : 0u;
     }
     auto vert = [&](const bpt_blas_desc& bd, uint32_t k, int c) {
         uint32_t idx = h.indices[(size_t)bd.index_offset + 3ull * k + c];
@@ -85,7 +87,7 @@ void build(const hc_scene& h, Built& b) {
             const bpt_blas_desc& bd = h.blas_desc[b.inst[s].blas];
             float3 v0 = xf_point(b.inst[s].o2w, vert(bd, k, 0)), v1 = xf_point(b.inst[s].o2w, vert(bd, k, 1)), v2 = xf_point(b.inst[s].o2w, vert(bd, k, 2));
             float3 e1 = v1 - v0, e2 = v2 - v0;
-            b.tris[0][3 * j] = f4(v0.x, v0.y, v0.z, k); b.tris[0][3 * j + 1] = f4(e1.x, e1.y, e1.z, s); b.tris[0][3 * j + 2] = f4(e2.x, e2.y, e2.z, 0);
+            b.tris[0][3 * j] = f4(v0.x, v0.y, v0.z, k); b.tris[0][3 * j + 1] = f4(e1.x, e1.y, e1.z, s); b.tris[0][3 * j + 2] = f4(e2.x, e2.y, e2.z, b.inst[s].anyhit);
         }
     }
     for (uint32_t bi = 0; bi < nb; bi++)
