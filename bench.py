@@ -256,19 +256,33 @@ def main():
         lights_bytes = scene.dir_lights.nbytes + scene.point_lights.nbytes + scene.rect_lights.nbytes
         h2d = lights_bytes + 3 * 64 + 32            # lights (update_params) + camera matrices + settings
         d2h = W * H * 16
-        e2e_steps = max(4, min(args.steps, 32))
+        e2e_steps = max(8, min(args.steps, 64))
         for i in range(3):
             r.ctx.upload_lights(scene); r.frame(RAY_LENGTH, B, True)
         r.ctx.sync(); r.ctx.reset_counters()
         barrier()
+        host_imgs = [host_img, torch.empty(H, W, 4, dtype=torch.float32).pin_memory()]
+        dev_imgs = [dev_img, torch.empty(H, W, 4, dtype=torch.float32, device="cuda")]
+        copy_stream = torch.cuda.Stream()
+        done = [None, None]
         t0 = time.perf_counter()
         n = 0
         for i in range(e2e_steps):
+            b = i & 1
+            if done[b] is not None:
+                done[b].synchronize()                       # the host buffer of frame i-2 has landed
             r.ctx.upload_lights(scene)                      # PathTracingPass::update_params: per-frame H2D of the light arrays
             n = r.frame(RAY_LENGTH, B, True)                # Camera::update_shader_params + PathTracingPass::render + RenderGraph::execute
-            r.ctx.resolve_device(n, dev_img.data_ptr())     # the frame's result ...
-            host_img.copy_(dev_img, non_blocking=True)      # ... read back to pinned host memory
-            stream.synchronize()
+            r.ctx.resolve_device(n, dev_imgs[b].data_ptr()) # the frame's result ...
+            ready = torch.cuda.Event(); ready.record(stream)
+            with torch.cuda.stream(copy_stream):            # ... read back to pinned host memory while the next frame renders
+                copy_stream.wait_event(ready)
+                host_imgs[b].copy_(dev_imgs[b], non_blocking=True)
+                done[b] = torch.cuda.Event(); done[b].record(copy_stream)
+        for ev in done:
+            if ev is not None:
+                ev.synchronize()
+        stream.synchronize()
         barrier()
         dt = time.perf_counter() - t0
         ec = r.ctx.counters()

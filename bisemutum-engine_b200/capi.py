@@ -167,6 +167,9 @@ BPT_ONLY_API = {
     "resolve_device": [_VP, _U32, _VP],
     "accum_device_ptr": [_VP, C.POINTER(_VP)],
     "upload_accum": [_VP, _VP],
+    "render_ahead": [_VP, C.POINTER(Camera), _U32, _U32, C.POINTER(Settings), _PU32],
+    "accumulate_ahead": [_VP, _U32],
+    "pending_ahead": [_VP, _PU32, _PU32],
     "profile_enable": [_VP, _U32],
     "profile_read": [_VP, C.POINTER(KernelTimes)],
 }

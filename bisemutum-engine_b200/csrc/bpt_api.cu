@@ -168,6 +168,13 @@ bpt_status bpt_scene_upload_lights(bpt_context* c, const bpt_dir_light_data* d, 
     NEED(c);
     if ((nd && !d) || (np && !p) || (nr && !r)) return fail(c, BPT_ERR_INVALID, "lights: null array");
     bpt_status s;
+    if (nd == c->num_dir && np == c->num_point && nr == c->num_rect && c->d_dir.p && (!nr || c->d_ltc[0].p)) {
+        // per-frame refresh (PathTracingPass::update_params): same counts → overwrite in place, stream-ordered
+        if (nd) BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_dir.p, d, (size_t)nd * sizeof(*d), cudaMemcpyHostToDevice, c->stream));
+        if (np) BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_point.p, p, (size_t)np * sizeof(*p), cudaMemcpyHostToDevice, c->stream));
+        if (nr) BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_rect.p, r, (size_t)nr * sizeof(*r), cudaMemcpyHostToDevice, c->stream));
+        return BPT_OK;
+    }
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if ((s = dev_upload(c, c->d_dir, d, (size_t)nd * sizeof(*d)))) return s;
     if ((s = dev_upload(c, c->d_point, p, (size_t)np * sizeof(*p)))) return s;
@@ -271,6 +278,7 @@ bpt_status bpt_debug_read_bvh(bpt_context* c, uint32_t which, uint32_t* np, uint
 
 bpt_status bpt_clear_accum(bpt_context* c) {
     NEED(c);
+    c->wf.ahead_slots = c->wf.ahead_cursor = 0;
     BPT_CUDA_TRY(c, cudaMemsetAsync(c->wf.accum.p, 0, (size_t)c->width * c->height * 16, c->stream));
     return BPT_OK;
 }
@@ -282,6 +290,24 @@ bpt_status bpt_render(bpt_context* c, const bpt_camera* cam, uint32_t first, uin
     if (st->state_precision != BPT_STATE_FP32 || st->russian_roulette || st->pixel_jitter || st->rect_shadow)
         return fail(c, BPT_ERR_UNSUPPORTED, "mode switch not implemented");
     return wavefront_render(c, *cam, first, ns, *st);
+}
+
+bpt_status bpt_render_ahead(bpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t max_samples, const bpt_settings* st, uint32_t* out_samples) {
+    NEED(c);
+    if (!cam || !st || !max_samples) return BPT_ERR_INVALID;
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
+    if (st->state_precision != BPT_STATE_FP32 || st->russian_roulette || st->pixel_jitter || st->rect_shadow)
+        return fail(c, BPT_ERR_UNSUPPORTED, "mode switch not implemented");
+    bpt_status s = wavefront_render(c, *cam, first, max_samples, *st, true);
+    if (out_samples) *out_samples = c->wf.ahead_slots;
+    return s;
+}
+bpt_status bpt_accumulate_ahead(bpt_context* c, uint32_t count) { NEED(c); return wavefront_accumulate_ahead(c, count); }
+bpt_status bpt_pending_ahead(bpt_context* c, uint32_t* pending, uint32_t* next_frame) {
+    NEED(c);
+    if (pending) *pending = c->wf.ahead_slots - c->wf.ahead_cursor;
+    if (next_frame) *next_frame = c->wf.ahead_frame_first + c->wf.ahead_cursor;
+    return BPT_OK;
 }
 
 bpt_status bpt_resolve_device(bpt_context* c, uint32_t total, float* d_out) {

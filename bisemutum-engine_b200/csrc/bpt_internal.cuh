@@ -26,6 +26,7 @@ struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through 
     uint64_t capacity = 0;  // paths in flight = slots * width * height
     uint32_t npx = 0, slots = 1;
     DevBuf color;           // float4 per path: per-sample colour C_s
+    uint32_t ahead_slots = 0, ahead_cursor = 0, ahead_frame_first = 0;   // prefetched samples still in `color`
     unsigned grid_extend = 0, grid_connect = 0, grid_extend_m = 0, grid_connect_m = 0;   // resident grid sizes of the persistent traversal kernels
     DevBuf ray_o[2], ray_d[2], ray_w[2];   // float4 each: (O|pixel), (D|-), (W|-)
     DevBuf hit;             // float4 (t,u,v,prim)
@@ -105,6 +106,7 @@ bpt_status upload_instance_table(bpt_context* ctx);
 
 // render.cu
 bpt_status wavefront_alloc(bpt_context* ctx);
-bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st);
+bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st, bool keep_ahead = false);
+bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count);
 bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out);
 bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t n, uint32_t frame_index, bpt_hit* h_hits, uint8_t* h_visible);

@@ -278,11 +278,11 @@ __global__ void k_tally(const uint32_t* __restrict__ qcount, uint64_t* __restric
 }
 
 // ---- accumulate (pt_accumulate.hlsl:3-11 as FP32 sum): sum[p] += C_s[p], slots in ascending order ---
-__global__ void k_accumulate(const float4* __restrict__ color, float4* __restrict__ accum, uint32_t npx, uint32_t nslots) {
+__global__ void k_accumulate(const float4* __restrict__ color, float4* __restrict__ accum, uint32_t npx, uint32_t slot_begin, uint32_t slot_end) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npx) return;
     float4 v = accum[p];
-    for (uint32_t s = 0; s < nslots; s++) {
+    for (uint32_t s = slot_begin; s < slot_end; s++) {
         float4 c = color[(size_t)s * npx + p];
         v.x += c.x; v.y += c.y; v.z += c.z;
     }
@@ -424,10 +424,12 @@ static bpt_status capture_bounce(bpt_context* ctx, uint32_t bounce, int in_buf) 
     return BPT_OK;
 }
 
-bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st) {
+bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st, bool keep_ahead) {
     bpt_status s;
     if ((s = wavefront_alloc(ctx))) return s;
     WavefrontState& wf = ctx->wf;
+    wf.ahead_slots = wf.ahead_cursor = 0;         // the colour buffer is about to be overwritten
+    if (keep_ahead) nsamples = std::min(nsamples, wf.slots);
     const uint32_t npx = ctx->width * ctx->height;
     const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);           // path_tracing.cpp:187,290
     RenderArgs a;
@@ -487,10 +489,20 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
             if (capture && (s = capture_bounce(ctx, i, cur))) return s;
             cur ^= 1;
         }
-        LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, slots);
+        if (keep_ahead) { wf.ahead_slots = slots; wf.ahead_cursor = 0; wf.ahead_frame_first = frame_first; }
+        else LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, 0u, slots);
         LAUNCH_T(ctx, 4, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), (uint32_t)paths);
         done += slots;
     }
+    return BPT_OK;
+}
+
+bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count) {
+    WavefrontState& wf = ctx->wf;
+    if (count == 0 || wf.ahead_cursor + count > wf.ahead_slots) { ctx->err = "accumulate_ahead: not enough prefetched samples"; return BPT_ERR_STATE; }
+    const uint32_t npx = ctx->width * ctx->height;
+    LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, wf.ahead_cursor, wf.ahead_cursor + count);
+    wf.ahead_cursor += count;
     return BPT_OK;
 }
 

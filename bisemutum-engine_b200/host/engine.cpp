@@ -164,8 +164,20 @@ auto PathTracingPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, In
             st.ray_length = settings.ray_length;
             st.max_bounces = settings.max_bounces;
             st.accumulate = settings.accumulate;
-            if (reset) status_ = bpt_clear_accum(ctx_);
-            if (status_ == BPT_OK) status_ = bpt_render(ctx_, &cam, camera.frame_index(), 1, &st);
+            if (reset) status_ = bpt_clear_accum(ctx_);                       // also drops prefetched samples
+            if (status_ != BPT_OK) return;
+            // Sample prefetch: while the history is valid the next frames will ask for frame_index+1, +2, ...
+            // with the same camera, so a whole wave of samples is traced at once and handed out one per frame.
+            // The accumulated image is bit-identical to tracing one sample per frame.
+            uint32_t pending = 0, next = 0;
+            bpt_pending_ahead(ctx_, &pending, &next);
+            bool same_settings = std::memcmp(&st, &ahead_settings_, sizeof(st)) == 0;
+            if (pending == 0 || next != camera.frame_index() || !same_settings) {
+                uint32_t depth = settings.accumulate ? prefetch_frames_ : 1u;
+                status_ = bpt_render_ahead(ctx_, &cam, camera.frame_index(), depth, &st, nullptr);
+                ahead_settings_ = st;
+            }
+            if (status_ == BPT_OK) status_ = bpt_accumulate_ahead(ctx_, 1);
         });
     return out;
 }

@@ -178,8 +178,11 @@ private:
     bpt_context* ctx_;
     bpt_status status_ = BPT_OK;
     uint64_t frame_counter_ = 0;      // stands in for g_engine->window()->frame_count()
+    uint32_t prefetch_frames_ = 8;    // samples traced per wave when the history is valid (clamped by the library)
+    bpt_settings ahead_settings_{};
 public:
     auto set_frame_count(uint64_t f) -> void { frame_counter_ = f; }
+    auto set_prefetch_frames(uint32_t n) -> void { prefetch_frames_ = n ? n : 1; }
 };
 
 } // namespace bi

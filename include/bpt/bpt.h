@@ -300,6 +300,17 @@ BPT_API bpt_status bpt_clear_accum(bpt_context* ctx);
 BPT_API bpt_status bpt_render(
     bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index_first, uint32_t num_samples,
     const bpt_settings* settings);
+/* Sample prefetch for frame-at-a-time callers (the reference renders ONE sample per engine frame and
+ * accumulates while the camera is static, path_tracing.cpp:231-246): bpt_render_ahead traces up to
+ * `max_samples` consecutive samples (frame_index_first, +1, ...) in one wave and keeps their per-sample
+ * colours; bpt_accumulate_ahead then adds the next `count` of them to the sum buffer, in frame order.
+ * The image after k accumulated frames is bit-identical to k calls of bpt_render(.., 1, ..). Any other
+ * render / clear / resize call drops the pending samples. `*out_samples` = samples actually traced. */
+BPT_API bpt_status bpt_render_ahead(
+    bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index_first, uint32_t max_samples,
+    const bpt_settings* settings, uint32_t* out_samples);
+BPT_API bpt_status bpt_accumulate_ahead(bpt_context* ctx, uint32_t count);
+BPT_API bpt_status bpt_pending_ahead(bpt_context* ctx, uint32_t* out_pending, uint32_t* out_next_frame_index);
 /* out[p] = (sum[p].rgb * (1/total_samples), 1). Host destination (synchronises). */
 BPT_API bpt_status bpt_resolve(bpt_context* ctx, uint32_t total_samples, float* out_rgba32f);
 /* Same, written to device memory (no synchronisation). */
