@@ -14,6 +14,7 @@ bpt_status dev_alloc(bpt_context* ctx, DevBuf& b, size_t bytes) {
     if (e != cudaSuccess) {
         ctx->err = std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e);
         b.p = nullptr;
+        (void)cudaGetLastError();      // clear the sticky last-error so a later launch check does not report it
         return e == cudaErrorMemoryAllocation ? BPT_ERR_OOM : BPT_ERR_CUDA;
     }
     b.bytes = bytes;

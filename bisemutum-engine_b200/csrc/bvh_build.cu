@@ -303,7 +303,13 @@ struct Scratch {
     do {                                                                        \
         kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);             \
         (ctx)->launches++;                                                      \
-        BPT_CUDA_TRY(ctx, cudaGetLastError());                                  \
+        {                                                                       \
+            cudaError_t le__ = cudaGetLastError();                              \
+            if (le__ != cudaSuccess) {                                          \
+                (ctx)->err = std::string("launch of " #kernel " (grid ") + std::to_string((unsigned long long)(grid)) + "): " + cudaGetErrorString(le__); \
+                return BPT_ERR_CUDA;                                            \
+            }                                                                   \
+        }                                                                       \
     } while (0)
 
 bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi) {
@@ -402,6 +408,11 @@ bpt_status build_blas_merged(bpt_context* ctx) {
     for (auto& in : ctx->h_instances) total += ctx->h_blas_desc[(uint32_t)in.blas].num_triangles;
     if (total == 0 || total > 0x7fffffffull) { ctx->err = "merged accel: triangle count out of range"; return BPT_ERR_INVALID; }
     uint32_t n = (uint32_t)total;
+    {   // refuse up front when the merged soup cannot fit (build scratch + result ≈ 300 B per triangle)
+        size_t free_b = 0, total_b = 0;
+        BPT_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        if ((double)total * 300.0 > (double)free_b) { ctx->err = "merged accel: not enough device memory for the flattened scene; use BPT_ACCEL_TWO_LEVEL"; return BPT_ERR_OOM; }
+    }
     Scratch sc; DevBuf raw, lo, hi; bpt_status s;
     if ((s = sc.get(ctx, raw, (size_t)n * 48))) return s;
     if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;

@@ -322,7 +322,13 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ 
     do {                                                                        \
         kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);             \
         (ctx)->launches++;                                                      \
-        BPT_CUDA_TRY(ctx, cudaGetLastError());                                  \
+        {                                                                       \
+            cudaError_t le__ = cudaGetLastError();                              \
+            if (le__ != cudaSuccess) {                                          \
+                (ctx)->err = std::string("launch of " #kernel " (grid ") + std::to_string((unsigned long long)(grid)) + "): " + cudaGetErrorString(le__); \
+                return BPT_ERR_CUDA;                                            \
+            }                                                                   \
+        }                                                                       \
     } while (0)
 
 // LAUNCH with optional event bracketing (bpt_profile_enable): class 0 raygen, 1 extend, 2 shade, 3 connect, 4 other

@@ -494,3 +494,36 @@ def load_ltc_luts(npz_path: str):
 def mixed_lights(ltc_luts, seed: int = ATRIUM_SEED) -> SceneData:
     """configs[2]: the atrium with 64 point/spot lights + 16 LTC rect lights."""
     return add_mixed_lights(atrium(seed), 64, 16, ltc_luts, seed=seed & 0xffff)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: one large mesh x many instances (two-level BVH). Full size: a displaced
+# sphere of 2048 x 512 quads = 2 097 152 triangles, 512 instances on a jittered 8x8x8 grid with
+# random rotations (SURVEY §8d config 4). Smaller parameters give the parity-test version.
+# ---------------------------------------------------------------------------------------------
+INSTANCED_SEED = 0x1257A9CE
+
+
+def instanced(mesh_seg: int = 2048, mesh_ring: int = 512, grid: int = 8, seed: int = INSTANCED_SEED, sky_size: int = 64) -> SceneData:
+    rng = np.random.default_rng(seed)
+    b = SceneBuilder(f"instanced_{mesh_seg * mesh_ring * 2}x{grid ** 3}")
+    mats = [b.add_material(tuple(rng.uniform(0.1, 0.9, 3)), roughness=float(rng.uniform(0.15, 1.0)),
+                           metallic=1.0 if rng.uniform() < 0.25 else 0.0) for _ in range(16)]
+    mesh = b.add_mesh(sphere_mesh(1.0, mesh_seg, mesh_ring, bumps=0.18, seed=seed & 0xffff))
+    spacing = 3.4
+    half = (grid - 1) * spacing * 0.5
+    k = 0
+    for ix in range(grid):
+        for iy in range(grid):
+            for iz in range(grid):
+                c = np.array([ix, iy, iz]) * spacing - half + rng.uniform(-0.6, 0.6, 3)
+                s = rng.uniform(0.7, 1.25)
+                b.add_drawable(mesh, mats[k % len(mats)], translate(*c) @ random_rotation(rng) @ scale(s))
+                k += 1
+    ext = half + 2.5
+    ground = b.add_mesh(grid_patch(8, 8, lambda u, v: np.stack([(2 * u - 1) * ext * 2, 0 * u - ext, (1 - 2 * v) * ext * 2], -1)))
+    b.add_drawable(ground, b.add_material((0.55, 0.55, 0.5), roughness=0.85))
+    sun = (0.35, 1.0, 0.45)
+    cam = dict(position=(0.2 * ext, 0.35 * ext, 3.1 * ext), front_dir=(-0.05, -0.1, -1.0), up_dir=(0.0, 1.0, 0.0), yfov=30.0, near_z=0.001, far_z=1e5)
+    return b.finish(dir_lights=dir_light(sun, (1.0, 0.95, 0.9), 3.5), sky_faces=procedural_sky(sky_size, sun) if sky_size else None,
+                    camera=cam, bounds=(np.full(3, -ext), np.full(3, ext)))

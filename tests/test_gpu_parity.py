@@ -167,3 +167,83 @@ def test_host_pass_accumulates_like_reference(lib, oracle):
     r.set_camera(cam2)
     assert r.frame(max_bounces=4) == 1          # history invalidated by the camera change
     r.close()
+
+
+# ---- BASELINE configs[2]: mixed lights (64 point/spot + 16 LTC rect) ---------------------------------
+def test_mixed_lights_config3(lib, oracle):
+    import os
+    luts = scenes.load_ltc_luts(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ltc_luts.npz"))
+    scene = scenes.mixed_lights(luts)
+    assert len(scene.point_lights) == 64 and len(scene.rect_lights) == 16
+    W, H = 160, 90
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_MERGED)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=3)                                   # reference default (basic.hpp:78)
+    gpu.debug_capture(True); ref.debug_capture(True)
+    gpu.render(cam, 0, 1, st); ref.render(cam, 0, 1, st)
+    a, b = gpu.resolve(1), ref.resolve(1)
+    # up to 64 shadow rays per vertex land on one pixel through unordered atomics → 1e-4 relative, not bitwise
+    assert (np.abs(a - b) / np.maximum(np.abs(b), 1e-3)).max() <= 1e-4
+    for bounce in (1, 2):                                               # NEE-heavy shadow queue: contents bit-exact as a set
+        sa, sb = gpu.read_queue(bounce, 1), ref.read_queue(bounce, 1)
+        np.testing.assert_array_equal(np.sort(sa["pixels"].astype(np.uint64) << 32 | sa["lights"]),
+                                      np.sort(sb["pixels"].astype(np.uint64) << 32 | sb["lights"]))
+    ca, cb = gpu.counters(), ref.counters()
+    assert ca.shadow_rays == cb.shadow_rays and ca.extend_rays == cb.extend_rays
+    assert ca.shadow_rays > 5 * ca.extend_rays                          # many lights per vertex
+    gpu.close()
+    big = capi.Context(lib, 1920, 1080)                                 # full size: runs, finite, bounded ray counts
+    big.upload_scene(scene, capi.ACCEL_MERGED)
+    big.render(engine.camera_matrices(scene.camera, 1920, 1080), 0, 2, st)
+    img = big.resolve(2)
+    c = big.counters()
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0
+    assert c.shadow_rays <= 64 * c.extend_rays and c.extend_rays_per_bounce[1] == 2 * 1920 * 1080
+
+
+# ---- BASELINE configs[3]: large mesh x many instances, two-level BVH ---------------------------------
+@pytest.mark.parametrize("mode", MODES)
+def test_instanced_small_parity(lib, oracle, mode):
+    scene = scenes.instanced(48, 24, 3)
+    W, H = 128, 72
+    gpu, ref = make_pair(lib, oracle, scene, W, H, mode)
+    if mode == capi.ACCEL_TWO_LEVEL:
+        assert_bvh_equal(gpu.read_bvh(0), ref.read_bvh(0))
+        assert_bvh_equal(gpu.read_bvh(capi.BVH_TLAS), ref.read_bvh(capi.BVH_TLAS))
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=8, ray_length=1000.0)
+    gpu.render(cam, 0, 2, st); ref.render(cam, 0, 2, st)
+    np.testing.assert_array_equal(gpu.resolve(2), ref.resolve(2))
+    ca, cb = gpu.counters(), ref.counters()
+    assert list(ca.extend_rays_per_bounce) == list(cb.extend_rays_per_bounce)
+
+
+def test_instanced_full_size_config4(lib, oracle):
+    """2 097 152-triangle mesh x 512 instances: bit-exact BLAS/TLAS, bit-exact hits of 20 000 random rays
+    against the oracle, and a 3840x2160 sample with sane counters."""
+    scene = scenes.instanced()
+    assert scene.blas["num_triangles"][0] == 2097152 and len(scene.instances) == 513
+    gpu, ref = make_pair(lib, oracle, scene, 64, 36, capi.ACCEL_TWO_LEVEL)
+    assert_bvh_equal(gpu.read_bvh(0), ref.read_bvh(0))
+    assert_bvh_equal(gpu.read_bvh(capi.BVH_TLAS), ref.read_bvh(capi.BVH_TLAS))
+    rays = random_rays(scene, 20000, 17)
+    rays["tmax"] = 1000.0
+    a, b = gpu.trace_rays(rays, 1), ref.trace_rays(rays, 1)
+    for f in ("t", "u", "v", "instance", "primitive"):
+        np.testing.assert_array_equal(a[f], b[f])
+    assert (a["t"] > 0).mean() > 0.3
+    cam = engine.camera_matrices(scene.camera, 64, 36)
+    st = capi.Settings(max_bounces=8, ray_length=1000.0)
+    gpu.render(cam, 0, 1, st); ref.render(cam, 0, 1, st)
+    np.testing.assert_array_equal(gpu.resolve(1), ref.resolve(1))
+    with pytest.raises(capi.BptError):
+        gpu.build_accel(capi.ACCEL_MERGED)                              # 1.07 G merged triangles: refused, not attempted
+    gpu.close()
+    W, H = 3840, 2160
+    big = capi.Context(lib, W, H)
+    big.upload_scene(scene, capi.ACCEL_TWO_LEVEL)
+    big.render(engine.camera_matrices(scene.camera, W, H), 0, 1, st)
+    img = big.resolve(1)
+    c = big.counters()
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0
+    assert c.extend_rays_per_bounce[1] == W * H and c.extend_rays_per_bounce[2] > 0.2 * W * H
