@@ -318,6 +318,15 @@ class Context:
         self._call("trace_shadow_rays", _ptr(rays), len(rays), frame_index, _ptr(vis))
         return vis
 
+    def trace_probes(self, volume: ProbeVolume, sample_table: np.ndarray, frame_index: int, num_bounces: int) -> np.ndarray:
+        """(num_probes * rays_per_probe, 4) float32: radiance rgb + first hit distance (or -1)."""
+        n = volume.probe_counts[0] * volume.probe_counts[1] * volume.probe_counts[2] * volume.rays_per_probe
+        out = np.zeros((n, 4), dtype=f32)
+        table = np.ascontiguousarray(sample_table, dtype=f32)
+        assert table.shape == (8192, 2)
+        self._call("trace_probes", C.byref(volume), _ptr(table), frame_index, num_bounces, _ptr(out))
+        return out
+
     def debug_capture(self, enable: bool):
         self._call("debug_capture", 1 if enable else 0)
 

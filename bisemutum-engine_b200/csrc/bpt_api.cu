@@ -420,9 +420,11 @@ bpt_status bpt_debug_read_queue(bpt_context* c, uint32_t bounce, uint32_t kind, 
     return BPT_OK;
 }
 
-bpt_status bpt_trace_probes(bpt_context* c, const bpt_probe_volume*, const float*, uint32_t, uint32_t, float*) {
+bpt_status bpt_trace_probes(bpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, uint32_t bounces, float* out) {
     NEED(c);
-    return fail(c, BPT_ERR_UNSUPPORTED, "probe tracing not implemented yet");
+    if (!vol || !table || !out) return BPT_ERR_INVALID;
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "trace_probes before build_accel");
+    return wavefront_trace_probes(c, *vol, table, frame, bounces, out);
 }
 
 } // extern "C"

@@ -257,4 +257,19 @@ BPT_HD void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t
     O = v3(iv[12], iv[13], iv[14]);
 }
 
+// ---- DDGI-style probe rays (ddgi/trace_gbuffer.hlsl:10-36) ---------------------------------------
+BPT_HD void probe_ray(const bpt_probe_volume& vol, const float2* sample_table, uint32_t path, uint32_t frame_index, float3& O, float3& D) {
+    uint32_t ray_index = path % vol.rays_per_probe, lin = path / vol.rays_per_probe;
+    uint32_t ix = lin % vol.probe_counts[0], iy = (lin / vol.probe_counts[0]) % vol.probe_counts[1], iz = lin / vol.probe_counts[0] / vol.probe_counts[1];
+    float mx = (float)(vol.probe_counts[0] > 1 ? vol.probe_counts[0] - 1 : 1), my = (float)(vol.probe_counts[1] > 1 ? vol.probe_counts[1] - 1 : 1),
+          mz = (float)(vol.probe_counts[2] > 1 ? vol.probe_counts[2] - 1 : 1);
+    float3 fx = v3(vol.frame_x[0], vol.frame_x[1], vol.frame_x[2]), fy = v3(vol.frame_y[0], vol.frame_y[1], vol.frame_y[2]), fz = v3(vol.frame_z[0], vol.frame_z[1], vol.frame_z[2]);
+    O = ((v3(vol.base_position[0], vol.base_position[1], vol.base_position[2]) + ((float)ix * vol.extent[0] / mx) * fx) + ((float)iy * vol.extent[1] / my) * fy) +
+        ((float)iz * vol.extent[2] / mz) * fz;
+    uint32_t seed = rng_tea(lin, frame_index);
+    uint32_t rand_index = ((uint32_t)(rng_next(seed) * 8192.0f) + ray_index) % 8192u;
+    float2 r = BPT_LDG(sample_table + rand_index);
+    D = uniform_sphere_sample(r.x, r.y);
+}
+
 } // namespace bptd

@@ -19,6 +19,7 @@ struct ShadeParams {
     uint32_t max_bounces;      // clamped to [2,16] (path_tracing.cpp:290)
     uint32_t nee_mode;
     float ray_length;
+    uint32_t diffuse_only;     // probe tracing: light every vertex as surface_data_diffuse(base_color) (ddgi/deferred_lighting.hlsl:44)
 };
 
 // Sink concept:
@@ -38,7 +39,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     const DInstance& in = sc.instances[hit.slot];
     const bpt_drawable_sbt_data& dr = sc.drawables[in.instance_id];
     const bpt_material& mat = sc.materials[dr.material_offset / (uint32_t)sizeof(bpt_material)];
-    const uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
+    uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
     float3 P = O + D * hit.t;                                           // rt_gbuffer.hlsl:32
     HitVertex hv = fetch_hit_vertex(sc, in, hit.prim, hit.u, hit.v);
     Surface surf = eval_material(sc, mat, hv.texcoord);
@@ -48,6 +49,12 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     float3 T = tangent_after_gbuffer(N, hv.tangent_world);              // gbuffer.hlsl:27,41
     float3 B = cross3(N, T);
     surf.opacity = 1.0f;                                                // gbuffer.hlsl:44
+    if (sp.diffuse_only) {                                              // ddgi/deferred_lighting.hlsl:44-45
+        Surface d = surface_default();
+        d.base_color = surf.base_color;
+        surf = d;
+        surface_model = 1u;                                             // MATERIAL_SURFACE_MODEL_LIT (:45)
+    }
     float3 V = normalize3(O - P);                                       // deferred_lighting_secondary.hlsl:45
 
     for (uint32_t l = 0; l < sc.num_rect; l++)                          // :72-96 (unshadowed, as the reference)

@@ -39,6 +39,8 @@ struct RenderArgs {
     uint32_t npx, nslots;     // pixels, samples in this wave; a path's id is slot * npx + pixel
     uint32_t frame_base;      // frame_index of slot 0
     const float4* m_nodes; const float4* m_tris; int32_t m_root; uint32_t m_n;   // the single BVH of merged mode
+    uint32_t pixel_base;      // probe tracing in chunks: global path id = pixel_base + local id (RNG key)
+    uint32_t probe_mode;      // 1: paths start at probes; colour.w receives the first hit distance
 };
 
 // warp-aggregated append: returns the slot for this lane (valid only if `emit`)
@@ -68,6 +70,20 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
     a.ray_d_out[id] = make_float4(D.x, D.y, D.z, 0.0f);
     a.ray_w_out[id] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     a.color[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// ---- probe raygen (ddgi/trace_gbuffer.hlsl:10-36): one thread per (probe, ray) of the chunk -------
+__global__ void __launch_bounds__(kBlock) k_probe_raygen(const __grid_constant__ RenderArgs a, const __grid_constant__ bpt_probe_volume vol,
+                                                         const float2* __restrict__ sample_table) {
+    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id == 0) a.qcount[QE + 1] = a.npx;
+    if (id >= a.npx) return;
+    float3 O, D;
+    probe_ray(vol, sample_table, a.pixel_base + id, a.frame_base, O, D);
+    a.ray_o_out[id] = make_float4(O.x, O.y, O.z, __uint_as_float(id));
+    a.ray_d_out[id] = make_float4(D.x, D.y, D.z, 0.0f);
+    a.ray_w_out[id] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    a.color[id] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
 }
 
 // ---- persistent while-while traversal (extend: rt_gbuffer.hlsl:7-36; connect: NEW shadow rays) ------
@@ -255,9 +271,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Ren
     if (live) {
         float4 o = a.ray_o_in[i], d = a.ray_d_in[i], w = a.ray_w_in[i], h = a.hit[i];
         path = __float_as_uint(o.w);
-        uint32_t pixel = path % a.npx, frame = a.frame_base + path / a.npx;
+        uint32_t pixel = path % a.npx + a.pixel_base, frame = a.frame_base + path / a.npx;
         TraceResult r;
         r.t = h.x; r.u = h.y; r.v = h.z; r.prim = __float_as_uint(h.w); r.slot = a.hit_slot[i]; r.hit = h.x >= 0.0f;
+        if (a.probe_mode && bounce == 1) a.color[path].w = r.t;          // hit distance of the probe ray (or -1)
         KernelSink sink{a, bounce, path};
         cont = shade_vertex(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
     }
@@ -430,23 +447,17 @@ static bpt_status capture_bounce(bpt_context* ctx, uint32_t bounce, int in_buf) 
     return BPT_OK;
 }
 
-bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st, bool keep_ahead) {
-    bpt_status s;
-    if ((s = wavefront_alloc(ctx))) return s;
+// Fills the parts of RenderArgs that do not depend on the wave.
+static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settings& st, uint32_t B) {
     WavefrontState& wf = ctx->wf;
-    wf.ahead_slots = wf.ahead_cursor = 0;         // the colour buffer is about to be overwritten
-    if (keep_ahead) nsamples = std::min(nsamples, wf.slots);
-    const uint32_t npx = ctx->width * ctx->height;
-    const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);           // path_tracing.cpp:187,290
-    RenderArgs a;
     a.sc = ctx->scene_view();
     a.sp.width = ctx->width; a.sp.height = ctx->height; a.sp.max_bounces = B; a.sp.nee_mode = st.nee_mode; a.sp.ray_length = st.ray_length;
-    a.cam = cam;
-    a.npx = npx;
+    a.sp.diffuse_only = 0;
     a.hit = wf.hit.as<float4>(); a.hit_slot = wf.hit_slot.as<uint32_t>();
     a.sh_o = wf.sh_o.as<float4>(); a.sh_d = wf.sh_d.as<float4>(); a.sh_c = wf.sh_c.as<float4>();
     a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();
     a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
+    a.pixel_base = 0; a.probe_mode = 0;
     if (!wf.grid_extend) {      // resident grids of the persistent traversal kernels: SMs x blocks that fit per SM
         int dev = 0, sms = 0, be = 0, ba = 0;
         BPT_CUDA_TRY(ctx, cudaGetDevice(&dev));
@@ -458,11 +469,47 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_merged<true>, kBlock, 0));
         wf.grid_extend_m = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_m = (unsigned)(sms * std::max(ba, 1));
     }
-    const bool merged = ctx->accel_mode == BPT_ACCEL_MERGED;
-    if (merged) {
+    if (ctx->accel_mode == BPT_ACCEL_MERGED) {
         a.m_nodes = ctx->blas[0].nodes.as<float4>(); a.m_tris = ctx->blas[0].tris.as<float4>(); a.m_root = ctx->blas[0].root; a.m_n = ctx->blas[0].n;
     } else { a.m_nodes = nullptr; a.m_tris = nullptr; a.m_root = 0; a.m_n = 0; }
-    const unsigned persistent_grid = wf.grid_extend, persistent_grid_any = wf.grid_connect;
+    return BPT_OK;
+}
+
+// (extend → shade → connect) for bounces 1..B-1 over the queue that raygen left in ray buffer 0.
+static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_settings& st, uint32_t B, uint64_t paths, bool capture) {
+    WavefrontState& wf = ctx->wf;
+    const bool merged = ctx->accel_mode == BPT_ACCEL_MERGED;
+    const unsigned grid_paths = (unsigned)((paths + kBlock - 1) / kBlock);
+    bpt_status s;
+    int cur = 0;
+    for (uint32_t i = 1; i < B; i++) {
+        a.ray_o_in = wf.ray_o[cur].as<float4>(); a.ray_d_in = wf.ray_d[cur].as<float4>(); a.ray_w_in = wf.ray_w[cur].as<float4>();
+        a.ray_o_out = wf.ray_o[cur ^ 1].as<float4>(); a.ray_d_out = wf.ray_d[cur ^ 1].as<float4>(); a.ray_w_out = wf.ray_w[cur ^ 1].as<float4>();
+        if (merged) LAUNCH_T(ctx, 1, k_trace_merged<false>, wf.grid_extend_m, kBlock, a, i);
+        else LAUNCH_T(ctx, 1, k_trace_persistent<false>, wf.grid_extend, kBlock, a, i);
+        LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
+        if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
+            if (merged) LAUNCH_T(ctx, 3, k_trace_merged<true>, wf.grid_connect_m, kBlock, a, i);
+            else LAUNCH_T(ctx, 3, k_trace_persistent<true>, wf.grid_connect, kBlock, a, i);
+        }
+        if (capture && (s = capture_bounce(ctx, i, cur))) return s;
+        cur ^= 1;
+    }
+    return BPT_OK;
+}
+
+bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st, bool keep_ahead) {
+    bpt_status s;
+    if ((s = wavefront_alloc(ctx))) return s;
+    WavefrontState& wf = ctx->wf;
+    wf.ahead_slots = wf.ahead_cursor = 0;         // the colour buffer is about to be overwritten
+    if (keep_ahead) nsamples = std::min(nsamples, wf.slots);
+    const uint32_t npx = ctx->width * ctx->height;
+    const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);           // path_tracing.cpp:187,290
+    RenderArgs a;
+    if ((s = prepare_args(ctx, a, st, B))) return s;
+    a.cam = cam;
+    a.npx = npx;
     const bool capture = ctx->capture && nsamples == 1;
     if (capture) {
         ctx->cap_bounces = B;
@@ -472,34 +519,53 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
     for (uint32_t done = 0; done < nsamples;) {
         const uint32_t slots = std::min(nsamples - done, wf.slots);
         const uint64_t paths = (uint64_t)npx * slots;
-        const unsigned grid_paths = (unsigned)((paths + kBlock - 1) / kBlock);
         a.nslots = slots;
         a.frame_base = frame_first + done;
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream));
-        int cur = 0;
-        auto bind = [&](int in, int out) {
-            a.ray_o_in = wf.ray_o[in].as<float4>(); a.ray_d_in = wf.ray_d[in].as<float4>(); a.ray_w_in = wf.ray_w[in].as<float4>();
-            a.ray_o_out = wf.ray_o[out].as<float4>(); a.ray_d_out = wf.ray_d[out].as<float4>(); a.ray_w_out = wf.ray_w[out].as<float4>();
-        };
-        bind(1, 0);
-        LAUNCH_T(ctx, 0, k_raygen, grid_paths, kBlock, a);
-        for (uint32_t i = 1; i < B; i++) {
-            bind(cur, cur ^ 1);
-            if (merged) LAUNCH_T(ctx, 1, k_trace_merged<false>, wf.grid_extend_m, kBlock, a, i);
-            else LAUNCH_T(ctx, 1, k_trace_persistent<false>, persistent_grid, kBlock, a, i);
-            LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
-            if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
-                if (merged) LAUNCH_T(ctx, 3, k_trace_merged<true>, wf.grid_connect_m, kBlock, a, i);
-                else LAUNCH_T(ctx, 3, k_trace_persistent<true>, persistent_grid_any, kBlock, a, i);
-            }
-            if (capture && (s = capture_bounce(ctx, i, cur))) return s;
-            cur ^= 1;
-        }
+        a.ray_o_out = wf.ray_o[0].as<float4>(); a.ray_d_out = wf.ray_d[0].as<float4>(); a.ray_w_out = wf.ray_w[0].as<float4>();
+        LAUNCH_T(ctx, 0, k_raygen, (unsigned)((paths + kBlock - 1) / kBlock), kBlock, a);
+        if ((s = run_bounces(ctx, a, st, B, paths, capture))) return s;
         if (keep_ahead) { wf.ahead_slots = slots; wf.ahead_cursor = 0; wf.ahead_frame_first = frame_first; }
         else LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, 0u, slots);
         LAUNCH_T(ctx, 4, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), (uint32_t)paths);
         done += slots;
     }
+    return BPT_OK;
+}
+
+// DDGI-style probe tracing through the same extend / shade / connect kernels (BASELINE configs[4]).
+bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, uint32_t num_bounces, float* h_out) {
+    bpt_status s;
+    if ((s = wavefront_alloc(ctx))) return s;
+    WavefrontState& wf = ctx->wf;
+    wf.ahead_slots = wf.ahead_cursor = 0;
+    const uint64_t total = (uint64_t)vol.probe_counts[0] * vol.probe_counts[1] * vol.probe_counts[2] * vol.rays_per_probe;
+    if (total == 0 || total > 0xffffffffull || vol.rays_per_probe == 0) { ctx->err = "trace_probes: bad volume"; return BPT_ERR_INVALID; }
+    const uint32_t B = std::min(std::max(num_bounces, 1u), 15u) + 1;          // num_bounces extend passes
+    bpt_settings st{};
+    st.ray_length = vol.ray_length; st.max_bounces = B; st.nee_mode = BPT_NEE_SHADOW_RAY;
+    RenderArgs a;
+    if ((s = prepare_args(ctx, a, st, B))) return s;
+    a.sp.diffuse_only = 1; a.probe_mode = 1; a.nslots = 1; a.frame_base = frame_index;
+    memset(&a.cam, 0, sizeof(a.cam));
+    DevBuf table;
+    if ((s = dev_upload(ctx, table, h_table, 8192 * sizeof(float2)))) return s;
+    for (uint64_t base = 0; base < total; base += wf.capacity) {
+        const uint32_t count = (uint32_t)std::min<uint64_t>(wf.capacity, total - base);
+        a.npx = count; a.pixel_base = (uint32_t)base;
+        cudaError_t e = cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream);
+        if (e != cudaSuccess) { dev_free(table); ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+        a.ray_o_out = wf.ray_o[0].as<float4>(); a.ray_d_out = wf.ray_d[0].as<float4>(); a.ray_w_out = wf.ray_w[0].as<float4>();
+        k_probe_raygen<<<(count + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(a, vol, table.as<float2>());
+        ctx->launches++;
+        if ((s = run_bounces(ctx, a, st, B, count, false))) { dev_free(table); return s; }
+        k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), count);
+        ctx->launches++;
+        e = cudaMemcpyAsync(h_out + 4 * base, wf.color.p, (size_t)count * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { dev_free(table); ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    }
+    dev_free(table);
     return BPT_OK;
 }
 

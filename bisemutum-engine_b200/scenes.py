@@ -527,3 +527,34 @@ def instanced(mesh_seg: int = 2048, mesh_ring: int = 512, grid: int = 8, seed: i
     cam = dict(position=(0.2 * ext, 0.35 * ext, 3.1 * ext), front_dir=(-0.05, -0.1, -1.0), up_dir=(0.0, 1.0, 0.0), yfov=30.0, near_z=0.001, far_z=1e5)
     return b.finish(dir_lights=dir_light(sun, (1.0, 0.95, 0.9), 3.5), sky_faces=procedural_sky(sky_size, sun) if sky_size else None,
                     camera=cam, bounds=(np.full(3, -ext), np.full(3, ext)))
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: DDGI-style probe grid over a scene's bounds.
+# ---------------------------------------------------------------------------------------------
+def ddgi_sample_randoms() -> np.ndarray:
+    """The 8192-entry R2 sequence of DdgiContext::init_sample_randoms (src/renderer/context/ddgi.cpp:125-145),
+    float32 accumulation exactly as the reference does it."""
+    phi2 = 1.0 / 1.3247179572447
+    delta = np.array([phi2, phi2 * phi2], dtype=f32)
+    out = np.zeros((8192, 2), f32)
+    out[0] = (0.5, 0.5)
+    for i in range(1, 8192):
+        v = out[i - 1] + delta
+        v = np.where(v >= f32(1.0), v - f32(1.0), v).astype(f32)
+        out[i] = v
+    return out
+
+
+def probe_volume(scene: SceneData, counts=(32, 32, 16), rays_per_probe: int = 256, ray_length: float = 1024.0, margin: float = 0.04):
+    """Axis-aligned probe volume covering the scene bounds (slightly inset); counts follow the axes (x, y, z)."""
+    lo, hi = (np.asarray(b, np.float64) for b in scene.bounds)
+    pad = margin * (hi - lo)
+    v = capi.ProbeVolume()
+    v.base_position[:] = list((lo + pad).astype(f32))
+    v.frame_x[:] = [1, 0, 0]; v.frame_y[:] = [0, 1, 0]; v.frame_z[:] = [0, 0, 1]
+    v.extent[:] = list((hi - lo - 2 * pad).astype(f32))
+    v.ray_length = ray_length
+    v.probe_counts[:] = list(counts)
+    v.rays_per_probe = rays_per_probe
+    return v

@@ -183,6 +183,11 @@ static inline SurfaceData surface_data_default() {   // material/utils.hlsl:18-3
     s.roughness = 0.5f; s.anisotropy = 0.0f; s.ior = 1.5f; s.opacity = 1.0f; s.two_sided = false;
     return s;
 }
+static inline SurfaceData surface_data_diffuse(f3 base_color) {   // material/utils.hlsl:32-36
+    SurfaceData s = surface_data_default();
+    s.base_color = base_color;
+    return s;
+}
 static inline f3 schlick_mix(f3 f0, f3 f90, float cos_theta) {    // utils.hlsl:40-42
     return lerp3(f0, f90, pow5(1.0f - cos_theta));
 }

@@ -205,15 +205,13 @@ struct ThreadOut {
     std::vector<CapS> cap_s;
 };
 
+// One path from (O, D): the loop of SURVEY Appendix A. `pixel` keys the RNG stream (py * W + px for camera
+// paths, probe * rays + ray for probe paths); `first_t` (optional) receives the first hit distance or -1.
 template <class Acc>
-static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const bpt_settings& st, uint32_t frame_index,
-                         uint32_t px, uint32_t py, Acc* a, ThreadOut& out) {
+static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool diffuse_only, uint32_t frame_index, uint32_t pixel,
+                       f3 O, f3 D, Acc* a, float* first_t, ThreadOut& out) {
     const Scene& sc = ctx.scene;
-    const uint32_t W = ctx.width, H = ctx.height;
     const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);               // path_tracing.cpp:290
-    const uint32_t pixel = py * W + px;
-    f3 O, D;
-    camera_ray(cam, px, py, W, H, O, D);
     f3 Wt = splat3(1.0f);
     // Per-sample colour C_s starts at 0, receives this sample's contributions in order, and is added to the
     // FP32 sum buffer when the sample ends (the reference's color texture + accumulate pass,
@@ -225,6 +223,7 @@ static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const b
         out.ext_per_bounce[i]++;
         HitRec h = trace_closest(sc, O, D, 0.001f, st.ray_length, frame_index, out.ext);   // rt_gbuffer.hlsl:17-25
         if (ctx.capture) out.cap_e.push_back({i, pixel, bpt_hit{h.t, h.u, h.v, h.hit ? h.instance_id : 0xffffffffu, h.hit ? h.prim : 0xffffffffu}});
+        if (i == 1 && first_t) *first_t = h.hit ? h.t : -1.0f;
         if (!h.hit) {                                                                       // deferred_lighting_secondary.hlsl:24-29
             const float* m = sc.sky_transform;
             f3 dir = mk3((m[0] * D.x + m[1] * D.y) + m[2] * D.z, (m[3] * D.x + m[4] * D.y) + m[5] * D.z, (m[6] * D.x + m[7] * D.y) + m[8] * D.z);
@@ -237,7 +236,7 @@ static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const b
         const InstanceXf& x = sc.xf[h.inst_slot];
         const bpt_drawable_sbt_data& dr = sc.drawables[x.instance_id];
         const bpt_material& mat = sc.materials[dr.material_offset / sizeof(bpt_material)];
-        const uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
+        uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
         f3 P = O + D * h.t;                                                                 // rt_gbuffer.hlsl:32
         Vertex vt = fetch_vertex_attributes(sc, x, h.prim, h.u, h.v);
         SurfaceData surf = material_function(sc, mat, vt.texcoord);
@@ -247,6 +246,10 @@ static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const b
         f3 T = gbuffer_roundtrip_tangent(N, vt.tangent_world);                              // gbuffer.hlsl:27,41
         f3 Bv = cross(N, T);                                                                // deferred_lighting_secondary.hlsl:41
         surf.opacity = 1.0f;                                                                // gbuffer.hlsl:44
+        if (diffuse_only) {                                                                 // ddgi/deferred_lighting.hlsl:44-45
+            surf = surface_data_diffuse(surf.base_color);
+            surface_model = 1u;
+        }
         f3 V = normalize(O - P);                                                            // deferred_lighting_secondary.hlsl:45
 
         // Contributions of this vertex. The GPU adds the unshadowed (immediate) terms in the shade
@@ -281,7 +284,7 @@ static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const b
         f3 V_local = frame_to_local(frame, V);
         float rx, ry;
         get_anisotropic_roughness(surf.roughness, surf.anisotropy, rx, ry);
-        uint32_t seed = rng_tea(py * W + px, frame_index + i * 3u);                         // :52
+        uint32_t seed = rng_tea(pixel, frame_index + i * 3u);                               // :52 (pixel = py * W + px)
         float u1 = rng_next(seed);
         float u2 = rng_next(seed);
         f3 half_dir = ggx_vndf_sample(V_local, rx, ry, u1, u2);
@@ -298,6 +301,14 @@ static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const b
         if (newW.x == 0.0f && newW.y == 0.0f && newW.z == 0.0f) return;
         O = P; D = out_dir; Wt = newW;
     }
+}
+
+template <class Acc>
+static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const bpt_settings& st, uint32_t frame_index,
+                         uint32_t px, uint32_t py, Acc* a, ThreadOut& out) {
+    f3 O, D;
+    camera_ray(cam, px, py, ctx.width, ctx.height, O, D);                                  // generate_camera_ray.hlsl:4-16
+    trace_path(ctx, st, false, frame_index, py * ctx.width + px, O, D, a, (float*)nullptr, out);
 }
 
 template <class Acc>
@@ -561,8 +572,55 @@ bpt_status obpt_debug_read_queue(obpt_context* c, uint32_t bounce, uint32_t kind
     if (kind == 1 && lights) std::copy(c->cap_shadow_lights[bounce].begin(), c->cap_shadow_lights[bounce].end(), lights);
     return BPT_OK;
 }
-bpt_status obpt_trace_probes(obpt_context* c, const bpt_probe_volume*, const float*, uint32_t, uint32_t, float*) {
-    return fail(c, BPT_ERR_UNSUPPORTED, "probe tracing not implemented yet");
+// DDGI-style probe tracing: ddgi/trace_gbuffer.hlsl:10-51 (probe centre, R2-table direction, TraceRay) +
+// ddgi/deferred_lighting.hlsl:12-118 (diffuse-only surface, V = normalize(probe - P)); further bounces continue
+// the path through the same trace/shade code (BASELINE configs[4]); previous-frame DDGI feedback is not modelled.
+bpt_status obpt_trace_probes(obpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, uint32_t num_bounces, float* out) {
+    CHECK_CTX(c); if (!vol || !table || !out) return BPT_ERR_INVALID;
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "trace_probes before build_accel");
+    const uint64_t total = (uint64_t)vol->probe_counts[0] * vol->probe_counts[1] * vol->probe_counts[2] * vol->rays_per_probe;
+    if (total == 0 || total > 0xffffffffull) return fail(c, BPT_ERR_INVALID, "trace_probes: bad volume");
+    bpt_settings st{};
+    st.ray_length = vol->ray_length; st.max_bounces = std::min(std::max(num_bounces, 1u), 15u) + 1; st.nee_mode = BPT_NEE_SHADOW_RAY;
+    uint32_t nt = obpt_get_threads(c);
+    std::vector<ThreadOut> outs(nt);
+    std::atomic<uint64_t> next{0};
+    bool cap = c->capture; c->capture = false;
+    auto work = [&](uint32_t tid) {
+        const uint64_t CH = 1024;
+        for (;;) {
+            uint64_t b0 = next.fetch_add(CH);
+            if (b0 >= total) break;
+            for (uint64_t path = b0; path < std::min(b0 + CH, total); path++) {
+                uint32_t ray_index = (uint32_t)(path % vol->rays_per_probe), lin = (uint32_t)(path / vol->rays_per_probe);
+                uint32_t ix = lin % vol->probe_counts[0], iy = (lin / vol->probe_counts[0]) % vol->probe_counts[1], iz = lin / vol->probe_counts[0] / vol->probe_counts[1];
+                float mx = (float)(vol->probe_counts[0] > 1 ? vol->probe_counts[0] - 1 : 1), my = (float)(vol->probe_counts[1] > 1 ? vol->probe_counts[1] - 1 : 1),
+                      mz = (float)(vol->probe_counts[2] > 1 ? vol->probe_counts[2] - 1 : 1);
+                f3 fx = mk3(vol->frame_x[0], vol->frame_x[1], vol->frame_x[2]), fy = mk3(vol->frame_y[0], vol->frame_y[1], vol->frame_y[2]), fz = mk3(vol->frame_z[0], vol->frame_z[1], vol->frame_z[2]);
+                f3 O = ((mk3(vol->base_position[0], vol->base_position[1], vol->base_position[2]) + ((float)ix * vol->extent[0] / mx) * fx) + ((float)iy * vol->extent[1] / my) * fy) +
+                       ((float)iz * vol->extent[2] / mz) * fz;                                   // trace_gbuffer.hlsl:20-23
+                uint32_t seed = rng_tea(lin, frame);                                             // :25
+                uint32_t rand_index = ((uint32_t)(rng_next(seed) * 8192.0f) + ray_index) % 8192u;   // :26
+                f3 D = uniform_sphere_sample(table[2 * rand_index], table[2 * rand_index + 1]);  // :27-29
+                float rgb[3] = {0, 0, 0}, first_t = -1.0f;
+                trace_path<float>(*c, st, true, frame, (uint32_t)path, O, D, rgb, &first_t, outs[tid]);
+                out[4 * path] = rgb[0]; out[4 * path + 1] = rgb[1]; out[4 * path + 2] = rgb[2]; out[4 * path + 3] = first_t;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    c->capture = cap;
+    for (auto& o : outs) {
+        c->counters.extend_rays += o.ext.rays; c->counters.shadow_rays += o.shd.rays;
+        for (int b = 0; b < 16; b++) { c->counters.extend_rays_per_bounce[b] += o.ext_per_bounce[b]; c->counters.shadow_rays_per_bounce[b] += o.shd_per_bounce[b]; }
+        c->stats.extend_rays += o.ext.rays; c->stats.extend_nodes += o.ext.nodes; c->stats.extend_tris += o.ext.tris;
+        c->stats.shadow_rays += o.shd.rays; c->stats.shadow_nodes += o.shd.nodes; c->stats.shadow_tris += o.shd.tris;
+    }
+    c->counters.samples += total;
+    return BPT_OK;
 }
 
 uint32_t obpt_rng_tea(uint32_t a, uint32_t b) { return rng_tea(a, b); }

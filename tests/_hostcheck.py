@@ -52,6 +52,7 @@ def lib():
         _lib.hc_surface_eval_lit.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p]
         _lib.hc_render.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.POINTER(capi.Settings), C.c_void_p]
+        _lib.hc_trace_probes.argtypes = [C.POINTER(HcScene), C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -107,3 +108,9 @@ class HostScene:
         vis = np.zeros(len(rays), np.uint8)
         lib().hc_trace(C.byref(self.h), rays.ctypes.data_as(C.c_void_p), len(rays), frame_index, hits.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p))
         return hits, vis
+
+    def trace_probes(self, volume, table, frame_index, num_bounces):
+        n = volume.probe_counts[0] * volume.probe_counts[1] * volume.probe_counts[2] * volume.rays_per_probe
+        out = np.zeros((n, 4), np.float32)
+        lib().hc_trace_probes(C.byref(self.h), C.byref(volume), table.ctypes.data_as(C.c_void_p), frame_index, num_bounces, out.ctypes.data_as(C.c_void_p))
+        return out

@@ -125,7 +125,7 @@ __attribute__((visibility("default")))
 int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t height, uint32_t frame_first, uint32_t nsamples,
               const bpt_settings* st, float* accum_rgba) {
     Built b; build(*h, b);
-    ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = std::min(std::max(st->max_bounces, 2u), 16u); sp.nee_mode = st->nee_mode; sp.ray_length = st->ray_length;
+    ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = std::min(std::max(st->max_bounces, 2u), 16u); sp.nee_mode = st->nee_mode; sp.ray_length = st->ray_length; sp.diffuse_only = 0;
     for (uint32_t s = 0; s < nsamples; s++)
         for (uint32_t p = 0; p < width * height; p++) {
             float3 O, D, W = v3s(1.0f);
@@ -142,6 +142,32 @@ int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t
             }
             for (int k = 0; k < 3; k++) accum_rgba[4ull * p + k] += color[k];
         }
+    return 0;
+}
+
+// Probe paths (bpt_trace_probes): same loop, rays start at probe centres, diffuse-only surface.
+__attribute__((visibility("default")))
+int hc_trace_probes(const hc_scene* h, const bpt_probe_volume* vol, const float* table, uint32_t frame_index, uint32_t num_bounces, float* out) {
+    Built b; build(*h, b);
+    ShadeParams sp; sp.width = 0; sp.height = 0; sp.max_bounces = std::min(std::max(num_bounces, 1u), 15u) + 1; sp.nee_mode = BPT_NEE_SHADOW_RAY;
+    sp.ray_length = vol->ray_length; sp.diffuse_only = 1;
+    uint64_t total = (uint64_t)vol->probe_counts[0] * vol->probe_counts[1] * vol->probe_counts[2] * vol->rays_per_probe;
+    for (uint64_t p = 0; p < total; p++) {
+        float3 O, D, W = v3s(1.0f);
+        probe_ray(*vol, reinterpret_cast<const float2*>(table), (uint32_t)p, frame_index, O, D);
+        float color[4] = {0, 0, 0, -1.0f};
+        for (uint32_t i = 1; i < sp.max_bounces; i++) {
+            TraceResult r = trace_ray<false>(b.sc, O, D, 0.001f, sp.ray_length, frame_index);
+            if (i == 1) color[3] = r.t;
+            HostSink sink{b.sc, BPT_NEE_SHADOW_RAY, frame_index, color, {}};
+            float3 nO, nD, nW;
+            bool cont = shade_vertex(b.sc, sp, frame_index, i, (uint32_t)p, O, D, W, r, sink, nO, nD, nW);
+            for (auto& c : sink.pending) sink.add(c);
+            if (!cont) break;
+            O = nO; D = nD; W = nW;
+        }
+        for (int k = 0; k < 4; k++) out[4 * p + k] = color[k];
+    }
     return 0;
 }
 

@@ -98,3 +98,18 @@ def test_trace_bit_exact(oracle, mode):
         np.testing.assert_array_equal(hits[f], ref[f])
     np.testing.assert_array_equal(vis, ctx.trace_shadow_rays(rays, 3))
     assert 0.2 < (ref["t"] >= 0).mean() < 0.98
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_probe_tracing_bit_exact(oracle, mode):
+    """DDGI-style probe rays (ddgi/trace_gbuffer.hlsl + ddgi/deferred_lighting.hlsl) through the same code."""
+    scene = _scene("mixed")
+    table = scenes.ddgi_sample_randoms()
+    assert table.shape == (8192, 2) and table.min() >= 0 and table.max() < 1 and tuple(table[0]) == (0.5, 0.5)
+    vol = scenes.probe_volume(scene, (3, 2, 3), 16, ray_length=50.0)
+    ctx = oracle.OracleContext(8, 8); ctx.upload_scene(scene, mode)
+    for bounces in (1, 3):
+        ref = ctx.trace_probes(vol, table, 4, bounces)
+        got = HC.HostScene(scene, ctx, mode).trace_probes(vol, table, 4, bounces)
+        np.testing.assert_array_equal(got, ref)
+    assert (ref[:, 3] > 0).any() and (ref[:, 3] < 0).any() and np.isfinite(ref).all()
