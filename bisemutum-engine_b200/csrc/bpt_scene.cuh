@@ -243,10 +243,13 @@ BPT_HD float3 eval_point_light(const bpt_point_light_data& l, float3 P, float3& 
 }
 
 // ---- camera ray (generate_camera_ray.hlsl:4-16, camera.hlsl:7-9) --------------------------------
-BPT_HD void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t W, uint32_t H, float3& O, float3& D) {
+// pixel_jitter (NEW switch, default off = the reference's fixed pixel centres): offsets from the bounce-0 RNG stream
+BPT_HD void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t W, uint32_t H, uint32_t jitter, uint32_t frame_index, float3& O, float3& D) {
     const float* ip = cam.matrix_inv_proj;
     const float* iv = cam.matrix_inv_view;
-    float uvx = ((float)px + 0.5f) / (float)W, uvy = ((float)py + 0.5f) / (float)H;
+    float jx = 0.5f, jy = 0.5f;
+    if (jitter) { uint32_t seed = rng_tea(py * W + px, frame_index); jx = rng_next(seed); jy = rng_next(seed); }
+    float uvx = ((float)px + jx) / (float)W, uvy = ((float)py + jy) / (float)H;
     float nx = uvx * 2.0f - 1.0f, ny = 1.0f - uvy * 2.0f;
     float3 dl = v3(((ip[0] * nx + ip[4] * ny) + ip[8]) + ip[12], ((ip[1] * nx + ip[5] * ny) + ip[9]) + ip[13],
                    ((ip[2] * nx + ip[6] * ny) + ip[10]) + ip[14]);

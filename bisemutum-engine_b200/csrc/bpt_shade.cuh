@@ -19,6 +19,7 @@ struct ShadeParams {
     uint32_t max_bounces;      // clamped to [2,16] (path_tracing.cpp:290)
     uint32_t nee_mode;
     float ray_length;
+    uint32_t russian_roulette; // NEW switch, default off
     uint32_t diffuse_only;     // probe tracing: light every vertex as surface_data_diffuse(base_color) (ddgi/deferred_lighting.hlsl:44)
 };
 
@@ -93,6 +94,12 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     float3 w2 = weight * Wt;
     // a zero-weight path can never contribute again (deferred_lighting_secondary.hlsl:17-21): drop it
     if (w2.x == 0.0f && w2.y == 0.0f && w2.z == 0.0f) return false;
+    if (sp.russian_roulette && bounce >= 2) {                           // third draw of this bounce's stream
+        float q = clampf_(max3c(w2), 0.05f, 1.0f);
+        float u3 = rng_next(seed);
+        if (!(u3 < q)) return false;
+        w2 = w2 / q;
+    }
     nO = P; nD = out_dir; nW = w2;
     return true;
 }

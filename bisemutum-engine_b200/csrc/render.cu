@@ -40,6 +40,7 @@ struct RenderArgs {
     uint32_t frame_base;      // frame_index of slot 0
     const float4* m_nodes; const float4* m_tris; int32_t m_root; uint32_t m_n;   // the single BVH of merged mode
     uint32_t pixel_base;      // probe tracing in chunks: global path id = pixel_base + local id (RNG key)
+    uint32_t pixel_jitter;
     uint32_t probe_mode;      // 1: paths start at probes; colour.w receives the first hit distance
 };
 
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
     if (id >= total) return;
     uint32_t p = id % a.npx;
     float3 O, D;
-    camera_ray(a.cam, p % a.sp.width, p / a.sp.width, a.sp.width, a.sp.height, O, D);
+    camera_ray(a.cam, p % a.sp.width, p / a.sp.width, a.sp.width, a.sp.height, a.pixel_jitter, a.frame_base + id / a.npx, O, D);
     a.ray_o_out[id] = make_float4(O.x, O.y, O.z, __uint_as_float(id));
     a.ray_d_out[id] = make_float4(D.x, D.y, D.z, 0.0f);
     a.ray_w_out[id] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
@@ -452,7 +453,7 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
     WavefrontState& wf = ctx->wf;
     a.sc = ctx->scene_view();
     a.sp.width = ctx->width; a.sp.height = ctx->height; a.sp.max_bounces = B; a.sp.nee_mode = st.nee_mode; a.sp.ray_length = st.ray_length;
-    a.sp.diffuse_only = 0;
+    a.sp.diffuse_only = 0; a.sp.russian_roulette = st.russian_roulette; a.pixel_jitter = st.pixel_jitter;
     a.hit = wf.hit.as<float4>(); a.hit_slot = wf.hit_slot.as<uint32_t>();
     a.sh_o = wf.sh_o.as<float4>(); a.sh_d = wf.sh_d.as<float4>(); a.sh_c = wf.sh_c.as<float4>();
     a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();

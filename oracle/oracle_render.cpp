@@ -177,10 +177,14 @@ static inline f3 point_light_eval(const bpt_point_light_data& l, f3 P, f3& light
 }
 
 // ---- camera ray: generate_camera_ray.hlsl:4-16, camera.hlsl:7-9 (glm column-major storage) ----
-static inline void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t W, uint32_t H, f3& O, f3& D) {
+// pixel_jitter is a NEW switch (default off = the reference's fixed pixel centres, generate_camera_ray.hlsl:9):
+// when on, the sub-pixel offset comes from the bounce-0 stream rng_tea(pixel, frame_index).
+static inline void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t W, uint32_t H, uint32_t jitter, uint32_t frame_index, f3& O, f3& D) {
     const float* ip = cam.matrix_inv_proj;
     const float* iv = cam.matrix_inv_view;
-    float uvx = ((float)px + 0.5f) / (float)W, uvy = ((float)py + 0.5f) / (float)H;
+    float jx = 0.5f, jy = 0.5f;
+    if (jitter) { uint32_t seed = rng_tea(py * W + px, frame_index); jx = rng_next(seed); jy = rng_next(seed); }
+    float uvx = ((float)px + jx) / (float)W, uvy = ((float)py + jy) / (float)H;
     float nx = uvx * 2.0f - 1.0f, ny = 1.0f - uvy * 2.0f;
     // mul(M, float4(nx, ny, 1, 1)).xyz, M column-major: M[c*4 + r]
     f3 dl = mk3(((ip[0] * nx + ip[4] * ny) + ip[8]) + ip[12],
@@ -299,6 +303,12 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
         // A zero-weight path can never contribute again (deferred_lighting_secondary.hlsl:17-21
         // writes 0 and the next sample pass kills it), so it is dropped here instead of traced.
         if (newW.x == 0.0f && newW.y == 0.0f && newW.z == 0.0f) return;
+        if (st.russian_roulette && i >= 2) {   // NEW switch: third draw of this bounce's stream, survive with q
+            float q = clampf(fmax_(newW.x, fmax_(newW.y, newW.z)), 0.05f, 1.0f);
+            float u3 = rng_next(seed);
+            if (!(u3 < q)) return;
+            newW = newW / q;
+        }
         O = P; D = out_dir; Wt = newW;
     }
 }
@@ -307,7 +317,7 @@ template <class Acc>
 static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const bpt_settings& st, uint32_t frame_index,
                          uint32_t px, uint32_t py, Acc* a, ThreadOut& out) {
     f3 O, D;
-    camera_ray(cam, px, py, ctx.width, ctx.height, O, D);                                  // generate_camera_ray.hlsl:4-16
+    camera_ray(cam, px, py, ctx.width, ctx.height, st.pixel_jitter, frame_index, O, D);                                  // generate_camera_ray.hlsl:4-16
     trace_path(ctx, st, false, frame_index, py * ctx.width + px, O, D, a, (float*)nullptr, out);
 }
 
@@ -491,7 +501,7 @@ bpt_status obpt_clear_accum(obpt_context* c) { CHECK_CTX(c); std::fill(c->accum.
 bpt_status obpt_render(obpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t ns, const bpt_settings* st) {
     CHECK_CTX(c); if (!cam || !st) return BPT_ERR_INVALID;
     if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
-    if (st->state_precision != BPT_STATE_FP32 || st->russian_roulette || st->pixel_jitter || st->rect_shadow) return fail(c, BPT_ERR_UNSUPPORTED, "mode switch not implemented");
+    if (st->state_precision != BPT_STATE_FP32 || st->rect_shadow) return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 and rect_shadow=mrp_ray are not implemented");
     render_impl<float>(*c, *cam, first, ns, *st, c->accum.data(), true);
     return BPT_OK;
 }

@@ -282,3 +282,18 @@ def test_probe_tracing_full_size_config5(lib, oracle):
     b = ref.trace_probes(sub, table, 0, 2)
     a = gpu.trace_probes(sub, table, 0, 2)
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("switch", ["russian_roulette", "pixel_jitter", "nee_none"])
+def test_mode_switches(lib, oracle, switch):
+    scene = scenes.small_test_scene()
+    W, H = 96, 64
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_MERGED)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=8, nee_mode=capi.NEE_NONE) if switch == "nee_none" else capi.Settings(max_bounces=8, **{switch: 1})
+    gpu.render(cam, 4, 3, st); ref.render(cam, 4, 3, st)
+    np.testing.assert_array_equal(gpu.resolve(3), ref.resolve(3))
+    ca, cb = gpu.counters(), ref.counters()
+    assert ca.extend_rays == cb.extend_rays and ca.shadow_rays == cb.shadow_rays
+    with pytest.raises(capi.BptError):
+        gpu.render(cam, 0, 1, capi.Settings(rect_shadow=1))

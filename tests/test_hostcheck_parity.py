@@ -113,3 +113,23 @@ def test_probe_tracing_bit_exact(oracle, mode):
         got = HC.HostScene(scene, ctx, mode).trace_probes(vol, table, 4, bounces)
         np.testing.assert_array_equal(got, ref)
     assert (ref[:, 3] > 0).any() and (ref[:, 3] < 0).any() and np.isfinite(ref).all()
+
+
+@pytest.mark.parametrize("switch", ["russian_roulette", "pixel_jitter"])
+def test_mode_switches_bit_exact(oracle, switch):
+    """The NEW switches of SURVEY §0 (default off) are implemented identically on both sides."""
+    scene = _scene("small")
+    W, H = 36, 24
+    ctx = oracle.OracleContext(W, H); ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    cam = oracle.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=8, **{switch: 1})
+    base = oracle.OracleContext(W, H); base.upload_scene(scene, capi.ACCEL_MERGED)
+    base.render(cam, 2, 2, capi.Settings(max_bounces=8))
+    ctx.render(cam, 2, 2, st)
+    ref = ctx.resolve(1)
+    np.testing.assert_array_equal(HC.HostScene(scene, ctx, capi.ACCEL_MERGED).render(cam, W, H, 2, 2, st)[..., :3], ref[..., :3])
+    assert (ref != base.resolve(1)).any()                                       # the switch does something
+    if switch == "russian_roulette":
+        assert ctx.counters().extend_rays < base.counters().extend_rays          # fewer rays on dark paths
+    with pytest.raises(capi.BptError):
+        ctx.render(cam, 0, 1, capi.Settings(state_precision=1))                 # rejected, not silently ignored
