@@ -60,16 +60,30 @@ __device__ __forceinline__ uint32_t queue_push(uint32_t* counter, bool emit) {
 // ---- raygen (generate_camera_ray.hlsl:4-16): one thread per (sample slot, pixel), weight = 1, no jitter;
 //      also zeroes the path's per-sample colour -----------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ RenderArgs a) {
-    uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t total = a.npx * a.nslots;
-    if (id == 0) a.qcount[QE + 1] = total;
-    if (id >= total) return;
-    uint32_t p = id % a.npx;
+    // Thread → pixel through 8x4 tiles (a warp = one tile) so that the rays of a warp, and the hit points and
+    // shadow rays they spawn, stay spatially coherent. The pixel's identity (RNG key, colour slot) is unchanged.
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tiles_x = (a.sp.width + 7) / 8, tiles_y = (a.sp.height + 3) / 4;
+    const uint32_t per_slot = tiles_x * tiles_y * 32;
+    if (tid == 0) a.qcount[QE + 1] = a.npx * a.nslots;
+    if (tid >= per_slot * a.nslots) return;
+    uint32_t slot = tid / per_slot, r = tid % per_slot;
+    uint32_t tile = r / 32, in_tile = r % 32;
+    uint32_t px = (tile % tiles_x) * 8 + (in_tile & 7), py = (tile / tiles_x) * 4 + (in_tile >> 3);
+    bool valid = px < a.sp.width && py < a.sp.height;
+    // compact the valid pixels of the wave to consecutive queue slots (edge tiles may be partial)
+    uint32_t p = py * a.sp.width + px;
+    uint32_t id = slot * a.npx + p;                                          // path id = slot * npx + pixel
+    // full tiles everywhere (e.g. 1920x1080): the slot is the thread id, no atomic; otherwise compact the
+    // valid pixels with the warp-aggregated push (scratch counter, zeroed with the queue counters)
+    const bool exact = (a.sp.width % 8 == 0) && (a.sp.height % 4 == 0);
+    uint32_t qslot = exact ? tid : queue_push(&a.qcount[QN - 1], valid);
+    if (!valid) return;
     float3 O, D;
-    camera_ray(a.cam, p % a.sp.width, p / a.sp.width, a.sp.width, a.sp.height, a.pixel_jitter, a.frame_base + id / a.npx, O, D);
-    a.ray_o_out[id] = make_float4(O.x, O.y, O.z, __uint_as_float(id));
-    a.ray_d_out[id] = make_float4(D.x, D.y, D.z, 0.0f);
-    a.ray_w_out[id] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    camera_ray(a.cam, px, py, a.sp.width, a.sp.height, a.pixel_jitter, a.frame_base + slot, O, D);
+    a.ray_o_out[qslot] = make_float4(O.x, O.y, O.z, __uint_as_float(id));
+    a.ray_d_out[qslot] = make_float4(D.x, D.y, D.z, 0.0f);
+    a.ray_w_out[qslot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     a.color[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
     RayState rs;
     RaySpace sp_;
     rs.found = false; rs.tbest = 0.0f; rs.tcull = 0.0f; rs.tmin = 0.001f;
-    int32_t node = kEmpty, leaf = 0;
+    int32_t node = kEmpty, leaf = 0, leaf2 = 0;
     int sp = 0;
     uint32_t ray = 0xffffffffu, path = 0;
     bool exhausted = false;
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
                         rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu; rs.bu = 0.0f; rs.bv = 0.0f;
                         rs.frame_index = a.frame_base + path / a.npx; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
                         sp_ = make_space(rs.O, rs.D);
-                        sp = 0; leaf = 0;
+                        sp = 0; leaf = 0; leaf2 = 0;
                         node = a.m_n == 0 ? kEmpty : a.m_root;
                         if (node < 0) { leaf = node; node = kEmpty; }      // single-triangle BVH: the root is a leaf
                     }
@@ -219,12 +233,16 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
         if (__ballot_sync(0xffffffffu, ray != 0xffffffffu) == 0) break;
         for (;;) {
             // ---- node phase: until no lane is still searching for its first leaf ----
+            // A lane postpones up to two leaves (leaf, leaf2) and keeps descending; it only idles when a third shows up.
             for (;;) {
                 if (node >= 0 && node != kEmpty) {
                     int32_t next = node_step(nodes, node, sp_, rs.tmin, rs.tcull, stack, sp);
                     if (next == BPT_POP) next = sp ? stack[--sp] : kEmpty;
                     node = next;
-                    if (node < 0 && leaf == 0) { leaf = node; node = sp ? stack[--sp] : kEmpty; }   // postpone, keep descending
+                    if (node < 0 && leaf2 == 0) {                         // postpone, keep descending
+                        if (leaf == 0) leaf = node; else leaf2 = node;
+                        node = sp ? stack[--sp] : kEmpty;
+                    }
                 }
                 bool searching = leaf == 0 && node >= 0 && node != kEmpty;
                 if (!__any_sync(0xffffffffu, searching)) break;
@@ -232,9 +250,9 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
             // ---- triangle phase ----
             while (leaf != 0) {
                 bool accepted = test_triangle<ANY>(a.sc, rs, tris + 3 * (size_t)(uint32_t)~leaf, rs.O, rs.D, 0xffffffffu, 0u);
-                leaf = 0;
-                if (ANY && accepted) { node = kEmpty; sp = 0; break; }
-                if (node < 0) { leaf = node; node = sp ? stack[--sp] : kEmpty; }
+                leaf = leaf2; leaf2 = 0;
+                if (ANY && accepted) { node = kEmpty; sp = 0; leaf = 0; break; }
+                if (leaf == 0 && node < 0) { leaf = node; node = sp ? stack[--sp] : kEmpty; }
             }
             uint32_t alive = __ballot_sync(0xffffffffu, node != kEmpty);
             if (alive == 0) break;
@@ -263,7 +281,7 @@ struct KernelSink {
     }
 };
 
-__global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+__global__ void __launch_bounds__(kBlock, 8) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < a.qcount[QE + bounce];
     bool cont = false;
@@ -279,7 +297,22 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Ren
         KernelSink sink{a, bounce, path};
         cont = shade_vertex(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
     }
-    uint32_t slot = queue_push(&a.qcount[QE + bounce + 1], cont);
+    // next-ray queue: ballot per warp, ONE atomicAdd per block (all threads of the block reach this point)
+    __shared__ uint32_t s_warp_cnt[kBlock / 32], s_warp_base[kBlock / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, cont);
+    if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) { s_warp_base[w] = total; total += s_warp_cnt[w]; }
+        uint32_t base = total ? atomicAdd(&a.qcount[QE + bounce + 1], total) : 0u;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) s_warp_base[w] += base;
+    }
+    __syncthreads();
+    uint32_t slot = s_warp_base[warp] + __popc(ballot & ((1u << lane) - 1u));
     if (cont) {
         a.ray_o_out[slot] = make_float4(nO.x, nO.y, nO.z, __uint_as_float(path));
         a.ray_d_out[slot] = make_float4(nD.x, nD.y, nD.z, 0.0f);
@@ -524,7 +557,10 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         a.frame_base = frame_first + done;
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream));
         a.ray_o_out = wf.ray_o[0].as<float4>(); a.ray_d_out = wf.ray_d[0].as<float4>(); a.ray_w_out = wf.ray_w[0].as<float4>();
-        LAUNCH_T(ctx, 0, k_raygen, (unsigned)((paths + kBlock - 1) / kBlock), kBlock, a);
+        {
+            const uint64_t gen_threads = (uint64_t)((ctx->width + 7) / 8) * ((ctx->height + 3) / 4) * 32 * slots;
+            LAUNCH_T(ctx, 0, k_raygen, (unsigned)((gen_threads + kBlock - 1) / kBlock), kBlock, a);
+        }
         if ((s = run_bounces(ctx, a, st, B, paths, capture))) return s;
         if (keep_ahead) { wf.ahead_slots = slots; wf.ahead_cursor = 0; wf.ahead_frame_first = frame_first; }
         else LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, 0u, slots);
