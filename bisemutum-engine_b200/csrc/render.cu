@@ -101,86 +101,27 @@ __global__ void __launch_bounds__(kBlock) k_probe_raygen(const __grid_constant__
     a.color[id] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
 }
 
-// ---- persistent while-while traversal (extend: rt_gbuffer.hlsl:7-36; connect: NEW shadow rays) ------
-// ncu on the one-thread-per-ray version showed 9.5/32 active lanes on incoherent bounces: rays of a warp
-// finish at very different times and node/leaf steps diverge. So: one resident grid, every warp keeps 32
-// traversal state machines and (a) runs all lanes through internal nodes until each holds a leaf
-// (while-while, leaf work is batched), (b) when fewer than kRefillThreshold rays are still in flight it
-// writes out the finished lanes and refills them from the queue (one atomicAdd per warp). Results do not
-// depend on the order (tie-break rule in bpt_trace.cuh).
-template <bool ANY>
-__global__ void __launch_bounds__(kBlock) k_trace_persistent(const __grid_constant__ RenderArgs a, uint32_t bounce) {
-    const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
-    uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
-    const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
-    const float4* __restrict__ qd = ANY ? a.sh_d : a.ray_d_in;
-    const uint32_t lane = threadIdx.x & 31;
-    int32_t stack[kStackSize];
-    Trav t;
-    t.done = true;
-    uint32_t ray = 0xffffffffu;       // queue index owned by this lane, or none
-    uint32_t path = 0;
-    bool exhausted = false;           // the queue has no more rays for this warp
-    for (;;) {
-        // ---- write out finished lanes, refill from the queue ----
-        if (ray != 0xffffffffu && t.done) {
-            if (ANY) {
-                if (!t.rs.found) {    // unoccluded: add the carried contribution to the path's per-sample colour
-                    float4 c = a.sh_c[ray];
-                    float* px = reinterpret_cast<float*>(a.color + path);
-                    atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
-                }
-            } else {
-                a.hit[ray] = make_float4(t.rs.found ? t.rs.tbest : -1.0f, t.rs.bu, t.rs.bv, __uint_as_float(t.rs.best_prim));
-                a.hit_slot[ray] = t.rs.best_slot;
-            }
-            ray = 0xffffffffu;
-        }
-        if (!exhausted) {
-            bool want = ray == 0xffffffffu;
-            uint32_t mask = __ballot_sync(0xffffffffu, want);
-            if (mask) {
-                uint32_t base = 0;
-                if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(cursor, (uint32_t)__popc(mask));
-                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
-                if (want) {
-                    uint32_t idx = base + __popc(mask & ((1u << lane) - 1u));
-                    if (idx < n) {
-                        float4 o = qo[idx], d = qd[idx];
-                        ray = idx;
-                        path = __float_as_uint(o.w);
-                        trav_begin(a.sc, t, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.001f, ANY ? d.w : a.sp.ray_length, a.frame_base + path / a.npx);
-                    }
-                }
-                if (base + (uint32_t)__popc(mask) >= n) exhausted = true;    // warp-uniform
-            }
-        }
-        if (__ballot_sync(0xffffffffu, ray != 0xffffffffu) == 0) break;
-        // ---- traverse ----
-        for (;;) {
-            while (!t.done && t.node >= 0) trav_node(a.sc, t, stack);
-            if (!t.done) trav_leaf<ANY>(a.sc, t, stack);
-            uint32_t alive = __ballot_sync(0xffffffffu, !t.done);
-            if (alive == 0) break;
-            if (!exhausted && __popc(alive) < kRefillThreshold) break;
-        }
-    }
-}
-
-// ---- merged-mode specialisation: speculative while-while (Aila & Laine 2009) -----------------------
-// One world-space BVH, no instance transitions, so the per-lane state is just (ray, node, postponed leaf,
-// stack). A lane that reaches a leaf POSTPONES it and keeps descending; the warp switches to the triangle
+// ---- persistent speculative while-while traversal (extend: rt_gbuffer.hlsl:7-36; connect: NEW shadow rays) ---
+// ncu on the one-thread-per-ray version showed 9.5/32 active lanes on incoherent bounces: rays of a warp finish at
+// very different times and node/leaf steps diverge. So: one resident grid; every warp keeps 32 traversal state
+// machines, finished lanes are written out and refilled from the queue (one atomicAdd per warp) once fewer than
+// kRefillThreshold rays are in flight. Results do not depend on the order (tie-break + cull margin, bpt_trace.cuh).
+// Speculative while-while (Aila & Laine 2009). Merged mode: one world-space BVH, the per-lane state is just
+// (ray, node, postponed leaves, stack). A lane that reaches a leaf POSTPONES it and keeps descending; the warp switches to the triangle
 // phase only when no lane is still searching, so both phases run with (nearly) all live lanes — the
 // one-step-at-a-time loop above measured 9.7/32 active lanes on incoherent bounces.
 constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this lane
-template <bool ANY>
-__global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+// TWO_LEVEL: TLAS leaves (instances) are entered at once — push kSentinel, switch to the object-space ray,
+// continue at the BLAS root — and only triangles are postponed. A lane never leaves an instance (pops the
+// sentinel) while it still holds postponed triangles of that instance: they need its object-space ray.
+template <bool ANY, bool TWO_LEVEL>
+__global__ void __launch_bounds__(kBlock, 8) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
     uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
     const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
     const float4* __restrict__ qd = ANY ? a.sh_d : a.ray_d_in;
-    const float4* __restrict__ nodes = a.m_nodes;
-    const float4* __restrict__ tris = a.m_tris;
+    const float4* __restrict__ nodes = TWO_LEVEL ? a.sc.tlas_nodes : a.m_nodes;
+    const float4* __restrict__ tris = TWO_LEVEL ? nullptr : a.m_tris;
     const uint32_t lane = threadIdx.x & 31;
     int32_t stack[kStackSize];
     RayState rs;
@@ -189,7 +130,35 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
     int32_t node = kEmpty, leaf = 0, leaf2 = 0;
     int sp = 0;
     uint32_t ray = 0xffffffffu, path = 0;
+    uint32_t slot = 0xffffffffu, inst_anyhit = 0;     // TWO_LEVEL: the instance being traversed
+    bool in_blas = !TWO_LEVEL;
     bool exhausted = false;
+
+    // Brings `node` into a state the node phase understands: enters instances, leaves them when allowed.
+    auto settle = [&]() {
+        if (!TWO_LEVEL) return;
+        for (;;) {
+            if (node == kSentinel) {
+                if (leaf != 0) return;                 // postponed triangles of this instance first
+                sp_ = make_space(rs.O, rs.D); nodes = a.sc.tlas_nodes; tris = nullptr; in_blas = false;
+                node = sp ? stack[--sp] : kEmpty;
+                continue;
+            }
+            if (node < 0 && !in_blas) {                // TLAS leaf: enter the instance
+                slot = __ldg(a.sc.tlas_prims + (uint32_t)~node);
+                const DInstance& in = a.sc.instances[slot];
+                const DBlas bl = a.sc.blas[in.blas];
+                inst_anyhit = in.anyhit;
+                sp_ = make_space(xf_point(in.w2o, rs.O), xf_vector(in.w2o, rs.D));
+                nodes = bl.nodes; tris = bl.tris; in_blas = true;
+                stack[sp++] = kSentinel;
+                node = bl.root;
+                continue;
+            }
+            return;
+        }
+    };
+
     for (;;) {
         if (ray != 0xffffffffu && node == kEmpty && leaf == 0) {          // finished: write out
             if (ANY) {
@@ -223,8 +192,14 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
                         rs.frame_index = a.frame_base + path / a.npx; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
                         sp_ = make_space(rs.O, rs.D);
                         sp = 0; leaf = 0; leaf2 = 0;
-                        node = a.m_n == 0 ? kEmpty : a.m_root;
-                        if (node < 0) { leaf = node; node = kEmpty; }      // single-triangle BVH: the root is a leaf
+                        if (TWO_LEVEL) {
+                            nodes = a.sc.tlas_nodes; tris = nullptr; in_blas = false; slot = 0xffffffffu;
+                            node = a.sc.tlas_n == 0 ? kEmpty : a.sc.tlas_root;
+                            settle();
+                        } else {
+                            node = a.m_n == 0 ? kEmpty : a.m_root;
+                        }
+                        if (node < 0 && node != kSentinel) { leaf = node; node = sp ? stack[--sp] : kEmpty; settle(); }   // root is a leaf
                     }
                 }
                 if (base + (uint32_t)__popc(mask) >= n) exhausted = true;  // warp-uniform
@@ -239,9 +214,11 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
                     int32_t next = node_step(nodes, node, sp_, rs.tmin, rs.tcull, stack, sp);
                     if (next == BPT_POP) next = sp ? stack[--sp] : kEmpty;
                     node = next;
-                    if (node < 0 && leaf2 == 0) {                         // postpone, keep descending
+                    settle();
+                    if (node < 0 && node != kSentinel && leaf2 == 0) {    // a triangle: postpone, keep descending
                         if (leaf == 0) leaf = node; else leaf2 = node;
                         node = sp ? stack[--sp] : kEmpty;
+                        settle();
                     }
                 }
                 bool searching = leaf == 0 && node >= 0 && node != kEmpty;
@@ -249,10 +226,13 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
             }
             // ---- triangle phase ----
             while (leaf != 0) {
-                bool accepted = test_triangle<ANY>(a.sc, rs, tris + 3 * (size_t)(uint32_t)~leaf, rs.O, rs.D, 0xffffffffu, 0u);
+                bool accepted = test_triangle<ANY>(a.sc, rs, tris + 3 * (size_t)(uint32_t)~leaf, sp_.O, sp_.D, TWO_LEVEL ? slot : 0xffffffffu, inst_anyhit);
                 leaf = leaf2; leaf2 = 0;
                 if (ANY && accepted) { node = kEmpty; sp = 0; leaf = 0; break; }
-                if (leaf == 0 && node < 0) { leaf = node; node = sp ? stack[--sp] : kEmpty; }
+                if (leaf == 0) {
+                    settle();                                            // a sentinel that was waiting for the triangles
+                    if (node < 0 && node != kSentinel) { leaf = node; node = sp ? stack[--sp] : kEmpty; settle(); }
+                }
             }
             uint32_t alive = __ballot_sync(0xffffffffu, node != kEmpty);
             if (alive == 0) break;
@@ -260,6 +240,12 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_merged(const __grid_constan
         }
     }
 }
+
+// the four instantiations (macro arguments cannot carry the template commas)
+static const auto k_extend_merged = k_trace_spec<false, false>;
+static const auto k_connect_merged = k_trace_spec<true, false>;
+static const auto k_extend_two_level = k_trace_spec<false, true>;
+static const auto k_connect_two_level = k_trace_spec<true, true>;
 
 // ---- shade: material + lighting + next direction, emits shadow rays and the next extend ray ---
 struct KernelSink {
@@ -496,11 +482,11 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
         int dev = 0, sms = 0, be = 0, ba = 0;
         BPT_CUDA_TRY(ctx, cudaGetDevice(&dev));
         BPT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_persistent<false>, kBlock, 0));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_persistent<true>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, true>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, true>, kBlock, 0));
         wf.grid_extend = (unsigned)(sms * std::max(be, 1)); wf.grid_connect = (unsigned)(sms * std::max(ba, 1));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_merged<false>, kBlock, 0));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_merged<true>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, false>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, false>, kBlock, 0));
         wf.grid_extend_m = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_m = (unsigned)(sms * std::max(ba, 1));
     }
     if (ctx->accel_mode == BPT_ACCEL_MERGED) {
@@ -519,12 +505,12 @@ static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_setting
     for (uint32_t i = 1; i < B; i++) {
         a.ray_o_in = wf.ray_o[cur].as<float4>(); a.ray_d_in = wf.ray_d[cur].as<float4>(); a.ray_w_in = wf.ray_w[cur].as<float4>();
         a.ray_o_out = wf.ray_o[cur ^ 1].as<float4>(); a.ray_d_out = wf.ray_d[cur ^ 1].as<float4>(); a.ray_w_out = wf.ray_w[cur ^ 1].as<float4>();
-        if (merged) LAUNCH_T(ctx, 1, k_trace_merged<false>, wf.grid_extend_m, kBlock, a, i);
-        else LAUNCH_T(ctx, 1, k_trace_persistent<false>, wf.grid_extend, kBlock, a, i);
+        if (merged) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i);
+        else LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i);
         LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
         if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
-            if (merged) LAUNCH_T(ctx, 3, k_trace_merged<true>, wf.grid_connect_m, kBlock, a, i);
-            else LAUNCH_T(ctx, 3, k_trace_persistent<true>, wf.grid_connect, kBlock, a, i);
+            if (merged) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
+            else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
         }
         if (capture && (s = capture_bounce(ctx, i, cur))) return s;
         cur ^= 1;
