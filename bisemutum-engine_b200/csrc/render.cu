@@ -11,6 +11,7 @@
 #include <algorithm>
 #include "bpt_internal.cuh"
 #include "bpt_shade.cuh"
+#pragma nv_diag_suppress 128   // "loop is not reachable": the two-level branch of the merged-mode instantiation
 
 using namespace bptd;
 
