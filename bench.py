@@ -324,8 +324,17 @@ def main():
             avg_s = kt.extend_ms * 1e-3 / kt.extend_launches
             achieved = per_ray * rays_per_launch / avg_s / 1e9
             total_k = kt.raygen_ms + kt.extend_ms + kt.shade_ms + kt.connect_ms + kt.other_ms
-            roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": None, "peak_source": peak_src, "bytes_per_ray": per_ray, "nodes_per_ray": nodes, "tris_per_ray": tris,
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r1_extend_traffic.json")
+            if os.path.exists(tpath) and (W, H, B, args.accel) == (WIDTH, HEIGHT, BOUNCES, "merged"):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                traffic, traffic_src = tj["traffic_bytes_per_launch"] / 1e9, tj["source"]     # GB per launch (dram read + write, ncu --set full)
+            roofline = {"bound": "hbm", "kernel": "k_trace_spec<false,false> (extend)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
+                        "algorithmic_gb_per_launch": per_ray * rays_per_launch / 1e9,
+                        "note": "frac > 1 is expected here: the 29 MB scene+BVH is L2-resident (traffic << algorithmic bytes); the kernel is issue/divergence-bound, see profiles/r1_v6_kernels.md",
+                        "peak_source": peak_src, "bytes_per_ray": per_ray, "nodes_per_ray": nodes, "tris_per_ray": tris,
                         "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_s * 1e3,
                         "kernel_time_share": {"raygen": kt.raygen_ms / total_k, "extend": kt.extend_ms / total_k, "shade": kt.shade_ms / total_k,
                                               "connect": kt.connect_ms / total_k, "other": kt.other_ms / total_k}}
