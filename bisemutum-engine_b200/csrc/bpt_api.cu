@@ -288,8 +288,8 @@ bpt_status bpt_render(bpt_context* c, const bpt_camera* cam, uint32_t first, uin
     NEED(c);
     if (!cam || !st) return BPT_ERR_INVALID;
     if (!c->accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
-    if (st->state_precision != BPT_STATE_FP32 || st->rect_shadow)
-        return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 and rect_shadow=mrp_ray are not implemented");
+    if (st->state_precision != BPT_STATE_FP32)
+        return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 is not implemented");
     return wavefront_render(c, *cam, first, ns, *st);
 }
 
@@ -297,8 +297,8 @@ bpt_status bpt_render_ahead(bpt_context* c, const bpt_camera* cam, uint32_t firs
     NEED(c);
     if (!cam || !st || !max_samples) return BPT_ERR_INVALID;
     if (!c->accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
-    if (st->state_precision != BPT_STATE_FP32 || st->rect_shadow)
-        return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 and rect_shadow=mrp_ray are not implemented");
+    if (st->state_precision != BPT_STATE_FP32)
+        return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 is not implemented");
     bpt_status s = wavefront_render(c, *cam, first, max_samples, *st, true);
     if (out_samples) *out_samples = c->wf.ahead_slots;
     return s;

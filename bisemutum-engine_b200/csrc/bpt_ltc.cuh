@@ -146,7 +146,7 @@ BPT_HD float4 ltc_edge(float3 v1, float3 v2) {                                  
     float3 c = cross3(v1, v2);
     return make_float4(c.x * k, c.y * k, c.z * k, c.z * k);
 }
-BPT_HD float ltc_integrate(float3 P, float3 N, float3 T, float3 B, const Mat3& Minv, const float3* L, bool two_sided) {   // lights.hlsl:383-423
+BPT_HD float ltc_integrate(float3 P, float3 N, float3 T, float3 B, const Mat3& Minv, const float3* L, bool two_sided, float3* mrp = nullptr) {   // lights.hlsl:383-423
     Mat3 TBN; TBN.r0 = T; TBN.r1 = B; TBN.r2 = N;
     float3 LP[5];
 #pragma unroll
@@ -164,12 +164,14 @@ BPT_HD float ltc_integrate(float3 P, float3 N, float3 T, float3 B, const Mat3& M
     if (n == 5) { e = ltc_edge(LP[4], LP[0]); sum.x += e.x; sum.y += e.y; sum.z += e.z; sum.w += e.w; }
     float integral = two_sided ? fabsf(sum.w) : tmax_(0.0f, sum.w);
     if (!is_finite1(integral)) integral = 0.0f;
+    // most representative point direction, lights.hlsl:420 with the identity matrix: mul(sum.xyz, TBN) = x*T + y*B + z*N
+    if (mrp) *mrp = normalize3((sum.x * T + sum.y * B) + sum.z * N);
     return integral;
 }
 
 // rect_light_eval_ltc (lights.hlsl:449-513) + surface_eval_lut
 BPT_HD float3 eval_rect_light(const DScene& sc, const bpt_rect_light_data& light, float3 P, float3 N, float3 T, float3 B, float3 V,
-                              const Surface& s, uint32_t surface_model) {
+                              const Surface& s, uint32_t surface_model, float3* diff_mrp = nullptr) {
     float rx, ry;
     aniso_roughness(s.roughness, s.anisotropy, rx, ry);
     float3 lv = v3(dot3(V, T), dot3(V, B), dot3(V, N));
@@ -180,7 +182,7 @@ BPT_HD float3 eval_rect_light(const DScene& sc, const bpt_rect_light_data& light
                        v3(light.position1[0], light.position1[1], light.position1[2]), v3(light.position0[0], light.position0[1], light.position0[2])};
         float3 emission = v3(light.emission[0], light.emission[1], light.emission[2]);
         Mat3 I; I.r0 = v3(1, 0, 0); I.r1 = v3(0, 1, 0); I.r2 = v3(0, 0, 1);
-        diff = emission * ltc_integrate(P, N, T, B, I, L, light.two_sided != 0);
+        diff = emission * ltc_integrate(P, N, T, B, I, L, light.two_sided != 0, diff_mrp);
         Mat3 M;
         ltc_matrix_and_brdf(sc, lv, rx, ry, L, M, brdf);
         Mat3 Minv = mat3_inverse(M);

@@ -20,6 +20,7 @@ struct ShadeParams {
     uint32_t nee_mode;
     float ray_length;
     uint32_t russian_roulette; // NEW switch, default off
+    uint32_t rect_shadow;      // NEW switch: 1 = one shadow ray per rect light towards its most representative point
     uint32_t diffuse_only;     // probe tracing: light every vertex as surface_data_diffuse(base_color) (ddgi/deferred_lighting.hlsl:44)
 };
 
@@ -58,8 +59,19 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     }
     float3 V = normalize3(O - P);                                       // deferred_lighting_secondary.hlsl:45
 
-    for (uint32_t l = 0; l < sc.num_rect; l++)                          // :72-96 (unshadowed, as the reference)
-        sink.add(eval_rect_light(sc, sc.rect_lights[l], P, N, T, B, V, surf, surface_model) * Wt);
+    for (uint32_t l = 0; l < sc.num_rect; l++) {                        // :72-96 (unshadowed, as the reference, unless rect_shadow)
+        const bpt_rect_light_data& rl = sc.rect_lights[l];
+        float3 mrp = v3s(0.0f);
+        float3 c = eval_rect_light(sc, rl, P, N, T, B, V, surf, surface_model, sp.rect_shadow ? &mrp : nullptr) * Wt;
+        if (!sp.rect_shadow) { sink.add(c); continue; }
+        if (!(max3c(c) > 0.0f)) continue;
+        // distance to the light's plane along mrp (as rect_light_sample_texture, lights.hlsl:425-438)
+        float3 ln = v3(rl.normal[0], rl.normal[1], rl.normal[2]);
+        float step = fabsf(dot3(mrp, ln));
+        if (!(step >= 0.0001f)) { sink.add(c); continue; }
+        float dist = fabsf(dot3(P - v3(rl.position2[0], rl.position2[1], rl.position2[2]), ln));
+        sink.shadow(P, mrp, (dist / step) * 0.999f, c, sc.num_dir + sc.num_point + l);
+    }
     for (uint32_t l = 0; l < sc.num_dir; l++) {                         // :51-60
         const bpt_dir_light_data& li = sc.dir_lights[l];
         float3 L = v3(li.direction[0], li.direction[1], li.direction[2]);

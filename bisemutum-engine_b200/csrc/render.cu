@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ 
 // over more paths. Bounded by a path budget and by the shadow-queue footprint.
 static uint32_t wave_slots(const bpt_context* ctx) {
     const uint64_t npx = (uint64_t)ctx->width * ctx->height;
-    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point, 1);
+    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point + ctx->num_rect, 1);
     uint64_t by_paths = std::max<uint64_t>(1, (1ull << 24) / npx);                 // <= 16.7 M paths in flight
     uint64_t by_shadow = std::max<uint64_t>(1, (8ull << 30) / (npx * nl * 48));    // <= 8 GiB of shadow-ray records
     return (uint32_t)std::min<uint64_t>(std::min(by_paths, by_shadow), 64);
@@ -425,7 +425,7 @@ bpt_status wavefront_alloc(bpt_context* ctx) {
         if ((s = dev_alloc(ctx, wf.totals, 40 * sizeof(uint64_t)))) return s;
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.totals.p, 0, 40 * sizeof(uint64_t), ctx->stream));
     }
-    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point, 1);
+    const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point + ctx->num_rect, 1);   // rect lights may emit rays (rect_shadow)
     const uint64_t need = paths * nl;
     if (wf.shadow_capacity < need) {
         if (need * 48 > (64ull << 30)) { ctx->err = "shadow-ray queue would exceed 64 GiB; reduce lights or resolution"; return BPT_ERR_OOM; }
@@ -473,7 +473,7 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
     WavefrontState& wf = ctx->wf;
     a.sc = ctx->scene_view();
     a.sp.width = ctx->width; a.sp.height = ctx->height; a.sp.max_bounces = B; a.sp.nee_mode = st.nee_mode; a.sp.ray_length = st.ray_length;
-    a.sp.diffuse_only = 0; a.sp.russian_roulette = st.russian_roulette; a.pixel_jitter = st.pixel_jitter;
+    a.sp.diffuse_only = 0; a.sp.russian_roulette = st.russian_roulette; a.sp.rect_shadow = st.rect_shadow; a.pixel_jitter = st.pixel_jitter;
     a.hit = wf.hit.as<float4>(); a.hit_slot = wf.hit_slot.as<uint32_t>();
     a.sh_o = wf.sh_o.as<float4>(); a.sh_d = wf.sh_d.as<float4>(); a.sh_c = wf.sh_c.as<float4>();
     a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();
@@ -509,7 +509,7 @@ static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_setting
         if (merged) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i);
         else LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i);
         LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
-        if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point) > 0) {
+        if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point + (st.rect_shadow ? ctx->num_rect : 0)) > 0) {
             if (merged) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
             else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
         }

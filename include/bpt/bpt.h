@@ -281,7 +281,8 @@ enum { BPT_RECT_SHADOW_OFF = 0, BPT_RECT_SHADOW_MRP_RAY = 1 };
 enum { BPT_STATE_FP32 = 0, BPT_STATE_REFERENCE_FP16 = 1 };
 
 /* BasicRenderer::PathTracingSettings (renderer/basic.hpp:76-81) + the mode switches of
- * SURVEY.md §0. Defaults (all-zero switches) are the parity configuration. */
+ * SURVEY.md §0. Defaults (all-zero switches) are the parity configuration. Implemented: nee_mode,
+ * rect_shadow, russian_roulette, pixel_jitter; state_precision = reference_fp16 returns BPT_ERR_UNSUPPORTED. */
 typedef struct bpt_settings {
     float ray_length;        /* 100 */
     uint32_t max_bounces;    /* clamped to [2,16] as path_tracing.cpp:187,290 */

@@ -155,7 +155,7 @@ static inline f4 ltc_integrate_edge(f3 v1, f3 v2) {
     return f4{c.x * tdst, c.y * tdst, c.z * tdst, c.z * tdst};
 }
 // lights.hlsl:383-423 (mrp is only consumed by the unsupported light-texture lookup)
-static inline float ltc_integrate(f3 P, f3 N, f3 T, f3 B, const m33& ltc_matrix_inv, const f3 L[4], bool two_sided) {
+static inline float ltc_integrate(f3 P, f3 N, f3 T, f3 B, const m33& ltc_matrix_inv, const f3 L[4], bool two_sided, f3* mrp = nullptr) {
     m33 TBN{T, B, N};
     f3 LP[5];
     for (int k = 0; k < 4; k++) LP[k] = mul(ltc_matrix_inv, mul(TBN, L[k] - P));
@@ -172,12 +172,14 @@ static inline float ltc_integrate(f3 P, f3 N, f3 T, f3 B, const m33& ltc_matrix_
     if (n == 5) acc(ltc_integrate_edge(LP[4], LP[0]));
     float integral = two_sided ? fabsf(sum.w) : fmax_(0.0f, sum.w);
     if (!std::isfinite(integral)) integral = 0.0f;
+    // lights.hlsl:420 with the identity matrix (the diffuse lobe): mrp = normalize(mul(sum.xyz, TBN)) = x*T + y*B + z*N
+    if (mrp) *mrp = normalize((sum.x * T + sum.y * B) + sum.z * N);
     return integral;
 }
 
 // rect_light_eval_ltc (lights.hlsl:449-513) + surface_eval_lut (deferred_lighting_secondary.hlsl:80-96)
 static inline f3 ltc_rect_light(const Scene& sc, const bpt_rect_light_data& light, f3 P, f3 N, f3 T, f3 B, f3 V,
-                                const SurfaceData& surf, uint32_t surface_model) {
+                                const SurfaceData& surf, uint32_t surface_model, f3* diff_mrp = nullptr) {
     float rx, ry;
     get_anisotropic_roughness(surf.roughness, surf.anisotropy, rx, ry);
     f3 local_v = mk3(dot(V, T), dot(V, B), dot(V, N));
@@ -188,7 +190,7 @@ static inline f3 ltc_rect_light(const Scene& sc, const bpt_rect_light_data& ligh
                    mk3(light.position1[0], light.position1[1], light.position1[2]), mk3(light.position0[0], light.position0[1], light.position0[2])};
         f3 emission = mk3(light.emission[0], light.emission[1], light.emission[2]);
         m33 identity{mk3(1, 0, 0), mk3(0, 1, 0), mk3(0, 0, 1)};
-        float integral_diff = ltc_integrate(P, N, T, B, identity, L, light.two_sided != 0);
+        float integral_diff = ltc_integrate(P, N, T, B, identity, L, light.two_sided != 0, diff_mrp);
         ltc_diff = emission * integral_diff;
         m33 ltc_matrix;
         get_ltc_matrix_and_brdf(sc, local_v, rx, ry, L, ltc_matrix, ltc_brdf);

@@ -268,8 +268,23 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             if (ctx.capture) out.cap_s.push_back({i, pixel, light_index});
             if (!trace_any(sc, P, L, 0.001f, tmax, frame_index, out.shd)) out.pending.push_back(c);
         };
-        for (size_t l = 0; l < sc.rect_lights.size(); l++)                                  // deferred_lighting_secondary.hlsl:72-96
-            add(ltc_rect_light(sc, sc.rect_lights[l], P, N, T, Bv, V, surf, surface_model) * Wt);
+        for (size_t l = 0; l < sc.rect_lights.size(); l++) {                                // deferred_lighting_secondary.hlsl:72-96
+            const bpt_rect_light_data& rl = sc.rect_lights[l];
+            f3 mrp = splat3(0.0f);
+            f3 c = ltc_rect_light(sc, rl, P, N, T, Bv, V, surf, surface_model, st.rect_shadow ? &mrp : nullptr) * Wt;
+            if (!st.rect_shadow) { add(c); continue; }                                      // reference: rect lights are unshadowed
+            // NEW switch rect_shadow = mrp_ray: one shadow ray towards the most representative point of the diffuse lobe;
+            // distance to the light's plane as in rect_light_sample_texture (lights.hlsl:425-438)
+            if (!(fmax_(c.x, fmax_(c.y, c.z)) > 0.0f)) continue;
+            f3 ln = mk3(rl.normal[0], rl.normal[1], rl.normal[2]);
+            float step = fabsf(dot(mrp, ln));
+            if (!(step >= 0.0001f)) { add(c); continue; }
+            float dist = fabsf(dot(P - mk3(rl.position2[0], rl.position2[1], rl.position2[2]), ln));
+            out.shd_per_bounce[i]++;
+            uint32_t light_index = (uint32_t)(sc.dir_lights.size() + sc.point_lights.size() + l);
+            if (ctx.capture) out.cap_s.push_back({i, pixel, light_index});
+            if (!trace_any(sc, P, mrp, 0.001f, (dist / step) * 0.999f, frame_index, out.shd)) out.pending.push_back(c);
+        }
         for (size_t l = 0; l < sc.dir_lights.size(); l++) {                                 // deferred_lighting_secondary.hlsl:51-60
             const bpt_dir_light_data& li = sc.dir_lights[l];
             direct(mk3(li.emission[0], li.emission[1], li.emission[2]), mk3(li.direction[0], li.direction[1], li.direction[2]), st.ray_length, (uint32_t)l);
@@ -501,7 +516,7 @@ bpt_status obpt_clear_accum(obpt_context* c) { CHECK_CTX(c); std::fill(c->accum.
 bpt_status obpt_render(obpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t ns, const bpt_settings* st) {
     CHECK_CTX(c); if (!cam || !st) return BPT_ERR_INVALID;
     if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
-    if (st->state_precision != BPT_STATE_FP32 || st->rect_shadow) return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 and rect_shadow=mrp_ray are not implemented");
+    if (st->state_precision != BPT_STATE_FP32) return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 is not implemented");
     render_impl<float>(*c, *cam, first, ns, *st, c->accum.data(), true);
     return BPT_OK;
 }

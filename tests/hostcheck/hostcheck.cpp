@@ -125,7 +125,7 @@ __attribute__((visibility("default")))
 int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t height, uint32_t frame_first, uint32_t nsamples,
               const bpt_settings* st, float* accum_rgba) {
     Built b; build(*h, b);
-    ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = std::min(std::max(st->max_bounces, 2u), 16u); sp.nee_mode = st->nee_mode; sp.ray_length = st->ray_length; sp.diffuse_only = 0; sp.russian_roulette = st->russian_roulette;
+    ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = std::min(std::max(st->max_bounces, 2u), 16u); sp.nee_mode = st->nee_mode; sp.ray_length = st->ray_length; sp.diffuse_only = 0; sp.russian_roulette = st->russian_roulette; sp.rect_shadow = st->rect_shadow;
     for (uint32_t s = 0; s < nsamples; s++)
         for (uint32_t p = 0; p < width * height; p++) {
             float3 O, D, W = v3s(1.0f);
@@ -150,7 +150,7 @@ __attribute__((visibility("default")))
 int hc_trace_probes(const hc_scene* h, const bpt_probe_volume* vol, const float* table, uint32_t frame_index, uint32_t num_bounces, float* out) {
     Built b; build(*h, b);
     ShadeParams sp; sp.width = 0; sp.height = 0; sp.max_bounces = std::min(std::max(num_bounces, 1u), 15u) + 1; sp.nee_mode = BPT_NEE_SHADOW_RAY;
-    sp.ray_length = vol->ray_length; sp.diffuse_only = 1; sp.russian_roulette = 0;
+    sp.ray_length = vol->ray_length; sp.diffuse_only = 1; sp.russian_roulette = 0; sp.rect_shadow = 0;
     uint64_t total = (uint64_t)vol->probe_counts[0] * vol->probe_counts[1] * vol->probe_counts[2] * vol->rays_per_probe;
     for (uint64_t p = 0; p < total; p++) {
         float3 O, D, W = v3s(1.0f);

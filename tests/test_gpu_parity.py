@@ -296,4 +296,24 @@ def test_mode_switches(lib, oracle, switch):
     ca, cb = gpu.counters(), ref.counters()
     assert ca.extend_rays == cb.extend_rays and ca.shadow_rays == cb.shadow_rays
     with pytest.raises(capi.BptError):
-        gpu.render(cam, 0, 1, capi.Settings(rect_shadow=1))
+        gpu.render(cam, 0, 1, capi.Settings(state_precision=1))             # reference_fp16: rejected, not ignored
+
+
+def test_rect_shadow_switch(lib, oracle):
+    """rect_shadow = mrp_ray: one shadow ray per rect light towards its most representative point."""
+    import os
+    luts = scenes.load_ltc_luts(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ltc_luts.npz"))
+    scene = scenes.add_mixed_lights(scenes.small_test_scene(), 4, 3, luts, keep_dir_lights=True, light_range=12.0)
+    W, H = 80, 56
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_TWO_LEVEL)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=4, rect_shadow=1)
+    gpu.render(cam, 1, 2, st); ref.render(cam, 1, 2, st)
+    a, b = gpu.resolve(2), ref.resolve(2)
+    assert (np.abs(a - b) / np.maximum(np.abs(b), 1e-3)).max() <= 1e-4
+    ca, cb = gpu.counters(), ref.counters()
+    assert ca.shadow_rays == cb.shadow_rays and ca.extend_rays == cb.extend_rays
+    base = oracle.OracleContext(W, H); base.upload_scene(scene, capi.ACCEL_TWO_LEVEL)
+    base.render(cam, 1, 2, capi.Settings(max_bounces=4))
+    assert cb.shadow_rays > base.counters().shadow_rays                     # the rect lights now cast rays
+    assert (b[..., :3] <= base.resolve(2)[..., :3] + 1e-5).all()            # shadowing never adds light

@@ -115,10 +115,10 @@ def test_probe_tracing_bit_exact(oracle, mode):
     assert (ref[:, 3] > 0).any() and (ref[:, 3] < 0).any() and np.isfinite(ref).all()
 
 
-@pytest.mark.parametrize("switch", ["russian_roulette", "pixel_jitter"])
+@pytest.mark.parametrize("switch", ["russian_roulette", "pixel_jitter", "rect_shadow"])
 def test_mode_switches_bit_exact(oracle, switch):
     """The NEW switches of SURVEY §0 (default off) are implemented identically on both sides."""
-    scene = _scene("small")
+    scene = _scene("mixed" if switch == "rect_shadow" else "small")
     W, H = 36, 24
     ctx = oracle.OracleContext(W, H); ctx.upload_scene(scene, capi.ACCEL_MERGED)
     cam = oracle.camera_matrices(scene.camera, W, H)
