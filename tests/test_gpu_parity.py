@@ -317,3 +317,35 @@ def test_rect_shadow_switch(lib, oracle):
     base.render(cam, 1, 2, capi.Settings(max_bounces=4))
     assert cb.shadow_rays > base.counters().shadow_rays                     # the rect lights now cast rays
     assert (b[..., :3] <= base.resolve(2)[..., :3] + 1e-5).all()            # shadowing never adds light
+
+
+def test_update_tlas_and_resize(lib, oracle):
+    """The reference rebuilds its TLAS every frame (render_graph.cpp:818-825): move instances, bpt_update_tlas,
+    compare with the oracle doing the same; then bpt_resize drops the history and renders at the new extent."""
+    scene = scenes.instanced(24, 12, 2)
+    W, H = 64, 40
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_TWO_LEVEL)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=4, ray_length=1000.0)
+    rng = np.random.default_rng(5)
+    moved = scene.instances.copy()
+    for i in range(len(moved) - 1):
+        moved[i]["transform"][:, 3] += rng.uniform(-1.0, 1.0, 3).astype(np.float32)
+    for ctx in (gpu, ref):
+        ctx.upload_instances(moved)
+        ctx.update_tlas()
+    assert_bvh_equal(gpu.read_bvh(capi.BVH_TLAS), ref.read_bvh(capi.BVH_TLAS))
+    gpu.render(cam, 0, 1, st); ref.render(cam, 0, 1, st)
+    a = gpu.resolve(1)
+    np.testing.assert_array_equal(a, ref.resolve(1))
+    # moving instances changed the picture
+    still = oracle.OracleContext(W, H); still.upload_scene(scene, capi.ACCEL_TWO_LEVEL); still.render(cam, 0, 1, st)
+    assert (a != still.resolve(1)).any()
+    W2, H2 = 48, 48
+    for ctx in (gpu, ref):
+        ctx._call("resize", W2, H2); ctx.width, ctx.height = W2, H2
+    cam2 = engine.camera_matrices(scene.camera, W2, H2)
+    gpu.render(cam2, 3, 1, st); ref.render(cam2, 3, 1, st)
+    np.testing.assert_array_equal(gpu.resolve(1), ref.resolve(1))           # history was dropped: exactly one sample
+    with pytest.raises(capi.BptError):
+        merged = capi.Context(lib, 8, 8); merged.upload_scene(scene, capi.ACCEL_MERGED); merged.update_tlas()
