@@ -121,6 +121,10 @@ class ProbeVolume(C.Structure):
                 ("extent", C.c_float * 3), ("ray_length", C.c_float), ("probe_counts", C.c_uint32 * 3), ("rays_per_probe", C.c_uint32)]
 
 
+class ProbeBlend(C.Structure):
+    _fields_ = [("irradiance_size", C.c_uint32), ("visibility_size", C.c_uint32), ("alpha", C.c_float), ("history_valid", C.c_uint32)]
+
+
 class BptError(RuntimeError):
     def __init__(self, status: int, where: str, detail: str):
         super().__init__(f"{where}: {STATUS_NAMES.get(status, status)} — {detail}")
@@ -159,6 +163,7 @@ COMMON_API = {
     "debug_capture": [_VP, _U32],
     "debug_read_queue": [_VP, _U32, _U32, _VP, _VP, _VP, _U64, _PU64],
     "trace_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _VP],
+    "blend_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _VP, C.POINTER(ProbeBlend), _VP, _VP],
 }
 # Exported by the CUDA library only.
 BPT_ONLY_API = {
@@ -326,6 +331,18 @@ class Context:
         assert table.shape == (8192, 2)
         self._call("trace_probes", C.byref(volume), _ptr(table), frame_index, num_bounces, _ptr(out))
         return out
+
+    def blend_probes(self, volume: ProbeVolume, sample_table, frame_index, rays, irradiance=None, visibility=None,
+                     irradiance_size=6, visibility_size=14, alpha=0.97):
+        """Returns (irradiance atlas (H, W, 4), visibility atlas (H, W, 2)); pass the previous atlases to blend temporally."""
+        nx, ny, nz = volume.probe_counts[0], volume.probe_counts[1], volume.probe_counts[2]
+        hist = irradiance is not None and visibility is not None
+        irr = np.ascontiguousarray(irradiance, f32).copy() if hist else np.zeros((nz * (irradiance_size + 2), nx * ny * (irradiance_size + 2), 4), f32)
+        vis = np.ascontiguousarray(visibility, f32).copy() if hist else np.zeros((nz * (visibility_size + 2), nx * ny * (visibility_size + 2), 2), f32)
+        bl = ProbeBlend(irradiance_size, visibility_size, alpha, 1 if hist else 0)
+        self._call("blend_probes", C.byref(volume), _ptr(np.ascontiguousarray(sample_table, f32)), frame_index,
+                   _ptr(np.ascontiguousarray(rays, f32)), C.byref(bl), _ptr(irr), _ptr(vis))
+        return irr, vis
 
     def debug_capture(self, enable: bool):
         self._call("debug_capture", 1 if enable else 0)

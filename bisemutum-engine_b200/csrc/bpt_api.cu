@@ -427,4 +427,11 @@ bpt_status bpt_trace_probes(bpt_context* c, const bpt_probe_volume* vol, const f
     return wavefront_trace_probes(c, *vol, table, frame, bounces, out);
 }
 
+bpt_status bpt_blend_probes(bpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, const float* rays,
+                            const bpt_probe_blend* blend, float* irr, float* vis) {
+    NEED(c);
+    if (!vol || !table || !rays || !blend || !irr || !vis) return BPT_ERR_INVALID;
+    return launch_blend_probes(c, *vol, table, frame, rays, *blend, irr, vis);
+}
+
 } // extern "C"

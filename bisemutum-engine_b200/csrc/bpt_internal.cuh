@@ -109,5 +109,7 @@ bpt_status wavefront_alloc(bpt_context* ctx);
 bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st, bool keep_ahead = false);
 bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count);
 bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, uint32_t num_bounces, float* h_out);
+bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, const float* h_rays,
+                               const bpt_probe_blend& bl, float* h_irr, float* h_vis);
 bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out);
 bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t n, uint32_t frame_index, bpt_hit* h_hits, uint8_t* h_visible);

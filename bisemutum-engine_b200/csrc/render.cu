@@ -11,6 +11,7 @@
 #include <algorithm>
 #include "bpt_internal.cuh"
 #include "bpt_shade.cuh"
+#include "bpt_ddgi.cuh"
 #pragma nv_diag_suppress 128   // "loop is not reachable": the two-level branch of the merged-mode instantiation
 
 using namespace bptd;
@@ -354,6 +355,47 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ 
     }
 }
 
+// ---- DDGI probe blending: one block per probe, one thread per octahedral texel --------------------
+template <bool VIS>
+__global__ void k_probe_blend(const __grid_constant__ bpt_probe_volume vol, const float2* __restrict__ table, uint32_t frame_index,
+                              const float4* __restrict__ rays, uint32_t size, float alpha, uint32_t history_valid, float* __restrict__ atlas) {
+    extern __shared__ float4 s_mem[];
+    const uint32_t nrays = vol.rays_per_probe, probe = blockIdx.x;
+    float4* s_rad = s_mem;
+    float3* s_dir = reinterpret_cast<float3*>(s_mem + nrays);
+    for (uint32_t r = threadIdx.x; r < nrays; r += blockDim.x) {
+        float3 O, D;
+        probe_ray(vol, table, probe * nrays + r, frame_index, O, D);
+        float4 v = rays[(size_t)probe * nrays + r];
+        s_rad[r] = v;
+        s_dir[r] = blend_trace_dir(O, D, v.w);
+    }
+    __syncthreads();
+    const bool active = threadIdx.x < size * size;       // (block size is rounded up to a warp multiple)
+    const uint32_t tx = threadIdx.x % size, ty = active ? threadIdx.x / size : 0;
+    float3 val = active ? blend_texel<VIS>(tx, ty, size, s_dir, s_rad, nrays) : v3s(0.0f);
+    const uint32_t nx = vol.probe_counts[0], ny = vol.probe_counts[1];
+    const uint32_t ix = probe % nx, iy = (probe / nx) % ny, iz = probe / nx / ny;
+    const uint32_t stride = nx * ny * (size + 2), ch = VIS ? 2 : 4;
+    const uint32_t sx = (iy * nx + ix) * (size + 2), sy = iz * (size + 2);
+    const uint32_t cx = tx + 1, cy = ty + 1;
+    auto at = [&](uint32_t x, uint32_t y) { return atlas + ((size_t)(sy + y) * stride + (sx + x)) * ch; };
+    if (history_valid && active) {
+        const float* h = at(cx, cy);
+        val.x = temporal_blend(val.x, h[0], alpha); val.y = temporal_blend(val.y, h[1], alpha);
+        if (!VIS) val.z = temporal_blend(val.z, h[2], alpha);
+    }
+    auto put = [&](uint32_t x, uint32_t y) { float* o = at(x, y); o[0] = val.x; o[1] = val.y; if (!VIS) { o[2] = val.z; o[3] = 1.0f; } };
+    __syncthreads();     // every history texel of this probe has been read before borders are overwritten
+    if (!active) return;
+    put(cx, cy);
+    uint32_t bx, by;
+    border_coord(cx, cy, size, bx, by);
+    put(bx, by);
+    uint32_t c[4];
+    if (corner_coords(cx, cy, size, c)) { put(c[0], c[1]); put(c[2], c[3]); }
+}
+
 } // namespace
 
 #define LAUNCH(ctx, kernel, grid, block, ...)                                   \
@@ -625,5 +667,34 @@ bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     dev_free(rays); dev_free(out);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}
+
+bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, const float* h_rays,
+                               const bpt_probe_blend& bl, float* h_irr, float* h_vis) {
+    const uint32_t nprobes = vol.probe_counts[0] * vol.probe_counts[1] * vol.probe_counts[2];
+    const uint64_t nrays = (uint64_t)nprobes * vol.rays_per_probe;
+    if (!nprobes || !vol.rays_per_probe || bl.irradiance_size < 2 || bl.visibility_size < 2 || bl.irradiance_size > 30 || bl.visibility_size > 30 ||
+        vol.rays_per_probe > 1024) { ctx->err = "blend_probes: bad sizes"; return BPT_ERR_INVALID; }
+    const size_t irr_bytes = (size_t)vol.probe_counts[0] * vol.probe_counts[1] * (bl.irradiance_size + 2) * vol.probe_counts[2] * (bl.irradiance_size + 2) * 16;
+    const size_t vis_bytes = (size_t)vol.probe_counts[0] * vol.probe_counts[1] * (bl.visibility_size + 2) * vol.probe_counts[2] * (bl.visibility_size + 2) * 8;
+    DevBuf table, rays, irr, vis;
+    bpt_status s = BPT_OK;
+    auto cleanup = [&]() { dev_free(table); dev_free(rays); dev_free(irr); dev_free(vis); };
+    if ((s = dev_upload(ctx, table, h_table, 8192 * sizeof(float2))) || (s = dev_upload(ctx, rays, h_rays, nrays * 16)) ||
+        (s = dev_upload(ctx, irr, h_irr, irr_bytes)) || (s = dev_upload(ctx, vis, h_vis, vis_bytes))) { cleanup(); return s; }
+    const size_t smem = (size_t)vol.rays_per_probe * (16 + 12);
+    auto threads = [](uint32_t size) { return ((size * size + 31) / 32) * 32; };
+    k_probe_blend<false><<<nprobes, threads(bl.irradiance_size), smem, ctx->stream>>>(vol, table.as<float2>(), frame_index, rays.as<float4>(), bl.irradiance_size,
+                                                                                     bl.alpha, bl.history_valid, irr.as<float>());
+    k_probe_blend<true><<<nprobes, threads(bl.visibility_size), smem, ctx->stream>>>(vol, table.as<float2>(), frame_index, rays.as<float4>(), bl.visibility_size,
+                                                                                    bl.alpha, bl.history_valid, vis.as<float>());
+    ctx->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_irr, irr.p, irr_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_vis, vis.p, vis_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) { ctx->err = std::string("blend_probes: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
     return BPT_OK;
 }

@@ -388,6 +388,22 @@ BPT_API bpt_status bpt_trace_probes(
     bpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2 /* 8192 float2 */,
     uint32_t frame_index, uint32_t num_bounces, float* out_radiance_dist);
 
+/* DDGI probe blending (ddgi/probe_blend_irradiance.hlsl, probe_blend_visibility.hlsl):
+ * gathers the per-ray output of bpt_trace_probes into octahedral atlases with a 1-texel border,
+ *   irradiance: rgba32f, width = nx*ny*(irradiance_size+2), height = nz*(irradiance_size+2)   (reference: 6)
+ *   visibility: rg32f,   width = nx*ny*(visibility_size+2), height = nz*(visibility_size+2)   (reference: 14)
+ * probe (ix,iy,iz) starts at ((iy*nx + ix), iz) * (size+2). When history_valid != 0 the atlases are read as the
+ * previous frame and blended with alpha (reference 0.97) in gamma-5 space; they are overwritten with the result. */
+typedef struct bpt_probe_blend {
+    uint32_t irradiance_size, visibility_size;
+    float alpha;
+    uint32_t history_valid;
+} bpt_probe_blend;
+BPT_API bpt_status bpt_blend_probes(
+    bpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2, uint32_t frame_index,
+    const float* ray_radiance_dist /* output of bpt_trace_probes */, const bpt_probe_blend* blend,
+    float* irradiance_atlas_rgba32f, float* visibility_atlas_rg32f);
+
 #ifdef __cplusplus
 }
 #endif

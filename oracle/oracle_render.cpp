@@ -648,6 +648,103 @@ bpt_status obpt_trace_probes(obpt_context* c, const bpt_probe_volume* vol, const
     return BPT_OK;
 }
 
+// ---- DDGI probe blending: ddgi/probe_blend_irradiance.hlsl:11-80, probe_blend_visibility.hlsl:10-78 ----
+namespace {
+f3 oct_decode_01(float fx, float fy) {                                   // core/utils/pack.hlsl:94-102
+    float x = fx * 2.0f - 1.0f, y = fy * 2.0f - 1.0f;
+    f3 n = mk3(x, y, (1.0f - fabsf(x)) - fabsf(y));
+    float t = clampf(-n.z, 0.0f, 1.0f);
+    n.x = n.x + (n.x >= 0.0f ? -t : t);
+    n.y = n.y + (n.y >= 0.0f ? -t : t);
+    return normalize(n);
+}
+// pow(x, 1/5), pow(x, 5), pow(x, 50) in the fixed-order forms of the numeric contract
+float root5(float x) {
+    if (!(x > 0.0f)) return 0.0f;
+    int32_t i = (int32_t)f2u(x);
+    float y = u2f((uint32_t)((i - 0x3f800000) / 5 + 0x3f800000));
+    for (int k = 0; k < 6; k++) { float y2 = y * y; float y4 = y2 * y2; y = (4.0f * y + x / y4) * 0.2f; }
+    return y;
+}
+float pow5f(float x) { float x2 = x * x; return (x2 * x2) * x; }
+float pow50f(float x) { float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8, x32 = x16 * x16; return (x32 * x16) * x2; }
+float temporal(float cur, float hist, float alpha) { return pow5f(lerpf(root5(cur), root5(hist), alpha)); }   // gamma = 5
+void border_coord(uint32_t cx, uint32_t cy, uint32_t size, uint32_t& bx, uint32_t& by) {                      // probe_blend_common.hlsl:3-26
+    bx = cx; by = cy;
+    if (cx == 1) { if (cy == 1) { bx = size + 1; by = size + 1; } else if (cy == size) { bx = size + 1; by = 0; } else { bx = 0; by = size + 1 - cy; } }
+    else if (cx == size) { if (cy == 1) { bx = 0; by = size + 1; } else if (cy == size) { bx = 0; by = 0; } else { bx = size + 1; by = size + 1 - cy; } }
+    else if (cy == 1) { bx = size + 1 - cx; by = 0; }
+    else if (cy == size) { bx = size + 1 - cx; by = size + 1; }
+}
+bool corner_coords(uint32_t cx, uint32_t cy, uint32_t size, uint32_t c[4]) {                                   // probe_blend_common.hlsl:28-50
+    if (cx == 1) { if (cy == 1) { c[0] = size; c[1] = 0; c[2] = 0; c[3] = size; return true; } if (cy == size) { c[0] = 0; c[1] = 1; c[2] = size; c[3] = size + 1; return true; } }
+    else if (cx == size) { if (cy == 1) { c[0] = 1; c[1] = 0; c[2] = size + 1; c[3] = size; return true; } if (cy == size) { c[0] = size + 1; c[1] = 1; c[2] = 1; c[3] = size + 1; return true; } }
+    return false;
+}
+} // namespace
+
+bpt_status obpt_blend_probes(obpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, const float* rays,
+                             const bpt_probe_blend* bl, float* irr, float* vis) {
+    CHECK_CTX(c); if (!vol || !table || !rays || !bl || !irr || !vis) return BPT_ERR_INVALID;
+    const uint32_t nx = vol->probe_counts[0], ny = vol->probe_counts[1], nz = vol->probe_counts[2], nr = vol->rays_per_probe;
+    if (!nx || !ny || !nz || !nr || bl->irradiance_size < 2 || bl->visibility_size < 2) return fail(c, BPT_ERR_INVALID, "blend_probes: bad sizes");
+    std::vector<f3> dirs(nr);
+    for (uint32_t probe = 0; probe < nx * ny * nz; probe++) {
+        uint32_t ix = probe % nx, iy = (probe / nx) % ny, iz = probe / nx / ny;
+        float mx = (float)(nx > 1 ? nx - 1 : 1), my = (float)(ny > 1 ? ny - 1 : 1), mz = (float)(nz > 1 ? nz - 1 : 1);
+        f3 fx = mk3(vol->frame_x[0], vol->frame_x[1], vol->frame_x[2]), fy = mk3(vol->frame_y[0], vol->frame_y[1], vol->frame_y[2]), fz = mk3(vol->frame_z[0], vol->frame_z[1], vol->frame_z[2]);
+        f3 O = ((mk3(vol->base_position[0], vol->base_position[1], vol->base_position[2]) + ((float)ix * vol->extent[0] / mx) * fx) + ((float)iy * vol->extent[1] / my) * fy) +
+               ((float)iz * vol->extent[2] / mz) * fz;
+        const float* pr = rays + 4ull * probe * nr;
+        for (uint32_t r = 0; r < nr; r++) {
+            uint32_t seed = rng_tea(probe, frame);
+            uint32_t rand_index = ((uint32_t)(rng_next(seed) * 8192.0f) + r) % 8192u;
+            f3 D = uniform_sphere_sample(table[2 * rand_index], table[2 * rand_index + 1]);
+            float t = pr[4 * r + 3];
+            dirs[r] = t < 0.0f ? D : normalize((O + D * t) - O);                                 // probe_blend_irradiance.hlsl:49
+        }
+        for (int pass = 0; pass < 2; pass++) {
+            const bool visp = pass == 1;
+            const uint32_t size = visp ? bl->visibility_size : bl->irradiance_size, ch = visp ? 2 : 4;
+            const uint32_t stride = nx * ny * (size + 2), sx = (iy * nx + ix) * (size + 2), sy = iz * (size + 2);
+            float* atlas = visp ? vis : irr;
+            auto at = [&](uint32_t x, uint32_t y) { return atlas + ((size_t)(sy + y) * stride + (sx + x)) * ch; };
+            std::vector<f3> vals(size * size);
+            for (uint32_t ty = 0; ty < size; ty++)
+                for (uint32_t tx = 0; tx < size; tx++) {
+                    f3 probe_dir = oct_decode_01(((float)tx + 0.5f) / (float)size, ((float)ty + 0.5f) / (float)size);
+                    f3 sum = splat3(0.0f); float wsum = 0.0f;
+                    for (uint32_t r = 0; r < nr; r++) {
+                        float w = fmax_(dot(probe_dir, dirs[r]), 0.0f);
+                        if (visp) {                                                               // probe_blend_visibility.hlsl:45-50
+                            w = pow50f(w);
+                            float dist = pr[4 * r + 3] < 0.0f ? 1e6f : pr[4 * r + 3];
+                            sum.x += w * dist; sum.y += w * (dist * dist);
+                        } else sum = sum + w * mk3(pr[4 * r], pr[4 * r + 1], pr[4 * r + 2]);       // probe_blend_irradiance.hlsl:50-52
+                        wsum += w;
+                    }
+                    f3 v = wsum == 0.0f ? splat3(0.0f) : sum / wsum;
+                    if (bl->history_valid) {
+                        const float* h = at(tx + 1, ty + 1);
+                        v.x = temporal(v.x, h[0], bl->alpha); v.y = temporal(v.y, h[1], bl->alpha);
+                        if (!visp) v.z = temporal(v.z, h[2], bl->alpha);
+                    }
+                    vals[ty * size + tx] = v;
+                }
+            for (uint32_t ty = 0; ty < size; ty++)
+                for (uint32_t tx = 0; tx < size; tx++) {
+                    f3 v = vals[ty * size + tx];
+                    auto put = [&](uint32_t x, uint32_t y) { float* o = at(x, y); o[0] = v.x; o[1] = v.y; if (!visp) { o[2] = v.z; o[3] = 1.0f; } };
+                    uint32_t cx = tx + 1, cy = ty + 1, bx, by, cc[4];
+                    put(cx, cy);
+                    border_coord(cx, cy, size, bx, by); put(bx, by);
+                    if (corner_coords(cx, cy, size, cc)) { put(cc[0], cc[1]); put(cc[2], cc[3]); }
+                }
+        }
+    }
+    return BPT_OK;
+}
+
 uint32_t obpt_rng_tea(uint32_t a, uint32_t b) { return rng_tea(a, b); }
 uint32_t obpt_rng_lcg(uint32_t* s) { return rng_lcg(*s); }
 void obpt_sincos_2pi(float u, float* s, float* c) { sincos_2pi(u, *s, *c); }

@@ -53,6 +53,7 @@ def lib():
         _lib.hc_render.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.POINTER(capi.Settings), C.c_void_p]
         _lib.hc_trace_probes.argtypes = [C.POINTER(HcScene), C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.hc_blend_probes.argtypes = [C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(capi.ProbeBlend), C.c_void_p, C.c_void_p]
         _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -114,3 +115,12 @@ class HostScene:
         out = np.zeros((n, 4), np.float32)
         lib().hc_trace_probes(C.byref(self.h), C.byref(volume), table.ctypes.data_as(C.c_void_p), frame_index, num_bounces, out.ctypes.data_as(C.c_void_p))
         return out
+
+
+def blend_probes(volume, table, frame_index, rays, irr, vis, irradiance_size=6, visibility_size=14, alpha=0.97, history_valid=0):
+    """Host build of bpt_ddgi.cuh; irr / vis are modified in place (pass copies)."""
+    bl = capi.ProbeBlend(irradiance_size, visibility_size, alpha, history_valid)
+    lib().hc_blend_probes(C.byref(volume), np.ascontiguousarray(table, np.float32).ctypes.data_as(C.c_void_p), frame_index,
+                          np.ascontiguousarray(rays, np.float32).ctypes.data_as(C.c_void_p), C.byref(bl),
+                          irr.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p))
+    return irr, vis

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <vector>
 #include "../../bisemutum-engine_b200/csrc/bpt_shade.cuh"
+#include "../../bisemutum-engine_b200/csrc/bpt_ddgi.cuh"
 
 using namespace bptd;
 
@@ -181,6 +182,49 @@ int hc_trace(const hc_scene* h, const bpt_ray* rays, uint64_t n, uint32_t frame_
             hits[i] = bpt_hit{t.t, t.u, t.v, t.hit ? b.inst[t.slot].instance_id : 0xffffffffu, t.hit ? t.prim : 0xffffffffu};
         }
         if (visible) visible[i] = trace_ray<true>(b.sc, O, D, rays[i].tmin, rays[i].tmax, frame_index).hit ? 0 : 1;
+    }
+    return 0;
+}
+
+// Probe blending: the per-texel device functions of bpt_ddgi.cuh driven like k_probe_blend drives them.
+__attribute__((visibility("default")))
+int hc_blend_probes(const bpt_probe_volume* vol, const float* table, uint32_t frame_index, const float* rays, const bpt_probe_blend* bl, float* irr, float* vis) {
+    const uint32_t nx = vol->probe_counts[0], ny = vol->probe_counts[1], nz = vol->probe_counts[2], nr = vol->rays_per_probe;
+    std::vector<float3> dirs(nr); std::vector<float4> rad(nr);
+    for (uint32_t probe = 0; probe < nx * ny * nz; probe++) {
+        for (uint32_t r = 0; r < nr; r++) {
+            float3 O, D;
+            probe_ray(*vol, reinterpret_cast<const float2*>(table), probe * nr + r, frame_index, O, D);
+            const float* p = rays + 4ull * (probe * nr + r);
+            rad[r] = make_float4(p[0], p[1], p[2], p[3]);
+            dirs[r] = blend_trace_dir(O, D, p[3]);
+        }
+        const uint32_t ix = probe % nx, iy = (probe / nx) % ny, iz = probe / nx / ny;
+        for (int pass = 0; pass < 2; pass++) {
+            const bool visp = pass == 1;
+            const uint32_t size = visp ? bl->visibility_size : bl->irradiance_size, ch = visp ? 2 : 4;
+            const uint32_t stride = nx * ny * (size + 2), sx = (iy * nx + ix) * (size + 2), sy = iz * (size + 2);
+            float* atlas = visp ? vis : irr;
+            auto at = [&](uint32_t x, uint32_t y) { return atlas + ((size_t)(sy + y) * stride + (sx + x)) * ch; };
+            std::vector<float3> vals(size * size);
+            for (uint32_t t = 0; t < size * size; t++) {
+                uint32_t tx = t % size, ty = t / size;
+                float3 v = visp ? blend_texel<true>(tx, ty, size, dirs.data(), rad.data(), nr) : blend_texel<false>(tx, ty, size, dirs.data(), rad.data(), nr);
+                if (bl->history_valid) {
+                    const float* h = at(tx + 1, ty + 1);
+                    v.x = temporal_blend(v.x, h[0], bl->alpha); v.y = temporal_blend(v.y, h[1], bl->alpha);
+                    if (!visp) v.z = temporal_blend(v.z, h[2], bl->alpha);
+                }
+                vals[t] = v;
+            }
+            for (uint32_t t = 0; t < size * size; t++) {
+                uint32_t cx = t % size + 1, cy = t / size + 1, bx, by, c[4];
+                float3 v = vals[t];
+                auto put = [&](uint32_t x, uint32_t y) { float* o = at(x, y); o[0] = v.x; o[1] = v.y; if (!visp) { o[2] = v.z; o[3] = 1.0f; } };
+                put(cx, cy); border_coord(cx, cy, size, bx, by); put(bx, by);
+                if (corner_coords(cx, cy, size, c)) { put(c[0], c[1]); put(c[2], c[3]); }
+            }
+        }
     }
     return 0;
 }

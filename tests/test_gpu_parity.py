@@ -349,3 +349,21 @@ def test_update_tlas_and_resize(lib, oracle):
     np.testing.assert_array_equal(gpu.resolve(1), ref.resolve(1))           # history was dropped: exactly one sample
     with pytest.raises(capi.BptError):
         merged = capi.Context(lib, 8, 8); merged.upload_scene(scene, capi.ACCEL_MERGED); merged.update_tlas()
+
+
+def test_probe_blending_parity(lib, oracle):
+    """SURVEY §8f rank 1 on the device: trace → blend → blend with history, bit-exact against the oracle."""
+    scene = scenes.small_test_scene()
+    gpu, ref = make_pair(lib, oracle, scene, 32, 32, capi.ACCEL_MERGED)
+    table = scenes.ddgi_sample_randoms()
+    vol = scenes.probe_volume(scene, (8, 8, 8), 64, ray_length=100.0)       # the reference's 8^3 probes x 64 rays
+    ra, rb = gpu.trace_probes(vol, table, 0, 1), ref.trace_probes(vol, table, 0, 1)
+    np.testing.assert_array_equal(ra, rb)
+    ia, va = gpu.blend_probes(vol, table, 0, ra)
+    ib, vb = ref.blend_probes(vol, table, 0, rb)
+    np.testing.assert_array_equal(ia, ib); np.testing.assert_array_equal(va, vb)
+    assert ia.shape == (64, 512, 4) and va.shape == (128, 1024, 2)          # ddgi.hpp:70-78 atlas sizes
+    r1 = gpu.trace_probes(vol, table, 1, 1)
+    ia2, va2 = gpu.blend_probes(vol, table, 1, r1, ia, va)
+    ib2, vb2 = ref.blend_probes(vol, table, 1, r1, ib, vb)
+    np.testing.assert_array_equal(ia2, ib2); np.testing.assert_array_equal(va2, vb2)

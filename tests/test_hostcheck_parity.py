@@ -133,3 +133,29 @@ def test_mode_switches_bit_exact(oracle, switch):
         assert ctx.counters().extend_rays < base.counters().extend_rays          # fewer rays on dark paths
     with pytest.raises(capi.BptError):
         ctx.render(cam, 0, 1, capi.Settings(state_precision=1))                 # rejected, not silently ignored
+
+
+def test_probe_blending_bit_exact(oracle):
+    """DDGI probe blending: irradiance / visibility octahedral gathers, gamma-5 temporal blend,
+    border + corner copies — CUDA source (host build) vs oracle, plus structural properties of the atlases."""
+    scene = _scene("small")
+    table = scenes.ddgi_sample_randoms()
+    vol = scenes.probe_volume(scene, (3, 2, 2), 64, ray_length=100.0)
+    ctx = oracle.OracleContext(8, 8); ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    rays0, rays1 = ctx.trace_probes(vol, table, 0, 2), ctx.trace_probes(vol, table, 1, 2)
+    irr0, vis0 = ctx.blend_probes(vol, table, 0, rays0)
+    assert irr0.shape == (2 * 8, 3 * 2 * 8, 4) and vis0.shape == (2 * 16, 3 * 2 * 16, 2)
+    h_irr, h_vis = HC.blend_probes(vol, table, 0, rays0, np.zeros_like(irr0), np.zeros_like(vis0))
+    np.testing.assert_array_equal(h_irr, irr0); np.testing.assert_array_equal(h_vis, vis0)
+    irr1, vis1 = ctx.blend_probes(vol, table, 1, rays1, irr0, vis0)                      # temporal blend, alpha 0.97
+    h_irr, h_vis = HC.blend_probes(vol, table, 1, rays1, irr0.copy(), vis0.copy(), history_valid=1)
+    np.testing.assert_array_equal(h_irr, irr1); np.testing.assert_array_equal(h_vis, vis1)
+    assert np.isfinite(irr1).all() and np.isfinite(vis1).all()
+    assert 0 < np.abs(irr1 - irr0).max() < 0.2 * irr0.max()                               # history dominates (alpha = 0.97)
+    p = irr0[0:8, 0:8, :3]                                                                # first probe: 6x6 interior + border
+    np.testing.assert_array_equal(p[0, 0], p[6, 6]); np.testing.assert_array_equal(p[7, 7], p[1, 1])   # corners: diagonally opposite interior
+    np.testing.assert_array_equal(p[0, 2], p[1, 5])                                       # top border row mirrors the first interior row
+    # a uniform radiance field gives that radiance back in every texel (weights normalise)
+    flat = rays0.copy(); flat[:, :3] = (0.25, 0.5, 1.0)
+    irr_flat, _ = ctx.blend_probes(vol, table, 0, flat)
+    np.testing.assert_allclose(irr_flat[..., :3], np.broadcast_to(np.float32([0.25, 0.5, 1.0]), irr_flat[..., :3].shape), rtol=2e-6)
