@@ -52,10 +52,11 @@ assert RECT_LIGHT.itemsize == 112 and BVH_NODE.itemsize == 64 and RAY.itemsize =
 VA_POSITION, VA_NORMAL, VA_TANGENT, VA_COLOR, VA_TEXCOORD, VA_TEXCOORD2 = 1, 2, 4, 8, 16, 32
 INSTANCE_FORCE_OPAQUE, INSTANCE_FORCE_NON_OPAQUE = 4, 8
 MATERIAL_KIND_GLTF_PBR, MATERIAL_KIND_ASSIMP_DIFFUSE, MATERIAL_KIND_DEFAULT = 0, 1, 2
+MATERIAL_KIND_CONSTANT_COLOR, MATERIAL_KIND_CHECKERBOARD, MATERIAL_KIND_TEXTURED, MATERIAL_KIND_TRANSPARENT, MATERIAL_KIND_CAGE = 3, 4, 5, 6, 7
 SURFACE_MODEL_UNLIT, SURFACE_MODEL_LIT = 0, 1
 BLEND_OPAQUE, BLEND_ALPHA_TEST, BLEND_TRANSLUCENT = 0, 1, 2
 MATERIAL_FLAG_TWO_SIDED = 1
-TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32_FLOAT = 0, 1
+TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32_FLOAT, TEXTURE_RGBA8_SRGB = 0, 1, 2
 ADDRESS_REPEAT, ADDRESS_CLAMP = 0, 1
 ACCEL_TWO_LEVEL, ACCEL_MERGED = 0, 1
 NEE_SHADOW_RAY, NEE_NONE = 0, 1

@@ -1,6 +1,7 @@
 // bpt_api.cu — the C ABI of include/bpt/bpt.h: context, scene upload, accel build, render, debug.
 // Each entry point cites the reference interface it replaces in the header.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include "bpt_internal.cuh"
@@ -154,10 +155,23 @@ bpt_status bpt_scene_upload_materials(bpt_context* c, const bpt_material* m, uin
     c->d_texels.assign(nt, DevBuf{});
     std::vector<DTexture> table(std::max(nt, 1u));
     for (uint32_t i = 0; i < nt; i++) {
-        if (!t[i].texels || !t[i].width || !t[i].height || t[i].format > BPT_TEXTURE_RGBA32_FLOAT) return fail(c, BPT_ERR_INVALID, "bad texture desc");
-        size_t bytes = (size_t)t[i].width * t[i].height * (t[i].format == BPT_TEXTURE_RGBA8_UNORM ? 4 : 16);
-        if ((s = dev_upload(c, c->d_texels[i], t[i].texels, bytes))) return s;
-        table[i] = DTexture{c->d_texels[i].p, t[i].width, t[i].height, t[i].format, t[i].address_mode_u, t[i].address_mode_v, t[i].filter_linear};
+        if (!t[i].texels || !t[i].width || !t[i].height || t[i].format > BPT_TEXTURE_RGBA8_SRGB) return fail(c, BPT_ERR_INVALID, "bad texture desc");
+        uint32_t fmt = t[i].format;
+        if (fmt == BPT_TEXTURE_RGBA8_SRGB) {
+            // decode to linear FP32 texels once (the sampler decodes before filtering): 256-entry sRGB EOTF table
+            float lut[256];
+            for (int k = 0; k < 256; k++) { double v = k / 255.0; lut[k] = (float)(v <= 0.04045 ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4)); }
+            const uint8_t* src = static_cast<const uint8_t*>(t[i].texels);
+            std::vector<float> lin((size_t)t[i].width * t[i].height * 4);
+            for (size_t k = 0; k < lin.size(); k += 4) { lin[k] = lut[src[k]]; lin[k + 1] = lut[src[k + 1]]; lin[k + 2] = lut[src[k + 2]]; lin[k + 3] = (float)src[k + 3] / 255.0f; }
+            if ((s = dev_upload(c, c->d_texels[i], lin.data(), lin.size() * 4))) return s;
+            BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            fmt = BPT_TEXTURE_RGBA32_FLOAT;
+        } else {
+            size_t bytes = (size_t)t[i].width * t[i].height * (fmt == BPT_TEXTURE_RGBA8_UNORM ? 4 : 16);
+            if ((s = dev_upload(c, c->d_texels[i], t[i].texels, bytes))) return s;
+        }
+        table[i] = DTexture{c->d_texels[i].p, t[i].width, t[i].height, fmt, t[i].address_mode_u, t[i].address_mode_v, t[i].filter_linear};
     }
     if ((s = dev_upload(c, c->d_textures, table.data(), table.size() * sizeof(DTexture)))) return s;
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));

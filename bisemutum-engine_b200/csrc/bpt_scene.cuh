@@ -149,7 +149,7 @@ BPT_HD float3 sample_sky(const DScene& sc, float3 d) {
 }
 
 // ---- vertex fetch (core/raytracing/hit.hlsl:27-164) ---------------------------------------------
-struct HitVertex { float3 normal_world, tangent_world, bitangent_world; float2 texcoord; };
+struct HitVertex { float3 normal_world, tangent_world, bitangent_world, position_world; float2 texcoord; };
 
 BPT_HD void load_tri_indices(const DScene& sc, const bpt_drawable_sbt_data& dr, uint32_t prim, uint32_t idx[3]) {
     const uint32_t* p = sc.indices + (size_t)dr.index_offset + 3ull * prim;
@@ -165,7 +165,7 @@ BPT_HD float2 load_texcoord(const DScene& sc, const bpt_drawable_sbt_data& dr, u
     return make_float2(bary_mix(t0.x, t1.x, t2.x, bu, bv), bary_mix(t0.y, t1.y, t2.y, bu, bv));
 }
 BPT_HD float3 load3(const float* p) { return v3(BPT_LDG(p), BPT_LDG(p + 1), BPT_LDG(p + 2)); }
-BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_t prim, float bu, float bv) {
+BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_t prim, float bu, float bv, bool need_position) {
     const bpt_drawable_sbt_data& dr = sc.drawables[in.instance_id];
     uint32_t va = BPT_LDG(sc.drawable_va + in.instance_id);
     uint32_t idx[3];
@@ -190,11 +190,19 @@ BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_
     hv.tangent_world = normalize3(xf_vector(in.o2w, tangent));                       // hit.hlsl:158
     hv.bitangent_world = normalize3(cross3(hv.normal_world, hv.tangent_world)) * tangent_w;   // hit.hlsl:159
     hv.texcoord = load_texcoord(sc, dr, va, idx, bu, bv);
+    hv.position_world = v3s(0.0f);
+    if (need_position) {                                                             // hit.hlsl:34-52,152
+        const float* b = sc.positions + dr.position_offset;
+        float3 p0 = load3(b + 3ull * idx[0]), p1 = load3(b + 3ull * idx[1]), p2 = load3(b + 3ull * idx[2]);
+        float3 p = v3(bary_mix(p0.x, p1.x, p2.x, bu, bv), bary_mix(p0.y, p1.y, p2.y, bu, bv), bary_mix(p0.z, p1.z, p2.z, bu, bv));
+        hv.position_world = xf_point(in.o2w, p);
+    }
     return hv;
 }
 
 // ---- material_function: closed set of the reference's HLSL snippets -----------------------------
-BPT_HD Surface eval_material(const DScene& sc, const bpt_material& m, float2 uv) {
+BPT_HD bool material_needs_position(const bpt_material& m) { return ((m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu) == BPT_MATERIAL_KIND_CHECKERBOARD; }
+BPT_HD Surface eval_material(const DScene& sc, const bpt_material& m, float2 uv, float3 position_world) {
     Surface s = surface_default();
     uint32_t kind = (m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu;
     if (kind == BPT_MATERIAL_KIND_GLTF_PBR) {                                        // import_model.cpp:208-230
@@ -216,6 +224,29 @@ BPT_HD Surface eval_material(const DScene& sc, const bpt_material& m, float2 uv)
     } else if (kind == BPT_MATERIAL_KIND_ASSIMP_DIFFUSE) {                           // import_model.cpp:490-493
         s.base_color = v3(m.base_color[0], m.base_color[1], m.base_color[2]);
         s.roughness = m.roughness;
+    } else if (kind == BPT_MATERIAL_KIND_CONSTANT_COLOR) {                           // examples/scene_basic/materials/white.toml
+        s.base_color = v3(m.base_color[0], m.base_color[1], m.base_color[2]);
+    } else if (kind == BPT_MATERIAL_KIND_CHECKERBOARD) {                             // .../checkerboard.toml
+        int grid = (int)floorf(position_world.x) ^ (int)floorf(position_world.z);
+        bool odd = (grid & 1) == 1;
+        s.base_color = odd ? v3(m.base_color[0], m.base_color[1], m.base_color[2]) : v3(m.emission[0], m.emission[1], m.emission[2]);
+        s.roughness = odd ? m.base_color[3] : m.roughness;
+    } else if (kind == BPT_MATERIAL_KIND_TEXTURED) {                                 // .../textured.toml
+        float4 bt = sample_or(sc, m.base_color_tex, uv, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+        float4 nt = sample_or(sc, m.normal_map_tex, uv, make_float4(0.5f, 0.5f, 1.0f, 1.0f));
+        s.base_color = v3(bt.x, bt.y, bt.z);
+        s.normal_map_value = v3(nt.x, nt.y, nt.z);
+        s.roughness = m.roughness;
+    } else if (kind == BPT_MATERIAL_KIND_TRANSPARENT) {                              // .../transparent.toml
+        s.base_color = v3(m.base_color[0], m.base_color[1], m.base_color[2]);
+        s.opacity = m.base_color[3];
+        s.two_sided = true;
+    } else if (kind == BPT_MATERIAL_KIND_CAGE) {                                     // .../cage.toml
+        float4 v = sample_or(sc, m.base_color_tex, uv, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+        s.base_color = v3(v.x, v.y, v.z);
+        s.f0_color = v3(v.x, v.y, v.z);
+        s.opacity = v.w < 0.5f ? 0.0f : 1.0f;
+        s.two_sided = true;
     }
     return s;
 }
@@ -225,7 +256,7 @@ BPT_HD float eval_hit_opacity(const DScene& sc, uint32_t instance_id, uint32_t p
     uint32_t idx[3];
     load_tri_indices(sc, dr, prim, idx);
     float2 uv = load_texcoord(sc, dr, BPT_LDG(sc.drawable_va + instance_id), idx, bu, bv);
-    return eval_material(sc, m, uv).opacity;
+    return eval_material(sc, m, uv, v3s(0.0f)).opacity;
 }
 
 // ---- point / spot light (lights.hlsl:14-25) -----------------------------------------------------

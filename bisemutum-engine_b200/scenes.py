@@ -558,3 +558,59 @@ def probe_volume(scene: SceneData, counts=(32, 32, 16), rays_per_probe: int = 25
     v.probe_counts[:] = list(counts)
     v.rays_per_probe = rays_per_probe
     return v
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's own example project (examples/scene_basic): its three .biasset meshes, its five
+# materials and its scene.toml placement. The asset bytes travel as tests/golden/scene_basic.npz
+# (made by tests/golden/make_scene_basic_fixture.py); transforms follow Transform (TRS, rotation =
+# glm::eulerAngleZXY(z, x, y) in degrees → radians, src/math/transform.cpp:98-123).
+# ---------------------------------------------------------------------------------------------
+def _euler_zxy(deg):
+    x, y, z = np.radians(np.asarray(deg, np.float64))
+    cx, sx, cy, sy, cz, sz = np.cos(x), np.sin(x), np.cos(y), np.sin(y), np.cos(z), np.sin(z)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    return Rz @ Rx @ Ry
+
+
+def _trs(translation, rotation_deg, scaling):
+    m = np.eye(4)
+    m[:3, :3] = _euler_zxy(rotation_deg) @ np.diag(scaling)
+    m[:3, 3] = translation
+    return m
+
+
+def scene_basic(npz_path: str) -> SceneData:
+    z = np.load(npz_path)
+    b = SceneBuilder("scene_basic")
+
+    def mesh(name):
+        idx = z[f"{name}.indices"].reshape(-1, 3).astype(u32)
+        return b.add_mesh((z[f"{name}.positions"], z[f"{name}.normals"], z[f"{name}.tangents"], z[f"{name}.texcoords"], idx))
+    plane, cube, sphere = mesh("plane"), mesh("cube"), mesh("sphere")
+    t_earth = b.add_texture(z["earth_diffuse_srgb"], fmt=capi.TEXTURE_RGBA8_SRGB)
+    t_normal = b.add_texture(z["earth_normal"], fmt=capi.TEXTURE_RGBA8_UNORM)
+    t_cage = b.add_texture(z["cage"], fmt=capi.TEXTURE_RGBA8_UNORM)
+    K = capi
+    checker = b.add_material((0.8, 0.8, 0.8, 1.0), roughness=0.1, kind=K.MATERIAL_KIND_CHECKERBOARD)     # base_color.a = roughness_0 = 1.0
+    b.materials[checker]["emission"] = (0.1, 0.1, 0.1)                                                   # base_color_1; roughness_1 = 0.1
+    textured = b.add_material(roughness=0.2, kind=K.MATERIAL_KIND_TEXTURED, base_color_tex=t_earth, normal_map_tex=t_normal)
+    white = b.add_material((1.0, 1.0, 1.0), kind=K.MATERIAL_KIND_CONSTANT_COLOR)
+    transparent = b.add_material((1.0, 0.0, 0.5, 0.5), kind=K.MATERIAL_KIND_TRANSPARENT, blend=K.BLEND_TRANSLUCENT, two_sided=True)
+    cage = b.add_material(kind=K.MATERIAL_KIND_CAGE, blend=K.BLEND_ALPHA_TEST, two_sided=True, base_color_tex=t_cage)
+    # scene.toml objects, in file order (drawable index = order of StaticMeshRenderSystem's view)
+    b.add_drawable(sphere, textured, _trs((-1.0, 0.0, 1.0), (0, 0, 0), (1, 1, 1)))
+    b.add_drawable(cube, white, _trs((1.0, 0.0, -1.0), (0.0, 30.000001907348633, 0.0), (1, 1, 1)))
+    b.add_drawable(cube, transparent, _trs((2.5, 0.01, 2.5), (0.0, 30.000001907348633, 0.0), (1, 1, 1)))
+    b.add_drawable(cube, cage, _trs((1.0, 2.5, -1.0), (0.0, 30.000001907348633, 0.0), (1, 1, 1)))
+    b.add_drawable(plane, checker, _trs((0.0, -1.0, 0.0), (0, 0, 0), (5.0, 1.0, 5.0)))
+    # Dir Light: rotation (10, 0, -30) deg; lights point along local +Y (lights.cpp:61); colour (1, .9, .8) x strength 4
+    light_dir = _euler_zxy((10.000005722045898, 0.0, -30.000001907348633)) @ np.array([0.0, 1.0, 0.0])
+    # Camera: looks down local -Z, up +Y (camera_system.cpp:17-29); yfov 30, near 0.01, far 1e4, 1298 x 635 target
+    R = _euler_zxy((-9.3324127197265625, 63.346549987792969, 17.90446662902832))
+    cam = dict(position=(10.5, 4.5, 6.0), front_dir=tuple(R @ np.array([0.0, 0.0, -1.0])), up_dir=tuple(R @ np.array([0.0, 1.0, 0.0])),
+               yfov=30.0, near_z=0.010000000707805157, far_z=10000.0)
+    return b.finish(dir_lights=dir_light(light_dir, (1.0, 0.89999997615814209, 0.80000001192092896), 4.0), camera=cam,
+                    sky_faces=procedural_sky(32, light_dir), bounds=(np.array([-5.0, -1.0, -5.0]), np.array([5.0, 3.5, 5.0])))

@@ -142,7 +142,14 @@ BPT_API bpt_status bpt_scene_upload_instances(bpt_context* ctx, const bpt_instan
 enum {
     BPT_MATERIAL_KIND_GLTF_PBR = 0,        /* import_model.cpp:208-230 */
     BPT_MATERIAL_KIND_ASSIMP_DIFFUSE = 1,  /* import_model.cpp:490-493 (base_color, roughness) */
-    BPT_MATERIAL_KIND_DEFAULT = 2          /* surface_data_default, material/utils.hlsl:18-31 */
+    BPT_MATERIAL_KIND_DEFAULT = 2,         /* surface_data_default, material/utils.hlsl:18-31 */
+    /* the five materials of the reference's example project (examples/scene_basic/materials/*.toml) */
+    BPT_MATERIAL_KIND_CONSTANT_COLOR = 3,  /* white.toml: base_color = PARAM_base_color */
+    BPT_MATERIAL_KIND_CHECKERBOARD = 4,    /* checkerboard.toml: world-space xz checker. base_color.rgb = base_color_0,
+                                              base_color.a = roughness_0, emission.rgb = base_color_1, roughness = roughness_1 */
+    BPT_MATERIAL_KIND_TEXTURED = 5,        /* textured.toml: base_color_tex, normal_map_tex (raw texel), roughness */
+    BPT_MATERIAL_KIND_TRANSPARENT = 6,     /* transparent.toml: base_color.rgb, opacity = base_color.a, two-sided */
+    BPT_MATERIAL_KIND_CAGE = 7             /* cage.toml: base = f0 = tex.rgb, opacity = tex.a < 0.5 ? 0 : 1, two-sided */
 };
 enum { BPT_SURFACE_MODEL_UNLIT = 0, BPT_SURFACE_MODEL_LIT = 1 };         /* material.hlsl:3-5 */
 enum { BPT_BLEND_OPAQUE = 0, BPT_BLEND_ALPHA_TEST = 1, BPT_BLEND_TRANSLUCENT = 2 };
@@ -169,7 +176,8 @@ typedef struct bpt_material {
     int32_t occlusion_tex;
 } bpt_material;
 
-enum { BPT_TEXTURE_RGBA8_UNORM = 0, BPT_TEXTURE_RGBA32_FLOAT = 1 };
+/* RGBA8_SRGB (rhi format rgba8_srgb) is decoded to linear FP32 texels at upload (256-entry table), then filtered. */
+enum { BPT_TEXTURE_RGBA8_UNORM = 0, BPT_TEXTURE_RGBA32_FLOAT = 1, BPT_TEXTURE_RGBA8_SRGB = 2 };
 enum { BPT_ADDRESS_REPEAT = 0, BPT_ADDRESS_CLAMP = 1 };
 typedef struct bpt_texture_desc {
     const void* texels;   /* level 0 only (hit shaders have no derivatives → level 0) */

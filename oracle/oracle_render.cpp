@@ -82,7 +82,7 @@ static inline f3 sample_sky(const Scene& sc, f3 d) {
 }
 
 // ---- vertex fetch: core/raytracing/hit.hlsl:27-164 ---------------------------------------------
-struct Vertex { f3 normal_world, tangent_world, bitangent_world; f2 texcoord; };
+struct Vertex { f3 normal_world, tangent_world, bitangent_world, position_world; f2 texcoord; };
 
 static inline void fetch_indices(const Scene& sc, const bpt_drawable_sbt_data& dr, uint32_t prim, uint32_t idx[3]) {
     for (int c = 0; c < 3; c++) idx[c] = sc.indices[(size_t)dr.index_offset + 3ull * prim + c];   // hit.hlsl:28-32
@@ -121,11 +121,16 @@ static Vertex fetch_vertex_attributes(const Scene& sc, const InstanceXf& x, uint
     vt.tangent_world = normalize(xf_vector(x.o2w, tangent));                                       // hit.hlsl:158
     vt.bitangent_world = normalize(cross(vt.normal_world, vt.tangent_world)) * tangent_w;          // hit.hlsl:159
     vt.texcoord = fetch_texcoord(sc, dr, va, idx, bu, bv);
+    {                                                                                               // hit.hlsl:34-52,152
+        const float* b = &sc.positions[dr.position_offset];
+        f3 p = interp3(b + 3ull * idx[0], b + 3ull * idx[1], b + 3ull * idx[2], bu, bv);
+        vt.position_world = xf_point(x.o2w, p);
+    }
     return vt;
 }
 
 // ---- material_function: the closed set of snippets (hit.hlsl:166-173) --------------------------
-static SurfaceData material_function(const Scene& sc, const bpt_material& m, f2 uv) {
+static SurfaceData material_function(const Scene& sc, const bpt_material& m, f2 uv, f3 position_world) {
     SurfaceData s = surface_data_default();
     uint32_t kind = (m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu;
     if (kind == BPT_MATERIAL_KIND_GLTF_PBR) {                    // import_model.cpp:208-230
@@ -149,6 +154,29 @@ static SurfaceData material_function(const Scene& sc, const bpt_material& m, f2 
     } else if (kind == BPT_MATERIAL_KIND_ASSIMP_DIFFUSE) {       // import_model.cpp:490-493
         s.base_color = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
         s.roughness = m.roughness;
+    } else if (kind == BPT_MATERIAL_KIND_CONSTANT_COLOR) {       // examples/scene_basic/materials/white.toml
+        s.base_color = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
+    } else if (kind == BPT_MATERIAL_KIND_CHECKERBOARD) {         // examples/scene_basic/materials/checkerboard.toml
+        int grid = (int)floorf(position_world.x) ^ (int)floorf(position_world.z);
+        bool odd = (grid & 1) == 1;
+        s.base_color = odd ? mk3(m.base_color[0], m.base_color[1], m.base_color[2]) : mk3(m.emission[0], m.emission[1], m.emission[2]);
+        s.roughness = odd ? m.base_color[3] : m.roughness;
+    } else if (kind == BPT_MATERIAL_KIND_TEXTURED) {             // examples/scene_basic/materials/textured.toml
+        f4 bt = sample_or_default(sc, m.base_color_tex, uv, f4{1, 1, 1, 1});
+        f4 nt = sample_or_default(sc, m.normal_map_tex, uv, f4{0.5f, 0.5f, 1.0f, 1.0f});
+        s.base_color = mk3(bt.x, bt.y, bt.z);
+        s.normal_map_value = mk3(nt.x, nt.y, nt.z);
+        s.roughness = m.roughness;
+    } else if (kind == BPT_MATERIAL_KIND_TRANSPARENT) {          // examples/scene_basic/materials/transparent.toml
+        s.base_color = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
+        s.opacity = m.base_color[3];
+        s.two_sided = true;
+    } else if (kind == BPT_MATERIAL_KIND_CAGE) {                 // examples/scene_basic/materials/cage.toml
+        f4 v = sample_or_default(sc, m.base_color_tex, uv, f4{1, 1, 1, 1});
+        s.base_color = mk3(v.x, v.y, v.z);
+        s.f0_color = mk3(v.x, v.y, v.z);
+        s.opacity = v.w < 0.5f ? 0.0f : 1.0f;
+        s.two_sided = true;
     }
     return s;
 }
@@ -159,7 +187,7 @@ float eval_opacity(const Scene& sc, uint32_t instance_id, uint32_t prim, float u
     uint32_t idx[3];
     fetch_indices(sc, dr, prim, idx);
     f2 uv = fetch_texcoord(sc, dr, sc.drawable_va[instance_id], idx, u, v);
-    return material_function(sc, m, uv).opacity;
+    return material_function(sc, m, uv, splat3(0.0f)).opacity;
 }
 
 // ---- lights: shaders/renderer/lights.hlsl:10-25 -------------------------------------------------
@@ -243,7 +271,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
         uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
         f3 P = O + D * h.t;                                                                 // rt_gbuffer.hlsl:32
         Vertex vt = fetch_vertex_attributes(sc, x, h.prim, h.u, h.v);
-        SurfaceData surf = material_function(sc, mat, vt.texcoord);
+        SurfaceData surf = material_function(sc, mat, vt.texcoord, vt.position_world);
         f3 nts = surf.normal_map_value * 2.0f - splat3(1.0f);                               // rt_gbuffer_hit.hlsl:10-14
         f3 N = normalize((nts.x * vt.tangent_world + nts.y * vt.bitangent_world) + nts.z * vt.normal_world);
         if (surf.two_sided && dot(D, N) > 0.0f) N = -N;
@@ -450,8 +478,18 @@ bpt_status obpt_scene_upload_materials(obpt_context* c, const bpt_material* m, u
     c->scene.textures.clear();
     for (uint32_t i = 0; i < nt; i++) {
         Texture tx; tx.w = t[i].width; tx.h = t[i].height; tx.format = t[i].format; tx.addr_u = t[i].address_mode_u; tx.addr_v = t[i].address_mode_v; tx.linear = t[i].filter_linear;
-        size_t bytes = (size_t)tx.w * tx.h * (tx.format == BPT_TEXTURE_RGBA8_UNORM ? 4 : 16);
-        tx.texels.assign((const uint8_t*)t[i].texels, (const uint8_t*)t[i].texels + bytes);
+        if (tx.format == BPT_TEXTURE_RGBA8_SRGB) {      // decode once to linear FP32 texels (filtering happens after the decode)
+            float lut[256];
+            for (int k = 0; k < 256; k++) { double v = k / 255.0; lut[k] = (float)(v <= 0.04045 ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4)); }
+            const uint8_t* src = (const uint8_t*)t[i].texels;
+            std::vector<float> lin((size_t)tx.w * tx.h * 4);
+            for (size_t k = 0; k < lin.size(); k += 4) { lin[k] = lut[src[k]]; lin[k + 1] = lut[src[k + 1]]; lin[k + 2] = lut[src[k + 2]]; lin[k + 3] = (float)src[k + 3] / 255.0f; }
+            tx.format = BPT_TEXTURE_RGBA32_FLOAT;
+            tx.texels.assign((const uint8_t*)lin.data(), (const uint8_t*)lin.data() + lin.size() * 4);
+        } else {
+            size_t bytes = (size_t)tx.w * tx.h * (tx.format == BPT_TEXTURE_RGBA8_UNORM ? 4 : 16);
+            tx.texels.assign((const uint8_t*)t[i].texels, (const uint8_t*)t[i].texels + bytes);
+        }
         c->scene.textures.push_back(std::move(tx));
     }
     return BPT_OK;

@@ -30,7 +30,8 @@ class HcScene(C.Structure):
                 ("ltc_m0", C.c_void_p), ("ltc_m1", C.c_void_p), ("ltc_m2", C.c_void_p), ("ltc_norm", C.c_void_p),
                 ("sky_faces", C.c_void_p), ("sky_size", C.c_uint32), ("sky_transform", C.c_float * 9), ("sky_color", C.c_float * 3),
                 ("accel_mode", C.c_uint32),
-                ("blas_bvh", C.POINTER(HcBvh)), ("tlas", HcBvh)]
+                ("blas_bvh", C.POINTER(HcBvh)), ("tlas", HcBvh),
+                ("textures", C.POINTER(capi.TextureDesc)), ("num_textures", C.c_uint32)]
 
 
 _lib = None
@@ -96,6 +97,12 @@ class HostScene:
             self.keep.append(tv)
             h.tlas = HcBvh(tv["n"], tv["root"], _p(tv["nodes"]), _p(tv["prims"]))
         self.keep.append(arr)
+        texs = (capi.TextureDesc * max(1, len(scene.textures)))()
+        for i, t in enumerate(scene.textures):
+            texs[i] = capi.TextureDesc(texels=_p(t["texels"]), width=t["width"], height=t["height"], format=t["format"],
+                                       address_mode_u=t.get("address_u", 0), address_mode_v=t.get("address_v", 0), filter_linear=t.get("linear", 1))
+        h.textures, h.num_textures = texs, len(scene.textures)
+        self.keep.append(texs)
         self.scene = scene
         self.h = h
 

@@ -34,6 +34,8 @@ def cases():
     yield "small", scenes.small_test_scene(), 6
     yield "cornell", scenes.cornell_box(tess=8), 5
     yield "mixed", scenes.add_mixed_lights(scenes.small_test_scene(), 5, 3, luts, keep_dir_lights=True, light_range=12.0), 3
+    # the reference's own example project: its meshes, its five materials (textures, alpha test, translucency)
+    yield "scene_basic", scenes.scene_basic(os.path.join(HERE, "scene_basic.npz")), 3
 
 
 def compute(name, scene, bounces, make_ctx):

@@ -34,6 +34,7 @@ struct hc_scene {
     uint32_t accel_mode;
     const hc_bvh* blas_bvh;        // num_blas entries (two-level) or 1 (merged)
     hc_bvh tlas;
+    const bpt_texture_desc* textures; uint32_t num_textures;
 };
 
 namespace {
@@ -41,6 +42,8 @@ struct Built {
     std::vector<DInstance> inst;
     std::vector<std::vector<float4>> tris;
     std::vector<DBlas> blas;
+    std::vector<DTexture> textures;
+    std::vector<std::vector<float>> decoded;     // sRGB textures decoded to linear FP32 (as bpt_scene_upload_materials does)
     DScene sc{};
 };
 
@@ -95,7 +98,23 @@ void build(const hc_scene& h, Built& b) {
         b.blas[bi] = DBlas{reinterpret_cast<const float4*>(h.blas_bvh[bi].nodes), b.tris[bi].data(), h.blas_bvh[bi].root, h.blas_bvh[bi].n};
     DScene& s = b.sc;
     s.positions = h.positions; s.normals = h.normals; s.tangents = h.tangents; s.texcoords = h.texcoords; s.indices = h.indices;
-    s.drawables = h.drawables; s.drawable_va = h.drawable_va; s.materials = h.materials; s.textures = nullptr; s.num_textures = 0;
+    s.drawables = h.drawables; s.drawable_va = h.drawable_va; s.materials = h.materials;
+    b.textures.resize(h.num_textures); b.decoded.resize(h.num_textures);
+    for (uint32_t i = 0; i < h.num_textures; i++) {
+        const bpt_texture_desc& t = h.textures[i];
+        const void* texels = t.texels; uint32_t fmt = t.format;
+        if (fmt == BPT_TEXTURE_RGBA8_SRGB) {
+            float lut[256];
+            for (int k = 0; k < 256; k++) { double v = k / 255.0; lut[k] = (float)(v <= 0.04045 ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4)); }
+            const uint8_t* src = static_cast<const uint8_t*>(t.texels);
+            std::vector<float>& lin = b.decoded[i];
+            lin.resize((size_t)t.width * t.height * 4);
+            for (size_t k = 0; k < lin.size(); k += 4) { lin[k] = lut[src[k]]; lin[k + 1] = lut[src[k + 1]]; lin[k + 2] = lut[src[k + 2]]; lin[k + 3] = (float)src[k + 3] / 255.0f; }
+            texels = lin.data(); fmt = BPT_TEXTURE_RGBA32_FLOAT;
+        }
+        b.textures[i] = DTexture{texels, t.width, t.height, fmt, t.address_mode_u, t.address_mode_v, t.filter_linear};
+    }
+    s.textures = b.textures.data(); s.num_textures = h.num_textures;
     s.instances = b.inst.data(); s.num_instances = h.num_instances;
     s.accel_mode = h.accel_mode;
     s.tlas_nodes = reinterpret_cast<const float4*>(h.tlas.nodes); s.tlas_prims = h.tlas.prims; s.tlas_root = h.tlas.root; s.tlas_n = h.tlas.n;

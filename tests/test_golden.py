@@ -29,7 +29,7 @@ def check(golden, got, multi_light):
             np.testing.assert_array_equal(v, golden[k], err_msg=k)
 
 
-@pytest.mark.parametrize("case", ["small", "cornell", "mixed"])
+@pytest.mark.parametrize("case", ["small", "cornell", "mixed", "scene_basic"])
 def test_oracle_reproduces_golden(oracle, golden, case):
     for name, scene, bounces in make_golden.cases():
         if name == case:
@@ -37,7 +37,7 @@ def test_oracle_reproduces_golden(oracle, golden, case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["small", "cornell", "mixed"])
+@pytest.mark.parametrize("case", ["small", "cornell", "mixed", "scene_basic"])
 def test_cuda_reproduces_golden(golden, case):
     lib = pkg.load_library()
     for name, scene, bounces in make_golden.cases():
