@@ -261,21 +261,24 @@ def main():
             r.ctx.upload_lights(scene); r.frame(RAY_LENGTH, B, True)
         r.ctx.sync(); r.ctx.reset_counters()
         barrier()
-        host_imgs = [host_img, torch.empty(H, W, 4, dtype=torch.float32).pin_memory()]
-        dev_imgs = [dev_img, torch.empty(H, W, 4, dtype=torch.float32, device="cuda")]
+        # ring of pinned host buffers deep enough for one sample wave + slack: the pass prefetches a wave of samples,
+        # so results arrive in bursts; the host must be able to queue the next wave while the previous read-backs drain
+        ring = 12
+        host_imgs = [host_img] + [torch.empty(H, W, 4, dtype=torch.float32).pin_memory() for _ in range(ring - 1)]
+        dev_imgs = [dev_img] + [torch.empty(H, W, 4, dtype=torch.float32, device="cuda") for _ in range(ring - 1)]
         copy_stream = torch.cuda.Stream()
-        done = [None, None]
+        done = [None] * ring
         t0 = time.perf_counter()
         n = 0
         for i in range(e2e_steps):
-            b = i & 1
+            b = i % ring
             if done[b] is not None:
-                done[b].synchronize()                       # the host buffer of frame i-2 has landed
+                done[b].synchronize()                       # the host buffer of frame i-ring has landed
             r.ctx.upload_lights(scene)                      # PathTracingPass::update_params: per-frame H2D of the light arrays
             n = r.frame(RAY_LENGTH, B, True)                # Camera::update_shader_params + PathTracingPass::render + RenderGraph::execute
             r.ctx.resolve_device(n, dev_imgs[b].data_ptr()) # the frame's result ...
             ready = torch.cuda.Event(); ready.record(stream)
-            with torch.cuda.stream(copy_stream):            # ... read back to pinned host memory while the next frame renders
+            with torch.cuda.stream(copy_stream):            # ... read back to pinned host memory while the next frames render
                 copy_stream.wait_event(ready)
                 host_imgs[b].copy_(dev_imgs[b], non_blocking=True)
                 done[b] = torch.cuda.Event(); done[b].record(copy_stream)

@@ -367,3 +367,25 @@ def test_probe_blending_parity(lib, oracle):
     ia2, va2 = gpu.blend_probes(vol, table, 1, r1, ia, va)
     ib2, vb2 = ref.blend_probes(vol, table, 1, r1, ib, vb)
     np.testing.assert_array_equal(ia2, ib2); np.testing.assert_array_equal(va2, vb2)
+
+
+def test_converged_image_relmse(lib, oracle):
+    """BASELINE.json gate: the converged image reaches relative MSE <= 1e-3 against a 4096-spp oracle render
+    (configs[0] Cornell box, reduced to 64x64 so the double-precision oracle finishes in seconds)."""
+    scene = scenes.cornell_box(tess=8)
+    W, H, N = 64, 64, 4096
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_MERGED)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=5)
+    truth = ref.render_converged(cam, 0, N, st)[..., :3].astype(np.float64)       # 4096 spp, float64 accumulation
+    gpu.render(cam, 0, N, st)
+    img = gpu.resolve(N)[..., :3].astype(np.float64)
+
+    def relmse(a, b):
+        return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-4)))
+    assert relmse(img, truth) <= 1e-3
+    assert relmse(img, truth) <= 1e-9          # in fact: same samples, FP32 vs FP64 summation only
+    # an independent set of 4096 samples (other frame indices) differs only by Monte-Carlo noise
+    gpu.clear_accum(); gpu.render(cam, 100000, N, st)
+    other = gpu.resolve(N)[..., :3].astype(np.float64)
+    assert relmse(other, truth) < 0.5 and abs(other.mean() / truth.mean() - 1) < 0.05
