@@ -1,0 +1,38 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): both accel modes, lights of every
+kind, any-hit materials, probes + blending, prefetch path, TLAS update. Kept small: the tools slow kernels ~50x."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import bisemutum_engine_b200 as pkg
+from bisemutum_engine_b200 import capi, engine, scenes
+
+lib = pkg.load_library()
+luts = scenes.load_ltc_luts(os.path.join(pkg.REPO_ROOT, "tests", "golden", "ltc_luts.npz"))
+scene = scenes.add_mixed_lights(scenes.small_test_scene(), 3, 2, luts, keep_dir_lights=True, light_range=12.0)
+basic = scenes.scene_basic(os.path.join(pkg.REPO_ROOT, "tests", "golden", "scene_basic.npz"))
+W, H = 40, 24
+for sc in (scene, basic):
+    for mode in (capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED):
+        ctx = capi.Context(lib, W, H)
+        ctx.upload_scene(sc, mode)
+        cam = engine.camera_matrices(sc.camera, W, H)
+        ctx.render(cam, 0, 3, capi.Settings(max_bounces=5, rect_shadow=1, russian_roulette=1, pixel_jitter=1))
+        img = ctx.resolve(3)
+        assert np.isfinite(img).all()
+        rays = np.zeros(64, capi.RAY); rays["origin"] = (0, 2, 5); rays["direction"] = (0, -0.3, -1); rays["tmin"] = 0.001; rays["tmax"] = 50
+        ctx.trace_rays(rays); ctx.trace_shadow_rays(rays)
+        if mode == capi.ACCEL_TWO_LEVEL:
+            ctx.upload_instances(sc.instances); ctx.update_tlas()
+        vol = scenes.probe_volume(sc, (2, 2, 2), 16, ray_length=50.0); tab = scenes.ddgi_sample_randoms()
+        r = ctx.trace_probes(vol, tab, 0, 2)
+        irr, vis = ctx.blend_probes(vol, tab, 0, r)
+        ctx.blend_probes(vol, tab, 1, r, irr, vis)
+        ctx.close()
+r = engine.Renderer(W, H); r.set_scene(scene, capi.ACCEL_MERGED)
+for _ in range(3):
+    n = r.frame(max_bounces=4)
+r.image(n); r.close()
+print("sanitize smoke ok")
