@@ -60,6 +60,7 @@ TEXTURE_RGBA8_UNORM, TEXTURE_RGBA32_FLOAT, TEXTURE_RGBA8_SRGB = 0, 1, 2
 ADDRESS_REPEAT, ADDRESS_CLAMP = 0, 1
 ACCEL_TWO_LEVEL, ACCEL_MERGED = 0, 1
 NEE_SHADOW_RAY, NEE_NONE = 0, 1
+STATE_FP32, STATE_REFERENCE_FP16 = 0, 1
 BVH_TLAS = 0xFFFFFFFF
 
 STATUS_NAMES = {0: "BPT_OK", 1: "BPT_ERR_INVALID", 2: "BPT_ERR_CUDA", 3: "BPT_ERR_OOM", 4: "BPT_ERR_STATE",
@@ -298,6 +299,15 @@ class Context:
 
     def render(self, camera: Camera, frame_index_first: int, num_samples: int, settings: Settings):
         self._call("render", C.byref(camera), frame_index_first, num_samples, C.byref(settings))
+
+    def render_ahead(self, camera: Camera, frame_index_first: int, max_samples: int, settings: Settings) -> int:
+        """Traces up to max_samples consecutive samples in one wave and keeps them; returns how many (bpt_render_ahead)."""
+        n = C.c_uint32(0)
+        self._call("render_ahead", C.byref(camera), frame_index_first, max_samples, C.byref(settings), C.byref(n))
+        return n.value
+
+    def accumulate_ahead(self, count: int = 1):
+        self._call("accumulate_ahead", count)
 
     def resolve(self, total_samples: int) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), dtype=f32)

@@ -84,7 +84,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
                       &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
-                      &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims};
+                      &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims};
     for (DevBuf* b : bufs) dev_free(*b);
     for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
     for (auto& t : c->d_texels) dev_free(t);
@@ -294,7 +294,20 @@ bpt_status bpt_debug_read_bvh(bpt_context* c, uint32_t which, uint32_t* np, uint
 bpt_status bpt_clear_accum(bpt_context* c) {
     NEED(c);
     c->wf.ahead_slots = c->wf.ahead_cursor = 0;
+    c->wf.accum_count = 0; c->wf.accum_fp16 = false; c->accum_used = false;
     BPT_CUDA_TRY(c, cudaMemsetAsync(c->wf.accum.p, 0, (size_t)c->width * c->height * 16, c->stream));
+    return BPT_OK;
+}
+
+// The accumulation buffer follows ONE rule between two bpt_clear_accum calls: FP32 sum (fp32 state) or the reference's
+// running fp16 lerp (reference_fp16, pt_accumulate.hlsl:3-11); mixing them would make bpt_resolve meaningless.
+static bpt_status check_precision(bpt_context* c, const bpt_settings* st) {
+    if (st->state_precision != BPT_STATE_FP32 && st->state_precision != BPT_STATE_REFERENCE_FP16)
+        return fail(c, BPT_ERR_INVALID, "state_precision: unknown value");
+    const bool fp16 = st->state_precision == BPT_STATE_REFERENCE_FP16;
+    if (c->accum_used && fp16 != c->wf.accum_fp16)
+        return fail(c, BPT_ERR_STATE, "state_precision changed without bpt_clear_accum");
+    c->accum_used = true; c->wf.accum_fp16 = fp16;
     return BPT_OK;
 }
 
@@ -302,8 +315,7 @@ bpt_status bpt_render(bpt_context* c, const bpt_camera* cam, uint32_t first, uin
     NEED(c);
     if (!cam || !st) return BPT_ERR_INVALID;
     if (!c->accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
-    if (st->state_precision != BPT_STATE_FP32)
-        return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 is not implemented");
+    if (bpt_status ps = check_precision(c, st)) return ps;
     return wavefront_render(c, *cam, first, ns, *st);
 }
 
@@ -311,8 +323,7 @@ bpt_status bpt_render_ahead(bpt_context* c, const bpt_camera* cam, uint32_t firs
     NEED(c);
     if (!cam || !st || !max_samples) return BPT_ERR_INVALID;
     if (!c->accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
-    if (st->state_precision != BPT_STATE_FP32)
-        return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 is not implemented");
+    if (bpt_status ps = check_precision(c, st)) return ps;
     bpt_status s = wavefront_render(c, *cam, first, max_samples, *st, true);
     if (out_samples) *out_samples = c->wf.ahead_slots;
     return s;

@@ -33,7 +33,10 @@ struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through 
     DevBuf hit_slot;        // uint32
     uint64_t shadow_capacity = 0;
     DevBuf sh_o, sh_d, sh_c; // float4 each: (P|pixel), (L|tmax), (c|light)
-    DevBuf accum;           // float4 per pixel: FP32 sums
+    DevBuf accum;           // float4 per pixel: FP32 sums (reference_fp16: the running half-valued average)
+    DevBuf bcol;            // float4 per path, reference_fp16 only: light terms of the current bounce before the half store
+    uint32_t accum_count = 0;   // reference_fp16: samples already folded into `accum` (pt_accumulate weight = 1 / (count + 1))
+    bool accum_fp16 = false;    // which of the two accumulation rules `accum` currently follows (fixed until bpt_clear_accum)
     DevBuf qcount;          // uint32[128]: extend / shadow queue lengths per bounce + work cursors of the persistent kernels
     DevBuf totals;          // uint64[40]: extend per bounce [0..15], shadow per bounce [16..31], samples [32]
 };
@@ -44,6 +47,7 @@ struct bpt_context {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    bool accum_used = false;    // a render has added to wf.accum since the last bpt_clear_accum
 
     // host copies needed for validation / rebuilds
     std::vector<bpt_drawable_sbt_data> h_drawables;

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #if defined(__CUDACC__)
+#include <cuda_fp16.h>
 #define BPT_HD __host__ __device__ __forceinline__
 #else
 #define BPT_HD inline
@@ -163,6 +164,87 @@ BPT_HD float3 tangent_after_gbuffer(float3 N, float3 T) {
     return normalize3(fr.x * projected_x + fr.y * projected_y);
 }
 
+// ---- storage formats of state_precision = reference_fp16 (SURVEY §8a storage quantisation note) ---------
+// The reference keeps its wavefront state in textures (path_tracing.cpp:248-288, pass/gbuffer.hpp:14-17):
+// rgba16_sfloat (directions, weights, colours, base colour, normal/roughness), rgba16_unorm (Fresnel) and
+// rgba8_unorm (material_0). A store to those formats is modelled as round-to-nearest-even of the FP32 value;
+// q_*() return the value a later load sees.
+BPT_HD float q_half(float f) {
+#if defined(__CUDA_ARCH__)
+    return __half2float(__float2half_rn(f));           // IEEE RNE, identical to the host form below
+#else
+    uint32_t x = f2u(f), sign = x & 0x80000000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return f;                     // inf / NaN pass through
+    if (x >= 0x477ff000u) return u2f(sign | 0x7f800000u);   // >= 65520 rounds to inf
+    if (x <= 0x33000000u) return u2f(sign);             // <= 2^-25 rounds to (signed) zero
+    uint32_t h;
+    if (x < 0x38800000u) {                              // below 2^-14: half denormal, unit 2^-24
+        uint32_t e = x >> 23, m = (x & 0x7fffffu) | 0x800000u, shift = 126u - e;
+        h = m >> shift;
+        uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1u);
+        if (rem > halfway || (rem == halfway && (h & 1u))) h++;
+        return u2f(sign | f2u((float)h * 5.9604644775390625e-8f));
+    }
+    h = (x - 0x38000000u) >> 13;
+    uint32_t rem = x & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+    return u2f(sign | ((h << 13) + 0x38000000u));      // (h = 0x7c00 cannot happen: x < 65520)
+#endif
+}
+BPT_HD float3 q_half3(float3 v) { return v3(q_half(v.x), q_half(v.y), q_half(v.z)); }
+BPT_HD float q_unorm(float f, float scale) {            // float -> unorm -> float; NaN -> 0
+    float c = f > 0.0f ? (f < 1.0f ? f : 1.0f) : 0.0f;
+    return rintf(c * scale) / scale;
+}
+BPT_HD uint32_t ftou(float f) {                         // HLSL uint(x): truncation; out of range saturates (as cvt.rzi.u32.f32)
+    if (!(f > 0.0f)) return 0u;
+    if (f >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)f;
+}
+BPT_HD uint32_t pack_color_rg11b10(float3 c) {          // pack.hlsl:14-16
+    return ftou(c.x * 2047.0f) | (ftou(c.y * 2047.0f) << 11) | (ftou(c.z * 1023.0f) << 22);
+}
+BPT_HD float3 unpack_color_rg11b10(uint32_t p) {        // pack.hlsl:17-23
+    return v3((float)(p & 0x7ffu) / 2047.0f, (float)((p >> 11) & 0x7ffu) / 2047.0f, (float)((p >> 22) & 0x3ffu) / 1023.0f);
+}
+// Fresnel colour through gbuffer.fresnel: rg11b10 -> two unorm16 channels (value k/65536, pack.hlsl:6-8) -> rgba16_unorm
+// texel -> uint(x * 65535.5) (pack.hlsl:9-12) -> rg11b10. (For k > 32768 the texel rounds to k-1: a reference quirk.)
+BPT_HD float3 fresnel_through_gbuffer(float3 c) {
+    uint32_t p = pack_color_rg11b10(c);
+    float lo = q_unorm((float)(p & 0xffffu) / 65536.0f, 65535.0f), hi = q_unorm((float)(p >> 16) / 65536.0f, 65535.0f);
+    return unpack_color_rg11b10(ftou(lo * 65535.5f) | (ftou(hi * 65535.5f) << 16));
+}
+BPT_HD float2 oct_encode(float3 n) {                    // pack.hlsl:88-95
+    float l1 = (fabsf(n.x) + fabsf(n.y)) + fabsf(n.z);
+    n = n / l1;
+    if (n.z >= 0.0f) return make_float2(n.x, n.y);
+    return make_float2((1.0f - fabsf(n.y)) * (n.x >= 0.0f ? 1.0f : -1.0f), (1.0f - fabsf(n.x)) * (n.y >= 0.0f ? 1.0f : -1.0f));
+}
+BPT_HD float3 oct_decode(float2 f) {                    // pack.hlsl:99-104
+    float3 n = v3(f.x, f.y, (1.0f - fabsf(f.x)) - fabsf(f.y));
+    float t = clampf_(-n.z, 0.0f, 1.0f);
+    n.x = n.x + (n.x >= 0.0f ? -t : t);
+    n.y = n.y + (n.y >= 0.0f ? -t : t);
+    return normalize3(n);
+}
+// (N, T) through gbuffer.normal_roughness.xyz (pack.hlsl:112-129) stored as three halves.
+BPT_HD void frame_through_gbuffer(float3 N, float3 T, float3& No, float3& To) {
+    float2 oct = oct_encode(N);
+    Frame3 fr = frame_from_normal(N);
+    float px = dot3(T, fr.x), py = dot3(T, fr.y);
+    float lnorm = fabsf(px) + fabsf(py);
+    px = px / lnorm; py = py / lnorm;
+    float packed_x = px * 0.5f + 0.5f;
+    float pz = q_half(py < 0.0f ? -packed_x : packed_x);
+    No = oct_decode(make_float2(q_half(oct.x), q_half(oct.y)));
+    float sign = pz < 0.0f ? -1.0f : 1.0f;
+    float projected_x = (sign * pz) * 2.0f - 1.0f;
+    float projected_y = sign * (1.0f - fabsf(projected_x));
+    Frame3 fo = frame_from_normal(No);
+    To = normalize3(fo.x * projected_x + fo.y * projected_y);
+}
+
 // ---- surface / BSDF (material/utils.hlsl, material/lit.hlsl) ----------------------------------
 struct Surface {
     float3 base_color, f0_color, f90_color, normal_map_value;
@@ -175,6 +257,19 @@ BPT_HD Surface surface_default() {                               // utils.hlsl:1
     s.normal_map_value = v3(0.5f, 0.5f, 1.0f);
     s.roughness = 0.5f; s.anisotropy = 0.0f; s.ior = 1.5f; s.opacity = 1.0f; s.two_sided = false;
     return s;
+}
+// pack_surface_to_gbuffer -> texture formats -> unpack_gbuffer_to_surface (gbuffer.hlsl:18-45), state_precision =
+// reference_fp16: base colour and roughness as halves, Fresnel colours as rg11b10 in unorm16 pairs, anisotropy /
+// 1/ior / surface model as unorm8; emission and two_sided are not stored, opacity reads back as 1.
+BPT_HD void surface_through_gbuffer(Surface& s, uint32_t& surface_model) {
+    s.base_color = q_half3(s.base_color);
+    s.f0_color = fresnel_through_gbuffer(s.f0_color);
+    s.f90_color = fresnel_through_gbuffer(s.f90_color);
+    s.roughness = q_half(s.roughness);
+    s.anisotropy = q_unorm(s.anisotropy, 255.0f);
+    s.ior = 1.0f / q_unorm(1.0f / s.ior, 255.0f);
+    surface_model = ftou(q_unorm((float)surface_model / 256.0f, 255.0f) * 255.5f);
+    s.opacity = 1.0f;
 }
 BPT_HD float3 schlick_fresnel(float3 f0, float3 f90, float cos_theta, float ior) {   // utils.hlsl:40-51
     if (cos_theta < 0.0f) {

@@ -22,7 +22,25 @@ struct ShadeParams {
     uint32_t russian_roulette; // NEW switch, default off
     uint32_t rect_shadow;      // NEW switch: 1 = one shadow ray per rect light towards its most representative point
     uint32_t diffuse_only;     // probe tracing: light every vertex as surface_data_diffuse(base_color) (ddgi/deferred_lighting.hlsl:44)
+    uint32_t state_precision;  // BPT_STATE_REFERENCE_FP16: the reference's texture formats are applied to the state (see below)
 };
+
+// state_precision = reference_fp16 (SURVEY §8a "storage quantisation"; formats at path_tracing.cpp:248-288 and
+// pass/gbuffer.hpp:14-17). Every value the reference moves between passes through a texture takes that texture's
+// format here too: ray directions and throughput are halves (also the camera ray's), the surface goes through
+// pack_surface_to_gbuffer / unpack_gbuffer_to_surface, and a bounce's colour is the half of
+// (sum of its light terms) * throughput (deferred_lighting_secondary.hlsl:110), which bounce 1 writes and later
+// bounces add to the colour texture with a half result (the additive blit, path_tracing.cpp:441-459). The sink
+// then receives UNWEIGHTED light terms and the caller commits them with commit_bounce_fp16.
+BPT_HD float3 commit_bounce_fp16(float3 C, float3 bounce_sum, float3 Wt, uint32_t bounce) {
+    float3 c = q_half3(bounce_sum * Wt);
+    return bounce == 1 ? c : q_half3(C + c);
+}
+// pt_accumulate.hlsl:3-11 on an rgba16_sfloat target: image = n == 1 ? C : half(lerp(image, C, 1/n))
+BPT_HD float3 accumulate_fp16(float3 image, float3 C, uint32_t n) {
+    if (n <= 1) return C;
+    return q_half3(mix3(image, C, 1.0f / (float)n));
+}
 
 // Sink concept:
 //   void add(float3 c)                                         — unshadowed radiance for this pixel
@@ -31,11 +49,13 @@ struct ShadeParams {
 template <class Sink>
 BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame_index, uint32_t bounce, uint32_t pixel,
                          float3 O, float3 D, float3 Wt, const TraceResult& hit, Sink& sink, float3& nO, float3& nD, float3& nW) {
+    const bool fp16 = sp.state_precision == BPT_STATE_REFERENCE_FP16;
+    const float3 Wl = fp16 ? v3s(1.0f) : Wt;                            // weight of the light terms handed to the sink
     if (!hit.hit) {                                                     // deferred_lighting_secondary.hlsl:24-29
         const float* m = sc.sky_transform;
         float3 dir = v3((m[0] * D.x + m[1] * D.y) + m[2] * D.z, (m[3] * D.x + m[4] * D.y) + m[5] * D.z, (m[6] * D.x + m[7] * D.y) + m[8] * D.z);
         float3 color = sample_sky(sc, dir) * v3(sc.sky_color[0], sc.sky_color[1], sc.sky_color[2]);
-        sink.add(color * Wt);
+        sink.add(fp16 ? color : color * Wt);
         return false;
     }
     const DInstance& in = sc.instances[hit.slot];
@@ -48,7 +68,15 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     float3 nts = surf.normal_map_value * 2.0f - v3s(1.0f);              // rt_gbuffer_hit.hlsl:10-14
     float3 N = normalize3((nts.x * hv.tangent_world + nts.y * hv.bitangent_world) + nts.z * hv.normal_world);
     if (surf.two_sided && dot3(D, N) > 0.0f) N = -N;
-    float3 T = tangent_after_gbuffer(N, hv.tangent_world);              // gbuffer.hlsl:27,41
+    float3 T;
+    if (fp16) {                                                         // gbuffer.hlsl:18-45 through the texture formats
+        float3 Nq;
+        frame_through_gbuffer(N, hv.tangent_world, Nq, T);
+        N = Nq;
+        surface_through_gbuffer(surf, surface_model);
+    } else {
+        T = tangent_after_gbuffer(N, hv.tangent_world);                 // gbuffer.hlsl:27,41
+    }
     float3 B = cross3(N, T);
     surf.opacity = 1.0f;                                                // gbuffer.hlsl:44
     if (sp.diffuse_only) {                                              // ddgi/deferred_lighting.hlsl:44-45
@@ -62,7 +90,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     for (uint32_t l = 0; l < sc.num_rect; l++) {                        // :72-96 (unshadowed, as the reference, unless rect_shadow)
         const bpt_rect_light_data& rl = sc.rect_lights[l];
         float3 mrp = v3s(0.0f);
-        float3 c = eval_rect_light(sc, rl, P, N, T, B, V, surf, surface_model, sp.rect_shadow ? &mrp : nullptr) * Wt;
+        float3 c = eval_rect_light(sc, rl, P, N, T, B, V, surf, surface_model, sp.rect_shadow ? &mrp : nullptr) * Wl;
         if (!sp.rect_shadow) { sink.add(c); continue; }
         if (!(max3c(c) > 0.0f)) continue;
         // distance to the light's plane along mrp (as rect_light_sample_texture, lights.hlsl:425-438)
@@ -75,13 +103,13 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     for (uint32_t l = 0; l < sc.num_dir; l++) {                         // :51-60
         const bpt_dir_light_data& li = sc.dir_lights[l];
         float3 L = v3(li.direction[0], li.direction[1], li.direction[2]);
-        float3 c = (v3(li.emission[0], li.emission[1], li.emission[2]) * bsdf_eval(N, T, B, V, L, surf, surface_model)) * Wt;
+        float3 c = (v3(li.emission[0], li.emission[1], li.emission[2]) * bsdf_eval(N, T, B, V, L, surf, surface_model)) * Wl;
         if (max3c(c) > 0.0f) sink.shadow(P, L, sp.ray_length, c, l);
     }
     for (uint32_t l = 0; l < sc.num_point; l++) {                       // :61-70
         float3 L; float dist;
         float3 le = eval_point_light(sc.point_lights[l], P, L, dist);
-        float3 c = (le * bsdf_eval(N, T, B, V, L, surf, surface_model)) * Wt;
+        float3 c = (le * bsdf_eval(N, T, B, V, L, surf, surface_model)) * Wl;
         if (max3c(c) > 0.0f) sink.shadow(P, L, dist * 0.999f, c, sc.num_dir + l);
     }
 
@@ -104,6 +132,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     float3 weight = bsdf / pdf;
     if (!is_finite3(weight)) weight = v3s(0.0f);                        // :62-64
     float3 w2 = weight * Wt;
+    if (fp16) { w2 = q_half3(w2); out_dir = q_half3(out_dir); }         // ray_weights / ray_directions are rgba16_sfloat (:66-68)
     // a zero-weight path can never contribute again (deferred_lighting_secondary.hlsl:17-21): drop it
     if (w2.x == 0.0f && w2.y == 0.0f && w2.z == 0.0f) return false;
     if (sp.russian_roulette && bounce >= 2) {                           // third draw of this bounce's stream
@@ -111,6 +140,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
         float u3 = rng_next(seed);
         if (!(u3 < q)) return false;
         w2 = w2 / q;
+        if (fp16) w2 = q_half3(w2);
     }
     nO = P; nD = out_dir; nW = w2;
     return true;

@@ -39,6 +39,7 @@ struct RenderArgs {
     float4 *sh_o, *sh_d, *sh_c;
     float4* accum;
     float4* color;            // per-sample colour, [slot][pixel]
+    float4* contrib;          // where light terms are added: `color` (fp32 state) or the per-bounce sum `bcol` (reference_fp16)
     uint32_t* qcount;
     uint64_t shadow_capacity;
     uint32_t npx, nslots;     // pixels, samples in this wave; a path's id is slot * npx + pixel
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Rende
     if (!valid) return;
     float3 O, D;
     camera_ray(a.cam, px, py, a.sp.width, a.sp.height, a.pixel_jitter, a.frame_base + slot, O, D);
+    if (a.sp.state_precision == BPT_STATE_REFERENCE_FP16) { D = q_half3(D); a.contrib[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); }   // ray_directions is rgba16_sfloat
     a.ray_o_out[qslot] = make_float4(O.x, O.y, O.z, __uint_as_float(id));
     a.ray_d_out[qslot] = make_float4(D.x, D.y, D.z, 0.0f);
     a.ray_w_out[qslot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_trace_spec(const __grid_constant_
             if (ANY) {
                 if (!rs.found) {
                     float4 c = a.sh_c[ray];
-                    float* px = reinterpret_cast<float*>(a.color + path);
+                    float* px = reinterpret_cast<float*>(a.contrib + path);
                     atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
                 }
             } else {
@@ -261,9 +263,9 @@ struct KernelSink {
     const RenderArgs& a;
     uint32_t bounce, path;      // path = slot * npx + pixel
     __device__ void add(float3 c) {
-        float4 v = a.color[path];
+        float4 v = a.contrib[path];
         v.x += c.x; v.y += c.y; v.z += c.z;
-        a.color[path] = v;
+        a.contrib[path] = v;
     }
     __device__ void shadow(float3 P, float3 L, float tmax, float3 c, uint32_t light) {
         if (a.sp.nee_mode == BPT_NEE_NONE) { add(c); return; }
@@ -315,6 +317,19 @@ __global__ void __launch_bounds__(kBlock, 8) k_shade(const __grid_constant__ Ren
     }
 }
 
+// ---- reference_fp16 only: end of a bounce. colour = half(bounce sum * throughput), written (bounce 1) or added with a
+//      half result (deferred_lighting_secondary.hlsl:110 + the additive blit, path_tracing.cpp:441-459) --------------
+__global__ void __launch_bounds__(kBlock) k_commit_bounce(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.qcount[QE + bounce]) return;
+    float4 w = a.ray_w_in[i];
+    uint32_t path = __float_as_uint(a.ray_o_in[i].w);
+    float4 b = a.contrib[path], c = a.color[path];
+    float3 r = commit_bounce_fp16(v3(c.x, c.y, c.z), v3(b.x, b.y, b.z), v3(w.x, w.y, w.z), bounce);
+    a.color[path] = make_float4(r.x, r.y, r.z, c.w);
+    a.contrib[path] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
 // ---- per-sample bookkeeping: queue lengths → 64-bit totals -------------------------------------
 __global__ void k_tally(const uint32_t* __restrict__ qcount, uint64_t* __restrict__ totals, uint32_t npx) {
     uint32_t t = threadIdx.x;
@@ -333,6 +348,19 @@ __global__ void k_accumulate(const float4* __restrict__ color, float4* __restric
         v.x += c.x; v.y += c.y; v.z += c.z;
     }
     accum[p] = v;
+}
+
+// reference_fp16: the running fp16 lerp of pt_accumulate.hlsl, samples in ascending frame order; `count` = samples already in the image
+__global__ void k_accumulate_fp16(const float4* __restrict__ color, float4* __restrict__ accum, uint32_t npx, uint32_t slot_begin, uint32_t slot_end, uint32_t count) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    float4 v = accum[p];
+    float3 img = v3(v.x, v.y, v.z);
+    for (uint32_t s = slot_begin; s < slot_end; s++) {
+        float4 c = color[(size_t)s * npx + p];
+        img = accumulate_fp16(img, v3(c.x, c.y, c.z), ++count);
+    }
+    accum[p] = make_float4(img.x, img.y, img.z, v.w);
 }
 
 __global__ void k_resolve(const float4* __restrict__ accum, float4* __restrict__ out, uint32_t npx, float inv) {
@@ -453,6 +481,7 @@ bpt_status wavefront_alloc(bpt_context* ctx) {
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.accum.p, 0, (size_t)npx * 16, ctx->stream));
         wf.npx = npx;
         wf.capacity = 0;
+        wf.accum_count = 0; wf.accum_fp16 = false; ctx->accum_used = false;
     }
     if (wf.capacity != paths) {
         for (int k = 0; k < 2; k++) {
@@ -461,7 +490,7 @@ bpt_status wavefront_alloc(bpt_context* ctx) {
             if ((s = dev_alloc(ctx, wf.ray_d[k], paths * 16))) return s;
             if ((s = dev_alloc(ctx, wf.ray_w[k], paths * 16))) return s;
         }
-        dev_free(wf.hit); dev_free(wf.hit_slot); dev_free(wf.color);
+        dev_free(wf.hit); dev_free(wf.hit_slot); dev_free(wf.color); dev_free(wf.bcol);
         if ((s = dev_alloc(ctx, wf.hit, paths * 16))) return s;
         if ((s = dev_alloc(ctx, wf.hit_slot, paths * 4))) return s;
         if ((s = dev_alloc(ctx, wf.color, paths * 16))) return s;
@@ -523,9 +552,15 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
     a.sc = ctx->scene_view();
     a.sp.width = ctx->width; a.sp.height = ctx->height; a.sp.max_bounces = B; a.sp.nee_mode = st.nee_mode; a.sp.ray_length = st.ray_length;
     a.sp.diffuse_only = 0; a.sp.russian_roulette = st.russian_roulette; a.sp.rect_shadow = st.rect_shadow; a.pixel_jitter = st.pixel_jitter;
+    a.sp.state_precision = st.state_precision;
+    if (st.state_precision == BPT_STATE_REFERENCE_FP16 && !wf.bcol.p) {          // per-bounce light sums, only this mode needs them
+        bpt_status sb = dev_alloc(ctx, wf.bcol, wf.capacity * 16);
+        if (sb) return sb;
+    }
     a.hit = wf.hit.as<float4>(); a.hit_slot = wf.hit_slot.as<uint32_t>();
     a.sh_o = wf.sh_o.as<float4>(); a.sh_d = wf.sh_d.as<float4>(); a.sh_c = wf.sh_c.as<float4>();
     a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();
+    a.contrib = st.state_precision == BPT_STATE_REFERENCE_FP16 ? wf.bcol.as<float4>() : a.color;
     a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
     a.pixel_base = 0; a.probe_mode = 0;
     if (!wf.grid_extend) {      // resident grids of the persistent traversal kernels: SMs x blocks that fit per SM
@@ -562,6 +597,7 @@ static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_setting
             if (merged) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
             else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
         }
+        if (st.state_precision == BPT_STATE_REFERENCE_FP16) LAUNCH_T(ctx, 4, k_commit_bounce, grid_paths, kBlock, a, i);
         if (capture && (s = capture_bounce(ctx, i, cur))) return s;
         cur ^= 1;
     }
@@ -599,7 +635,10 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         }
         if ((s = run_bounces(ctx, a, st, B, paths, capture))) return s;
         if (keep_ahead) { wf.ahead_slots = slots; wf.ahead_cursor = 0; wf.ahead_frame_first = frame_first; }
-        else LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, 0u, slots);
+        else if (st.state_precision == BPT_STATE_REFERENCE_FP16) {
+            LAUNCH_T(ctx, 4, k_accumulate_fp16, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, 0u, slots, wf.accum_count);
+            wf.accum_count += slots;
+        } else LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, 0u, slots);
         LAUNCH_T(ctx, 4, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), (uint32_t)paths);
         done += slots;
     }
@@ -646,14 +685,17 @@ bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count) {
     WavefrontState& wf = ctx->wf;
     if (count == 0 || wf.ahead_cursor + count > wf.ahead_slots) { ctx->err = "accumulate_ahead: not enough prefetched samples"; return BPT_ERR_STATE; }
     const uint32_t npx = ctx->width * ctx->height;
-    LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, wf.ahead_cursor, wf.ahead_cursor + count);
+    if (wf.accum_fp16) {
+        LAUNCH_T(ctx, 4, k_accumulate_fp16, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, wf.ahead_cursor, wf.ahead_cursor + count, wf.accum_count);
+        wf.accum_count += count;
+    } else LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, wf.ahead_cursor, wf.ahead_cursor + count);
     wf.ahead_cursor += count;
     return BPT_OK;
 }
 
 bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out) {
     uint32_t npx = ctx->width * ctx->height;
-    float inv = 1.0f / (float)total_samples;
+    float inv = ctx->wf.accum_fp16 ? 1.0f : 1.0f / (float)total_samples;      // reference_fp16: the buffer already is the running average
     LAUNCH(ctx, k_resolve, (npx + 255) / 256, 256, ctx->wf.accum.as<float4>(), reinterpret_cast<float4*>(d_out), npx, inv);
     return BPT_OK;
 }

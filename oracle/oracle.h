@@ -122,6 +122,10 @@ BPT_API void obpt_ggx_vndf_sample(const float v[3], float rx, float ry, float u1
 BPT_API void obpt_surface_eval_lit(const float N[3], const float T[3], const float V[3], const float L[3],
                                    const float base[3], const float f0[3], const float f90[3],
                                    float roughness, float anisotropy, float out_rgb[3]);
+/* state_precision = reference_fp16: one value through an rgba16_sfloat store; (N, T, surface) through the four G-buffer
+ * textures (gbuffer.hlsl:18-45). in12 = base[3] f0[3] f90[3] roughness anisotropy ior; out18 = N T base f0 f90 roughness anisotropy ior. */
+BPT_API float obpt_store_half(float f);
+BPT_API void obpt_gbuffer_roundtrip(const float N[3], const float T[3], const float in12[12], uint32_t model, float out18[18], uint32_t* model_out);
 BPT_API uint64_t obpt_morton63(const float c[3], const float lo[3], const float hi[3]);
 
 #ifdef __cplusplus

@@ -170,6 +170,70 @@ static inline f3 gbuffer_roundtrip_tangent(f3 N, f3 T) {
     return normalize(fr.x * projected_x + fr.y * projected_y);
 }
 
+// ---- texture formats of state_precision = reference_fp16 -------------------------------------
+// The reference's wavefront state lives in rgba16_sfloat / rgba16_unorm / rgba8_unorm textures
+// (src/renderer/pass/path_tracing.cpp:248-288, src/renderer/pass/gbuffer.hpp:14-17). A store is modelled as the
+// round-to-nearest-even conversion of the FP32 value; these return what a later load reads.
+static inline float store_half(float f) {
+    if (!std::isfinite(f) || f == 0.0f) return f;
+    float a = fabsf(f);
+    if (a >= 65520.0f) return copysignf(INFINITY, f);           // half max 65504, next step would be 65536
+    int e;
+    (void)frexpf(a, &e);                                        // a = m * 2^e, m in [0.5, 1)
+    int ulp_exp = (e - 1 < -14 ? -14 : e - 1) - 10;             // spacing of halves around a (denormals below 2^-14)
+    float r = ldexpf(nearbyintf(ldexpf(a, -ulp_exp)), ulp_exp); // exact scaling; nearbyint = ties-to-even (default mode)
+    return copysignf(r, f);
+}
+static inline f3 store_half3(f3 v) { return mk3(store_half(v.x), store_half(v.y), store_half(v.z)); }
+static inline float store_unorm(float f, int bits) {            // NaN and negatives -> 0, >1 -> 1
+    float scale = (float)((1u << bits) - 1u);
+    float c = f > 0.0f ? (f < 1.0f ? f : 1.0f) : 0.0f;
+    return nearbyintf(c * scale) / scale;
+}
+static inline uint32_t to_uint(float f) {                       // HLSL uint(x): truncate; saturating outside [0, 2^32)
+    if (!(f > 0.0f)) return 0u;
+    if (f >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)f;
+}
+// core/utils/pack.hlsl:6-23
+static inline f2 pack_u32_to_unorm16x2(uint32_t x) { return f2{(float)(x & 0xffffu) / 65536.0f, (float)(x >> 16) / 65536.0f}; }
+static inline uint32_t unpack_u32_from_unorm16x2(f2 x) { return to_uint(x.x * 65535.5f) | (to_uint(x.y * 65535.5f) << 16); }
+static inline uint32_t pack_color_rg11b10(f3 c) { return to_uint(c.x * 2047.0f) | (to_uint(c.y * 2047.0f) << 11) | (to_uint(c.z * 1023.0f) << 22); }
+static inline f3 unpack_color_rg11b10(uint32_t p) {
+    return mk3((float)(p & 0x7ffu) / 2047.0f, (float)((p >> 11) & 0x7ffu) / 2047.0f, (float)((p >> 22) & 0x3ffu) / 1023.0f);
+}
+// core/utils/pack.hlsl:85-104
+static inline f2 oct_wrap(f2 v) { return f2{(1.0f - fabsf(v.y)) * (v.x >= 0.0f ? 1.0f : -1.0f), (1.0f - fabsf(v.x)) * (v.y >= 0.0f ? 1.0f : -1.0f)}; }
+static inline f2 oct_encode(f3 n) {
+    n = n / ((fabsf(n.x) + fabsf(n.y)) + fabsf(n.z));
+    return n.z >= 0.0f ? f2{n.x, n.y} : oct_wrap(f2{n.x, n.y});
+}
+static inline f3 oct_decode(f2 f) {
+    f3 n = mk3(f.x, f.y, (1.0f - fabsf(f.x)) - fabsf(f.y));
+    float t = clampf(-n.z, 0.0f, 1.0f);
+    float ax = n.x >= 0.0f ? -t : t, ay = n.y >= 0.0f ? -t : t;
+    n.x = n.x + ax; n.y = n.y + ay;
+    return normalize(n);
+}
+// core/utils/pack.hlsl:112-129
+static inline f3 pack_normal_and_tangent(f3 N, f3 T) {
+    f2 oct = oct_encode(N);
+    Frame fr = create_frame(N);
+    float px = dot(T, fr.x), py = dot(T, fr.y);
+    float lnorm = fabsf(px) + fabsf(py);
+    px = px / lnorm; py = py / lnorm;
+    float projected_x = px * 0.5f + 0.5f;
+    return mk3(oct.x, oct.y, py < 0.0f ? -projected_x : projected_x);
+}
+static inline void unpack_normal_and_tangent(f3 packed, f3& N, f3& T) {
+    N = oct_decode(f2{packed.x, packed.y});
+    float sign = packed.z < 0.0f ? -1.0f : 1.0f;
+    float projected_x = (sign * packed.z) * 2.0f - 1.0f;
+    float projected_y = sign * (1.0f - fabsf(projected_x));
+    Frame fr = create_frame(N);
+    T = normalize(fr.x * projected_x + fr.y * projected_y);
+}
+
 // ---- surface + BSDF: core/material/utils.hlsl, core/material/lit.hlsl -------------------
 struct SurfaceData {                                  // material/utils.hlsl:5-16
     f3 emission, base_color, f0_color, f90_color, normal_map_value;
@@ -187,6 +251,38 @@ static inline SurfaceData surface_data_diffuse(f3 base_color) {   // material/ut
     SurfaceData s = surface_data_default();
     s.base_color = base_color;
     return s;
+}
+// renderer/gbuffer.hlsl:18-45: pack_surface_to_gbuffer -> the four G-buffer textures (rgba16_sfloat base colour,
+// rgba16_sfloat normal+roughness, rgba16_unorm Fresnel, rgba8_unorm material_0) -> unpack_gbuffer_to_surface.
+struct GBuffer { f4 base_color, normal_roughness, fresnel, material_0; };
+static inline GBuffer pack_surface_to_gbuffer(f3 N, f3 T, const SurfaceData& s, uint32_t surface_model) {
+    GBuffer g;
+    g.base_color = f4{s.base_color.x, s.base_color.y, s.base_color.z, 1.0f};
+    f2 a = pack_u32_to_unorm16x2(pack_color_rg11b10(s.f0_color)), b = pack_u32_to_unorm16x2(pack_color_rg11b10(s.f90_color));
+    g.fresnel = f4{a.x, a.y, b.x, b.y};
+    f3 pf = pack_normal_and_tangent(N, T);
+    g.normal_roughness = f4{pf.x, pf.y, pf.z, s.roughness};
+    g.material_0 = f4{s.anisotropy, 1.0f / s.ior, 0.0f, (float)surface_model / 256.0f};
+    return g;
+}
+static inline GBuffer store_gbuffer(const GBuffer& g) {           // the texture formats of pass/gbuffer.hpp:14-17
+    GBuffer o;
+    o.base_color = f4{store_half(g.base_color.x), store_half(g.base_color.y), store_half(g.base_color.z), store_half(g.base_color.w)};
+    o.normal_roughness = f4{store_half(g.normal_roughness.x), store_half(g.normal_roughness.y), store_half(g.normal_roughness.z), store_half(g.normal_roughness.w)};
+    o.fresnel = f4{store_unorm(g.fresnel.x, 16), store_unorm(g.fresnel.y, 16), store_unorm(g.fresnel.z, 16), store_unorm(g.fresnel.w, 16)};
+    o.material_0 = f4{store_unorm(g.material_0.x, 8), store_unorm(g.material_0.y, 8), store_unorm(g.material_0.z, 8), store_unorm(g.material_0.w, 8)};
+    return o;
+}
+static inline void unpack_gbuffer_to_surface(const GBuffer& g, f3& N, f3& T, SurfaceData& s, uint32_t& surface_model) {
+    surface_model = to_uint(g.material_0.w * 255.5f);
+    s.base_color = mk3(g.base_color.x, g.base_color.y, g.base_color.z);
+    s.f0_color = unpack_color_rg11b10(unpack_u32_from_unorm16x2(f2{g.fresnel.x, g.fresnel.y}));
+    s.f90_color = unpack_color_rg11b10(unpack_u32_from_unorm16x2(f2{g.fresnel.z, g.fresnel.w}));
+    s.roughness = g.normal_roughness.w;
+    unpack_normal_and_tangent(mk3(g.normal_roughness.x, g.normal_roughness.y, g.normal_roughness.z), N, T);
+    s.anisotropy = g.material_0.x;
+    s.ior = 1.0f / g.material_0.y;
+    s.opacity = 1.0f;
 }
 static inline f3 schlick_mix(f3 f0, f3 f90, float cos_theta) {    // utils.hlsl:40-42
     return lerp3(f0, f90, pow5(1.0f - cos_theta));

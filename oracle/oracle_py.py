@@ -69,6 +69,9 @@ def library() -> capi.Library:
         L.obpt_ggx_vndf_sample.argtypes, L.obpt_ggx_vndf_sample.restype = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p], None
         L.obpt_surface_eval_lit.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p]
         L.obpt_surface_eval_lit.restype = None
+        L.obpt_store_half.argtypes, L.obpt_store_half.restype = [C.c_float], C.c_float
+        L.obpt_gbuffer_roundtrip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.obpt_gbuffer_roundtrip.restype = None
         L.obpt_morton63.argtypes, L.obpt_morton63.restype = [C.c_void_p, C.c_void_p, C.c_void_p], C.c_uint64
     return _lib
 

@@ -9,12 +9,16 @@
 //   lighting         shaders/renderer/raytracing/deferred_lighting_secondary.hlsl:11-111
 //                    shaders/renderer/lights.hlsl:10-25
 //   next direction   shaders/renderer/raytracing/direction_sample/sample_secondary_ray.hlsl:11-69
-//   accumulate       shaders/renderer/raytracing/pt_accumulate.hlsl:3-11 (as FP32 sum / N)
-// with state_precision = fp32 (no fp16/unorm G-buffer quantisation) and NEE visibility by
-// shadow ray instead of the reference's rasterised shadow maps (NEW).
+//   accumulate       shaders/renderer/raytracing/pt_accumulate.hlsl:3-11
+// NEE visibility is a shadow ray instead of the reference's rasterised shadow maps (NEW).
+// state_precision = fp32 (default): state and colours stay FP32, accumulation is an FP32 sum / N.
+// state_precision = reference_fp16: every value the reference passes between its passes through a texture takes that
+// texture's format (path_tracing.cpp:248-288, pass/gbuffer.hpp:14-17): half ray directions / throughput / colours,
+// the packed G-buffer, the half additive blit per bounce, and the running half lerp of pt_accumulate.
 #include <algorithm>
 #include <cfloat>
 #include <thread>
+#include <type_traits>
 #include "oracle_scene.hpp"
 #include "oracle_ltc.hpp"
 
@@ -241,17 +245,38 @@ struct ThreadOut {
 // paths, probe * rays + ray for probe paths); `first_t` (optional) receives the first hit distance or -1.
 template <class Acc>
 static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool diffuse_only, uint32_t frame_index, uint32_t pixel,
-                       f3 O, f3 D, Acc* a, float* first_t, ThreadOut& out) {
+                       f3 O, f3 D, Acc* a, float* first_t, ThreadOut& out, uint32_t fp16_n = 0) {
     const Scene& sc = ctx.scene;
     const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);               // path_tracing.cpp:290
+    const bool fp16 = st.state_precision == BPT_STATE_REFERENCE_FP16;
     f3 Wt = splat3(1.0f);
     // Per-sample colour C_s starts at 0, receives this sample's contributions in order, and is added to the
     // FP32 sum buffer when the sample ends (the reference's color texture + accumulate pass,
     // path_tracing.cpp:421-480): sum += C_s, samples in ascending frame order.
     Acc C[3] = {0, 0, 0};
-    struct Flush { Acc* a; Acc* C; ~Flush() { a[0] += C[0]; a[1] += C[1]; a[2] += C[2]; } } flush{a, C};
-    auto add = [&](f3 c) { C[0] += c.x; C[1] += c.y; C[2] += c.z; };
+    // reference_fp16: C is the rgba16_sfloat colour texture; a bounce's light terms are summed in FP32 (bsum), multiplied
+    // by the throughput, stored as halves (deferred_lighting_secondary.hlsl:110) and written (bounce 1) or blended
+    // additively with a half result (path_tracing.cpp:441-459). The sample is folded into the image by the running
+    // lerp of pt_accumulate.hlsl:9 with weight 1/n, n = `fp16_n` (path_tracing.cpp:473).
+    struct Flush {
+        Acc* a; Acc* C; uint32_t n;
+        ~Flush() {
+            if (n == 0) { a[0] += C[0]; a[1] += C[1]; a[2] += C[2]; return; }
+            for (int k = 0; k < 3; k++) a[k] = n == 1 ? C[k] : (Acc)store_half(lerpf((float)a[k], (float)C[k], 1.0f / (float)n));
+        }
+    } flush{a, C, fp16_n};
+    f3 bsum = splat3(0.0f);
+    auto add = [&](f3 c) { if (fp16) bsum = bsum + c; else { C[0] += c.x; C[1] += c.y; C[2] += c.z; } };
+    auto commit = [&](uint32_t i) {
+        if (!fp16) return;
+        f3 c = store_half3(bsum * Wt);
+        f3 prev = mk3((float)C[0], (float)C[1], (float)C[2]);
+        f3 r = i == 1 ? c : store_half3(prev + c);
+        C[0] = r.x; C[1] = r.y; C[2] = r.z;
+        bsum = splat3(0.0f);
+    };
     for (uint32_t i = 1; i < B; i++) {
+        const f3 Wl = fp16 ? splat3(1.0f) : Wt;  // fp16: the light terms are summed unweighted, `commit` applies the throughput
         out.ext_per_bounce[i]++;
         HitRec h = trace_closest(sc, O, D, 0.001f, st.ray_length, frame_index, out.ext);   // rt_gbuffer.hlsl:17-25
         if (ctx.capture) out.cap_e.push_back({i, pixel, bpt_hit{h.t, h.u, h.v, h.hit ? h.instance_id : 0xffffffffu, h.hit ? h.prim : 0xffffffffu}});
@@ -260,7 +285,8 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             const float* m = sc.sky_transform;
             f3 dir = mk3((m[0] * D.x + m[1] * D.y) + m[2] * D.z, (m[3] * D.x + m[4] * D.y) + m[5] * D.z, (m[6] * D.x + m[7] * D.y) + m[8] * D.z);
             f3 color = sample_sky(sc, dir) * mk3(sc.sky_color[0], sc.sky_color[1], sc.sky_color[2]);
-            add(color * Wt);
+            add(fp16 ? color : color * Wt);
+            commit(i);
             out.missed++;
             return;
         }
@@ -275,7 +301,13 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
         f3 nts = surf.normal_map_value * 2.0f - splat3(1.0f);                               // rt_gbuffer_hit.hlsl:10-14
         f3 N = normalize((nts.x * vt.tangent_world + nts.y * vt.bitangent_world) + nts.z * vt.normal_world);
         if (surf.two_sided && dot(D, N) > 0.0f) N = -N;
-        f3 T = gbuffer_roundtrip_tangent(N, vt.tangent_world);                              // gbuffer.hlsl:27,41
+        f3 T;
+        if (fp16) {                                                                         // rt_gbuffer_hit.hlsl:15, rt_gbuffer.hlsl:27-31
+            GBuffer g = store_gbuffer(pack_surface_to_gbuffer(N, vt.tangent_world, surf, surface_model));
+            unpack_gbuffer_to_surface(g, N, T, surf, surface_model);                        // deferred_lighting_secondary.hlsl:37-40
+        } else {
+            T = gbuffer_roundtrip_tangent(N, vt.tangent_world);                             // gbuffer.hlsl:27,41
+        }
         f3 Bv = cross(N, T);                                                                // deferred_lighting_secondary.hlsl:41
         surf.opacity = 1.0f;                                                                // gbuffer.hlsl:44
         if (diffuse_only) {                                                                 // ddgi/deferred_lighting.hlsl:44-45
@@ -289,7 +321,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
         // that order: rect lights (LTC, unshadowed) first, then the NEE terms in light order.
         out.pending.clear();
         auto direct = [&](f3 le, f3 L, float tmax, uint32_t light_index) {
-            f3 c = (le * surface_eval(N, T, Bv, V, L, surf, surface_model)) * Wt;
+            f3 c = (le * surface_eval(N, T, Bv, V, L, surf, surface_model)) * Wl;
             if (!(fmax_(c.x, fmax_(c.y, c.z)) > 0.0f)) return;            // zero contribution: no ray
             if (st.nee_mode == BPT_NEE_NONE) { out.pending.push_back(c); return; }
             out.shd_per_bounce[i]++;
@@ -299,7 +331,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
         for (size_t l = 0; l < sc.rect_lights.size(); l++) {                                // deferred_lighting_secondary.hlsl:72-96
             const bpt_rect_light_data& rl = sc.rect_lights[l];
             f3 mrp = splat3(0.0f);
-            f3 c = ltc_rect_light(sc, rl, P, N, T, Bv, V, surf, surface_model, st.rect_shadow ? &mrp : nullptr) * Wt;
+            f3 c = ltc_rect_light(sc, rl, P, N, T, Bv, V, surf, surface_model, st.rect_shadow ? &mrp : nullptr) * Wl;
             if (!st.rect_shadow) { add(c); continue; }                                      // reference: rect lights are unshadowed
             // NEW switch rect_shadow = mrp_ray: one shadow ray towards the most representative point of the diffuse lobe;
             // distance to the light's plane as in rect_light_sample_texture (lights.hlsl:425-438)
@@ -323,6 +355,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             direct(le, L, dist * 0.999f, (uint32_t)(sc.dir_lights.size() + l));
         }
         for (const f3& c : out.pending) add(c);
+        commit(i);
 
         // next direction: sample_secondary_ray.hlsl:11-69 (bounce_index = i)
         if (i + 1 >= B) return;
@@ -343,6 +376,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
         f3 weight = bsdf / pdf;
         if (!finite3(weight)) weight = splat3(0.0f);                                        // :62-64
         f3 newW = weight * Wt;
+        if (fp16) { newW = store_half3(newW); out_dir = store_half3(out_dir); }             // rgba16_sfloat ray_weights / ray_directions (:66-68)
         // A zero-weight path can never contribute again (deferred_lighting_secondary.hlsl:17-21
         // writes 0 and the next sample pass kills it), so it is dropped here instead of traced.
         if (newW.x == 0.0f && newW.y == 0.0f && newW.z == 0.0f) return;
@@ -351,6 +385,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             float u3 = rng_next(seed);
             if (!(u3 < q)) return;
             newW = newW / q;
+            if (fp16) newW = store_half3(newW);
         }
         O = P; D = out_dir; Wt = newW;
     }
@@ -358,14 +393,16 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
 
 template <class Acc>
 static void render_pixel(const obpt_context& ctx, const bpt_camera& cam, const bpt_settings& st, uint32_t frame_index,
-                         uint32_t px, uint32_t py, Acc* a, ThreadOut& out) {
+                         uint32_t px, uint32_t py, Acc* a, ThreadOut& out, uint32_t fp16_n) {
     f3 O, D;
     camera_ray(cam, px, py, ctx.width, ctx.height, st.pixel_jitter, frame_index, O, D);                                  // generate_camera_ray.hlsl:4-16
-    trace_path(ctx, st, false, frame_index, py * ctx.width + px, O, D, a, (float*)nullptr, out);
+    if (st.state_precision == BPT_STATE_REFERENCE_FP16) D = store_half3(D);                                              // ray_directions is rgba16_sfloat (path_tracing.cpp:276-280)
+    trace_path(ctx, st, false, frame_index, py * ctx.width + px, O, D, a, (float*)nullptr, out, fp16_n);
 }
 
 template <class Acc>
-static void render_impl(obpt_context& ctx, const bpt_camera& cam, uint32_t first, uint32_t ns, const bpt_settings& st, Acc* accum, bool count) {
+static void render_impl(obpt_context& ctx, const bpt_camera& cam, uint32_t first, uint32_t ns, const bpt_settings& st, Acc* accum, bool count, uint32_t fp16_done = 0) {
+    const bool fp16_lerp = st.state_precision == BPT_STATE_REFERENCE_FP16 && std::is_same<Acc, float>::value;   // (the double-precision "converged" path sums)
     const uint32_t W = ctx.width, H = ctx.height;
     uint32_t nt = ctx.threads ? ctx.threads : std::max(1u, std::thread::hardware_concurrency());
     const uint32_t TILE = 16;
@@ -382,7 +419,7 @@ static void render_impl(obpt_context& ctx, const bpt_camera& cam, uint32_t first
             for (uint32_t y = y0; y < std::min(y0 + TILE, H); y++)
                 for (uint32_t x = x0; x < std::min(x0 + TILE, W); x++)
                     for (uint32_t s = 0; s < ns; s++, out.pixel_samples++)
-                        render_pixel(ctx, cam, st, first + s, x, y, accum + 4ull * (y * W + x), out);
+                        render_pixel(ctx, cam, st, first + s, x, y, accum + 4ull * (y * W + x), out, fp16_lerp ? fp16_done + s + 1 : 0u);
         }
     };
     std::vector<std::thread> th;
@@ -441,7 +478,9 @@ bpt_status obpt_set_threads(obpt_context* c, uint32_t n) { CHECK_CTX(c); c->thre
 uint32_t obpt_get_threads(const obpt_context* c) { return c->threads ? c->threads : std::max(1u, std::thread::hardware_concurrency()); }
 bpt_status obpt_resize(obpt_context* c, uint32_t w, uint32_t h) {
     CHECK_CTX(c); if (!w || !h) return BPT_ERR_INVALID;
-    c->width = w; c->height = h; c->accum.assign((size_t)w * h * 4, 0.0f); return BPT_OK;
+    c->width = w; c->height = h; c->accum.assign((size_t)w * h * 4, 0.0f);
+    c->accum_used = false; c->accum_fp16 = false; c->accum_count = 0;
+    return BPT_OK;
 }
 
 bpt_status obpt_scene_upload_geometry(obpt_context* c, const bpt_geometry_streams* s, const bpt_drawable_sbt_data* dr, const uint32_t* va,
@@ -550,12 +589,21 @@ bpt_status obpt_debug_read_bvh(obpt_context* c, uint32_t which, uint32_t* np, ui
     return BPT_OK;
 }
 
-bpt_status obpt_clear_accum(obpt_context* c) { CHECK_CTX(c); std::fill(c->accum.begin(), c->accum.end(), 0.0f); return BPT_OK; }
+bpt_status obpt_clear_accum(obpt_context* c) {
+    CHECK_CTX(c);
+    std::fill(c->accum.begin(), c->accum.end(), 0.0f);
+    c->accum_used = false; c->accum_fp16 = false; c->accum_count = 0;
+    return BPT_OK;
+}
 bpt_status obpt_render(obpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t ns, const bpt_settings* st) {
     CHECK_CTX(c); if (!cam || !st) return BPT_ERR_INVALID;
     if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
-    if (st->state_precision != BPT_STATE_FP32) return fail(c, BPT_ERR_UNSUPPORTED, "state_precision=reference_fp16 is not implemented");
-    render_impl<float>(*c, *cam, first, ns, *st, c->accum.data(), true);
+    if (st->state_precision != BPT_STATE_FP32 && st->state_precision != BPT_STATE_REFERENCE_FP16) return fail(c, BPT_ERR_INVALID, "state_precision: unknown value");
+    const bool fp16 = st->state_precision == BPT_STATE_REFERENCE_FP16;
+    if (c->accum_used && fp16 != c->accum_fp16) return fail(c, BPT_ERR_STATE, "state_precision changed without bpt_clear_accum");
+    c->accum_used = true; c->accum_fp16 = fp16;
+    render_impl<float>(*c, *cam, first, ns, *st, c->accum.data(), true, c->accum_count);
+    if (fp16) c->accum_count += ns;
     return BPT_OK;
 }
 bpt_status obpt_render_converged(obpt_context* c, const bpt_camera* cam, uint32_t first, uint32_t ns, const bpt_settings* st, float* out) {
@@ -573,7 +621,7 @@ bpt_status obpt_render_converged(obpt_context* c, const bpt_camera* cam, uint32_
 }
 bpt_status obpt_resolve(obpt_context* c, uint32_t total, float* out) {
     CHECK_CTX(c); if (!out || !total) return BPT_ERR_INVALID;
-    float inv = 1.0f / (float)total;
+    float inv = c->accum_fp16 ? 1.0f : 1.0f / (float)total;       // reference_fp16: the buffer already is the running average
     for (size_t p = 0; p < (size_t)c->width * c->height; p++) {
         for (int k = 0; k < 3; k++) out[p * 4 + k] = c->accum[p * 4 + k] * inv;
         out[p * 4 + 3] = 1.0f;
@@ -799,6 +847,18 @@ void obpt_surface_eval_lit(const float N[3], const float T[3], const float V[3],
     f3 n = mk3(N[0], N[1], N[2]), t = mk3(T[0], T[1], T[2]);
     f3 r = surface_eval(n, t, cross(n, t), mk3(V[0], V[1], V[2]), mk3(L[0], L[1], L[2]), s, 1u);
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+float obpt_store_half(float f) { return store_half(f); }
+void obpt_gbuffer_roundtrip(const float N[3], const float T[3], const float in[12], uint32_t model, float out[18], uint32_t* model_out) {
+    SurfaceData s = surface_data_default();
+    s.base_color = mk3(in[0], in[1], in[2]); s.f0_color = mk3(in[3], in[4], in[5]); s.f90_color = mk3(in[6], in[7], in[8]);
+    s.roughness = in[9]; s.anisotropy = in[10]; s.ior = in[11];
+    GBuffer g = store_gbuffer(pack_surface_to_gbuffer(mk3(N[0], N[1], N[2]), mk3(T[0], T[1], T[2]), s, model));
+    f3 No, To;
+    unpack_gbuffer_to_surface(g, No, To, s, model);
+    const float o[18] = {No.x, No.y, No.z, To.x, To.y, To.z, s.base_color.x, s.base_color.y, s.base_color.z, s.f0_color.x, s.f0_color.y, s.f0_color.z,
+                         s.f90_color.x, s.f90_color.y, s.f90_color.z, s.roughness, s.anisotropy, s.ior};
+    std::memcpy(out, o, sizeof(o)); *model_out = model;
 }
 uint64_t obpt_morton63(const float c[3], const float lo[3], const float hi[3]) {
     return morton63(mk3(c[0], c[1], c[2]), mk3(lo[0], lo[1], lo[2]), mk3(hi[0], hi[1], hi[2]));

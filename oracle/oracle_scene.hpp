@@ -105,7 +105,9 @@ struct obpt_context {
     uint32_t threads = 0;
     uint32_t tile_stride = 1, tile_offset = 0;
     std::string err;
-    std::vector<float> accum;        // W*H*4 FP32 sums
+    std::vector<float> accum;        // W*H*4 FP32 sums (reference_fp16: the running half-valued average)
+    bool accum_used = false, accum_fp16 = false;   // accumulation rule in force since the last clear
+    uint32_t accum_count = 0;        // reference_fp16: samples already folded in (pt_accumulate weight 1/(count+1))
     bpt_counters counters{};
     obpt_stats stats{};
     bool capture = false;

@@ -51,6 +51,8 @@ def lib():
         _lib.hc_acos.argtypes, _lib.hc_acos.restype = [C.c_float], C.c_float
         _lib.hc_ggx_vndf_sample.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
         _lib.hc_surface_eval_lit.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p]
+        _lib.hc_q_half.argtypes, _lib.hc_q_half.restype = [C.c_float], C.c_float
+        _lib.hc_surface_through_gbuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
         _lib.hc_render.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.POINTER(capi.Settings), C.c_void_p]
         _lib.hc_trace_probes.argtypes = [C.POINTER(HcScene), C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]

@@ -146,21 +146,33 @@ int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t
               const bpt_settings* st, float* accum_rgba) {
     Built b; build(*h, b);
     ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = std::min(std::max(st->max_bounces, 2u), 16u); sp.nee_mode = st->nee_mode; sp.ray_length = st->ray_length; sp.diffuse_only = 0; sp.russian_roulette = st->russian_roulette; sp.rect_shadow = st->rect_shadow;
+    sp.state_precision = st->state_precision;
+    const bool fp16 = st->state_precision == BPT_STATE_REFERENCE_FP16;      // driven like k_raygen / k_commit_bounce / k_accumulate_fp16 drive it
     for (uint32_t s = 0; s < nsamples; s++)
         for (uint32_t p = 0; p < width * height; p++) {
             float3 O, D, W = v3s(1.0f);
             float color[4] = {0, 0, 0, 0};           // per-sample colour, added to the sum when the sample ends
             camera_ray(*cam, p % width, p / width, width, height, st->pixel_jitter, frame_first + s, O, D);
+            if (fp16) D = q_half3(D);
             for (uint32_t i = 1; i < sp.max_bounces; i++) {
                 TraceResult r = trace_ray<false>(b.sc, O, D, 0.001f, sp.ray_length, frame_first + s);
-                HostSink sink{b.sc, st->nee_mode, frame_first + s, color, {}};
+                float bsum[4] = {0, 0, 0, 0};
+                HostSink sink{b.sc, st->nee_mode, frame_first + s, fp16 ? bsum : color, {}};
                 float3 nO, nD, nW;
                 bool cont = shade_vertex(b.sc, sp, frame_first + s, i, p, O, D, W, r, sink, nO, nD, nW);
                 for (auto& c : sink.pending) sink.add(c);
+                if (fp16) {
+                    float3 c = commit_bounce_fp16(v3(color[0], color[1], color[2]), v3(bsum[0], bsum[1], bsum[2]), W, i);
+                    color[0] = c.x; color[1] = c.y; color[2] = c.z;
+                }
                 if (!cont) break;
                 O = nO; D = nD; W = nW;
             }
-            for (int k = 0; k < 3; k++) accum_rgba[4ull * p + k] += color[k];
+            float* px = accum_rgba + 4ull * p;
+            if (fp16) {
+                float3 img = accumulate_fp16(v3(px[0], px[1], px[2]), v3(color[0], color[1], color[2]), s + 1);
+                px[0] = img.x; px[1] = img.y; px[2] = img.z;
+            } else for (int k = 0; k < 3; k++) px[k] += color[k];
         }
     return 0;
 }
@@ -170,7 +182,7 @@ __attribute__((visibility("default")))
 int hc_trace_probes(const hc_scene* h, const bpt_probe_volume* vol, const float* table, uint32_t frame_index, uint32_t num_bounces, float* out) {
     Built b; build(*h, b);
     ShadeParams sp; sp.width = 0; sp.height = 0; sp.max_bounces = std::min(std::max(num_bounces, 1u), 15u) + 1; sp.nee_mode = BPT_NEE_SHADOW_RAY;
-    sp.ray_length = vol->ray_length; sp.diffuse_only = 1; sp.russian_roulette = 0; sp.rect_shadow = 0;
+    sp.ray_length = vol->ray_length; sp.diffuse_only = 1; sp.russian_roulette = 0; sp.rect_shadow = 0; sp.state_precision = BPT_STATE_FP32;
     uint64_t total = (uint64_t)vol->probe_counts[0] * vol->probe_counts[1] * vol->probe_counts[2] * vol->rays_per_probe;
     for (uint64_t p = 0; p < total; p++) {
         float3 O, D, W = v3s(1.0f);
@@ -248,6 +260,18 @@ int hc_blend_probes(const bpt_probe_volume* vol, const float* table, uint32_t fr
     return 0;
 }
 
+__attribute__((visibility("default"))) float hc_q_half(float f) { return q_half(f); }
+__attribute__((visibility("default"))) void hc_surface_through_gbuffer(const float N[3], const float T[3], const float in[12], uint32_t model, float out[18], uint32_t* model_out) {
+    Surface s = surface_default();
+    s.base_color = v3(in[0], in[1], in[2]); s.f0_color = v3(in[3], in[4], in[5]); s.f90_color = v3(in[6], in[7], in[8]);
+    s.roughness = in[9]; s.anisotropy = in[10]; s.ior = in[11];
+    float3 No, To;
+    frame_through_gbuffer(v3(N[0], N[1], N[2]), v3(T[0], T[1], T[2]), No, To);
+    surface_through_gbuffer(s, model);
+    const float o[18] = {No.x, No.y, No.z, To.x, To.y, To.z, s.base_color.x, s.base_color.y, s.base_color.z, s.f0_color.x, s.f0_color.y, s.f0_color.z,
+                         s.f90_color.x, s.f90_color.y, s.f90_color.z, s.roughness, s.anisotropy, s.ior};
+    memcpy(out, o, sizeof(o)); *model_out = model;
+}
 __attribute__((visibility("default"))) uint32_t hc_rng_tea(uint32_t a, uint32_t b) { return rng_tea(a, b); }
 __attribute__((visibility("default"))) void hc_sincos_2pi(float u, float* s, float* c) { sincos_2pi(u, *s, *c); }
 __attribute__((visibility("default"))) float hc_atan2(float y, float x) { return atan2_(y, x); }

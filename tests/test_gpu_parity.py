@@ -296,7 +296,48 @@ def test_mode_switches(lib, oracle, switch):
     ca, cb = gpu.counters(), ref.counters()
     assert ca.extend_rays == cb.extend_rays and ca.shadow_rays == cb.shadow_rays
     with pytest.raises(capi.BptError):
-        gpu.render(cam, 0, 1, capi.Settings(state_precision=1))             # reference_fp16: rejected, not ignored
+        gpu.render(cam, 0, 1, capi.Settings(state_precision=1))             # a change of accumulation rule needs clear_accum
+    with pytest.raises(capi.BptError):
+        gpu.render(cam, 0, 1, capi.Settings(state_precision=7))             # unknown value: rejected, not ignored
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("scene_fn,W,H,bounces", [(scenes.small_test_scene, 96, 64, 6), (scenes.cornell_box, 100, 75, 5)])
+def test_reference_fp16_state(lib, oracle, scene_fn, W, H, bounces, mode):
+    """state_precision = reference_fp16 (SURVEY §8a storage note; rows a1/a8/a16/a17 literally): half ray directions and
+    throughput, the packed G-buffer through its texture formats, the half additive blit per bounce and the running half
+    lerp of pt_accumulate. One light => one shadow ray per vertex => the image is bit-identical to the oracle."""
+    scene = scene_fn()
+    gpu, ref = make_pair(lib, oracle, scene, W, H, mode)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=bounces, state_precision=capi.STATE_REFERENCE_FP16)
+    gpu.render(cam, 0, 3, st); ref.render(cam, 0, 3, st)
+    gpu.render(cam, 3, 2, st); ref.render(cam, 3, 2, st)                   # the sample count carries over between calls
+    a, b = gpu.resolve(5), ref.resolve(5)
+    np.testing.assert_array_equal(a[..., :3].view(np.uint32), b[..., :3].view(np.uint32))
+    np.testing.assert_array_equal(a[..., :3], a[..., :3].astype(np.float16).astype(np.float32))   # an rgba16_sfloat image
+    ca, cb = gpu.counters(), ref.counters()
+    assert ca.extend_rays == cb.extend_rays and ca.shadow_rays == cb.shadow_rays
+    gpu.clear_accum(); ref.clear_accum()                                    # back to the FP32 rule
+    gpu.render(cam, 0, 2, capi.Settings(max_bounces=bounces)); ref.render(cam, 0, 2, capi.Settings(max_bounces=bounces))
+    f32 = gpu.resolve(2)
+    np.testing.assert_array_equal(f32, ref.resolve(2))
+    assert (f32[..., :3] != a[..., :3]).any()
+
+
+def test_reference_fp16_host_pass(lib, oracle):
+    """The frame-at-a-time host pass (render_ahead / accumulate_ahead) follows the same running lerp."""
+    scene = scenes.small_test_scene()
+    W, H = 64, 48
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_MERGED)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=5, state_precision=capi.STATE_REFERENCE_FP16)
+    n = gpu.render_ahead(cam, 10, 4, st)
+    assert n >= 1
+    for _ in range(n):
+        gpu.accumulate_ahead(1)
+    ref.render(cam, 10, n, st)
+    np.testing.assert_array_equal(gpu.resolve(n)[..., :3].view(np.uint32), ref.resolve(n)[..., :3].view(np.uint32))
 
 
 def test_rect_shadow_switch(lib, oracle):

@@ -132,7 +132,81 @@ def test_mode_switches_bit_exact(oracle, switch):
     if switch == "russian_roulette":
         assert ctx.counters().extend_rays < base.counters().extend_rays          # fewer rays on dark paths
     with pytest.raises(capi.BptError):
-        ctx.render(cam, 0, 1, capi.Settings(state_precision=1))                 # rejected, not silently ignored
+        ctx.render(cam, 0, 1, capi.Settings(state_precision=1))                 # a change of accumulation rule needs clear_accum
+    with pytest.raises(capi.BptError):
+        ctx.render(cam, 0, 1, capi.Settings(state_precision=7))                 # unknown value: rejected, not silently ignored
+
+
+def test_fp16_storage_formats_bit_exact(oracle):
+    """state_precision = reference_fp16 building blocks: the half store is IEEE round-to-nearest-even (pinned against
+    numpy.float16, an independent implementation), and the G-buffer pack -> texture formats -> unpack round trip
+    (gbuffer.hlsl:18-45, pack.hlsl) is bit-identical between the CUDA source (host build) and the oracle."""
+    H, L = HC.lib(), oracle.library().lib
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([
+        rng.normal(size=4000).astype(np.float32) * np.float32(10.0) ** rng.integers(-9, 6, 4000).astype(np.float32),
+        np.float32([0.0, -0.0, 65504.0, 65519.99, 65520.0, 1e9, -1e9, 2.0 ** -24, 2.0 ** -25, 2.0 ** -25 * 1.0001, 2.0 ** -14, 6.0e-8, 3.0e-8,
+                    1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 0.1, 1 / 3, np.inf, -np.inf]),
+        (np.arange(2048, dtype=np.float32) + 0.5) * np.float32(2.0 ** -24),          # every denormal-half tie
+    ])
+    with np.errstate(over="ignore"):
+        want = vals.astype(np.float16).astype(np.float32)
+    got_h = np.float32([H.hc_q_half(float(v)) for v in vals]); got_o = np.float32([L.obpt_store_half(float(v)) for v in vals])
+    np.testing.assert_array_equal(got_h.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(got_o.view(np.uint32), want.view(np.uint32))
+    assert np.isnan(H.hc_q_half(float("nan"))) and np.isnan(L.obpt_store_half(float("nan")))
+    o1, o2, m1, m2 = np.zeros(18, np.float32), np.zeros(18, np.float32), C.c_uint32(), C.c_uint32()
+    worst_n = worst_f0 = 0.0
+    for k in range(1500):
+        N = rng.normal(size=3).astype(np.float32); N /= np.linalg.norm(N)
+        if k < 6: N = np.float32(np.eye(3)[k % 3] * (1 if k < 3 else -1))               # axis-aligned normals (oct-map corners / poles)
+        T = np.cross(N, rng.normal(size=3)).astype(np.float32); T /= np.linalg.norm(T)
+        surf = np.concatenate([rng.uniform(0, 1, 3), rng.uniform(0.02, 1, 6), rng.uniform(0.02, 1, 1), rng.uniform(0, 1, 1), rng.uniform(1.0, 2.5, 1)]).astype(np.float32)
+        args = (N.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p), surf.ctypes.data_as(C.c_void_p), 1)
+        H.hc_surface_through_gbuffer(*args, o1.ctypes.data_as(C.c_void_p), C.byref(m1))
+        L.obpt_gbuffer_roundtrip(*args, o2.ctypes.data_as(C.c_void_p), C.byref(m2))
+        np.testing.assert_array_equal(o1.view(np.uint32), o2.view(np.uint32))
+        assert m1.value == m2.value == 1                                                # MATERIAL_SURFACE_MODEL_LIT survives /256 -> unorm8 -> *255.5
+        worst_n = max(worst_n, float(np.abs(o1[0:3] - N).max())); worst_f0 = max(worst_f0, float(np.abs(o1[9:12] - surf[3:6]).max()))
+        assert abs(np.linalg.norm(o1[0:3]) - 1) < 1e-6 and abs(np.linalg.norm(o1[3:6]) - 1) < 1e-6 and abs(np.dot(o1[0:3], o1[3:6])) < 1e-6
+        assert np.abs(o1[6:9] - surf[0:3]).max() <= 2.0 ** -11 and abs(o1[15] - surf[9]) <= 2.0 ** -11     # half: 11 significant bits
+        assert abs(o1[16] - surf[10]) <= 0.5 / 255 + 1e-7 and abs(1 / o1[17] - 1 / surf[11]) <= 0.5 / 255 + 1e-7
+    assert 0 < worst_n < 2e-3 and 0 < worst_f0 < 34 / 2047         # quantised; green can lose 32/2047: the unorm16 quirk below takes 1 off the HIGH half-word when blue >= 0.5
+    # Reference quirk reproduced literally: pack_u32_to_unorm16x2 stores k/65536 in a unorm16 texel, which rounds to k-1
+    # for k > 32768, and unpack_u32_from_unorm16x2 only tolerates errors upwards — so a zero 11-bit red field BORROWS:
+    # f0 = (0, .5, .5) comes back with red = 2047/2047.
+    N, T = np.float32([0, 0, 1]), np.float32([1, 0, 0])
+    surf = np.float32([0.5, 0.5, 0.5, 0.0, 0.5, 0.5, 1, 1, 1, 0.5, 0, 1.5])
+    L.obpt_gbuffer_roundtrip(N.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p), surf.ctypes.data_as(C.c_void_p), 1, o2.ctypes.data_as(C.c_void_p), C.byref(m2))
+    assert o2[9] == 1.0 and abs(o2[10] - 0.5) < 34 / 2047 and abs(o2[11] - 0.5) < 2e-3
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name,bounces", [("cornell", 5), ("small", 6)])
+def test_render_reference_fp16_bit_exact(oracle, name, bounces, mode):
+    """state_precision = reference_fp16 (half state, packed G-buffer, half additive blit, running half lerp): CUDA source
+    (host build) == oracle bit for bit; every stored value is a half; and the mode differs from fp32 by ~1e-3, not more."""
+    scene = _scene(name)
+    W, H = 40, 28
+    ctx = oracle.OracleContext(W, H); ctx.upload_scene(scene, mode)
+    cam = oracle.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=bounces, state_precision=capi.STATE_REFERENCE_FP16)
+    ctx.render(cam, 3, 2, st); ctx.render(cam, 5, 1, st)                                  # 3 samples, in two calls (count carries over)
+    ref = ctx.resolve(3)
+    got = HC.HostScene(scene, ctx, mode).render(cam, W, H, 3, 3, st)
+    np.testing.assert_array_equal(got[..., :3].view(np.uint32), ref[..., :3].view(np.uint32))
+    np.testing.assert_array_equal(ref[..., :3], ref[..., :3].astype(np.float16).astype(np.float32))      # an rgba16_sfloat image
+    full = oracle.OracleContext(W, H); full.upload_scene(scene, mode)
+    full.render(cam, 3, 3, capi.Settings(max_bounces=bounces))
+    f32 = full.resolve(3)[..., :3]
+    assert (ref[..., :3] != f32).any()
+    # the fp16 state decorrelates individual paths (a 1e-3 change of a direction is a different sample after a bounce),
+    # but the image mean must agree closely
+    assert abs(float(ref[..., :3].mean()) - float(f32.mean())) < 0.03 * float(f32.mean())
+    one = oracle.OracleContext(W, H); one.upload_scene(scene, mode)
+    one.render(cam, 3, 1, st)
+    first = one.resolve(1)[..., :3]
+    assert first.max() > 0 and np.isfinite(first).all()
 
 
 def test_probe_blending_bit_exact(oracle):
