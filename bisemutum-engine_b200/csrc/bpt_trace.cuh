@@ -97,9 +97,10 @@ BPT_HD RaySpace make_space(float3 O, float3 D) {
     return r;
 }
 
-// One node step: returns the next node to visit (or kSentinel+1 == "pop") and optionally pushes.
+// One node step: returns the next node to visit (or BPT_POP) and, when both children are hit, the farther one in `far`
+// (BPT_POP otherwise) for the caller to push.
 #define BPT_POP ((int32_t)0x80000001)
-BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, float tmin, float tcull, int32_t* stack, int& sp) {
+BPT_HD int32_t node_step2(const float4* nodes, int32_t cur, const RaySpace& r, float tmin, float tcull, int32_t& far) {
     const float4* n = nodes + 4 * (size_t)cur;
     float4 n0 = BPT_LDG(n), n1 = BPT_LDG(n + 1), n2 = BPT_LDG(n + 2), n3 = BPT_LDG(n + 3);
     float c0lox = fmaf(n0.x, r.idir.x, -r.ood.x), c0hix = fmaf(n0.y, r.idir.x, -r.ood.x);
@@ -114,14 +115,21 @@ BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, fl
     float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tcull));
     bool h0 = t0n <= t0f, h1 = t1n <= t1f;
     int32_t ch0 = (int32_t)f2u(n3.x), ch1 = (int32_t)f2u(n3.y);
+    far = BPT_POP;
     if (h0 && h1) {
         bool c0_near = t0n <= t1n;
-        stack[sp++] = c0_near ? ch1 : ch0;
+        far = c0_near ? ch1 : ch0;
         return c0_near ? ch0 : ch1;
     }
     if (h0) return ch0;
     if (h1) return ch1;
     return BPT_POP;
+}
+BPT_HD int32_t node_step(const float4* nodes, int32_t cur, const RaySpace& r, float tmin, float tcull, int32_t* stack, int& sp) {
+    int32_t far;
+    int32_t next = node_step2(nodes, cur, r, tmin, tcull, far);
+    if (far != BPT_POP) stack[sp++] = far;
+    return next;
 }
 
 // ---- resumable traversal state -------------------------------------------------------------------
