@@ -347,7 +347,7 @@ def main():
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "width": W, "height": H, "max_bounces": B, "accel": args.accel, "triangles": scene.num_triangles,
-                   "step": "1 spp over the full frame per GPU (rank r renders frames [r*steps, (r+1)*steps)); samples_per_wave = min(steps, 2^24 / pixels)",
+                   "step": "1 spp over the full frame per GPU (rank r renders frames [r*steps, (r+1)*steps)); samples_per_wave = min(steps, 2^26 / pixels)",
                    "l2_policy": "inputs larger than L2: ~%d MB of per-path wavefront state streams through HBM every step; the %.0f MB scene+BVH is the steady-state L2-resident working set"
                    % (W * H * (6 * 16 + 20 + 16) // 1000000, (scene.num_triangles * (48 + 64)) / 1e6),
                    "multi_gpu": "sample-index sharding, scene+BVH replicated, one NCCL reduce of the FP32 sum buffer per batch" if world > 1 else "single GPU"},

@@ -477,7 +477,11 @@ __global__ void k_probe_blend(const __grid_constant__ bpt_probe_volume vol, cons
 static uint32_t wave_slots(const bpt_context* ctx) {
     const uint64_t npx = (uint64_t)ctx->width * ctx->height;
     const uint64_t nl = std::max<uint64_t>((uint64_t)ctx->num_dir + ctx->num_point + ctx->num_rect, 1);
-    uint64_t by_paths = std::max<uint64_t>(1, (1ull << 24) / npx);                 // <= 16.7 M paths in flight
+    // <= 67 M paths in flight (32 samples at 1080p; measured on configs[1]: 2^24 -> 1.95, 2^25 -> 1.87, 2^26 -> 1.82, 2^27 -> 1.80 ms
+    // per sample: every late, nearly empty bounce has a ~150 us latency floor that more samples per wave amortise);
+    // BPT_WAVE_PATHS_LOG2 overrides for tuning
+    static const int log2_paths = [] { const char* e = getenv("BPT_WAVE_PATHS_LOG2"); int v = e ? atoi(e) : 26; return v < 16 ? 16 : (v > 30 ? 30 : v); }();
+    uint64_t by_paths = std::max<uint64_t>(1, (1ull << log2_paths) / npx);
     uint64_t by_shadow = std::max<uint64_t>(1, (8ull << 30) / (npx * nl * 48));    // <= 8 GiB of shadow-ray records
     return (uint32_t)std::min<uint64_t>(std::min(by_paths, by_shadow), 64);
 }
