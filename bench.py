@@ -256,14 +256,16 @@ def main():
         lights_bytes = scene.dir_lights.nbytes + scene.point_lights.nbytes + scene.rect_lights.nbytes
         h2d = lights_bytes + 3 * 64 + 32            # lights (update_params) + camera matrices + settings
         d2h = W * H * 16
-        e2e_steps = max(8, min(args.steps, 64))
+        e2e_steps = max(8, min(args.steps, 128))
+        prefetch = 32                                   # samples per wave of the pass (the library clamps it to its wave size)
+        r.set_prefetch(prefetch)
         for i in range(3):
             r.ctx.upload_lights(scene); r.frame(RAY_LENGTH, B, True)
         r.ctx.sync(); r.ctx.reset_counters()
         barrier()
         # ring of pinned host buffers deep enough for one sample wave + slack: the pass prefetches a wave of samples,
         # so results arrive in bursts; the host must be able to queue the next wave while the previous read-backs drain
-        ring = 12
+        ring = prefetch + 8
         host_imgs = [host_img] + [torch.empty(H, W, 4, dtype=torch.float32).pin_memory() for _ in range(ring - 1)]
         dev_imgs = [dev_img] + [torch.empty(H, W, 4, dtype=torch.float32, device="cuda") for _ in range(ring - 1)]
         copy_stream = torch.cuda.Stream()
