@@ -127,6 +127,14 @@ class ProbeBlend(C.Structure):
     _fields_ = [("irradiance_size", C.c_uint32), ("visibility_size", C.c_uint32), ("alpha", C.c_float), ("history_valid", C.c_uint32)]
 
 
+class AoSettings(C.Structure):
+    """bpt_ao_settings = BasicRenderer::AmbientOcclusionSettings (renderer/basic.hpp:40-50)."""
+    _fields_ = [("range", C.c_float), ("strength", C.c_float), ("half_resolution", C.c_uint32)]
+
+
+GBUFFER_TEXEL = np.dtype([("base_color", np.float32, 4), ("normal_roughness", np.float32, 4), ("fresnel", np.float32, 4), ("material_0", np.float32, 4)])
+
+
 class BptError(RuntimeError):
     def __init__(self, status: int, where: str, detail: str):
         super().__init__(f"{where}: {STATUS_NAMES.get(status, status)} — {detail}")
@@ -164,6 +172,8 @@ COMMON_API = {
     "trace_shadow_rays": [_VP, _VP, _U64, _U32, _VP],
     "debug_capture": [_VP, _U32],
     "debug_read_queue": [_VP, _U32, _U32, _VP, _VP, _VP, _U64, _PU64],
+    "render_primary": [_VP, C.POINTER(Camera), _U32, C.POINTER(Settings), _VP, _VP],
+    "trace_ao": [_VP, C.POINTER(Camera), _U32, C.POINTER(AoSettings), _VP, _VP, _VP],
     "trace_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _VP],
     "blend_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _VP, C.POINTER(ProbeBlend), _VP, _VP],
 }
@@ -333,6 +343,24 @@ class Context:
         vis = np.zeros(len(rays), dtype=np.uint8)
         self._call("trace_shadow_rays", _ptr(rays), len(rays), frame_index, _ptr(vis))
         return vis
+
+    def render_primary(self, camera: Camera, frame_index: int, settings: Settings):
+        """OutputData{depth, gbuffer} of the pass: (H, W) float32 reverse-Z depth and (H, W) GBUFFER_TEXEL records."""
+        depth = np.zeros((self.height, self.width), dtype=f32)
+        gbuffer = np.zeros((self.height, self.width), dtype=GBUFFER_TEXEL)
+        self._call("render_primary", C.byref(camera), frame_index, C.byref(settings), _ptr(depth), _ptr(gbuffer))
+        return depth, gbuffer
+
+    def trace_ao(self, camera: Camera, frame_index: int, depth: np.ndarray, normal_roughness: np.ndarray, range_: float = 0.5, strength: float = 0.5,
+                 half_resolution: bool = True) -> np.ndarray:
+        """Ray-traced ambient occlusion: (ah, aw, 2) float32 = (ao, valid)."""
+        ao = AoSettings(range_, strength, 1 if half_resolution else 0)
+        ah, aw = (self.height // 2, self.width // 2) if half_resolution else (self.height, self.width)
+        out = np.zeros((ah, aw, 2), dtype=f32)
+        d = np.ascontiguousarray(depth, dtype=f32); nr = np.ascontiguousarray(normal_roughness, dtype=f32)
+        assert d.shape == (self.height, self.width) and nr.shape == (self.height, self.width, 4)
+        self._call("trace_ao", C.byref(camera), frame_index, C.byref(ao), _ptr(d), _ptr(nr), _ptr(out))
+        return out
 
     def trace_probes(self, volume: ProbeVolume, sample_table: np.ndarray, frame_index: int, num_bounces: int) -> np.ndarray:
         """(num_probes * rays_per_probe, 4) float32: radiance rgb + first hit distance (or -1)."""

@@ -336,6 +336,20 @@ bpt_status bpt_pending_ahead(bpt_context* c, uint32_t* pending, uint32_t* next_f
     return BPT_OK;
 }
 
+bpt_status bpt_render_primary(bpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_settings* st, float* out_depth, bpt_gbuffer_texel* out_gbuffer) {
+    NEED(c);
+    if (!cam || !st) return BPT_ERR_INVALID;
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "render_primary before build_accel");
+    if (st->state_precision != BPT_STATE_FP32 && st->state_precision != BPT_STATE_REFERENCE_FP16) return fail(c, BPT_ERR_INVALID, "state_precision: unknown value");
+    return wavefront_render_primary(c, *cam, frame_index, *st, out_depth, out_gbuffer);
+}
+bpt_status bpt_trace_ao(bpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_ao_settings* ao, const float* depth, const float* normal_roughness, float* out_ao) {
+    NEED(c);
+    if (!cam || !ao || !depth || !normal_roughness || !out_ao) return BPT_ERR_INVALID;
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "trace_ao before build_accel");
+    return wavefront_trace_ao(c, *cam, frame_index, *ao, depth, normal_roughness, out_ao);
+}
+
 bpt_status bpt_resolve_device(bpt_context* c, uint32_t total, float* d_out) {
     NEED(c);
     if (!total || !d_out) return BPT_ERR_INVALID;

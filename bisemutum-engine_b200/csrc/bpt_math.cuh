@@ -208,13 +208,14 @@ BPT_HD uint32_t pack_color_rg11b10(float3 c) {          // pack.hlsl:14-16
 BPT_HD float3 unpack_color_rg11b10(uint32_t p) {        // pack.hlsl:17-23
     return v3((float)(p & 0x7ffu) / 2047.0f, (float)((p >> 11) & 0x7ffu) / 2047.0f, (float)((p >> 22) & 0x3ffu) / 1023.0f);
 }
-// Fresnel colour through gbuffer.fresnel: rg11b10 -> two unorm16 channels (value k/65536, pack.hlsl:6-8) -> rgba16_unorm
-// texel -> uint(x * 65535.5) (pack.hlsl:9-12) -> rg11b10. (For k > 32768 the texel rounds to k-1: a reference quirk.)
-BPT_HD float3 fresnel_through_gbuffer(float3 c) {
+// Fresnel colour into gbuffer.fresnel: rg11b10 -> two unorm16 channels (value k/65536, pack.hlsl:6-8) -> rgba16_unorm texel;
+// and back: uint(x * 65535.5) (pack.hlsl:9-12) -> rg11b10. (For k > 32768 the texel rounds to k-1: a reference quirk.)
+BPT_HD float2 fresnel_to_gbuffer(float3 c) {
     uint32_t p = pack_color_rg11b10(c);
-    float lo = q_unorm((float)(p & 0xffffu) / 65536.0f, 65535.0f), hi = q_unorm((float)(p >> 16) / 65536.0f, 65535.0f);
-    return unpack_color_rg11b10(ftou(lo * 65535.5f) | (ftou(hi * 65535.5f) << 16));
+    return make_float2(q_unorm((float)(p & 0xffffu) / 65536.0f, 65535.0f), q_unorm((float)(p >> 16) / 65536.0f, 65535.0f));
 }
+BPT_HD float3 fresnel_from_gbuffer(float2 t) { return unpack_color_rg11b10(ftou(t.x * 65535.5f) | (ftou(t.y * 65535.5f) << 16)); }
+BPT_HD float3 fresnel_through_gbuffer(float3 c) { return fresnel_from_gbuffer(fresnel_to_gbuffer(c)); }
 BPT_HD float2 oct_encode(float3 n) {                    // pack.hlsl:88-95
     float l1 = (fabsf(n.x) + fabsf(n.y)) + fabsf(n.z);
     n = n / l1;
@@ -228,22 +229,26 @@ BPT_HD float3 oct_decode(float2 f) {                    // pack.hlsl:99-104
     n.y = n.y + (n.y >= 0.0f ? -t : t);
     return normalize3(n);
 }
-// (N, T) through gbuffer.normal_roughness.xyz (pack.hlsl:112-129) stored as three halves.
-BPT_HD void frame_through_gbuffer(float3 N, float3 T, float3& No, float3& To) {
+// (N, T) into gbuffer.normal_roughness.xyz (pack_normal_and_tangent, pack.hlsl:112-120) stored as three halves, and back
+// (unpack_normal_and_tangent, pack.hlsl:121-129).
+BPT_HD float3 frame_to_gbuffer(float3 N, float3 T) {
     float2 oct = oct_encode(N);
     Frame3 fr = frame_from_normal(N);
     float px = dot3(T, fr.x), py = dot3(T, fr.y);
     float lnorm = fabsf(px) + fabsf(py);
     px = px / lnorm; py = py / lnorm;
     float packed_x = px * 0.5f + 0.5f;
-    float pz = q_half(py < 0.0f ? -packed_x : packed_x);
-    No = oct_decode(make_float2(q_half(oct.x), q_half(oct.y)));
-    float sign = pz < 0.0f ? -1.0f : 1.0f;
-    float projected_x = (sign * pz) * 2.0f - 1.0f;
+    return v3(q_half(oct.x), q_half(oct.y), q_half(py < 0.0f ? -packed_x : packed_x));
+}
+BPT_HD void frame_from_gbuffer(float3 packed, float3& No, float3& To) {
+    No = oct_decode(make_float2(packed.x, packed.y));
+    float sign = packed.z < 0.0f ? -1.0f : 1.0f;
+    float projected_x = (sign * packed.z) * 2.0f - 1.0f;
     float projected_y = sign * (1.0f - fabsf(projected_x));
     Frame3 fo = frame_from_normal(No);
     To = normalize3(fo.x * projected_x + fo.y * projected_y);
 }
+BPT_HD void frame_through_gbuffer(float3 N, float3 T, float3& No, float3& To) { frame_from_gbuffer(frame_to_gbuffer(N, T), No, To); }
 
 // ---- surface / BSDF (material/utils.hlsl, material/lit.hlsl) ----------------------------------
 struct Surface {
@@ -343,6 +348,12 @@ BPT_HD float3 bsdf_eval_lut(float3 N, float3 V, const Surface& s, float3 int_dif
     float3 diffuse = (v3s(1.0f) - fr) * s.base_color * kInvPi;
     float3 specular = s.f0_color * int_brdf.x + s.f90_color * int_brdf.y;
     return diffuse * int_diffuse + specular * int_specular;
+}
+BPT_HD float3 cos_hemisphere_sample(float rand_x, float rand_y) {                           // sampling.hlsl:24-28
+    float sn, cs;
+    sincos_2pi(rand_x, sn, cs);
+    float r = sqrtf(rand_y);
+    return v3(cs * r, sn * r, sqrtf(tmax_(1.0f - rand_y, 0.0f)));
 }
 BPT_HD float3 uniform_sphere_sample(float rand_x, float rand_y) {                           // sampling.hlsl:14-19
     float sn, cs;

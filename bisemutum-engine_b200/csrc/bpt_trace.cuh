@@ -34,6 +34,7 @@ struct RayState {
     uint32_t frame_index;
     float opacity_u;
     bool have_u, found;
+    bool cull_non_opaque; // RAY_FLAG_CULL_NON_OPAQUE (RTAO rays): triangles that would run the any-hit rule are skipped instead
 };
 
 BPT_HD float ray_opacity_random(RayState& rs) {                 // hits/rt_gbuffer.hlsl:14-19
@@ -81,7 +82,7 @@ BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, flo
     if (!better) return false;
     // any-hit flag: per triangle (merged: e2.w) or per entered instance (two-level)
     uint32_t need_anyhit = slot_or_none == 0xffffffffu ? f2u(c.w) : instance_anyhit;
-    if (need_anyhit && !anyhit_keep(sc, rs, slot, prim, u, v)) return false;
+    if (need_anyhit && (rs.cull_non_opaque || !anyhit_keep(sc, rs, slot, prim, u, v))) return false;
     rs.tbest = t; rs.tcull = t * 1.00001f; rs.bu = u; rs.bv = v; rs.best_slot = slot; rs.best_prim = prim; rs.found = true;
     return true;
 }
@@ -150,7 +151,7 @@ struct Trav {
 
 BPT_HD void trav_begin(const DScene& sc, Trav& t, float3 O, float3 D, float tmin, float tmax, uint32_t frame_index) {
     t.rs.O = O; t.rs.D = D; t.rs.tmin = tmin; t.rs.tbest = tmax; t.rs.tcull = tmax * 1.00001f; t.rs.best_slot = 0xffffffffu; t.rs.best_prim = 0xffffffffu;
-    t.rs.bu = 0.0f; t.rs.bv = 0.0f; t.rs.frame_index = frame_index; t.rs.opacity_u = 0.0f; t.rs.have_u = false; t.rs.found = false;
+    t.rs.bu = 0.0f; t.rs.bv = 0.0f; t.rs.frame_index = frame_index; t.rs.opacity_u = 0.0f; t.rs.have_u = false; t.rs.found = false; t.rs.cull_non_opaque = false;
     const bool two_level = sc.accel_mode == BPT_ACCEL_TWO_LEVEL;
     t.world = make_space(O, D);
     t.cur = t.world;
@@ -201,10 +202,11 @@ BPT_HD TraceResult trav_result(const Trav& t) {
 }
 
 template <bool ANY>
-BPT_HD TraceResult trace_ray(const DScene& sc, float3 O, float3 D, float tmin, float tmax, uint32_t frame_index) {
+BPT_HD TraceResult trace_ray(const DScene& sc, float3 O, float3 D, float tmin, float tmax, uint32_t frame_index, bool cull_non_opaque = false) {
     Trav t;
     int32_t stack[kStackSize];
     trav_begin(sc, t, O, D, tmin, tmax, frame_index);
+    t.rs.cull_non_opaque = cull_non_opaque;
     while (!t.done) {
         if (t.node >= 0) trav_node(sc, t, stack);
         else trav_leaf<ANY>(sc, t, stack);

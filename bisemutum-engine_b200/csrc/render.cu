@@ -12,6 +12,7 @@
 #include "bpt_internal.cuh"
 #include "bpt_shade.cuh"
 #include "bpt_ddgi.cuh"
+#include "bpt_aov.cuh"
 #pragma nv_diag_suppress 128   // "loop is not reachable": the two-level branch of the merged-mode instantiation
 
 using namespace bptd;
@@ -48,6 +49,7 @@ struct RenderArgs {
     uint32_t pixel_base;      // probe tracing in chunks: global path id = pixel_base + local id (RNG key)
     uint32_t pixel_jitter;
     uint32_t probe_mode;      // 1: paths start at probes; colour.w receives the first hit distance
+    uint32_t cull_non_opaque; // connect kernel only: RAY_FLAG_CULL_NON_OPAQUE (the RTAO rays)
 };
 
 // warp-aggregated append: returns the slot for this lane (valid only if `emit`)
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kBlock, BPT_TRACE_MIN_BLOCKS) k_trace_spec(con
     int32_t stack[kStackSize];
     RayState rs;
     RaySpace sp_;
-    rs.found = false; rs.tbest = 0.0f; rs.tcull = 0.0f; rs.tmin = 0.001f;
+    rs.found = false; rs.tbest = 0.0f; rs.tcull = 0.0f; rs.tmin = 0.001f; rs.cull_non_opaque = ANY && a.cull_non_opaque != 0;
     int32_t node = kEmpty, leaf = 0, leaf2 = 0;
     // The top of the stack lives in a register (`tos`, kEmpty = nothing left): a pop hands out `tos` at once and the load of
     // the entry below it overlaps the node fetch instead of preceding it (ncu: 9 % of the stall samples sat behind that load).
@@ -403,6 +405,47 @@ __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ 
     }
 }
 
+// ---- primary-hit outputs (OutputData.depth / .gbuffer of PathTracingPass::render): one thread per camera ray ----
+__global__ void __launch_bounds__(kBlock) k_primary_aov(const __grid_constant__ RenderArgs a, float* __restrict__ depth, bpt_gbuffer_texel* __restrict__ gbuffer) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.qcount[QE + 1]) return;
+    float4 o = a.ray_o_in[i], d = a.ray_d_in[i], h = a.hit[i];
+    uint32_t pixel = __float_as_uint(o.w);                             // one slot: path id = pixel
+    TraceResult r;
+    r.t = h.x; r.u = h.y; r.v = h.z; r.prim = __float_as_uint(h.w); r.slot = a.hit_slot[i]; r.hit = h.x >= 0.0f;
+    float z; bpt_gbuffer_texel g;
+    primary_outputs(a.sc, a.cam, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), r, z, g);
+    depth[pixel] = z;
+    gbuffer[pixel] = g;
+}
+
+// ---- ray-traced ambient occlusion (ambient_occlusion_rt.hlsl:14-66): 4 any-hit rays per pixel through the connect kernel ----
+__global__ void __launch_bounds__(kBlock) k_ao_raygen(const __grid_constant__ RenderArgs a, uint32_t aw, uint32_t ah, uint32_t half_res, float range,
+                                                      const float* __restrict__ depth, const float4* __restrict__ normal_roughness) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    float3 origin = v3s(0.0f), dirs[4];
+    if (p < aw * ah) {
+        valid = ao_pixel_rays(a.cam, p % aw, p / aw, aw, ah, a.sp.width, a.sp.height, a.frame_base, half_res, depth, normal_roughness, origin, dirs);
+        a.color[p] = make_float4(0.0f, 0.0f, 0.0f, valid ? 1.0f : 0.0f);       // x counts the UNoccluded rays
+    }
+    for (int i = 0; i < 4; i++) {                                               // (all threads of the warp reach queue_push)
+        uint32_t slot = queue_push(&a.qcount[QS + 1], valid);
+        if (valid && slot < a.shadow_capacity) {
+            a.sh_o[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(p));
+            a.sh_d[slot] = make_float4(dirs[i].x, dirs[i].y, dirs[i].z, range);
+            a.sh_c[slot] = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+        }
+    }
+}
+__global__ void k_ao_finish(const float4* __restrict__ color, uint32_t n, float strength, float2* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float4 c = color[p];
+    // ao_tex is rg16_sfloat (ambient_occlusion.cpp:14): the value a later pass loads is the half
+    out[p] = c.w != 0.0f ? make_float2(q_half(ao_value(4u - (uint32_t)c.x, strength)), 1.0f) : make_float2(1.0f, 0.0f);
+}
+
 // ---- DDGI probe blending: one block per probe, one thread per octahedral texel --------------------
 template <bool VIS>
 __global__ void k_probe_blend(const __grid_constant__ bpt_probe_volume vol, const float2* __restrict__ table, uint32_t frame_index,
@@ -579,7 +622,7 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
     a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();
     a.contrib = st.state_precision == BPT_STATE_REFERENCE_FP16 ? wf.bcol.as<float4>() : a.color;
     a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
-    a.pixel_base = 0; a.probe_mode = 0;
+    a.pixel_base = 0; a.probe_mode = 0; a.cull_non_opaque = 0;
     if (!wf.grid_extend) {      // resident grids of the persistent traversal kernels: SMs x blocks that fit per SM
         int dev = 0, sms = 0, be = 0, ba = 0;
         BPT_CUDA_TRY(ctx, cudaGetDevice(&dev));
@@ -659,6 +702,78 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         LAUNCH_T(ctx, 4, k_tally, 1, 64, wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), (uint32_t)paths);
         done += slots;
     }
+    return BPT_OK;
+}
+
+// OutputData{depth, gbuffer} of PathTracingPass::render: camera rays of one frame, their closest hits, packed like the trace pass packs them.
+bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_settings& st, float* h_depth, bpt_gbuffer_texel* h_gbuffer) {
+    bpt_status s;
+    if ((s = wavefront_alloc(ctx))) return s;
+    WavefrontState& wf = ctx->wf;
+    wf.ahead_slots = wf.ahead_cursor = 0;                                     // raygen overwrites the per-sample colours
+    const uint32_t npx = ctx->width * ctx->height;
+    RenderArgs a;
+    if ((s = prepare_args(ctx, a, st, 2))) return s;
+    a.cam = cam; a.npx = npx; a.nslots = 1; a.frame_base = frame_index;
+    DevBuf d_depth, d_g;
+    auto cleanup = [&]() { dev_free(d_depth); dev_free(d_g); };
+    if ((s = dev_alloc(ctx, d_depth, (size_t)npx * 4)) || (s = dev_alloc(ctx, d_g, (size_t)npx * sizeof(bpt_gbuffer_texel)))) { cleanup(); return s; }
+    cudaError_t e = cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream);
+    a.ray_o_out = wf.ray_o[0].as<float4>(); a.ray_d_out = wf.ray_d[0].as<float4>(); a.ray_w_out = wf.ray_w[0].as<float4>();
+    a.ray_o_in = a.ray_o_out; a.ray_d_in = a.ray_d_out; a.ray_w_in = a.ray_w_out;
+    const uint64_t gen_threads = (uint64_t)((ctx->width + 7) / 8) * ((ctx->height + 3) / 4) * 32;
+    if (e == cudaSuccess) {
+        k_raygen<<<(unsigned)((gen_threads + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(a);
+        if (ctx->accel_mode == BPT_ACCEL_MERGED) k_extend_merged<<<wf.grid_extend_m, kBlock, 0, ctx->stream>>>(a, 1u);
+        else k_extend_two_level<<<wf.grid_extend, kBlock, 0, ctx->stream>>>(a, 1u);
+        k_primary_aov<<<(npx + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(a, d_depth.as<float>(), d_g.as<bpt_gbuffer_texel>());
+        k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), 0u);
+        ctx->launches += 4;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && h_depth) e = cudaMemcpyAsync(h_depth, d_depth.p, (size_t)npx * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && h_gbuffer) e = cudaMemcpyAsync(h_gbuffer, d_g.p, (size_t)npx * sizeof(bpt_gbuffer_texel), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) { ctx->err = std::string("render_primary: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}
+
+// AmbientOcclusionPass::render_raytraced (ambient_occlusion.cpp:217-262): depth + normal G-buffer in, rg16_sfloat (ao, valid) out.
+bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_ao_settings& ao, const float* h_depth,
+                              const float* h_normal_roughness, float* h_out) {
+    bpt_status s;
+    if ((s = wavefront_alloc(ctx))) return s;
+    WavefrontState& wf = ctx->wf;
+    wf.ahead_slots = wf.ahead_cursor = 0;
+    const uint32_t W = ctx->width, H = ctx->height;
+    if (ao.half_resolution && ((W | H) & 1u)) { ctx->err = "trace_ao: half resolution needs even width and height (texel-centre reads)"; return BPT_ERR_UNSUPPORTED; }
+    const uint32_t aw = ao.half_resolution ? W / 2 : W, ah = ao.half_resolution ? H / 2 : H, n = aw * ah;
+    if ((uint64_t)n * 4 > wf.shadow_capacity || n > wf.capacity) { ctx->err = "trace_ao: frame too large for the shadow-ray queue"; return BPT_ERR_UNSUPPORTED; }
+    bpt_settings st{};
+    st.ray_length = ao.range; st.max_bounces = 2; st.nee_mode = BPT_NEE_SHADOW_RAY;
+    RenderArgs a;
+    if ((s = prepare_args(ctx, a, st, 2))) return s;
+    a.cam = cam; a.npx = n; a.nslots = 1; a.frame_base = frame_index; a.cull_non_opaque = 1;
+    DevBuf d_depth, d_nr, d_out;
+    auto cleanup = [&]() { dev_free(d_depth); dev_free(d_nr); dev_free(d_out); };
+    if ((s = dev_upload(ctx, d_depth, h_depth, (size_t)W * H * 4)) || (s = dev_upload(ctx, d_nr, h_normal_roughness, (size_t)W * H * 16)) ||
+        (s = dev_alloc(ctx, d_out, (size_t)n * 8))) { cleanup(); return s; }
+    cudaError_t e = cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream);
+    if (e == cudaSuccess) {
+        const float range = ao.range > 0.05f ? ao.range : 0.05f;              // ambient_occlusion.cpp:241
+        k_ao_raygen<<<(n + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(a, aw, ah, ao.half_resolution ? 1u : 0u, range, d_depth.as<float>(), d_nr.as<float4>());
+        if (ctx->accel_mode == BPT_ACCEL_MERGED) k_connect_merged<<<wf.grid_connect_m, kBlock, 0, ctx->stream>>>(a, 1u);
+        else k_connect_two_level<<<wf.grid_connect, kBlock, 0, ctx->stream>>>(a, 1u);
+        k_ao_finish<<<(n + 255) / 256, 256, 0, ctx->stream>>>(wf.color.as<float4>(), n, ao.strength, d_out.as<float2>());
+        k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), 0u);
+        ctx->launches += 4;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) { ctx->err = std::string("trace_ao: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
     return BPT_OK;
 }
 

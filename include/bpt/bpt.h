@@ -379,6 +379,39 @@ BPT_API bpt_status bpt_debug_read_queue(
     uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t capacity, uint64_t* count);
 
 /* ---------------------------------------------------------------------------------------
+ * Primary-hit outputs: PathTracingPass::render returns OutputData{color, depth, velocity = invalid, gbuffer}
+ * (path_tracing.cpp:482-487; consumed by basic.cpp:162-165 and the post-process pass). bpt_render_primary produces
+ * `depth` (pt_depth.hlsl:7-16: reverse-Z device depth of the primary hit, 0 = background) and the primary G-buffer as
+ * the trace pass packs it (hits/rt_gbuffer_hit.hlsl:6-18, gbuffer.hlsl:18-33) — every channel holds the value a later
+ * pass LOADS from the reference's texture format (gbuffer.hpp:14-17: rgba16_sfloat, rgba16_sfloat, rgba16_unorm,
+ * rgba8_unorm). Texels of rays that miss are zero. Synchronous; either output may be NULL.
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_gbuffer_texel {   /* 64 B */
+    float base_color[4];
+    float normal_roughness[4];
+    float fresnel[4];
+    float material_0[4];
+} bpt_gbuffer_texel;
+BPT_API bpt_status bpt_render_primary(
+    bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_settings* settings,
+    float* out_depth /* W*H */, bpt_gbuffer_texel* out_gbuffer /* W*H */);
+
+/* Ray-traced ambient occlusion: AmbientOcclusionPass::render_raytraced (ambient_occlusion.cpp:217-262)
+ * = ambient_occlusion_rt.hlsl:14-66 through the connect kernel: per pixel 4 cosine-hemisphere any-hit rays from the
+ * position reconstructed from `depth`, RAY_FLAG_CULL_NON_OPAQUE | ACCEPT_FIRST_HIT, t in [0.001, max(range, 0.05)].
+ * Inputs are full-resolution W x H images in the layout bpt_render_primary writes (depth; normal_roughness = float4 per
+ * pixel). out_ao: (W or W/2) x (H or H/2) float2 = (ao, valid) as stored in the reference's rg16_sfloat target.
+ * half_resolution follows the shader's per-frame sub-pixel choice and needs even W and H. Synchronous. */
+typedef struct bpt_ao_settings {     /* BasicRenderer::AmbientOcclusionSettings (renderer/basic.hpp:40-50) */
+    float range;                     /* 0.5 */
+    float strength;                  /* 0.5 */
+    uint32_t half_resolution;        /* reference default: 1 */
+} bpt_ao_settings;
+BPT_API bpt_status bpt_trace_ao(
+    bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_ao_settings* settings,
+    const float* depth /* W*H */, const float* normal_roughness /* W*H*4 */, float* out_ao /* aw*ah*2 */);
+
+/* ---------------------------------------------------------------------------------------
  * DDGI-style probe tracing through the same extend/shade kernels
  * (shaders/renderer/ddgi/trace_gbuffer.hlsl:10-51, ddgi/deferred_lighting.hlsl:12-118).
  * ------------------------------------------------------------------------------------- */

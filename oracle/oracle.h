@@ -71,6 +71,11 @@ BPT_API bpt_status obpt_debug_capture(obpt_context* ctx, uint32_t enable);
 BPT_API bpt_status obpt_debug_read_queue(
     obpt_context* ctx, uint32_t bounce, uint32_t kind,
     uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t capacity, uint64_t* count);
+/* OutputData{depth, gbuffer} of PathTracingPass::render (path_tracing.cpp:482-487) and AmbientOcclusionPass::render_raytraced. */
+BPT_API bpt_status obpt_render_primary(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_settings* settings,
+                                       float* out_depth, bpt_gbuffer_texel* out_gbuffer);
+BPT_API bpt_status obpt_trace_ao(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_ao_settings* settings,
+                                 const float* depth, const float* normal_roughness, float* out_ao);
 BPT_API bpt_status obpt_trace_probes(
     obpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2,
     uint32_t frame_index, uint32_t num_bounces, float* out_radiance_dist);

@@ -281,6 +281,7 @@ struct RayCtx {
     bool any_mode, terminated;
     uint32_t frame_index;
     bool have_u; float opacity_u;
+    bool cull_non_opaque;    // RAY_FLAG_CULL_NON_OPAQUE (ambient_occlusion_rt.hlsl:59)
 };
 
 static inline float opacity_random(RayCtx& rc) {        // hits/rt_gbuffer.hlsl:14-19
@@ -301,6 +302,9 @@ static inline bool anyhit_accept(const Scene& sc, RayCtx& rc, uint32_t slot, uin
     const bpt_material& m = sc.materials[dr.material_offset / sizeof(bpt_material)];
     uint32_t blend = (m.flags >> BPT_MATERIAL_BLEND_SHIFT) & 0xffu;
     if (blend == BPT_BLEND_OPAQUE) return true;  // MATERIAL_BLEND_MODE_OPAQUE: any-hit body compiled out
+    // RAY_FLAG_CULL_NON_OPAQUE drops non-opaque geometry. The reference marks an instance non-opaque iff its material's
+    // blend mode is not opaque (accel.cpp:121-125), i.e. exactly the triangles that reach this point.
+    if (rc.cull_non_opaque) return false;
     float opacity = eval_opacity(sc, x.instance_id, prim, u, v);
     if (blend == BPT_BLEND_ALPHA_TEST) return !(opacity < 0.01f);
     return !(opacity_random(rc) < 1.0f - opacity);
@@ -408,8 +412,9 @@ HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32
     return h;
 }
 
-bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st) {
+bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool cull_non_opaque) {
     RayCtx rc{};
+    rc.cull_non_opaque = cull_non_opaque;
     rc.O = O; rc.D = D; rc.tmin = tmin; rc.tbest = tmax; rc.tcull = tmax * 1.00001f; rc.best_id = ~0ull;
     rc.any_mode = true; rc.terminated = false; rc.frame_index = frame_index; rc.have_u = false;
     trace_generic(sc, rc, st);

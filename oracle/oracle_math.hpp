@@ -363,6 +363,13 @@ static inline f3 surface_eval_lut(f3 N, f3 V, const SurfaceData& s, f3 int_diffu
 }
 
 // ---- sampling: core/utils/sampling.hlsl:14-19 -------------------------------------------
+// core/utils/sampling.hlsl:24-28
+static inline f3 cos_hemisphere_sample(float rand_x, float rand_y) {
+    float sn, cs;
+    sincos_2pi(rand_x, sn, cs);                         // phi = rand.x * TWO_PI
+    float r = sqrtf(rand_y);
+    return mk3(cs * r, sn * r, sqrtf(fmax_(1.0f - rand_y, 0.0f)));
+}
 static inline f3 uniform_sphere_sample(float rand_x, float rand_y) {
     float sn, cs;
     sincos_2pi(rand_x, sn, cs);

@@ -683,6 +683,108 @@ bpt_status obpt_debug_read_queue(obpt_context* c, uint32_t bounce, uint32_t kind
     if (kind == 1 && lights) std::copy(c->cap_shadow_lights[bounce].begin(), c->cap_shadow_lights[bounce].end(), lights);
     return BPT_OK;
 }
+// Primary-hit outputs of the pass: the first trace pass's G-buffer (rt_gbuffer_hit.hlsl:6-18 packed by gbuffer.hlsl:18-33 into the
+// formats of pass/gbuffer.hpp:14-17) and the depth pass (pt_depth.hlsl:7-16). Texels of missing rays: 0 (the reference leaves them untouched).
+bpt_status obpt_render_primary(obpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_settings* st, float* out_depth, bpt_gbuffer_texel* out_g) {
+    CHECK_CTX(c); if (!cam || !st) return BPT_ERR_INVALID;
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "render_primary before build_accel");
+    const Scene& sc = c->scene;
+    const uint32_t W = c->width, H = c->height;
+    uint32_t nt = obpt_get_threads(c);
+    std::vector<std::thread> th; std::vector<TraceStats> sts(nt);
+    auto work = [&](uint32_t tid) {
+        for (uint32_t p = tid; p < W * H; p += nt) {
+            f3 O, D;
+            camera_ray(*cam, p % W, p / W, W, H, st->pixel_jitter, frame_index, O, D);
+            if (st->state_precision == BPT_STATE_REFERENCE_FP16) D = store_half3(D);
+            HitRec h = trace_closest(sc, O, D, 0.001f, st->ray_length, frame_index, sts[tid]);
+            float depth = 0.0f;                                                          // DEVICE_Z_FARTHEST
+            bpt_gbuffer_texel g{};
+            if (h.hit) {
+                const InstanceXf& x = sc.xf[h.inst_slot];
+                const bpt_material& mat = sc.materials[sc.drawables[x.instance_id].material_offset / sizeof(bpt_material)];
+                uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
+                f3 P = O + D * h.t;
+                Vertex vt = fetch_vertex_attributes(sc, x, h.prim, h.u, h.v);
+                SurfaceData surf = material_function(sc, mat, vt.texcoord, vt.position_world);
+                f3 nts = surf.normal_map_value * 2.0f - splat3(1.0f);
+                f3 N = normalize((nts.x * vt.tangent_world + nts.y * vt.bitangent_world) + nts.z * vt.normal_world);
+                if (surf.two_sided && dot(D, N) > 0.0f) N = -N;
+                GBuffer gb = store_gbuffer(pack_surface_to_gbuffer(N, vt.tangent_world, surf, surface_model));
+                std::memcpy(g.base_color, &gb.base_color, 16); std::memcpy(g.normal_roughness, &gb.normal_roughness, 16);
+                std::memcpy(g.fresnel, &gb.fresnel, 16); std::memcpy(g.material_0, &gb.material_0, 16);
+                const float* m = cam->matrix_proj_view;                                  // pt_depth.hlsl:13-15
+                float z = ((m[2] * P.x + m[6] * P.y) + m[10] * P.z) + m[14];
+                float w = ((m[3] * P.x + m[7] * P.y) + m[11] * P.z) + m[15];
+                depth = z / w;
+            }
+            if (out_depth) out_depth[p] = depth;
+            if (out_g) out_g[p] = g;
+        }
+    };
+    for (uint32_t i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    for (auto& s : sts) { c->stats.extend_rays += s.rays; c->stats.extend_nodes += s.nodes; c->stats.extend_tris += s.tris; c->counters.extend_rays += s.rays; c->counters.extend_rays_per_bounce[1] += s.rays; }
+    return BPT_OK;
+}
+
+// ambient_occlusion_rt.hlsl:14-66 (AmbientOcclusionPass::render_raytraced, ambient_occlusion.cpp:217-262).
+bpt_status obpt_trace_ao(obpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_ao_settings* ao, const float* depth_img, const float* nr_img, float* out) {
+    CHECK_CTX(c); if (!cam || !ao || !depth_img || !nr_img || !out) return BPT_ERR_INVALID;
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "trace_ao before build_accel");
+    const Scene& sc = c->scene;
+    const uint32_t W = c->width, H = c->height;
+    if (ao->half_resolution && ((W | H) & 1u)) return fail(c, BPT_ERR_UNSUPPORTED, "trace_ao: half resolution needs even width and height (texel-centre reads)");
+    const uint32_t aw = ao->half_resolution ? W / 2 : W, ah = ao->half_resolution ? H / 2 : H;   // ambient_occlusion.cpp:217-218
+    const float range = ao->range > 0.05f ? ao->range : 0.05f;                                   // :241
+    uint32_t nt = obpt_get_threads(c);
+    std::vector<std::thread> th; std::vector<TraceStats> sts(nt);
+    auto work = [&](uint32_t tid) {
+        for (uint32_t p = tid; p < aw * ah; p += nt) {
+            uint32_t px = p % aw, py = p / aw;
+            float sx = 0.5f, sy = 0.5f;                                                          // :18-26
+            uint32_t tx = px, ty = py;
+            if (ao->half_resolution) {
+                sx = (frame_index & 1u) ? 0.75f : 0.25f; sy = (frame_index & 2u) ? 0.75f : 0.25f;
+                tx = std::min(2u * px + ((frame_index & 1u) ? 1u : 0u), W - 1u); ty = std::min(2u * py + ((frame_index & 2u) ? 1u : 0u), H - 1u);
+            }
+            float uvx = ((float)px + sx) / (float)aw, uvy = ((float)py + sy) / (float)ah;
+            float depth = depth_img[(size_t)ty * W + tx];                                        // linear sampler at a texel centre = that texel
+            if (depth == 0.0f) { out[2 * p] = 1.0f; out[2 * p + 1] = 0.0f; continue; }           // :29-32
+            const float* q = nr_img + 4 * ((size_t)ty * W + tx);
+            f3 normal, tangent;
+            unpack_normal_and_tangent(mk3(q[0], q[1], q[2]), normal, tangent);                   // :35-38
+            Frame frame = create_frame(normal, tangent);
+            const float* ip = cam->matrix_inv_proj; const float* iv = cam->matrix_inv_view;      // projection.hlsl:5-10
+            float nx = uvx * 2.0f - 1.0f, ny = 1.0f - uvy * 2.0f;
+            float vx = ((ip[0] * nx + ip[4] * ny) + ip[8] * depth) + ip[12];
+            float vy = ((ip[1] * nx + ip[5] * ny) + ip[9] * depth) + ip[13];
+            float vz = ((ip[2] * nx + ip[6] * ny) + ip[10] * depth) + ip[14];
+            float vw = ((ip[3] * nx + ip[7] * ny) + ip[11] * depth) + ip[15];
+            vx = vx / vw; vy = vy / vw; vz = vz / vw;
+            f3 Pw = mk3(((iv[0] * vx + iv[4] * vy) + iv[8] * vz) + iv[12], ((iv[1] * vx + iv[5] * vy) + iv[9] * vz) + iv[13],
+                        ((iv[2] * vx + iv[6] * vy) + iv[10] * vz) + iv[14]);                     // :41-42
+            f3 origin = Pw + normal * 0.001f;                                                    // :56
+            uint32_t seed = rng_tea(py * aw + px, frame_index);                                  // :44
+            uint32_t occluded = 0;
+            for (int i = 0; i < 4; i++) {                                                        // :47-63
+                float r0 = rng_next(seed);
+                float r1 = rng_next(seed);
+                f3 dir = frame_to_world(frame, cos_hemisphere_sample(r0, r1));
+                if (trace_any(sc, origin, dir, 0.001f, range, frame_index, sts[tid], true)) occluded++;
+            }
+            out[2 * p] = store_half(1.0f - ((float)occluded * ao->strength) / 4.0f);             // :64, rg16_sfloat target (ambient_occlusion.cpp:14)
+            out[2 * p + 1] = 1.0f;
+        }
+    };
+    for (uint32_t i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    for (auto& s : sts) { c->stats.shadow_rays += s.rays; c->stats.shadow_nodes += s.nodes; c->stats.shadow_tris += s.tris; c->counters.shadow_rays += s.rays; c->counters.shadow_rays_per_bounce[1] += s.rays; }
+    return BPT_OK;
+}
+
 // DDGI-style probe tracing: ddgi/trace_gbuffer.hlsl:10-51 (probe centre, R2-table direction, TraceRay) +
 // ddgi/deferred_lighting.hlsl:12-118 (diffuse-only surface, V = normalize(probe - P)); further bounces continue
 // the path through the same trace/shade code (BASELINE configs[4]); previous-frame DDGI feedback is not modelled.

@@ -92,7 +92,7 @@ static inline f3 xf_vector_transposed(const float m[12], f3 v) {
 
 struct HitRec { float t, u, v; uint32_t inst_slot, instance_id, prim; bool hit; };
 HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st);
-bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st);
+bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool cull_non_opaque = false);
 
 // oracle_render.cpp helpers used by traversal (any-hit opacity)
 float eval_opacity(const Scene& sc, uint32_t instance_id, uint32_t prim, float u, float v);

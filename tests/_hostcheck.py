@@ -55,6 +55,8 @@ def lib():
         _lib.hc_surface_through_gbuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
         _lib.hc_render.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.POINTER(capi.Settings), C.c_void_p]
+        _lib.hc_render_primary.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.Settings), C.c_void_p, C.c_void_p]
+        _lib.hc_trace_ao.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.AoSettings), C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_trace_probes.argtypes = [C.POINTER(HcScene), C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.hc_blend_probes.argtypes = [C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(capi.ProbeBlend), C.c_void_p, C.c_void_p]
         _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -112,6 +114,19 @@ class HostScene:
         accum = np.zeros((height, width, 4), np.float32)
         lib().hc_render(C.byref(self.h), C.byref(camera), width, height, frame_first, nsamples, C.byref(settings), accum.ctypes.data_as(C.c_void_p))
         return accum
+
+    def render_primary(self, camera, width, height, frame_index, settings):
+        depth = np.zeros((height, width), np.float32); g = np.zeros((height, width), capi.GBUFFER_TEXEL)
+        lib().hc_render_primary(C.byref(self.h), C.byref(camera), width, height, frame_index, C.byref(settings), depth.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p))
+        return depth, g
+
+    def trace_ao(self, camera, width, height, frame_index, depth, normal_roughness, range_=0.5, strength=0.5, half_resolution=True):
+        ao = capi.AoSettings(range_, strength, 1 if half_resolution else 0)
+        ah, aw = (height // 2, width // 2) if half_resolution else (height, width)
+        out = np.zeros((ah, aw, 2), np.float32)
+        d = np.ascontiguousarray(depth, np.float32); nr = np.ascontiguousarray(normal_roughness, np.float32)
+        lib().hc_trace_ao(C.byref(self.h), C.byref(camera), width, height, frame_index, C.byref(ao), d.ctypes.data_as(C.c_void_p), nr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
 
     def trace(self, rays, frame_index=0):
         hits = np.zeros(len(rays), capi.HIT)

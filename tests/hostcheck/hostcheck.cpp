@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../bisemutum-engine_b200/csrc/bpt_shade.cuh"
 #include "../../bisemutum-engine_b200/csrc/bpt_ddgi.cuh"
+#include "../../bisemutum-engine_b200/csrc/bpt_aov.cuh"
 
 using namespace bptd;
 
@@ -174,6 +175,37 @@ int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t
                 px[0] = img.x; px[1] = img.y; px[2] = img.z;
             } else for (int k = 0; k < 3; k++) px[k] += color[k];
         }
+    return 0;
+}
+
+// Primary-hit outputs and RTAO: the per-thread functions of bpt_aov.cuh driven like k_primary_aov / k_ao_raygen + connect + k_ao_finish.
+__attribute__((visibility("default")))
+int hc_render_primary(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t height, uint32_t frame_index, const bpt_settings* st, float* depth, bpt_gbuffer_texel* g) {
+    Built b; build(*h, b);
+    for (uint32_t p = 0; p < width * height; p++) {
+        float3 O, D;
+        camera_ray(*cam, p % width, p / width, width, height, st->pixel_jitter, frame_index, O, D);
+        if (st->state_precision == BPT_STATE_REFERENCE_FP16) D = q_half3(D);
+        TraceResult r = trace_ray<false>(b.sc, O, D, 0.001f, st->ray_length, frame_index);
+        primary_outputs(b.sc, *cam, O, D, r, depth[p], g[p]);
+    }
+    return 0;
+}
+__attribute__((visibility("default")))
+int hc_trace_ao(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t height, uint32_t frame_index, const bpt_ao_settings* ao, const float* depth,
+                const float* normal_roughness, float* out) {
+    Built b; build(*h, b);
+    const uint32_t aw = ao->half_resolution ? width / 2 : width, ah = ao->half_resolution ? height / 2 : height;
+    const float range = ao->range > 0.05f ? ao->range : 0.05f;
+    for (uint32_t p = 0; p < aw * ah; p++) {
+        float3 origin, dirs[4];
+        if (!ao_pixel_rays(*cam, p % aw, p / aw, aw, ah, width, height, frame_index, ao->half_resolution, depth, reinterpret_cast<const float4*>(normal_roughness), origin, dirs)) {
+            out[2 * p] = 1.0f; out[2 * p + 1] = 0.0f; continue;
+        }
+        uint32_t unoccluded = 0;
+        for (int i = 0; i < 4; i++) unoccluded += trace_ray<true>(b.sc, origin, dirs[i], 0.001f, range, frame_index, true).hit ? 0u : 1u;
+        out[2 * p] = q_half(ao_value(4u - unoccluded, ao->strength)); out[2 * p + 1] = 1.0f;
+    }
     return 0;
 }
 

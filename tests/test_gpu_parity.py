@@ -325,6 +325,34 @@ def test_reference_fp16_state(lib, oracle, scene_fn, W, H, bounces, mode):
     assert (f32[..., :3] != a[..., :3]).any()
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_primary_outputs_and_rtao(lib, oracle, mode):
+    """bpt_render_primary (OutputData.depth / .gbuffer) and bpt_trace_ao (RTAO through the connect kernel, cull-non-opaque
+    any-hit rays) against the oracle: bit-exact, on the reference's own example scene (alpha-tested + translucent drawables)."""
+    import os
+    scene = scenes.scene_basic(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scene_basic.npz"))
+    W, H = 160, 96
+    gpu, ref = make_pair(lib, oracle, scene, W, H, mode)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=4)
+    depth, g = gpu.render_primary(cam, 2, st)
+    rdepth, rg = ref.render_primary(cam, 2, st)
+    np.testing.assert_array_equal(depth.view(np.uint32), rdepth.view(np.uint32))
+    for f in capi.GBUFFER_TEXEL.names:
+        np.testing.assert_array_equal(g[f].view(np.uint32), rg[f].view(np.uint32), err_msg=f)
+    assert 0.3 < (depth > 0).mean() < 1.0
+    for half, frame in ((False, 5), (True, 4), (True, 7)):
+        a = gpu.trace_ao(cam, frame, depth, g["normal_roughness"], 0.5, 0.5, half)
+        b = ref.trace_ao(cam, frame, rdepth, rg["normal_roughness"], 0.5, 0.5, half)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert (a[..., 1] == 1).any() and (a[..., 0] < 1).any()
+    ca, cb = gpu.counters(), ref.counters()
+    assert ca.extend_rays == cb.extend_rays == W * H and ca.shadow_rays == cb.shadow_rays > 0
+    # the render path is unaffected by the extra passes (they reuse its buffers)
+    gpu.render(cam, 0, 2, st); ref.render(cam, 0, 2, st)
+    np.testing.assert_array_equal(gpu.resolve(2), ref.resolve(2))
+
+
 def test_reference_fp16_host_pass(lib, oracle):
     """The frame-at-a-time host pass (render_ahead / accumulate_ahead) follows the same running lerp."""
     scene = scenes.small_test_scene()

@@ -209,6 +209,53 @@ def test_render_reference_fp16_bit_exact(oracle, name, bounces, mode):
     assert first.max() > 0 and np.isfinite(first).all()
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_primary_outputs_and_rtao_bit_exact(oracle, mode):
+    """OutputData{depth, gbuffer} of the pass (pt_depth.hlsl, rt_gbuffer_hit.hlsl + gbuffer.hlsl packing into the texture
+    formats) and the RTAO pass that consumes depth + normal G-buffer (ambient_occlusion_rt.hlsl): CUDA source (host build)
+    == oracle, plus the properties the formats and the geometry imply."""
+    scene = scenes.scene_basic(os.path.join(GOLDEN, "scene_basic.npz"))       # has an alpha-tested and a translucent drawable
+    W, H = 64, 40
+    ctx = oracle.OracleContext(W, H); ctx.upload_scene(scene, mode)
+    cam = oracle.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=4)
+    depth, g = ctx.render_primary(cam, 0, st)
+    hs = HC.HostScene(scene, ctx, mode)
+    hdepth, hg = hs.render_primary(cam, W, H, 0, st)
+    np.testing.assert_array_equal(depth.view(np.uint32), hdepth.view(np.uint32))
+    for f in capi.GBUFFER_TEXEL.names:
+        np.testing.assert_array_equal(g[f].view(np.uint32), hg[f].view(np.uint32), err_msg=f)
+    hit = depth > 0
+    assert 0.3 < hit.mean() < 1.0 and (depth[hit] < 1.0).all()                                   # reverse-Z: (0, 1), 0 = background
+    assert (g["base_color"][~hit] == 0).all() and (g["base_color"][hit][:, 3] == 1).all()
+    for f in ("base_color", "normal_roughness"):                                                 # rgba16_sfloat texels
+        np.testing.assert_array_equal(g[f], g[f].astype(np.float16).astype(np.float32))
+    np.testing.assert_array_equal(g["fresnel"] * 65535, np.round(g["fresnel"] * 65535))          # rgba16_unorm
+    np.testing.assert_allclose(g["material_0"] * 255, np.round(g["material_0"] * 255), atol=1e-4)   # rgba8_unorm
+    assert (np.round(g["material_0"][hit][:, 3] * 255) == 1).all()                               # MATERIAL_SURFACE_MODEL_LIT / 256 -> texel 1
+    # depth -> position: the hit point reprojected with inv(proj_view) lies on the camera ray at the traced distance
+    # (checked through the AO pass below, whose origin is that reconstruction)
+    for half, frame in ((False, 3), (True, 0), (True, 1), (True, 2), (True, 3)):
+        ao = ctx.trace_ao(cam, frame, depth, g["normal_roughness"], 0.5, 0.5, half)
+        hao = hs.trace_ao(cam, W, H, frame, depth, g["normal_roughness"], 0.5, 0.5, half)
+        np.testing.assert_array_equal(ao.view(np.uint32), hao.view(np.uint32))
+        valid = ao[..., 1] == 1
+        assert set(np.unique(ao[..., 1])) <= {0.0, 1.0} and valid.any()
+        assert set(np.unique(ao[valid][:, 0])) <= {np.float32(np.float16(1 - k * 0.5 / 4)) for k in range(5)}   # 4 rays, strength 0.5, half store
+        assert (ao[~valid][:, 0] == 1).all()
+        if not half:
+            np.testing.assert_array_equal(valid, hit)
+            assert 0.02 < (ao[valid][:, 0] < 1).mean() < 0.9                                     # contact shadows exist, open floor is unoccluded
+    far = ctx.trace_ao(cam, 3, depth, g["normal_roughness"], 50.0, 1.0, False)                   # longer rays can only occlude more
+    near = ctx.trace_ao(cam, 3, depth, g["normal_roughness"], 0.5, 1.0, False)
+    assert (far[..., 0] <= near[..., 0]).all() and (far[..., 0] < near[..., 0]).any()
+    # fp16 state: the camera ray direction is a half, so the primary outputs move slightly
+    d16, _ = ctx.render_primary(cam, 0, capi.Settings(max_bounces=4, state_precision=capi.STATE_REFERENCE_FP16))
+    h16, _ = hs.render_primary(cam, W, H, 0, capi.Settings(max_bounces=4, state_precision=capi.STATE_REFERENCE_FP16))
+    np.testing.assert_array_equal(d16.view(np.uint32), h16.view(np.uint32))
+    assert (d16 != depth).any() and np.abs(d16 - depth)[hit & (d16 > 0)].max() < 0.05
+
+
 def test_probe_blending_bit_exact(oracle):
     """DDGI probe blending: irradiance / visibility octahedral gathers, gamma-5 temporal blend,
     border + corner copies — CUDA source (host build) vs oracle, plus structural properties of the atlases."""
