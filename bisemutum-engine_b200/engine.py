@@ -45,6 +45,7 @@ def host_library():
         h.bpt_host_pass_set_camera.argtypes = [C.c_void_p, C.POINTER(HostCameraDesc)]
         h.bpt_host_pass_set_frame.argtypes = [C.c_void_p, C.c_uint64]
         h.bpt_host_pass_set_prefetch.argtypes = [C.c_void_p, C.c_uint32]
+        h.bpt_host_pass_read_primary.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p]
         h.bpt_host_pass_frame.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         h.bpt_host_pass_frame.restype = C.c_int
         _host = h
@@ -139,6 +140,15 @@ class Renderer:
         if st != 0:
             raise capi.BptError(st, "PathTracingPass::render", self.lib.fn("last_error")(self.ctx._h).decode())
         return n.value
+
+    def primary_outputs(self, ray_length: float = 100.0, max_bounces: int = 3):
+        """OutputData.depth / .gbuffer of the current frame: (H, W) float32 depth, (H, W) capi.GBUFFER_TEXEL."""
+        depth = np.zeros((self.height, self.width), np.float32)
+        g = np.zeros((self.height, self.width), capi.GBUFFER_TEXEL)
+        st = host_library().bpt_host_pass_read_primary(self._pass, ray_length, max_bounces, depth.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p))
+        if st != 0:
+            raise capi.BptError(st, "PathTracingPass::read_primary_outputs", self.lib.fn("last_error")(self.ctx._h).decode())
+        return depth, g
 
     def image(self, accumulated_frames: int) -> np.ndarray:
         return self.ctx.resolve(accumulated_frames)

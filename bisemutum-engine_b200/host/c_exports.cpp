@@ -102,6 +102,12 @@ HOST_API void bpt_host_pass_set_camera(bpt_host_pass* p, const bpt_host_camera_d
     p->camera.set_target_extent(cam->width, cam->height);
 }
 HOST_API void bpt_host_pass_set_frame(bpt_host_pass* p, uint64_t frame) { p->frame = frame; }
+// OutputData.depth / .gbuffer of the camera's current frame (PathTracingPass::read_primary_outputs). Returns bpt_status.
+HOST_API int bpt_host_pass_read_primary(bpt_host_pass* p, float ray_length, uint32_t max_bounces, float* depth, bpt_gbuffer_texel* gbuffer) {
+    BasicRenderer::PathTracingSettings s; s.ray_length = ray_length; s.max_bounces = max_bounces;
+    p->camera.update_shader_params(p->frame);
+    return (int)p->pass->read_primary_outputs(p->camera, s, depth, gbuffer);
+}
 // Samples traced ahead per wave while the history stays valid (throughput vs latency of the first frame; default 8).
 HOST_API void bpt_host_pass_set_prefetch(bpt_host_pass* p, uint32_t frames) { p->pass->set_prefetch_frames(frames); }
 // One engine frame: camera.update_shader_params → pass.render (records) → rg.execute. Returns bpt_status.

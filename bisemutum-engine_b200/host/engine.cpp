@@ -148,8 +148,12 @@ auto PathTracingPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, In
 
     OutputData out;
     out.color = rg.add_texture(width, height, 16);
-    out.depth = gfx::TextureHandle{};
-    out.velocity = gfx::TextureHandle{};
+    out.depth = rg.add_texture(width, height, 4);                                  // d32_sfloat (path_tracing.cpp:258-262)
+    out.velocity = gfx::TextureHandle{};                                           // invalid, as the reference (:485)
+    out.gbuffer.base_color = rg.add_texture(width, height, 8);                     // gbuffer.hpp:14-17
+    out.gbuffer.normal_roughness = rg.add_texture(width, height, 8);
+    out.gbuffer.fresnel = rg.add_texture(width, height, 8);
+    out.gbuffer.material_0 = rg.add_texture(width, height, 4);
 
     struct PassData { gfx::TextureHandle color; };
     auto [builder, pass_data] = rg.add_compute_pass<PassData>("PT CUDA wavefront");
@@ -180,6 +184,19 @@ auto PathTracingPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, In
             if (status_ == BPT_OK) status_ = bpt_accumulate_ahead(ctx_, 1);
         });
     return out;
+}
+
+auto PathTracingPass::read_primary_outputs(gfx::Camera const& camera, BasicRenderer::PathTracingSettings const& settings, float* depth,
+                                           bpt_gbuffer_texel* gbuffer) -> bpt_status {
+    bpt_camera cam;
+    std::memcpy(cam.matrix_inv_view, camera.matrix_inv_view().data(), 64);
+    std::memcpy(cam.matrix_inv_proj, camera.matrix_inv_proj().data(), 64);
+    std::memcpy(cam.matrix_proj_view, camera.matrix_proj_view().data(), 64);
+    bpt_settings st{};
+    st.ray_length = settings.ray_length;
+    st.max_bounces = settings.max_bounces;
+    status_ = bpt_render_primary(ctx_, &cam, camera.frame_index(), &st, depth, gbuffer);
+    return status_;
 }
 
 auto PathTracingPass::accumulated_frames(gfx::Camera const& camera) const -> uint64_t {

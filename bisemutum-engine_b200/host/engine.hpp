@@ -160,7 +160,8 @@ struct BasicRenderer {
 // Drop-in for bi::PathTracingPass (src/renderer/pass/path_tracing.hpp:12-69): same two methods.
 struct PathTracingPass final {
     struct InputData final { gfx::AccelerationStructureHandle scene_accel; };
-    struct OutputData final { gfx::TextureHandle color; gfx::TextureHandle depth; gfx::TextureHandle velocity; };
+    struct GBufferTextures final { gfx::TextureHandle base_color, normal_roughness, fresnel, material_0; };   // src/renderer/pass/gbuffer.hpp:9-17
+    struct OutputData final { gfx::TextureHandle color; gfx::TextureHandle depth; gfx::TextureHandle velocity; GBufferTextures gbuffer; };
 
     explicit PathTracingPass(bpt_context* ctx) : ctx_(ctx) {}
 
@@ -171,6 +172,9 @@ struct PathTracingPass final {
     // frames accumulated for `camera` so far (the `frame_count` of path_tracing.cpp:239-246,473)
     auto accumulated_frames(gfx::Camera const& camera) const -> uint64_t;
     auto last_status() const -> bpt_status { return status_; }
+    // Content of OutputData.depth / .gbuffer for `camera`'s current frame (the reference writes them in its first trace
+    // pass and "PT Depth", path_tracing.cpp:351-385,421-435; here they are produced on demand by bpt_render_primary).
+    auto read_primary_outputs(gfx::Camera const& camera, BasicRenderer::PathTracingSettings const& settings, float* depth, bpt_gbuffer_texel* gbuffer) -> bpt_status;
 
 private:
     struct CameraHistoryInfo final { uint64_t last_frame; uint64_t frame_count; float4x4 proj_view; uint32_t width; uint32_t height; };

@@ -163,6 +163,14 @@ def test_host_pass_accumulates_like_reference(lib, oracle):
     ref.upload_scene(scene, capi.ACCEL_MERGED)
     ref.render(engine.camera_matrices(scene.camera, W, H), 0, 3, capi.Settings(max_bounces=4))
     np.testing.assert_array_equal(img, ref.resolve(3))
+    # OutputData.depth / .gbuffer of the pass (path_tracing.cpp:482-487) through the host mirror; asking for them must not
+    # disturb the accumulation (the prefetched samples are re-traced)
+    depth, g = r.primary_outputs(max_bounces=4)
+    rdepth, rg = ref.render_primary(engine.camera_matrices(scene.camera, W, H), 3, capi.Settings(max_bounces=4))
+    np.testing.assert_array_equal(depth, rdepth); np.testing.assert_array_equal(g["normal_roughness"], rg["normal_roughness"])
+    assert r.frame(max_bounces=4) == 4
+    ref.render(engine.camera_matrices(scene.camera, W, H), 3, 1, capi.Settings(max_bounces=4))
+    np.testing.assert_array_equal(r.image(4), ref.resolve(4))
     cam2 = dict(scene.camera); cam2["position"] = (0.5, 2.2, 6.5)
     r.set_camera(cam2)
     assert r.frame(max_bounces=4) == 1          # history invalidated by the camera change
