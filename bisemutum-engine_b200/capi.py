@@ -176,6 +176,8 @@ COMMON_API = {
     "trace_ao": [_VP, C.POINTER(Camera), _U32, C.POINTER(AoSettings), _VP, _VP, _VP],
     "trace_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _VP],
     "blend_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _VP, C.POINTER(ProbeBlend), _VP, _VP],
+    "set_ddgi_volume": [_VP, C.POINTER(ProbeVolume), C.POINTER(ProbeBlend), _VP, _VP],
+    "ddgi_lighting": [_VP, _U64, _VP, _VP, _VP, _VP],
 }
 # Exported by the CUDA library only.
 BPT_ONLY_API = {
@@ -369,6 +371,23 @@ class Context:
         table = np.ascontiguousarray(sample_table, dtype=f32)
         assert table.shape == (8192, 2)
         self._call("trace_probes", C.byref(volume), _ptr(table), frame_index, num_bounces, _ptr(out))
+        return out
+
+    def set_ddgi_volume(self, volume: ProbeVolume | None, irradiance=None, visibility=None, irradiance_size=6, visibility_size=14):
+        """Binds the atlases of the previous DDGI update (None unbinds): feedback for trace_probes, input of ddgi_lighting."""
+        if volume is None:
+            self._call("set_ddgi_volume", None, None, None, None)
+            return
+        bl = ProbeBlend(irradiance_size, visibility_size, 0.0, 0)
+        irr = np.ascontiguousarray(irradiance, dtype=f32); vis = np.ascontiguousarray(visibility, dtype=f32)
+        self._call("set_ddgi_volume", C.byref(volume), C.byref(bl), _ptr(irr), _ptr(vis))
+
+    def ddgi_lighting(self, position, normal, view) -> np.ndarray:
+        """calc_ddgi_volume_lighting for n points: (n, 4) float32 = (irradiance rgb, 1) or 0 outside the volume."""
+        p = np.ascontiguousarray(position, dtype=f32); n = np.ascontiguousarray(normal, dtype=f32); v = np.ascontiguousarray(view, dtype=f32)
+        assert p.shape == n.shape == v.shape and p.shape[1] == 3
+        out = np.zeros((len(p), 4), dtype=f32)
+        self._call("ddgi_lighting", len(p), _ptr(p), _ptr(n), _ptr(v), _ptr(out))
         return out
 
     def blend_probes(self, volume: ProbeVolume, sample_table, frame_index, rays, irradiance=None, visibility=None,

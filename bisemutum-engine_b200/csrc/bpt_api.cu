@@ -51,6 +51,8 @@ DScene bpt_context::scene_view() const {
     s.sky_faces = d_sky.as<float4>(); s.sky_size = sky_size;
     memcpy(s.sky_transform, sky_transform, sizeof(sky_transform));
     memcpy(s.sky_color, sky_color, sizeof(sky_color));
+    s.ddgi_enabled = ddgi_enabled ? 1u : 0u; s.ddgi_irr_size = ddgi_irr_size; s.ddgi_vis_size = ddgi_vis_size;
+    s.ddgi_irradiance = d_ddgi_irr.as<float4>(); s.ddgi_visibility = d_ddgi_vis.as<float2>(); s.ddgi_volume = ddgi_volume;
     return s;
 }
 
@@ -83,7 +85,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
-                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
+                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
                       &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims};
     for (DevBuf* b : bufs) dev_free(*b);
     for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
@@ -348,6 +350,26 @@ bpt_status bpt_trace_ao(bpt_context* c, const bpt_camera* cam, uint32_t frame_in
     if (!cam || !ao || !depth || !normal_roughness || !out_ao) return BPT_ERR_INVALID;
     if (!c->accel_built) return fail(c, BPT_ERR_STATE, "trace_ao before build_accel");
     return wavefront_trace_ao(c, *cam, frame_index, *ao, depth, normal_roughness, out_ao);
+}
+
+bpt_status bpt_set_ddgi_volume(bpt_context* c, const bpt_probe_volume* vol, const bpt_probe_blend* bl, const float* irr, const float* vis) {
+    NEED(c);
+    if (!vol || !bl || !irr || !vis) { c->ddgi_enabled = false; return BPT_OK; }        // unbind
+    const uint64_t nx = vol->probe_counts[0], ny = vol->probe_counts[1], nz = vol->probe_counts[2];
+    if (!nx || !ny || !nz || bl->irradiance_size < 2 || bl->visibility_size < 2 || bl->irradiance_size > 30 || bl->visibility_size > 30)
+        return fail(c, BPT_ERR_INVALID, "set_ddgi_volume: bad sizes");
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    bpt_status s;
+    if ((s = dev_upload(c, c->d_ddgi_irr, irr, nx * ny * (bl->irradiance_size + 2) * nz * (bl->irradiance_size + 2) * 16))) return s;
+    if ((s = dev_upload(c, c->d_ddgi_vis, vis, nx * ny * (bl->visibility_size + 2) * nz * (bl->visibility_size + 2) * 8))) return s;
+    c->ddgi_volume = *vol; c->ddgi_irr_size = bl->irradiance_size; c->ddgi_vis_size = bl->visibility_size; c->ddgi_enabled = true;
+    return BPT_OK;
+}
+bpt_status bpt_ddgi_lighting(bpt_context* c, uint64_t n, const float* pos, const float* normal, const float* view, float* out) {
+    NEED(c);
+    if (!pos || !normal || !view || !out) return BPT_ERR_INVALID;
+    if (!c->ddgi_enabled) return fail(c, BPT_ERR_STATE, "ddgi_lighting: no volume bound (bpt_set_ddgi_volume)");
+    return launch_ddgi_lighting(c, n, pos, normal, view, out);
 }
 
 bpt_status bpt_resolve_device(bpt_context* c, uint32_t total, float* d_out) {

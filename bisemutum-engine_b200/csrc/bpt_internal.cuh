@@ -64,6 +64,8 @@ struct bpt_context {
     DevBuf d_instances;          // DInstance[]
     DevBuf d_dir, d_point, d_rect, d_ltc[4];
     DevBuf d_sky; uint32_t sky_size = 0;
+    DevBuf d_ddgi_irr, d_ddgi_vis;      // atlases of the bound DDGI volume (bpt_set_ddgi_volume)
+    bool ddgi_enabled = false; uint32_t ddgi_irr_size = 0, ddgi_vis_size = 0; bpt_probe_volume ddgi_volume{};
     float sky_transform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     float sky_color[3] = {1, 1, 1};
 
@@ -115,6 +117,7 @@ bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count);
 bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_settings& st, float* h_depth, bpt_gbuffer_texel* h_gbuffer);
 bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_ao_settings& ao, const float* h_depth,
                               const float* h_normal_roughness, float* h_out);
+bpt_status launch_ddgi_lighting(bpt_context* ctx, uint64_t n, const float* h_pos, const float* h_normal, const float* h_view, float* h_out);
 bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, uint32_t num_bounces, float* h_out);
 bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, const float* h_rays,
                                const bpt_probe_blend& bl, float* h_irr, float* h_vis);

@@ -57,6 +57,10 @@ struct DScene {
     // sky
     const float4* sky_faces; uint32_t sky_size;
     float sky_transform[9]; float sky_color[3];
+    // DDGI volume of the previous update (bpt_set_ddgi_volume; ddgi_enabled = 0: none): atlases in bpt_blend_probes' layout
+    uint32_t ddgi_enabled, ddgi_irr_size, ddgi_vis_size;
+    const float4* ddgi_irradiance; const float2* ddgi_visibility;
+    bpt_probe_volume ddgi_volume;
 };
 
 BPT_HD float3 xf_point(const float* m, float3 p) {

@@ -10,6 +10,7 @@
 // the reference samples rasterised shadow maps, lights.hlsl:27-159).
 #pragma once
 #include "bpt_ltc.cuh"
+#include "bpt_ddgi.cuh"
 #include "bpt_trace.cuh"
 
 namespace bptd {
@@ -99,6 +100,13 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
         if (!(step >= 0.0001f)) { sink.add(c); continue; }
         float dist = fabsf(dot3(P - v3(rl.position2[0], rl.position2[1], rl.position2[2]), ln));
         sink.shadow(P, mrp, (dist / step) * 0.999f, c, sc.num_dir + sc.num_point + l);
+    }
+    // Probe paths only: the previous DDGI update lights the path's last vertex (ddgi/deferred_lighting.hlsl:102-115:
+    // color += ddgi.xyz / ddgi.a * base_color / pi). The reference traces one bounce, so every probe-ray hit gets it; with
+    // more bounces (BASELINE configs[4]) it closes the path instead of being added at every vertex.
+    if (sp.diffuse_only && sc.ddgi_enabled && bounce + 1 >= sp.max_bounces) {
+        float4 g = ddgi_volume_lighting(sc.ddgi_volume, sc.ddgi_irr_size, sc.ddgi_vis_size, sc.ddgi_irradiance, sc.ddgi_visibility, P, N, V);
+        if (g.w > 0.0f) sink.add(((v3(g.x / g.w, g.y / g.w, g.z / g.w) * surf.base_color) * kInvPi) * Wl);
     }
     for (uint32_t l = 0; l < sc.num_dir; l++) {                         // :51-60
         const bpt_dir_light_data& li = sc.dir_lights[l];

@@ -446,6 +446,16 @@ __global__ void k_ao_finish(const float4* __restrict__ color, uint32_t n, float 
     out[p] = c.w != 0.0f ? make_float2(q_half(ao_value(4u - (uint32_t)c.x, strength)), 1.0f) : make_float2(1.0f, 0.0f);
 }
 
+// ---- DDGI consumer for arbitrary points (calc_ddgi_volume_lighting as the deferred lighting passes call it) ----
+__global__ void k_ddgi_lighting(const __grid_constant__ DScene sc, uint64_t n, const float* __restrict__ pos, const float* __restrict__ normal,
+                                const float* __restrict__ view, float4* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = ddgi_volume_lighting(sc.ddgi_volume, sc.ddgi_irr_size, sc.ddgi_vis_size, sc.ddgi_irradiance, sc.ddgi_visibility,
+                                  v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), v3(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]),
+                                  v3(view[3 * i], view[3 * i + 1], view[3 * i + 2]));
+}
+
 // ---- DDGI probe blending: one block per probe, one thread per octahedral texel --------------------
 template <bool VIS>
 __global__ void k_probe_blend(const __grid_constant__ bpt_probe_volume vol, const float2* __restrict__ table, uint32_t frame_index,
@@ -848,6 +858,23 @@ bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     dev_free(rays); dev_free(out);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}
+
+bpt_status launch_ddgi_lighting(bpt_context* ctx, uint64_t n, const float* h_pos, const float* h_normal, const float* h_view, float* h_out) {
+    if (n == 0) return BPT_OK;
+    DevBuf pos, nrm, view, out;
+    auto cleanup = [&]() { dev_free(pos); dev_free(nrm); dev_free(view); dev_free(out); };
+    bpt_status s;
+    if ((s = dev_upload(ctx, pos, h_pos, n * 12)) || (s = dev_upload(ctx, nrm, h_normal, n * 12)) || (s = dev_upload(ctx, view, h_view, n * 12)) ||
+        (s = dev_alloc(ctx, out, n * 16))) { cleanup(); return s; }
+    k_ddgi_lighting<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene_view(), n, pos.as<float>(), nrm.as<float>(), view.as<float>(), out.as<float4>());
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, out.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) { ctx->err = std::string("ddgi_lighting: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
     return BPT_OK;
 }
 

@@ -445,6 +445,19 @@ BPT_API bpt_status bpt_blend_probes(
     const float* ray_radiance_dist /* output of bpt_trace_probes */, const bpt_probe_blend* blend,
     float* irradiance_atlas_rgba32f, float* visibility_atlas_rg32f);
 
+/* The consumer of the atlases: calc_ddgi_volume_lighting (ddgi/ddgi_lighting.hlsl:7-83) — 8-probe trilinear weights x
+ * wrap-shading weight x Chebyshev visibility^3, generalised from the reference's 8x8x8 probes to the volume's own counts.
+ * bpt_set_ddgi_volume binds one volume and its atlases (layout of bpt_blend_probes; copied to the device; all-NULL
+ * unbinds). While bound, bpt_trace_probes adds the previous update's irradiance at the last vertex of every probe path
+ * (ddgi/deferred_lighting.hlsl:102-115), which is how the reference's one-bounce probes converge to multi-bounce GI. */
+BPT_API bpt_status bpt_set_ddgi_volume(
+    bpt_context* ctx, const bpt_probe_volume* volume, const bpt_probe_blend* sizes,
+    const float* irradiance_atlas_rgba32f, const float* visibility_atlas_rg32f);
+/* out[i] = calc_ddgi_volume_lighting(position[i], normal[i], view[i]) for the bound volume: (irradiance rgb, 1) or 0
+ * outside the volume. position/normal/view: n x float3. Synchronous. */
+BPT_API bpt_status bpt_ddgi_lighting(
+    bpt_context* ctx, uint64_t n, const float* position, const float* normal, const float* view, float* out_rgba);
+
 #ifdef __cplusplus
 }
 #endif

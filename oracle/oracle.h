@@ -71,6 +71,10 @@ BPT_API bpt_status obpt_debug_capture(obpt_context* ctx, uint32_t enable);
 BPT_API bpt_status obpt_debug_read_queue(
     obpt_context* ctx, uint32_t bounce, uint32_t kind,
     uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t capacity, uint64_t* count);
+/* calc_ddgi_volume_lighting (ddgi/ddgi_lighting.hlsl:7-83) and the previous-update feedback of the probe lighting pass. */
+BPT_API bpt_status obpt_set_ddgi_volume(obpt_context* ctx, const bpt_probe_volume* volume, const bpt_probe_blend* sizes,
+                                        const float* irradiance_atlas, const float* visibility_atlas);
+BPT_API bpt_status obpt_ddgi_lighting(obpt_context* ctx, uint64_t n, const float* position, const float* normal, const float* view, float* out_rgba);
 /* OutputData{depth, gbuffer} of PathTracingPass::render (path_tracing.cpp:482-487) and AmbientOcclusionPass::render_raytraced. */
 BPT_API bpt_status obpt_render_primary(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_settings* settings,
                                        float* out_depth, bpt_gbuffer_texel* out_gbuffer);

@@ -230,6 +230,73 @@ static inline void camera_ray(const bpt_camera& cam, uint32_t px, uint32_t py, u
     O = mk3(iv[12], iv[13], iv[14]);
 }
 
+// ---- calc_ddgi_volume_lighting: shaders/renderer/ddgi/ddgi_lighting.hlsl:7-83, one volume ---------------------------
+// Generalised from DDGI_PROBES_SIZE = 8 / 6 / 14 (ddgi_struct.hlsl:3-12) to the bound volume's probe counts and atlas sizes.
+// Texture2DArray.SampleLevel with the linear sampler (ddgi.cpp:14-17) = explicit FP32 bilinear inside the probe's tile.
+static inline f2 oct_encode_01(f3 n) { f2 e = oct_encode(n); return f2{e.x * 0.5f + 0.5f, e.y * 0.5f + 0.5f}; }   // pack.hlsl:96-98
+template <int CH>
+static inline void atlas_bilinear(const float* atlas, size_t row_stride_texels, size_t tile_x0, size_t tile_y0, float cx, float cy, float out[CH]) {
+    float tx = cx - 0.5f, ty = cy - 0.5f;
+    float x0f = floorf(tx), y0f = floorf(ty);
+    float fx = tx - x0f, fy = ty - y0f;
+    size_t x0 = tile_x0 + (size_t)(int)x0f, y0 = tile_y0 + (size_t)(int)y0f;
+    const float* p00 = atlas + (y0 * row_stride_texels + x0) * CH;
+    const float* p10 = p00 + CH;
+    const float* p01 = atlas + ((y0 + 1) * row_stride_texels + x0) * CH;
+    const float* p11 = p01 + CH;
+    for (int k = 0; k < CH; k++) out[k] = lerpf(lerpf(p00[k], p10[k], fx), lerpf(p01[k], p11[k], fx), fy);
+}
+static f4 calc_ddgi_volume_lighting(const obpt_context& ctx, f3 pos, f3 normal, f3 view) {
+    const bpt_probe_volume& vol = ctx.ddgi_volume;
+    const uint32_t IS = ctx.ddgi_irr_size, VS = ctx.ddgi_vis_size;
+    pos = (pos + normal * 0.2f) + view * 0.8f;                                               // :16
+    f3 base = mk3(vol.base_position[0], vol.base_position[1], vol.base_position[2]);
+    f3 fx = mk3(vol.frame_x[0], vol.frame_x[1], vol.frame_x[2]), fy = mk3(vol.frame_y[0], vol.frame_y[1], vol.frame_y[2]), fz = mk3(vol.frame_z[0], vol.frame_z[1], vol.frame_z[2]);
+    f3 vec = pos - base;
+    float x = dot(vec, fx), y = dot(vec, fy), z = dot(vec, fz);                              // :18-21
+    if (x < 0.0f || x > vol.extent[0] || y < 0.0f || y > vol.extent[1] || z < 0.0f || z > vol.extent[2]) return f4{0, 0, 0, 0};   // :22-28
+    const uint32_t n[3] = {vol.probe_counts[0], vol.probe_counts[1], vol.probe_counts[2]};
+    const float m1[3] = {(float)(n[0] > 1 ? n[0] - 1 : 1), (float)(n[1] > 1 ? n[1] - 1 : 1), (float)(n[2] > 1 ? n[2] - 1 : 1)};   // DDGI_PROBES_SIZE_M_1
+    f2 oct_norm = oct_encode_01(normal);                                                     // :30
+    // probe uv (oct * SIZE + 1) / (SIZE + 2) of a (SIZE + 2)-texel tile, in texels of that tile (:31-32)
+    float icx = oct_norm.x * (float)IS + 1.0f, icy = oct_norm.y * (float)IS + 1.0f;
+    float vcx = oct_norm.x * (float)VS + 1.0f, vcy = oct_norm.y * (float)VS + 1.0f;
+    float idx_f[3] = {vol.extent[0] > 0.0f ? x * m1[0] / vol.extent[0] : 0.0f, vol.extent[1] > 0.0f ? y * m1[1] / vol.extent[1] : 0.0f,
+                      vol.extent[2] > 0.0f ? z * m1[2] / vol.extent[2] : 0.0f};              // :34-38
+    uint32_t idx[3];
+    for (int a = 0; a < 3; a++) {                                                            // :39-40
+        uint32_t cap = n[a] > 1 ? n[a] - 2 : 0;
+        idx[a] = std::min(to_uint(idx_f[a]), cap);
+        idx_f[a] = idx_f[a] - (float)idx[a];
+    }
+    const size_t istride = (size_t)n[0] * n[1] * (IS + 2), vstride = (size_t)n[0] * n[1] * (VS + 2);
+    f3 sum = splat3(0.0f);
+    float sum_weight = 0.0f;
+    for (uint32_t i = 0; i < 8; i++) {                                                       // :44-79
+        uint32_t d[3] = {i & 1u, (i >> 1) & 1u, i >> 2};
+        float w_probe = (lerpf(1.0f - idx_f[0], idx_f[0], (float)d[0]) * lerpf(1.0f - idx_f[1], idx_f[1], (float)d[1])) * lerpf(1.0f - idx_f[2], idx_f[2], (float)d[2]);
+        uint32_t pi[3];
+        for (int a = 0; a < 3; a++) pi[a] = std::min(idx[a] + d[a], n[a] - 1);
+        f3 probe_center = ((base + ((float)pi[0] * vol.extent[0] / m1[0]) * fx) + ((float)pi[1] * vol.extent[1] / m1[1]) * fy) + ((float)pi[2] * vol.extent[2] / m1[2]) * fz;
+        f3 to_probe = probe_center - pos;
+        f3 dir = normalize(to_probe);
+        float w_dir = pow2((dot(dir, normal) + 1.0f) * 0.5f) + 0.2f;                         // :57
+        size_t tile = (size_t)pi[1] * n[0] + pi[0];                                          // probe_start.x (:59)
+        float visibility[2], irradiance[4];
+        atlas_bilinear<2>(ctx.ddgi_visibility.data(), vstride, tile * (VS + 2), (size_t)pi[2] * (VS + 2), vcx, vcy, visibility);
+        float sigma2 = visibility[1] - pow2(visibility[0]);                                  // :66
+        float dist = sqrtf(dot(to_probe, to_probe));
+        float w_vis = sigma2 / (sigma2 + pow2(fmax_(dist - visibility[0], 0.0f)));           // :68
+        atlas_bilinear<4>(ctx.ddgi_irradiance.data(), istride, tile * (IS + 2), (size_t)pi[2] * (IS + 2), icx, icy, irradiance);
+        float w = (w_probe * w_dir) * ((w_vis * w_vis) * w_vis);                             // :75
+        sum = sum + mk3(irradiance[0], irradiance[1], irradiance[2]) * w;
+        sum_weight += w;
+    }
+    f4 r = sum_weight == 0.0f ? f4{0, 0, 0, 1} : f4{sum.x / sum_weight, sum.y / sum_weight, sum.z / sum_weight, 1.0f};   // :81
+    if (!finite3(mk3(r.x, r.y, r.z))) r = f4{0, 0, 0, 0};                                    // :82
+    return r;
+}
+
 struct ThreadOut {
     TraceStats ext, shd;
     uint64_t ext_per_bounce[16] = {0}, shd_per_bounce[16] = {0};
@@ -344,6 +411,12 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             uint32_t light_index = (uint32_t)(sc.dir_lights.size() + sc.point_lights.size() + l);
             if (ctx.capture) out.cap_s.push_back({i, pixel, light_index});
             if (!trace_any(sc, P, mrp, 0.001f, (dist / step) * 0.999f, frame_index, out.shd)) out.pending.push_back(c);
+        }
+        // Probe paths: the previous DDGI update at the path's last vertex (ddgi/deferred_lighting.hlsl:102-115). The reference
+        // traces one bounce, so every probe-ray hit receives it; with more bounces it closes the path.
+        if (diffuse_only && ctx.ddgi_enabled && i + 1 >= B) {
+            f4 g = calc_ddgi_volume_lighting(ctx, P, N, V);
+            if (g.w > 0.0f) add(((mk3(g.x / g.w, g.y / g.w, g.z / g.w) * surf.base_color) * INV_PI) * Wl);
         }
         for (size_t l = 0; l < sc.dir_lights.size(); l++) {                                 // deferred_lighting_secondary.hlsl:51-60
             const bpt_dir_light_data& li = sc.dir_lights[l];
@@ -683,6 +756,28 @@ bpt_status obpt_debug_read_queue(obpt_context* c, uint32_t bounce, uint32_t kind
     if (kind == 1 && lights) std::copy(c->cap_shadow_lights[bounce].begin(), c->cap_shadow_lights[bounce].end(), lights);
     return BPT_OK;
 }
+bpt_status obpt_set_ddgi_volume(obpt_context* c, const bpt_probe_volume* vol, const bpt_probe_blend* bl, const float* irr, const float* vis) {
+    CHECK_CTX(c);
+    if (!vol || !bl || !irr || !vis) { c->ddgi_enabled = false; return BPT_OK; }
+    const uint64_t nx = vol->probe_counts[0], ny = vol->probe_counts[1], nz = vol->probe_counts[2];
+    if (!nx || !ny || !nz || bl->irradiance_size < 2 || bl->visibility_size < 2 || bl->irradiance_size > 30 || bl->visibility_size > 30)
+        return fail(c, BPT_ERR_INVALID, "set_ddgi_volume: bad sizes");
+    c->ddgi_irradiance.assign(irr, irr + nx * ny * (bl->irradiance_size + 2) * nz * (bl->irradiance_size + 2) * 4);
+    c->ddgi_visibility.assign(vis, vis + nx * ny * (bl->visibility_size + 2) * nz * (bl->visibility_size + 2) * 2);
+    c->ddgi_volume = *vol; c->ddgi_irr_size = bl->irradiance_size; c->ddgi_vis_size = bl->visibility_size; c->ddgi_enabled = true;
+    return BPT_OK;
+}
+bpt_status obpt_ddgi_lighting(obpt_context* c, uint64_t n, const float* pos, const float* normal, const float* view, float* out) {
+    CHECK_CTX(c); if (!pos || !normal || !view || !out) return BPT_ERR_INVALID;
+    if (!c->ddgi_enabled) return fail(c, BPT_ERR_STATE, "ddgi_lighting: no volume bound (obpt_set_ddgi_volume)");
+    for (uint64_t i = 0; i < n; i++) {
+        f4 r = calc_ddgi_volume_lighting(*c, mk3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]), mk3(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]),
+                                         mk3(view[3 * i], view[3 * i + 1], view[3 * i + 2]));
+        out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    }
+    return BPT_OK;
+}
+
 // Primary-hit outputs of the pass: the first trace pass's G-buffer (rt_gbuffer_hit.hlsl:6-18 packed by gbuffer.hlsl:18-33 into the
 // formats of pass/gbuffer.hpp:14-17) and the depth pass (pt_depth.hlsl:7-16). Texels of missing rays: 0 (the reference leaves them untouched).
 bpt_status obpt_render_primary(obpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_settings* st, float* out_depth, bpt_gbuffer_texel* out_g) {

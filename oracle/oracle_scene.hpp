@@ -105,6 +105,9 @@ struct obpt_context {
     uint32_t threads = 0;
     uint32_t tile_stride = 1, tile_offset = 0;
     std::string err;
+    // DDGI volume of the previous update (obpt_set_ddgi_volume): atlases in obpt_blend_probes' layout
+    bool ddgi_enabled = false; uint32_t ddgi_irr_size = 0, ddgi_vis_size = 0; bpt_probe_volume ddgi_volume{};
+    std::vector<float> ddgi_irradiance, ddgi_visibility;
     std::vector<float> accum;        // W*H*4 FP32 sums (reference_fp16: the running half-valued average)
     bool accum_used = false, accum_fp16 = false;   // accumulation rule in force since the last clear
     uint32_t accum_count = 0;        // reference_fp16: samples already folded in (pt_accumulate weight 1/(count+1))

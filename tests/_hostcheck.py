@@ -59,6 +59,8 @@ def lib():
         _lib.hc_trace_ao.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.AoSettings), C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_trace_probes.argtypes = [C.POINTER(HcScene), C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.hc_blend_probes.argtypes = [C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(capi.ProbeBlend), C.c_void_p, C.c_void_p]
+        _lib.hc_set_ddgi.argtypes = [C.POINTER(capi.ProbeVolume), C.POINTER(capi.ProbeBlend), C.c_void_p, C.c_void_p]
+        _lib.hc_ddgi_lighting.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -139,6 +141,23 @@ class HostScene:
         out = np.zeros((n, 4), np.float32)
         lib().hc_trace_probes(C.byref(self.h), C.byref(volume), table.ctypes.data_as(C.c_void_p), frame_index, num_bounces, out.ctypes.data_as(C.c_void_p))
         return out
+
+
+def set_ddgi(volume, irr=None, vis=None, irradiance_size=6, visibility_size=14):
+    """Binds (or, with volume None, unbinds) the DDGI volume the host build's probe paths and ddgi_lighting read."""
+    if volume is None:
+        lib().hc_set_ddgi(None, None, None, None)
+        return
+    bl = capi.ProbeBlend(irradiance_size, visibility_size, 0.0, 0)
+    irr = np.ascontiguousarray(irr, np.float32); vis = np.ascontiguousarray(vis, np.float32)
+    lib().hc_set_ddgi(C.byref(volume), C.byref(bl), irr.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p))
+
+
+def ddgi_lighting(position, normal, view):
+    p = np.ascontiguousarray(position, np.float32); n = np.ascontiguousarray(normal, np.float32); v = np.ascontiguousarray(view, np.float32)
+    out = np.zeros((len(p), 4), np.float32)
+    lib().hc_ddgi_lighting(len(p), p.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def blend_probes(volume, table, frame_index, rays, irr, vis, irradiance_size=6, visibility_size=14, alpha=0.97, history_valid=0):

@@ -39,6 +39,8 @@ struct hc_scene {
 };
 
 namespace {
+// DDGI volume bound by hc_set_ddgi (the host-check counterpart of bpt_set_ddgi_volume); applied by build()
+struct { bool enabled = false; bpt_probe_volume vol{}; uint32_t irr_size = 0, vis_size = 0; std::vector<float> irr, vis; } g_ddgi;
 struct Built {
     std::vector<DInstance> inst;
     std::vector<std::vector<float4>> tris;
@@ -124,6 +126,8 @@ void build(const hc_scene& h, Built& b) {
     s.ltc_m0 = h.ltc_m0; s.ltc_m1 = h.ltc_m1; s.ltc_m2 = h.ltc_m2; s.ltc_norm = h.ltc_norm;
     s.sky_faces = reinterpret_cast<const float4*>(h.sky_faces); s.sky_size = h.sky_size;
     memcpy(s.sky_transform, h.sky_transform, 36); memcpy(s.sky_color, h.sky_color, 12);
+    s.ddgi_enabled = g_ddgi.enabled ? 1u : 0u; s.ddgi_irr_size = g_ddgi.irr_size; s.ddgi_vis_size = g_ddgi.vis_size; s.ddgi_volume = g_ddgi.vol;
+    s.ddgi_irradiance = reinterpret_cast<const float4*>(g_ddgi.irr.data()); s.ddgi_visibility = reinterpret_cast<const float2*>(g_ddgi.vis.data());
 }
 
 struct HostSink {
@@ -292,6 +296,24 @@ int hc_blend_probes(const bpt_probe_volume* vol, const float* table, uint32_t fr
     return 0;
 }
 
+__attribute__((visibility("default")))
+void hc_set_ddgi(const bpt_probe_volume* vol, const bpt_probe_blend* bl, const float* irr, const float* vis) {
+    g_ddgi.enabled = vol && bl && irr && vis;
+    if (!g_ddgi.enabled) return;
+    const size_t nx = vol->probe_counts[0], ny = vol->probe_counts[1], nz = vol->probe_counts[2];
+    g_ddgi.vol = *vol; g_ddgi.irr_size = bl->irradiance_size; g_ddgi.vis_size = bl->visibility_size;
+    g_ddgi.irr.assign(irr, irr + nx * ny * (bl->irradiance_size + 2) * nz * (bl->irradiance_size + 2) * 4);
+    g_ddgi.vis.assign(vis, vis + nx * ny * (bl->visibility_size + 2) * nz * (bl->visibility_size + 2) * 2);
+}
+__attribute__((visibility("default")))
+void hc_ddgi_lighting(uint64_t n, const float* pos, const float* normal, const float* view, float* out) {
+    for (uint64_t i = 0; i < n; i++) {
+        float4 r = ddgi_volume_lighting(g_ddgi.vol, g_ddgi.irr_size, g_ddgi.vis_size, reinterpret_cast<const float4*>(g_ddgi.irr.data()),
+                                        reinterpret_cast<const float2*>(g_ddgi.vis.data()), v3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]),
+                                        v3(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]), v3(view[3 * i], view[3 * i + 1], view[3 * i + 2]));
+        out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    }
+}
 __attribute__((visibility("default"))) float hc_q_half(float f) { return q_half(f); }
 __attribute__((visibility("default"))) void hc_surface_through_gbuffer(const float N[3], const float T[3], const float in[12], uint32_t model, float out[18], uint32_t* model_out) {
     Surface s = surface_default();

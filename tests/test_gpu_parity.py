@@ -361,6 +361,39 @@ def test_primary_outputs_and_rtao(lib, oracle, mode):
     np.testing.assert_array_equal(gpu.resolve(2), ref.resolve(2))
 
 
+def test_ddgi_volume_lighting_and_feedback(lib, oracle):
+    """bpt_set_ddgi_volume / bpt_ddgi_lighting (calc_ddgi_volume_lighting) and the previous-update feedback inside
+    bpt_trace_probes: a two-update DDGI loop (trace -> blend -> bind -> trace with feedback -> blend) matches the oracle bit for bit."""
+    scene = scenes.small_test_scene()
+    table = scenes.ddgi_sample_randoms()
+    vol = scenes.probe_volume(scene, (6, 4, 4), 128, ray_length=100.0)
+    gpu, ref = make_pair(lib, oracle, scene, 16, 16, capi.ACCEL_MERGED)
+    r0g, r0r = gpu.trace_probes(vol, table, 0, 1), ref.trace_probes(vol, table, 0, 1)
+    np.testing.assert_array_equal(r0g, r0r)
+    irr_g, vis_g = gpu.blend_probes(vol, table, 0, r0g); irr_r, vis_r = ref.blend_probes(vol, table, 0, r0r)
+    np.testing.assert_array_equal(irr_g, irr_r); np.testing.assert_array_equal(vis_g, vis_r)
+    gpu.set_ddgi_volume(vol, irr_g, vis_g); ref.set_ddgi_volume(vol, irr_r, vis_r)
+    rng = np.random.default_rng(9)
+    lo = np.float32(vol.base_position[:]); ext = np.float32(vol.extent[:])
+    n = 20000
+    pos = (lo + rng.uniform(-0.1, 1.1, (n, 3)) * ext).astype(np.float32)
+    nrm = rng.normal(size=(n, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    view = rng.normal(size=(n, 3)); view = (view / np.linalg.norm(view, axis=1, keepdims=True)).astype(np.float32)
+    a, b = gpu.ddgi_lighting(pos, nrm, view), ref.ddgi_lighting(pos, nrm, view)
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert (a[:, 3] == 1).mean() > 0.3 and a[:, :3].max() > 0
+    for bounces in (1, 3):
+        r1g, r1r = gpu.trace_probes(vol, table, 1, bounces), ref.trace_probes(vol, table, 1, bounces)
+        np.testing.assert_array_equal(r1g.view(np.uint32), r1r.view(np.uint32))
+    assert (r1g[:, :3] >= 0).all()
+    irr1_g, _ = gpu.blend_probes(vol, table, 1, r1g, irr_g, vis_g); irr1_r, _ = ref.blend_probes(vol, table, 1, r1r, irr_r, vis_r)
+    np.testing.assert_array_equal(irr1_g, irr1_r)
+    gpu.set_ddgi_volume(None); ref.set_ddgi_volume(None)
+    np.testing.assert_array_equal(gpu.trace_probes(vol, table, 1, 1), ref.trace_probes(vol, table, 1, 1))
+    with pytest.raises(capi.BptError):
+        gpu.ddgi_lighting(pos[:4], nrm[:4], view[:4])                                        # nothing bound
+
+
 def test_reference_fp16_host_pass(lib, oracle):
     """The frame-at-a-time host pass (render_ahead / accumulate_ahead) follows the same running lerp."""
     scene = scenes.small_test_scene()

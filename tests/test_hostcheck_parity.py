@@ -282,6 +282,53 @@ def test_probe_blending_bit_exact(oracle):
     np.testing.assert_allclose(irr_flat[..., :3], np.broadcast_to(np.float32([0.25, 0.5, 1.0]), irr_flat[..., :3].shape), rtol=2e-6)
 
 
+def test_ddgi_volume_lighting_and_feedback_bit_exact(oracle):
+    """The consumer of the probe atlases, calc_ddgi_volume_lighting (ddgi_lighting.hlsl:7-83), and the previous-update
+    feedback of the probe lighting pass (ddgi/deferred_lighting.hlsl:102-115): CUDA source (host build) == oracle, and the
+    properties the formula implies (constant atlas -> that constant; outside the volume -> 0; feedback only adds light)."""
+    scene = _scene("small")
+    table = scenes.ddgi_sample_randoms()
+    vol = scenes.probe_volume(scene, (4, 3, 3), 64, ray_length=100.0)
+    ctx = oracle.OracleContext(8, 8); ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    rays0 = ctx.trace_probes(vol, table, 0, 1)                                             # the reference's one bounce, no history yet
+    irr0, vis0 = ctx.blend_probes(vol, table, 0, rays0)
+    ctx.set_ddgi_volume(vol, irr0, vis0); HC.set_ddgi(vol, irr0, vis0)
+    rng = np.random.default_rng(3)
+    lo = np.float32(vol.base_position[:]); ext = np.float32(vol.extent[:])
+    n = 600
+    pos = (lo + rng.uniform(-0.15, 1.15, (n, 3)) * ext).astype(np.float32)                 # some outside
+    nrm = rng.normal(size=(n, 3)); nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    view = rng.normal(size=(n, 3)); view = (view / np.linalg.norm(view, axis=1, keepdims=True)).astype(np.float32)
+    a, b = ctx.ddgi_lighting(pos, nrm, view), HC.ddgi_lighting(pos, nrm, view)
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    moved = pos + nrm * np.float32(0.2) + view * np.float32(0.8)
+    inside = ((moved >= lo) & (moved <= lo + ext)).all(axis=1)
+    margin = (np.abs(moved - lo) > 1e-4).all(axis=1) & (np.abs(moved - lo - ext) > 1e-4).all(axis=1)
+    assert (a[~inside & margin] == 0).all() and (a[inside & margin][:, 3] <= 1).all() and inside.sum() > 50
+    assert np.isfinite(a).all() and (a[..., :3] >= 0).all() and a[inside & margin][:, :3].max() > 0
+    # constant atlases: every probe says (0.25, 0.5, 1.0) and visibility (mean 50, mean-square 2600) -> that colour back
+    irr_c = np.zeros_like(irr0); irr_c[..., :3] = (0.25, 0.5, 1.0); irr_c[..., 3] = 1
+    vis_c = np.zeros_like(vis0); vis_c[..., 0] = 50.0; vis_c[..., 1] = 2600.0
+    ctx.set_ddgi_volume(vol, irr_c, vis_c)
+    c = ctx.ddgi_lighting(pos, nrm, view)
+    ok = inside & margin & (c[:, 3] == 1)
+    np.testing.assert_allclose(c[ok][:, :3], np.broadcast_to(np.float32([0.25, 0.5, 1.0]), c[ok][:, :3].shape), rtol=3e-6)
+    # feedback: probe paths with the previous update bound == host build, and never darker than without it
+    ctx.set_ddgi_volume(vol, irr0, vis0)
+    for bounces in (1, 2):
+        fb = ctx.trace_probes(vol, table, 1, bounces)
+        np.testing.assert_array_equal(fb.view(np.uint32), HC.HostScene(scene, ctx, capi.ACCEL_MERGED).trace_probes(vol, table, 1, bounces).view(np.uint32))
+        ctx.set_ddgi_volume(None); HC.set_ddgi(None)
+        plain = ctx.trace_probes(vol, table, 1, bounces)
+        np.testing.assert_array_equal(plain.view(np.uint32), HC.HostScene(scene, ctx, capi.ACCEL_MERGED).trace_probes(vol, table, 1, bounces).view(np.uint32))
+        assert (fb[:, :3] >= plain[:, :3]).all() and (fb[:, :3] > plain[:, :3]).any()
+        np.testing.assert_array_equal(fb[:, 3], plain[:, 3])                                # hit distances unchanged
+        ctx.set_ddgi_volume(vol, irr0, vis0); HC.set_ddgi(vol, irr0, vis0)
+    HC.set_ddgi(None)
+    with pytest.raises(capi.BptError):
+        oracle.OracleContext(8, 8).ddgi_lighting(pos, nrm, view)                             # nothing bound
+
+
 @pytest.mark.parametrize("mode", MODES)
 def test_reference_example_scene_bit_exact(oracle, mode):
     """examples/scene_basic of the reference (its meshes, its five materials incl. sRGB / normal-map textures,
