@@ -163,6 +163,7 @@ COMMON_API = {
     "build_accel": [_VP, _U32],
     "update_tlas": [_VP],
     "debug_read_bvh": [_VP, _U32, _PU32, _VP, _VP, _VP, _U32, C.POINTER(C.c_int32)],
+    "debug_read_wide": [_VP, _VP, _VP, _U32],
     "clear_accum": [_VP],
     "render": [_VP, C.POINTER(Camera), _U32, _U32, C.POINTER(Settings)],
     "resolve": [_VP, _U32, _VP],
@@ -306,6 +307,13 @@ class Context:
         return {"n": n.value, "root": root.value, "morton": morton, "prims": prims, "nodes": nodes}
 
     # -- render ---------------------------------------------------------------------------------
+    def read_wide(self):
+        """Merged mode: the 4-wide quantised nodes ((n-1, 16) uint32, raw bits of the 64-B records) and the exact leaf boxes ((n, 8) float32)."""
+        n = self.read_bvh(0)["n"]
+        wide = np.zeros((max(n - 1, 0), 16), dtype=np.uint32); leafbox = np.zeros((n, 8), dtype=f32)
+        self._call("debug_read_wide", _ptr(wide), _ptr(leafbox), n)
+        return wide, leafbox
+
     def clear_accum(self):
         self._call("clear_accum")
 

@@ -90,7 +90,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     for (DevBuf* b : bufs) dev_free(*b);
     for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
     for (auto& t : c->d_texels) dev_free(t);
-    for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); }
+    for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
     delete c;
     return BPT_OK;
 }
@@ -251,7 +251,7 @@ bpt_status bpt_build_accel(bpt_context* c, uint32_t mode) {
     c->accel_built = false;
     c->accel_mode = mode;
     if ((s = upload_instance_table(c))) return s;
-    for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); }
+    for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
     if (mode == BPT_ACCEL_TWO_LEVEL) {
         c->blas.assign(c->h_blas_desc.size(), DevBvh{});
         for (uint32_t b = 0; b < c->blas.size(); b++)
@@ -290,6 +290,18 @@ bpt_status bpt_debug_read_bvh(bpt_context* c, uint32_t which, uint32_t* np, uint
     if (morton) BPT_CUDA_TRY(c, cudaMemcpy(morton, b->morton.p, (size_t)b->n * 8, cudaMemcpyDeviceToHost));
     if (prims) BPT_CUDA_TRY(c, cudaMemcpy(prims, b->prims.p, (size_t)b->n * 4, cudaMemcpyDeviceToHost));
     if (nodes && b->n >= 2) BPT_CUDA_TRY(c, cudaMemcpy(nodes, b->nodes.p, (size_t)(b->n - 1) * 64, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+
+bpt_status bpt_debug_read_wide(bpt_context* c, float* wide, float* leafbox, uint32_t cap) {
+    NEED(c);
+    if (!c->accel_built || c->accel_mode != BPT_ACCEL_MERGED) return fail(c, BPT_ERR_STATE, "debug_read_wide: needs a built merged accel");
+    const DevBvh& b = c->blas[0];
+    if (cap < b.n) return fail(c, BPT_ERR_INVALID, "capacity too small");
+    if (b.n < 2) return BPT_OK;
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (wide) BPT_CUDA_TRY(c, cudaMemcpy(wide, b.wide.p, (size_t)(b.n - 1) * 64, cudaMemcpyDeviceToHost));
+    if (leafbox) BPT_CUDA_TRY(c, cudaMemcpy(leafbox, b.leafbox.p, (size_t)b.n * 32, cudaMemcpyDeviceToHost));
     return BPT_OK;
 }
 

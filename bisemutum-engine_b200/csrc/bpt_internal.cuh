@@ -17,6 +17,8 @@ struct DevBvh {
     int32_t root = 0;
     DevBuf nodes;      // float4[4*(n-1)]
     DevBuf tris;       // float4[3*n] (BLAS only)
+    DevBuf wide;       // float4[4*(n-1)]: 4-wide quantised nodes (merged BLAS only, bpt_wide.cuh); node i = subtree of binary node i
+    DevBuf leafbox;    // float4[2*n]: exact box of every leaf (merged BLAS only)
     DevBuf morton;     // uint64[n] sorted
     DevBuf prims;      // uint32[n] sorted primitive ids
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -27,7 +29,7 @@ struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through 
     uint32_t npx = 0, slots = 1;
     DevBuf color;           // float4 per path: per-sample colour C_s
     uint32_t ahead_slots = 0, ahead_cursor = 0, ahead_frame_first = 0;   // prefetched samples still in `color`
-    unsigned grid_extend = 0, grid_connect = 0, grid_extend_m = 0, grid_connect_m = 0;   // resident grid sizes of the persistent traversal kernels
+    unsigned grid_extend = 0, grid_connect = 0, grid_extend_m = 0, grid_connect_m = 0, grid_extend_w = 0, grid_connect_w = 0;   // resident grid sizes of the persistent traversal kernels
     DevBuf ray_o[2], ray_d[2], ray_w[2];   // float4 each: (O|pixel), (D|-), (W|-)
     DevBuf hit;             // float4 (t,u,v,prim)
     DevBuf hit_slot;        // uint32

@@ -61,8 +61,15 @@ BPT_HD bool anyhit_keep(const DScene& sc, RayState& rs, uint32_t slot, uint32_t 
 
 // Möller–Trumbore on the (v0, e1, e2) record; unfused arithmetic (see bpt_math.cuh header).
 template <bool ANY>
+BPT_HD bool test_triangle_rec(const DScene& sc, RayState& rs, float4 a, float4 b, float4 c, float3 O, float3 D, uint32_t slot_or_none, uint32_t instance_anyhit);
+template <bool ANY>
 BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, float3 O, float3 D, uint32_t slot_or_none, uint32_t instance_anyhit) {
     float4 a = BPT_LDG(tri), b = BPT_LDG(tri + 1), c = BPT_LDG(tri + 2);
+    return test_triangle_rec<ANY>(sc, rs, a, b, c, O, D, slot_or_none, instance_anyhit);
+}
+// the same test on an already fetched (v0 | prim), (e1 | slot), (e2 | any-hit flag) record
+template <bool ANY>
+BPT_HD bool test_triangle_rec(const DScene& sc, RayState& rs, float4 a, float4 b, float4 c, float3 O, float3 D, uint32_t slot_or_none, uint32_t instance_anyhit) {
     float3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
     float3 pvec = cross3(D, e2);
     float det = dot3(e1, pvec);

@@ -10,6 +10,7 @@
 // All passes are streaming and HBM-bound; build time is reported separately from render time.
 #include <cfloat>
 #include "bpt_internal.cuh"
+#include "bpt_wide.cuh"
 
 using namespace bptd;
 
@@ -240,6 +241,16 @@ __global__ void k_refit(uint32_t n, const uint32_t* __restrict__ prims, const fl
     }
 }
 
+// ---- 4-wide quantised nodes + exact leaf boxes from the refitted binary tree (bpt_wide.cuh): one thread per binary node ----
+__global__ void k_collapse4(uint32_t n_internal, const float4* __restrict__ nodes2, float4* __restrict__ wide, float4* __restrict__ leafbox) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    float4 out[4];
+    collapse_node4(nodes2, (int32_t)i, out);
+    wide[4 * (size_t)i] = out[0]; wide[4 * (size_t)i + 1] = out[1]; wide[4 * (size_t)i + 2] = out[2]; wide[4 * (size_t)i + 3] = out[3];
+    leaf_boxes_of_node(nodes2, (int32_t)i, leafbox);
+}
+
 __global__ void k_emit_tris(uint32_t n, const uint32_t* __restrict__ prims, const float4* __restrict__ raw, float4* __restrict__ tris) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -425,7 +436,16 @@ bpt_status build_blas_merged(bpt_context* ctx) {
         base += bd.num_triangles;
     }
     if ((s = lbvh_build(ctx, ctx->blas[0], n, lo.as<float4>(), hi.as<float4>()))) return s;
-    return emit_tris(ctx, ctx->blas[0], raw.as<float4>());
+    if ((s = emit_tris(ctx, ctx->blas[0], raw.as<float4>()))) return s;
+    DevBvh& b = ctx->blas[0];
+    dev_free(b.wide); dev_free(b.leafbox);
+    if (n >= 2) {
+        if ((s = dev_alloc(ctx, b.wide, (size_t)(n - 1) * 64))) return s;
+        if ((s = dev_alloc(ctx, b.leafbox, (size_t)n * 32))) return s;
+        LAUNCH(ctx, k_collapse4, grid_for(n - 1), kThreads, n - 1, b.nodes.as<float4>(), b.wide.as<float4>(), b.leafbox.as<float4>());
+        BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return BPT_OK;
 }
 
 bpt_status build_tlas(bpt_context* ctx) {

@@ -13,6 +13,7 @@
 #include "bpt_shade.cuh"
 #include "bpt_ddgi.cuh"
 #include "bpt_aov.cuh"
+#include "bpt_wide.cuh"
 #pragma nv_diag_suppress 128   // "loop is not reachable": the two-level branch of the merged-mode instantiation
 
 using namespace bptd;
@@ -46,6 +47,7 @@ struct RenderArgs {
     uint32_t npx, nslots;     // pixels, samples in this wave; a path's id is slot * npx + pixel
     uint32_t frame_base;      // frame_index of slot 0
     const float4* m_nodes; const float4* m_tris; int32_t m_root; uint32_t m_n;   // the single BVH of merged mode
+    const float4* m_wide; const float4* m_leafbox;                                // its 4-wide quantised form (bpt_wide.cuh)
     uint32_t pixel_base;      // probe tracing in chunks: global path id = pixel_base + local id (RNG key)
     uint32_t pixel_jitter;
     uint32_t probe_mode;      // 1: paths start at probes; colour.w receives the first hit distance
@@ -126,13 +128,16 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 #ifndef BPT_TRACE_MIN_BLOCKS
 #define BPT_TRACE_MIN_BLOCKS 8
 #endif
-template <bool ANY, bool TWO_LEVEL>
+// WIDE (merged mode only): the node phase steps through the 4-wide quantised tree (a.m_wide) instead of the binary one, and a
+// proposed triangle is tested only if the ray passes that leaf's exact box (bpt_wide.cuh: same hits, about half the node fetches).
+template <bool ANY, bool TWO_LEVEL, bool WIDE = false>
 __global__ void __launch_bounds__(kBlock, BPT_TRACE_MIN_BLOCKS) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    static_assert(!(WIDE && TWO_LEVEL), "the wide tree exists for the merged BVH only");
     const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
     uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
     const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
     const float4* __restrict__ qd = ANY ? a.sh_d : a.ray_d_in;
-    const float4* __restrict__ nodes = TWO_LEVEL ? a.sc.tlas_nodes : a.m_nodes;
+    const float4* __restrict__ nodes = TWO_LEVEL ? a.sc.tlas_nodes : (WIDE ? a.m_wide : a.m_nodes);
     const float4* __restrict__ tris = TWO_LEVEL ? nullptr : a.m_tris;
     const uint32_t lane = threadIdx.x & 31;
     int32_t stack[kStackSize];
@@ -144,8 +149,9 @@ __global__ void __launch_bounds__(kBlock, BPT_TRACE_MIN_BLOCKS) k_trace_spec(con
     // the entry below it overlaps the node fetch instead of preceding it (ncu: 9 % of the stall samples sat behind that load).
     int32_t tos = kEmpty;
     int sp = 0;
-    auto push = [&](int32_t v) { stack[sp++] = tos; tos = v; };
-    auto pop = [&]() { int32_t v = tos; tos = sp ? stack[--sp] : kEmpty; return v; };
+    // (the wide kernels push up to three nodes per step with predicated stores and keep a plain stack)
+    auto push = [&](int32_t v) { if (WIDE) { stack[sp++] = v; } else { stack[sp++] = tos; tos = v; } };
+    auto pop = [&]() { if (WIDE) return sp ? stack[--sp] : kEmpty; int32_t v = tos; tos = sp ? stack[--sp] : kEmpty; return v; };
     uint32_t ray = 0xffffffffu, path = 0;
     uint32_t slot = 0xffffffffu, inst_anyhit = 0;     // TWO_LEVEL: the instance being traversed
     bool in_blas = !TWO_LEVEL;
@@ -228,9 +234,21 @@ __global__ void __launch_bounds__(kBlock, BPT_TRACE_MIN_BLOCKS) k_trace_spec(con
             // A lane postpones up to two leaves (leaf, leaf2) and keeps descending; it only idles when a third shows up.
             for (;;) {
                 if (node >= 0 && node != kEmpty) {
-                    int32_t far;
-                    int32_t next = node_step2(nodes, node, sp_, rs.tmin, rs.tcull, far);
-                    if (far != BPT_POP) push(far);
+                    int32_t next;
+                    if (WIDE) {
+                        int32_t ch[4]; uint32_t hitmask; int best;
+                        node_test4q(nodes, node, sp_, rs.tmin, rs.tcull, ch, hitmask, best);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {                       // store above the top unconditionally, keep it only if wanted
+                            stack[sp] = ch[k];
+                            sp += (((hitmask >> k) & 1u) && k != best) ? 1 : 0;
+                        }
+                        next = best < 0 ? BPT_POP : (best == 0 ? ch[0] : (best == 1 ? ch[1] : (best == 2 ? ch[2] : ch[3])));
+                    } else {
+                        int32_t far;
+                        next = node_step2(nodes, node, sp_, rs.tmin, rs.tcull, far);
+                        if (far != BPT_POP) push(far);
+                    }
                     if (next == BPT_POP) next = pop();
                     node = next;
                     settle();
@@ -252,7 +270,19 @@ __global__ void __launch_bounds__(kBlock, BPT_TRACE_MIN_BLOCKS) k_trace_spec(con
             }
             // ---- triangle phase ----
             while (leaf != 0) {
-                bool accepted = test_triangle<ANY>(a.sc, rs, tris + 3 * (size_t)(uint32_t)~leaf, sp_.O, sp_.D, TWO_LEVEL ? slot : 0xffffffffu, inst_anyhit);
+                bool accepted;
+                if (WIDE) {                                                  // leaf box and triangle fetched together: one latency, not two
+                    const uint32_t j = (uint32_t)~leaf;
+                    const float4* tp = tris + 3 * (size_t)j;
+                    const float4* bp = a.m_leafbox + 2 * (size_t)(a.m_n == 1 ? 0u : j);
+                    float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
+                    float4 blo = ta, bhi = ta;
+                    if (a.m_n != 1) { blo = BPT_LDG(bp); bhi = BPT_LDG(bp + 1); }
+                    accepted = (a.m_n == 1 || leaf_box_hit_rec(blo, bhi, sp_, rs.tmin, rs.tcull)) &&
+                               test_triangle_rec<ANY>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, 0xffffffffu, 0u);
+                } else {
+                    accepted = test_triangle<ANY>(a.sc, rs, tris + 3 * (size_t)(uint32_t)~leaf, sp_.O, sp_.D, TWO_LEVEL ? slot : 0xffffffffu, inst_anyhit);
+                }
                 leaf = leaf2; leaf2 = 0;
                 if (ANY && accepted) { node = kEmpty; sp = 0; tos = kEmpty; leaf = 0; break; }
                 if (leaf == 0) {
@@ -270,6 +300,8 @@ __global__ void __launch_bounds__(kBlock, BPT_TRACE_MIN_BLOCKS) k_trace_spec(con
 // the four instantiations (macro arguments cannot carry the template commas)
 static const auto k_extend_merged = k_trace_spec<false, false>;
 static const auto k_connect_merged = k_trace_spec<true, false>;
+static const auto k_extend_wide = k_trace_spec<false, false, true>;
+static const auto k_connect_wide = k_trace_spec<true, false, true>;
 static const auto k_extend_two_level = k_trace_spec<false, true>;
 static const auto k_connect_two_level = k_trace_spec<true, true>;
 
@@ -387,20 +419,21 @@ __global__ void k_resolve(const float4* __restrict__ accum, float4* __restrict__
 
 // ---- arbitrary ray batches (bpt_trace_rays / bpt_trace_shadow_rays) ----------------------------
 __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ DScene sc, const bpt_ray* __restrict__ rays, uint64_t n, uint32_t frame_index,
-                                                        bpt_hit* __restrict__ hits, uint8_t* __restrict__ visible, const DInstance* __restrict__ inst) {
+                                                        bpt_hit* __restrict__ hits, uint8_t* __restrict__ visible, const DInstance* __restrict__ inst,
+                                                        const float4* __restrict__ wide, const float4* __restrict__ leafbox) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     bpt_ray r = rays[i];
     float3 O = v3(r.origin[0], r.origin[1], r.origin[2]), D = v3(r.direction[0], r.direction[1], r.direction[2]);
     if (hits) {
-        TraceResult t = trace_ray<false>(sc, O, D, r.tmin, r.tmax, frame_index);
+        TraceResult t = wide ? trace_ray_wide<false>(sc, wide, leafbox, O, D, r.tmin, r.tmax, frame_index) : trace_ray<false>(sc, O, D, r.tmin, r.tmax, frame_index);
         bpt_hit h;
         h.t = t.t; h.u = t.u; h.v = t.v;
         h.instance = t.hit ? inst[t.slot].instance_id : 0xffffffffu;
         h.primitive = t.hit ? t.prim : 0xffffffffu;
         hits[i] = h;
     } else {
-        TraceResult t = trace_ray<true>(sc, O, D, r.tmin, r.tmax, frame_index);
+        TraceResult t = wide ? trace_ray_wide<true>(sc, wide, leafbox, O, D, r.tmin, r.tmax, frame_index) : trace_ray<true>(sc, O, D, r.tmin, r.tmax, frame_index);
         visible[i] = t.hit ? 0 : 1;
     }
 }
@@ -643,29 +676,52 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
         BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, false>, kBlock, 0));
         BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, false>, kBlock, 0));
         wf.grid_extend_m = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_m = (unsigned)(sms * std::max(ba, 1));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, false, true>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, false, true>, kBlock, 0));
+        wf.grid_extend_w = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_w = (unsigned)(sms * std::max(ba, 1));
     }
     if (ctx->accel_mode == BPT_ACCEL_MERGED) {
         a.m_nodes = ctx->blas[0].nodes.as<float4>(); a.m_tris = ctx->blas[0].tris.as<float4>(); a.m_root = ctx->blas[0].root; a.m_n = ctx->blas[0].n;
-    } else { a.m_nodes = nullptr; a.m_tris = nullptr; a.m_root = 0; a.m_n = 0; }
+        a.m_wide = ctx->blas[0].wide.as<float4>(); a.m_leafbox = ctx->blas[0].leafbox.as<float4>();
+    } else { a.m_nodes = nullptr; a.m_tris = nullptr; a.m_root = 0; a.m_n = 0; a.m_wide = nullptr; a.m_leafbox = nullptr; }
+    return BPT_OK;
+}
+
+// Which traversal kernel serves the current acceleration structure: merged mode uses the 4-wide quantised tree when it was
+// built (always, unless BPT_WIDE=0 asks for the binary tree — kept for A/B measurements), two-level mode the binary trees.
+static bool use_wide(const bpt_context* ctx, uint32_t bounce = 99) {
+    static const bool enabled = [] { const char* e = getenv("BPT_WIDE"); return !e || atoi(e) != 0; }();
+    static const uint32_t from_bounce = [] { const char* e = getenv("BPT_WIDE_FROM_BOUNCE"); return e ? (uint32_t)atoi(e) : 2u; }();
+    return enabled && bounce >= from_bounce && ctx->accel_mode == BPT_ACCEL_MERGED && ctx->blas[0].wide.p != nullptr;
+}
+static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
+    WavefrontState& wf = ctx->wf;
+    if (use_wide(ctx, i)) LAUNCH_T(ctx, 1, k_extend_wide, wf.grid_extend_w, kBlock, a, i);
+    else if (ctx->accel_mode == BPT_ACCEL_MERGED) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i);
+    else LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i);
+    return BPT_OK;
+}
+static bpt_status launch_connect(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
+    WavefrontState& wf = ctx->wf;
+    if (use_wide(ctx, i)) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i);
+    else if (ctx->accel_mode == BPT_ACCEL_MERGED) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
+    else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
     return BPT_OK;
 }
 
 // (extend → shade → connect) for bounces 1..B-1 over the queue that raygen left in ray buffer 0.
 static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_settings& st, uint32_t B, uint64_t paths, bool capture) {
     WavefrontState& wf = ctx->wf;
-    const bool merged = ctx->accel_mode == BPT_ACCEL_MERGED;
     const unsigned grid_paths = (unsigned)((paths + kBlock - 1) / kBlock);
     bpt_status s;
     int cur = 0;
     for (uint32_t i = 1; i < B; i++) {
         a.ray_o_in = wf.ray_o[cur].as<float4>(); a.ray_d_in = wf.ray_d[cur].as<float4>(); a.ray_w_in = wf.ray_w[cur].as<float4>();
         a.ray_o_out = wf.ray_o[cur ^ 1].as<float4>(); a.ray_d_out = wf.ray_d[cur ^ 1].as<float4>(); a.ray_w_out = wf.ray_w[cur ^ 1].as<float4>();
-        if (merged) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i);
-        else LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i);
+        if ((s = launch_extend(ctx, a, i))) return s;
         LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
         if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point + (st.rect_shadow ? ctx->num_rect : 0)) > 0) {
-            if (merged) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
-            else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
+            if ((s = launch_connect(ctx, a, i))) return s;
         }
         if (st.state_precision == BPT_STATE_REFERENCE_FP16) LAUNCH_T(ctx, 4, k_commit_bounce, grid_paths, kBlock, a, i);
         if (capture && (s = capture_bounce(ctx, i, cur))) return s;
@@ -734,8 +790,7 @@ bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uin
     const uint64_t gen_threads = (uint64_t)((ctx->width + 7) / 8) * ((ctx->height + 3) / 4) * 32;
     if (e == cudaSuccess) {
         k_raygen<<<(unsigned)((gen_threads + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(a);
-        if (ctx->accel_mode == BPT_ACCEL_MERGED) k_extend_merged<<<wf.grid_extend_m, kBlock, 0, ctx->stream>>>(a, 1u);
-        else k_extend_two_level<<<wf.grid_extend, kBlock, 0, ctx->stream>>>(a, 1u);
+        if (launch_extend(ctx, a, 1u) != BPT_OK) e = cudaErrorLaunchFailure;
         k_primary_aov<<<(npx + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(a, d_depth.as<float>(), d_g.as<bpt_gbuffer_texel>());
         k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), 0u);
         ctx->launches += 4;
@@ -773,8 +828,7 @@ bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t 
     if (e == cudaSuccess) {
         const float range = ao.range > 0.05f ? ao.range : 0.05f;              // ambient_occlusion.cpp:241
         k_ao_raygen<<<(n + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(a, aw, ah, ao.half_resolution ? 1u : 0u, range, d_depth.as<float>(), d_nr.as<float4>());
-        if (ctx->accel_mode == BPT_ACCEL_MERGED) k_connect_merged<<<wf.grid_connect_m, kBlock, 0, ctx->stream>>>(a, 1u);
-        else k_connect_two_level<<<wf.grid_connect, kBlock, 0, ctx->stream>>>(a, 1u);
+        if (launch_connect(ctx, a, 1u) != BPT_OK) e = cudaErrorLaunchFailure;
         k_ao_finish<<<(n + 255) / 256, 256, 0, ctx->stream>>>(wf.color.as<float4>(), n, ao.strength, d_out.as<float2>());
         k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), 0u);
         ctx->launches += 4;
@@ -851,7 +905,8 @@ bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t 
     if ((s = dev_alloc(ctx, out, out_bytes))) { dev_free(rays); return s; }
     DScene sc = ctx->scene_view();
     k_trace_batch<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(sc, rays.as<bpt_ray>(), n, frame_index,
-        h_hits ? out.as<bpt_hit>() : nullptr, h_hits ? nullptr : out.as<uint8_t>(), ctx->d_instances.as<DInstance>());
+        h_hits ? out.as<bpt_hit>() : nullptr, h_hits ? nullptr : out.as<uint8_t>(), ctx->d_instances.as<DInstance>(),
+        use_wide(ctx) ? ctx->blas[0].wide.as<float4>() : nullptr, use_wide(ctx) ? ctx->blas[0].leafbox.as<float4>() : nullptr);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_hits ? (void*)h_hits : (void*)h_visible, out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);

@@ -369,6 +369,11 @@ BPT_API bpt_status bpt_trace_rays(bpt_context* ctx, const bpt_ray* rays, uint64_
 /* Any-hit (occlusion) trace through the connect kernel; out_visible[i] = 1 if unoccluded. */
 BPT_API bpt_status bpt_trace_shadow_rays(bpt_context* ctx, const bpt_ray* rays, uint64_t num_rays, uint32_t frame_index, uint8_t* out_visible);
 
+/* Merged mode: the 4-wide quantised tree the traversal kernels walk (csrc/bpt_wide.cuh; derived from the binary LBVH by a
+ * deterministic collapse) and the exact leaf boxes: wide_nodes = (n-1) x 16 floats (64-B nodes, raw bits), leaf_boxes =
+ * n x 8 floats. Either may be NULL. For bit-exact structure checks against the oracle. */
+BPT_API bpt_status bpt_debug_read_wide(bpt_context* ctx, float* wide_nodes, float* leaf_boxes, uint32_t capacity_leaves);
+
 /* When enabled, bpt_render(num_samples == 1) keeps, per bounce, the extend queue (pixel index
  * per live path), the hit records and the shadow-ray queue (pixel, light) for read-back. */
 BPT_API bpt_status bpt_debug_capture(bpt_context* ctx, uint32_t enable);

@@ -71,6 +71,11 @@ BPT_API bpt_status obpt_debug_capture(obpt_context* ctx, uint32_t enable);
 BPT_API bpt_status obpt_debug_read_queue(
     obpt_context* ctx, uint32_t bounce, uint32_t kind,
     uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t capacity, uint64_t* count);
+/* The 4-wide quantised tree of merged mode (oracle_wide.cpp = the definition csrc/bpt_wide.cuh must reproduce) and work
+ * statistics of wide traversals on a ray batch: counts = {rays, wide nodes, triangles, child boxes, exact leaf boxes}. */
+BPT_API bpt_status obpt_debug_read_wide(obpt_context* ctx, float* wide_nodes, float* leaf_boxes, uint32_t capacity_leaves);
+BPT_API bpt_status obpt_wide_stats(obpt_context* ctx, uint32_t width, uint32_t quantised, uint32_t order, const bpt_ray* rays, uint64_t n,
+                                   float* t_out, uint32_t* prim_out, uint64_t counts[5]);
 /* calc_ddgi_volume_lighting (ddgi/ddgi_lighting.hlsl:7-83) and the previous-update feedback of the probe lighting pass. */
 BPT_API bpt_status obpt_set_ddgi_volume(obpt_context* ctx, const bpt_probe_volume* volume, const bpt_probe_blend* sizes,
                                         const float* irradiance_atlas, const float* visibility_atlas);

@@ -72,6 +72,8 @@ def library() -> capi.Library:
         L.obpt_store_half.argtypes, L.obpt_store_half.restype = [C.c_float], C.c_float
         L.obpt_gbuffer_roundtrip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
         L.obpt_gbuffer_roundtrip.restype = None
+        L.obpt_wide_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.obpt_wide_stats.restype = C.c_int
         L.obpt_morton63.argtypes, L.obpt_morton63.restype = [C.c_void_p, C.c_void_p, C.c_void_p], C.c_uint64
     return _lib
 
@@ -93,6 +95,16 @@ class OracleContext(capi.Context):
         s = Stats()
         self._call("get_stats", C.byref(s))
         return s
+
+    def wide_stats(self, rays, width=4, quantised=True, order=0):
+        """Closest hits through a `width`-ary collapse of the merged BVH + work counters (oracle_wide.cpp).
+        Returns (t, prim, dict(rays, nodes, tris, boxes, leaf_boxes))."""
+        t = np.zeros(len(rays), np.float32); prim = np.zeros(len(rays), np.uint32); cnt = np.zeros(5, np.uint64)
+        st = library().lib.obpt_wide_stats(self._h, width, 1 if quantised else 0, order, rays.ctypes.data_as(C.c_void_p), len(rays),
+                                          t.ctypes.data_as(C.c_void_p), prim.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
+        if st != 0:
+            raise capi.BptError(st, "obpt_wide_stats", "")
+        return t, prim, dict(zip(("rays", "nodes", "tris", "boxes", "leaf_boxes"), (int(x) for x in cnt)))
 
     def render_converged(self, camera, frame_first, num_samples, settings) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), np.float32)

@@ -62,6 +62,8 @@ def lib():
         _lib.hc_set_ddgi.argtypes = [C.POINTER(capi.ProbeVolume), C.POINTER(capi.ProbeBlend), C.c_void_p, C.c_void_p]
         _lib.hc_ddgi_lighting.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.hc_trace_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.hc_read_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -135,6 +137,19 @@ class HostScene:
         vis = np.zeros(len(rays), np.uint8)
         lib().hc_trace(C.byref(self.h), rays.ctypes.data_as(C.c_void_p), len(rays), frame_index, hits.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p))
         return hits, vis
+
+    def trace_wide(self, rays, frame_index=0):
+        """Closest hits and visibility through the 4-wide quantised tree (merged mode)."""
+        hits = np.zeros(len(rays), capi.HIT)
+        vis = np.zeros(len(rays), np.uint8)
+        assert lib().hc_trace_wide(C.byref(self.h), rays.ctypes.data_as(C.c_void_p), len(rays), frame_index, hits.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p)) == 0
+        return hits, vis
+
+    def read_wide(self):
+        n = self.keep[0]["n"]
+        wide = np.zeros((max(n - 1, 0), 16), np.uint32); leafbox = np.zeros((n, 8), np.float32)
+        assert lib().hc_read_wide(C.byref(self.h), wide.ctypes.data_as(C.c_void_p), leafbox.ctypes.data_as(C.c_void_p)) == 0
+        return wide, leafbox
 
     def trace_probes(self, volume, table, frame_index, num_bounces):
         n = volume.probe_counts[0] * volume.probe_counts[1] * volume.probe_counts[2] * volume.rays_per_probe

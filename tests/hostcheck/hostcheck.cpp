@@ -12,6 +12,7 @@
 #include "../../bisemutum-engine_b200/csrc/bpt_shade.cuh"
 #include "../../bisemutum-engine_b200/csrc/bpt_ddgi.cuh"
 #include "../../bisemutum-engine_b200/csrc/bpt_aov.cuh"
+#include "../../bisemutum-engine_b200/csrc/bpt_wide.cuh"
 
 using namespace bptd;
 
@@ -249,6 +250,44 @@ int hc_trace(const hc_scene* h, const bpt_ray* rays, uint64_t n, uint32_t frame_
             hits[i] = bpt_hit{t.t, t.u, t.v, t.hit ? b.inst[t.slot].instance_id : 0xffffffffu, t.hit ? t.prim : 0xffffffffu};
         }
         if (visible) visible[i] = trace_ray<true>(b.sc, O, D, rays[i].tmin, rays[i].tmax, frame_index).hit ? 0 : 1;
+    }
+    return 0;
+}
+
+// 4-wide quantised tree of the merged BVH: collapse_node4 / leaf_boxes_of_node per binary node like k_collapse4, then the
+// run-to-completion wide traversal (trace_ray_wide) that the persistent kernels interleave.
+static void build_wide(const hc_scene& h, std::vector<float4>& wide, std::vector<float4>& leafbox) {
+    const hc_bvh& hb = h.blas_bvh[0];
+    wide.assign(hb.n >= 2 ? 4ull * (hb.n - 1) : 0, make_float4(0, 0, 0, 0));
+    leafbox.assign(2ull * hb.n, make_float4(0, 0, 0, 0));
+    const float4* nodes2 = reinterpret_cast<const float4*>(hb.nodes);
+    for (uint32_t i = 0; i + 1 < hb.n; i++) {
+        collapse_node4(nodes2, (int32_t)i, &wide[4ull * i]);
+        leaf_boxes_of_node(nodes2, (int32_t)i, leafbox.data());
+    }
+}
+__attribute__((visibility("default")))
+int hc_read_wide(const hc_scene* h, float* wide_out, float* leafbox_out) {
+    if (h->accel_mode != BPT_ACCEL_MERGED) return 1;
+    std::vector<float4> wide, leafbox;
+    build_wide(*h, wide, leafbox);
+    if (wide_out) memcpy(wide_out, wide.data(), wide.size() * 16);
+    if (leafbox_out) memcpy(leafbox_out, leafbox.data(), leafbox.size() * 16);
+    return 0;
+}
+__attribute__((visibility("default")))
+int hc_trace_wide(const hc_scene* h, const bpt_ray* rays, uint64_t n, uint32_t frame_index, bpt_hit* hits, uint8_t* visible) {
+    if (h->accel_mode != BPT_ACCEL_MERGED) return 1;
+    Built b; build(*h, b);
+    std::vector<float4> wide, leafbox;
+    build_wide(*h, wide, leafbox);
+    for (uint64_t i = 0; i < n; i++) {
+        float3 O = v3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), D = v3(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
+        if (hits) {
+            TraceResult t = trace_ray_wide<false>(b.sc, wide.data(), leafbox.data(), O, D, rays[i].tmin, rays[i].tmax, frame_index);
+            hits[i] = bpt_hit{t.t, t.u, t.v, t.hit ? b.inst[t.slot].instance_id : 0xffffffffu, t.hit ? t.prim : 0xffffffffu};
+        }
+        if (visible) visible[i] = trace_ray_wide<true>(b.sc, wide.data(), leafbox.data(), O, D, rays[i].tmin, rays[i].tmax, frame_index).hit ? 0 : 1;
     }
     return 0;
 }

@@ -282,6 +282,77 @@ def test_probe_blending_bit_exact(oracle):
     np.testing.assert_allclose(irr_flat[..., :3], np.broadcast_to(np.float32([0.25, 0.5, 1.0]), irr_flat[..., :3].shape), rtol=2e-6)
 
 
+def _random_rays(scene, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = scene.bounds
+    rays = np.zeros(n, capi.RAY)
+    rays["origin"] = rng.uniform(lo - 0.5, hi + 0.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d[: n // 8] = np.round(d[: n // 8])                                      # some axis-aligned / diagonal directions (zeros included)
+    d[np.abs(d).sum(axis=1) == 0] = (0, 0, 1)
+    rays["direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tmin"] = 0.001
+    rays["tmax"] = rng.choice([100.0, 3.0, 0.5], n).astype(np.float32)
+    return rays
+
+
+@pytest.mark.parametrize("name", ["cornell", "small", "scene_basic"])
+def test_wide_bvh_bit_exact(oracle, name):
+    """The 4-wide quantised tree of merged mode (csrc/bpt_wide.cuh): its nodes equal the oracle's definition bit for bit, every
+    decoded child box contains the exact one, and traversing it (with the exact leaf-box test) returns exactly the hits and
+    visibilities of the binary traversal — on axis-aligned geometry (Cornell), any-hit materials (the reference's example
+    scene) and grazing / axis-parallel rays."""
+    scene = scenes.scene_basic(os.path.join(GOLDEN, "scene_basic.npz")) if name == "scene_basic" else _scene(name)
+    ctx = oracle.OracleContext(8, 8); ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    hs = HC.HostScene(scene, ctx, capi.ACCEL_MERGED)
+    wide, leafbox = hs.read_wide()
+    owide, oleafbox = ctx.read_wide()
+    np.testing.assert_array_equal(wide, owide); np.testing.assert_array_equal(leafbox.view(np.uint32), oleafbox.view(np.uint32))
+    bv = ctx.read_bvh(0)
+    n = bv["n"]
+    assert wide.shape == (n - 1, 16)
+    # structure: reachable wide nodes partition the leaves; decoded boxes are supersets of the binary child boxes
+    origin = wide[:, 0:3].view(np.float32); ebits = wide[:, 3]
+    scale = np.stack([np.ldexp(np.float32(1), ((ebits >> (8 * a)) & 0xff).astype(np.int32) - 127) for a in range(3)], axis=1).astype(np.float32)
+    child = wide[:, 4:8].view(np.int32)
+    qlo = np.stack([(wide[:, 8 + a][:, None] >> (8 * np.arange(4))) & 0xff for a in range(3)], axis=2).astype(np.float32)          # (node, child, axis)
+    qhi = np.stack([(wide[:, [11, 12, 13][a]][:, None] >> (8 * np.arange(4))) & 0xff for a in range(3)], axis=2).astype(np.float32)
+    dlo = origin[:, None, :] + qlo * scale[:, None, :]; dhi = origin[:, None, :] + qhi * scale[:, None, :]
+    nodes = bv["nodes"]
+    blo = np.stack([np.stack([nodes[f"c{c}_lo_{a}"] for a in "xyz"], axis=1) for c in (0, 1)], axis=1)                            # (node, 2, 3): child boxes held by the parent
+    bhi = np.stack([np.stack([nodes[f"c{c}_hi_{a}"] for a in "xyz"], axis=1) for c in (0, 1)], axis=1)
+    parent_of = {}                                                                                                                 # binary node / leaf ref -> (its exact box)
+    for i in range(n - 1):
+        for c, ref in enumerate((int(nodes["child0"][i]), int(nodes["child1"][i]))):
+            parent_of[ref] = (blo[i, c], bhi[i, c])
+    seen_leaves, stack, visited = [], [int(bv["root"])], 0
+    while stack:
+        i = stack.pop(); visited += 1
+        kids = [int(c) for c in child[i] if c != 0x7ffffffe]
+        assert 2 <= len(kids) <= 4
+        for k, ref in enumerate(kids):
+            elo, ehi = parent_of[ref]
+            assert (dlo[i, k] <= elo).all() and (dhi[i, k] >= ehi).all(), (i, k)
+            assert ((elo - dlo[i, k]) <= scale[i] * 1.0001).all() and ((dhi[i, k] - ehi) <= scale[i] * 1.0001).all()                # and by less than one grid step
+            (stack if ref >= 0 else seen_leaves).append(ref if ref >= 0 else ~ref)
+    assert sorted(seen_leaves) == list(range(n)) and visited < 0.62 * (n - 1)                                                      # every leaf once; about half the binary nodes
+    # traversal: wide == binary, hits and visibility, bit for bit
+    rays = _random_rays(scene, 6000, 21)
+    cam = oracle.camera_matrices(scene.camera, 40, 30)                                                                             # + camera rays (coherent, hit the walls head-on)
+    want_h, want_v = ctx.trace_rays(rays, 7), ctx.trace_shadow_rays(rays, 7)
+    got_h, got_v = hs.trace_wide(rays, 7)
+    for f in ("t", "u", "v", "instance", "primitive"):
+        np.testing.assert_array_equal(got_h[f], want_h[f], err_msg=f)
+    np.testing.assert_array_equal(got_v, want_v)
+    assert (want_h["t"] >= 0).mean() > 0.1
+    t, prim, cnt = ctx.wide_stats(rays, 4, True, 0)                                                                                # the oracle's own wide traversal agrees too
+    if name == "cornell":                                                                                                          # (it ignores any-hit materials, which the other two scenes have)
+        np.testing.assert_array_equal(t, want_h["t"])
+    ctx.reset_counters(); ctx.trace_rays(rays, 7); st = ctx.stats()
+    assert cnt["nodes"] < 0.7 * st.extend_nodes and cnt["leaf_boxes"] >= cnt["tris"]                                               # fewer steps; the leaf test filters
+    del cam
+
+
 def test_ddgi_volume_lighting_and_feedback_bit_exact(oracle):
     """The consumer of the probe atlases, calc_ddgi_volume_lighting (ddgi_lighting.hlsl:7-83), and the previous-update
     feedback of the probe lighting pass (ddgi/deferred_lighting.hlsl:102-115): CUDA source (host build) == oracle, and the
