@@ -119,9 +119,27 @@ def oracle_sample(scene, accel_mode, width, height, bounces, tile_stride, frames
     out = dict(rays_per_s=rays / dt, seconds=dt, rays=rays, pixel_samples=c.samples, cores=ctx.threads, desc=desc,
                ext_nodes=s.extend_nodes / max(1, s.extend_rays), ext_tris=s.extend_tris / max(1, s.extend_rays),
                shd_nodes=s.shadow_nodes / max(1, s.shadow_rays), shd_tris=s.shadow_tris / max(1, s.shadow_rays),
-               ext_inst=s.extend_instances / max(1, s.extend_rays))
+               ext_inst=s.extend_instances / max(1, s.extend_rays), ext_wide_nodes=0.0, ext_leaf_boxes=0.0, ext_wide_ray_share=0.0)
+    # Untimed second pass for the byte accounting: the same rays through the trees the CUDA kernels actually walk
+    # (merged mode: binary tree at bounce 1, 4-wide quantised tree + exact leaf boxes from bounce WIDE_FROM on).
+    wide_from = wide_from_bounce()
+    if accel_mode == capi.ACCEL_MERGED and wide_from:
+        ctx.set_wide_from_bounce(wide_from)
+        ctx.reset_counters()
+        ctx.render(cam, 0, max(1, min(frames, 4)), st)
+        w = ctx.stats()
+        n = max(1, w.extend_rays)
+        out.update(ext_nodes=w.extend_nodes / n, ext_tris=w.extend_tris / n, ext_wide_nodes=w.extend_wide_nodes / n,
+                   ext_leaf_boxes=w.extend_leaf_boxes / n, ext_wide_ray_share=w.extend_wide_rays / n)
     ctx.close()
     return out
+
+
+def wide_from_bounce():
+    """Mirror of use_wide() in csrc/render.cu: the first bounce whose rays walk the 4-wide tree (0 = never)."""
+    if os.environ.get("BPT_WIDE", "1") == "0":
+        return 0
+    return int(os.environ.get("BPT_WIDE_FROM_BOUNCE", "2"))
 
 
 def run_reference(args, rank, world):
@@ -321,10 +339,11 @@ def main():
         cpu = {"value": ora["rays_per_s"] / 1e6, "unit": "Mrays/s", "cores": ora["cores"], "kind": "port",
                "sample": ora["desc"], "seconds": ora["seconds"]}
     if kt.extend_launches:
-        # extend ray = 32 B ray in + 16 B hit out + 64 B x nodes + 48 B x tris (oracle counters)
+        # extend ray = 32 B ray in + 16 B hit out + 64 B x nodes + 48 B x tris (oracle counters on the same rays);
+        # rays that walk the 4-wide tree: 64 B per wide node + 32 B per exact leaf box instead of the binary nodes
         nodes, tris = (ora["ext_nodes"], ora["ext_tris"]) if ora else (None, None)
         if nodes is not None:
-            per_ray = 32 + 16 + 64 * nodes + 48 * tris
+            per_ray = 32 + 16 + 64 * nodes + 64 * ora["ext_wide_nodes"] + 32 * ora["ext_leaf_boxes"] + 48 * tris
             rays_per_launch = pc.extend_rays / kt.extend_launches
             avg_s = kt.extend_ms * 1e-3 / kt.extend_launches
             achieved = per_ray * rays_per_launch / avg_s / 1e9
@@ -338,8 +357,9 @@ def main():
             roofline = {"bound": "hbm", "kernel": "k_trace_spec<false,false> (extend)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
                         "algorithmic_gb_per_launch": per_ray * rays_per_launch / 1e9,
-                        "note": "frac > 1 is expected here: the 29 MB scene+BVH is L2-resident (traffic << algorithmic bytes); the kernel is issue/divergence-bound, see profiles/r1_v6_kernels.md",
+                        "note": "the 29 MB scene+BVH is L2-resident (traffic << algorithmic bytes), so HBM does not bind this kernel: bounce 1 (binary tree) is issue-bound, later bounces (4-wide quantised tree) are L1/issue-bound; see profiles/r1_v8_kernels.md",
                         "peak_source": peak_src, "bytes_per_ray": per_ray, "nodes_per_ray": nodes, "tris_per_ray": tris,
+                        "wide_nodes_per_ray": ora["ext_wide_nodes"], "leaf_boxes_per_ray": ora["ext_leaf_boxes"], "wide_ray_share": ora["ext_wide_ray_share"],
                         "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_s * 1e3,
                         "kernel_time_share": {"raygen": kt.raygen_ms / total_k, "extend": kt.extend_ms / total_k, "shade": kt.shade_ms / total_k,
                                               "connect": kt.connect_ms / total_k, "other": kt.other_ms / total_k}}

@@ -10,7 +10,7 @@
 // values are monotone in the plane coordinates, so passing the exact leaf box implies passing every exact ancestor box
 // of the binary tree — the set of triangles that reach the triangle test is exactly the binary traversal's (the
 // quantised boxes are supersets by construction, see collapse_node4), and the result rule of bpt_trace.cuh makes the
-// answer independent of the visiting order. tests/: hits bit-equal to the oracle's binary traversal.
+// answer independent of the visiting order. tests/: hits bit-equal to the binary traversal of the CPU restatement.
 //
 // Node i of the wide tree describes the subtree of binary node i (same index: no allocation, every binary node gets a
 // wide node, only those reachable from the root are ever read). Layout (4 x 16 B):

@@ -26,10 +26,19 @@ constexpr int QS = 32;     // qcount[QS + bounce]  : shadow queue length of that
 constexpr int QWE = 64;    // qcount[QWE + bounce] : work-fetch cursor of the persistent extend kernel
 constexpr int QWS = 96;    // qcount[QWS + bounce] : work-fetch cursor of the persistent connect kernel
 constexpr int QN = 128;
-constexpr int kMinNodeLanes = 12;       // node phase ends when fewer lanes than this still have an internal node
-constexpr int kRefillThreshold = 8;    // refill a warp's finished lanes when fewer rays than this are still in flight (measured: 2 → 1.18 ms,
-                                       // 8 → 1.14, 14 → 1.16, 20 → 1.21, 26 → 1.25 ms of extend per 1080p sample: refilling early mixes
-                                       // root-level rays into warps that are deep in the tree and costs more than the idle lanes)
+// Tunables of the persistent traversal kernels (overridable at compile time for tuning runs, tools/build_variant.sh).
+// Measured on configs[1] with the binary tree: refill threshold 2 -> 1.18, 8 -> 1.14, 14 -> 1.16, 20 -> 1.21, 26 -> 1.25 ms of
+// extend per 1080p sample (refilling early mixes root-level rays into warps that are deep in the tree and costs more than the
+// idle lanes). Re-tuned with the 4-wide tree from bounce 2 (whole frame): node-phase exit at 1 / 4 / 6 / 8 / 12 / 16 lanes ->
+// 1.888 / 1.739 / 1.704 / 1.696 / 1.709 / 1.739 ms; refill 4 / 8 / 14 -> 1.755 / 1.709 / 1.707; (8, 12) -> 1.690 ms.
+#ifndef BPT_MIN_NODE_LANES
+#define BPT_MIN_NODE_LANES 8
+#endif
+#ifndef BPT_REFILL
+#define BPT_REFILL 12
+#endif
+constexpr int kMinNodeLanes = BPT_MIN_NODE_LANES;       // node phase ends when fewer lanes than this still have an internal node
+constexpr int kRefillThreshold = BPT_REFILL;            // refill a warp's finished lanes when fewer rays than this are still in flight
 
 struct RenderArgs {
     DScene sc;

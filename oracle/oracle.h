@@ -71,6 +71,9 @@ BPT_API bpt_status obpt_debug_capture(obpt_context* ctx, uint32_t enable);
 BPT_API bpt_status obpt_debug_read_queue(
     obpt_context* ctx, uint32_t bounce, uint32_t kind,
     uint32_t* pixels, uint32_t* lights, bpt_hit* hits, uint64_t capacity, uint64_t* count);
+/* Oracle-only: bounces >= `bounce` of obpt_render / obpt_trace_probes walk the 4-wide quantised tree (as the CUDA kernels do with
+ * bounce = 2); 0 = binary tree everywhere (default). Hits are identical by construction; only obpt_stats changes. Merged mode. */
+BPT_API bpt_status obpt_set_wide_from_bounce(obpt_context* ctx, uint32_t bounce);
 /* The 4-wide quantised tree of merged mode (oracle_wide.cpp = the definition csrc/bpt_wide.cuh must reproduce) and work
  * statistics of wide traversals on a ray batch: counts = {rays, wide nodes, triangles, child boxes, exact leaf boxes}. */
 BPT_API bpt_status obpt_debug_read_wide(obpt_context* ctx, float* wide_nodes, float* leaf_boxes, uint32_t capacity_leaves);
@@ -101,6 +104,9 @@ typedef struct obpt_stats {
     uint64_t shaded_vertices;  /* path vertices that ran material + lighting */
     uint64_t miss_vertices;    /* paths that ended on the sky               */
     uint64_t samples;
+    /* rays of bounces >= obpt_set_wide_from_bounce walk the 4-wide quantised tree: steps and exact leaf-box tests */
+    uint64_t extend_wide_nodes, extend_leaf_boxes, shadow_wide_nodes, shadow_leaf_boxes;
+    uint64_t extend_wide_rays, shadow_wide_rays;
 } obpt_stats;
 BPT_API bpt_status obpt_get_stats(obpt_context* ctx, obpt_stats* out);
 /* Oracle-only: render only the 16x16 tiles t with t % stride == offset (a bounded, spatially uniform

@@ -199,6 +199,7 @@ bool build_tlas(Scene& sc, std::string& err) {
 
 bool build_accel(Scene& sc, uint32_t mode, std::string& err) {
     sc.accel_built = false;
+    sc.wide_from_bounce = 0;
     if (sc.blas_descs.empty() || sc.instances.empty()) { err = "build_accel: no geometry or no instances"; return false; }
     for (auto& bd : sc.blas_descs) {
         if (bd.num_triangles == 0) { err = "empty BLAS"; return false; }
@@ -378,9 +379,68 @@ static inline void traverse(const Bvh& b, f3 O, f3 D, RayCtx& rc, TraceStats& st
     }
 }
 
-static void trace_generic(const Scene& sc, RayCtx& rc, TraceStats& st) {
+// The 4-wide quantised tree (oracle_wide.cpp): nearest hit child first, the others pushed in slot order; a proposed leaf
+// reaches the triangle test only if the ray passes its exact box (the child box held by its binary parent).
+template <class LeafFn>
+static inline void traverse_wide(const Bvh& b, f3 O, f3 D, RayCtx& rc, TraceStats& st, LeafFn&& leaf) {
+    if (b.n == 0) return;
+    f3 idir, ood;
+    ray_prep(D, O, idir, ood);
+    auto slab = [&](f3 lo, f3 hi, float& tn) {
+        float lx = fmaf(lo.x, idir.x, -ood.x), hx = fmaf(hi.x, idir.x, -ood.x);
+        float ly = fmaf(lo.y, idir.y, -ood.y), hy = fmaf(hi.y, idir.y, -ood.y);
+        float lz = fmaf(lo.z, idir.z, -ood.z), hz = fmaf(hi.z, idir.z, -ood.z);
+        tn = fmax_(fmax_(fmin_(lx, hx), fmin_(ly, hy)), fmax_(fmin_(lz, hz), rc.tmin));
+        float tf = fmin_(fmin_(fmax_(lx, hx), fmax_(ly, hy)), fmin_(fmax_(lz, hz), rc.tcull));
+        return tn <= tf;
+    };
+    int32_t stack[512];
+    int sp = 0;
+    int32_t cur = b.root;
+    for (;;) {
+        if (cur >= 0) {
+            const Bvh::Wide4& n = b.wide[cur];
+            st.wide_nodes++;
+            int best = -1; float tb = 0.0f; bool hit[4] = {false, false, false, false};
+            for (int k = 0; k < n.nchild; k++) {
+                float tn;
+                if (slab(n.clo[k], n.chi[k], tn)) { hit[k] = true; if (best < 0 || tn < tb) { best = k; tb = tn; } }
+            }
+            if (best >= 0) {
+                for (int k = 0; k < n.nchild; k++) if (hit[k] && k != best) stack[sp++] = n.child[k];
+                cur = n.child[best];
+                continue;
+            }
+        } else {
+            const uint32_t j = (uint32_t)~cur;
+            bool candidate = true;
+            if (b.n > 1) {
+                const bpt_bvh_node& pn = b.nodes[b.leaf_parent[j]];
+                const bool first = pn.child0 == cur;
+                float tn;
+                st.leaf_boxes++;
+                candidate = first ? slab(mk3(pn.c0_lo_x, pn.c0_lo_y, pn.c0_lo_z), mk3(pn.c0_hi_x, pn.c0_hi_y, pn.c0_hi_z), tn)
+                                  : slab(mk3(pn.c1_lo_x, pn.c1_lo_y, pn.c1_lo_z), mk3(pn.c1_hi_x, pn.c1_hi_y, pn.c1_hi_z), tn);
+            }
+            if (candidate) {
+                leaf(j);
+                if (rc.terminated) return;
+            }
+        }
+        if (sp == 0) return;
+        cur = stack[--sp];
+    }
+}
+
+static void trace_generic(const Scene& sc, RayCtx& rc, TraceStats& st, bool wide = false) {
     st.rays++;
-    if (sc.accel_mode == BPT_ACCEL_MERGED) {
+    if (sc.accel_mode == BPT_ACCEL_MERGED && wide && !sc.blas[0].wide.empty()) {
+        const Bvh& b = sc.blas[0];
+        traverse_wide(b, rc.O, rc.D, rc, st, [&](uint32_t j) {
+            const Tri& tr = b.tris[j];
+            tri_test(sc, rc, tr, rc.O, rc.D, tr.inst, st);
+        });
+    } else if (sc.accel_mode == BPT_ACCEL_MERGED) {
         const Bvh& b = sc.blas[0];
         traverse(b, rc.O, rc.D, rc, st, [&](uint32_t j) {
             const Tri& tr = b.tris[j];
@@ -398,11 +458,11 @@ static void trace_generic(const Scene& sc, RayCtx& rc, TraceStats& st) {
     }
 }
 
-HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st) {
+HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool wide) {
     RayCtx rc{};
     rc.O = O; rc.D = D; rc.tmin = tmin; rc.tbest = tmax; rc.tcull = tmax * 1.00001f; rc.best_id = ~0ull;
     rc.any_mode = false; rc.terminated = false; rc.frame_index = frame_index; rc.have_u = false;
-    trace_generic(sc, rc, st);
+    trace_generic(sc, rc, st, wide);
     HitRec h{};
     h.hit = rc.best_id != ~0ull;
     if (h.hit) {
@@ -412,12 +472,12 @@ HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32
     return h;
 }
 
-bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool cull_non_opaque) {
+bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool cull_non_opaque, bool wide) {
     RayCtx rc{};
     rc.cull_non_opaque = cull_non_opaque;
     rc.O = O; rc.D = D; rc.tmin = tmin; rc.tbest = tmax; rc.tcull = tmax * 1.00001f; rc.best_id = ~0ull;
     rc.any_mode = true; rc.terminated = false; rc.frame_index = frame_index; rc.have_u = false;
-    trace_generic(sc, rc, st);
+    trace_generic(sc, rc, st, wide);
     return rc.terminated;  // true = occluded
 }
 

@@ -23,7 +23,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "extend_rays", "extend_nodes", "extend_tris", "extend_instances",
         "shadow_rays", "shadow_nodes", "shadow_tris", "shadow_instances",
-        "shaded_vertices", "miss_vertices", "samples")]
+        "shaded_vertices", "miss_vertices", "samples",
+        "extend_wide_nodes", "extend_leaf_boxes", "shadow_wide_nodes", "shadow_leaf_boxes", "extend_wide_rays", "shadow_wide_rays")]
 
 
 class CameraDesc(C.Structure):
@@ -72,6 +73,7 @@ def library() -> capi.Library:
         L.obpt_store_half.argtypes, L.obpt_store_half.restype = [C.c_float], C.c_float
         L.obpt_gbuffer_roundtrip.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32)]
         L.obpt_gbuffer_roundtrip.restype = None
+        L.obpt_set_wide_from_bounce.argtypes, L.obpt_set_wide_from_bounce.restype = [C.c_void_p, C.c_uint32], C.c_int
         L.obpt_wide_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.obpt_wide_stats.restype = C.c_int
         L.obpt_morton63.argtypes, L.obpt_morton63.restype = [C.c_void_p, C.c_void_p, C.c_void_p], C.c_uint64
@@ -95,6 +97,12 @@ class OracleContext(capi.Context):
         s = Stats()
         self._call("get_stats", C.byref(s))
         return s
+
+    def set_wide_from_bounce(self, bounce: int):
+        """Bounces >= bounce walk the 4-wide quantised tree (what the CUDA kernels do with 2); 0 = binary everywhere."""
+        st = library().lib.obpt_set_wide_from_bounce(self._h, bounce)
+        if st != 0:
+            raise capi.BptError(st, "obpt_set_wide_from_bounce", "")
 
     def wide_stats(self, rays, width=4, quantised=True, order=0):
         """Closest hits through a `width`-ary collapse of the merged BVH + work counters (oracle_wide.cpp).

@@ -300,7 +300,7 @@ static f4 calc_ddgi_volume_lighting(const obpt_context& ctx, f3 pos, f3 normal, 
 struct ThreadOut {
     TraceStats ext, shd;
     uint64_t ext_per_bounce[16] = {0}, shd_per_bounce[16] = {0};
-    uint64_t shaded = 0, missed = 0, pixel_samples = 0;
+    uint64_t shaded = 0, missed = 0, pixel_samples = 0, ext_wide_rays = 0, shd_wide_rays = 0;
     struct CapE { uint32_t bounce, pixel; bpt_hit hit; };
     struct CapS { uint32_t bounce, pixel, light; };
     std::vector<CapE> cap_e;
@@ -345,7 +345,9 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
     for (uint32_t i = 1; i < B; i++) {
         const f3 Wl = fp16 ? splat3(1.0f) : Wt;  // fp16: the light terms are summed unweighted, `commit` applies the throughput
         out.ext_per_bounce[i]++;
-        HitRec h = trace_closest(sc, O, D, 0.001f, st.ray_length, frame_index, out.ext);   // rt_gbuffer.hlsl:17-25
+        const bool wide = sc.wide_from_bounce != 0 && i >= sc.wide_from_bounce;           // which tree the CUDA kernels walk at this bounce
+        if (wide) { out.ext_wide_rays++; }
+        HitRec h = trace_closest(sc, O, D, 0.001f, st.ray_length, frame_index, out.ext, wide);   // rt_gbuffer.hlsl:17-25
         if (ctx.capture) out.cap_e.push_back({i, pixel, bpt_hit{h.t, h.u, h.v, h.hit ? h.instance_id : 0xffffffffu, h.hit ? h.prim : 0xffffffffu}});
         if (i == 1 && first_t) *first_t = h.hit ? h.t : -1.0f;
         if (!h.hit) {                                                                       // deferred_lighting_secondary.hlsl:24-29
@@ -393,7 +395,8 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             if (st.nee_mode == BPT_NEE_NONE) { out.pending.push_back(c); return; }
             out.shd_per_bounce[i]++;
             if (ctx.capture) out.cap_s.push_back({i, pixel, light_index});
-            if (!trace_any(sc, P, L, 0.001f, tmax, frame_index, out.shd)) out.pending.push_back(c);
+            if (wide) out.shd_wide_rays++;
+            if (!trace_any(sc, P, L, 0.001f, tmax, frame_index, out.shd, false, wide)) out.pending.push_back(c);
         };
         for (size_t l = 0; l < sc.rect_lights.size(); l++) {                                // deferred_lighting_secondary.hlsl:72-96
             const bpt_rect_light_data& rl = sc.rect_lights[l];
@@ -410,7 +413,8 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             out.shd_per_bounce[i]++;
             uint32_t light_index = (uint32_t)(sc.dir_lights.size() + sc.point_lights.size() + l);
             if (ctx.capture) out.cap_s.push_back({i, pixel, light_index});
-            if (!trace_any(sc, P, mrp, 0.001f, (dist / step) * 0.999f, frame_index, out.shd)) out.pending.push_back(c);
+            if (wide) out.shd_wide_rays++;
+            if (!trace_any(sc, P, mrp, 0.001f, (dist / step) * 0.999f, frame_index, out.shd, false, wide)) out.pending.push_back(c);
         }
         // Probe paths: the previous DDGI update at the path's last vertex (ddgi/deferred_lighting.hlsl:102-115). The reference
         // traces one bounce, so every probe-ray hit receives it; with more bounces it closes the path.
@@ -515,6 +519,9 @@ static void render_impl(obpt_context& ctx, const bpt_camera& cam, uint32_t first
     ctx.counters.extend_rays += ext.rays; ctx.counters.shadow_rays += shd.rays;
     ctx.stats.extend_rays += ext.rays; ctx.stats.extend_nodes += ext.nodes; ctx.stats.extend_tris += ext.tris; ctx.stats.extend_instances += ext.instances;
     ctx.stats.shadow_rays += shd.rays; ctx.stats.shadow_nodes += shd.nodes; ctx.stats.shadow_tris += shd.tris; ctx.stats.shadow_instances += shd.instances;
+    ctx.stats.extend_wide_nodes += ext.wide_nodes; ctx.stats.extend_leaf_boxes += ext.leaf_boxes;
+    ctx.stats.shadow_wide_nodes += shd.wide_nodes; ctx.stats.shadow_leaf_boxes += shd.leaf_boxes;
+    for (auto& o : outs) { ctx.stats.extend_wide_rays += o.ext_wide_rays; ctx.stats.shadow_wide_rays += o.shd_wide_rays; }
     if (ctx.capture) {
         uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);
         ctx.cap_extend_pixels.assign(B, {}); ctx.cap_extend_hits.assign(B, {});
@@ -754,6 +761,13 @@ bpt_status obpt_debug_read_queue(obpt_context* c, uint32_t bounce, uint32_t kind
     if (pixels) std::copy(px[bounce].begin(), px[bounce].end(), pixels);
     if (kind == 0 && hits) std::copy(c->cap_extend_hits[bounce].begin(), c->cap_extend_hits[bounce].end(), hits);
     if (kind == 1 && lights) std::copy(c->cap_shadow_lights[bounce].begin(), c->cap_shadow_lights[bounce].end(), lights);
+    return BPT_OK;
+}
+bpt_status obpt_set_wide_from_bounce(obpt_context* c, uint32_t bounce) {
+    CHECK_CTX(c);
+    if (bounce && (!c->scene.accel_built || c->scene.accel_mode != BPT_ACCEL_MERGED)) return fail(c, BPT_ERR_STATE, "set_wide_from_bounce needs a built merged accel");
+    if (bounce && c->scene.blas[0].wide.empty()) build_wide4(c->scene.blas[0]);
+    c->scene.wide_from_bounce = bounce;
     return BPT_OK;
 }
 bpt_status obpt_set_ddgi_volume(obpt_context* c, const bpt_probe_volume* vol, const bpt_probe_blend* bl, const float* irr, const float* vis) {

@@ -23,7 +23,12 @@ struct Bvh {
     int32_t root = 0;                  // 0, or ~0 when n == 1
     f3 lo{0, 0, 0}, hi{0, 0, 0};       // root bounds
     std::vector<Tri> tris;             // BLAS only, sorted order
+    // 4-wide quantised form of this tree (oracle_wide.cpp; merged mode, built on demand): node i = subtree of binary node i,
+    // boxes already decoded to the planes the traversal tests
+    struct Wide4 { int nchild; int32_t child[4]; f3 clo[4], chi[4]; };
+    std::vector<Wide4> wide;
 };
+void build_wide4(Bvh& b);
 
 struct Texture {
     uint32_t w = 0, h = 0, format = 0, addr_u = 0, addr_v = 0, linear = 1;
@@ -38,7 +43,8 @@ struct InstanceXf {      // derived per instance at build time
 
 struct TraceStats {
     uint64_t rays = 0, nodes = 0, tris = 0, instances = 0;
-    void add(const TraceStats& o) { rays += o.rays; nodes += o.nodes; tris += o.tris; instances += o.instances; }
+    uint64_t wide_nodes = 0, leaf_boxes = 0;      // steps through the 4-wide tree and exact leaf-box tests (rays traced with wide = true)
+    void add(const TraceStats& o) { rays += o.rays; nodes += o.nodes; tris += o.tris; instances += o.instances; wide_nodes += o.wide_nodes; leaf_boxes += o.leaf_boxes; }
 };
 
 struct Scene {
@@ -61,6 +67,7 @@ struct Scene {
 
     // accel
     bool accel_built = false;
+    uint32_t wide_from_bounce = 0;   // obpt_set_wide_from_bounce: bounces >= this walk the 4-wide tree (0 = never; merged mode only)
     uint32_t accel_mode = 0;
     std::vector<Bvh> blas;
     Bvh tlas;
@@ -91,8 +98,10 @@ static inline f3 xf_vector_transposed(const float m[12], f3 v) {
 }
 
 struct HitRec { float t, u, v; uint32_t inst_slot, instance_id, prim; bool hit; };
-HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st);
-bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool cull_non_opaque = false);
+// wide = true (merged mode with sc.blas[0].wide built): walk the 4-wide quantised tree like the CUDA kernels do from the second
+// bounce on. Same hits by construction (oracle_wide.cpp header); only the work counters differ.
+HitRec trace_closest(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool wide = false);
+bool trace_any(const Scene& sc, f3 O, f3 D, float tmin, float tmax, uint32_t frame_index, TraceStats& st, bool cull_non_opaque = false, bool wide = false);
 
 // oracle_render.cpp helpers used by traversal (any-hit opacity)
 float eval_opacity(const Scene& sc, uint32_t instance_id, uint32_t prim, float u, float v);

@@ -116,6 +116,21 @@ static void collapse_all(const Bvh& b, int W, bool quant, WideBvh& out) {
     for (uint32_t i = 0; i + 1 < b.n; i++) out.nodes[i] = collapse_one(b, (int32_t)i, W, quant);
 }
 
+} // namespace orc
+// Fills b.wide (declared in oracle_scene.hpp) with the decoded 4-wide quantised nodes, one per binary node.
+void orc::build_wide4(Bvh& b) {
+    b.wide.clear();
+    if (b.n < 2) return;
+    b.wide.resize(b.n - 1);
+    for (uint32_t i = 0; i + 1 < b.n; i++) {
+        WideNode w = collapse_one(b, (int32_t)i, 4, true);
+        Bvh::Wide4& o = b.wide[i];
+        o.nchild = w.nchild;
+        for (int k = 0; k < 4; k++) { o.child[k] = k < w.nchild ? w.child[k] : 0; o.clo[k] = w.clo[k]; o.chi[k] = w.chi[k]; }
+    }
+}
+namespace orc {
+
 struct WideCounts { uint64_t rays = 0, nodes = 0, tris = 0, boxes = 0, leaf_boxes = 0; };
 
 static inline bool slab(f3 lo, f3 hi, f3 idir, f3 ood, float tmin, float tcull, float& tnear) {

@@ -252,3 +252,32 @@ def test_empty_and_edge_inputs(oracle):
     # max_bounces is clamped to [2, 16] (path_tracing.cpp:290)
     ctx.render(oracle.camera_matrices(sc.camera, 4, 4), 0, 1, capi.Settings(max_bounces=0))
     assert ctx.counters().extend_rays_per_bounce[1] == 16 and ctx.counters().extend_rays_per_bounce[2] == 0
+
+
+def test_wide_tree_render_is_identical(oracle):
+    """The oracle can walk the 4-wide quantised tree from any bounce on (what the CUDA kernels do from bounce 2): image, ray counts
+    and queue contents are unchanged — only the work counters differ (fewer node steps, an exact leaf-box test per proposed leaf)."""
+    from bisemutum_engine_b200 import capi, scenes
+    scene = scenes.small_test_scene()
+    W, H = 48, 32
+    cam = oracle.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=6)
+    a = oracle.OracleContext(W, H); a.upload_scene(scene, capi.ACCEL_MERGED)
+    b = oracle.OracleContext(W, H); b.upload_scene(scene, capi.ACCEL_MERGED)
+    b.set_wide_from_bounce(2)
+    a.render(cam, 0, 3, st); b.render(cam, 0, 3, st)
+    np.testing.assert_array_equal(a.resolve(3), b.resolve(3))
+    ca, cb = a.counters(), b.counters()
+    assert ca.extend_rays == cb.extend_rays and ca.shadow_rays == cb.shadow_rays
+    sa, sb = a.stats(), b.stats()
+    assert sa.extend_wide_nodes == 0 and sb.extend_wide_nodes > 0 and sb.extend_wide_rays == cb.extend_rays - W * H * 3
+    # (the visiting ORDER differs, so the cull distance at the time a leaf is proposed does too: the number of triangle tests moves by a fraction of a percent)
+    assert abs(sa.extend_tris - sb.extend_tris) < 0.02 * sa.extend_tris and sb.extend_leaf_boxes > 0
+    per_ray_bin = (sa.extend_nodes - sb.extend_nodes) / sb.extend_wide_rays                       # binary steps those rays took before
+    per_ray_wide = sb.extend_wide_nodes / sb.extend_wide_rays
+    assert per_ray_wide < 0.7 * per_ray_bin
+    b.set_wide_from_bounce(1); b.clear_accum(); b.render(cam, 0, 3, st)
+    np.testing.assert_array_equal(a.resolve(3), b.resolve(3))
+    two = oracle.OracleContext(W, H); two.upload_scene(scene, capi.ACCEL_TWO_LEVEL)
+    with pytest.raises(capi.BptError):
+        two.set_wide_from_bounce(2)                                                               # merged mode only
