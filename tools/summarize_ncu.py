@@ -89,10 +89,14 @@ def full(rep, traffic_out=None):
               f"{f(d, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} |")
     print("\n(units as exported by ncu: time " + units["gpu__time_duration.sum"] + ", dram " + units["dram__bytes_read.sum"] + ")")
     print("\n## Detail: first extend, first shade, first connect\n")
-    firsts = []
+    firsts, heads = [], []
     for want in ("k_trace_spec (extend)", "k_shade", "k_trace_spec (connect)"):
-        firsts.append(next(d for d in rows if short(d["Kernel Name"]) == want))
-    print("| metric | unit | extend #0 | shade #0 | connect #0 |\n|---|---|---|---|---|")
+        hit = [d for d in rows if short(d["Kernel Name"]) == want]
+        if hit:
+            firsts.append(hit[0]); heads.append(want + " #0")
+            if want == "k_trace_spec (extend)" and len(hit) > 1:
+                firsts.append(hit[1]); heads.append(want + " #1")
+    print("| metric | unit | " + " | ".join(heads) + " |\n|---|---|" + "---|" * len(heads))
     for m in RAW:
         if m in firsts[0]:
             print(f"| `{m}` | {units.get(m, '')} | " + " | ".join(d[m] for d in firsts) + " |")
