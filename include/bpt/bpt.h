@@ -289,8 +289,10 @@ enum { BPT_RECT_SHADOW_OFF = 0, BPT_RECT_SHADOW_MRP_RAY = 1 };
 enum { BPT_STATE_FP32 = 0, BPT_STATE_REFERENCE_FP16 = 1 };
 
 /* BasicRenderer::PathTracingSettings (renderer/basic.hpp:76-81) + the mode switches of
- * SURVEY.md §0. Defaults (all-zero switches) are the parity configuration. Implemented: nee_mode,
- * rect_shadow, russian_roulette, pixel_jitter; state_precision = reference_fp16 returns BPT_ERR_UNSUPPORTED. */
+ * SURVEY.md §0. Defaults (all-zero switches) are the parity configuration. All are implemented.
+ * state_precision = reference_fp16 applies the reference's texture formats to every value it passes between passes
+ * (half ray directions / throughput / colours, the packed G-buffer, the half additive blit, the running half lerp of
+ * pt_accumulate.hlsl); the accumulation buffer then follows that rule until bpt_clear_accum (mixing: BPT_ERR_STATE). */
 typedef struct bpt_settings {
     float ray_length;        /* 100 */
     uint32_t max_bounces;    /* clamped to [2,16] as path_tracing.cpp:187,290 */
