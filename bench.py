@@ -212,7 +212,9 @@ def main():
     build_ms = (time.perf_counter() - t0) * 1e3
     cam = engine.camera_matrices(scene.camera, W, H)
     st = capi.Settings(ray_length=RAY_LENGTH, max_bounces=B)
-    reduce_buf = torch.zeros(H, W, 4, dtype=torch.float32, device="cuda")
+    if world > 1:
+        sharding.comm_init(ctx, torch.device("cuda", local_rank))     # the library's own NCCL communicator (bpt_comm_init)
+        ctx.reduce(0); ctx.sync()                                       # first collective sets the rings up, outside the timed region
 
     def barrier():
         if world > 1:
@@ -230,9 +232,8 @@ def main():
     barrier()
     ev0.record(stream)
     ctx.render(cam, sharding.first_frame(args.steps, rank, world), args.steps, st)     # K steps = K frames of 1 spp
-    if world > 1:   # the one exchange step: FP32 sum buffers → rank 0 (one NCCL reduce per batch of frames)
-        ctx.resolve_device(1, reduce_buf.data_ptr())
-        sharding.reduce_sums(reduce_buf, dst=0)
+    if world > 1:   # the one exchange step: FP32 sum buffers → rank 0 (one NCCL reduce per batch of frames, issued by the library)
+        ctx.reduce(0)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()

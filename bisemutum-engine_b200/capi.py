@@ -190,6 +190,11 @@ BPT_ONLY_API = {
     "render_ahead": [_VP, C.POINTER(Camera), _U32, _U32, C.POINTER(Settings), _PU32],
     "accumulate_ahead": [_VP, _U32],
     "pending_ahead": [_VP, _PU32, _PU32],
+    "comm_unique_id": [_VP],
+    "comm_init": [_VP, _VP, C.c_int, C.c_int],
+    "comm_attach": [_VP, _VP],
+    "comm_destroy": [_VP],
+    "reduce": [_VP, C.c_int],
     "profile_enable": [_VP, _U32],
     "profile_read": [_VP, C.POINTER(KernelTimes)],
 }
@@ -217,6 +222,14 @@ class Library:
 
     def fn(self, name):
         return getattr(self.lib, self.prefix + name)
+
+    def comm_unique_id(self) -> bytes:
+        """128-byte NCCL unique id (bpt_comm_unique_id): rank 0 creates it and hands it to every rank."""
+        buf = (C.c_uint8 * 128)()
+        st = self.fn("comm_unique_id")(C.cast(buf, C.c_void_p))
+        if st != 0:
+            raise BptError(st, self.prefix + "comm_unique_id", "NCCL could not be loaded" if st == 6 else "")
+        return bytes(buf)
 
 
 class Context:
@@ -437,6 +450,16 @@ class Context:
 
     def resolve_device(self, total_samples: int, device_ptr: int):
         self._call("resolve_device", total_samples, _VP(device_ptr))
+
+    def comm_init(self, unique_id: bytes, rank: int, world_size: int):
+        """Joins the NCCL communicator identified by `unique_id` (128 bytes from Library.comm_unique_id() on rank 0)."""
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._call("comm_init", C.cast(buf, C.c_void_p), rank, world_size)
+
+    def reduce(self, root: int = 0):
+        """In-place NCCL sum of every rank's FP32 accumulation buffer into `root` (stream-ordered)."""
+        self._call("reduce", root)
 
     def profile_enable(self, enable: bool):
         self._call("profile_enable", 1 if enable else 0)

@@ -59,6 +59,38 @@ DScene bpt_context::scene_view() const {
 static bpt_status fail(bpt_context* c, bpt_status s, const char* msg) { c->err = msg; return s; }
 #define NEED(c) do { if (!(c)) return BPT_ERR_INVALID; cudaSetDevice((c)->device); } while (0)
 
+// ---- NCCL, loaded at run time so that libbpt.so has no link-time dependency on it (single-GPU hosts need none) -------------
+#include <dlfcn.h>
+namespace {
+struct NcclId { char internal[128]; };        // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128), passed BY VALUE to ncclCommInitRank
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) return a;
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.lib, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.lib, "ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.lib, "ncclCommDestroy"));
+        a.Reduce = reinterpret_cast<decltype(a.Reduce)>(dlsym(a.lib, "ncclReduce"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.lib, "ncclGetErrorString"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Reduce && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;      // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since NCCL 2.0)
+} // namespace
+
 extern "C" {
 
 const char* bpt_version(void) { return "bpt 0.1 (sm_100a)"; }
@@ -83,6 +115,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     if (!c) return BPT_OK;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->nccl_comm && c->nccl_owned) nccl().CommDestroy(c->nccl_comm);
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
                       &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
@@ -290,6 +323,51 @@ bpt_status bpt_debug_read_bvh(bpt_context* c, uint32_t which, uint32_t* np, uint
     if (morton) BPT_CUDA_TRY(c, cudaMemcpy(morton, b->morton.p, (size_t)b->n * 8, cudaMemcpyDeviceToHost));
     if (prims) BPT_CUDA_TRY(c, cudaMemcpy(prims, b->prims.p, (size_t)b->n * 4, cudaMemcpyDeviceToHost));
     if (nodes && b->n >= 2) BPT_CUDA_TRY(c, cudaMemcpy(nodes, b->nodes.p, (size_t)(b->n - 1) * 64, cudaMemcpyDeviceToHost));
+    return BPT_OK;
+}
+
+bpt_status bpt_comm_unique_id(uint8_t out_id[BPT_COMM_UNIQUE_ID_BYTES]) {
+    if (!out_id) return BPT_ERR_INVALID;
+    if (!nccl().ok) return BPT_ERR_UNSUPPORTED;
+    NcclId id;
+    if (nccl().GetUniqueId(&id) != 0) return BPT_ERR_CUDA;
+    memcpy(out_id, id.internal, BPT_COMM_UNIQUE_ID_BYTES);
+    return BPT_OK;
+}
+bpt_status bpt_comm_destroy(bpt_context* c) {
+    NEED(c);
+    if (c->nccl_comm && c->nccl_owned) { cudaStreamSynchronize(c->stream); nccl().CommDestroy(c->nccl_comm); }
+    c->nccl_comm = nullptr; c->nccl_owned = false;
+    return BPT_OK;
+}
+bpt_status bpt_comm_init(bpt_context* c, const uint8_t id[BPT_COMM_UNIQUE_ID_BYTES], int rank, int world) {
+    NEED(c);
+    if (!id || world < 1 || rank < 0 || rank >= world) return BPT_ERR_INVALID;
+    if (!nccl().ok) return fail(c, BPT_ERR_UNSUPPORTED, "comm_init: libnccl.so.2 could not be loaded");
+    bpt_comm_destroy(c);
+    NcclId uid;
+    memcpy(uid.internal, id, 128);
+    void* comm = nullptr;
+    int r = nccl().CommInitRank(&comm, world, uid, rank);
+    if (r != 0) { c->err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(r); return BPT_ERR_CUDA; }
+    c->nccl_comm = comm; c->nccl_owned = true;
+    return BPT_OK;
+}
+bpt_status bpt_comm_attach(bpt_context* c, void* comm) {
+    NEED(c);
+    if (!comm) return BPT_ERR_INVALID;
+    if (!nccl().ok) return fail(c, BPT_ERR_UNSUPPORTED, "comm_attach: libnccl.so.2 could not be loaded");
+    bpt_comm_destroy(c);
+    c->nccl_comm = comm; c->nccl_owned = false;
+    return BPT_OK;
+}
+bpt_status bpt_reduce(bpt_context* c, int root) {
+    NEED(c);
+    if (!c->nccl_comm) return fail(c, BPT_ERR_STATE, "reduce: no communicator (bpt_comm_init / bpt_comm_attach)");
+    if (c->wf.accum_fp16) return fail(c, BPT_ERR_STATE, "reduce: the reference_fp16 running average cannot be summed across GPUs");
+    const size_t count = (size_t)c->width * c->height * 4;
+    int r = nccl().Reduce(c->wf.accum.p, c->wf.accum.p, count, kNcclFloat32, kNcclSum, root, c->nccl_comm, c->stream);
+    if (r != 0) { c->err = std::string("ncclReduce: ") + nccl().GetErrorString(r); return BPT_ERR_CUDA; }
     return BPT_OK;
 }
 

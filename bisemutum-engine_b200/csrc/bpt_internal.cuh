@@ -49,6 +49,7 @@ struct bpt_context {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    void* nccl_comm = nullptr; bool nccl_owned = false;   // bpt_comm_init / bpt_comm_attach (NCCL is dlopen'ed, see bpt_api.cu)
     bool accum_used = false;    // a render has added to wf.accum since the last bpt_clear_accum
 
     // host copies needed for validation / rebuilds

@@ -38,3 +38,17 @@ def resolve(sum_buffer: torch.Tensor, total_samples: int) -> torch.Tensor:
     out = sum_buffer * (1.0 / float(total_samples))
     out[..., 3] = 1.0
     return out
+
+
+def comm_init(ctx, device: torch.device | None = None) -> None:
+    """Gives `ctx` (a capi.Context of the CUDA library) its own NCCL communicator over the ranks of the current
+    torch.distributed group: rank 0 draws the unique id (bpt_comm_unique_id), torch.distributed only carries its 128 bytes.
+    Afterwards ctx.reduce(root) is the one exchange step of SURVEY §8e, issued by the library on its own stream."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(ctx.L.comm_unique_id()), dtype=torch.uint8).clone()
+    if device is not None and dist.get_backend() == "nccl":
+        uid = uid.to(device)
+    dist.broadcast(uid, src=0)
+    ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)

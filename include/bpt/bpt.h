@@ -352,6 +352,23 @@ BPT_API bpt_status bpt_profile_enable(bpt_context* ctx, uint32_t enable);
 BPT_API bpt_status bpt_profile_read(bpt_context* ctx, bpt_kernel_times* out); /* synchronises, then resets */
 
 /* ---------------------------------------------------------------------------------------
+ * Multi-GPU: samples shard by frame_index, scene + BVH are replicated, and ONE reduce of the
+ * W x H x 4 FP32 sum buffers per batch of frames is the only exchange. One process (and one bpt_context) per GPU.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2"); nothing here is needed for single-GPU use.
+ *   rank 0: bpt_comm_unique_id -> send the 128 bytes to every rank by any means (MPI, torch.distributed, a file);
+ *   every rank: bpt_comm_init(ctx, id, rank, world), or bpt_comm_attach with an ncclComm_t the host already owns;
+ *   per batch: bpt_render(...) with this rank's frames, then bpt_reduce(ctx, root): in-place ncclReduce(sum) of the
+ *   accumulation buffer to `root`, stream-ordered on the context's stream; root then calls bpt_resolve(total samples).
+ * state_precision = reference_fp16 cannot be reduced (a running lerp is order-dependent): BPT_ERR_STATE.
+ * ------------------------------------------------------------------------------------- */
+#define BPT_COMM_UNIQUE_ID_BYTES 128
+BPT_API bpt_status bpt_comm_unique_id(uint8_t out_id[BPT_COMM_UNIQUE_ID_BYTES]);
+BPT_API bpt_status bpt_comm_init(bpt_context* ctx, const uint8_t id[BPT_COMM_UNIQUE_ID_BYTES], int rank, int world_size);
+BPT_API bpt_status bpt_comm_attach(bpt_context* ctx, void* nccl_comm /* ncclComm_t, stays owned by the caller */);
+BPT_API bpt_status bpt_comm_destroy(bpt_context* ctx);
+BPT_API bpt_status bpt_reduce(bpt_context* ctx, int root);
+
+/* ---------------------------------------------------------------------------------------
  * Debug / parity hooks
  * ------------------------------------------------------------------------------------- */
 typedef struct bpt_ray {       /* 32 B */

@@ -394,6 +394,26 @@ def test_ddgi_volume_lighting_and_feedback(lib, oracle):
         gpu.ddgi_lighting(pos[:4], nrm[:4], view[:4])                                        # nothing bound
 
 
+def test_library_reduce_single_rank(lib, oracle):
+    """bpt_comm_unique_id / bpt_comm_init / bpt_reduce with a one-rank communicator: NCCL loads, the reduce is the identity, the
+    fp16 running average refuses it. (The N >= 2 check is tools/check_reduce.py under torchrun; the CPU suite covers the sharding
+    arithmetic with gloo.)"""
+    scene = scenes.small_test_scene()
+    W, H = 64, 48
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_MERGED)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=4)
+    with pytest.raises(capi.BptError):
+        gpu.reduce(0)                                                        # no communicator yet
+    gpu.comm_init(lib.comm_unique_id(), 0, 1)
+    gpu.render(cam, 0, 2, st); ref.render(cam, 0, 2, st)
+    gpu.reduce(0); gpu.sync()
+    np.testing.assert_array_equal(gpu.resolve(2), ref.resolve(2))
+    gpu.clear_accum(); gpu.render(cam, 0, 1, capi.Settings(max_bounces=4, state_precision=capi.STATE_REFERENCE_FP16))
+    with pytest.raises(capi.BptError):
+        gpu.reduce(0)
+
+
 def test_reference_fp16_host_pass(lib, oracle):
     """The frame-at-a-time host pass (render_ahead / accumulate_ahead) follows the same running lerp."""
     scene = scenes.small_test_scene()
