@@ -698,10 +698,14 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
 
 // Which traversal kernel serves the current acceleration structure: merged mode uses the 4-wide quantised tree when it was
 // built (always, unless BPT_WIDE=0 asks for the binary tree — kept for A/B measurements), two-level mode the binary trees.
-static bool use_wide(const bpt_context* ctx, uint32_t bounce = 99) {
+// (both from bounce 2: camera rays and the shadow rays of camera-ray hits are coherent — a warp fetches 32 neighbouring pixels'
+// rays towards the same light — and issue-bound, so the binary tree is faster for them. Measured: extend wide from bounce 1 / 2 /
+// 3 -> 1.838 / 1.725 / 1.774 ms per configs[1] frame; connect wide from 1 vs 2: equal on configs[1], 22.65 vs 22.12 ms on configs[2].)
+static bool use_wide(const bpt_context* ctx, uint32_t bounce = 99, bool connect = false) {
     static const bool enabled = [] { const char* e = getenv("BPT_WIDE"); return !e || atoi(e) != 0; }();
     static const uint32_t from_bounce = [] { const char* e = getenv("BPT_WIDE_FROM_BOUNCE"); return e ? (uint32_t)atoi(e) : 2u; }();
-    return enabled && bounce >= from_bounce && ctx->accel_mode == BPT_ACCEL_MERGED && ctx->blas[0].wide.p != nullptr;
+    static const uint32_t connect_from = [] { const char* e = getenv("BPT_WIDE_CONNECT_FROM_BOUNCE"); return e ? (uint32_t)atoi(e) : 2u; }();
+    return enabled && bounce >= (connect ? connect_from : from_bounce) && ctx->accel_mode == BPT_ACCEL_MERGED && ctx->blas[0].wide.p != nullptr;
 }
 static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     WavefrontState& wf = ctx->wf;
@@ -712,7 +716,7 @@ static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t 
 }
 static bpt_status launch_connect(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     WavefrontState& wf = ctx->wf;
-    if (use_wide(ctx, i)) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i);
+    if (use_wide(ctx, i, true)) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i);
     else if (ctx->accel_mode == BPT_ACCEL_MERGED) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
     else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
     return BPT_OK;
