@@ -30,6 +30,23 @@ for sc in (scene, basic):
         r = ctx.trace_probes(vol, tab, 0, 2)
         irr, vis = ctx.blend_probes(vol, tab, 0, r)
         ctx.blend_probes(vol, tab, 1, r, irr, vis)
+        # added after the first sanitizer run: DDGI consumer + feedback, fp16 state mode, primary outputs, RTAO (the merged
+        # mode runs all of these through the 4-wide tree kernels from bounce 2 on)
+        ctx.set_ddgi_volume(vol, irr, vis)
+        ctx.trace_probes(vol, tab, 1, 2)
+        pts = np.float32(np.random.default_rng(0).uniform(-3, 3, (64, 3))); up = np.float32(np.tile([0, 1, 0], (64, 1)))
+        ctx.ddgi_lighting(pts, up, up)
+        ctx.set_ddgi_volume(None)
+        ctx.clear_accum()
+        ctx.render(cam, 0, 2, capi.Settings(max_bounces=4, state_precision=capi.STATE_REFERENCE_FP16))
+        assert np.isfinite(ctx.resolve(2)).all()
+        ctx.clear_accum()
+        depth, g = ctx.render_primary(cam, 0, capi.Settings(max_bounces=4))
+        ctx.trace_ao(cam, 1, depth, g["normal_roughness"], 0.5, 0.5, True)
+        ctx.trace_ao(cam, 2, depth, g["normal_roughness"], 0.5, 0.5, False)
+        if mode == capi.ACCEL_MERGED:
+            ctx.read_wide()
+            ctx.comm_init(lib.comm_unique_id(), 0, 1); ctx.render(cam, 0, 1, capi.Settings(max_bounces=3)); ctx.reduce(0); ctx.sync()
         ctx.close()
 r = engine.Renderer(W, H); r.set_scene(scene, capi.ACCEL_MERGED)
 for _ in range(3):
