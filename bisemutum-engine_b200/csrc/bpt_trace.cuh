@@ -16,7 +16,9 @@
 
 namespace bptd {
 
-constexpr int kStackSize = 160;           // Karras depth bound: 63 code bits + 32 index bits per level
+// Karras depth bound: 63 code bits + 32 index bits = 95 levels. The binary traversal holds at most one entry per level; a step of the
+// 4-wide tree pushes up to three nodes and may descend a single binary level, hence 3 x 95 + 1 (only touched entries cost anything).
+constexpr int kStackSize = 288;
 constexpr int32_t kSentinel = (int32_t)0x80000000;
 
 struct TraceResult {
