@@ -135,7 +135,8 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 // continue at the BLAS root — and only triangles are postponed. A lane never leaves an instance (pops the
 // sentinel) while it still holds postponed triangles of that instance: they need its object-space ray.
 // Resident blocks per SM of the traversal kernels = the register budget: 8 -> 64 registers, 10 -> 48 (a few bytes of spills), 12 -> 40
-// (1 KB of spills). With the binary tree only, 8 was best (10: extend -2 %, connect +4 %). With the wide tree and the re-tuned phase
+// (1 KB of spills). The two-level kernels carry more state and stay at 8 (at 10: atrium two-level 1427 -> 1089, instanced 680 -> 536
+// Mrays/s). Merged mode with the binary tree only: 8 was best (10: extend -2 %, connect +4 %). With the wide tree and the re-tuned phase
 // thresholds, whole frame: (binary, wide) = (8, 8) 1.690, (8, 10) 1.680, (8, 12) 1.700, (9, 9) 1.666, (10, 10) 1.665, (10, 12) 1.685 ms.
 #ifndef BPT_TRACE_MIN_BLOCKS
 #define BPT_TRACE_MIN_BLOCKS 10
@@ -146,7 +147,7 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 // WIDE (merged mode only): the node phase steps through the 4-wide quantised tree (a.m_wide) instead of the binary one, and a
 // proposed triangle is tested only if the ray passes that leaf's exact box (bpt_wide.cuh: same hits, about half the node fetches).
 template <bool ANY, bool TWO_LEVEL, bool WIDE = false>
-__global__ void __launch_bounds__(kBlock, WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : BPT_TRACE_MIN_BLOCKS) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+__global__ void __launch_bounds__(kBlock, WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : (TWO_LEVEL ? 8 : BPT_TRACE_MIN_BLOCKS)) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     static_assert(!(WIDE && TWO_LEVEL), "the wide tree exists for the merged BVH only");
     const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
     uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
