@@ -102,6 +102,82 @@ def drawable_world_aabbs(scene) -> np.ndarray:
     return out
 
 
+class ProjectInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("num_drawables", "num_blas", "num_materials", "num_textures", "num_dir_lights", "num_point_lights",
+                                          "num_rect_lights", "target_width", "target_height")] + \
+               [("camera", HostCameraDesc), ("ray_length", C.c_float), ("max_bounces", C.c_uint32), ("accumulate", C.c_uint32),
+                ("ambient_occlusion", capi.AoSettings)]
+
+
+class Project:
+    """A bisemutum project directory (project.toml, asset_metadata.toml, scene.toml, materials/*.toml, *.biasset) loaded by the C++
+    host library (host/project.cpp) — the headless stand-in for the reference's asset manager + ECS deserialisation."""
+    _ARRAYS = {"positions": (0, np.float32), "normals": (1, np.float32), "tangents": (2, np.float32), "texcoords": (3, np.float32),
+               "indices": (4, np.uint32), "blas": (5, capi.BLAS_DESC), "drawables": (6, capi.DRAWABLE_SBT), "instances": (7, capi.INSTANCE_DESC),
+               "materials": (8, capi.MATERIAL), "dir_lights": (9, capi.DIR_LIGHT), "point_lights": (10, capi.POINT_LIGHT), "rect_lights": (11, capi.RECT_LIGHT)}
+
+    def __init__(self, directory: str):
+        h = host_library()
+        h.bpt_host_project_load.argtypes, h.bpt_host_project_load.restype = [C.c_char_p, C.c_char_p, C.c_uint64], C.c_void_p
+        h.bpt_host_project_free.argtypes = [C.c_void_p]
+        h.bpt_host_project_get_info.argtypes = [C.c_void_p, C.POINTER(ProjectInfo)]
+        h.bpt_host_project_array.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        h.bpt_host_project_array.restype = C.c_void_p
+        h.bpt_host_project_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        h.bpt_host_project_error.argtypes, h.bpt_host_project_error.restype = [C.c_void_p], C.c_char_p
+        err = C.create_string_buffer(512)
+        self._h = h.bpt_host_project_load(directory.encode(), err, 512)
+        if not self._h:
+            raise RuntimeError(f"project {directory}: {err.value.decode()}")
+        self.info = ProjectInfo()
+        h.bpt_host_project_get_info(self._h, C.byref(self.info))
+
+    def array(self, name: str) -> np.ndarray:
+        which, dt = self._ARRAYS[name]
+        n = C.c_uint64()
+        p = host_library().bpt_host_project_array(self._h, which, C.byref(n), None, None, None)
+        return np.frombuffer((C.c_uint8 * n.value).from_address(p), dtype=dt).copy() if n.value else np.zeros(0, dt)
+
+    def texture(self, k: int):
+        """(texels (H, W, 4) uint8 for the 8-bit formats, rhi format id)."""
+        n, w, hh, f = C.c_uint64(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        p = host_library().bpt_host_project_array(self._h, 16 + k, C.byref(n), C.byref(w), C.byref(hh), C.byref(f))
+        raw = np.frombuffer((C.c_uint8 * n.value).from_address(p), dtype=np.uint8).copy()
+        return (raw.reshape(hh.value, w.value, 4) if f.value in (37, 43) else raw.view(np.float32).reshape(hh.value, w.value, 4)), f.value
+
+    def camera(self) -> dict:
+        c = self.info.camera
+        return dict(position=tuple(c.position), front_dir=tuple(c.front_dir), up_dir=tuple(c.up_dir), yfov=c.yfov, near_z=c.near_z, far_z=c.far_z,
+                    orthographic=bool(c.orthographic))
+
+    def scene_data(self):
+        """The loaded project as a scenes.SceneData (for contexts that upload through the Python path, e.g. the CPU oracle in tests)."""
+        from . import scenes
+        texs = []
+        for k in range(self.info.num_textures):
+            texels, fmt = self.texture(k)
+            texs.append({"texels": np.ascontiguousarray(texels), "width": texels.shape[1], "height": texels.shape[0],
+                         "format": {43: capi.TEXTURE_RGBA8_SRGB, 109: capi.TEXTURE_RGBA32_FLOAT}.get(fmt, capi.TEXTURE_RGBA8_UNORM),
+                         "address_u": capi.ADDRESS_REPEAT, "address_v": capi.ADDRESS_REPEAT, "linear": 1})
+        nd = self.info.num_drawables
+        va = np.full(nd, capi.VA_POSITION | capi.VA_NORMAL | capi.VA_TANGENT | capi.VA_TEXCOORD, np.uint32)
+        return scenes.SceneData(name="project", positions=self.array("positions"), normals=self.array("normals"), tangents=self.array("tangents"),
+                                texcoords=self.array("texcoords"), indices=self.array("indices"), drawables=self.array("drawables"), drawable_va=va,
+                                blas=self.array("blas"), instances=self.array("instances"), materials=self.array("materials"), textures=texs,
+                                dir_lights=self.array("dir_lights"), point_lights=self.array("point_lights"), rect_lights=self.array("rect_lights"),
+                                camera=self.camera())
+
+    def upload(self, ctx: capi.Context, accel_mode: int = capi.ACCEL_TWO_LEVEL):
+        st = host_library().bpt_host_project_upload(self._h, ctx._h, accel_mode)
+        if st != 0:
+            raise capi.BptError(st, "bpt_host_project_upload", host_library().bpt_host_project_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            host_library().bpt_host_project_free(self._h)
+            self._h = None
+
+
 class Renderer:
     """BasicRenderer in path-tracing mode, reduced to what the pass needs."""
 

@@ -1,6 +1,7 @@
 // host/c_exports.cpp — plain-C view of the host mirror for the Python harness (tests / bench).
 #include <cstring>
 #include "engine.hpp"
+#include "project.hpp"
 
 using namespace bi;
 
@@ -108,6 +109,74 @@ HOST_API int bpt_host_pass_read_primary(bpt_host_pass* p, float ray_length, uint
     p->camera.update_shader_params(p->frame);
     return (int)p->pass->read_primary_outputs(p->camera, s, depth, gbuffer);
 }
+// ---- headless project loading (host/project.hpp): the reference's project directory -> the C ABI's arrays ------------------------
+struct bpt_host_project { project::Project p; std::string err; };
+struct bpt_host_project_info {
+    uint32_t num_drawables, num_blas, num_materials, num_textures, num_dir_lights, num_point_lights, num_rect_lights;
+    uint32_t target_width, target_height;
+    bpt_host_camera_desc camera;
+    float ray_length; uint32_t max_bounces; uint32_t accumulate;
+    bpt_ao_settings ambient_occlusion;
+};
+HOST_API bpt_host_project* bpt_host_project_load(const char* dir, char* err, uint64_t err_len) {
+    auto* h = new bpt_host_project();
+    if (!project::load_project(dir, h->p, h->err)) {
+        if (err && err_len) { std::strncpy(err, h->err.c_str(), err_len - 1); err[err_len - 1] = 0; }
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+HOST_API void bpt_host_project_free(bpt_host_project* h) { delete h; }
+HOST_API void bpt_host_project_get_info(const bpt_host_project* h, bpt_host_project_info* o) {
+    const project::Project& p = h->p;
+    *o = bpt_host_project_info{};
+    o->num_drawables = (uint32_t)p.drawables.size(); o->num_blas = (uint32_t)p.blas.size(); o->num_materials = (uint32_t)p.materials.size();
+    o->num_textures = (uint32_t)p.textures.size(); o->num_dir_lights = (uint32_t)p.lights.dir_lights.size();
+    o->num_point_lights = (uint32_t)p.lights.point_lights.size(); o->num_rect_lights = (uint32_t)p.lights.rect_lights.size();
+    o->target_width = p.target_width; o->target_height = p.target_height;
+    for (int k = 0; k < 3; k++) { o->camera.position[k] = p.cam_position[k]; o->camera.front_dir[k] = p.cam_front[k]; o->camera.up_dir[k] = p.cam_up[k]; }
+    o->camera.yfov = p.yfov; o->camera.near_z = p.near_z; o->camera.far_z = p.far_z; o->camera.width = p.target_width; o->camera.height = p.target_height;
+    o->camera.orthographic = p.orthographic ? 1u : 0u;
+    o->ray_length = p.path_tracing.ray_length; o->max_bounces = p.path_tracing.max_bounces; o->accumulate = p.path_tracing.accumulate ? 1u : 0u;
+    o->ambient_occlusion = p.ambient_occlusion;
+}
+// which: 0 positions, 1 normals, 2 tangents, 3 texcoords, 4 indices, 5 blas descs, 6 drawables, 7 instances, 8 materials, 9 dir lights,
+// 10 point lights, 11 rect lights, 16 + k: texels of texture k. Returns the array and its size in BYTES (for tests and for hosts that upload themselves).
+HOST_API const void* bpt_host_project_array(const bpt_host_project* h, uint32_t which, uint64_t* bytes, uint32_t* width, uint32_t* height, uint32_t* format) {
+    const project::Project& p = h->p;
+    auto ret = [&](const void* d, size_t n) { *bytes = n; return d; };
+    switch (which) {
+        case 0: return ret(p.positions.data(), p.positions.size() * 4);
+        case 1: return ret(p.normals.data(), p.normals.size() * 4);
+        case 2: return ret(p.tangents.data(), p.tangents.size() * 4);
+        case 3: return ret(p.texcoords.data(), p.texcoords.size() * 4);
+        case 4: return ret(p.indices.data(), p.indices.size() * 4);
+        case 5: return ret(p.blas.data(), p.blas.size() * sizeof(bpt_blas_desc));
+        case 6: return ret(p.drawables.data(), p.drawables.size() * sizeof(bpt_drawable_sbt_data));
+        case 7: return ret(p.instances.data(), p.instances.size() * sizeof(bpt_instance_desc));
+        case 8: return ret(p.materials.data(), p.materials.size() * sizeof(bpt_material));
+        case 9: return ret(p.lights.dir_lights.data(), p.lights.dir_lights.size() * sizeof(bpt_dir_light_data));
+        case 10: return ret(p.lights.point_lights.data(), p.lights.point_lights.size() * sizeof(bpt_point_light_data));
+        case 11: return ret(p.lights.rect_lights.data(), p.lights.rect_lights.size() * sizeof(bpt_rect_light_data));
+        default: break;
+    }
+    if (which >= 16 && which - 16 < p.textures.size()) {
+        auto& t = p.textures[which - 16];
+        if (width) *width = t.width;
+        if (height) *height = t.height;
+        if (format) *format = t.format;
+        return ret(t.texels.data(), t.texels.size());
+    }
+    *bytes = 0;
+    return nullptr;
+}
+// geometry + materials/textures + instances + lights + sky + acceleration structure into `ctx`. Returns bpt_status.
+HOST_API int bpt_host_project_upload(bpt_host_project* h, bpt_context* ctx, uint32_t accel_mode) {
+    return (int)project::upload_project(h->p, ctx, accel_mode, h->err);
+}
+HOST_API const char* bpt_host_project_error(const bpt_host_project* h) { return h->err.c_str(); }
+
 // Samples traced ahead per wave while the history stays valid (throughput vs latency of the first frame; default 8).
 HOST_API void bpt_host_pass_set_prefetch(bpt_host_pass* p, uint32_t frames) { p->pass->set_prefetch_frames(frames); }
 // One engine frame: camera.update_shader_params → pass.render (records) → rg.execute. Returns bpt_status.

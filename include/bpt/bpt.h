@@ -143,7 +143,7 @@ enum {
     BPT_MATERIAL_KIND_GLTF_PBR = 0,        /* import_model.cpp:208-230 */
     BPT_MATERIAL_KIND_ASSIMP_DIFFUSE = 1,  /* import_model.cpp:490-493 (base_color, roughness) */
     BPT_MATERIAL_KIND_DEFAULT = 2,         /* surface_data_default, material/utils.hlsl:18-31 */
-    /* the five materials of the reference's example project (examples/scene_basic/materials/*.toml) */
+    /* the five materials of the reference's example project (the .toml files under examples/scene_basic/materials) */
     BPT_MATERIAL_KIND_CONSTANT_COLOR = 3,  /* white.toml: base_color = PARAM_base_color */
     BPT_MATERIAL_KIND_CHECKERBOARD = 4,    /* checkerboard.toml: world-space xz checker. base_color.rgb = base_color_0,
                                               base_color.a = roughness_0, emission.rgb = base_color_1, roughness = roughness_1 */
