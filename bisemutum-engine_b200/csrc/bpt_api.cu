@@ -25,9 +25,14 @@ void dev_free(DevBuf& b) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr; b.bytes = 0;
 }
-bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes) {
+bpt_status dev_reserve(bpt_context* ctx, DevBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.p && b.bytes >= bytes && b.bytes <= 2 * bytes + (1u << 20)) return BPT_OK;
     dev_free(b);
-    bpt_status s = dev_alloc(ctx, b, bytes);
+    return dev_alloc(ctx, b, bytes);
+}
+bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes) {
+    bpt_status s = dev_reserve(ctx, b, bytes);
     if (s) return s;
     if (bytes && src) BPT_CUDA_TRY(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return BPT_OK;
@@ -43,6 +48,7 @@ DScene bpt_context::scene_view() const {
     s.instances = d_instances.as<DInstance>(); s.num_instances = (uint32_t)h_instances.size();
     s.accel_mode = accel_mode;
     s.tlas_nodes = tlas.nodes.as<float4>(); s.tlas_prims = tlas.prims.as<uint32_t>(); s.tlas_root = tlas.root; s.tlas_n = tlas.n;
+    s.tlas_wide = tlas.wide.as<float4>(); s.tlas_leafbox = tlas.leafbox.as<float4>();
     s.blas = d_blas_table.as<DBlas>();
     s.dir_lights = d_dir.as<bpt_dir_light_data>(); s.num_dir = num_dir;
     s.point_lights = d_point.as<bpt_point_light_data>(); s.num_point = num_point;
@@ -119,11 +125,13 @@ bpt_status bpt_destroy(bpt_context* c) {
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
                       &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
-                      &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims};
+                      &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims,
+                      &c->tlas.wide, &c->tlas.leafbox};
     for (DevBuf* b : bufs) dev_free(*b);
     for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
     for (auto& t : c->d_texels) dev_free(t);
     for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
+    for (auto& a : c->arena_chunks) dev_free(a);
     delete c;
     return BPT_OK;
 }
@@ -269,7 +277,8 @@ static bpt_status validate_scene(bpt_context* c) {
 
 static bpt_status upload_blas_table(bpt_context* c) {
     std::vector<DBlas> t(c->blas.size());
-    for (size_t i = 0; i < c->blas.size(); i++) t[i] = DBlas{c->blas[i].nodes.as<float4>(), c->blas[i].tris.as<float4>(), c->blas[i].root, c->blas[i].n};
+    for (size_t i = 0; i < c->blas.size(); i++) t[i] = DBlas{c->blas[i].nodes.as<float4>(), c->blas[i].tris.as<float4>(), c->blas[i].root, c->blas[i].n,
+                                                               c->blas[i].wide.as<float4>(), c->blas[i].leafbox.as<float4>()};
     bpt_status s = dev_upload(c, c->d_blas_table, t.data(), t.size() * sizeof(DBlas));
     if (s) return s;
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -284,16 +293,19 @@ bpt_status bpt_build_accel(bpt_context* c, uint32_t mode) {
     c->accel_built = false;
     c->accel_mode = mode;
     if ((s = upload_instance_table(c))) return s;
-    for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
+    // buffers of a previous build are kept when the BLAS count is unchanged (dev_reserve re-uses them)
+    size_t want_blas = mode == BPT_ACCEL_TWO_LEVEL ? c->h_blas_desc.size() : 1;
+    if (c->blas.size() != want_blas) {
+        for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
+        c->blas.assign(want_blas, DevBvh{});
+    }
     if (mode == BPT_ACCEL_TWO_LEVEL) {
-        c->blas.assign(c->h_blas_desc.size(), DevBvh{});
         for (uint32_t b = 0; b < c->blas.size(); b++)
             if ((s = build_blas_two_level(c, b))) return s;
         if ((s = build_tlas(c))) return s;
     } else {
-        c->blas.assign(1, DevBvh{});
         if ((s = build_blas_merged(c))) return s;
-        dev_free(c->tlas.nodes); dev_free(c->tlas.morton); dev_free(c->tlas.prims);
+        dev_free(c->tlas.nodes); dev_free(c->tlas.morton); dev_free(c->tlas.prims); dev_free(c->tlas.wide); dev_free(c->tlas.leafbox);
         c->tlas = DevBvh{};
     }
     if ((s = upload_blas_table(c))) return s;

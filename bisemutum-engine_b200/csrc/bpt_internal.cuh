@@ -79,6 +79,9 @@ struct bpt_context {
     DevBvh tlas;
     DevBuf d_blas_table;         // DBlas[]
     DevBuf d_inst_aabb;          // scratch for TLAS build
+    // build scratch: grow-only chunks, bump-allocated with stack discipline (bvh_build.cu: Scratch), so a per-frame rebuild
+    // (the reference rebuilds its TLAS every frame, accel.cpp:134-159) makes no cudaMalloc / cudaFree calls
+    std::vector<DevBuf> arena_chunks; size_t arena_chunk = 0, arena_offset = 0;
 
     WavefrontState wf;
     bool profile = false;
@@ -103,6 +106,8 @@ struct bpt_context {
 
 bpt_status dev_alloc(bpt_context* ctx, DevBuf& b, size_t bytes);
 void dev_free(DevBuf& b);
+// keeps the allocation when it already holds `bytes` without being more than twice too large (rebuilds of the same scene)
+bpt_status dev_reserve(bpt_context* ctx, DevBuf& b, size_t bytes);
 bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes);
 
 // bvh_build.cu

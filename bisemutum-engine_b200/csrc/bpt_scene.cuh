@@ -22,6 +22,8 @@ struct DBlas {
     const float4* tris;    // 3 per triangle, leaf order
     int32_t root;
     uint32_t n;
+    const float4* wide;    // 4 per node: 4-wide quantised form (bpt_wide.cuh); nullptr when not built
+    const float4* leafbox; // 2 per leaf: exact leaf boxes for the wide traversal
 };
 
 struct DTexture {
@@ -48,6 +50,7 @@ struct DScene {
     // accel
     uint32_t accel_mode;
     const float4* tlas_nodes; const uint32_t* tlas_prims; int32_t tlas_root; uint32_t tlas_n;
+    const float4* tlas_wide; const float4* tlas_leafbox;      // 4-wide form of the TLAS + exact instance boxes (two-level mode)
     const DBlas* blas;
     // lights
     const bpt_dir_light_data* dir_lights; uint32_t num_dir;

@@ -28,13 +28,19 @@ __global__ void k_init_bounds(uint32_t* keys) {
     else if (threadIdx.x < 6) keys[threadIdx.x] = 0u;           // max keys
 }
 
-// Triangle gather: object space (xf == nullptr) or world space (merged mode: o2w of one instance).
-// Writes unsorted 48-B records (v0|prim, v1|slot, v2|-) and the AABB.
-__global__ void k_gather_tris(const float* __restrict__ positions, const uint32_t* __restrict__ indices, bpt_blas_desc bd,
-                              const DInstance* __restrict__ inst, uint32_t slot, uint32_t out_base,
+// Triangle gather: object space (inst == nullptr: one BLAS, `ranges` has one entry) or world space (merged mode: every
+// instance's triangles through its o2w; `ranges[slot]` = first output record of instance `slot`, found by binary search).
+// Writes unsorted 48-B records (v0|prim, v1|slot, v2|any-hit) and the AABB.
+struct GatherRange { bpt_blas_desc bd; uint32_t base; };
+__global__ void k_gather_tris(const float* __restrict__ positions, const uint32_t* __restrict__ indices, const GatherRange* __restrict__ ranges,
+                              uint32_t num_ranges, uint32_t total, const DInstance* __restrict__ inst,
                               float4* __restrict__ raw, float4* __restrict__ lo, float4* __restrict__ hi) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= bd.num_triangles) return;
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    uint32_t slot = 0, end = num_ranges;
+    while (end - slot > 1) { uint32_t m = (slot + end) >> 1; if (ranges[m].base <= g) slot = m; else end = m; }
+    const bpt_blas_desc bd = ranges[slot].bd;
+    const uint32_t k = g - ranges[slot].base;
     float3 v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -43,10 +49,9 @@ __global__ void k_gather_tris(const float* __restrict__ positions, const uint32_
         v[c] = v3(p[0], p[1], p[2]);
         if (inst) v[c] = xf_point(inst[slot].o2w, v[c]);
     }
-    size_t g = (size_t)out_base + k;
-    raw[3 * g + 0] = make_float4(v[0].x, v[0].y, v[0].z, __uint_as_float(k));
-    raw[3 * g + 1] = make_float4(v[1].x, v[1].y, v[1].z, __uint_as_float(slot));
-    raw[3 * g + 2] = make_float4(v[2].x, v[2].y, v[2].z, __uint_as_float(inst ? inst[slot].anyhit : 0u));
+    raw[3 * (size_t)g + 0] = make_float4(v[0].x, v[0].y, v[0].z, __uint_as_float(k));
+    raw[3 * (size_t)g + 1] = make_float4(v[1].x, v[1].y, v[1].z, __uint_as_float(slot));
+    raw[3 * (size_t)g + 2] = make_float4(v[2].x, v[2].y, v[2].z, __uint_as_float(inst ? inst[slot].anyhit : 0u));
     float3 l = vmin(vmin(v[0], v[1]), v[2]), h = vmax(vmax(v[0], v[1]), v[2]);
     lo[g] = make_float4(l.x, l.y, l.z, 0.0f);
     hi[g] = make_float4(h.x, h.y, h.z, 0.0f);
@@ -117,41 +122,45 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t* __re
     __syncthreads();
     hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];     // digit-major
 }
-// exclusive scan of `total` counters, single block
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, uint32_t total) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+// exclusive scan of 256 values held one per thread of a 256-thread block
+__device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t* warp_sums /* [8] shared */, uint32_t* total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+    if (lane == 31) warp_sums[warp] = x;
     __syncthreads();
-    for (uint32_t base = 0; base < total; base += 1024) {
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { uint32_t t = warp_sums[w]; if ((uint32_t)w < warp) before += t; all += t; }
+    __syncthreads();
+    if (total) *total = all;
+    return x - v + before;
+}
+// Block d turns the per-block counts of digit d (hist is digit-major) into exclusive offsets WITHIN the digit and
+// writes the digit's total; the scatter kernel adds the prefix over the 256 digit totals itself.
+__global__ void __launch_bounds__(kSortThreads) k_sort_scan(uint32_t* __restrict__ hist, uint32_t nblocks, uint32_t* __restrict__ digit_total) {
+    __shared__ uint32_t warp_sums[8];
+    uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nblocks; base += kSortThreads) {
         uint32_t i = base + threadIdx.x;
-        uint32_t v = i < total ? hist[i] : 0;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
-        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = warp_sums[threadIdx.x], s = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (threadIdx.x >= o) s += y; }
-            warp_sums[threadIdx.x] = s - w;
-        }
-        __syncthreads();
-        uint32_t excl = x - v + warp_sums[threadIdx.x >> 5] + carry;
-        if (i < total) hist[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
+        uint32_t v = i < nblocks ? row[i] : 0, tot;
+        uint32_t e = block_excl_scan256(v, warp_sums, &tot);
+        if (i < nblocks) row[i] = carry + e;
+        carry += tot;
     }
+    if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
 }
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                                                               uint32_t n, int shift, const uint32_t* __restrict__ hist, uint32_t nblocks) {
+                                                               uint32_t n, int shift, const uint32_t* __restrict__ hist, uint32_t nblocks,
+                                                               const uint32_t* __restrict__ digit_total) {
     __shared__ uint32_t digit_base[256];                       // global offset of this block's first key of each digit
     __shared__ uint32_t warp_count[kSortThreads / 32][256];
+    __shared__ uint32_t warp_sums[8];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    digit_base[threadIdx.x] = hist[threadIdx.x * nblocks + blockIdx.x];
+    digit_base[threadIdx.x] = block_excl_scan256(digit_total[threadIdx.x], warp_sums, nullptr) + hist[threadIdx.x * nblocks + blockIdx.x];
     uint32_t base = blockIdx.x * kSortTile;
     for (int r = 0; r < kSortItems; r++) {
 #pragma unroll
@@ -299,12 +308,24 @@ __global__ void k_instance_bounds(const DInstance* __restrict__ inst, uint32_t n
     hi[i] = make_float4(mx.x, mx.y, mx.z, 0.0f);
 }
 
+// Build scratch from the context's grow-only arena (bpt_internal.cuh): bump allocation, released in stack order when the
+// Scratch goes out of scope. Everything runs on ctx->stream, so re-use by the next build is stream-ordered.
 struct Scratch {
-    std::vector<DevBuf> bufs;
-    ~Scratch() { for (auto& b : bufs) dev_free(b); }
-    bpt_status get(bpt_context* ctx, DevBuf& out, size_t bytes) {
-        DevBuf b; bpt_status s = dev_alloc(ctx, b, bytes); if (s) return s;
-        bufs.push_back(b); out = b; return BPT_OK;
+    bpt_context* ctx;
+    size_t chunk0, offset0;
+    explicit Scratch(bpt_context* c) : ctx(c), chunk0(c->arena_chunk), offset0(c->arena_offset) {}
+    ~Scratch() { ctx->arena_chunk = chunk0; ctx->arena_offset = offset0; }
+    bpt_status get(bpt_context*, DevBuf& out, size_t bytes) {
+        bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+        auto& ch = ctx->arena_chunks;
+        while (ctx->arena_chunk < ch.size() && ctx->arena_offset + bytes > ch[ctx->arena_chunk].bytes) { ctx->arena_chunk++; ctx->arena_offset = 0; }
+        if (ctx->arena_chunk == ch.size()) {
+            DevBuf b; bpt_status s = dev_alloc(ctx, b, std::max<size_t>(bytes, (size_t)32 << 20)); if (s) return s;
+            ch.push_back(b); ctx->arena_offset = 0;
+        }
+        out.p = (char*)ch[ctx->arena_chunk].p + ctx->arena_offset; out.bytes = bytes;
+        ctx->arena_offset += bytes;
+        return BPT_OK;
     }
 };
 
@@ -326,7 +347,7 @@ struct Scratch {
 bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi) {
     out.n = n;
     out.root = n == 1 ? ~0 : 0;
-    Scratch sc;
+    Scratch sc(ctx);
     DevBuf bkeys, b6;
     bpt_status s;
     if ((s = sc.get(ctx, bkeys, 6 * sizeof(uint32_t)))) return s;
@@ -337,27 +358,27 @@ bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d
     float hb[6];
     BPT_CUDA_TRY(ctx, cudaMemcpyAsync(hb, b6.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
     // sort
-    dev_free(out.morton); dev_free(out.prims); dev_free(out.nodes);
     DevBuf keys2, vals2;
-    if ((s = dev_alloc(ctx, out.morton, (size_t)n * 8))) return s;
-    if ((s = dev_alloc(ctx, out.prims, (size_t)n * 4))) return s;
+    if ((s = dev_reserve(ctx, out.morton, (size_t)n * 8))) return s;
+    if ((s = dev_reserve(ctx, out.prims, (size_t)n * 4))) return s;
     if ((s = sc.get(ctx, keys2, (size_t)n * 8))) return s;
     if ((s = sc.get(ctx, vals2, (size_t)n * 4))) return s;
     LAUNCH(ctx, k_morton, grid_for(n), kThreads, d_lo, d_hi, n, b6.as<float>(), out.morton.as<uint64_t>(), out.prims.as<uint32_t>());
     uint32_t nblocks = (n + kSortTile - 1) / kSortTile;
-    DevBuf hist;
+    DevBuf hist, dtot;
     if ((s = sc.get(ctx, hist, (size_t)256 * nblocks * 4))) return s;
+    if ((s = sc.get(ctx, dtot, 256 * 4))) return s;
     uint64_t* ka = out.morton.as<uint64_t>(); uint64_t* kb = keys2.as<uint64_t>();
     uint32_t* va = out.prims.as<uint32_t>(); uint32_t* vb = vals2.as<uint32_t>();
     for (int pass = 0; pass < 8; pass++) {       // 63-bit keys: all 8 bytes
         int shift = pass * 8;
         LAUNCH(ctx, k_sort_hist, nblocks, kSortThreads, ka, n, shift, hist.as<uint32_t>(), nblocks);
-        LAUNCH(ctx, k_sort_scan, 1, 1024, hist.as<uint32_t>(), 256u * nblocks);
-        LAUNCH(ctx, k_sort_scatter, nblocks, kSortThreads, ka, va, kb, vb, n, shift, hist.as<uint32_t>(), nblocks);
+        LAUNCH(ctx, k_sort_scan, 256, kSortThreads, hist.as<uint32_t>(), nblocks, dtot.as<uint32_t>());
+        LAUNCH(ctx, k_sort_scatter, nblocks, kSortThreads, ka, va, kb, vb, n, shift, hist.as<uint32_t>(), nblocks, dtot.as<uint32_t>());
         std::swap(ka, kb); std::swap(va, vb);
     }   // even number of passes: result is back in out.morton / out.prims
     if (n >= 2) {
-        if ((s = dev_alloc(ctx, out.nodes, (size_t)(n - 1) * 64))) return s;
+        if ((s = dev_reserve(ctx, out.nodes, (size_t)(n - 1) * 64))) return s;
         DevBuf c0, c1, np, lp, nlo, nhi, flags;
         if ((s = sc.get(ctx, c0, (size_t)(n - 1) * 4))) return s;
         if ((s = sc.get(ctx, c1, (size_t)(n - 1) * 4))) return s;
@@ -378,40 +399,49 @@ bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d
 
 bpt_status upload_instance_table(bpt_context* ctx) {
     uint32_t n = (uint32_t)ctx->h_instances.size();
+    Scratch sc(ctx);
     DevBuf desc;
     bpt_status s;
-    if ((s = dev_upload(ctx, desc, ctx->h_instances.data(), (size_t)n * sizeof(bpt_instance_desc)))) return s;
-    dev_free(ctx->d_instances);
-    if ((s = dev_alloc(ctx, ctx->d_instances, (size_t)n * sizeof(DInstance)))) { dev_free(desc); return s; }
-    k_make_instances<<<grid_for(n), kThreads, 0, ctx->stream>>>(desc.as<bpt_instance_desc>(), n, ctx->d_drawables.as<bpt_drawable_sbt_data>(),
-                                                                 ctx->d_materials.as<bpt_material>(), ctx->d_instances.as<DInstance>());
-    ctx->launches++;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    dev_free(desc);
-    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
-    return BPT_OK;
+    if ((s = sc.get(ctx, desc, (size_t)n * sizeof(bpt_instance_desc)))) return s;
+    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(desc.p, ctx->h_instances.data(), (size_t)n * sizeof(bpt_instance_desc), cudaMemcpyHostToDevice, ctx->stream));
+    if ((s = dev_reserve(ctx, ctx->d_instances, (size_t)n * sizeof(DInstance)))) return s;
+    LAUNCH(ctx, k_make_instances, grid_for(n), kThreads, desc.as<bpt_instance_desc>(), n, ctx->d_drawables.as<bpt_drawable_sbt_data>(),
+           ctx->d_materials.as<bpt_material>(), ctx->d_instances.as<DInstance>());
+    return BPT_OK;      // stream-ordered: the builds that follow run on the same stream
 }
 
 static bpt_status emit_tris(bpt_context* ctx, DevBvh& b, const float4* raw) {
-    dev_free(b.tris);
     bpt_status s;
-    if ((s = dev_alloc(ctx, b.tris, (size_t)b.n * 48))) return s;
+    if ((s = dev_reserve(ctx, b.tris, (size_t)b.n * 48))) return s;
     LAUNCH(ctx, k_emit_tris, grid_for(b.n), kThreads, b.n, b.prims.as<uint32_t>(), raw, b.tris.as<float4>());
-    BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPT_OK;      // `raw` is arena scratch: its re-use by a later build is stream-ordered
+}
+
+// 4-wide quantised nodes + exact leaf boxes of a built binary tree (any BLAS, or the TLAS with instance boxes as leaves)
+static bpt_status collapse_wide(bpt_context* ctx, DevBvh& b) {
+    if (b.n < 2) { dev_free(b.wide); dev_free(b.leafbox); return BPT_OK; }     // a single leaf is entered without any box test
+    bpt_status s;
+    if ((s = dev_reserve(ctx, b.wide, (size_t)(b.n - 1) * 64))) return s;
+    if ((s = dev_reserve(ctx, b.leafbox, (size_t)b.n * 32))) return s;
+    LAUNCH(ctx, k_collapse4, grid_for(b.n - 1), kThreads, b.n - 1, b.nodes.as<float4>(), b.wide.as<float4>(), b.leafbox.as<float4>());
     return BPT_OK;
 }
 
 bpt_status build_blas_two_level(bpt_context* ctx, uint32_t bi) {
     const bpt_blas_desc& bd = ctx->h_blas_desc[bi];
     uint32_t n = bd.num_triangles;
-    Scratch sc; DevBuf raw, lo, hi; bpt_status s;
+    Scratch sc(ctx); DevBuf raw, lo, hi, rng; bpt_status s;
     if ((s = sc.get(ctx, raw, (size_t)n * 48))) return s;
     if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
     if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
-    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), bd, (const DInstance*)nullptr, 0u, 0u,
-           raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
+    if ((s = sc.get(ctx, rng, sizeof(GatherRange)))) return s;
+    GatherRange one{bd, 0u};
+    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(rng.p, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), rng.as<GatherRange>(), 1u, n,
+           (const DInstance*)nullptr, raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
     if ((s = lbvh_build(ctx, ctx->blas[bi], n, lo.as<float4>(), hi.as<float4>()))) return s;
-    return emit_tris(ctx, ctx->blas[bi], raw.as<float4>());
+    if ((s = emit_tris(ctx, ctx->blas[bi], raw.as<float4>()))) return s;
+    return collapse_wide(ctx, ctx->blas[bi]);
 }
 
 bpt_status build_blas_merged(bpt_context* ctx) {
@@ -422,30 +452,28 @@ bpt_status build_blas_merged(bpt_context* ctx) {
     {   // refuse up front when the merged soup cannot fit (build scratch + result ≈ 300 B per triangle)
         size_t free_b = 0, total_b = 0;
         BPT_CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        for (auto& a : ctx->arena_chunks) free_b += a.bytes;       // scratch of an earlier build is re-used
+        const DevBvh& old = ctx->blas[0];
+        free_b += old.nodes.bytes + old.tris.bytes + old.morton.bytes + old.prims.bytes + old.wide.bytes + old.leafbox.bytes;
         if ((double)total * 300.0 > (double)free_b) { ctx->err = "merged accel: not enough device memory for the flattened scene; use BPT_ACCEL_TWO_LEVEL"; return BPT_ERR_OOM; }
     }
-    Scratch sc; DevBuf raw, lo, hi; bpt_status s;
+    Scratch sc(ctx); DevBuf raw, lo, hi, rng; bpt_status s;
     if ((s = sc.get(ctx, raw, (size_t)n * 48))) return s;
     if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
     if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
+    std::vector<GatherRange> ranges(ctx->h_instances.size());
     uint32_t base = 0;
     for (uint32_t slot = 0; slot < ctx->h_instances.size(); slot++) {
-        const bpt_blas_desc& bd = ctx->h_blas_desc[(uint32_t)ctx->h_instances[slot].blas];
-        LAUNCH(ctx, k_gather_tris, grid_for(bd.num_triangles), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), bd,
-               ctx->d_instances.as<DInstance>(), slot, base, raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
-        base += bd.num_triangles;
+        ranges[slot] = GatherRange{ctx->h_blas_desc[(uint32_t)ctx->h_instances[slot].blas], base};
+        base += ranges[slot].bd.num_triangles;
     }
+    if ((s = sc.get(ctx, rng, ranges.size() * sizeof(GatherRange)))) return s;
+    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(rng.p, ranges.data(), ranges.size() * sizeof(GatherRange), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), rng.as<GatherRange>(),
+           (uint32_t)ranges.size(), n, ctx->d_instances.as<DInstance>(), raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
     if ((s = lbvh_build(ctx, ctx->blas[0], n, lo.as<float4>(), hi.as<float4>()))) return s;
     if ((s = emit_tris(ctx, ctx->blas[0], raw.as<float4>()))) return s;
-    DevBvh& b = ctx->blas[0];
-    dev_free(b.wide); dev_free(b.leafbox);
-    if (n >= 2) {
-        if ((s = dev_alloc(ctx, b.wide, (size_t)(n - 1) * 64))) return s;
-        if ((s = dev_alloc(ctx, b.leafbox, (size_t)n * 32))) return s;
-        LAUNCH(ctx, k_collapse4, grid_for(n - 1), kThreads, n - 1, b.nodes.as<float4>(), b.wide.as<float4>(), b.leafbox.as<float4>());
-        BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    return BPT_OK;
+    return collapse_wide(ctx, ctx->blas[0]);
 }
 
 bpt_status build_tlas(bpt_context* ctx) {
@@ -453,11 +481,12 @@ bpt_status build_tlas(bpt_context* ctx) {
     std::vector<float> bb(6 * ctx->blas.size());
     for (size_t b = 0; b < ctx->blas.size(); b++)
         for (int k = 0; k < 3; k++) { bb[6 * b + k] = ctx->blas[b].lo[k]; bb[6 * b + 3 + k] = ctx->blas[b].hi[k]; }
-    Scratch sc; DevBuf dbb, lo, hi; bpt_status s;
+    Scratch sc(ctx); DevBuf dbb, lo, hi; bpt_status s;
     if ((s = sc.get(ctx, dbb, bb.size() * 4))) return s;
     BPT_CUDA_TRY(ctx, cudaMemcpyAsync(dbb.p, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
     if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
     LAUNCH(ctx, k_instance_bounds, grid_for(n), kThreads, ctx->d_instances.as<DInstance>(), n, dbb.as<float>(), lo.as<float4>(), hi.as<float4>());
-    return lbvh_build(ctx, ctx->tlas, n, lo.as<float4>(), hi.as<float4>());
+    if ((s = lbvh_build(ctx, ctx->tlas, n, lo.as<float4>(), hi.as<float4>()))) return s;
+    return collapse_wide(ctx, ctx->tlas);
 }

@@ -99,7 +99,7 @@ void build(const hc_scene& h, Built& b) {
         }
     }
     for (uint32_t bi = 0; bi < nb; bi++)
-        b.blas[bi] = DBlas{reinterpret_cast<const float4*>(h.blas_bvh[bi].nodes), b.tris[bi].data(), h.blas_bvh[bi].root, h.blas_bvh[bi].n};
+        b.blas[bi] = DBlas{reinterpret_cast<const float4*>(h.blas_bvh[bi].nodes), b.tris[bi].data(), h.blas_bvh[bi].root, h.blas_bvh[bi].n, nullptr, nullptr};
     DScene& s = b.sc;
     s.positions = h.positions; s.normals = h.normals; s.tangents = h.tangents; s.texcoords = h.texcoords; s.indices = h.indices;
     s.drawables = h.drawables; s.drawable_va = h.drawable_va; s.materials = h.materials;
