@@ -124,7 +124,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     if (c->nccl_comm && c->nccl_owned) nccl().CommDestroy(c->nccl_comm);
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
-                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
+                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
                       &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims,
                       &c->tlas.wide, &c->tlas.leafbox};
     for (DevBuf* b : bufs) dev_free(*b);
@@ -138,7 +138,12 @@ bpt_status bpt_destroy(bpt_context* c) {
 
 const char* bpt_last_error(const bpt_context* c) { return c ? c->err.c_str() : "null context"; }
 
-bpt_status bpt_set_stream(bpt_context* c, void* stream) { NEED(c); c->stream = (cudaStream_t)stream; return BPT_OK; }
+bpt_status bpt_set_stream(bpt_context* c, void* stream) {
+    NEED(c);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // build scratch and uploads are ordered on the stream they were issued on
+    c->stream = (cudaStream_t)stream;
+    return BPT_OK;
+}
 bpt_status bpt_sync(bpt_context* c) { NEED(c); BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return BPT_OK; }
 
 bpt_status bpt_resize(bpt_context* c, uint32_t w, uint32_t h) {
@@ -299,6 +304,7 @@ bpt_status bpt_build_accel(bpt_context* c, uint32_t mode) {
         for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
         c->blas.assign(want_blas, DevBvh{});
     }
+    if ((s = dev_reserve(c, c->d_blas_bounds, want_blas * 6 * sizeof(float)))) return s;
     if (mode == BPT_ACCEL_TWO_LEVEL) {
         for (uint32_t b = 0; b < c->blas.size(); b++)
             if ((s = build_blas_two_level(c, b))) return s;

@@ -21,7 +21,6 @@ struct DevBvh {
     DevBuf leafbox;    // float4[2*n]: exact box of every leaf (merged BLAS only)
     DevBuf morton;     // uint64[n] sorted
     DevBuf prims;      // uint32[n] sorted primitive ids
-    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 };
 
 struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through compaction)
@@ -29,7 +28,7 @@ struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through 
     uint32_t npx = 0, slots = 1;
     DevBuf color;           // float4 per path: per-sample colour C_s
     uint32_t ahead_slots = 0, ahead_cursor = 0, ahead_frame_first = 0;   // prefetched samples still in `color`
-    unsigned grid_extend = 0, grid_connect = 0, grid_extend_m = 0, grid_connect_m = 0, grid_extend_w = 0, grid_connect_w = 0;   // resident grid sizes of the persistent traversal kernels
+    unsigned grid_extend = 0, grid_connect = 0, grid_extend_m = 0, grid_connect_m = 0, grid_extend_w = 0, grid_connect_w = 0, grid_extend_w2 = 0, grid_connect_w2 = 0;   // resident grid sizes of the persistent traversal kernels
     DevBuf ray_o[2], ray_d[2], ray_w[2];   // float4 each: (O|pixel), (D|-), (W|-)
     DevBuf hit;             // float4 (t,u,v,prim)
     DevBuf hit_slot;        // uint32
@@ -79,6 +78,7 @@ struct bpt_context {
     DevBvh tlas;
     DevBuf d_blas_table;         // DBlas[]
     DevBuf d_inst_aabb;          // scratch for TLAS build
+    DevBuf d_blas_bounds;        // float[6] per BLAS (lo, hi), written by the BLAS builds, read by the TLAS build
     // build scratch: grow-only chunks, bump-allocated with stack discipline (bvh_build.cu: Scratch), so a per-frame rebuild
     // (the reference rebuilds its TLAS every frame, accel.cpp:134-159) makes no cudaMalloc / cudaFree calls
     std::vector<DevBuf> arena_chunks; size_t arena_chunk = 0, arena_offset = 0;
@@ -112,7 +112,7 @@ bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes
 
 // bvh_build.cu
 // Builds an LBVH over `n` primitives whose AABBs are in d_lo/d_hi (float4 each, device).
-bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi);
+bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi, float* d_bounds6);
 bpt_status build_blas_two_level(bpt_context* ctx, uint32_t blas_index);
 bpt_status build_blas_merged(bpt_context* ctx);
 bpt_status build_tlas(bpt_context* ctx);

@@ -211,4 +211,57 @@ BPT_HD TraceResult trace_ray_wide(const DScene& sc, const float4* wide, const fl
     return res;
 }
 
+// Two-level counterpart (ray batches, host-check): wide TLAS whose proposed instances must pass their exact world box, then the
+// instance's wide BLAS with the object-space ray. Same candidates as the binary two-level traversal of bpt_trace.cuh, hence the same hits.
+template <bool ANY>
+BPT_HD TraceResult trace_ray_wide_two_level(const DScene& sc, float3 O, float3 D, float tmin, float tmax, uint32_t frame_index, bool cull_non_opaque = false) {
+    RayState rs;
+    rs.O = O; rs.D = D; rs.tmin = tmin; rs.tbest = tmax; rs.tcull = tmax * 1.00001f; rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu;
+    rs.bu = 0.0f; rs.bv = 0.0f; rs.frame_index = frame_index; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false; rs.cull_non_opaque = cull_non_opaque;
+    const RaySpace world = make_space(O, D);
+    RaySpace cur = world;
+    const float4* nodes = sc.tlas_wide; const float4* tris = nullptr; const float4* leafbox = nullptr;
+    uint32_t slot = 0xffffffffu, inst_anyhit = 0;
+    bool in_blas = false;
+    int32_t stack[2 * kStackSize];
+    int sp = 0;
+    TraceResult res;
+    if (sc.tlas_n != 0) {
+        int32_t node = sc.tlas_root;                         // ~0 when the TLAS is a single instance
+        for (;;) {
+            if (node == kSentinel) {
+                cur = world; nodes = sc.tlas_wide; tris = nullptr; in_blas = false;
+            } else if (node >= 0) {
+                int32_t push[3]; int np;
+                int32_t next = node_step4q(nodes, node, cur, rs.tmin, rs.tcull, push, np);
+                for (int k = 0; k < np; k++) stack[sp++] = push[k];
+                if (next != BPT_POP) { node = next; continue; }
+            } else if (!in_blas) {
+                uint32_t j = (uint32_t)~node;
+                if (sc.tlas_n == 1 || leaf_box_hit(sc.tlas_leafbox, j, cur, rs.tmin, rs.tcull)) {
+                    slot = BPT_LDG(sc.tlas_prims + j);
+                    const DInstance& in = sc.instances[slot];
+                    const DBlas& bl = sc.blas[in.blas];
+                    inst_anyhit = in.anyhit;
+                    cur = make_space(xf_point(in.w2o, rs.O), xf_vector(in.w2o, rs.D));
+                    nodes = bl.wide; tris = bl.tris; leafbox = bl.n == 1 ? nullptr : bl.leafbox; in_blas = true;
+                    stack[sp++] = kSentinel;
+                    node = bl.root;
+                    continue;
+                }
+            } else {
+                uint32_t j = (uint32_t)~node;
+                if (!leafbox || leaf_box_hit(leafbox, j, cur, rs.tmin, rs.tcull)) {
+                    bool accepted = test_triangle<ANY>(sc, rs, tris + 3 * (size_t)j, cur.O, cur.D, slot, inst_anyhit);
+                    if (ANY && accepted) break;
+                }
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    res.hit = rs.found; res.t = rs.found ? rs.tbest : -1.0f; res.u = rs.bu; res.v = rs.bv; res.slot = rs.best_slot; res.prim = rs.best_prim;
+    return res;
+}
+
 } // namespace bptd

@@ -32,15 +32,15 @@ __global__ void k_init_bounds(uint32_t* keys) {
 // instance's triangles through its o2w; `ranges[slot]` = first output record of instance `slot`, found by binary search).
 // Writes unsorted 48-B records (v0|prim, v1|slot, v2|any-hit) and the AABB.
 struct GatherRange { bpt_blas_desc bd; uint32_t base; };
-__global__ void k_gather_tris(const float* __restrict__ positions, const uint32_t* __restrict__ indices, const GatherRange* __restrict__ ranges,
+__global__ void k_gather_tris(const float* __restrict__ positions, const uint32_t* __restrict__ indices, const GatherRange* __restrict__ ranges, GatherRange single,
                               uint32_t num_ranges, uint32_t total, const DInstance* __restrict__ inst,
                               float4* __restrict__ raw, float4* __restrict__ lo, float4* __restrict__ hi) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total) return;
     uint32_t slot = 0, end = num_ranges;
     while (end - slot > 1) { uint32_t m = (slot + end) >> 1; if (ranges[m].base <= g) slot = m; else end = m; }
-    const bpt_blas_desc bd = ranges[slot].bd;
-    const uint32_t k = g - ranges[slot].base;
+    const bpt_blas_desc bd = ranges ? ranges[slot].bd : single.bd;       // (one BLAS: the range travels as a kernel argument)
+    const uint32_t k = g - (ranges ? ranges[slot].base : 0u);
     float3 v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -195,10 +195,8 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ k, uint32_t n,
     uint64_t a = k[i], c = k[j];
     return a != c ? __clzll((long long)(a ^ c)) : 64 + __clz((int)((uint32_t)i ^ (uint32_t)j));
 }
-__global__ void k_karras(const uint64_t* __restrict__ keys, uint32_t n, int32_t* __restrict__ child0, int32_t* __restrict__ child1,
-                         int32_t* __restrict__ node_parent, int32_t* __restrict__ leaf_parent) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n - 1) return;
+__device__ __forceinline__ void karras_node(const uint64_t* __restrict__ keys, uint32_t n, int64_t i, int32_t* __restrict__ child0, int32_t* __restrict__ child1,
+                                            int32_t* __restrict__ node_parent, int32_t* __restrict__ leaf_parent) {
     if (i == 0) node_parent[0] = -1;
     int d = delta(keys, n, i, i + 1) > delta(keys, n, i, i - 1) ? 1 : -1;
     int dmin = delta(keys, n, i, i - d);
@@ -222,13 +220,18 @@ __global__ void k_karras(const uint64_t* __restrict__ keys, uint32_t n, int32_t*
     if (left >= 0) node_parent[left] = (int32_t)i; else leaf_parent[~left] = (int32_t)i;
     if (right >= 0) node_parent[right] = (int32_t)i; else leaf_parent[~right] = (int32_t)i;
 }
+__global__ void k_karras(const uint64_t* __restrict__ keys, uint32_t n, int32_t* __restrict__ child0, int32_t* __restrict__ child1,
+                         int32_t* __restrict__ node_parent, int32_t* __restrict__ leaf_parent) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n - 1) return;
+    karras_node(keys, n, i, child0, child1, node_parent, leaf_parent);
+}
 
 // ---- bottom-up refit ---------------------------------------------------------------------------
-__global__ void k_refit(uint32_t n, const uint32_t* __restrict__ prims, const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
-                        const int32_t* __restrict__ child0, const int32_t* __restrict__ child1, const int32_t* __restrict__ node_parent,
-                        const int32_t* __restrict__ leaf_parent, float4* node_lo, float4* node_hi, uint32_t* flags, float4* __restrict__ nodes) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
+// Leaf j walks towards the root; at every node the SECOND arrival (atomic flag) merges the two child boxes and goes on.
+__device__ __forceinline__ void refit_from_leaf(uint32_t j, const uint32_t* __restrict__ prims, const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                                                const int32_t* __restrict__ child0, const int32_t* __restrict__ child1, const int32_t* __restrict__ node_parent,
+                                                const int32_t* __restrict__ leaf_parent, float4* node_lo, float4* node_hi, uint32_t* flags, float4* __restrict__ nodes) {
     int32_t node = leaf_parent[j];
     while (node >= 0) {
         __threadfence();
@@ -248,6 +251,84 @@ __global__ void k_refit(uint32_t n, const uint32_t* __restrict__ prims, const fl
         __stcg(&node_hi[node], make_float4(uh.x, uh.y, uh.z, 0.0f));
         node = node_parent[node];
     }
+}
+__global__ void k_refit(uint32_t n, const uint32_t* __restrict__ prims, const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                        const int32_t* __restrict__ child0, const int32_t* __restrict__ child1, const int32_t* __restrict__ node_parent,
+                        const int32_t* __restrict__ leaf_parent, float4* node_lo, float4* node_hi, uint32_t* flags, float4* __restrict__ nodes) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    refit_from_leaf(j, prims, prim_lo, prim_hi, child0, child1, node_parent, leaf_parent, node_lo, node_hi, flags, nodes);
+}
+
+// ---- small trees (TLAS, small BLASes): the whole build in ONE block ------------------------------------------------
+// Same definition, same result: bounds (min/max are exact in any order), the same Morton codes, a bitonic sort of the
+// composite (code, primitive index) — whose order is unique, i.e. the stable LSD sort's — in shared memory, then the Karras
+// and refit steps above separated by block barriers. One launch instead of 33: the reference rebuilds its TLAS every frame
+// (accel.cpp:134-159), and a 512-instance TLAS was 0.2 ms of launch latency.
+constexpr uint32_t kSmallMax = 4096;
+constexpr int kSmallThreads = 1024;
+__global__ void __launch_bounds__(kSmallThreads) k_lbvh_small(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, uint32_t np2,
+                                                              float* __restrict__ bounds6, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ prims_out,
+                                                              int32_t* __restrict__ child0, int32_t* __restrict__ child1, int32_t* __restrict__ node_parent,
+                                                              int32_t* __restrict__ leaf_parent, float4* node_lo, float4* node_hi, uint32_t* flags,
+                                                              float4* __restrict__ nodes) {
+    extern __shared__ uint64_t s_keys[];                     // np2 codes, then np2 primitive indices
+    uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_keys + np2);
+    __shared__ uint32_t s_bkeys[6];
+    __shared__ float s_b6[6];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 3) s_bkeys[tid] = 0xffffffffu; else if (tid < 6) s_bkeys[tid] = 0u;
+    __syncthreads();
+    {
+        float3 l = v3s(FLT_MAX), h = v3s(-FLT_MAX);
+        for (uint32_t i = tid; i < n; i += kSmallThreads) {
+            float4 a = lo[i], b = hi[i];
+            l = vmin(l, v3(a.x, a.y, a.z)); h = vmax(h, v3(b.x, b.y, b.z));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l.x = fminf(l.x, __shfl_xor_sync(0xffffffffu, l.x, o)); l.y = fminf(l.y, __shfl_xor_sync(0xffffffffu, l.y, o)); l.z = fminf(l.z, __shfl_xor_sync(0xffffffffu, l.z, o));
+            h.x = fmaxf(h.x, __shfl_xor_sync(0xffffffffu, h.x, o)); h.y = fmaxf(h.y, __shfl_xor_sync(0xffffffffu, h.y, o)); h.z = fmaxf(h.z, __shfl_xor_sync(0xffffffffu, h.z, o));
+        }
+        if ((tid & 31) == 0) {
+            atomicMin(&s_bkeys[0], f_key(l.x)); atomicMin(&s_bkeys[1], f_key(l.y)); atomicMin(&s_bkeys[2], f_key(l.z));
+            atomicMax(&s_bkeys[3], f_key(h.x)); atomicMax(&s_bkeys[4], f_key(h.y)); atomicMax(&s_bkeys[5], f_key(h.z));
+        }
+    }
+    __syncthreads();
+    if (tid < 6) { float v = key_f(s_bkeys[tid]); s_b6[tid] = v; bounds6[tid] = v; }
+    __syncthreads();
+    for (uint32_t i = tid; i < np2; i += kSmallThreads) {
+        uint64_t key = ~0ull; uint32_t idx = 0xffffffffu;       // padding sorts behind every 63-bit code
+        if (i < n) {
+            float4 a = lo[i], b = hi[i];
+            float3 c = (v3(a.x, a.y, a.z) + v3(b.x, b.y, b.z)) * 0.5f;
+            key = (expand21(quant21(c.x, s_b6[0], s_b6[3])) << 2) | (expand21(quant21(c.y, s_b6[1], s_b6[4])) << 1) | expand21(quant21(c.z, s_b6[2], s_b6[5]));
+            idx = i;
+        }
+        s_keys[i] = key; s_idx[i] = idx;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= np2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = tid; i < np2; i += kSmallThreads) {
+                uint32_t x = i ^ j;
+                if (x > i) {
+                    uint64_t ka = s_keys[i], kb = s_keys[x]; uint32_t ia = s_idx[i], ib = s_idx[x];
+                    bool a_after_b = ka > kb || (ka == kb && ia > ib);
+                    bool up = (i & k) == 0;
+                    if (a_after_b == up) { s_keys[i] = kb; s_keys[x] = ka; s_idx[i] = ib; s_idx[x] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t i = tid; i < n; i += kSmallThreads) { keys_out[i] = s_keys[i]; prims_out[i] = s_idx[i]; }
+    if (n < 2) return;
+    for (uint32_t i = tid; i < n - 1; i += kSmallThreads) flags[i] = 0u;
+    for (uint32_t i = tid; i < n - 1; i += kSmallThreads) karras_node(s_keys, n, (int64_t)i, child0, child1, node_parent, leaf_parent);
+    __syncthreads();                                         // (block barrier: global writes of this block are visible to it)
+    for (uint32_t j = tid; j < n; j += kSmallThreads)
+        refit_from_leaf(j, s_idx, lo, hi, child0, child1, node_parent, leaf_parent, node_lo, node_hi, flags, nodes);
 }
 
 // ---- 4-wide quantised nodes + exact leaf boxes from the refitted binary tree (bpt_wide.cuh): one thread per binary node ----
@@ -344,26 +425,48 @@ struct Scratch {
         }                                                                       \
     } while (0)
 
-bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi) {
+// `d_bounds6` (device, 6 floats) receives the bounds of the primitives: they stay on the device (the TLAS build reads the
+// BLAS bounds there), so a build never waits for the GPU.
+bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi, float* d_bounds6) {
     out.n = n;
     out.root = n == 1 ? ~0 : 0;
     Scratch sc(ctx);
-    DevBuf bkeys, b6;
     bpt_status s;
-    if ((s = sc.get(ctx, bkeys, 6 * sizeof(uint32_t)))) return s;
-    if ((s = sc.get(ctx, b6, 6 * sizeof(float)))) return s;
-    LAUNCH(ctx, k_init_bounds, 1, 32, bkeys.as<uint32_t>());
-    LAUNCH(ctx, k_reduce_bounds, std::min(grid_for(n), 1024u), kThreads, d_lo, d_hi, n, bkeys.as<uint32_t>());
-    LAUNCH(ctx, k_decode_bounds, 1, 32, bkeys.as<uint32_t>(), b6.as<float>());
-    float hb[6];
-    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(hb, b6.p, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
-    // sort
-    DevBuf keys2, vals2;
     if ((s = dev_reserve(ctx, out.morton, (size_t)n * 8))) return s;
     if ((s = dev_reserve(ctx, out.prims, (size_t)n * 4))) return s;
+    DevBuf c0, c1, np, lp, nlo, nhi, flags;
+    const uint32_t ni = n >= 2 ? n - 1 : 1;
+    if (n >= 2 && (s = dev_reserve(ctx, out.nodes, (size_t)(n - 1) * 64))) return s;
+    if ((s = sc.get(ctx, c0, (size_t)ni * 4))) return s;
+    if ((s = sc.get(ctx, c1, (size_t)ni * 4))) return s;
+    if ((s = sc.get(ctx, np, (size_t)ni * 4))) return s;
+    if ((s = sc.get(ctx, lp, (size_t)n * 4))) return s;
+    if ((s = sc.get(ctx, nlo, (size_t)ni * 16))) return s;
+    if ((s = sc.get(ctx, nhi, (size_t)ni * 16))) return s;
+    if ((s = sc.get(ctx, flags, (size_t)ni * 4))) return s;
+    if (n <= kSmallMax) {                        // TLAS / small BLAS: one block does everything
+        uint32_t np2 = 2; while (np2 < n) np2 <<= 1;
+        const size_t smem = (size_t)np2 * 12;
+        static bool attr_set = false;
+        if (!attr_set) { BPT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_lbvh_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallMax * 12))); attr_set = true; }
+        k_lbvh_small<<<1, kSmallThreads, smem, ctx->stream>>>(d_lo, d_hi, n, np2, d_bounds6, out.morton.as<uint64_t>(), out.prims.as<uint32_t>(), c0.as<int32_t>(),
+                                                              c1.as<int32_t>(), np.as<int32_t>(), lp.as<int32_t>(), nlo.as<float4>(), nhi.as<float4>(),
+                                                              flags.as<uint32_t>(), out.nodes.as<float4>());
+        ctx->launches++;
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { ctx->err = std::string("launch of k_lbvh_small: ") + cudaGetErrorString(le); return BPT_ERR_CUDA; }
+        return BPT_OK;
+    }
+    DevBuf bkeys;
+    if ((s = sc.get(ctx, bkeys, 6 * sizeof(uint32_t)))) return s;
+    LAUNCH(ctx, k_init_bounds, 1, 32, bkeys.as<uint32_t>());
+    LAUNCH(ctx, k_reduce_bounds, std::min(grid_for(n), 1024u), kThreads, d_lo, d_hi, n, bkeys.as<uint32_t>());
+    LAUNCH(ctx, k_decode_bounds, 1, 32, bkeys.as<uint32_t>(), d_bounds6);
+    // sort
+    DevBuf keys2, vals2;
     if ((s = sc.get(ctx, keys2, (size_t)n * 8))) return s;
     if ((s = sc.get(ctx, vals2, (size_t)n * 4))) return s;
-    LAUNCH(ctx, k_morton, grid_for(n), kThreads, d_lo, d_hi, n, b6.as<float>(), out.morton.as<uint64_t>(), out.prims.as<uint32_t>());
+    LAUNCH(ctx, k_morton, grid_for(n), kThreads, d_lo, d_hi, n, d_bounds6, out.morton.as<uint64_t>(), out.prims.as<uint32_t>());
     uint32_t nblocks = (n + kSortTile - 1) / kSortTile;
     DevBuf hist, dtot;
     if ((s = sc.get(ctx, hist, (size_t)256 * nblocks * 4))) return s;
@@ -377,23 +480,10 @@ bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d
         LAUNCH(ctx, k_sort_scatter, nblocks, kSortThreads, ka, va, kb, vb, n, shift, hist.as<uint32_t>(), nblocks, dtot.as<uint32_t>());
         std::swap(ka, kb); std::swap(va, vb);
     }   // even number of passes: result is back in out.morton / out.prims
-    if (n >= 2) {
-        if ((s = dev_reserve(ctx, out.nodes, (size_t)(n - 1) * 64))) return s;
-        DevBuf c0, c1, np, lp, nlo, nhi, flags;
-        if ((s = sc.get(ctx, c0, (size_t)(n - 1) * 4))) return s;
-        if ((s = sc.get(ctx, c1, (size_t)(n - 1) * 4))) return s;
-        if ((s = sc.get(ctx, np, (size_t)(n - 1) * 4))) return s;
-        if ((s = sc.get(ctx, lp, (size_t)n * 4))) return s;
-        if ((s = sc.get(ctx, nlo, (size_t)(n - 1) * 16))) return s;
-        if ((s = sc.get(ctx, nhi, (size_t)(n - 1) * 16))) return s;
-        if ((s = sc.get(ctx, flags, (size_t)(n - 1) * 4))) return s;
-        BPT_CUDA_TRY(ctx, cudaMemsetAsync(flags.p, 0, (size_t)(n - 1) * 4, ctx->stream));
-        LAUNCH(ctx, k_karras, grid_for(n - 1), kThreads, out.morton.as<uint64_t>(), n, c0.as<int32_t>(), c1.as<int32_t>(), np.as<int32_t>(), lp.as<int32_t>());
-        LAUNCH(ctx, k_refit, grid_for(n), kThreads, n, out.prims.as<uint32_t>(), d_lo, d_hi, c0.as<int32_t>(), c1.as<int32_t>(), np.as<int32_t>(),
-               lp.as<int32_t>(), nlo.as<float4>(), nhi.as<float4>(), flags.as<uint32_t>(), out.nodes.as<float4>());
-    }
-    BPT_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));     // scratch is freed on return; bounds are read on the host
-    for (int k = 0; k < 3; k++) { out.lo[k] = hb[k]; out.hi[k] = hb[3 + k]; }
+    BPT_CUDA_TRY(ctx, cudaMemsetAsync(flags.p, 0, (size_t)(n - 1) * 4, ctx->stream));
+    LAUNCH(ctx, k_karras, grid_for(n - 1), kThreads, out.morton.as<uint64_t>(), n, c0.as<int32_t>(), c1.as<int32_t>(), np.as<int32_t>(), lp.as<int32_t>());
+    LAUNCH(ctx, k_refit, grid_for(n), kThreads, n, out.prims.as<uint32_t>(), d_lo, d_hi, c0.as<int32_t>(), c1.as<int32_t>(), np.as<int32_t>(),
+           lp.as<int32_t>(), nlo.as<float4>(), nhi.as<float4>(), flags.as<uint32_t>(), out.nodes.as<float4>());
     return BPT_OK;
 }
 
@@ -430,16 +520,13 @@ static bpt_status collapse_wide(bpt_context* ctx, DevBvh& b) {
 bpt_status build_blas_two_level(bpt_context* ctx, uint32_t bi) {
     const bpt_blas_desc& bd = ctx->h_blas_desc[bi];
     uint32_t n = bd.num_triangles;
-    Scratch sc(ctx); DevBuf raw, lo, hi, rng; bpt_status s;
+    Scratch sc(ctx); DevBuf raw, lo, hi; bpt_status s;
     if ((s = sc.get(ctx, raw, (size_t)n * 48))) return s;
     if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
     if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
-    if ((s = sc.get(ctx, rng, sizeof(GatherRange)))) return s;
-    GatherRange one{bd, 0u};
-    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(rng.p, &one, sizeof(one), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), rng.as<GatherRange>(), 1u, n,
+    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), (const GatherRange*)nullptr, GatherRange{bd, 0u}, 1u, n,
            (const DInstance*)nullptr, raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
-    if ((s = lbvh_build(ctx, ctx->blas[bi], n, lo.as<float4>(), hi.as<float4>()))) return s;
+    if ((s = lbvh_build(ctx, ctx->blas[bi], n, lo.as<float4>(), hi.as<float4>(), ctx->d_blas_bounds.as<float>() + 6 * (size_t)bi))) return s;
     if ((s = emit_tris(ctx, ctx->blas[bi], raw.as<float4>()))) return s;
     return collapse_wide(ctx, ctx->blas[bi]);
 }
@@ -469,24 +556,20 @@ bpt_status build_blas_merged(bpt_context* ctx) {
     }
     if ((s = sc.get(ctx, rng, ranges.size() * sizeof(GatherRange)))) return s;
     BPT_CUDA_TRY(ctx, cudaMemcpyAsync(rng.p, ranges.data(), ranges.size() * sizeof(GatherRange), cudaMemcpyHostToDevice, ctx->stream));
-    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), rng.as<GatherRange>(),
+    LAUNCH(ctx, k_gather_tris, grid_for(n), kThreads, ctx->d_positions.as<float>(), ctx->d_indices.as<uint32_t>(), rng.as<GatherRange>(), GatherRange{},
            (uint32_t)ranges.size(), n, ctx->d_instances.as<DInstance>(), raw.as<float4>(), lo.as<float4>(), hi.as<float4>());
-    if ((s = lbvh_build(ctx, ctx->blas[0], n, lo.as<float4>(), hi.as<float4>()))) return s;
+    if ((s = lbvh_build(ctx, ctx->blas[0], n, lo.as<float4>(), hi.as<float4>(), ctx->d_blas_bounds.as<float>()))) return s;
     if ((s = emit_tris(ctx, ctx->blas[0], raw.as<float4>()))) return s;
     return collapse_wide(ctx, ctx->blas[0]);
 }
 
 bpt_status build_tlas(bpt_context* ctx) {
     uint32_t n = (uint32_t)ctx->h_instances.size();
-    std::vector<float> bb(6 * ctx->blas.size());
-    for (size_t b = 0; b < ctx->blas.size(); b++)
-        for (int k = 0; k < 3; k++) { bb[6 * b + k] = ctx->blas[b].lo[k]; bb[6 * b + 3 + k] = ctx->blas[b].hi[k]; }
-    Scratch sc(ctx); DevBuf dbb, lo, hi; bpt_status s;
-    if ((s = sc.get(ctx, dbb, bb.size() * 4))) return s;
-    BPT_CUDA_TRY(ctx, cudaMemcpyAsync(dbb.p, bb.data(), bb.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    Scratch sc(ctx); DevBuf lo, hi, tb; bpt_status s;
     if ((s = sc.get(ctx, lo, (size_t)n * 16))) return s;
     if ((s = sc.get(ctx, hi, (size_t)n * 16))) return s;
-    LAUNCH(ctx, k_instance_bounds, grid_for(n), kThreads, ctx->d_instances.as<DInstance>(), n, dbb.as<float>(), lo.as<float4>(), hi.as<float4>());
-    if ((s = lbvh_build(ctx, ctx->tlas, n, lo.as<float4>(), hi.as<float4>()))) return s;
+    if ((s = sc.get(ctx, tb, 6 * sizeof(float)))) return s;
+    LAUNCH(ctx, k_instance_bounds, grid_for(n), kThreads, ctx->d_instances.as<DInstance>(), n, ctx->d_blas_bounds.as<float>(), lo.as<float4>(), hi.as<float4>());
+    if ((s = lbvh_build(ctx, ctx->tlas, n, lo.as<float4>(), hi.as<float4>(), tb.as<float>()))) return s;
     return collapse_wide(ctx, ctx->tlas);
 }

@@ -144,19 +144,21 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 #ifndef BPT_TRACE_MIN_BLOCKS_WIDE
 #define BPT_TRACE_MIN_BLOCKS_WIDE 10
 #endif
-// WIDE (merged mode only): the node phase steps through the 4-wide quantised tree (a.m_wide) instead of the binary one, and a
-// proposed triangle is tested only if the ray passes that leaf's exact box (bpt_wide.cuh: same hits, about half the node fetches).
+// WIDE: the node phase steps through the 4-wide quantised trees (merged: a.m_wide; two-level: the TLAS's and every BLAS's own) instead
+// of the binary ones, and a proposed leaf — a triangle, or an instance of the TLAS — is taken only if the ray passes that leaf's exact
+// box (bpt_wide.cuh: same hits, about half the node fetches).
 template <bool ANY, bool TWO_LEVEL, bool WIDE = false>
-__global__ void __launch_bounds__(kBlock, WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : (TWO_LEVEL ? 8 : BPT_TRACE_MIN_BLOCKS)) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
-    static_assert(!(WIDE && TWO_LEVEL), "the wide tree exists for the merged BVH only");
+__global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : BPT_TRACE_MIN_BLOCKS)) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
     uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
     const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
     const float4* __restrict__ qd = ANY ? a.sh_d : a.ray_d_in;
-    const float4* __restrict__ nodes = TWO_LEVEL ? a.sc.tlas_nodes : (WIDE ? a.m_wide : a.m_nodes);
+    const float4* const tlas_nodes = WIDE ? a.sc.tlas_wide : a.sc.tlas_nodes;
+    const float4* __restrict__ nodes = TWO_LEVEL ? tlas_nodes : (WIDE ? a.m_wide : a.m_nodes);
     const float4* __restrict__ tris = TWO_LEVEL ? nullptr : a.m_tris;
+    const float4* __restrict__ leafbox = nullptr;       // TWO_LEVEL && WIDE: exact leaf boxes of the BLAS being traversed (nullptr: single-leaf BLAS)
     const uint32_t lane = threadIdx.x & 31;
-    int32_t stack[kStackSize];
+    int32_t stack[(TWO_LEVEL && WIDE) ? 2 * kStackSize : kStackSize];     // two wide trees deep
     RayState rs;
     RaySpace sp_;
     rs.found = false; rs.tbest = 0.0f; rs.tcull = 0.0f; rs.tmin = 0.001f; rs.cull_non_opaque = ANY && a.cull_non_opaque != 0;
@@ -179,17 +181,22 @@ __global__ void __launch_bounds__(kBlock, WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : (TW
         for (;;) {
             if (node == kSentinel) {
                 if (leaf != 0) return;                 // postponed triangles of this instance first
-                sp_ = make_space(rs.O, rs.D); nodes = a.sc.tlas_nodes; tris = nullptr; in_blas = false;
+                sp_ = make_space(rs.O, rs.D); nodes = tlas_nodes; tris = nullptr; in_blas = false;
                 node = pop();
                 continue;
             }
             if (node < 0 && !in_blas) {                // TLAS leaf: enter the instance
+                if (WIDE && a.sc.tlas_n != 1 && !leaf_box_hit(a.sc.tlas_leafbox, (uint32_t)~node, sp_, rs.tmin, rs.tcull)) {
+                    node = pop();                      // only proposed by a quantised box: the binary TLAS would not have reached it
+                    continue;
+                }
                 slot = __ldg(a.sc.tlas_prims + (uint32_t)~node);
                 const DInstance& in = a.sc.instances[slot];
                 const DBlas bl = a.sc.blas[in.blas];
                 inst_anyhit = in.anyhit;
                 sp_ = make_space(xf_point(in.w2o, rs.O), xf_vector(in.w2o, rs.D));
-                nodes = bl.nodes; tris = bl.tris; in_blas = true;
+                nodes = WIDE ? bl.wide : bl.nodes; tris = bl.tris; in_blas = true;
+                if (WIDE) leafbox = bl.leafbox;
                 push(kSentinel);
                 node = bl.root;
                 continue;
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(kBlock, WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : (TW
                         sp_ = make_space(rs.O, rs.D);
                         sp = 0; tos = kEmpty; leaf = 0; leaf2 = 0;
                         if (TWO_LEVEL) {
-                            nodes = a.sc.tlas_nodes; tris = nullptr; in_blas = false; slot = 0xffffffffu;
+                            nodes = tlas_nodes; tris = nullptr; in_blas = false; slot = 0xffffffffu;
                             node = a.sc.tlas_n == 0 ? kEmpty : a.sc.tlas_root;
                             settle();
                         } else {
@@ -287,7 +294,15 @@ __global__ void __launch_bounds__(kBlock, WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : (TW
             // ---- triangle phase ----
             while (leaf != 0) {
                 bool accepted;
-                if (WIDE) {                                                  // leaf box and triangle fetched together: one latency, not two
+                if (WIDE && TWO_LEVEL) {
+                    const uint32_t j = (uint32_t)~leaf;
+                    const float4* tp = tris + 3 * (size_t)j;
+                    float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
+                    float4 blo = ta, bhi = ta;
+                    if (leafbox) { blo = BPT_LDG(leafbox + 2 * (size_t)j); bhi = BPT_LDG(leafbox + 2 * (size_t)j + 1); }
+                    accepted = (!leafbox || leaf_box_hit_rec(blo, bhi, sp_, rs.tmin, rs.tcull)) &&
+                               test_triangle_rec<ANY>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, slot, inst_anyhit);
+                } else if (WIDE) {                                           // leaf box and triangle fetched together: one latency, not two
                     const uint32_t j = (uint32_t)~leaf;
                     const float4* tp = tris + 3 * (size_t)j;
                     const float4* bp = a.m_leafbox + 2 * (size_t)(a.m_n == 1 ? 0u : j);
@@ -320,6 +335,8 @@ static const auto k_extend_wide = k_trace_spec<false, false, true>;
 static const auto k_connect_wide = k_trace_spec<true, false, true>;
 static const auto k_extend_two_level = k_trace_spec<false, true>;
 static const auto k_connect_two_level = k_trace_spec<true, true>;
+static const auto k_extend_two_level_wide = k_trace_spec<false, true, true>;
+static const auto k_connect_two_level_wide = k_trace_spec<true, true, true>;
 
 // ---- shade: material + lighting + next direction, emits shadow rays and the next extend ray ---
 struct KernelSink {
@@ -436,20 +453,20 @@ __global__ void k_resolve(const float4* __restrict__ accum, float4* __restrict__
 // ---- arbitrary ray batches (bpt_trace_rays / bpt_trace_shadow_rays) ----------------------------
 __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ DScene sc, const bpt_ray* __restrict__ rays, uint64_t n, uint32_t frame_index,
                                                         bpt_hit* __restrict__ hits, uint8_t* __restrict__ visible, const DInstance* __restrict__ inst,
-                                                        const float4* __restrict__ wide, const float4* __restrict__ leafbox) {
+                                                        const float4* __restrict__ wide, const float4* __restrict__ leafbox, uint32_t wide2) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     bpt_ray r = rays[i];
     float3 O = v3(r.origin[0], r.origin[1], r.origin[2]), D = v3(r.direction[0], r.direction[1], r.direction[2]);
     if (hits) {
-        TraceResult t = wide ? trace_ray_wide<false>(sc, wide, leafbox, O, D, r.tmin, r.tmax, frame_index) : trace_ray<false>(sc, O, D, r.tmin, r.tmax, frame_index);
+        TraceResult t = wide2 ? trace_ray_wide_two_level<false>(sc, O, D, r.tmin, r.tmax, frame_index) : wide ? trace_ray_wide<false>(sc, wide, leafbox, O, D, r.tmin, r.tmax, frame_index) : trace_ray<false>(sc, O, D, r.tmin, r.tmax, frame_index);
         bpt_hit h;
         h.t = t.t; h.u = t.u; h.v = t.v;
         h.instance = t.hit ? inst[t.slot].instance_id : 0xffffffffu;
         h.primitive = t.hit ? t.prim : 0xffffffffu;
         hits[i] = h;
     } else {
-        TraceResult t = wide ? trace_ray_wide<true>(sc, wide, leafbox, O, D, r.tmin, r.tmax, frame_index) : trace_ray<true>(sc, O, D, r.tmin, r.tmax, frame_index);
+        TraceResult t = wide2 ? trace_ray_wide_two_level<true>(sc, O, D, r.tmin, r.tmax, frame_index) : wide ? trace_ray_wide<true>(sc, wide, leafbox, O, D, r.tmin, r.tmax, frame_index) : trace_ray<true>(sc, O, D, r.tmin, r.tmax, frame_index);
         visible[i] = t.hit ? 0 : 1;
     }
 }
@@ -695,6 +712,9 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
         BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, false, true>, kBlock, 0));
         BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, false, true>, kBlock, 0));
         wf.grid_extend_w = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_w = (unsigned)(sms * std::max(ba, 1));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, true, true>, kBlock, 0));
+        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, true, true>, kBlock, 0));
+        wf.grid_extend_w2 = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_w2 = (unsigned)(sms * std::max(ba, 1));
     }
     if (ctx->accel_mode == BPT_ACCEL_MERGED) {
         a.m_nodes = ctx->blas[0].nodes.as<float4>(); a.m_tris = ctx->blas[0].tris.as<float4>(); a.m_root = ctx->blas[0].root; a.m_n = ctx->blas[0].n;
@@ -714,16 +734,26 @@ static bool use_wide(const bpt_context* ctx, uint32_t bounce = 99, bool connect 
     static const uint32_t connect_from = [] { const char* e = getenv("BPT_WIDE_CONNECT_FROM_BOUNCE"); return e ? (uint32_t)atoi(e) : 2u; }();
     return enabled && bounce >= (connect ? connect_from : from_bounce) && ctx->accel_mode == BPT_ACCEL_MERGED && ctx->blas[0].wide.p != nullptr;
 }
+// Two-level mode: the wide TLAS + wide BLASes (BPT_WIDE2=0: binary trees; BPT_WIDE2_FROM_BOUNCE / BPT_WIDE2_CONNECT_FROM_BOUNCE: thresholds).
+static bool use_wide2(const bpt_context* ctx, uint32_t bounce = 99, bool connect = false) {
+    static const bool enabled = [] { const char* e = getenv("BPT_WIDE2"); return !e || atoi(e) != 0; }();
+    static const uint32_t from_bounce = [] { const char* e = getenv("BPT_WIDE2_FROM_BOUNCE"); return e ? (uint32_t)atoi(e) : 1u; }();
+    static const uint32_t connect_from = [] { const char* e = getenv("BPT_WIDE2_CONNECT_FROM_BOUNCE"); return e ? (uint32_t)atoi(e) : 1u; }();
+    if (!enabled || bounce < (connect ? connect_from : from_bounce) || ctx->accel_mode != BPT_ACCEL_TWO_LEVEL) return false;
+    return ctx->tlas.n <= 1 || ctx->tlas.wide.p != nullptr;      // (every BLAS with two or more triangles has its wide form, bvh_build.cu)
+}
 static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     WavefrontState& wf = ctx->wf;
-    if (use_wide(ctx, i)) LAUNCH_T(ctx, 1, k_extend_wide, wf.grid_extend_w, kBlock, a, i);
+    if (use_wide2(ctx, i)) LAUNCH_T(ctx, 1, k_extend_two_level_wide, wf.grid_extend_w2, kBlock, a, i);
+    else if (use_wide(ctx, i)) LAUNCH_T(ctx, 1, k_extend_wide, wf.grid_extend_w, kBlock, a, i);
     else if (ctx->accel_mode == BPT_ACCEL_MERGED) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i);
     else LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i);
     return BPT_OK;
 }
 static bpt_status launch_connect(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     WavefrontState& wf = ctx->wf;
-    if (use_wide(ctx, i, true)) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i);
+    if (use_wide2(ctx, i, true)) LAUNCH_T(ctx, 3, k_connect_two_level_wide, wf.grid_connect_w2, kBlock, a, i);
+    else if (use_wide(ctx, i, true)) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i);
     else if (ctx->accel_mode == BPT_ACCEL_MERGED) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
     else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
     return BPT_OK;
@@ -926,7 +956,8 @@ bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t 
     DScene sc = ctx->scene_view();
     k_trace_batch<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(sc, rays.as<bpt_ray>(), n, frame_index,
         h_hits ? out.as<bpt_hit>() : nullptr, h_hits ? nullptr : out.as<uint8_t>(), ctx->d_instances.as<DInstance>(),
-        use_wide(ctx) ? ctx->blas[0].wide.as<float4>() : nullptr, use_wide(ctx) ? ctx->blas[0].leafbox.as<float4>() : nullptr);
+        use_wide(ctx) ? ctx->blas[0].wide.as<float4>() : nullptr, use_wide(ctx) ? ctx->blas[0].leafbox.as<float4>() : nullptr,
+        use_wide2(ctx) ? 1u : 0u);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_hits ? (void*)h_hits : (void*)h_visible, out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);

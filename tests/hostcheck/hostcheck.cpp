@@ -46,12 +46,24 @@ struct Built {
     std::vector<DInstance> inst;
     std::vector<std::vector<float4>> tris;
     std::vector<DBlas> blas;
+    std::vector<std::vector<float4>> wide, leafbox;   // two-level mode: 4-wide form of every BLAS ([0..nb)) and of the TLAS ([nb])
     std::vector<DTexture> textures;
     std::vector<std::vector<float>> decoded;     // sRGB textures decoded to linear FP32 (as bpt_scene_upload_materials does)
     DScene sc{};
 };
 
 float4 f4(float x, float y, float z, uint32_t w) { return make_float4(x, y, z, u2f(w)); }
+
+// collapse_node4 / leaf_boxes_of_node per binary node, as k_collapse4 runs them
+void collapse_tree(const hc_bvh& hb, std::vector<float4>& wide, std::vector<float4>& leafbox) {
+    wide.assign(hb.n >= 2 ? 4ull * (hb.n - 1) : 0, make_float4(0, 0, 0, 0));
+    leafbox.assign(2ull * hb.n, make_float4(0, 0, 0, 0));
+    const float4* nodes2 = reinterpret_cast<const float4*>(hb.nodes);
+    for (uint32_t i = 0; i + 1 < hb.n; i++) {
+        collapse_node4(nodes2, (int32_t)i, &wide[4ull * i]);
+        leaf_boxes_of_node(nodes2, (int32_t)i, leafbox.data());
+    }
+}
 
 void build(const hc_scene& h, Built& b) {
     b.inst.resize(h.num_instances);
@@ -98,8 +110,14 @@ void build(const hc_scene& h, Built& b) {
             b.tris[0][3 * j] = f4(v0.x, v0.y, v0.z, k); b.tris[0][3 * j + 1] = f4(e1.x, e1.y, e1.z, s); b.tris[0][3 * j + 2] = f4(e2.x, e2.y, e2.z, b.inst[s].anyhit);
         }
     }
-    for (uint32_t bi = 0; bi < nb; bi++)
-        b.blas[bi] = DBlas{reinterpret_cast<const float4*>(h.blas_bvh[bi].nodes), b.tris[bi].data(), h.blas_bvh[bi].root, h.blas_bvh[bi].n, nullptr, nullptr};
+    const bool two_level = h.accel_mode == BPT_ACCEL_TWO_LEVEL;
+    b.wide.resize(nb + 1); b.leafbox.resize(nb + 1);
+    for (uint32_t bi = 0; bi < nb; bi++) {
+        if (two_level) collapse_tree(h.blas_bvh[bi], b.wide[bi], b.leafbox[bi]);
+        b.blas[bi] = DBlas{reinterpret_cast<const float4*>(h.blas_bvh[bi].nodes), b.tris[bi].data(), h.blas_bvh[bi].root, h.blas_bvh[bi].n,
+                           two_level && h.blas_bvh[bi].n >= 2 ? b.wide[bi].data() : nullptr, two_level && h.blas_bvh[bi].n >= 2 ? b.leafbox[bi].data() : nullptr};
+    }
+    if (two_level) collapse_tree(h.tlas, b.wide[nb], b.leafbox[nb]);
     DScene& s = b.sc;
     s.positions = h.positions; s.normals = h.normals; s.tangents = h.tangents; s.texcoords = h.texcoords; s.indices = h.indices;
     s.drawables = h.drawables; s.drawable_va = h.drawable_va; s.materials = h.materials;
@@ -122,6 +140,7 @@ void build(const hc_scene& h, Built& b) {
     s.instances = b.inst.data(); s.num_instances = h.num_instances;
     s.accel_mode = h.accel_mode;
     s.tlas_nodes = reinterpret_cast<const float4*>(h.tlas.nodes); s.tlas_prims = h.tlas.prims; s.tlas_root = h.tlas.root; s.tlas_n = h.tlas.n;
+    s.tlas_wide = two_level && h.tlas.n >= 2 ? b.wide[nb].data() : nullptr; s.tlas_leafbox = two_level && h.tlas.n >= 2 ? b.leafbox[nb].data() : nullptr;
     s.blas = b.blas.data();
     s.dir_lights = h.dir; s.num_dir = h.num_dir; s.point_lights = h.point; s.num_point = h.num_point; s.rect_lights = h.rect; s.num_rect = h.num_rect;
     s.ltc_m0 = h.ltc_m0; s.ltc_m1 = h.ltc_m1; s.ltc_m2 = h.ltc_m2; s.ltc_norm = h.ltc_norm;
@@ -256,16 +275,7 @@ int hc_trace(const hc_scene* h, const bpt_ray* rays, uint64_t n, uint32_t frame_
 
 // 4-wide quantised tree of the merged BVH: collapse_node4 / leaf_boxes_of_node per binary node like k_collapse4, then the
 // run-to-completion wide traversal (trace_ray_wide) that the persistent kernels interleave.
-static void build_wide(const hc_scene& h, std::vector<float4>& wide, std::vector<float4>& leafbox) {
-    const hc_bvh& hb = h.blas_bvh[0];
-    wide.assign(hb.n >= 2 ? 4ull * (hb.n - 1) : 0, make_float4(0, 0, 0, 0));
-    leafbox.assign(2ull * hb.n, make_float4(0, 0, 0, 0));
-    const float4* nodes2 = reinterpret_cast<const float4*>(hb.nodes);
-    for (uint32_t i = 0; i + 1 < hb.n; i++) {
-        collapse_node4(nodes2, (int32_t)i, &wide[4ull * i]);
-        leaf_boxes_of_node(nodes2, (int32_t)i, leafbox.data());
-    }
-}
+static void build_wide(const hc_scene& h, std::vector<float4>& wide, std::vector<float4>& leafbox) { collapse_tree(h.blas_bvh[0], wide, leafbox); }
 __attribute__((visibility("default")))
 int hc_read_wide(const hc_scene* h, float* wide_out, float* leafbox_out) {
     if (h->accel_mode != BPT_ACCEL_MERGED) return 1;
@@ -277,8 +287,18 @@ int hc_read_wide(const hc_scene* h, float* wide_out, float* leafbox_out) {
 }
 __attribute__((visibility("default")))
 int hc_trace_wide(const hc_scene* h, const bpt_ray* rays, uint64_t n, uint32_t frame_index, bpt_hit* hits, uint8_t* visible) {
-    if (h->accel_mode != BPT_ACCEL_MERGED) return 1;
     Built b; build(*h, b);
+    if (h->accel_mode == BPT_ACCEL_TWO_LEVEL) {          // wide TLAS + wide BLASes (build() collapsed them)
+        for (uint64_t i = 0; i < n; i++) {
+            float3 O = v3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), D = v3(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]);
+            if (hits) {
+                TraceResult t = trace_ray_wide_two_level<false>(b.sc, O, D, rays[i].tmin, rays[i].tmax, frame_index);
+                hits[i] = bpt_hit{t.t, t.u, t.v, t.hit ? b.inst[t.slot].instance_id : 0xffffffffu, t.hit ? t.prim : 0xffffffffu};
+            }
+            if (visible) visible[i] = trace_ray_wide_two_level<true>(b.sc, O, D, rays[i].tmin, rays[i].tmax, frame_index).hit ? 0 : 1;
+        }
+        return 0;
+    }
     std::vector<float4> wide, leafbox;
     build_wide(*h, wide, leafbox);
     for (uint64_t i = 0; i < n; i++) {

@@ -353,6 +353,23 @@ def test_wide_bvh_bit_exact(oracle, name):
     del cam
 
 
+@pytest.mark.parametrize("name", ["cornell", "small", "scene_basic"])
+def test_wide_two_level_traversal_bit_exact(oracle, name):
+    """Two-level mode through the 4-wide trees (wide TLAS whose proposed instances must pass their exact world box, then the
+    instance's wide BLAS with the object-space ray — csrc/bpt_wide.cuh: trace_ray_wide_two_level, the steps k_trace_spec<.,true,true>
+    interleaves): hits and visibilities equal the oracle's binary two-level traversal bit for bit."""
+    scene = scenes.scene_basic(os.path.join(GOLDEN, "scene_basic.npz")) if name == "scene_basic" else _scene(name)
+    ctx = oracle.OracleContext(8, 8); ctx.upload_scene(scene, capi.ACCEL_TWO_LEVEL)
+    hs = HC.HostScene(scene, ctx, capi.ACCEL_TWO_LEVEL)
+    rays = _random_rays(scene, 6000, 22)
+    want_h, want_v = ctx.trace_rays(rays, 9), ctx.trace_shadow_rays(rays, 9)
+    got_h, got_v = hs.trace_wide(rays, 9)
+    for f in ("t", "u", "v", "instance", "primitive"):
+        np.testing.assert_array_equal(got_h[f], want_h[f], err_msg=f)
+    np.testing.assert_array_equal(got_v, want_v)
+    assert (want_h["t"] >= 0).mean() > 0.1
+
+
 def test_ddgi_volume_lighting_and_feedback_bit_exact(oracle):
     """The consumer of the probe atlases, calc_ddgi_volume_lighting (ddgi_lighting.hlsl:7-83), and the previous-update
     feedback of the probe lighting pass (ddgi/deferred_lighting.hlsl:102-115): CUDA source (host build) == oracle, and the

@@ -13,10 +13,19 @@ import bisemutum_engine_b200 as pkg
 from bisemutum_engine_b200 import capi, engine, scenes
 
 lib = pkg.load_library()
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]       # optional filter: config-name prefixes ("1_atrium_1080p_64spp", "3_", ...)
 GOLDEN = os.path.join(pkg.REPO_ROOT, "tests", "golden")
 
 
+def want(name):
+    return not ONLY or any(name.startswith(o) for o in ONLY)
+
+
 def run(name, scene, W, H, bounces, spp, mode, ray_length=100.0):
+    if not want(name):
+        return None
+    if callable(scene):
+        scene = scene()
     ctx = capi.Context(lib, W, H)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
@@ -37,20 +46,22 @@ def run(name, scene, W, H, bounces, spp, mode, ray_length=100.0):
 
 luts = scenes.load_ltc_luts(os.path.join(GOLDEN, "ltc_luts.npz"))
 res = []
-res.append(run("0_cornell_512x512_16spp_depth5", scenes.cornell_box(), 512, 512, 5, 16, capi.ACCEL_MERGED))
+res.append(run("0_cornell_512x512_16spp_depth5", scenes.cornell_box, 512, 512, 5, 16, capi.ACCEL_MERGED))
 atr = scenes.atrium()
 res.append(run("1_atrium_1080p_256spp_depth8", atr, 1920, 1080, 8, 256, capi.ACCEL_MERGED))
 res.append(run("1_atrium_1080p_64spp_depth8_two_level", atr, 1920, 1080, 8, 64, capi.ACCEL_TWO_LEVEL))
-res.append(run("2_mixed_lights_1080p_128spp_depth3", scenes.mixed_lights(luts), 1920, 1080, 3, 128, capi.ACCEL_MERGED))
-res.append(run("3_instanced_2Mx512_4k_8spp_depth8", scenes.instanced(), 3840, 2160, 8, 8, capi.ACCEL_TWO_LEVEL, ray_length=1000.0))
+res.append(run("2_mixed_lights_1080p_128spp_depth3", lambda: scenes.mixed_lights(luts), 1920, 1080, 3, 128, capi.ACCEL_MERGED))
+res.append(run("3_instanced_2Mx512_4k_8spp_depth8", scenes.instanced, 3840, 2160, 8, 8, capi.ACCEL_TWO_LEVEL, ray_length=1000.0))
 # config 4: probes
-ctx = capi.Context(lib, 1920, 1080); ctx.upload_scene(atr, capi.ACCEL_MERGED)
-vol = scenes.probe_volume(atr, (32, 32, 16), 256); tab = scenes.ddgi_sample_randoms()
-ctx.trace_probes(vol, tab, 100, 2); ctx.reset_counters()
-t0 = time.perf_counter(); ctx.trace_probes(vol, tab, 0, 2); dt = time.perf_counter() - t0
-c = ctx.counters()
-res.append(dict(config="4_ddgi_probes_32x32x16x256_2bounces", ms_total=dt * 1e3, mrays_per_s=(c.extend_rays + c.shadow_rays) / dt / 1e6,
-                extend_rays=c.extend_rays, shadow_rays=c.shadow_rays, note="wall clock incl. 67 MB read-back of per-ray results"))
-print(json.dumps(res[-1]))
+if want("4_ddgi"):
+    ctx = capi.Context(lib, 1920, 1080); ctx.upload_scene(atr, capi.ACCEL_MERGED)
+    vol = scenes.probe_volume(atr, (32, 32, 16), 256); tab = scenes.ddgi_sample_randoms()
+    ctx.trace_probes(vol, tab, 100, 2); ctx.reset_counters()
+    t0 = time.perf_counter(); ctx.trace_probes(vol, tab, 0, 2); dt = time.perf_counter() - t0
+    c = ctx.counters()
+    res.append(dict(config="4_ddgi_probes_32x32x16x256_2bounces", ms_total=dt * 1e3, mrays_per_s=(c.extend_rays + c.shadow_rays) / dt / 1e6,
+                    extend_rays=c.extend_rays, shadow_rays=c.shadow_rays, note="wall clock incl. 67 MB read-back of per-ray results"))
+    print(json.dumps(res[-1]))
+res = [r for r in res if r]
 os.makedirs(os.path.join(pkg.REPO_ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(pkg.REPO_ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
