@@ -132,6 +132,14 @@ class AoSettings(C.Structure):
     _fields_ = [("range", C.c_float), ("strength", C.c_float), ("half_resolution", C.c_uint32)]
 
 
+class PostSettings(C.Structure):
+    """bpt_post_settings = the bloom fields of PostProcessVolume (include/bisemutum/renderer/post_process_volume.hpp:13-15)."""
+    _fields_ = [("bloom", C.c_uint32), ("bloom_threshold", C.c_float), ("bloom_threshold_softness", C.c_float), ("_pad", C.c_uint32)]
+
+    def __init__(self, bloom=False, bloom_threshold=1.5, bloom_threshold_softness=0.5):
+        super().__init__(1 if bloom else 0, bloom_threshold, bloom_threshold_softness, 0)
+
+
 GBUFFER_TEXEL = np.dtype([("base_color", np.float32, 4), ("normal_roughness", np.float32, 4), ("fresnel", np.float32, 4), ("material_0", np.float32, 4)])
 
 
@@ -187,6 +195,8 @@ BPT_ONLY_API = {
     "resolve_device": [_VP, _U32, _VP],
     "accum_device_ptr": [_VP, C.POINTER(_VP)],
     "upload_accum": [_VP, _VP],
+    "post_process": [_VP, C.POINTER(PostSettings), _U32, _VP],
+    "post_process_device": [_VP, C.POINTER(PostSettings), _U32, _VP],
     "render_ahead": [_VP, C.POINTER(Camera), _U32, _U32, C.POINTER(Settings), _PU32],
     "accumulate_ahead": [_VP, _U32],
     "pending_ahead": [_VP, _PU32, _PU32],
@@ -471,3 +481,12 @@ class Context:
 
     def upload_accum(self, sums: np.ndarray):
         self._call("upload_accum", _ptr(np.ascontiguousarray(sums, dtype=f32)))
+
+    def post_process(self, settings: PostSettings, total_samples: int) -> np.ndarray:
+        """PostProcessPass::render on the accumulated image (bloom + output pass): H x W x 4 float32."""
+        out = np.zeros((self.height, self.width, 4), f32)
+        self._call("post_process", C.byref(settings), total_samples, _ptr(out))
+        return out
+
+    def post_process_device(self, settings: PostSettings, total_samples: int, device_ptr: int):
+        self._call("post_process_device", C.byref(settings), total_samples, _VP(device_ptr))

@@ -124,7 +124,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     if (c->nccl_comm && c->nccl_owned) nccl().CommDestroy(c->nccl_comm);
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
-                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
+                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->d_post, &c->d_post_out, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
                       &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims,
                       &c->tlas.wide, &c->tlas.leafbox};
     for (DevBuf* b : bufs) dev_free(*b);
@@ -484,6 +484,26 @@ bpt_status bpt_resolve_device(bpt_context* c, uint32_t total, float* d_out) {
     NEED(c);
     if (!total || !d_out) return BPT_ERR_INVALID;
     return launch_resolve(c, total, d_out);
+}
+
+bpt_status bpt_post_process_device(bpt_context* c, const bpt_post_settings* st, uint32_t total, float* d_out) {
+    NEED(c);
+    if (!st || !total || !d_out) return BPT_ERR_INVALID;
+    if (st->bloom > 1 || !(st->bloom_threshold_softness >= 0.0f && st->bloom_threshold_softness <= 1.0f) || !(st->bloom_threshold == st->bloom_threshold))
+        return fail(c, BPT_ERR_INVALID, "post settings: bloom must be 0/1, softness in [0, 1]");
+    return launch_post_process(c, *st, total, d_out);
+}
+
+bpt_status bpt_post_process(bpt_context* c, const bpt_post_settings* st, uint32_t total, float* out) {
+    NEED(c);
+    if (!out) return BPT_ERR_INVALID;
+    size_t bytes = (size_t)c->width * c->height * 16;
+    bpt_status s = dev_reserve(c, c->d_post_out, bytes);
+    if (s) return s;
+    if ((s = bpt_post_process_device(c, st, total, c->d_post_out.as<float>()))) return s;
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(out, c->d_post_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
 }
 
 bpt_status bpt_resolve(bpt_context* c, uint32_t total, float* out) {

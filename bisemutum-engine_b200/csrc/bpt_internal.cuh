@@ -84,6 +84,8 @@ struct bpt_context {
     std::vector<DevBuf> arena_chunks; size_t arena_chunk = 0, arena_offset = 0;
 
     WavefrontState wf;
+    DevBuf d_post;               // rgba16_sfloat targets of the bloom chain (post.cu)
+    DevBuf d_post_out;           // staging of bpt_post_process's host read-back
     bool profile = false;
     struct ProfEvent { cudaEvent_t a, b; int cls; };
     std::vector<ProfEvent> prof_events;
@@ -130,4 +132,6 @@ bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol,
 bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, const float* h_rays,
                                const bpt_probe_blend& bl, float* h_irr, float* h_vis);
 bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out);
+// post.cu
+bpt_status launch_post_process(bpt_context* ctx, const bpt_post_settings& st, uint32_t total_samples, float* d_out);
 bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t n, uint32_t frame_index, bpt_hit* h_hits, uint8_t* h_visible);

@@ -331,6 +331,26 @@ BPT_API bpt_status bpt_accum_device_ptr(bpt_context* ctx, float** out_device_ptr
 /* Replaces the sum buffer contents from the host (checkpoint/resume of the history). */
 BPT_API bpt_status bpt_upload_accum(bpt_context* ctx, const float* sum_rgba32f);
 
+/* ---------------------------------------------------------------------------------------
+ * The step after the path: PostProcessPass::render, called with the path tracer's colour
+ * (bisemutum/src/renderer/basic.cpp:228-231; bisemutum/src/renderer/pass/post_process.cpp:92-273) — bloom
+ * (bloom_pre.hlsl, 3 iterations of bloom_filter.hlsl at W>>1, W>>2, W>>3, bloom_combine.hlsl chain) and the output pass
+ * (post_process.hlsl: (colour.xyz, 1)). Settings = the bloom fields of PostProcessVolume
+ * (include/bisemutum/renderer/post_process_volume.hpp:13-15). Input = the resolved accumulation image
+ * (sum * 1/total_samples, as bpt_resolve); every intermediate target is rgba16_sfloat as in the reference
+ * (round-to-nearest-even half stores); sampling contract in oracle/oracle_post.cpp. bloom == 0: out = (colour.xyz, 1).
+ * ------------------------------------------------------------------------------------- */
+typedef struct bpt_post_settings {
+    uint32_t bloom;                    /* PostProcessVolume::bloom, default 0 */
+    float bloom_threshold;             /* default 1.5 */
+    float bloom_threshold_softness;    /* default 0.5, in [0, 1] */
+    uint32_t _pad;
+} bpt_post_settings;
+/* Host destination (W*H rgba32f; synchronises). */
+BPT_API bpt_status bpt_post_process(bpt_context* ctx, const bpt_post_settings* settings, uint32_t total_samples, float* out_rgba32f);
+/* Device destination (no synchronisation). */
+BPT_API bpt_status bpt_post_process_device(bpt_context* ctx, const bpt_post_settings* settings, uint32_t total_samples, float* out_rgba32f_device);
+
 typedef struct bpt_counters {
     uint64_t extend_rays;        /* rays actually traversed by the extend kernel          */
     uint64_t shadow_rays;        /* rays actually traversed by the connect kernel         */

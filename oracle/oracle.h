@@ -96,6 +96,9 @@ BPT_API bpt_status obpt_blend_probes(
     obpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2, uint32_t frame_index,
     const float* ray_radiance_dist, const bpt_probe_blend* blend, float* irradiance_atlas_rgba32f, float* visibility_atlas_rg32f);
 
+/* PostProcessPass::render (post_process.cpp:92-273): bloom chain + output pass on a W x H rgba32f image (oracle_post.cpp). */
+BPT_API bpt_status obpt_post_process_image(const float* in_rgba32f, uint32_t width, uint32_t height, const bpt_post_settings* settings, float* out_rgba32f);
+
 /* Oracle-only: traversal work counters, the source of the "algorithmic bytes" of SURVEY §8d
  * (64 B per node visit, 48 B per triangle test) on a BVH that is bit-identical to the GPU's. */
 typedef struct obpt_stats {

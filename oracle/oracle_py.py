@@ -77,6 +77,8 @@ def library() -> capi.Library:
         L.obpt_wide_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.obpt_wide_stats.restype = C.c_int
         L.obpt_morton63.argtypes, L.obpt_morton63.restype = [C.c_void_p, C.c_void_p, C.c_void_p], C.c_uint64
+        L.obpt_post_process_image.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(capi.PostSettings), C.c_void_p]
+        L.obpt_post_process_image.restype = C.c_int
     return _lib
 
 
@@ -118,6 +120,17 @@ class OracleContext(capi.Context):
         out = np.empty((self.height, self.width, 4), np.float32)
         self._call("render_converged", C.byref(camera), frame_first, num_samples, C.byref(settings), out.ctypes.data_as(C.c_void_p))
         return out
+
+
+def post_process_image(image: np.ndarray, settings: capi.PostSettings) -> np.ndarray:
+    """PostProcessPass::render (post_process.cpp:92-273) on an H x W x 4 float32 image: oracle_post.cpp."""
+    image = np.ascontiguousarray(image, np.float32)
+    h, w = image.shape[:2]
+    out = np.zeros_like(image)
+    st = library().lib.obpt_post_process_image(image.ctypes.data_as(C.c_void_p), w, h, C.byref(settings), out.ctypes.data_as(C.c_void_p))
+    if st != 0:
+        raise capi.BptError(st, "obpt_post_process_image", "")
+    return out
 
 
 def camera_desc(cam: dict, aspect: float) -> CameraDesc:

@@ -64,6 +64,7 @@ def lib():
         _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.hc_trace_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.hc_read_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_void_p]
+        _lib.hc_post_process.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.PostSettings), C.c_void_p]
     return _lib
 
 
@@ -182,3 +183,12 @@ def blend_probes(volume, table, frame_index, rays, irr, vis, irradiance_size=6, 
                           np.ascontiguousarray(rays, np.float32).ctypes.data_as(C.c_void_p), C.byref(bl),
                           irr.ctypes.data_as(C.c_void_p), vis.ctypes.data_as(C.c_void_p))
     return irr, vis
+
+
+def post_process(sums, total_samples, settings):
+    """bpt_post.cuh's per-pixel functions on the host, driven like post.cu's kernels (sums: H x W x 4 float32)."""
+    sums = np.ascontiguousarray(sums, np.float32)
+    h, w = sums.shape[:2]
+    out = np.zeros_like(sums)
+    assert lib().hc_post_process(sums.ctypes.data_as(C.c_void_p), w, h, total_samples, C.byref(settings), out.ctypes.data_as(C.c_void_p)) == 0
+    return out

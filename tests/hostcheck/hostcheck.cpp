@@ -13,6 +13,7 @@
 #include "../../bisemutum-engine_b200/csrc/bpt_ddgi.cuh"
 #include "../../bisemutum-engine_b200/csrc/bpt_aov.cuh"
 #include "../../bisemutum-engine_b200/csrc/bpt_wide.cuh"
+#include "../../bisemutum-engine_b200/csrc/bpt_post.cuh"
 
 using namespace bptd;
 
@@ -403,3 +404,51 @@ __attribute__((visibility("default"))) void hc_surface_eval_lit(const float N[3]
 }
 
 } // extern "C"
+
+// Post-process (bloom + output): the per-pixel device functions of bpt_post.cuh driven like post.cu's kernels drive them
+// (level kernel = horizontal pass into a tile, vertical pass out of it; here the "tile" is the whole target).
+namespace {
+struct HostTex {
+    const std::vector<float3>* px; int w;
+    float3 at(int x, int y) const { return (*px)[(size_t)y * w + x]; }
+};
+struct HostPre {
+    const float* in; int w; float inv; BloomWeights bw;
+    float3 at(int x, int y) const { const float* s = in + ((size_t)y * w + x) * 4; return bloom_pre(v3(s[0] * inv, s[1] * inv, s[2] * inv), bw); }
+};
+template <class Src>
+std::vector<float3> bloom_level(const Src& src, int sw, int sh, int dw, int dh) {
+    std::vector<float3> hpass((size_t)dw * dh), out((size_t)dw * dh);
+    for (int y = 0; y < dh; y++) for (int x = 0; x < dw; x++) hpass[(size_t)y * dw + x] = bloom_horizontal(src, sw, sh, x, y, dw, dh);
+    HostTex ht{&hpass, dw};
+    for (int y = 0; y < dh; y++) for (int x = 0; x < dw; x++) out[(size_t)y * dw + x] = bloom_vertical(ht, x, y, dw, dh);
+    return out;
+}
+}
+extern "C" __attribute__((visibility("default")))
+int hc_post_process(const float* sums_rgba32f, uint32_t width, uint32_t height, uint32_t total_samples, const bpt_post_settings* st, float* out) {
+    const int W = (int)width, H = (int)height;
+    const float inv = 1.0f / (float)total_samples;
+    std::vector<float3> bloom; int bw_ = 1, bh_ = 1;
+    if (st->bloom) {
+        int lw[3], lh[3];
+        for (int i = 0; i < 3; i++) { lw[i] = std::max(W >> (i + 1), 1); lh[i] = std::max(H >> (i + 1), 1); }
+        auto v1 = bloom_level(HostPre{sums_rgba32f, W, inv, bloom_weights(st->bloom_threshold, st->bloom_threshold_softness)}, W, H, lw[0], lh[0]);
+        auto v2 = bloom_level(HostTex{&v1, lw[0]}, lw[0], lh[0], lw[1], lh[1]);
+        auto v3_ = bloom_level(HostTex{&v2, lw[1]}, lw[1], lh[1], lw[2], lh[2]);
+        std::vector<float3> c2((size_t)lw[1] * lh[1]), c1((size_t)lw[0] * lh[0]);
+        for (int y = 0; y < lh[1]; y++) for (int x = 0; x < lw[1]; x++)
+            c2[(size_t)y * lw[1] + x] = bloom_combine(v2[(size_t)y * lw[1] + x], HostTex{&v3_, lw[2]}, lw[2], lh[2], x, y, lw[1], lh[1]);
+        for (int y = 0; y < lh[0]; y++) for (int x = 0; x < lw[0]; x++)
+            c1[(size_t)y * lw[0] + x] = bloom_combine(v1[(size_t)y * lw[0] + x], HostTex{&c2, lw[1]}, lw[1], lh[1], x, y, lw[0], lh[0]);
+        bloom = std::move(c1); bw_ = lw[0]; bh_ = lh[0];
+    }
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+        const float* s = sums_rgba32f + ((size_t)y * W + x) * 4;
+        float3 c = v3(s[0] * inv, s[1] * inv, s[2] * inv);
+        if (st->bloom) c = bloom_combine(c, HostTex{&bloom, bw_}, bw_, bh_, x, y, W, H);
+        float* o = out + ((size_t)y * W + x) * 4;
+        o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = 1.0f;
+    }
+    return 0;
+}
