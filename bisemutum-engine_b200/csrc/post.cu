@@ -11,7 +11,13 @@ using namespace bptd;
 
 namespace {
 
-constexpr int kTX = 32, kTY = 32, kHalo = 5, kRows = kTY + 2 * kHalo, kPostThreads = 256;
+constexpr int kTX = 32, kTY = 16, kHalo = 5, kRows = kTY + 2 * kHalo, kPostThreads = 256;
+// Source footprint of one tile (taps reach 3.24 destination texels = ~6.5 source texels to either side, the source is ~2x the
+// destination): at most ceil((32 + 6.5) * 2.1) + 3 = 84 columns x ceil(26 * 2.1) + 3 = 58 rows for every size >= 10 texels.
+constexpr int kSrcCap = 88 * 60;
+// Both shared-memory images hold values that are half-representable by construction (an rgba16_sfloat target's content), so
+// they are kept as packed halves: 8 B per texel, one LDS.64 per fetch, 47 KB per block -> 4 blocks per SM.
+constexpr size_t kLevelSmem = (size_t)(kSrcCap + kRows * kTX) * sizeof(uint2);
 
 // rgba16_sfloat texel <-> float3 (values are already half-representable: the conversions are exact)
 __device__ __forceinline__ float3 unpack_h4(uint2 p) {
@@ -24,35 +30,81 @@ __device__ __forceinline__ uint2 pack_h4(float3 c) {
     uint2 p; p.x = *reinterpret_cast<uint32_t*>(&a); p.y = *reinterpret_cast<uint32_t*>(&b);
     return p;
 }
+// (raw() / conv() are split so that a batch of loads can be in flight before the first value is used)
 struct TexHalf {                      // an rgba16_sfloat target of an earlier pass
+    typedef uint2 Raw;
     const uint2* p; int w;
-    __device__ float3 at(int x, int y) const { return unpack_h4(__ldg(p + (size_t)y * w + x)); }
+    __device__ Raw raw(int x, int y) const { return __ldg(p + (size_t)y * w + x); }
+    __device__ float3 conv(Raw r) const { return unpack_h4(r); }
+    __device__ float3 at(int x, int y) const { return conv(raw(x, y)); }
 };
 struct TexPre {                       // bloom_pre of the resolved colour, evaluated on fetch (never stored)
+    typedef float4 Raw;
     const float4* accum; int w; float inv; BloomWeights bw;
-    __device__ float3 at(int x, int y) const {
-        float4 s = __ldg(accum + (size_t)y * w + x);
-        return bloom_pre(v3(s.x * inv, s.y * inv, s.z * inv), bw);
-    }
+    __device__ Raw raw(int x, int y) const { return __ldg(accum + (size_t)y * w + x); }
+    __device__ float3 conv(Raw s) const { return bloom_pre(v3(s.x * inv, s.y * inv, s.z * inv), bw); }
+    __device__ float3 at(int x, int y) const { return conv(raw(x, y)); }
+};
+struct TexStaged {                    // the tile's source footprint, fetched (and bloom_pre'd) once into shared memory
+    const uint2* p; int x_lo, y_lo, fw;
+    __device__ float3 at(int x, int y) const { return unpack_h4(p[(y - y_lo) * fw + (x - x_lo)]); }
 };
 struct TexTile {                      // horizontal-pass output of this block's tile (+ halo rows) in shared memory
-    const float* r; const float* g; const float* b; int x0, ybase;
-    __device__ float3 at(int x, int y) const { int i = (y - ybase) * kTX + (x - x0); return v3(r[i], g[i], b[i]); }
+    const uint2* p; int x0, ybase;
+    __device__ float3 at(int x, int y) const { return unpack_h4(p[(y - ybase) * kTX + (x - x0)]); }
 };
 
-// One bloom level: horizontal pass of the tile's rows (+ halo) into shared memory, vertical pass out of it.
+// One bloom level = bloom_horizontal_fs + bloom_vertical_fs of the reference in one launch. Per 32 x 16 tile:
+//   1. the source texels the tile's horizontal pass can touch go to shared memory ONCE (for level 1 that is where the resolve
+//      scale and bloom_pre run: one evaluation per source texel instead of one per bilinear fetch),
+//   2. the horizontal pass of the tile's rows + 5 halo rows goes to shared memory (values as the rgba16_sfloat target holds them),
+//   3. the vertical pass reads it from there and writes the level's only global output (8 B / texel).
+// The footprint is computed with the very coordinate function the taps use (monotone in x and in the offset), so it is exact;
+// a footprint that does not fit (degenerate aspect ratios only) falls back to fetching from global memory.
 template <class Src>
-__global__ void __launch_bounds__(kPostThreads) k_bloom_level(Src src, int sw, int sh, uint2* __restrict__ dst, int dw, int dh) {
-    __shared__ float s_r[kRows * kTX], s_g[kRows * kTX], s_b[kRows * kTX];
+__global__ void __launch_bounds__(kPostThreads, 4) k_bloom_level(Src src, int sw, int sh, uint2* __restrict__ dst, int dw, int dh) {
+    extern __shared__ uint2 smem[];
+    uint2* s_src = smem;                                   // kSrcCap texels
+    uint2* s_h = smem + kSrcCap;                           // kRows * kTX texels
     const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY, ybase = y0 - kHalo;
+    const int x_last = min(x0 + kTX, dw) - 1, row_lo = max(ybase, 0), row_hi = min(y0 + kTY + kHalo, dh) - 1;
+    const float offsets[5] = BPT_BLOOM_OFFSETS;
+    const float tx = 1.0f / (float)dw;
+    const int sx_lo = lin_coord(((float)x0 + 0.5f) / (float)dw + offsets[0] * tx, sw).i0;
+    const int sx_hi = lin_coord(((float)x_last + 0.5f) / (float)dw + offsets[4] * tx, sw).i1;
+    const int sy_lo = sh == dh ? row_lo : lin_coord(((float)row_lo + 0.5f) / (float)dh, sh).i0;
+    const int sy_hi = sh == dh ? row_hi : lin_coord(((float)row_hi + 0.5f) / (float)dh, sh).i1;
+    const int fw = sx_hi - sx_lo + 1, fh = sy_hi - sy_lo + 1;
+    const bool staged = fw * fh <= kSrcCap;                // block-uniform
+    if (staged) {
+        constexpr int kBatch = 8;                          // loads in flight per thread (the first version waited for each one: latency-bound)
+        const int n = fw * fh;
+        const float inv_fw = 1.0f / (float)fw;             // i / fw for i < 2^13: (i + 0.5) * (1 / fw) is never within 1e-3 of an integer
+        for (int base = threadIdx.x; base < n; base += kPostThreads * kBatch) {
+            typename Src::Raw raw[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; k++) {
+                int i = base + k * kPostThreads;
+                if (i < n) { int y = (int)(((float)i + 0.5f) * inv_fw); raw[k] = src.raw(sx_lo + (i - y * fw), sy_lo + y); }
+            }
+#pragma unroll
+            for (int k = 0; k < kBatch; k++) {
+                int i = base + k * kPostThreads;
+                if (i < n) s_src[i] = pack_h4(src.conv(raw[k]));
+            }
+        }
+        __syncthreads();
+    }
+    const TexStaged st{s_src, sx_lo, sy_lo, fw};
     for (int i = threadIdx.x; i < kRows * kTX; i += kPostThreads) {
         int x = x0 + (i % kTX), row = ybase + i / kTX;
         float3 h = v3(0.0f, 0.0f, 0.0f);
-        if (x < dw && row >= 0 && row < dh) h = bloom_horizontal(src, sw, sh, x, row, dw, dh);     // (rows outside the target are never read: the vertical pass clamps)
-        s_r[i] = h.x; s_g[i] = h.y; s_b[i] = h.z;
+        if (x < dw && row >= row_lo && row <= row_hi)      // (rows outside the target are never read: the vertical pass clamps)
+            h = staged ? bloom_horizontal(st, sw, sh, x, row, dw, dh) : bloom_horizontal(src, sw, sh, x, row, dw, dh);
+        s_h[i] = pack_h4(h);
     }
     __syncthreads();
-    const TexTile tile{s_r, s_g, s_b, x0, ybase};
+    const TexTile tile{s_h, x0, ybase};
     for (int i = threadIdx.x; i < kTY * kTX; i += kPostThreads) {
         int x = x0 + (i % kTX), y = y0 + i / kTX;
         if (x < dw && y < dh) dst[(size_t)y * dw + x] = pack_h4(bloom_vertical(tile, x, y, dw, dh));
@@ -80,9 +132,9 @@ __global__ void k_post_output(const float4* __restrict__ accum, float inv, TexHa
 
 } // namespace
 
-#define LAUNCH2(ctx, kernel, grid, block, ...)                                  \
+#define LAUNCH2(ctx, kernel, grid, block, smem_bytes, ...)                                  \
     do {                                                                        \
-        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);             \
+        kernel<<<(grid), (block), (smem_bytes), (ctx)->stream>>>(__VA_ARGS__);  \
         (ctx)->launches++;                                                      \
         cudaError_t le__ = cudaGetLastError();                                  \
         if (le__ != cudaSuccess) { (ctx)->err = std::string("launch of " #kernel ": ") + cudaGetErrorString(le__); return BPT_ERR_CUDA; } \
@@ -107,13 +159,19 @@ bpt_status launch_post_process(bpt_context* ctx, const bpt_post_settings& st, ui
         for (int i = 0; i < 5; i++) t[i] = reinterpret_cast<uint2*>(static_cast<char*>(ctx->d_post.p) + off[i]);
         auto gridt = [&](int w, int h) { return dim3((unsigned)((w + kTX - 1) / kTX), (unsigned)((h + kTY - 1) / kTY)); };
         const BloomWeights bw = bloom_weights(st.bloom_threshold, st.bloom_threshold_softness);
-        LAUNCH2(ctx, k_bloom_level<TexPre>, gridt(lw[0], lh[0]), kPostThreads, TexPre{accum, W, inv, bw}, W, H, t[0], lw[0], lh[0]);
-        LAUNCH2(ctx, k_bloom_level<TexHalf>, gridt(lw[1], lh[1]), kPostThreads, TexHalf{t[0], lw[0]}, lw[0], lh[0], t[1], lw[1], lh[1]);
-        LAUNCH2(ctx, k_bloom_level<TexHalf>, gridt(lw[2], lh[2]), kPostThreads, TexHalf{t[1], lw[1]}, lw[1], lh[1], t[2], lw[2], lh[2]);
-        LAUNCH2(ctx, k_bloom_combine, grid2(lw[1], lh[1]), blk2, t[1], TexHalf{t[2], lw[2]}, lh[2], t[3], lw[1], lh[1]);      // "Bloom Combine Pass #2"
-        LAUNCH2(ctx, k_bloom_combine, grid2(lw[0], lh[0]), blk2, t[0], TexHalf{t[3], lw[1]}, lh[1], t[4], lw[0], lh[0]);      // "Bloom Combine Pass #1"
+        static bool attr_set = false;
+        if (!attr_set) {
+            BPT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bloom_level<TexPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLevelSmem));
+            BPT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bloom_level<TexHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLevelSmem));
+            attr_set = true;
+        }
+        LAUNCH2(ctx, k_bloom_level<TexPre>, gridt(lw[0], lh[0]), kPostThreads, kLevelSmem, TexPre{accum, W, inv, bw}, W, H, t[0], lw[0], lh[0]);
+        LAUNCH2(ctx, k_bloom_level<TexHalf>, gridt(lw[1], lh[1]), kPostThreads, kLevelSmem, TexHalf{t[0], lw[0]}, lw[0], lh[0], t[1], lw[1], lh[1]);
+        LAUNCH2(ctx, k_bloom_level<TexHalf>, gridt(lw[2], lh[2]), kPostThreads, kLevelSmem, TexHalf{t[1], lw[1]}, lw[1], lh[1], t[2], lw[2], lh[2]);
+        LAUNCH2(ctx, k_bloom_combine, grid2(lw[1], lh[1]), blk2, 0, t[1], TexHalf{t[2], lw[2]}, lh[2], t[3], lw[1], lh[1]);      // "Bloom Combine Pass #2"
+        LAUNCH2(ctx, k_bloom_combine, grid2(lw[0], lh[0]), blk2, 0, t[0], TexHalf{t[3], lw[1]}, lh[1], t[4], lw[0], lh[0]);      // "Bloom Combine Pass #1"
         bloom = TexHalf{t[4], lw[0]}; bloom_h = lh[0];
     }
-    LAUNCH2(ctx, k_post_output, grid2(W, H), blk2, accum, inv, bloom, bloom_h, st.bloom ? 1 : 0, reinterpret_cast<float4*>(d_out), W, H);
+    LAUNCH2(ctx, k_post_output, grid2(W, H), blk2, 0, accum, inv, bloom, bloom_h, st.bloom ? 1 : 0, reinterpret_cast<float4*>(d_out), W, H);
     return BPT_OK;
 }
