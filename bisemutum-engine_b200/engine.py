@@ -48,6 +48,8 @@ def host_library():
         h.bpt_host_pass_read_primary.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p]
         h.bpt_host_pass_frame.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         h.bpt_host_pass_frame.restype = C.c_int
+        h.bpt_host_pass_post_process.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
+        h.bpt_host_pass_post_process.restype = C.c_int
         _host = h
     return _host
 
@@ -228,6 +230,14 @@ class Renderer:
 
     def image(self, accumulated_frames: int) -> np.ndarray:
         return self.ctx.resolve(accumulated_frames)
+
+    def post_process(self, bloom: bool = False, bloom_threshold: float = 1.5, bloom_threshold_softness: float = 0.5) -> np.ndarray:
+        """PostProcessPass::render on the camera's accumulated colour (basic.cpp:228-231): the back-buffer image, (H, W, 4) float32."""
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        st = host_library().bpt_host_pass_post_process(self._pass, 1 if bloom else 0, bloom_threshold, bloom_threshold_softness, out.ctypes.data_as(C.c_void_p))
+        if st != 0:
+            raise capi.BptError(st, "PostProcessPass::render", self.lib.fn("last_error")(self.ctx._h).decode())
+        return out
 
     def close(self):
         if self._pass:

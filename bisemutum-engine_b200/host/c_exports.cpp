@@ -192,4 +192,16 @@ HOST_API int bpt_host_pass_frame(bpt_host_pass* p, float ray_length, uint32_t ma
     return (int)p->pass->last_status();
 }
 
+// The step after the pass, as BasicRenderer::render_camera issues it (basic.cpp:228-231): PostProcessPass::render on the
+// camera's accumulated colour, written to `out_rgba32f` (W*H*4 floats, stands in for the back buffer). Returns bpt_status.
+HOST_API int bpt_host_pass_post_process(bpt_host_pass* p, int bloom, float threshold, float softness, float* out_rgba32f) {
+    PostProcessPass post(p->pass->context());
+    post.default_volume_.bloom = bloom != 0; post.default_volume_.bloom_threshold = threshold; post.default_volume_.bloom_threshold_softness = softness;
+    post.set_output(out_rgba32f, p->pass->accumulated_frames(p->camera));
+    gfx::RenderGraph rg;
+    post.render(p->camera, rg, {});
+    rg.execute();
+    return (int)post.last_status();
+}
+
 } // extern "C"

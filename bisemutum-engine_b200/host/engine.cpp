@@ -204,4 +204,23 @@ auto PathTracingPass::accumulated_frames(gfx::Camera const& camera) const -> uin
     return it == camera_history_infos_.end() ? 0 : it->second.frame_count;
 }
 
+// post_process.cpp:92-273: with bloom the reference records "Bloom Pre Pass", 3 x ("Bloom Horizontal Pass #i", "Bloom Vertical
+// Pass #i"), "Bloom Combine Pass #2", "#1", "Bloom Final Combine Pass" and "Post Process Pass"; here they are one pass.
+auto PostProcessPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, InputData const& input) -> void {
+    auto const& volume = default_volume_;
+    struct PassData { gfx::TextureHandle input_color; gfx::TextureHandle input_depth; gfx::TextureHandle output; };
+    auto [builder, pass_data] = rg.add_compute_pass<PassData>("Post Process CUDA");
+    pass_data->input_color = builder.read(input.color);
+    pass_data->input_depth = builder.read(input.depth);
+    pass_data->output = builder.write(rg.add_texture(camera.target_width(), camera.target_height(), 16));
+    builder.set_execution_function<PassData>(
+        [this, volume](CRef<PassData>, gfx::ComputePassContext const&) {
+            bpt_post_settings st{};
+            st.bloom = volume.bloom ? 1u : 0u;
+            st.bloom_threshold = volume.bloom_threshold;
+            st.bloom_threshold_softness = volume.bloom_threshold_softness;
+            status_ = out_ ? bpt_post_process(ctx_, &st, (uint32_t)frames_, out_) : BPT_ERR_INVALID;
+        });
+}
+
 } // namespace bi

@@ -172,6 +172,7 @@ struct PathTracingPass final {
     // frames accumulated for `camera` so far (the `frame_count` of path_tracing.cpp:239-246,473)
     auto accumulated_frames(gfx::Camera const& camera) const -> uint64_t;
     auto last_status() const -> bpt_status { return status_; }
+    auto context() const -> bpt_context* { return ctx_; }
     // Content of OutputData.depth / .gbuffer for `camera`'s current frame (the reference writes them in its first trace
     // pass and "PT Depth", path_tracing.cpp:351-385,421-435; here they are produced on demand by bpt_render_primary).
     auto read_primary_outputs(gfx::Camera const& camera, BasicRenderer::PathTracingSettings const& settings, float* depth, bpt_gbuffer_texel* gbuffer) -> bpt_status;
@@ -187,6 +188,32 @@ private:
 public:
     auto set_frame_count(uint64_t f) -> void { frame_counter_ = f; }
     auto set_prefetch_frames(uint32_t n) -> void { prefetch_frames_ = n ? n : 1; }
+};
+
+// ---- the step after it ------------------------------------------------------------------------------
+// PostProcessVolume (include/bisemutum/renderer/post_process_volume.hpp:12-16): the fields the pass reads.
+struct PostProcessVolume final {
+    bool bloom = false;
+    float bloom_threshold = 1.5f;
+    float bloom_threshold_softness = 0.5f;
+};
+// Drop-in for bi::PostProcessPass (src/renderer/pass/post_process.hpp; render: post_process.cpp:92-273): the same render()
+// signature; records ONE render-graph pass whose lambda calls bpt_post_process (the reference records 2 + 9 passes with bloom).
+struct PostProcessPass final {
+    struct InputData final { gfx::TextureHandle color; gfx::TextureHandle depth; };
+
+    explicit PostProcessPass(bpt_context* ctx) : ctx_(ctx) {}
+    auto render(gfx::Camera const& camera, gfx::RenderGraph& rg, InputData const& input) -> void;
+
+    PostProcessVolume default_volume_;                 // rt::find_volume_component_for(camera.position, default_volume_)
+    auto set_output(float* back_buffer_rgba32f, uint64_t accumulated_frames) -> void { out_ = back_buffer_rgba32f; frames_ = accumulated_frames; }
+    auto last_status() const -> bpt_status { return status_; }
+
+private:
+    bpt_context* ctx_;
+    float* out_ = nullptr;            // stands in for rg.import_back_buffer()
+    uint64_t frames_ = 1;             // samples in the accumulation buffer (PathTracingPass::accumulated_frames)
+    bpt_status status_ = BPT_OK;
 };
 
 } // namespace bi

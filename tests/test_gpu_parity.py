@@ -171,6 +171,9 @@ def test_host_pass_accumulates_like_reference(lib, oracle):
     assert r.frame(max_bounces=4) == 4
     ref.render(engine.camera_matrices(scene.camera, W, H), 3, 1, capi.Settings(max_bounces=4))
     np.testing.assert_array_equal(r.image(4), ref.resolve(4))
+    # the step after the pass (basic.cpp:228-231): PostProcessPass::render on the accumulated colour, through the host mirror
+    np.testing.assert_array_equal(r.post_process(True, 0.4, 0.5), oracle.post_process_image(ref.resolve(4), capi.PostSettings(True, 0.4, 0.5)))
+    np.testing.assert_array_equal(r.post_process(False), oracle.post_process_image(ref.resolve(4), capi.PostSettings(False)))
     cam2 = dict(scene.camera); cam2["position"] = (0.5, 2.2, 6.5)
     r.set_camera(cam2)
     assert r.frame(max_bounces=4) == 1          # history invalidated by the camera change
