@@ -132,6 +132,14 @@ class AoSettings(C.Structure):
     _fields_ = [("range", C.c_float), ("strength", C.c_float), ("half_resolution", C.c_uint32)]
 
 
+class ReflectionSettings(C.Structure):
+    """bpt_reflection_settings = BasicRenderer::ReflectionSettings (renderer/basic.hpp:52-65), mode = raytraced."""
+    _fields_ = [("range", C.c_float), ("strength", C.c_float), ("max_roughness", C.c_float), ("fade_roughness", C.c_float), ("half_resolution", C.c_uint32)]
+
+    def __init__(self, range_=16.0, strength=1.0, max_roughness=0.3, fade_roughness=0.1, half_resolution=True):
+        super().__init__(range_, strength, max_roughness, fade_roughness, 1 if half_resolution else 0)
+
+
 class PostSettings(C.Structure):
     """bpt_post_settings = the bloom fields of PostProcessVolume (include/bisemutum/renderer/post_process_volume.hpp:13-15)."""
     _fields_ = [("bloom", C.c_uint32), ("bloom_threshold", C.c_float), ("bloom_threshold_softness", C.c_float), ("_pad", C.c_uint32)]
@@ -183,6 +191,7 @@ COMMON_API = {
     "debug_read_queue": [_VP, _U32, _U32, _VP, _VP, _VP, _U64, _PU64],
     "render_primary": [_VP, C.POINTER(Camera), _U32, C.POINTER(Settings), _VP, _VP],
     "trace_ao": [_VP, C.POINTER(Camera), _U32, C.POINTER(AoSettings), _VP, _VP, _VP],
+    "trace_reflection": [_VP, C.POINTER(Camera), _U32, C.POINTER(ReflectionSettings), _VP, _VP, _VP, _VP],
     "trace_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _VP],
     "blend_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _VP, C.POINTER(ProbeBlend), _VP, _VP],
     "set_ddgi_volume": [_VP, C.POINTER(ProbeVolume), C.POINTER(ProbeBlend), _VP, _VP],
@@ -394,6 +403,16 @@ class Context:
         assert d.shape == (self.height, self.width) and nr.shape == (self.height, self.width, 4)
         self._call("trace_ao", C.byref(camera), frame_index, C.byref(ao), _ptr(d), _ptr(nr), _ptr(out))
         return out
+
+    def trace_reflection(self, camera: Camera, frame_index: int, depth: np.ndarray, gbuffer: np.ndarray, settings: ReflectionSettings | None = None):
+        """ReflectionPass::render_raytraced (reflection.cpp:317-450) from the camera's depth + G-buffer (render_primary's outputs).
+        Returns (reflection colour (rh, rw, 4), hit positions (rh, rw, 4))."""
+        settings = settings or ReflectionSettings()
+        rh, rw = ((self.height + 1) // 2, (self.width + 1) // 2) if settings.half_resolution else (self.height, self.width)
+        refl = np.zeros((rh, rw, 4), dtype=f32); hit = np.zeros((rh, rw, 4), dtype=f32)
+        self._call("trace_reflection", C.byref(camera), frame_index, C.byref(settings), _ptr(np.ascontiguousarray(depth, dtype=f32)),
+                   _ptr(np.ascontiguousarray(gbuffer, dtype=GBUFFER_TEXEL)), _ptr(refl), _ptr(hit))
+        return refl, hit
 
     def trace_probes(self, volume: ProbeVolume, sample_table: np.ndarray, frame_index: int, num_bounces: int) -> np.ndarray:
         """(num_probes * rays_per_probe, 4) float32: radiance rgb + first hit distance (or -1)."""

@@ -80,4 +80,67 @@ BPT_HD bool ao_pixel_rays(const bpt_camera& cam, uint32_t px, uint32_t py, uint3
 }
 BPT_HD float ao_value(uint32_t occluded_rays, float strength) { return 1.0f - ((float)occluded_rays * strength) / 4.0f; }   // :64
 
+// ---- ray-traced reflections: "RTR Sample Direction" (direction_sample/specular_sample.hlsl:14-83) ----
+// unpack_gbuffer_to_surface (gbuffer.hlsl:35-45) on the texel values of the four G-buffer textures
+BPT_HD void surface_from_gbuffer(const bpt_gbuffer_texel& g, float3& N, float3& T, Surface& s, uint32_t& surface_model) {
+    s = surface_default();
+    surface_model = ftou(g.material_0[3] * 255.5f);
+    s.base_color = v3(g.base_color[0], g.base_color[1], g.base_color[2]);
+    s.f0_color = fresnel_from_gbuffer(make_float2(g.fresnel[0], g.fresnel[1]));
+    s.f90_color = fresnel_from_gbuffer(make_float2(g.fresnel[2], g.fresnel[3]));
+    s.roughness = g.normal_roughness[3];
+    frame_from_gbuffer(v3(g.normal_roughness[0], g.normal_roughness[1], g.normal_roughness[2]), N, T);
+    s.anisotropy = g.material_0[0];
+    s.ior = 1.0f / g.material_0[1];
+    s.opacity = 1.0f;
+}
+// One reflection pixel: false = no ray (background, or rougher than max_roughness); otherwise the ray (origin = the pixel's
+// world position, VNDF-sampled direction) and its weight = specular BSDF * fade / pdf (NaN / Inf -> 0). Texel selection as RTAO.
+BPT_HD bool rtr_pixel_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint32_t rw, uint32_t rh, uint32_t W, uint32_t H, uint32_t frame_index,
+                          uint32_t half_res, const float* depth_img, const bpt_gbuffer_texel* gbuffer, float max_roughness, float fade_roughness,
+                          float3& origin, float3& dir, float3& weight) {
+    float sx = 0.5f, sy = 0.5f;
+    uint32_t tx = px, ty = py;
+    if (half_res) {
+        sx = (frame_index & 1u) ? 0.75f : 0.25f; sy = (frame_index & 2u) ? 0.75f : 0.25f;
+        tx = 2u * px + ((frame_index & 1u) ? 1u : 0u); ty = 2u * py + ((frame_index & 2u) ? 1u : 0u);
+        tx = tx < W ? tx : W - 1u; ty = ty < H ? ty : H - 1u;
+    }
+    float uvx = ((float)px + sx) / (float)rw, uvy = ((float)py + sy) / (float)rh;
+    float depth = depth_img[(size_t)ty * W + tx];
+    if (depth == 0.0f) return false;                                    // :28-33
+    float3 N, T; Surface surf; uint32_t surface_model;
+    surface_from_gbuffer(gbuffer[(size_t)ty * W + tx], N, T, surf, surface_model);
+    if (surf.roughness > max_roughness) return false;                   // :46-50
+    float3 B = cross3(N, T);
+    Frame3 frame = frame_from_nt(N, T);
+    const float* ip = cam.matrix_inv_proj; const float* iv = cam.matrix_inv_view;
+    float nx = uvx * 2.0f - 1.0f, ny = 1.0f - uvy * 2.0f;
+    float vx = ((ip[0] * nx + ip[4] * ny) + ip[8] * depth) + ip[12];
+    float vy = ((ip[1] * nx + ip[5] * ny) + ip[9] * depth) + ip[13];
+    float vz = ((ip[2] * nx + ip[6] * ny) + ip[10] * depth) + ip[14];
+    float vw = ((ip[3] * nx + ip[7] * ny) + ip[11] * depth) + ip[15];
+    vx = vx / vw; vy = vy / vw; vz = vz / vw;
+    float3 Pw = v3(((iv[0] * vx + iv[4] * vy) + iv[8] * vz) + iv[12], ((iv[1] * vx + iv[5] * vy) + iv[9] * vz) + iv[13],
+                   ((iv[2] * vx + iv[6] * vy) + iv[10] * vz) + iv[14]);
+    float3 V = normalize3(v3(iv[12], iv[13], iv[14]) - Pw);             // :57, camera_position_world (camera.hlsl:7-9)
+    float3 V_local = to_local(frame, V);
+    float rx, ry;
+    aniso_roughness(surf.roughness, surf.anisotropy, rx, ry);
+    uint32_t seed = rng_tea(py * rw + px, frame_index);                 // :63
+    float u1 = rng_next(seed);
+    float u2 = rng_next(seed);
+    float3 half_dir = ggx_vndf_sample(V_local, rx, ry, u1, u2);
+    float3 out_local = reflect3(-V_local, half_dir);
+    float pdf_wh = ggx_vndf_pdf(half_dir, V_local, rx, ry);
+    float pdf = pdf_wh / (4.0f * fabsf(dot3(half_dir, V_local)));
+    float3 out_dir = to_world(frame, out_local);
+    float3 spec = bsdf_eval_specular(N, T, B, V, out_dir, surf, surface_model);
+    float fade = 1.0f - tmax_(surf.roughness - fade_roughness, 0.0f) / tmax_(max_roughness - fade_roughness, 0.0001f);
+    weight = (spec * fade) / pdf;
+    if (!is_finite3(weight)) weight = v3s(0.0f);                        // :76-78
+    origin = Pw; dir = out_dir;
+    return true;
+}
+
 } // namespace bptd

@@ -460,6 +460,14 @@ bpt_status bpt_trace_ao(bpt_context* c, const bpt_camera* cam, uint32_t frame_in
     return wavefront_trace_ao(c, *cam, frame_index, *ao, depth, normal_roughness, out_ao);
 }
 
+bpt_status bpt_trace_reflection(bpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_reflection_settings* rs, const float* depth,
+                                const bpt_gbuffer_texel* gbuffer, float* out_reflection, float* out_hit_positions) {
+    NEED(c);
+    if (!cam || !rs || !depth || !gbuffer || !out_reflection || !out_hit_positions) return BPT_ERR_INVALID;
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "trace_reflection before build_accel");
+    return wavefront_trace_reflection(c, *cam, frame_index, *rs, depth, gbuffer, out_reflection, out_hit_positions);
+}
+
 bpt_status bpt_set_ddgi_volume(bpt_context* c, const bpt_probe_volume* vol, const bpt_probe_blend* bl, const float* irr, const float* vis) {
     NEED(c);
     if (!vol || !bl || !irr || !vis) { c->ddgi_enabled = false; return BPT_OK; }        // unbind

@@ -339,6 +339,21 @@ BPT_HD float3 bsdf_eval(float3 N, float3 T, float3 B, float3 V, float3 L, const 
     float3 specular = fr * ndf * vis * tmax_(ll.z, 0.0f);
     return diffuse + specular;
 }
+// the specular term alone: the `bsdf_specular` out-parameter of surface_eval (material.hlsl:81-118 / lit.hlsl:5-35)
+BPT_HD float3 bsdf_eval_specular(float3 N, float3 T, float3 B, float3 V, float3 L, const Surface& s, uint32_t surface_model) {
+    if (surface_model != 1u) return v3s(0.0f);
+    float3 H = normalize3(V + L);
+    float3 lh = v3(dot3(H, T), dot3(H, B), dot3(H, N));
+    float3 lv = v3(dot3(V, T), dot3(V, B), dot3(V, N));
+    float3 ll = v3(dot3(L, T), dot3(L, B), dot3(L, N));
+    if (lv.z <= 0.0f || ll.z <= 0.0f) return v3s(0.0f);
+    float3 fr = schlick_fresnel(s.f0_color, s.f90_color, tmax_(dot3(V, H), 0.0f), s.ior);
+    float rx, ry;
+    aniso_roughness(s.roughness, s.anisotropy, rx, ry);
+    float ndf = ggx_ndf(lh, rx, ry);
+    float vis = ggx_visible_hc(lv, ll, rx, ry);
+    return fr * ndf * vis * tmax_(ll.z, 0.0f);
+}
 // surface_eval_lut (lit.hlsl:37-58)
 BPT_HD float3 bsdf_eval_lut(float3 N, float3 V, const Surface& s, float3 int_diffuse, float3 int_specular, float2 int_brdf, uint32_t surface_model) {
     if (surface_model != 1u) return v3s(0.0f);

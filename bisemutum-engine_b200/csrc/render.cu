@@ -504,6 +504,41 @@ __global__ void __launch_bounds__(kBlock) k_ao_raygen(const __grid_constant__ Re
         }
     }
 }
+// ---- ray-traced reflections (reflection.cpp:317-450): specular_sample -> extend -> shade + connect of ONE bounce ----
+__global__ void __launch_bounds__(kBlock) k_rtr_raygen(const __grid_constant__ RenderArgs a, uint32_t rw, uint32_t rh, uint32_t half_res, float max_roughness,
+                                                       float fade_roughness, float strength, const float* __restrict__ depth, const bpt_gbuffer_texel* __restrict__ gbuffer) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    float3 O = v3s(0.0f), D = v3s(0.0f), Wt = v3s(0.0f);
+    if (p < rw * rh) {
+        valid = rtr_pixel_ray(a.cam, p % rw, p / rw, rw, rh, a.sp.width, a.sp.height, a.frame_base, half_res, depth, gbuffer, max_roughness, fade_roughness, O, D, Wt);
+        a.color[p] = make_float4(0.0f, 0.0f, 0.0f, -1.0f);             // w: hit distance of the reflection ray (probe_mode), -1 = miss / no ray
+    }
+    uint32_t slot = queue_push(&a.qcount[QE + 1], valid);             // (all threads of the warp reach queue_push)
+    if (valid) {
+        Wt = Wt * strength;                                             // deferred_lighting_secondary.hlsl:17
+        a.ray_o_out[slot] = make_float4(O.x, O.y, O.z, __uint_as_float(p));
+        a.ray_d_out[slot] = make_float4(D.x, D.y, D.z, 0.0f);
+        a.ray_w_out[slot] = make_float4(Wt.x, Wt.y, Wt.z, 0.0f);
+    }
+}
+// colour -> (rgb, 1); hit positions: (P, t) on a hit (rt_gbuffer.hlsl:32), (direction, -1) on a miss (:34), (0, 0, 0, -1) without a ray
+__global__ void __launch_bounds__(kBlock) k_rtr_finish(const __grid_constant__ RenderArgs a, uint32_t rw, uint32_t rh, uint32_t half_res, float max_roughness,
+                                                       float fade_roughness, const float* __restrict__ depth, const bpt_gbuffer_texel* __restrict__ gbuffer,
+                                                       float4* __restrict__ out_refl, float4* __restrict__ out_hit) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= rw * rh) return;
+    float4 c = a.color[p];
+    out_refl[p] = make_float4(c.x, c.y, c.z, 1.0f);
+    float3 O, D, Wt;
+    float4 hp = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+    if (rtr_pixel_ray(a.cam, p % rw, p / rw, rw, rh, a.sp.width, a.sp.height, a.frame_base, half_res, depth, gbuffer, max_roughness, fade_roughness, O, D, Wt)) {
+        if (c.w >= 0.0f) { float3 P = O + D * c.w; hp = make_float4(P.x, P.y, P.z, c.w); }
+        else hp = make_float4(D.x, D.y, D.z, -1.0f);
+    }
+    out_hit[p] = hp;
+}
+
 __global__ void k_ao_finish(const float4* __restrict__ color, uint32_t n, float strength, float2* __restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -888,6 +923,46 @@ bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("trace_ao: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}
+
+// Ray-traced reflections: one wave of (specular sample -> extend -> shade -> connect) over the reflection image.
+bpt_status wavefront_trace_reflection(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_reflection_settings& rs, const float* h_depth,
+                                      const bpt_gbuffer_texel* h_gbuffer, float* h_refl, float* h_hit) {
+    bpt_status s;
+    if ((s = wavefront_alloc(ctx))) return s;
+    WavefrontState& wf = ctx->wf;
+    wf.ahead_slots = wf.ahead_cursor = 0;
+    const uint32_t W = ctx->width, H = ctx->height;
+    if (rs.half_resolution && ((W | H) & 1u)) { ctx->err = "trace_reflection: half resolution needs even width and height (texel-centre reads)"; return BPT_ERR_UNSUPPORTED; }
+    const uint32_t rw = rs.half_resolution ? (W + 1) / 2 : W, rh = rs.half_resolution ? (H + 1) / 2 : H, n = rw * rh;     // reflection.cpp:324-325
+    const float max_roughness = rs.max_roughness, fade_roughness = std::min(rs.fade_roughness, max_roughness - 0.0001f);     // reflection.cpp:361-362
+    bpt_settings st{};
+    st.ray_length = rs.range; st.max_bounces = 2; st.nee_mode = BPT_NEE_SHADOW_RAY;
+    RenderArgs a;
+    if ((s = prepare_args(ctx, a, st, 2))) return s;
+    a.cam = cam; a.npx = n; a.nslots = 1; a.frame_base = frame_index; a.probe_mode = 1;
+    DevBuf d_depth, d_gb, d_refl, d_hit;
+    auto cleanup = [&]() { dev_free(d_depth); dev_free(d_gb); dev_free(d_refl); dev_free(d_hit); };
+    if ((s = dev_upload(ctx, d_depth, h_depth, (size_t)W * H * 4)) || (s = dev_upload(ctx, d_gb, h_gbuffer, (size_t)W * H * sizeof(bpt_gbuffer_texel))) ||
+        (s = dev_alloc(ctx, d_refl, (size_t)n * 16)) || (s = dev_alloc(ctx, d_hit, (size_t)n * 16))) { cleanup(); return s; }
+    cudaError_t e = cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream);
+    if (e != cudaSuccess) { cleanup(); ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    a.ray_o_out = wf.ray_o[0].as<float4>(); a.ray_d_out = wf.ray_d[0].as<float4>(); a.ray_w_out = wf.ray_w[0].as<float4>();
+    const uint32_t hr = rs.half_resolution ? 1u : 0u;
+    k_rtr_raygen<<<(n + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(a, rw, rh, hr, max_roughness, fade_roughness, rs.strength, d_depth.as<float>(), d_gb.as<bpt_gbuffer_texel>());
+    ctx->launches++;
+    if ((s = run_bounces(ctx, a, st, 2, n, false))) { cleanup(); return s; }
+    k_rtr_finish<<<(n + kBlock - 1) / kBlock, kBlock, 0, ctx->stream>>>(a, rw, rh, hr, max_roughness, fade_roughness, d_depth.as<float>(), d_gb.as<bpt_gbuffer_texel>(),
+                                                                         d_refl.as<float4>(), d_hit.as<float4>());
+    k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), 0u);
+    ctx->launches += 2;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_refl, d_refl.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hit, d_hit.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) { ctx->err = std::string("trace_reflection: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
     return BPT_OK;
 }
 

@@ -455,6 +455,30 @@ BPT_API bpt_status bpt_trace_ao(
     bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_ao_settings* settings,
     const float* depth /* W*H */, const float* normal_roughness /* W*H*4 */, float* out_ao /* aw*ah*2 */);
 
+/* Ray-traced reflections: ReflectionPass::render_raytraced (src/renderer/pass/reflection.cpp:317-450) =
+ *   "RTR Sample Direction"  shaders/renderer/raytracing/direction_sample/specular_sample.hlsl:14-83 (VNDF sample of the specular
+ *                           lobe from the camera's depth + G-buffer; pixels rougher than max_roughness are skipped, weights fade
+ *                           between fade_roughness and max_roughness),
+ *   "RTR Trace GBuffer"     rt_gbuffer.hlsl:7-36 with ray_length = range (the extend kernel),
+ *   "RTR Lighting"          deferred_lighting_secondary.hlsl:11-111 with lighting_strength = strength (the shade + connect kernels;
+ *                           light visibility by shadow ray as in the path tracer; the IBL term of that shader — prefiltered skybox
+ *                           textures of SkyboxContext — is NOT evaluated: the pass behaves as with DEFERRED_LIGHTING_NO_IBL).
+ * Inputs: full-resolution depth and G-buffer as bpt_render_primary writes them. Outputs: (W or W/2) x (H or H/2) rgba32f
+ * reflection colour (rgb, 1) and hit positions (hit: (P, t); miss: (ray direction, -1); pixel without a ray: (0, 0, 0, -1)).
+ * half_resolution follows the shader's per-frame sub-pixel and needs even W and H. The upscale and denoise passes that follow
+ * in the reference (reflection.cpp:452-571, ReBLUR) are not part of this call. Synchronous. */
+typedef struct bpt_reflection_settings {     /* BasicRenderer::ReflectionSettings (renderer/basic.hpp:52-65), mode = raytraced */
+    float range;                     /* 16 */
+    float strength;                  /* 1 */
+    float max_roughness;             /* 0.3 */
+    float fade_roughness;            /* 0.1 */
+    uint32_t half_resolution;        /* reference default: 1 */
+} bpt_reflection_settings;
+BPT_API bpt_status bpt_trace_reflection(
+    bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_reflection_settings* settings,
+    const float* depth /* W*H */, const bpt_gbuffer_texel* gbuffer /* W*H */,
+    float* out_reflection /* rw*rh*4 */, float* out_hit_positions /* rw*rh*4 */);
+
 /* ---------------------------------------------------------------------------------------
  * DDGI-style probe tracing through the same extend/shade kernels
  * (shaders/renderer/ddgi/trace_gbuffer.hlsl:10-51, ddgi/deferred_lighting.hlsl:12-118).

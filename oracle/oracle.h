@@ -88,6 +88,8 @@ BPT_API bpt_status obpt_render_primary(obpt_context* ctx, const bpt_camera* came
                                        float* out_depth, bpt_gbuffer_texel* out_gbuffer);
 BPT_API bpt_status obpt_trace_ao(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_ao_settings* settings,
                                  const float* depth, const float* normal_roughness, float* out_ao);
+BPT_API bpt_status obpt_trace_reflection(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_reflection_settings* settings,
+                                         const float* depth, const bpt_gbuffer_texel* gbuffer, float* out_reflection, float* out_hit_positions);
 BPT_API bpt_status obpt_trace_probes(
     obpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2,
     uint32_t frame_index, uint32_t num_bounces, float* out_radiance_dist);

@@ -351,6 +351,21 @@ static inline f3 surface_eval(f3 N, f3 T, f3 B, f3 V, f3 L, const SurfaceData& s
     f3 specular = fr * ndf * vis * fmax_(ll.z, 0.0f);
     return diffuse + specular;
 }
+// the specular term alone (the `bsdf_specular` out-parameter of surface_eval, material.hlsl:81-118 / lit.hlsl:5-35)
+static inline f3 surface_eval_specular(f3 N, f3 T, f3 B, f3 V, f3 L, const SurfaceData& s, uint32_t surface_model) {
+    if (surface_model != 1u) return splat3(0.0f);
+    f3 H = normalize(V + L);
+    f3 lh = mk3(dot(H, T), dot(H, B), dot(H, N));
+    f3 lv = mk3(dot(V, T), dot(V, B), dot(V, N));
+    f3 ll = mk3(dot(L, T), dot(L, B), dot(L, N));
+    if (lv.z <= 0.0f || ll.z <= 0.0f) return splat3(0.0f);
+    f3 fr = schlick_fresnel(s.f0_color, s.f90_color, fmax_(dot(V, H), 0.0f), s.ior);
+    float rx, ry;
+    get_anisotropic_roughness(s.roughness, s.anisotropy, rx, ry);
+    float ndf = ggx_ndf(lh, rx, ry);
+    float vis = ggx_visible_hc(lv, ll, rx, ry);
+    return fr * ndf * vis * fmax_(ll.z, 0.0f);
+}
 // core/material/lit.hlsl:37-58
 static inline f3 surface_eval_lut(f3 N, f3 V, const SurfaceData& s, f3 int_diffuse, f3 int_specular, f2 int_brdf, uint32_t surface_model) {
     if (surface_model != 1u) return splat3(0.0f);

@@ -312,11 +312,11 @@ struct ThreadOut {
 // paths, probe * rays + ray for probe paths); `first_t` (optional) receives the first hit distance or -1.
 template <class Acc>
 static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool diffuse_only, uint32_t frame_index, uint32_t pixel,
-                       f3 O, f3 D, Acc* a, float* first_t, ThreadOut& out, uint32_t fp16_n = 0) {
+                       f3 O, f3 D, Acc* a, float* first_t, ThreadOut& out, uint32_t fp16_n = 0, const f3* W0 = nullptr) {
     const Scene& sc = ctx.scene;
     const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);               // path_tracing.cpp:290
     const bool fp16 = st.state_precision == BPT_STATE_REFERENCE_FP16;
-    f3 Wt = splat3(1.0f);
+    f3 Wt = W0 ? *W0 : splat3(1.0f);              // (ray-traced reflections start with the specular sample's weight)
     // Per-sample colour C_s starts at 0, receives this sample's contributions in order, and is added to the
     // FP32 sum buffer when the sample ends (the reference's color texture + accumulate pass,
     // path_tracing.cpp:421-480): sum += C_s, samples in ascending frame order.
@@ -891,6 +891,99 @@ bpt_status obpt_trace_ao(obpt_context* c, const bpt_camera* cam, uint32_t frame_
     work(0);
     for (auto& t : th) t.join();
     for (auto& s : sts) { c->stats.shadow_rays += s.rays; c->stats.shadow_nodes += s.nodes; c->stats.shadow_tris += s.tris; c->counters.shadow_rays += s.rays; c->counters.shadow_rays_per_bounce[1] += s.rays; }
+    return BPT_OK;
+}
+
+// Ray-traced reflections: ReflectionPass::render_raytraced (reflection.cpp:317-450).
+//   specular_sample_cs              direction_sample/specular_sample.hlsl:14-83
+//   trace + lighting                rt_gbuffer.hlsl:7-36 (ray_length = range) and deferred_lighting_secondary.hlsl:11-111
+//                                   (lighting_strength = strength) = one bounce of trace_path starting with the sample's weight;
+//                                   the IBL block (:98-108) is not evaluated (as with DEFERRED_LIGHTING_NO_IBL), see bpt.h.
+bpt_status obpt_trace_reflection(obpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_reflection_settings* rs, const float* depth_img,
+                                 const bpt_gbuffer_texel* gb, float* out_refl, float* out_hit) {
+    CHECK_CTX(c); if (!cam || !rs || !depth_img || !gb || !out_refl || !out_hit) return BPT_ERR_INVALID;
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "trace_reflection before build_accel");
+    const uint32_t W = c->width, H = c->height;
+    if (rs->half_resolution && ((W | H) & 1u)) return fail(c, BPT_ERR_UNSUPPORTED, "trace_reflection: half resolution needs even width and height (texel-centre reads)");
+    const uint32_t rw = rs->half_resolution ? (W + 1) / 2 : W, rh = rs->half_resolution ? (H + 1) / 2 : H;      // reflection.cpp:324-325
+    const float max_roughness = rs->max_roughness;
+    const float fade_roughness = std::min(rs->fade_roughness, max_roughness - 0.0001f);                         // reflection.cpp:361-362
+    bpt_settings st{};
+    st.ray_length = rs->range; st.max_bounces = 2; st.nee_mode = BPT_NEE_SHADOW_RAY;
+    uint32_t nt = obpt_get_threads(c);
+    std::vector<ThreadOut> outs(nt);
+    bool cap = c->capture; c->capture = false;
+    auto work = [&](uint32_t tid) {
+        for (uint32_t p = tid; p < rw * rh; p += nt) {
+            float* refl = out_refl + 4 * (size_t)p; float* hitp = out_hit + 4 * (size_t)p;
+            refl[0] = refl[1] = refl[2] = 0.0f; refl[3] = 1.0f;
+            hitp[0] = hitp[1] = hitp[2] = 0.0f; hitp[3] = -1.0f;
+            uint32_t px = p % rw, py = p / rw;
+            float sx = 0.5f, sy = 0.5f;                                                          // specular_sample.hlsl:18-26
+            uint32_t tx = px, ty = py;
+            if (rs->half_resolution) {
+                sx = (frame_index & 1u) ? 0.75f : 0.25f; sy = (frame_index & 2u) ? 0.75f : 0.25f;
+                tx = std::min(2u * px + ((frame_index & 1u) ? 1u : 0u), W - 1u); ty = std::min(2u * py + ((frame_index & 2u) ? 1u : 0u), H - 1u);
+            }
+            float uvx = ((float)px + sx) / (float)rw, uvy = ((float)py + sy) / (float)rh;
+            float depth = depth_img[(size_t)ty * W + tx];                                        // a sampler at a texel centre = that texel
+            if (depth == 0.0f) continue;                                                         // :28-33 is_depth_background
+            const bpt_gbuffer_texel& t = gb[(size_t)ty * W + tx];
+            GBuffer g;
+            g.base_color = f4{t.base_color[0], t.base_color[1], t.base_color[2], t.base_color[3]};
+            g.normal_roughness = f4{t.normal_roughness[0], t.normal_roughness[1], t.normal_roughness[2], t.normal_roughness[3]};
+            g.fresnel = f4{t.fresnel[0], t.fresnel[1], t.fresnel[2], t.fresnel[3]};
+            g.material_0 = f4{t.material_0[0], t.material_0[1], t.material_0[2], t.material_0[3]};
+            f3 N, T; SurfaceData surface; uint32_t surface_model;
+            unpack_gbuffer_to_surface(g, N, T, surface, surface_model);                          // :41-44
+            if (surface.roughness > max_roughness) continue;                                     // :46-50
+            f3 Bv = cross(N, T);
+            Frame frame = create_frame(N, T);
+            const float* ip = cam->matrix_inv_proj; const float* iv = cam->matrix_inv_view;      // projection.hlsl:5-10
+            float nx = uvx * 2.0f - 1.0f, ny = 1.0f - uvy * 2.0f;
+            float vx = ((ip[0] * nx + ip[4] * ny) + ip[8] * depth) + ip[12];
+            float vy = ((ip[1] * nx + ip[5] * ny) + ip[9] * depth) + ip[13];
+            float vz = ((ip[2] * nx + ip[6] * ny) + ip[10] * depth) + ip[14];
+            float vw = ((ip[3] * nx + ip[7] * ny) + ip[11] * depth) + ip[15];
+            vx = vx / vw; vy = vy / vw; vz = vz / vw;
+            f3 Pw = mk3(((iv[0] * vx + iv[4] * vy) + iv[8] * vz) + iv[12], ((iv[1] * vx + iv[5] * vy) + iv[9] * vz) + iv[13],
+                        ((iv[2] * vx + iv[6] * vy) + iv[10] * vz) + iv[14]);                     // :56
+            f3 V = normalize(mk3(iv[12], iv[13], iv[14]) - Pw);                                  // :57, camera.hlsl:7-9
+            f3 V_local = frame_to_local(frame, V);
+            float rx, ry;
+            get_anisotropic_roughness(surface.roughness, surface.anisotropy, rx, ry);
+            uint32_t seed = rng_tea(py * rw + px, frame_index);                                  // :63
+            float u1 = rng_next(seed);
+            float u2 = rng_next(seed);
+            f3 half_dir = ggx_vndf_sample(V_local, rx, ry, u1, u2);
+            f3 out_local = reflect(-V_local, half_dir);
+            float pdf_wh = ggx_vndf_sample_pdf(half_dir, V_local, rx, ry);
+            float pdf = pdf_wh / (4.0f * fabsf(dot(half_dir, V_local)));
+            f3 out_dir = frame_to_world(frame, out_local);
+            f3 spec = surface_eval_specular(N, T, Bv, V, out_dir, surface, surface_model);       // :70-72
+            float fade = 1.0f - fmax_(surface.roughness - fade_roughness, 0.0f) / fmax_(max_roughness - fade_roughness, 0.0001f);
+            f3 weight = (spec * fade) / pdf;
+            if (!finite3(weight)) weight = splat3(0.0f);                                         // :76-78
+            // rt_gbuffer.hlsl:13-15 skips a zero direction (it cannot happen for a sampled pixel: out_dir is a unit vector)
+            f3 W0 = weight * rs->strength;                                                       // deferred_lighting_secondary.hlsl:17
+            float rgb[3] = {0, 0, 0}, first_t = -1.0f;
+            trace_path<float>(*c, st, false, frame_index, p, Pw, out_dir, rgb, &first_t, outs[tid], 0, &W0);
+            refl[0] = rgb[0]; refl[1] = rgb[1]; refl[2] = rgb[2];
+            if (first_t >= 0.0f) { f3 hp = Pw + out_dir * first_t; hitp[0] = hp.x; hitp[1] = hp.y; hitp[2] = hp.z; hitp[3] = first_t; }     // rt_gbuffer.hlsl:32
+            else { hitp[0] = out_dir.x; hitp[1] = out_dir.y; hitp[2] = out_dir.z; hitp[3] = -1.0f; }                                          // :34
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t i = 1; i < nt; i++) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    c->capture = cap;
+    for (auto& o : outs) {
+        c->counters.extend_rays += o.ext.rays; c->counters.shadow_rays += o.shd.rays;
+        for (int b = 0; b < 16; b++) { c->counters.extend_rays_per_bounce[b] += o.ext_per_bounce[b]; c->counters.shadow_rays_per_bounce[b] += o.shd_per_bounce[b]; }
+        c->stats.extend_rays += o.ext.rays; c->stats.extend_nodes += o.ext.nodes; c->stats.extend_tris += o.ext.tris;
+        c->stats.shadow_rays += o.shd.rays; c->stats.shadow_nodes += o.shd.nodes; c->stats.shadow_tris += o.shd.tris;
+    }
     return BPT_OK;
 }
 

@@ -57,6 +57,8 @@ def lib():
                                    C.POINTER(capi.Settings), C.c_void_p]
         _lib.hc_render_primary.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.Settings), C.c_void_p, C.c_void_p]
         _lib.hc_trace_ao.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.AoSettings), C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.hc_trace_reflection.argtypes = [C.POINTER(HcScene), C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.ReflectionSettings),
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_trace_probes.argtypes = [C.POINTER(HcScene), C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.hc_blend_probes.argtypes = [C.POINTER(capi.ProbeVolume), C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(capi.ProbeBlend), C.c_void_p, C.c_void_p]
         _lib.hc_set_ddgi.argtypes = [C.POINTER(capi.ProbeVolume), C.POINTER(capi.ProbeBlend), C.c_void_p, C.c_void_p]
@@ -132,6 +134,14 @@ class HostScene:
         d = np.ascontiguousarray(depth, np.float32); nr = np.ascontiguousarray(normal_roughness, np.float32)
         lib().hc_trace_ao(C.byref(self.h), C.byref(camera), width, height, frame_index, C.byref(ao), d.ctypes.data_as(C.c_void_p), nr.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         return out
+
+    def trace_reflection(self, camera, width, height, frame_index, depth, gbuffer, settings):
+        rh, rw = ((height + 1) // 2, (width + 1) // 2) if settings.half_resolution else (height, width)
+        refl = np.zeros((rh, rw, 4), np.float32); hit = np.zeros((rh, rw, 4), np.float32)
+        d = np.ascontiguousarray(depth, np.float32); g = np.ascontiguousarray(gbuffer, capi.GBUFFER_TEXEL)
+        lib().hc_trace_reflection(C.byref(self.h), C.byref(camera), width, height, frame_index, C.byref(settings), d.ctypes.data_as(C.c_void_p),
+                                  g.ctypes.data_as(C.c_void_p), refl.ctypes.data_as(C.c_void_p), hit.ctypes.data_as(C.c_void_p))
+        return refl, hit
 
     def trace(self, rays, frame_index=0):
         hits = np.zeros(len(rays), capi.HIT)

@@ -234,6 +234,35 @@ int hc_trace_ao(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32
     return 0;
 }
 
+// Ray-traced reflections (bpt_trace_reflection): rtr_pixel_ray, then one bounce of the same trace / shade functions.
+__attribute__((visibility("default")))
+int hc_trace_reflection(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t height, uint32_t frame_index, const bpt_reflection_settings* rs,
+                        const float* depth, const bpt_gbuffer_texel* gbuffer, float* out_refl, float* out_hit) {
+    Built b; build(*h, b);
+    const uint32_t rw = rs->half_resolution ? (width + 1) / 2 : width, rh = rs->half_resolution ? (height + 1) / 2 : height;
+    const float max_roughness = rs->max_roughness, fade_roughness = std::min(rs->fade_roughness, max_roughness - 0.0001f);
+    ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = 2; sp.nee_mode = BPT_NEE_SHADOW_RAY;
+    sp.ray_length = rs->range; sp.diffuse_only = 0; sp.russian_roulette = 0; sp.rect_shadow = 0; sp.state_precision = BPT_STATE_FP32;
+    for (uint32_t p = 0; p < rw * rh; p++) {
+        float color[4] = {0, 0, 0, -1.0f};
+        float hp[4] = {0, 0, 0, -1.0f};
+        float3 O, D, W;
+        if (rtr_pixel_ray(*cam, p % rw, p / rw, rw, rh, width, height, frame_index, rs->half_resolution, depth, gbuffer, max_roughness, fade_roughness, O, D, W)) {
+            W = W * rs->strength;
+            TraceResult r = trace_ray<false>(b.sc, O, D, 0.001f, sp.ray_length, frame_index);
+            HostSink sink{b.sc, BPT_NEE_SHADOW_RAY, frame_index, color, {}};
+            float3 nO, nD, nW;
+            shade_vertex(b.sc, sp, frame_index, 1u, p, O, D, W, r, sink, nO, nD, nW);
+            for (auto& c : sink.pending) sink.add(c);
+            if (r.hit) { float3 P = O + D * r.t; hp[0] = P.x; hp[1] = P.y; hp[2] = P.z; hp[3] = r.t; }
+            else { hp[0] = D.x; hp[1] = D.y; hp[2] = D.z; hp[3] = -1.0f; }
+        }
+        out_refl[4 * p] = color[0]; out_refl[4 * p + 1] = color[1]; out_refl[4 * p + 2] = color[2]; out_refl[4 * p + 3] = 1.0f;
+        for (int k = 0; k < 4; k++) out_hit[4 * p + k] = hp[k];
+    }
+    return 0;
+}
+
 // Probe paths (bpt_trace_probes): same loop, rays start at probe centres, diffuse-only surface.
 __attribute__((visibility("default")))
 int hc_trace_probes(const hc_scene* h, const bpt_probe_volume* vol, const float* table, uint32_t frame_index, uint32_t num_bounces, float* out) {
