@@ -44,6 +44,16 @@ for sc in (scene, basic):
         depth, g = ctx.render_primary(cam, 0, capi.Settings(max_bounces=4))
         ctx.trace_ao(cam, 1, depth, g["normal_roughness"], 0.5, 0.5, True)
         ctx.trace_ao(cam, 2, depth, g["normal_roughness"], 0.5, 0.5, False)
+        # added in v9: ray-traced reflections (two-level mode = the wide TLAS + wide BLAS kernels), post-process (bloom level kernels
+        # with two shared-memory tiles), rebuilds out of the scratch arena (single-block LBVH for the TLAS / small BLASes, the
+        # multi-kernel radix-sort build for the rest)
+        ctx.trace_reflection(cam, 1, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.5, True))
+        ctx.trace_reflection(cam, 2, depth, g, capi.ReflectionSettings(16.0, 1.0, 0.3, 0.1, False))
+        ctx.render(cam, 0, 2, capi.Settings(max_bounces=3))
+        assert np.isfinite(ctx.post_process(capi.PostSettings(True, 0.3, 0.5), 2)).all()
+        ctx.post_process(capi.PostSettings(False), 2)
+        ctx.build_accel(mode); ctx.build_accel(mode)
+        ctx.clear_accum(); ctx.render(cam, 0, 1, capi.Settings(max_bounces=3))
         if mode == capi.ACCEL_MERGED:
             ctx.read_wide()
             ctx.comm_init(lib.comm_unique_id(), 0, 1); ctx.render(cam, 0, 1, capi.Settings(max_bounces=3)); ctx.reduce(0); ctx.sync()
@@ -52,4 +62,13 @@ r = engine.Renderer(W, H); r.set_scene(scene, capi.ACCEL_MERGED)
 for _ in range(3):
     n = r.frame(max_bounces=4)
 r.image(n); r.close()
+# a tree above the single-block limit (4096 leaves) through the multi-kernel build, both modes, and an odd-sized post-process
+big = scenes.cornell_box(tess=40)
+for mode in (capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED):
+    ctx = capi.Context(lib, 37, 23)
+    ctx.upload_scene(big, mode)
+    cam = engine.camera_matrices(big.camera, 37, 23)
+    ctx.render(cam, 0, 2, capi.Settings(max_bounces=3))
+    assert np.isfinite(ctx.post_process(capi.PostSettings(True, 0.2, 1.0), 2)).all()
+    ctx.close()
 print("sanitize smoke ok")
