@@ -134,10 +134,23 @@ class AoSettings(C.Structure):
 
 class ReflectionSettings(C.Structure):
     """bpt_reflection_settings = BasicRenderer::ReflectionSettings (renderer/basic.hpp:52-65), mode = raytraced."""
-    _fields_ = [("range", C.c_float), ("strength", C.c_float), ("max_roughness", C.c_float), ("fade_roughness", C.c_float), ("half_resolution", C.c_uint32)]
+    _fields_ = [("range", C.c_float), ("strength", C.c_float), ("max_roughness", C.c_float), ("fade_roughness", C.c_float), ("half_resolution", C.c_uint32),
+                ("ibl", C.c_uint32)]
 
-    def __init__(self, range_=16.0, strength=1.0, max_roughness=0.3, fade_roughness=0.1, half_resolution=True):
-        super().__init__(range_, strength, max_roughness, fade_roughness, 1 if half_resolution else 0)
+    def __init__(self, range_=16.0, strength=1.0, max_roughness=0.3, fade_roughness=0.1, half_resolution=True, ibl=False):
+        super().__init__(range_, strength, max_roughness, fade_roughness, 1 if half_resolution else 0, 1 if ibl else 0)
+
+
+class SkyIblDesc(C.Structure):
+    """bpt_sky_ibl_desc: texture sizes of SkyboxContext (src/renderer/context/skybox.cpp:11-29) + Skybox::diffuse/specular_strength."""
+    _fields_ = [("diffuse_size", C.c_uint32), ("specular_size", C.c_uint32), ("specular_levels", C.c_uint32), ("brdf_lut_size", C.c_uint32),
+                ("diffuse_strength", C.c_float), ("specular_strength", C.c_float)]
+
+    def __init__(self, diffuse_size=256, specular_size=256, specular_levels=5, brdf_lut_size=128, diffuse_strength=1.0, specular_strength=1.0):
+        super().__init__(diffuse_size, specular_size, specular_levels, brdf_lut_size, diffuse_strength, specular_strength)
+
+    def specular_texels(self) -> int:
+        return sum(6 * (self.specular_size >> l) ** 2 for l in range(self.specular_levels))
 
 
 class PostSettings(C.Structure):
@@ -191,6 +204,8 @@ COMMON_API = {
     "debug_read_queue": [_VP, _U32, _U32, _VP, _VP, _VP, _U64, _PU64],
     "render_primary": [_VP, C.POINTER(Camera), _U32, C.POINTER(Settings), _VP, _VP],
     "trace_ao": [_VP, C.POINTER(Camera), _U32, C.POINTER(AoSettings), _VP, _VP, _VP],
+    "precompute_sky_ibl": [_VP, C.POINTER(SkyIblDesc)],
+    "debug_read_sky_ibl": [_VP, _VP, _VP, _VP],
     "trace_reflection": [_VP, C.POINTER(Camera), _U32, C.POINTER(ReflectionSettings), _VP, _VP, _VP, _VP],
     "trace_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _VP],
     "blend_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _VP, C.POINTER(ProbeBlend), _VP, _VP],
@@ -403,6 +418,20 @@ class Context:
         assert d.shape == (self.height, self.width) and nr.shape == (self.height, self.width, 4)
         self._call("trace_ao", C.byref(camera), frame_index, C.byref(ao), _ptr(d), _ptr(nr), _ptr(out))
         return out
+
+    def precompute_sky_ibl(self, desc: SkyIblDesc | None = None):
+        """SkyboxPrecomputePass::render on the uploaded sky; returns (diffuse (6, d, d, 4), specular [level] (6, s_l, s_l, 4), brdf lut (n, n, 2))."""
+        desc = desc or SkyIblDesc()
+        self._call("precompute_sky_ibl", C.byref(desc))
+        diffuse = np.zeros((6, desc.diffuse_size, desc.diffuse_size, 4), f32)
+        spec = np.zeros((desc.specular_texels(), 4), f32)
+        brdf = np.zeros((desc.brdf_lut_size, desc.brdf_lut_size, 2), f32)
+        self._call("debug_read_sky_ibl", _ptr(diffuse), _ptr(spec), _ptr(brdf))
+        levels, off = [], 0
+        for l in range(desc.specular_levels):
+            s_ = desc.specular_size >> l
+            levels.append(spec[off:off + 6 * s_ * s_].reshape(6, s_, s_, 4)); off += 6 * s_ * s_
+        return diffuse, levels, brdf
 
     def trace_reflection(self, camera: Camera, frame_index: int, depth: np.ndarray, gbuffer: np.ndarray, settings: ReflectionSettings | None = None):
         """ReflectionPass::render_raytraced (reflection.cpp:317-450) from the camera's depth + G-buffer (render_primary's outputs).

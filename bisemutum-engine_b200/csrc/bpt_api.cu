@@ -49,6 +49,10 @@ DScene bpt_context::scene_view() const {
     s.accel_mode = accel_mode;
     s.tlas_nodes = tlas.nodes.as<float4>(); s.tlas_prims = tlas.prims.as<uint32_t>(); s.tlas_root = tlas.root; s.tlas_n = tlas.n;
     s.tlas_wide = tlas.wide.as<float4>(); s.tlas_leafbox = tlas.leafbox.as<float4>();
+    s.ibl_enabled = ibl_valid ? 1u : 0u; s.ibl_diffuse_size = ibl_desc.diffuse_size; s.ibl_specular_size = ibl_desc.specular_size;
+    s.ibl_specular_levels = ibl_desc.specular_levels; s.ibl_brdf_size = ibl_desc.brdf_lut_size;
+    s.ibl_diffuse = d_ibl_diffuse.as<float4>(); s.ibl_specular = d_ibl_specular.as<float4>(); s.ibl_brdf = d_ibl_brdf.as<float2>();
+    for (int k = 0; k < 3; k++) { s.ibl_diffuse_color[k] = sky_color[k] * ibl_desc.diffuse_strength; s.ibl_specular_color[k] = sky_color[k] * ibl_desc.specular_strength; }
     s.blas = d_blas_table.as<DBlas>();
     s.dir_lights = d_dir.as<bpt_dir_light_data>(); s.num_dir = num_dir;
     s.point_lights = d_point.as<bpt_point_light_data>(); s.num_point = num_point;
@@ -124,7 +128,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     if (c->nccl_comm && c->nccl_owned) nccl().CommDestroy(c->nccl_comm);
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
-                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->d_post, &c->d_post_out, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
+                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->d_post, &c->d_post_out, &c->d_ibl_diffuse, &c->d_ibl_specular, &c->d_ibl_brdf, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
                       &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims,
                       &c->tlas.wide, &c->tlas.leafbox};
     for (DevBuf* b : bufs) dev_free(*b);
@@ -256,6 +260,7 @@ bpt_status bpt_scene_upload_lights(bpt_context* c, const bpt_dir_light_data* d, 
 bpt_status bpt_scene_upload_sky(bpt_context* c, const float* faces, uint32_t size, const float xf[9], const float col[3]) {
     NEED(c);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->ibl_valid = false;                                   // derived from the faces: bpt_precompute_sky_ibl again
     if (faces && size) {
         bpt_status s = dev_upload(c, c->d_sky, faces, (size_t)6 * size * size * 16);
         if (s) return s;
@@ -460,11 +465,38 @@ bpt_status bpt_trace_ao(bpt_context* c, const bpt_camera* cam, uint32_t frame_in
     return wavefront_trace_ao(c, *cam, frame_index, *ao, depth, normal_roughness, out_ao);
 }
 
+bpt_status bpt_precompute_sky_ibl(bpt_context* c, const bpt_sky_ibl_desc* d) {
+    NEED(c);
+    if (!d) return BPT_ERR_INVALID;
+    if (!d->diffuse_size || !d->specular_size || !d->brdf_lut_size || d->specular_levels < 2 || d->specular_levels > 12 ||
+        (d->specular_size >> (d->specular_levels - 1)) == 0 || d->diffuse_size > 4096 || d->specular_size > 4096 || d->brdf_lut_size > 4096)
+        return fail(c, BPT_ERR_INVALID, "sky ibl: sizes out of range (2 <= levels <= 12, last mip >= 1 texel)");
+    c->ibl_valid = false;
+    bpt_status s = launch_precompute_sky_ibl(c, *d);
+    if (s) return s;
+    c->ibl_desc = *d; c->ibl_valid = true;
+    return BPT_OK;
+}
+
+bpt_status bpt_debug_read_sky_ibl(bpt_context* c, float* diffuse, float* specular, float* brdf) {
+    NEED(c);
+    if (!c->ibl_valid) return fail(c, BPT_ERR_STATE, "sky ibl not computed");
+    const bpt_sky_ibl_desc& d = c->ibl_desc;
+    size_t spec = 0;
+    for (uint32_t l = 0; l < d.specular_levels; l++) { size_t n = d.specular_size >> l; spec += 6 * n * n * 16; }
+    if (diffuse) BPT_CUDA_TRY(c, cudaMemcpyAsync(diffuse, c->d_ibl_diffuse.p, (size_t)6 * d.diffuse_size * d.diffuse_size * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (specular) BPT_CUDA_TRY(c, cudaMemcpyAsync(specular, c->d_ibl_specular.p, spec, cudaMemcpyDeviceToHost, c->stream));
+    if (brdf) BPT_CUDA_TRY(c, cudaMemcpyAsync(brdf, c->d_ibl_brdf.p, (size_t)d.brdf_lut_size * d.brdf_lut_size * 8, cudaMemcpyDeviceToHost, c->stream));
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return BPT_OK;
+}
+
 bpt_status bpt_trace_reflection(bpt_context* c, const bpt_camera* cam, uint32_t frame_index, const bpt_reflection_settings* rs, const float* depth,
                                 const bpt_gbuffer_texel* gbuffer, float* out_reflection, float* out_hit_positions) {
     NEED(c);
     if (!cam || !rs || !depth || !gbuffer || !out_reflection || !out_hit_positions) return BPT_ERR_INVALID;
     if (!c->accel_built) return fail(c, BPT_ERR_STATE, "trace_reflection before build_accel");
+    if (rs->ibl > 1 || (rs->ibl && !c->ibl_valid)) return fail(c, rs->ibl > 1 ? BPT_ERR_INVALID : BPT_ERR_STATE, "trace_reflection: settings.ibl needs bpt_precompute_sky_ibl");
     return wavefront_trace_reflection(c, *cam, frame_index, *rs, depth, gbuffer, out_reflection, out_hit_positions);
 }
 

@@ -66,6 +66,8 @@ struct bpt_context {
     DevBuf d_instances;          // DInstance[]
     DevBuf d_dir, d_point, d_rect, d_ltc[4];
     DevBuf d_sky; uint32_t sky_size = 0;
+    DevBuf d_ibl_diffuse, d_ibl_specular, d_ibl_brdf;      // bpt_precompute_sky_ibl (ibl.cu)
+    bool ibl_valid = false; bpt_sky_ibl_desc ibl_desc{};
     DevBuf d_ddgi_irr, d_ddgi_vis;      // atlases of the bound DDGI volume (bpt_set_ddgi_volume)
     bool ddgi_enabled = false; uint32_t ddgi_irr_size = 0, ddgi_vis_size = 0; bpt_probe_volume ddgi_volume{};
     float sky_transform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -134,6 +136,8 @@ bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol,
 bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, const float* h_rays,
                                const bpt_probe_blend& bl, float* h_irr, float* h_vis);
 bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out);
+// ibl.cu
+bpt_status launch_precompute_sky_ibl(bpt_context* ctx, const bpt_sky_ibl_desc& desc);
 // post.cu
 bpt_status launch_post_process(bpt_context* ctx, const bpt_post_settings& st, uint32_t total_samples, float* d_out);
 bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t n, uint32_t frame_index, bpt_hit* h_hits, uint8_t* h_visible);

@@ -60,6 +60,10 @@ struct DScene {
     // sky
     const float4* sky_faces; uint32_t sky_size;
     float sky_transform[9]; float sky_color[3];
+    // image-based lighting of the sky (bpt_precompute_sky_ibl; ibl_enabled = 0: not computed). Layout: bpt_ibl.cuh
+    uint32_t ibl_enabled, ibl_diffuse_size, ibl_specular_size, ibl_specular_levels, ibl_brdf_size;
+    const float4* ibl_diffuse; const float4* ibl_specular; const float2* ibl_brdf;
+    float ibl_diffuse_color[3]; float ibl_specular_color[3];
     // DDGI volume of the previous update (bpt_set_ddgi_volume; ddgi_enabled = 0: none): atlases in bpt_blend_probes' layout
     uint32_t ddgi_enabled, ddgi_irr_size, ddgi_vis_size;
     const float4* ddgi_irradiance; const float2* ddgi_visibility;
@@ -132,8 +136,8 @@ BPT_HD float4 sample_or(const DScene& sc, int32_t tex, float2 uv, float4 dflt) {
 
 // ---- sky (deferred_lighting_secondary.hlsl:24-29; Vulkan cube face rule = inverse of
 //      core/utils/cubemap.hlsl:3-21; bilinear inside the face, clamp to edge) --------------------
-BPT_HD float3 sample_sky(const DScene& sc, float3 d) {
-    if (sc.sky_size == 0) return v3s(0.0f);
+BPT_HD float3 sample_cube(const float4* faces, uint32_t size, float3 d) {
+    if (size == 0) return v3s(0.0f);
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     int face; float s_, t_, ma;
     if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; ma = ax; s_ = d.x >= 0.0f ? -d.z : d.z; t_ = -d.y; }
@@ -141,19 +145,20 @@ BPT_HD float3 sample_sky(const DScene& sc, float3 d) {
     else { face = d.z >= 0.0f ? 4 : 5; ma = az; s_ = d.z >= 0.0f ? d.x : -d.x; t_ = -d.y; }
     if (!(ma > 0.0f)) return v3s(0.0f);
     float u = 0.5f * (s_ / ma + 1.0f), v = 0.5f * (t_ / ma + 1.0f);
-    int n = (int)sc.sky_size;
+    int n = (int)size;
     float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
     float x0f = floorf(x), y0f = floorf(y);
     float fx = x - x0f, fy = y - y0f;
     int x0 = wrap_tc((int)x0f, n, BPT_ADDRESS_CLAMP), x1 = wrap_tc((int)x0f + 1, n, BPT_ADDRESS_CLAMP);
     int y0 = wrap_tc((int)y0f, n, BPT_ADDRESS_CLAMP), y1 = wrap_tc((int)y0f + 1, n, BPT_ADDRESS_CLAMP);
-    const float4* base = sc.sky_faces + (size_t)face * n * n;
+    const float4* base = faces + (size_t)face * n * n;
     float4 a = BPT_LDG(base + (size_t)y0 * n + x0), b = BPT_LDG(base + (size_t)y0 * n + x1);
     float4 c = BPT_LDG(base + (size_t)y1 * n + x0), e = BPT_LDG(base + (size_t)y1 * n + x1);
     float3 top = mix3(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), fx);
     float3 bot = mix3(v3(c.x, c.y, c.z), v3(e.x, e.y, e.z), fx);
     return mix3(top, bot, fy);
 }
+BPT_HD float3 sample_sky(const DScene& sc, float3 d) { return sample_cube(sc.sky_faces, sc.sky_size, d); }
 
 // ---- vertex fetch (core/raytracing/hit.hlsl:27-164) ---------------------------------------------
 struct HitVertex { float3 normal_world, tangent_world, bitangent_world, position_world; float2 texcoord; };

@@ -11,6 +11,7 @@
 #pragma once
 #include "bpt_ltc.cuh"
 #include "bpt_ddgi.cuh"
+#include "bpt_ibl.cuh"
 #include "bpt_trace.cuh"
 
 namespace bptd {
@@ -24,6 +25,7 @@ struct ShadeParams {
     uint32_t rect_shadow;      // NEW switch: 1 = one shadow ray per rect light towards its most representative point
     uint32_t diffuse_only;     // probe tracing: light every vertex as surface_data_diffuse(base_color) (ddgi/deferred_lighting.hlsl:44)
     uint32_t state_precision;  // BPT_STATE_REFERENCE_FP16: the reference's texture formats are applied to the state (see below)
+    uint32_t ibl;              // ray-traced reflections: add the IBL block of deferred_lighting_secondary.hlsl:98-108 (the path tracer compiles it out)
 };
 
 // state_precision = reference_fp16 (SURVEY §8a "storage quantisation"; formats at path_tracing.cpp:248-288 and
@@ -101,6 +103,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
         float dist = fabsf(dot3(P - v3(rl.position2[0], rl.position2[1], rl.position2[2]), ln));
         sink.shadow(P, mrp, (dist / step) * 0.999f, c, sc.num_dir + sc.num_point + l);
     }
+    if (sp.ibl && sc.ibl_enabled) sink.add(ibl_lighting(sc, N, V, surf, surface_model) * Wl);     // deferred_lighting_secondary.hlsl:98-108
     // Probe paths only: the previous DDGI update lights the path's last vertex (ddgi/deferred_lighting.hlsl:102-115:
     // color += ddgi.xyz / ddgi.a * base_color / pi). The reference traces one bounce, so every probe-ray hit gets it; with
     // more bounces (BASELINE configs[4]) it closes the path instead of being added at every vertex.

@@ -723,7 +723,7 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
     a.sc = ctx->scene_view();
     a.sp.width = ctx->width; a.sp.height = ctx->height; a.sp.max_bounces = B; a.sp.nee_mode = st.nee_mode; a.sp.ray_length = st.ray_length;
     a.sp.diffuse_only = 0; a.sp.russian_roulette = st.russian_roulette; a.sp.rect_shadow = st.rect_shadow; a.pixel_jitter = st.pixel_jitter;
-    a.sp.state_precision = st.state_precision;
+    a.sp.state_precision = st.state_precision; a.sp.ibl = 0;
     if (st.state_precision == BPT_STATE_REFERENCE_FP16 && !wf.bcol.p) {          // per-bounce light sums, only this mode needs them
         bpt_status sb = dev_alloc(ctx, wf.bcol, wf.capacity * 16);
         if (sb) return sb;
@@ -941,7 +941,7 @@ bpt_status wavefront_trace_reflection(bpt_context* ctx, const bpt_camera& cam, u
     st.ray_length = rs.range; st.max_bounces = 2; st.nee_mode = BPT_NEE_SHADOW_RAY;
     RenderArgs a;
     if ((s = prepare_args(ctx, a, st, 2))) return s;
-    a.cam = cam; a.npx = n; a.nslots = 1; a.frame_base = frame_index; a.probe_mode = 1;
+    a.cam = cam; a.npx = n; a.nslots = 1; a.frame_base = frame_index; a.probe_mode = 1; a.sp.ibl = rs.ibl;
     DevBuf d_depth, d_gb, d_refl, d_hit;
     auto cleanup = [&]() { dev_free(d_depth); dev_free(d_gb); dev_free(d_refl); dev_free(d_hit); };
     if ((s = dev_upload(ctx, d_depth, h_depth, (size_t)W * H * 4)) || (s = dev_upload(ctx, d_gb, h_gbuffer, (size_t)W * H * sizeof(bpt_gbuffer_texel))) ||

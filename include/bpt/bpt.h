@@ -455,14 +455,33 @@ BPT_API bpt_status bpt_trace_ao(
     bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_ao_settings* settings,
     const float* depth /* W*H */, const float* normal_roughness /* W*H*4 */, float* out_ao /* aw*ah*2 */);
 
+/* Image-based lighting of the sky: SkyboxPrecomputePass::render (src/renderer/pass/skybox_precompute.cpp:66-162) =
+ *   "IBL BRDF LUT"                 shaders/renderer/skybox/ibl_brdf_lut.hlsl:8-32               rg8_unorm, brdf_lut_size^2 (reference 128)
+ *   "Skybox Precompute Diffuse"    shaders/renderer/skybox/skybox_precompute_diffuse.hlsl:12-41  rgba16_sfloat cube, diffuse_size (256)
+ *   "Skybox Precompute Specular i" shaders/renderer/skybox/skybox_precompute_specular.hlsl:12-41 rgba16_sfloat cube, specular_size (256),
+ *                                                                                                specular_levels mips (5), roughness = i / (levels - 1)
+ * computed from the faces given to bpt_scene_upload_sky (texture sizes / formats: src/renderer/context/skybox.cpp:11-29). The
+ * results stay on the device and feed the IBL block of the secondary lighting shader (bpt_trace_reflection with settings.ibl);
+ * diffuse_strength / specular_strength are Skybox::diffuse_strength / specular_strength (scene_basic/skybox.hpp:19-20), multiplied
+ * with the sky colour as SkyboxContext::update_shader_params does (skybox.cpp:40-43). A later bpt_scene_upload_sky invalidates them.
+ * bpt_debug_read_sky_ibl copies them out (any pointer may be NULL): diffuse 6*d*d*4 floats, specular sum over levels of 6*s_i*s_i*4
+ * floats (level 0 first), brdf lut n*n*2 floats. */
+typedef struct bpt_sky_ibl_desc {
+    uint32_t diffuse_size, specular_size, specular_levels, brdf_lut_size;
+    float diffuse_strength, specular_strength;
+} bpt_sky_ibl_desc;
+BPT_API bpt_status bpt_precompute_sky_ibl(bpt_context* ctx, const bpt_sky_ibl_desc* desc);
+BPT_API bpt_status bpt_debug_read_sky_ibl(bpt_context* ctx, float* diffuse_rgba32f, float* specular_rgba32f, float* brdf_lut_rg32f);
+
 /* Ray-traced reflections: ReflectionPass::render_raytraced (src/renderer/pass/reflection.cpp:317-450) =
  *   "RTR Sample Direction"  shaders/renderer/raytracing/direction_sample/specular_sample.hlsl:14-83 (VNDF sample of the specular
  *                           lobe from the camera's depth + G-buffer; pixels rougher than max_roughness are skipped, weights fade
  *                           between fade_roughness and max_roughness),
  *   "RTR Trace GBuffer"     rt_gbuffer.hlsl:7-36 with ray_length = range (the extend kernel),
  *   "RTR Lighting"          deferred_lighting_secondary.hlsl:11-111 with lighting_strength = strength (the shade + connect kernels;
- *                           light visibility by shadow ray as in the path tracer; the IBL term of that shader — prefiltered skybox
- *                           textures of SkyboxContext — is NOT evaluated: the pass behaves as with DEFERRED_LIGHTING_NO_IBL).
+ *                           light visibility by shadow ray as in the path tracer; with settings.ibl the IBL block :98-108 is
+ *                           evaluated from the textures of bpt_precompute_sky_ibl, otherwise the pass behaves as with
+ *                           DEFERRED_LIGHTING_NO_IBL).
  * Inputs: full-resolution depth and G-buffer as bpt_render_primary writes them. Outputs: (W or W/2) x (H or H/2) rgba32f
  * reflection colour (rgb, 1) and hit positions (hit: (P, t); miss: (ray direction, -1); pixel without a ray: (0, 0, 0, -1)).
  * half_resolution follows the shader's per-frame sub-pixel and needs even W and H. The upscale and denoise passes that follow
@@ -473,6 +492,7 @@ typedef struct bpt_reflection_settings {     /* BasicRenderer::ReflectionSetting
     float max_roughness;             /* 0.3 */
     float fade_roughness;            /* 0.1 */
     uint32_t half_resolution;        /* reference default: 1 */
+    uint32_t ibl;                    /* 1: add the IBL block of the lighting shader (needs bpt_precompute_sky_ibl); 0: lights + sky only */
 } bpt_reflection_settings;
 BPT_API bpt_status bpt_trace_reflection(
     bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_reflection_settings* settings,

@@ -88,6 +88,8 @@ BPT_API bpt_status obpt_render_primary(obpt_context* ctx, const bpt_camera* came
                                        float* out_depth, bpt_gbuffer_texel* out_gbuffer);
 BPT_API bpt_status obpt_trace_ao(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_ao_settings* settings,
                                  const float* depth, const float* normal_roughness, float* out_ao);
+BPT_API bpt_status obpt_precompute_sky_ibl(obpt_context* ctx, const bpt_sky_ibl_desc* desc);
+BPT_API bpt_status obpt_debug_read_sky_ibl(obpt_context* ctx, float* diffuse_rgba32f, float* specular_rgba32f, float* brdf_lut_rg32f);
 BPT_API bpt_status obpt_trace_reflection(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_reflection_settings* settings,
                                          const float* depth, const bpt_gbuffer_texel* gbuffer, float* out_reflection, float* out_hit_positions);
 BPT_API bpt_status obpt_trace_probes(

@@ -63,8 +63,8 @@ static inline f4 sample_or_default(const Scene& sc, int32_t tex, f2 uv, f4 dflt)
 
 // ---- sky: deferred_lighting_secondary.hlsl:24-29; face/uv selection is the Vulkan cube rule,
 //      the inverse of core/utils/cubemap.hlsl:3-21; bilinear inside the face, clamp to edge. ----
-static inline f3 sample_sky(const Scene& sc, f3 d) {
-    if (sc.sky_size == 0) return splat3(0.0f);
+static inline f3 sample_cube(const float* faces, uint32_t size, f3 d) {
+    if (size == 0) return splat3(0.0f);
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     int face; float sc_, tc, ma;
     if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; ma = ax; sc_ = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; }
@@ -72,17 +72,47 @@ static inline f3 sample_sky(const Scene& sc, f3 d) {
     else { face = d.z >= 0.0f ? 4 : 5; ma = az; sc_ = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; }
     if (!(ma > 0.0f)) return splat3(0.0f);
     float u = 0.5f * (sc_ / ma + 1.0f), v = 0.5f * (tc / ma + 1.0f);
-    int n = (int)sc.sky_size;
+    int n = (int)size;
     float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
     float x0f = floorf(x), y0f = floorf(y);
     float fx = x - x0f, fy = y - y0f;
     int x0 = wrap_coord((int)x0f, n, BPT_ADDRESS_CLAMP), x1 = wrap_coord((int)x0f + 1, n, BPT_ADDRESS_CLAMP);
     int y0 = wrap_coord((int)y0f, n, BPT_ADDRESS_CLAMP), y1 = wrap_coord((int)y0f + 1, n, BPT_ADDRESS_CLAMP);
-    const float* base = &sc.sky_faces[(size_t)face * n * n * 4];
+    const float* base = faces + (size_t)face * n * n * 4;
     auto tx = [&](int xx, int yy) { const float* p = base + ((size_t)yy * n + xx) * 4; return mk3(p[0], p[1], p[2]); };
     f3 top = lerp3(tx(x0, y0), tx(x1, y0), fx);
     f3 bot = lerp3(tx(x0, y1), tx(x1, y1), fx);
     return lerp3(top, bot, fy);
+}
+static inline f3 sample_sky(const Scene& sc, f3 d) { return sample_cube(sc.sky_faces.data(), sc.sky_size, d); }
+
+// ---- image-based lighting: the IBL block of deferred_lighting_secondary.hlsl:98-108 (textures: obpt_precompute_sky_ibl below).
+// skybox_sampler is linear / clamp_to_edge with the default NEAREST mip mode (src/renderer/context/skybox.cpp:31-37,
+// include/bisemutum/rhi/sampler.hpp:40): the specular level is ceil(lod + 0.5) - 1 (the Vulkan rule for nearest mip selection).
+static inline f3 ibl_lighting(const Scene& sc, f3 N, f3 V, const SurfaceData& surf, uint32_t surface_model) {
+    const float* m = sc.sky_transform;
+    auto xf = [&](f3 d) { return mk3((m[0] * d.x + m[1] * d.y) + m[2] * d.z, (m[3] * d.x + m[4] * d.y) + m[5] * d.z, (m[6] * d.x + m[7] * d.y) + m[8] * d.z); };
+    const bpt_sky_ibl_desc& d = sc.ibl_desc;
+    f3 diffuse_color = mk3(sc.sky_color[0] * d.diffuse_strength, sc.sky_color[1] * d.diffuse_strength, sc.sky_color[2] * d.diffuse_strength);      // skybox.cpp:42
+    f3 specular_color = mk3(sc.sky_color[0] * d.specular_strength, sc.sky_color[1] * d.specular_strength, sc.sky_color[2] * d.specular_strength);  // skybox.cpp:43
+    f3 ibl_diffuse = sample_cube(sc.ibl_diffuse.data(), d.diffuse_size, xf(N)) * diffuse_color;                 // :99-100
+    float lod = surf.roughness * (float)(d.specular_levels - 1u);                                               // :102-104
+    int level = (int)ceilf(lod + 0.5f) - 1;
+    level = level < 0 ? 0 : (level >= (int)d.specular_levels ? (int)d.specular_levels - 1 : level);
+    size_t offset = 0;
+    for (int l = 0; l < level; l++) { size_t s = d.specular_size >> l; offset += 6 * s * s * 4; }
+    f3 ibl_specular = sample_cube(sc.ibl_specular.data() + offset, d.specular_size >> level, xf(reflect(-V, N))) * specular_color;
+    const int n = (int)d.brdf_lut_size;                                                                         // :105 bilinear, clamp
+    float x = dot(N, V) * (float)n - 0.5f, y = surf.roughness * (float)n - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = wrap_coord((int)x0f, n, BPT_ADDRESS_CLAMP), x1 = wrap_coord((int)x0f + 1, n, BPT_ADDRESS_CLAMP);
+    int y0 = wrap_coord((int)y0f, n, BPT_ADDRESS_CLAMP), y1 = wrap_coord((int)y0f + 1, n, BPT_ADDRESS_CLAMP);
+    auto tx = [&](int xx, int yy) { const float* p = &sc.ibl_brdf[((size_t)yy * n + xx) * 2]; return f2{p[0], p[1]}; };
+    f2 a = tx(x0, y0), b = tx(x1, y0), c = tx(x0, y1), e = tx(x1, y1);
+    f2 top = f2{lerpf(a.x, b.x, fx), lerpf(a.y, b.y, fx)}, bot = f2{lerpf(c.x, e.x, fx), lerpf(c.y, e.y, fx)};
+    f2 brdf = f2{lerpf(top.x, bot.x, fy), lerpf(top.y, bot.y, fy)};
+    return surface_eval_lut(N, V, surf, ibl_diffuse, ibl_specular, brdf, surface_model);                        // :106-107
 }
 
 // ---- vertex fetch: core/raytracing/hit.hlsl:27-164 ---------------------------------------------
@@ -312,7 +342,7 @@ struct ThreadOut {
 // paths, probe * rays + ray for probe paths); `first_t` (optional) receives the first hit distance or -1.
 template <class Acc>
 static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool diffuse_only, uint32_t frame_index, uint32_t pixel,
-                       f3 O, f3 D, Acc* a, float* first_t, ThreadOut& out, uint32_t fp16_n = 0, const f3* W0 = nullptr) {
+                       f3 O, f3 D, Acc* a, float* first_t, ThreadOut& out, uint32_t fp16_n = 0, const f3* W0 = nullptr, bool ibl = false) {
     const Scene& sc = ctx.scene;
     const uint32_t B = std::min(std::max(st.max_bounces, 2u), 16u);               // path_tracing.cpp:290
     const bool fp16 = st.state_precision == BPT_STATE_REFERENCE_FP16;
@@ -416,6 +446,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
             if (wide) out.shd_wide_rays++;
             if (!trace_any(sc, P, mrp, 0.001f, (dist / step) * 0.999f, frame_index, out.shd, false, wide)) out.pending.push_back(c);
         }
+        if (ibl && sc.ibl_valid) add(ibl_lighting(sc, N, V, surf, surface_model) * Wl);       // deferred_lighting_secondary.hlsl:98-108 (RTR only)
         // Probe paths: the previous DDGI update at the path's last vertex (ddgi/deferred_lighting.hlsl:102-115). The reference
         // traces one bounce, so every probe-ray hit receives it; with more bounces it closes the path.
         if (diffuse_only && ctx.ddgi_enabled && i + 1 >= B) {
@@ -630,6 +661,7 @@ bpt_status obpt_scene_upload_lights(obpt_context* c, const bpt_dir_light_data* d
 bpt_status obpt_scene_upload_sky(obpt_context* c, const float* faces, uint32_t size, const float xf[9], const float col[3]) {
     CHECK_CTX(c);
     Scene& sc = c->scene;
+    sc.ibl_valid = false;
     if (faces && size) { sc.sky_faces.assign(faces, faces + (size_t)6 * size * size * 4); sc.sky_size = size; }
     else { sc.sky_faces.clear(); sc.sky_size = 0; }
     if (xf) std::memcpy(sc.sky_transform, xf, sizeof(float) * 9);
@@ -894,6 +926,137 @@ bpt_status obpt_trace_ao(obpt_context* c, const bpt_camera* cam, uint32_t frame_
     return BPT_OK;
 }
 
+// ---- SkyboxPrecomputePass::render (src/renderer/pass/skybox_precompute.cpp:66-162): the three precompute shaders ----
+namespace {
+float radical_inverse_vdc(uint32_t bits) {                               // core/utils/low_discrepancy.hlsl:3-10
+    bits = (bits << 16u) | (bits >> 16u);
+    bits = ((bits & 0x55555555u) << 1u) | ((bits & 0xAAAAAAAAu) >> 1u);
+    bits = ((bits & 0x33333333u) << 2u) | ((bits & 0xCCCCCCCCu) >> 2u);
+    bits = ((bits & 0x0F0F0F0Fu) << 4u) | ((bits & 0xF0F0F0F0u) >> 4u);
+    bits = ((bits & 0x00FF00FFu) << 8u) | ((bits & 0xFF00FF00u) >> 8u);
+    return (float)bits * 2.3283064365386963e-10f;
+}
+f3 cubemap_direction_from_layered_uv(float u, float v, uint32_t layer) { // core/utils/cubemap.hlsl:3-21
+    u = u * 2.0f - 1.0f; v = v * 2.0f - 1.0f;
+    f3 d;
+    if (layer == 0) d = mk3(1.0f, -v, -u);
+    else if (layer == 1) d = mk3(-1.0f, -v, u);
+    else if (layer == 2) d = mk3(u, 1.0f, v);
+    else if (layer == 3) d = mk3(u, -1.0f, -v);
+    else if (layer == 4) d = mk3(u, -v, 1.0f);
+    else d = mk3(-u, -v, -1.0f);
+    return normalize(d);
+}
+float luminance(f3 c) { return (c.x * 0.212671f + c.y * 0.715160f) + c.z * 0.072169f; }   // core/utils/color.hlsl:3-5
+float store_unorm8(float v) { float c = v > 0.0f ? (v < 1.0f ? v : 1.0f) : 0.0f; return rintf(c * 255.0f) / 255.0f; }
+const float INV_TWO_PI = 0.15915494309189533577f;      // sin / cos of an angle a are sincos_2pi(a / 2pi): the numeric contract's fixed-order form
+const uint32_t IBL_SAMPLES = 1024;                     // ibl_brdf_lut.hlsl:6, skybox_precompute_specular.hlsl:9
+const float CLAMP_LUM = 12.0f;                         // skybox_precompute_diffuse.hlsl:10, skybox_precompute_specular.hlsl:10
+} // namespace
+
+bpt_status obpt_precompute_sky_ibl(obpt_context* c, const bpt_sky_ibl_desc* d) {
+    CHECK_CTX(c); if (!d) return BPT_ERR_INVALID;
+    if (!d->diffuse_size || !d->specular_size || !d->brdf_lut_size || d->specular_levels < 2 || d->specular_levels > 12 ||
+        (d->specular_size >> (d->specular_levels - 1)) == 0 || d->diffuse_size > 4096 || d->specular_size > 4096 || d->brdf_lut_size > 4096)
+        return fail(c, BPT_ERR_INVALID, "sky ibl: sizes out of range (2 <= levels <= 12, last mip >= 1 texel)");
+    Scene& sc = c->scene;
+    sc.ibl_valid = false;
+    const float* sky = sc.sky_faces.data(); const uint32_t sky_size = sc.sky_size;
+    const uint32_t R = d->brdf_lut_size, DS = d->diffuse_size;
+    sc.ibl_brdf.assign((size_t)R * R * 2, 0.0f);
+    sc.ibl_diffuse.assign((size_t)6 * DS * DS * 4, 0.0f);
+    size_t spec_floats = 0;
+    for (uint32_t l = 0; l < d->specular_levels; l++) { size_t n = d->specular_size >> l; spec_floats += 6 * n * n * 4; }
+    sc.ibl_specular.assign(spec_floats, 0.0f);
+    uint32_t nt = obpt_get_threads(c);
+    auto parallel = [&](size_t n, auto&& fn) {
+        std::vector<std::thread> th;
+        auto work = [&](uint32_t tid) { for (size_t i = tid; i < n; i += nt) fn(i); };
+        for (uint32_t t = 1; t < nt; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& t : th) t.join();
+    };
+    // "IBL BRDF LUT": ibl_brdf_lut.hlsl:8-32, rg8_unorm (skybox.cpp:25-29)
+    parallel((size_t)R * R, [&](size_t i) {
+        uint32_t x = (uint32_t)(i % R), y = (uint32_t)(i / R);
+        const float inv = 1.0f / (float)R;                                                       // skybox_precompute.cpp:87
+        float ndotv = ((float)x + 0.5f) * inv, roughness = ((float)y + 0.5f) * inv;
+        f3 wi = mk3(sqrtf(1.0f - ndotv * ndotv), 0.0f, ndotv);
+        float vx = 0.0f, vy = 0.0f;
+        for (uint32_t k = 0; k < IBL_SAMPLES; k++) {
+            f3 wh = ggx_vndf_sample(wi, roughness, roughness, (float)k / (float)IBL_SAMPLES, radical_inverse_vdc(k));
+            f3 wo = reflect(-wi, wh);
+            if (wo.z <= 0.0f) continue;
+            float weight = ggx_g1(wo, roughness, roughness);                                     // ggx_vndf_sample_weight_sep, utils.hlsl:123-125
+            float hdotv = dot(wi, wh);
+            float f = pow5(1.0f - hdotv);
+            vx = vx + (1.0f - f) * weight; vy = vy + f * weight;
+        }
+        sc.ibl_brdf[2 * i] = store_unorm8(vx / (float)IBL_SAMPLES); sc.ibl_brdf[2 * i + 1] = store_unorm8(vy / (float)IBL_SAMPLES);
+    });
+    // "Skybox Precompute Diffuse": skybox_precompute_diffuse.hlsl:12-41, rgba16_sfloat cube
+    parallel((size_t)6 * DS * DS, [&](size_t i) {
+        uint32_t layer = (uint32_t)(i / ((size_t)DS * DS)), r = (uint32_t)(i % ((size_t)DS * DS)), x = r % DS, y = r / DS;
+        const float inv = 1.0f / (float)DS;
+        f3 dir = cubemap_direction_from_layered_uv(((float)x + 0.5f) * inv, ((float)y + 0.5f) * inv, layer);
+        Frame frame = create_frame(dir);
+        f3 irradiance = splat3(0.0f);
+        const float delta = PI / 64.0f;                                                          // num_samples_sqrt = 64
+        for (float phi = delta * 0.5f; phi < TWO_PI; phi += delta) {
+            float sin_phi, cos_phi;
+            sincos_2pi(phi * INV_TWO_PI, sin_phi, cos_phi);
+            for (float theta = delta * 0.5f; theta < 0.5f * PI; theta += delta) {
+                float sin_theta, cos_theta;
+                sincos_2pi(theta * INV_TWO_PI, sin_theta, cos_theta);
+                f3 v = frame_to_world(frame, mk3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta));
+                f3 color = sample_cube(sky, sky_size, v);
+                float scale = CLAMP_LUM / fmax_(luminance(color), CLAMP_LUM);
+                irradiance = irradiance + ((color * scale) * cos_theta) * sin_theta;
+            }
+        }
+        f3 o = store_half3((irradiance * PI) / 4096.0f);
+        sc.ibl_diffuse[4 * i] = o.x; sc.ibl_diffuse[4 * i + 1] = o.y; sc.ibl_diffuse[4 * i + 2] = o.z; sc.ibl_diffuse[4 * i + 3] = 1.0f;
+    });
+    // "Skybox Precompute Specular i": skybox_precompute_specular.hlsl:12-41, one pass per mip, roughness = i / (levels - 1)
+    size_t offset = 0;
+    for (uint32_t l = 0; l < d->specular_levels; l++) {
+        const uint32_t S = d->specular_size >> l;
+        const float roughness = (float)l / (float)(d->specular_levels - 1);                      // skybox_precompute.cpp:148
+        float* out = sc.ibl_specular.data() + offset;
+        parallel((size_t)6 * S * S, [&](size_t i) {
+            uint32_t layer = (uint32_t)(i / ((size_t)S * S)), r = (uint32_t)(i % ((size_t)S * S)), x = r % S, y = r / S;
+            const float inv = 1.0f / (float)S;
+            f3 dir = cubemap_direction_from_layered_uv(((float)x + 0.5f) * inv, ((float)y + 0.5f) * inv, layer);
+            Frame frame = create_frame(dir);
+            const f3 wi = mk3(0.0f, 0.0f, 1.0f);
+            f3 filtered = splat3(0.0f);
+            float weight_sum = 0.0f;
+            for (uint32_t k = 0; k < IBL_SAMPLES; k++) {
+                f3 wh = ggx_vndf_sample(wi, roughness, roughness, (float)k / (float)IBL_SAMPLES, radical_inverse_vdc(k));
+                f3 wo = reflect(-wi, wh);
+                if (wo.z <= 0.0f) continue;
+                f3 color = sample_cube(sky, sky_size, frame_to_world(frame, wo));
+                float scale = CLAMP_LUM / fmax_(luminance(color), CLAMP_LUM);
+                filtered = filtered + (color * scale) * wo.z;
+                weight_sum = weight_sum + wo.z;
+            }
+            f3 o = store_half3(filtered / weight_sum);
+            out[4 * i] = o.x; out[4 * i + 1] = o.y; out[4 * i + 2] = o.z; out[4 * i + 3] = 1.0f;
+        });
+        offset += (size_t)6 * S * S * 4;
+    }
+    sc.ibl_desc = *d; sc.ibl_valid = true;
+    return BPT_OK;
+}
+bpt_status obpt_debug_read_sky_ibl(obpt_context* c, float* diffuse, float* specular, float* brdf) {
+    CHECK_CTX(c);
+    if (!c->scene.ibl_valid) return fail(c, BPT_ERR_STATE, "sky ibl not computed");
+    if (diffuse) std::memcpy(diffuse, c->scene.ibl_diffuse.data(), c->scene.ibl_diffuse.size() * 4);
+    if (specular) std::memcpy(specular, c->scene.ibl_specular.data(), c->scene.ibl_specular.size() * 4);
+    if (brdf) std::memcpy(brdf, c->scene.ibl_brdf.data(), c->scene.ibl_brdf.size() * 4);
+    return BPT_OK;
+}
+
 // Ray-traced reflections: ReflectionPass::render_raytraced (reflection.cpp:317-450).
 //   specular_sample_cs              direction_sample/specular_sample.hlsl:14-83
 //   trace + lighting                rt_gbuffer.hlsl:7-36 (ray_length = range) and deferred_lighting_secondary.hlsl:11-111
@@ -905,6 +1068,7 @@ bpt_status obpt_trace_reflection(obpt_context* c, const bpt_camera* cam, uint32_
     if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "trace_reflection before build_accel");
     const uint32_t W = c->width, H = c->height;
     if (rs->half_resolution && ((W | H) & 1u)) return fail(c, BPT_ERR_UNSUPPORTED, "trace_reflection: half resolution needs even width and height (texel-centre reads)");
+    if (rs->ibl > 1 || (rs->ibl && !c->scene.ibl_valid)) return fail(c, rs->ibl > 1 ? BPT_ERR_INVALID : BPT_ERR_STATE, "trace_reflection: settings.ibl needs obpt_precompute_sky_ibl");
     const uint32_t rw = rs->half_resolution ? (W + 1) / 2 : W, rh = rs->half_resolution ? (H + 1) / 2 : H;      // reflection.cpp:324-325
     const float max_roughness = rs->max_roughness;
     const float fade_roughness = std::min(rs->fade_roughness, max_roughness - 0.0001f);                         // reflection.cpp:361-362
@@ -967,7 +1131,7 @@ bpt_status obpt_trace_reflection(obpt_context* c, const bpt_camera* cam, uint32_
             // rt_gbuffer.hlsl:13-15 skips a zero direction (it cannot happen for a sampled pixel: out_dir is a unit vector)
             f3 W0 = weight * rs->strength;                                                       // deferred_lighting_secondary.hlsl:17
             float rgb[3] = {0, 0, 0}, first_t = -1.0f;
-            trace_path<float>(*c, st, false, frame_index, p, Pw, out_dir, rgb, &first_t, outs[tid], 0, &W0);
+            trace_path<float>(*c, st, false, frame_index, p, Pw, out_dir, rgb, &first_t, outs[tid], 0, &W0, rs->ibl != 0);
             refl[0] = rgb[0]; refl[1] = rgb[1]; refl[2] = rgb[2];
             if (first_t >= 0.0f) { f3 hp = Pw + out_dir * first_t; hitp[0] = hp.x; hitp[1] = hp.y; hitp[2] = hp.z; hitp[3] = first_t; }     // rt_gbuffer.hlsl:32
             else { hitp[0] = out_dir.x; hitp[1] = out_dir.y; hitp[2] = out_dir.z; hitp[3] = -1.0f; }                                          // :34

@@ -64,6 +64,10 @@ struct Scene {
     uint32_t sky_size = 0;
     float sky_transform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     float sky_color[3] = {1, 1, 1};
+    // SkyboxPrecomputePass outputs (obpt_precompute_sky_ibl): rgba cube faces (diffuse; specular = all mips, level 0 first), rg LUT
+    bool ibl_valid = false;
+    bpt_sky_ibl_desc ibl_desc{};
+    std::vector<float> ibl_diffuse, ibl_specular, ibl_brdf;
 
     // accel
     bool accel_built = false;

@@ -66,6 +66,7 @@ def lib():
         _lib.hc_trace.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.hc_trace_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.hc_read_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_void_p]
+        _lib.hc_precompute_sky_ibl.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(capi.SkyIblDesc), C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_post_process.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.PostSettings), C.c_void_p]
     return _lib
 
@@ -202,3 +203,22 @@ def post_process(sums, total_samples, settings):
     out = np.zeros_like(sums)
     assert lib().hc_post_process(sums.ctypes.data_as(C.c_void_p), w, h, total_samples, C.byref(settings), out.ctypes.data_as(C.c_void_p)) == 0
     return out
+
+
+def precompute_sky_ibl(scene, desc):
+    """bpt_ibl.cuh's per-texel functions on the host; also binds the result for HostScene.trace_reflection (desc None: unbind)."""
+    if desc is None:
+        lib().hc_precompute_sky_ibl(None, 0, None, None, None, None)
+        return None
+    faces = np.ascontiguousarray(scene.sky_faces, np.float32) if scene.sky_faces is not None else None
+    size = 0 if faces is None else faces.shape[1]
+    diffuse = np.zeros((6, desc.diffuse_size, desc.diffuse_size, 4), np.float32)
+    spec = np.zeros((desc.specular_texels(), 4), np.float32)
+    brdf = np.zeros((desc.brdf_lut_size, desc.brdf_lut_size, 2), np.float32)
+    lib().hc_precompute_sky_ibl(faces.ctypes.data_as(C.c_void_p) if faces is not None else None, size, C.byref(desc),
+                                diffuse.ctypes.data_as(C.c_void_p), spec.ctypes.data_as(C.c_void_p), brdf.ctypes.data_as(C.c_void_p))
+    levels, off = [], 0
+    for l in range(desc.specular_levels):
+        s_ = desc.specular_size >> l
+        levels.append(spec[off:off + 6 * s_ * s_].reshape(6, s_, s_, 4)); off += 6 * s_ * s_
+    return diffuse, levels, brdf

@@ -43,6 +43,8 @@ struct hc_scene {
 namespace {
 // DDGI volume bound by hc_set_ddgi (the host-check counterpart of bpt_set_ddgi_volume); applied by build()
 struct { bool enabled = false; bpt_probe_volume vol{}; uint32_t irr_size = 0, vis_size = 0; std::vector<float> irr, vis; } g_ddgi;
+// Sky IBL textures bound by hc_precompute_sky_ibl (the host-check counterpart of bpt_precompute_sky_ibl); applied by build()
+struct { bool enabled = false; bpt_sky_ibl_desc desc{}; std::vector<float4> diffuse, specular; std::vector<float2> brdf; } g_ibl;
 struct Built {
     std::vector<DInstance> inst;
     std::vector<std::vector<float4>> tris;
@@ -147,6 +149,10 @@ void build(const hc_scene& h, Built& b) {
     s.ltc_m0 = h.ltc_m0; s.ltc_m1 = h.ltc_m1; s.ltc_m2 = h.ltc_m2; s.ltc_norm = h.ltc_norm;
     s.sky_faces = reinterpret_cast<const float4*>(h.sky_faces); s.sky_size = h.sky_size;
     memcpy(s.sky_transform, h.sky_transform, 36); memcpy(s.sky_color, h.sky_color, 12);
+    s.ibl_enabled = g_ibl.enabled ? 1u : 0u; s.ibl_diffuse_size = g_ibl.desc.diffuse_size; s.ibl_specular_size = g_ibl.desc.specular_size;
+    s.ibl_specular_levels = g_ibl.desc.specular_levels; s.ibl_brdf_size = g_ibl.desc.brdf_lut_size;
+    s.ibl_diffuse = g_ibl.diffuse.data(); s.ibl_specular = g_ibl.specular.data(); s.ibl_brdf = g_ibl.brdf.data();
+    for (int k = 0; k < 3; k++) { s.ibl_diffuse_color[k] = h.sky_color[k] * g_ibl.desc.diffuse_strength; s.ibl_specular_color[k] = h.sky_color[k] * g_ibl.desc.specular_strength; }
     s.ddgi_enabled = g_ddgi.enabled ? 1u : 0u; s.ddgi_irr_size = g_ddgi.irr_size; s.ddgi_vis_size = g_ddgi.vis_size; s.ddgi_volume = g_ddgi.vol;
     s.ddgi_irradiance = reinterpret_cast<const float4*>(g_ddgi.irr.data()); s.ddgi_visibility = reinterpret_cast<const float2*>(g_ddgi.vis.data());
 }
@@ -172,7 +178,7 @@ int hc_render(const hc_scene* h, const bpt_camera* cam, uint32_t width, uint32_t
               const bpt_settings* st, float* accum_rgba) {
     Built b; build(*h, b);
     ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = std::min(std::max(st->max_bounces, 2u), 16u); sp.nee_mode = st->nee_mode; sp.ray_length = st->ray_length; sp.diffuse_only = 0; sp.russian_roulette = st->russian_roulette; sp.rect_shadow = st->rect_shadow;
-    sp.state_precision = st->state_precision;
+    sp.state_precision = st->state_precision; sp.ibl = 0;
     const bool fp16 = st->state_precision == BPT_STATE_REFERENCE_FP16;      // driven like k_raygen / k_commit_bounce / k_accumulate_fp16 drive it
     for (uint32_t s = 0; s < nsamples; s++)
         for (uint32_t p = 0; p < width * height; p++) {
@@ -242,7 +248,7 @@ int hc_trace_reflection(const hc_scene* h, const bpt_camera* cam, uint32_t width
     const uint32_t rw = rs->half_resolution ? (width + 1) / 2 : width, rh = rs->half_resolution ? (height + 1) / 2 : height;
     const float max_roughness = rs->max_roughness, fade_roughness = std::min(rs->fade_roughness, max_roughness - 0.0001f);
     ShadeParams sp; sp.width = width; sp.height = height; sp.max_bounces = 2; sp.nee_mode = BPT_NEE_SHADOW_RAY;
-    sp.ray_length = rs->range; sp.diffuse_only = 0; sp.russian_roulette = 0; sp.rect_shadow = 0; sp.state_precision = BPT_STATE_FP32;
+    sp.ray_length = rs->range; sp.diffuse_only = 0; sp.russian_roulette = 0; sp.rect_shadow = 0; sp.state_precision = BPT_STATE_FP32; sp.ibl = rs->ibl;
     for (uint32_t p = 0; p < rw * rh; p++) {
         float color[4] = {0, 0, 0, -1.0f};
         float hp[4] = {0, 0, 0, -1.0f};
@@ -268,7 +274,7 @@ __attribute__((visibility("default")))
 int hc_trace_probes(const hc_scene* h, const bpt_probe_volume* vol, const float* table, uint32_t frame_index, uint32_t num_bounces, float* out) {
     Built b; build(*h, b);
     ShadeParams sp; sp.width = 0; sp.height = 0; sp.max_bounces = std::min(std::max(num_bounces, 1u), 15u) + 1; sp.nee_mode = BPT_NEE_SHADOW_RAY;
-    sp.ray_length = vol->ray_length; sp.diffuse_only = 1; sp.russian_roulette = 0; sp.rect_shadow = 0; sp.state_precision = BPT_STATE_FP32;
+    sp.ray_length = vol->ray_length; sp.diffuse_only = 1; sp.russian_roulette = 0; sp.rect_shadow = 0; sp.state_precision = BPT_STATE_FP32; sp.ibl = 0;
     uint64_t total = (uint64_t)vol->probe_counts[0] * vol->probe_counts[1] * vol->probe_counts[2] * vol->rays_per_probe;
     for (uint64_t p = 0; p < total; p++) {
         float3 O, D, W = v3s(1.0f);
@@ -479,5 +485,37 @@ int hc_post_process(const float* sums_rgba32f, uint32_t width, uint32_t height, 
         float* o = out + ((size_t)y * W + x) * 4;
         o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = 1.0f;
     }
+    return 0;
+}
+
+// Sky IBL precompute: the per-texel functions of bpt_ibl.cuh driven like ibl.cu's kernels (one call per texel). desc == NULL unbinds.
+extern "C" __attribute__((visibility("default")))
+int hc_precompute_sky_ibl(const float* sky_faces, uint32_t sky_size, const bpt_sky_ibl_desc* d, float* diffuse, float* specular, float* brdf) {
+    g_ibl.enabled = false;
+    if (!d) return 0;
+    const float4* sky = reinterpret_cast<const float4*>(sky_faces);
+    g_ibl.desc = *d;
+    g_ibl.brdf.resize((size_t)d->brdf_lut_size * d->brdf_lut_size);
+    for (uint32_t i = 0; i < d->brdf_lut_size * d->brdf_lut_size; i++) g_ibl.brdf[i] = ibl_brdf_lut_texel(i % d->brdf_lut_size, i / d->brdf_lut_size, d->brdf_lut_size);
+    const uint32_t DS = d->diffuse_size;
+    g_ibl.diffuse.resize((size_t)6 * DS * DS);
+    for (uint32_t i = 0; i < 6 * DS * DS; i++) {
+        uint32_t r = i % (DS * DS);
+        float3 c = ibl_diffuse_texel(sky, sky_size, r % DS, r / DS, i / (DS * DS), DS);
+        g_ibl.diffuse[i] = make_float4(c.x, c.y, c.z, 1.0f);
+    }
+    g_ibl.specular.clear();
+    for (uint32_t l = 0; l < d->specular_levels; l++) {
+        const uint32_t S = d->specular_size >> l;
+        for (uint32_t i = 0; i < 6 * S * S; i++) {
+            uint32_t r = i % (S * S);
+            float3 c = ibl_specular_texel(sky, sky_size, r % S, r / S, i / (S * S), S, (float)l / (float)(d->specular_levels - 1));
+            g_ibl.specular.push_back(make_float4(c.x, c.y, c.z, 1.0f));
+        }
+    }
+    if (diffuse) memcpy(diffuse, g_ibl.diffuse.data(), g_ibl.diffuse.size() * 16);
+    if (specular) memcpy(specular, g_ibl.specular.data(), g_ibl.specular.size() * 16);
+    if (brdf) memcpy(brdf, g_ibl.brdf.data(), g_ibl.brdf.size() * 8);
+    g_ibl.enabled = true;
     return 0;
 }
