@@ -189,6 +189,7 @@ COMMON_API = {
     "scene_upload_materials": [_VP, _VP, _U32, C.POINTER(TextureDesc), _U32],
     "scene_upload_lights": [_VP, _VP, _U32, _VP, _U32, _VP, _U32, C.POINTER(LtcLuts)],
     "scene_upload_sky": [_VP, _VP, _U32, _VP, _VP],
+    "scene_update_sky_params": [_VP, _VP, _VP],
     "build_accel": [_VP, _U32],
     "update_tlas": [_VP],
     "debug_read_bvh": [_VP, _U32, _PU32, _VP, _VP, _VP, _U32, C.POINTER(C.c_int32)],
@@ -336,6 +337,9 @@ class Context:
         col = np.ascontiguousarray(scene.sky_color, dtype=f32)
         size = 0 if scene.sky_faces is None else scene.sky_faces.shape[1]
         self._call("scene_upload_sky", _ptr(scene.sky_faces), size, _ptr(xf), _ptr(col))
+
+    def update_sky_params(self, transform, color):
+        self._call("scene_update_sky_params", _ptr(np.ascontiguousarray(transform, dtype=f32)), _ptr(np.ascontiguousarray(color, dtype=f32)))
 
     def build_accel(self, mode=ACCEL_TWO_LEVEL):
         self._call("build_accel", mode)

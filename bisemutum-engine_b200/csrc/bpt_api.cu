@@ -272,6 +272,13 @@ bpt_status bpt_scene_upload_sky(bpt_context* c, const float* faces, uint32_t siz
     return BPT_OK;
 }
 
+bpt_status bpt_scene_update_sky_params(bpt_context* c, const float xf[9], const float col[3]) {
+    NEED(c);
+    if (xf) memcpy(c->sky_transform, xf, sizeof(float) * 9);
+    if (col) memcpy(c->sky_color, col, sizeof(float) * 3);
+    return BPT_OK;
+}
+
 static bpt_status validate_scene(bpt_context* c) {
     if (c->h_blas_desc.empty() || c->h_instances.empty()) return fail(c, BPT_ERR_STATE, "build_accel: upload geometry and instances first");
     if (c->h_materials.empty()) return fail(c, BPT_ERR_STATE, "build_accel: upload materials first");

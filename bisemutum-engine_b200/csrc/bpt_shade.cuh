@@ -49,7 +49,9 @@ BPT_HD float3 accumulate_fp16(float3 image, float3 C, uint32_t n) {
 //   void add(float3 c)                                         — unshadowed radiance for this pixel
 //   void shadow(float3 P, float3 L, float tmax, float3 c, uint32_t light) — NEE candidate
 // Returns true when the path continues; (nO, nD, nW) is then the next extend ray.
-template <class Sink>
+// IBL (compile time): the reflection pass's kernel evaluates the IBL block; the path tracer's kernel is compiled without it, like
+// the reference compiles its shader with DEFERRED_LIGHTING_NO_IBL (path_tracing.cpp:152).
+template <class Sink, bool IBL = false>
 BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame_index, uint32_t bounce, uint32_t pixel,
                          float3 O, float3 D, float3 Wt, const TraceResult& hit, Sink& sink, float3& nO, float3& nD, float3& nW) {
     const bool fp16 = sp.state_precision == BPT_STATE_REFERENCE_FP16;
@@ -103,7 +105,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
         float dist = fabsf(dot3(P - v3(rl.position2[0], rl.position2[1], rl.position2[2]), ln));
         sink.shadow(P, mrp, (dist / step) * 0.999f, c, sc.num_dir + sc.num_point + l);
     }
-    if (sp.ibl && sc.ibl_enabled) sink.add(ibl_lighting(sc, N, V, surf, surface_model) * Wl);     // deferred_lighting_secondary.hlsl:98-108
+    if (IBL && sp.ibl && sc.ibl_enabled) sink.add(ibl_lighting(sc, N, V, surf, surface_model) * Wl);     // deferred_lighting_secondary.hlsl:98-108
     // Probe paths only: the previous DDGI update lights the path's last vertex (ddgi/deferred_lighting.hlsl:102-115:
     // color += ddgi.xyz / ddgi.a * base_color / pi). The reference traces one bounce, so every probe-ray hit gets it; with
     // more bounces (BASELINE configs[4]) it closes the path instead of being added at every vertex.

@@ -358,6 +358,7 @@ struct KernelSink {
     }
 };
 
+template <bool IBL>
 __global__ void __launch_bounds__(kBlock, 8) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < a.qcount[QE + bounce];
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(kBlock, 8) k_shade(const __grid_constant__ Ren
         r.t = h.x; r.u = h.y; r.v = h.z; r.prim = __float_as_uint(h.w); r.slot = a.hit_slot[i]; r.hit = h.x >= 0.0f;
         if (a.probe_mode && bounce == 1) a.color[path].w = r.t;          // hit distance of the probe ray (or -1)
         KernelSink sink{a, bounce, path};
-        cont = shade_vertex(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
+        cont = shade_vertex<KernelSink, IBL>(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
     }
     // next-ray queue: ballot per warp, ONE atomicAdd per block (all threads of the block reach this point)
     __shared__ uint32_t s_warp_cnt[kBlock / 32], s_warp_base[kBlock / 32];
@@ -804,7 +805,8 @@ static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_setting
         a.ray_o_in = wf.ray_o[cur].as<float4>(); a.ray_d_in = wf.ray_d[cur].as<float4>(); a.ray_w_in = wf.ray_w[cur].as<float4>();
         a.ray_o_out = wf.ray_o[cur ^ 1].as<float4>(); a.ray_d_out = wf.ray_d[cur ^ 1].as<float4>(); a.ray_w_out = wf.ray_w[cur ^ 1].as<float4>();
         if ((s = launch_extend(ctx, a, i))) return s;
-        LAUNCH_T(ctx, 2, k_shade, grid_paths, kBlock, a, i);
+        if (a.sp.ibl) LAUNCH_T(ctx, 2, k_shade<true>, grid_paths, kBlock, a, i);      // ray-traced reflections with settings.ibl
+        else LAUNCH_T(ctx, 2, k_shade<false>, grid_paths, kBlock, a, i);
         if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point + (st.rect_shadow ? ctx->num_rect : 0)) > 0) {
             if ((s = launch_connect(ctx, a, i))) return s;
         }

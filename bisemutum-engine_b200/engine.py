@@ -50,6 +50,9 @@ def host_library():
         h.bpt_host_pass_frame.restype = C.c_int
         h.bpt_host_pass_post_process.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]
         h.bpt_host_pass_post_process.restype = C.c_int
+        h.bpt_host_renderer_run.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(HostCameraDesc), C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                            C.c_void_p, C.c_void_p, C.c_float, C.c_uint32, C.c_int, C.c_float, C.c_float, C.c_void_p, C.POINTER(C.c_uint32)]
+        h.bpt_host_renderer_run.restype = C.c_int
         _host = h
     return _host
 
@@ -178,6 +181,29 @@ class Project:
         if self._h:
             host_library().bpt_host_project_free(self._h)
             self._h = None
+
+
+def run_renderer(ctx: "capi.Context", scene, width: int, height: int, frames: int, renderer: str = "CudaPathTracingRenderer", ray_length: float = 100.0,
+                 max_bounces: int = 3, bloom: bool = False, bloom_threshold: float = 1.5, bloom_threshold_softness: float = 0.5):
+    """The plugin path: GraphicsManager::register_renderer<CudaPathTracingRenderer>() + set_renderer(name), then `frames` engine frames of
+    prepare_renderer_per_frame_data / render_camera / RenderGraph::execute on a context whose geometry, materials and accel are uploaded.
+    Returns (back buffer (H, W, 4) float32, render-graph passes per frame); raises KeyError for an unregistered renderer name."""
+    h = host_library()
+    d = camera_desc(scene.camera, width, height)
+    out = np.zeros((height, width, 4), np.float32)
+    passes = C.c_uint32(0)
+    dirs = np.ascontiguousarray(scene.dir_lights)
+    faces = None if scene.sky_faces is None else np.ascontiguousarray(scene.sky_faces, np.float32)
+    xf = np.ascontiguousarray(scene.sky_transform, np.float32); col = np.ascontiguousarray(scene.sky_color, np.float32)
+    st = h.bpt_host_renderer_run(ctx._h, renderer.encode(), C.byref(d), frames, dirs.ctypes.data_as(C.c_void_p), len(dirs),
+                                 faces.ctypes.data_as(C.c_void_p) if faces is not None else None, 0 if faces is None else faces.shape[1],
+                                 xf.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p), ray_length, max_bounces, 1 if bloom else 0,
+                                 bloom_threshold, bloom_threshold_softness, out.ctypes.data_as(C.c_void_p), C.byref(passes))
+    if st == -1:
+        raise KeyError(f"renderer {renderer!r} is not registered")
+    if st != 0:
+        raise capi.BptError(st, "CudaPathTracingRenderer::render_camera", ctx.L.fn("last_error")(ctx._h).decode())
+    return out, passes.value
 
 
 class Renderer:

@@ -204,4 +204,38 @@ HOST_API int bpt_host_pass_post_process(bpt_host_pass* p, int bloom, float thres
     return (int)post.last_status();
 }
 
+// Renderer level: register_renderer<CudaPathTracingRenderer>() + set_renderer(name) + `frames` x (prepare_renderer_per_frame_data,
+// render_camera, RenderGraph::execute), as GraphicsManager::render_frame drives a renderer (graphics_manager.cpp:407-427). Lights are the
+// packed arrays a LightsContext would hold. Writes the back buffer of the last frame; *passes_per_frame = render-graph passes recorded.
+// Returns bpt_status; -1 when `renderer_name` is not registered.
+HOST_API int bpt_host_renderer_run(bpt_context* ctx, const char* renderer_name, const bpt_host_camera_desc* cam, uint32_t frames,
+                                   const bpt_dir_light_data* dir, uint32_t num_dir, const float* sky_faces, uint32_t sky_size, const float* sky_transform,
+                                   const float* sky_color, float ray_length, uint32_t max_bounces, int bloom, float bloom_threshold, float bloom_softness,
+                                   float* back_buffer, uint32_t* passes_per_frame) {
+    gfx::GraphicsManager mgr(ctx);
+    mgr.register_renderer<CudaPathTracingRenderer>();
+    if (!mgr.set_renderer(renderer_name)) return -1;
+    auto* r = static_cast<CudaPathTracingRenderer*>(mgr.renderer());
+    r->lights_ctx.dir_lights.assign(dir, dir + num_dir);
+    r->skybox_ctx.faces_rgba32f = sky_faces; r->skybox_ctx.face_size = sky_size;
+    if (sky_transform) std::memcpy(r->skybox_ctx.skybox_transform, sky_transform, 36);
+    if (sky_color) r->skybox_ctx.color = float3{sky_color[0], sky_color[1], sky_color[2]};
+    r->settings.path_tracing.ray_length = ray_length; r->settings.path_tracing.max_bounces = max_bounces;
+    r->post_process.bloom = bloom != 0; r->post_process.bloom_threshold = bloom_threshold; r->post_process.bloom_threshold_softness = bloom_softness;
+    r->back_buffer = back_buffer;
+    gfx::Camera camera = make_camera(cam);
+    for (uint32_t f = 0; f < frames; f++) {
+        camera.update_shader_params(f);
+        r->path_tracing_pass.set_frame_count(f);
+        r->prepare_renderer_per_frame_data();
+        r->prepare_renderer_per_camera_data(camera);
+        gfx::RenderGraph rg;
+        r->render_camera(camera, rg);
+        rg.execute();
+        if (passes_per_frame) *passes_per_frame = (uint32_t)rg.executed_pass_names().size();
+        if (r->last_status() != BPT_OK) break;
+    }
+    return (int)r->last_status();
+}
+
 } // extern "C"

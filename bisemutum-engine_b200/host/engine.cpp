@@ -123,7 +123,14 @@ auto PathTracingPass::update_params(LightsContext& lights_ctx, SkyboxContext& sk
                                       lights_ctx.rect_lights.data(), (uint32_t)lights_ctx.rect_lights.size(), &lights_ctx.ltc_luts);
     if (status_ != BPT_OK) return;
     float col[3] = {skybox_ctx.color.x, skybox_ctx.color.y, skybox_ctx.color.z};
-    status_ = bpt_scene_upload_sky(ctx_, skybox_ctx.faces_rgba32f, skybox_ctx.face_size, skybox_ctx.skybox_transform, col);
+    // The skybox texture is handed over only when it changes (the reference's `last_precomputed_skybox_ != current_skybox.tex`,
+    // skybox_precompute.cpp:97); transform and colour are per-frame uniforms (skybox.cpp:40-50).
+    if (!sky_uploaded_ || skybox_ctx.faces_rgba32f != last_sky_faces_ || skybox_ctx.face_size != last_sky_size_) {
+        status_ = bpt_scene_upload_sky(ctx_, skybox_ctx.faces_rgba32f, skybox_ctx.face_size, skybox_ctx.skybox_transform, col);
+        sky_uploaded_ = status_ == BPT_OK; last_sky_faces_ = skybox_ctx.faces_rgba32f; last_sky_size_ = skybox_ctx.face_size;
+    } else {
+        status_ = bpt_scene_update_sky_params(ctx_, skybox_ctx.skybox_transform, col);
+    }
 }
 
 auto PathTracingPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, InputData const&,
@@ -221,6 +228,28 @@ auto PostProcessPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, In
             st.bloom_threshold_softness = volume.bloom_threshold_softness;
             status_ = out_ ? bpt_post_process(ctx_, &st, (uint32_t)frames_, out_) : BPT_ERR_INVALID;
         });
+}
+
+// ---- renderer level ------------------------------------------------------------------------------------------------
+auto CudaPathTracingRenderer::prepare_renderer_per_frame_data() -> void {                 // basic.cpp:31-48
+    path_tracing_pass.update_params(lights_ctx, skybox_ctx, settings.path_tracing);
+}
+auto CudaPathTracingRenderer::prepare_renderer_per_camera_data(gfx::Camera const&) -> void {}   // basic.cpp:73-76: nothing for this pipeline
+auto CudaPathTracingRenderer::render_camera(gfx::Camera const& camera, gfx::RenderGraph& rg) -> void {
+    auto pt_output = path_tracing_pass.render(camera, rg, {scene_accel}, settings.path_tracing);          // basic.cpp:157-166
+    post_process_pass.default_volume_ = post_process;
+    post_process_pass.set_output(back_buffer, std::max<uint64_t>(path_tracing_pass.accumulated_frames(camera), 1));
+    post_process_pass.render(camera, rg, {pt_output.color, pt_output.depth});                             // basic.cpp:228-231
+}
+auto CudaPathTracingRenderer::last_status() const -> bpt_status {
+    return path_tracing_pass.last_status() != BPT_OK ? path_tracing_pass.last_status() : post_process_pass.last_status();
+}
+
+auto gfx::GraphicsManager::set_renderer(std::string_view name) -> bool {                  // graphics_manager.hpp:82-87, engine.cpp:147-148
+    auto it = renderer_creators_.find(std::string(name));
+    if (it == renderer_creators_.end()) return false;
+    renderer_ = it->second(ctx_);
+    return true;
 }
 
 } // namespace bi

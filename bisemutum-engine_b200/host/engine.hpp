@@ -14,6 +14,7 @@
 //   IRenderer              include/bisemutum/graphics/renderer.hpp:10-23 (as an abstract class; the
 //                          reference type-erases with AnyAny)
 #pragma once
+#include <algorithm>
 #include <any>
 #include <functional>
 #include <memory>
@@ -182,6 +183,7 @@ private:
     std::unordered_map<gfx::Camera const*, CameraHistoryInfo> camera_history_infos_;
     bpt_context* ctx_;
     bpt_status status_ = BPT_OK;
+    bool sky_uploaded_ = false; float const* last_sky_faces_ = nullptr; uint32_t last_sky_size_ = 0;   // see update_params
     uint64_t frame_counter_ = 0;      // stands in for g_engine->window()->frame_count()
     uint32_t prefetch_frames_ = 8;    // samples traced per wave when the history is valid (clamped by the library)
     bpt_settings ahead_settings_{};
@@ -215,5 +217,46 @@ private:
     uint64_t frames_ = 1;             // samples in the accumulation buffer (PathTracingPass::accumulated_frames)
     bpt_status status_ = BPT_OK;
 };
+
+// ---- renderer level: the plugin the engine selects with `renderer = "..."` in project.toml -----------------------------
+// An IRenderer (include/bisemutum/graphics/renderer.hpp:10-23) that runs BasicRenderer's path-tracing pipeline
+// (src/renderer/basic.cpp:31-48 per frame; :157-166 and :228-231 per camera) through the two CUDA passes above. Registered and
+// selected like the reference's renderers: GraphicsManager::register_renderer<T>() needs T::renderer_type_name
+// (graphics_manager.hpp:82-87, src/engine/register_renderer.cpp:9-11), set_renderer(name) instantiates it (engine.cpp:147-148).
+struct CudaPathTracingRenderer final : gfx::IRenderer {
+    static constexpr std::string_view renderer_type_name = "CudaPathTracingRenderer";
+    explicit CudaPathTracingRenderer(bpt_context* ctx) : path_tracing_pass(ctx), post_process_pass(ctx) {}
+
+    auto override_volume_component_name() const -> std::string_view override { return "BasicRendererOverrideVolume"; }   // basic.cpp:268-270
+    auto prepare_renderer_per_frame_data() -> void override;
+    auto prepare_renderer_per_camera_data(gfx::Camera const& camera) -> void override;
+    auto render_camera(gfx::Camera const& camera, gfx::RenderGraph& rg) -> void override;
+    auto last_status() const -> bpt_status;
+
+    struct Settings final { BasicRenderer::PathTracingSettings path_tracing; } settings;   // BasicRendererOverrideVolume::settings
+    PostProcessVolume post_process;
+    LightsContext lights_ctx;
+    SkyboxContext skybox_ctx;
+    gfx::AccelerationStructureHandle scene_accel;
+    float* back_buffer = nullptr;                     // W*H rgba32f, stands in for rg.import_back_buffer()
+    PathTracingPass path_tracing_pass;
+    PostProcessPass post_process_pass;
+};
+
+namespace gfx {
+struct GraphicsManager final {
+    explicit GraphicsManager(bpt_context* ctx) : ctx_(ctx) {}
+    template <typename Renderer>
+    auto register_renderer() -> void {
+        renderer_creators_[std::string(Renderer::renderer_type_name)] = [](bpt_context* c) -> std::unique_ptr<IRenderer> { return std::make_unique<Renderer>(c); };
+    }
+    auto set_renderer(std::string_view name) -> bool;
+    auto renderer() -> IRenderer* { return renderer_.get(); }
+private:
+    bpt_context* ctx_;
+    std::unordered_map<std::string, std::function<std::unique_ptr<IRenderer>(bpt_context*)>> renderer_creators_;
+    std::unique_ptr<IRenderer> renderer_;
+};
+} // namespace gfx
 
 } // namespace bi

@@ -240,6 +240,9 @@ BPT_API bpt_status bpt_scene_upload_lights(
 BPT_API bpt_status bpt_scene_upload_sky(
     bpt_context* ctx, const float* faces_rgba32f, uint32_t face_size,
     const float skybox_transform[9], const float skybox_color[3]);
+/* Same, transform and colour only: the faces (and the textures bpt_precompute_sky_ibl derived from them) stay. What the
+ * reference's per-frame SkyboxContext::update_shader_params changes when the skybox texture itself did not (skybox.cpp:40-50). */
+BPT_API bpt_status bpt_scene_update_sky_params(bpt_context* ctx, const float skybox_transform[9], const float skybox_color[3]);
 
 /* ---------------------------------------------------------------------------------------
  * Acceleration structure (replaces AccelerationStructure ctor, accel.cpp:11-159; rebuilt when

@@ -51,6 +51,7 @@ BPT_API bpt_status obpt_scene_upload_sky(
     obpt_context* ctx, const float* faces_rgba32f, uint32_t face_size,
     const float skybox_transform[9], const float skybox_color[3]);
 
+BPT_API bpt_status obpt_scene_update_sky_params(obpt_context* ctx, const float skybox_transform[9], const float skybox_color[3]);
 BPT_API bpt_status obpt_build_accel(obpt_context* ctx, uint32_t mode);
 BPT_API bpt_status obpt_update_tlas(obpt_context* ctx);
 BPT_API bpt_status obpt_debug_read_bvh(

@@ -669,6 +669,13 @@ bpt_status obpt_scene_upload_sky(obpt_context* c, const float* faces, uint32_t s
     return BPT_OK;
 }
 
+bpt_status obpt_scene_update_sky_params(obpt_context* c, const float xf[9], const float col[3]) {
+    CHECK_CTX(c);
+    if (xf) std::memcpy(c->scene.sky_transform, xf, sizeof(float) * 9);
+    if (col) std::memcpy(c->scene.sky_color, col, sizeof(float) * 3);
+    return BPT_OK;
+}
+
 bpt_status obpt_build_accel(obpt_context* c, uint32_t mode) {
     CHECK_CTX(c);
     if (c->scene.materials.empty()) return fail(c, BPT_ERR_STATE, "upload materials before build_accel");

@@ -258,7 +258,7 @@ int hc_trace_reflection(const hc_scene* h, const bpt_camera* cam, uint32_t width
             TraceResult r = trace_ray<false>(b.sc, O, D, 0.001f, sp.ray_length, frame_index);
             HostSink sink{b.sc, BPT_NEE_SHADOW_RAY, frame_index, color, {}};
             float3 nO, nD, nW;
-            shade_vertex(b.sc, sp, frame_index, 1u, p, O, D, W, r, sink, nO, nD, nW);
+            shade_vertex<HostSink, true>(b.sc, sp, frame_index, 1u, p, O, D, W, r, sink, nO, nD, nW);
             for (auto& c : sink.pending) sink.add(c);
             if (r.hit) { float3 P = O + D * r.t; hp[0] = P.x; hp[1] = P.y; hp[2] = P.z; hp[3] = r.t; }
             else { hp[0] = D.x; hp[1] = D.y; hp[2] = D.z; hp[3] = -1.0f; }

@@ -180,6 +180,23 @@ def test_host_pass_accumulates_like_reference(lib, oracle):
     r.close()
 
 
+def test_renderer_plugin_runs_pt_and_post_process(lib, oracle):
+    """The plugin level: an IRenderer registered by name and selected like `renderer = "..."` in project.toml runs
+    BasicRenderer's path-tracing pipeline — update_params per frame, PathTracingPass::render + PostProcessPass::render per camera
+    (basic.cpp:31-48,157-166,228-231) — as two render-graph passes; the back buffer equals oracle render + oracle post-process."""
+    scene = scenes.small_test_scene()                       # one directional light, procedural sky
+    W, H = 64, 48
+    gpu = capi.Context(lib, W, H); gpu.upload_scene(scene, capi.ACCEL_MERGED)
+    img, passes = engine.run_renderer(gpu, scene, W, H, 3, max_bounces=4, bloom=True, bloom_threshold=0.4)
+    assert passes == 2
+    ref = oracle.OracleContext(W, H); ref.upload_scene(scene, capi.ACCEL_MERGED)
+    ref.render(engine.camera_matrices(scene.camera, W, H), 0, 3, capi.Settings(max_bounces=4))
+    np.testing.assert_array_equal(img, oracle.post_process_image(ref.resolve(3), capi.PostSettings(True, 0.4, 0.5)))
+    with pytest.raises(KeyError):
+        engine.run_renderer(gpu, scene, W, H, 1, renderer="BasicRenderer")        # only what was registered can be selected
+    gpu.close(); ref.close()
+
+
 # ---- BASELINE configs[2]: mixed lights (64 point/spot + 16 LTC rect) ---------------------------------
 def test_mixed_lights_config3(lib, oracle):
     import os
