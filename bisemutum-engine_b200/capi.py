@@ -209,6 +209,7 @@ COMMON_API = {
     "debug_read_sky_ibl": [_VP, _VP, _VP, _VP],
     "trace_reflection": [_VP, C.POINTER(Camera), _U32, C.POINTER(ReflectionSettings), _VP, _VP, _VP, _VP],
     "trace_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _VP],
+    "trace_probes_range": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _U32, _U32, _U32, _VP],
     "blend_probes": [_VP, C.POINTER(ProbeVolume), _VP, _U32, _VP, C.POINTER(ProbeBlend), _VP, _VP],
     "set_ddgi_volume": [_VP, C.POINTER(ProbeVolume), C.POINTER(ProbeBlend), _VP, _VP],
     "ddgi_lighting": [_VP, _U64, _VP, _VP, _VP, _VP],
@@ -454,6 +455,15 @@ class Context:
         table = np.ascontiguousarray(sample_table, dtype=f32)
         assert table.shape == (8192, 2)
         self._call("trace_probes", C.byref(volume), _ptr(table), frame_index, num_bounces, _ptr(out))
+        return out
+
+    def trace_probes_range(self, volume: ProbeVolume, sample_table: np.ndarray, frame_index: int, num_bounces: int, first_probe: int, num_probes: int) -> np.ndarray:
+        """The rays of probes [first_probe, first_probe + num_probes): (num_probes * rays_per_probe, 4) float32, bit-identical to the
+        same rows of trace_probes (the sharding unit of the DDGI update, sharding.probe_range)."""
+        out = np.zeros((num_probes * volume.rays_per_probe, 4), dtype=f32)
+        table = np.ascontiguousarray(sample_table, dtype=f32)
+        assert table.shape == (8192, 2)
+        self._call("trace_probes_range", C.byref(volume), _ptr(table), frame_index, num_bounces, first_probe, num_probes, _ptr(out))
         return out
 
     def set_ddgi_volume(self, volume: ProbeVolume | None, irradiance=None, visibility=None, irradiance_size=6, visibility_size=14):

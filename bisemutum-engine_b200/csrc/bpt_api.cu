@@ -663,6 +663,14 @@ bpt_status bpt_trace_probes(bpt_context* c, const bpt_probe_volume* vol, const f
     return wavefront_trace_probes(c, *vol, table, frame, bounces, out);
 }
 
+bpt_status bpt_trace_probes_range(bpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, uint32_t bounces, uint32_t first_probe,
+                                  uint32_t num_probes, float* out) {
+    NEED(c);
+    if (!vol || !table || (!out && num_probes) || num_probes == 0xffffffffu) return BPT_ERR_INVALID;
+    if (!c->accel_built) return fail(c, BPT_ERR_STATE, "trace_probes before build_accel");
+    return wavefront_trace_probes(c, *vol, table, frame, bounces, out, first_probe, num_probes);
+}
+
 bpt_status bpt_blend_probes(bpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, const float* rays,
                             const bpt_probe_blend* blend, float* irr, float* vis) {
     NEED(c);

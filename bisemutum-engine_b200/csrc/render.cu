@@ -969,13 +969,19 @@ bpt_status wavefront_trace_reflection(bpt_context* ctx, const bpt_camera& cam, u
 }
 
 // DDGI-style probe tracing through the same extend / shade / connect kernels (BASELINE configs[4]).
-bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, uint32_t num_bounces, float* h_out) {
+bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, uint32_t num_bounces, float* h_out,
+                                  uint32_t first_probe, uint32_t num_probes) {
     bpt_status s;
     if ((s = wavefront_alloc(ctx))) return s;
     WavefrontState& wf = ctx->wf;
     wf.ahead_slots = wf.ahead_cursor = 0;
-    const uint64_t total = (uint64_t)vol.probe_counts[0] * vol.probe_counts[1] * vol.probe_counts[2] * vol.rays_per_probe;
-    if (total == 0 || total > 0xffffffffull || vol.rays_per_probe == 0) { ctx->err = "trace_probes: bad volume"; return BPT_ERR_INVALID; }
+    const uint64_t all_probes = (uint64_t)vol.probe_counts[0] * vol.probe_counts[1] * vol.probe_counts[2];
+    if (all_probes == 0 || all_probes * vol.rays_per_probe > 0xffffffffull || vol.rays_per_probe == 0) { ctx->err = "trace_probes: bad volume"; return BPT_ERR_INVALID; }
+    if (num_probes == 0xffffffffu) { first_probe = 0; num_probes = (uint32_t)all_probes; }          // the whole volume
+    if ((uint64_t)first_probe + num_probes > all_probes) { ctx->err = "trace_probes: probe range outside the volume"; return BPT_ERR_INVALID; }
+    if (num_probes == 0) return BPT_OK;
+    const uint64_t first_path = (uint64_t)first_probe * vol.rays_per_probe;                           // global path id = probe * rays_per_probe + ray
+    const uint64_t total = (uint64_t)num_probes * vol.rays_per_probe;
     const uint32_t B = std::min(std::max(num_bounces, 1u), 15u) + 1;          // num_bounces extend passes
     bpt_settings st{};
     st.ray_length = vol.ray_length; st.max_bounces = B; st.nee_mode = BPT_NEE_SHADOW_RAY;
@@ -987,7 +993,7 @@ bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol,
     if ((s = dev_upload(ctx, table, h_table, 8192 * sizeof(float2)))) return s;
     for (uint64_t base = 0; base < total; base += wf.capacity) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(wf.capacity, total - base);
-        a.npx = count; a.pixel_base = (uint32_t)base;
+        a.npx = count; a.pixel_base = (uint32_t)(first_path + base);
         cudaError_t e = cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream);
         if (e != cudaSuccess) { dev_free(table); ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
         a.ray_o_out = wf.ray_o[0].as<float4>(); a.ray_d_out = wf.ray_d[0].as<float4>(); a.ray_w_out = wf.ray_w[0].as<float4>();

@@ -52,3 +52,28 @@ def comm_init(ctx, device: torch.device | None = None) -> None:
         uid = uid.to(device)
     dist.broadcast(uid, src=0)
     ctx.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+
+# ---- DDGI update (last sentence): shard by probe index, all-gather the per-ray results ---------------------------
+def probe_range(num_probes: int, rank: int, world: int) -> tuple[int, int]:
+    """(first_probe, count) of rank `rank`: contiguous blocks, the first `num_probes % world` ranks get one probe more."""
+    base, extra = divmod(num_probes, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def allgather_probe_rays(local_rays: torch.Tensor, num_probes: int, rays_per_probe: int) -> torch.Tensor:
+    """The one exchange step of a sharded DDGI update: every rank contributes the (count * rays_per_probe, 4) float32 results of its
+    probe_range and receives the full (num_probes * rays_per_probe, 4) array in probe order — the input of bpt_blend_probes, which
+    every rank then runs for all probes (blending is ~1 % of the update). Uneven ranges are padded to the largest block for the
+    collective (NCCL / gloo all_gather needs equal sizes) and trimmed afterwards. No-op for world 1."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local_rays
+    world = dist.get_world_size()
+    counts = [probe_range(num_probes, r, world)[1] for r in range(world)]
+    rows = max(counts) * rays_per_probe
+    padded = torch.zeros((rows, 4), dtype=local_rays.dtype, device=local_rays.device)
+    padded[: local_rays.shape[0]] = local_rays
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat([p[: c * rays_per_probe] for p, c in zip(parts, counts)], dim=0)

@@ -519,6 +519,13 @@ typedef struct bpt_probe_volume {
 BPT_API bpt_status bpt_trace_probes(
     bpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2 /* 8192 float2 */,
     uint32_t frame_index, uint32_t num_bounces, float* out_radiance_dist);
+/* The same for the probes [first_probe, first_probe + num_probes) only (linear probe index = (iz * ny + iy) * nx + ix):
+ * out_radiance_dist holds num_probes*rays_per_probe float4. Every random choice is keyed by the probe's GLOBAL index
+ * (ddgi/trace_gbuffer.hlsl:25-29), so the rays of a range are bit-identical to the same rays of a full bpt_trace_probes — the unit
+ * of the multi-GPU sharding of the DDGI update (shard by probe index, all-gather the per-ray results, sharding.py). */
+BPT_API bpt_status bpt_trace_probes_range(
+    bpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2 /* 8192 float2 */,
+    uint32_t frame_index, uint32_t num_bounces, uint32_t first_probe, uint32_t num_probes, float* out_radiance_dist);
 
 /* DDGI probe blending (ddgi/probe_blend_irradiance.hlsl, probe_blend_visibility.hlsl):
  * gathers the per-ray output of bpt_trace_probes into octahedral atlases with a 1-texel border,

@@ -97,6 +97,10 @@ BPT_API bpt_status obpt_trace_probes(
     obpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2,
     uint32_t frame_index, uint32_t num_bounces, float* out_radiance_dist);
 
+BPT_API bpt_status obpt_trace_probes_range(
+    obpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2,
+    uint32_t frame_index, uint32_t num_bounces, uint32_t first_probe, uint32_t num_probes, float* out_radiance_dist);
+
 BPT_API bpt_status obpt_blend_probes(
     obpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2, uint32_t frame_index,
     const float* ray_radiance_dist, const bpt_probe_blend* blend, float* irradiance_atlas_rgba32f, float* visibility_atlas_rg32f);

@@ -1161,11 +1161,29 @@ bpt_status obpt_trace_reflection(obpt_context* c, const bpt_camera* cam, uint32_
 // DDGI-style probe tracing: ddgi/trace_gbuffer.hlsl:10-51 (probe centre, R2-table direction, TraceRay) +
 // ddgi/deferred_lighting.hlsl:12-118 (diffuse-only surface, V = normalize(probe - P)); further bounces continue
 // the path through the same trace/shade code (BASELINE configs[4]); previous-frame DDGI feedback is not modelled.
+static bpt_status trace_probes_impl(obpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, uint32_t num_bounces, uint64_t first_path,
+                                    uint64_t total, float* out);
 bpt_status obpt_trace_probes(obpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, uint32_t num_bounces, float* out) {
     CHECK_CTX(c); if (!vol || !table || !out) return BPT_ERR_INVALID;
     if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "trace_probes before build_accel");
     const uint64_t total = (uint64_t)vol->probe_counts[0] * vol->probe_counts[1] * vol->probe_counts[2] * vol->rays_per_probe;
     if (total == 0 || total > 0xffffffffull) return fail(c, BPT_ERR_INVALID, "trace_probes: bad volume");
+    return trace_probes_impl(c, vol, table, frame, num_bounces, 0, total, out);
+}
+// Probes [first_probe, first_probe + num_probes): the sharding unit of the DDGI update. Keys are the GLOBAL probe / path
+// indices, so a range reproduces the same rays of the full call bit for bit.
+bpt_status obpt_trace_probes_range(obpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, uint32_t num_bounces, uint32_t first_probe,
+                                   uint32_t num_probes, float* out) {
+    CHECK_CTX(c); if (!vol || !table || (!out && num_probes) || num_probes == 0xffffffffu) return BPT_ERR_INVALID;
+    if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "trace_probes before build_accel");
+    const uint64_t all_probes = (uint64_t)vol->probe_counts[0] * vol->probe_counts[1] * vol->probe_counts[2];
+    if (all_probes == 0 || vol->rays_per_probe == 0 || all_probes * vol->rays_per_probe > 0xffffffffull) return fail(c, BPT_ERR_INVALID, "trace_probes: bad volume");
+    if ((uint64_t)first_probe + num_probes > all_probes) return fail(c, BPT_ERR_INVALID, "trace_probes: probe range outside the volume");
+    if (num_probes == 0) return BPT_OK;
+    return trace_probes_impl(c, vol, table, frame, num_bounces, (uint64_t)first_probe * vol->rays_per_probe, (uint64_t)num_probes * vol->rays_per_probe, out);
+}
+static bpt_status trace_probes_impl(obpt_context* c, const bpt_probe_volume* vol, const float* table, uint32_t frame, uint32_t num_bounces, uint64_t first_path,
+                                    uint64_t total, float* out) {
     bpt_settings st{};
     st.ray_length = vol->ray_length; st.max_bounces = std::min(std::max(num_bounces, 1u), 15u) + 1; st.nee_mode = BPT_NEE_SHADOW_RAY;
     uint32_t nt = obpt_get_threads(c);
@@ -1177,7 +1195,8 @@ bpt_status obpt_trace_probes(obpt_context* c, const bpt_probe_volume* vol, const
         for (;;) {
             uint64_t b0 = next.fetch_add(CH);
             if (b0 >= total) break;
-            for (uint64_t path = b0; path < std::min(b0 + CH, total); path++) {
+            for (uint64_t local = b0; local < std::min(b0 + CH, total); local++) {
+                const uint64_t path = first_path + local;                                        // global path id = probe * rays_per_probe + ray
                 uint32_t ray_index = (uint32_t)(path % vol->rays_per_probe), lin = (uint32_t)(path / vol->rays_per_probe);
                 uint32_t ix = lin % vol->probe_counts[0], iy = (lin / vol->probe_counts[0]) % vol->probe_counts[1], iz = lin / vol->probe_counts[0] / vol->probe_counts[1];
                 float mx = (float)(vol->probe_counts[0] > 1 ? vol->probe_counts[0] - 1 : 1), my = (float)(vol->probe_counts[1] > 1 ? vol->probe_counts[1] - 1 : 1),
@@ -1190,7 +1209,7 @@ bpt_status obpt_trace_probes(obpt_context* c, const bpt_probe_volume* vol, const
                 f3 D = uniform_sphere_sample(table[2 * rand_index], table[2 * rand_index + 1]);  // :27-29
                 float rgb[3] = {0, 0, 0}, first_t = -1.0f;
                 trace_path<float>(*c, st, true, frame, (uint32_t)path, O, D, rgb, &first_t, outs[tid]);
-                out[4 * path] = rgb[0]; out[4 * path + 1] = rgb[1]; out[4 * path + 2] = rgb[2]; out[4 * path + 3] = first_t;
+                out[4 * local] = rgb[0]; out[4 * local + 1] = rgb[1]; out[4 * local + 2] = rgb[2]; out[4 * local + 3] = first_t;
             }
         }
     };

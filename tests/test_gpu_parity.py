@@ -290,6 +290,24 @@ def test_probe_tracing_parity(lib, oracle, mode):
         np.testing.assert_array_equal(a[:, :3], b[:, :3])              # one light → identical add order
 
 
+def test_probe_range_is_the_sharding_unit(lib, oracle):
+    """SURVEY §8e for the DDGI update: the probes of a volume split into per-rank ranges (sharding.probe_range) trace to exactly the
+    rows of the full call — keys are global probe indices — so an all-gather of the ranges reproduces the single-GPU update."""
+    from bisemutum_engine_b200 import sharding
+    scene = scenes.small_test_scene()
+    gpu, ref = make_pair(lib, oracle, scene, 32, 32, capi.ACCEL_TWO_LEVEL)
+    table = scenes.ddgi_sample_randoms()
+    vol = scenes.probe_volume(scene, (5, 3, 7), 64, ray_length=100.0)   # 105 probes: uneven over 4 ranks
+    full = gpu.trace_probes(vol, table, 3, 2)
+    np.testing.assert_array_equal(full, ref.trace_probes(vol, table, 3, 2))
+    parts = [gpu.trace_probes_range(vol, table, 3, 2, *sharding.probe_range(105, r, 4)) for r in range(4)]
+    np.testing.assert_array_equal(np.concatenate(parts).view(np.uint32), full.view(np.uint32))
+    np.testing.assert_array_equal(parts[2], ref.trace_probes_range(vol, table, 3, 2, *sharding.probe_range(105, 2, 4)))
+    assert gpu.trace_probes_range(vol, table, 3, 2, 10, 0).shape == (0, 4)
+    with pytest.raises(capi.BptError):
+        gpu.trace_probes_range(vol, table, 3, 2, 100, 6)
+
+
 def test_probe_tracing_full_size_config5(lib, oracle):
     """32 x 32 x 16 probes x 256 rays = 4 194 304 rays per bounce over the atrium; a 1/64 slice of the probes is
     compared with the oracle bit-exactly (probe rays are independent), the full volume is checked for sanity."""

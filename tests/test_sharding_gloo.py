@@ -49,3 +49,52 @@ def test_two_rank_sharding_equals_single_process(oracle, tmp_path):
     ref = ctx.resolve(2 * STEPS)
     # FP32 sums associate differently across ranks: equal to ~1e-7 relative, not bitwise
     np.testing.assert_allclose(img, ref, rtol=1e-5, atol=1e-7)
+
+
+# ---- DDGI update sharded by probe index + all-gather of the per-ray results -------------------------------------
+PROBES, RAYS = (3, 2, 3), 16
+
+
+def _probe_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bisemutum_engine_b200 import capi, scenes, sharding
+    from oracle import oracle_py
+    scene = scenes.small_test_scene()
+    ctx = oracle_py.OracleContext(8, 8, threads=2)
+    ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    vol = scenes.probe_volume(scene, PROBES, RAYS, ray_length=50.0); tab = scenes.ddgi_sample_randoms()
+    n = PROBES[0] * PROBES[1] * PROBES[2]
+    first, count = sharding.probe_range(n, rank, world)
+    mine = torch.from_numpy(ctx.trace_probes_range(vol, tab, 5, 2, first, count))
+    rays = sharding.allgather_probe_rays(mine, n, RAYS)
+    irr, vis = ctx.blend_probes(vol, tab, 5, rays.numpy())            # every rank blends all probes from the gathered rays
+    np.savez(out_path + f".{rank}.npz", rays=rays.numpy(), irr=irr, vis=vis)
+    dist.destroy_process_group()
+
+
+def test_two_rank_probe_sharding_equals_single_process(oracle, tmp_path):
+    from bisemutum_engine_b200 import capi, scenes, sharding
+    n = PROBES[0] * PROBES[1] * PROBES[2]                              # 18 probes over 2 and 4 ranks: even and uneven blocks
+    for world in (2, 4, 5):
+        r = [sharding.probe_range(n, k, world) for k in range(world)]
+        assert r[0][0] == 0 and sum(c for _, c in r) == n and all(r[k][0] + r[k][1] == r[k + 1][0] for k in range(world - 1))
+    out = str(tmp_path / "probes")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_probe_worker, args=(2, port, out), nprocs=2, join=True)
+    scene = scenes.small_test_scene()
+    ctx = oracle.OracleContext(8, 8); ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    vol = scenes.probe_volume(scene, PROBES, RAYS, ray_length=50.0); tab = scenes.ddgi_sample_randoms()
+    want = ctx.trace_probes(vol, tab, 5, 2)
+    irr, vis = ctx.blend_probes(vol, tab, 5, want)
+    for rank in (0, 1):
+        got = np.load(out + f".{rank}.npz")
+        np.testing.assert_array_equal(got["rays"].view(np.uint32), want.view(np.uint32))          # bit-identical: keys are global probe indices
+        np.testing.assert_array_equal(got["irr"], irr); np.testing.assert_array_equal(got["vis"], vis)
+    # a range in the middle of the volume equals the same rows of the full call; an out-of-range request is refused
+    part = ctx.trace_probes_range(vol, tab, 5, 2, 7, 4)
+    np.testing.assert_array_equal(part.view(np.uint32), want[7 * RAYS:11 * RAYS].view(np.uint32))
+    import pytest
+    with pytest.raises(capi.BptError):
+        ctx.trace_probes_range(vol, tab, 5, 2, n - 1, 2)
