@@ -66,6 +66,33 @@ def compute(name, scene, bounces, make_ctx):
     return out
 
 
+# ---- golden_v2.npz: the passes either side of the path (post-process, sky IBL, ray-traced reflections) ----
+OUT2 = os.path.join(HERE, "golden_v2.npz")
+IBL_DESC = dict(diffuse_size=4, specular_size=8, specular_levels=4, brdf_lut_size=8, diffuse_strength=0.9, specular_strength=0.7)
+
+
+def compute_v2(make_ctx, post_process):
+    """make_ctx(w, h) -> context of the implementation under test; post_process(ctx, sums, spp, settings) -> image."""
+    out = {}
+    scene = scenes.scene_basic(os.path.join(HERE, "scene_basic.npz"))
+    ctx = make_ctx(W, H)
+    ctx.upload_scene(scene, capi.ACCEL_TWO_LEVEL)
+    cam = oracle_py.camera_matrices(scene.camera, W, H)
+    ctx.render(cam, 0, 2, capi.Settings(max_bounces=3))
+    sums = ctx.resolve(1)
+    out["post.bloom"] = post_process(ctx, sums, 2, capi.PostSettings(True, 0.5, 0.5))[..., :3].copy()
+    d, s, b = ctx.precompute_sky_ibl(capi.SkyIblDesc(**IBL_DESC))
+    out["ibl.diffuse"] = d[..., :3].copy(); out["ibl.brdf"] = b
+    for l, lv in enumerate(s):
+        out[f"ibl.specular{l}"] = lv[..., :3].copy()
+    depth, g = ctx.render_primary(cam, 0, capi.Settings(max_bounces=3))
+    for half, ibl in ((True, False), (False, True)):
+        refl, hit = ctx.trace_reflection(cam, 3, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.5, half, ibl))
+        out[f"rtr.half{int(half)}.ibl{int(ibl)}.color"] = refl[..., :3].copy(); out[f"rtr.half{int(half)}.ibl{int(ibl)}.hit"] = hit
+    ctx.close()
+    return out
+
+
 def main():
     oracle_py.build()
     out = {}
@@ -73,6 +100,9 @@ def main():
         out.update(compute(name, scene, bounces, oracle_py.OracleContext))
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes,", len(out), "arrays")
+    out2 = compute_v2(oracle_py.OracleContext, lambda ctx, sums, spp, st: oracle_py.post_process_image(sums * (np.float32(1.0) / np.float32(spp)), st))
+    np.savez_compressed(OUT2, **out2)
+    print("wrote", OUT2, os.path.getsize(OUT2), "bytes,", len(out2), "arrays")
 
 
 if __name__ == "__main__":

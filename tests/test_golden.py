@@ -43,3 +43,31 @@ def test_cuda_reproduces_golden(golden, case):
     for name, scene, bounces in make_golden.cases():
         if name == case:
             check(golden, make_golden.compute(name, scene, bounces, lambda w, h: capi.Context(lib, w, h)), case == "mixed")
+
+
+# ---- golden_v2.npz: post-process, sky IBL, ray-traced reflections -------------------------------------------------------------
+@pytest.fixture(scope="module")
+def golden2():
+    return np.load(os.path.join(GOLDEN_DIR, "golden_v2.npz"))
+
+
+def test_oracle_reproduces_golden_v2(oracle, golden2):
+    got = make_golden.compute_v2(oracle.OracleContext, lambda ctx, sums, spp, st: oracle.post_process_image(sums * (np.float32(1.0) / np.float32(spp)), st))
+    assert set(got) == set(golden2.files)
+    for k, v in got.items():
+        np.testing.assert_array_equal(v, golden2[k], err_msg=k)
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_golden_v2(golden2):
+    lib = pkg.load_library()
+
+    def post(ctx, sums, spp, st):
+        ctx.upload_accum(sums)                       # (the render's own sums, handed back: post-process reads the accumulation buffer)
+        return ctx.post_process(st, spp)
+    got = make_golden.compute_v2(lambda w, h: capi.Context(lib, w, h), post)
+    for k, v in got.items():
+        if k.endswith(".color"):                     # several lights -> unordered shadow-ray atomics: 1e-4 (BASELINE.json)
+            np.testing.assert_allclose(v, golden2[k], rtol=1e-4, atol=1e-6, err_msg=k)
+        else:
+            np.testing.assert_array_equal(v, golden2[k], err_msg=k)

@@ -27,7 +27,8 @@ counts, rays_per_probe = (32, 32, 16), 256                        # BASELINE con
 vol = scenes.probe_volume(scene, counts, rays_per_probe); tab = scenes.ddgi_sample_randoms()
 n = counts[0] * counts[1] * counts[2]
 first, count = sharding.probe_range(n, rank, world)
-ctx.trace_probes_range(vol, tab, 100, 2, first, min(count, 64))   # warm-up
+warm = torch.from_numpy(ctx.trace_probes_range(vol, tab, 100, 2, first, count)).cuda()   # warm-up: kernels, pinned staging, NCCL communicator
+sharding.allgather_probe_rays(warm, n, rays_per_probe)
 dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
 mine = torch.from_numpy(ctx.trace_probes_range(vol, tab, 0, 2, first, count)).cuda()
