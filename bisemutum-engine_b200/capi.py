@@ -205,6 +205,7 @@ COMMON_API = {
     "debug_read_queue": [_VP, _U32, _U32, _VP, _VP, _VP, _U64, _PU64],
     "render_primary": [_VP, C.POINTER(Camera), _U32, C.POINTER(Settings), _VP, _VP],
     "trace_ao": [_VP, C.POINTER(Camera), _U32, C.POINTER(AoSettings), _VP, _VP, _VP],
+    "upscale_half_res": [_VP, C.POINTER(Camera), _U32, _VP, _VP, _VP, _VP],
     "precompute_sky_ibl": [_VP, C.POINTER(SkyIblDesc)],
     "debug_read_sky_ibl": [_VP, _VP, _VP, _VP],
     "trace_reflection": [_VP, C.POINTER(Camera), _U32, C.POINTER(ReflectionSettings), _VP, _VP, _VP, _VP],
@@ -422,6 +423,13 @@ class Context:
         d = np.ascontiguousarray(depth, dtype=f32); nr = np.ascontiguousarray(normal_roughness, dtype=f32)
         assert d.shape == (self.height, self.width) and nr.shape == (self.height, self.width, 4)
         self._call("trace_ao", C.byref(camera), frame_index, C.byref(ao), _ptr(d), _ptr(nr), _ptr(out))
+        return out
+
+    def upscale_half_res(self, camera: Camera, frame_index: int, depth: np.ndarray, normal_roughness: np.ndarray, half: np.ndarray) -> np.ndarray:
+        """simple_upscale_cs ("RTR Upscale Hit / Color"): ((H+1)/2, (W+1)/2, 4) -> (H, W, 4)."""
+        out = np.zeros((self.height, self.width, 4), dtype=f32)
+        self._call("upscale_half_res", C.byref(camera), frame_index, _ptr(np.ascontiguousarray(depth, dtype=f32)),
+                   _ptr(np.ascontiguousarray(normal_roughness, dtype=f32)), _ptr(np.ascontiguousarray(half, dtype=f32)), _ptr(out))
         return out
 
     def precompute_sky_ibl(self, desc: SkyIblDesc | None = None):

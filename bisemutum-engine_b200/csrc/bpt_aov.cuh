@@ -143,4 +143,44 @@ BPT_HD bool rtr_pixel_ray(const bpt_camera& cam, uint32_t px, uint32_t py, uint3
     return true;
 }
 
+// ---- simple_upscale_cs (shaders/renderer/simple_upscale.hlsl:47-97): one full-resolution pixel ----
+BPT_HD float linear_01_depth(float depth, const bpt_camera& cam) {      // core/utils/depth.hlsl:31-35; inv_proj[3] is ROW 3: (m[3], m[7], m[11], m[15])
+    const float a = cam.matrix_inv_proj[11], b = cam.matrix_inv_proj[15];
+    return ((1.0f - depth) * b) / (a * depth + b);
+}
+BPT_HD float4 upscale_pixel(const bpt_camera& cam, uint32_t x, uint32_t y, uint32_t W, uint32_t H, uint32_t frame_index, const float* depth_img,
+                            const float4* normal_roughness, const float4* in_half) {
+    const int rw = (int)((W + 1) / 2), rh = (int)((H + 1) / 2);
+    auto depth_at = [&](int px, int py) { return (px < (int)W && py < (int)H) ? depth_img[(size_t)py * W + px] : 0.0f; };        // Texture.Load: 0 out of range
+    auto normal_at = [&](int px, int py) {
+        float4 nr = (px < (int)W && py < (int)H) ? normal_roughness[(size_t)py * W + px] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return oct_decode(make_float2(nr.x, nr.y));
+    };
+    const float center_depth = linear_01_depth(depth_at((int)x, (int)y), cam);
+    const float3 center_normal = normal_at((int)x, (int)y);
+    const float cx = (x & 1u) ? 0.75f : 0.25f, cy = (y & 1u) ? 0.75f : 0.25f;                           // :66-73
+    const float ix = (frame_index & 1u) ? 0.75f : 0.25f, iy = (frame_index & 2u) ? 0.75f : 0.25f;
+    const int sx = (int)(frame_index & 1u), sy = (int)((frame_index >> 1) & 1u);
+    float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float sum_weight = 0.0f;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+            float ox = ((float)dx + ix) - cx, oy = ((float)dy + iy) - cy;
+            float r = sqrtf(sqrtf(ox * ox + oy * oy));
+            float temp = r / 0.2f;
+            float w = exp_neg(-(temp * temp));                                                              // gaussian(r, 0.2)
+            int hx = (int)(x / 2) + dx, hy = (int)(y / 2) + dy;                                            // fetch_shared_data, :25-35
+            hx = hx < 0 ? 0 : (hx > rw ? rw : hx); hy = hy < 0 ? 0 : (hy > rh ? rh : hy);               // clamp(.., 0, (tex_size + 1) / 2)
+            float4 v = (hx < rw && hy < rh) ? in_half[(size_t)hy * rw + hx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            float tap_depth = linear_01_depth(depth_at(hx * 2 + sx, hy * 2 + sy), cam);
+            float3 tap_normal = normal_at(hx * 2 + sx, hy * 2 + sy);
+            w = w * tmax_(dot3(tap_normal, center_normal), 0.0f);
+            w = w * tmax_(0.0f, 1.0f - fabsf(tap_depth - center_depth));
+            sum = make_float4(sum.x + v.x * w, sum.y + v.y * w, sum.z + v.z * w, sum.w + v.w * w);
+            sum_weight = sum_weight + w;
+        }
+    if (sum_weight == 0.0f) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    return make_float4(sum.x / sum_weight, sum.y / sum_weight, sum.z / sum_weight, sum.w / sum_weight);
+}
+
 } // namespace bptd

@@ -472,6 +472,12 @@ bpt_status bpt_trace_ao(bpt_context* c, const bpt_camera* cam, uint32_t frame_in
     return wavefront_trace_ao(c, *cam, frame_index, *ao, depth, normal_roughness, out_ao);
 }
 
+bpt_status bpt_upscale_half_res(bpt_context* c, const bpt_camera* cam, uint32_t frame_index, const float* depth, const float* nr, const float* in_half, float* out) {
+    NEED(c);
+    if (!cam || !depth || !nr || !in_half || !out) return BPT_ERR_INVALID;
+    return launch_upscale_half_res(c, *cam, frame_index, depth, nr, in_half, out);
+}
+
 bpt_status bpt_precompute_sky_ibl(bpt_context* c, const bpt_sky_ibl_desc* d) {
     NEED(c);
     if (!d) return BPT_ERR_INVALID;

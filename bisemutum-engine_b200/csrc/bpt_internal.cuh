@@ -131,6 +131,7 @@ bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t 
                               const float* h_normal_roughness, float* h_out);
 bpt_status wavefront_trace_reflection(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_reflection_settings& rs, const float* h_depth,
                                       const bpt_gbuffer_texel* h_gbuffer, float* h_refl, float* h_hit);
+bpt_status launch_upscale_half_res(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const float* h_depth, const float* h_nr, const float* h_in, float* h_out);
 bpt_status launch_ddgi_lighting(bpt_context* ctx, uint64_t n, const float* h_pos, const float* h_normal, const float* h_view, float* h_out);
 bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, uint32_t num_bounces, float* h_out,
                                   uint32_t first_probe = 0, uint32_t num_probes = 0xffffffffu);

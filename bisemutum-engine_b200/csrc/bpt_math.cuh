@@ -105,6 +105,19 @@ BPT_HD void sincos_2pi(float u, float& s, float& c) {
     s = qi == 0 ? sr : (qi == 1 ? cr : (qi == 2 ? -sr : -cr));
     c = qi == 0 ? cr : (qi == 1 ? -sr : (qi == 2 ? -cr : sr));
 }
+// exp(x) for x <= 0 in fixed order (range reduction by ln 2, degree-6 polynomial): ~2e-7 relative; 0 below -87
+BPT_HD float exp_neg(float x) {
+    if (x < -87.0f) return 0.0f;
+    float n = floorf(x * 1.44269504f + 0.5f);
+    float r = (x - n * 0.693145752f) - n * 1.42860677e-6f;
+    float p = 0.00833333333f + r * 0.00138888889f;
+    p = 0.0416666667f + r * p;
+    p = 0.166666667f + r * p;
+    p = 0.5f + r * p;
+    p = 1.0f + r * p;
+    p = 1.0f + r * p;
+    return p * u2f((uint32_t)((int)n + 127) << 23);
+}
 BPT_HD float atan_unit(float z) {
     float z2 = z * z;
     float p = 0.00282363896f;

@@ -540,6 +540,13 @@ __global__ void __launch_bounds__(kBlock) k_rtr_finish(const __grid_constant__ R
     out_hit[p] = hp;
 }
 
+__global__ void k_upscale_half_res(const __grid_constant__ bpt_camera cam, uint32_t W, uint32_t H, uint32_t frame_index, const float* __restrict__ depth,
+                                   const float4* __restrict__ normal_roughness, const float4* __restrict__ in_half, float4* __restrict__ out) {
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    out[(size_t)y * W + x] = upscale_pixel(cam, x, y, W, H, frame_index, depth, normal_roughness, in_half);
+}
+
 __global__ void k_ao_finish(const float4* __restrict__ color, uint32_t n, float strength, float2* __restrict__ out) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -965,6 +972,24 @@ bpt_status wavefront_trace_reflection(bpt_context* ctx, const bpt_camera& cam, u
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("trace_reflection: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
+    return BPT_OK;
+}
+
+bpt_status launch_upscale_half_res(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const float* h_depth, const float* h_nr, const float* h_in, float* h_out) {
+    const uint32_t W = ctx->width, H = ctx->height, rw = (W + 1) / 2, rh = (H + 1) / 2;
+    DevBuf d_depth, d_nr, d_in, d_out;
+    auto cleanup = [&]() { dev_free(d_depth); dev_free(d_nr); dev_free(d_in); dev_free(d_out); };
+    bpt_status s;
+    if ((s = dev_upload(ctx, d_depth, h_depth, (size_t)W * H * 4)) || (s = dev_upload(ctx, d_nr, h_nr, (size_t)W * H * 16)) ||
+        (s = dev_upload(ctx, d_in, h_in, (size_t)rw * rh * 16)) || (s = dev_alloc(ctx, d_out, (size_t)W * H * 16))) { cleanup(); return s; }
+    k_upscale_half_res<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, ctx->stream>>>(cam, W, H, frame_index, d_depth.as<float>(), d_nr.as<float4>(),
+                                                                                     d_in.as<float4>(), d_out.as<float4>());
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out.p, (size_t)W * H * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) { ctx->err = std::string("upscale_half_res: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
     return BPT_OK;
 }
 

@@ -501,6 +501,14 @@ BPT_API bpt_status bpt_trace_reflection(
     bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_reflection_settings* settings,
     const float* depth /* W*H */, const bpt_gbuffer_texel* gbuffer /* W*H */,
     float* out_reflection /* rw*rh*4 */, float* out_hit_positions /* rw*rh*4 */);
+/* "RTR Upscale Hit" / "RTR Upscale Color" (ReflectionPass::render_upscale, reflection.cpp:452-530; shaders/renderer/simple_upscale.hlsl):
+ * a half-resolution image ((W+1)/2 x (H+1)/2 float4, traced with the frame's sub-pixel) to full resolution with a 3 x 3 half-res
+ * neighbourhood weighted by a Gaussian of the sub-pixel distance, the normal agreement and the linear-depth difference. `depth`
+ * and `normal_roughness` are the full-resolution images of bpt_render_primary; out-of-range taps read 0 like Texture.Load.
+ * exp() is the fixed-order form of the numeric contract. Synchronous. */
+BPT_API bpt_status bpt_upscale_half_res(
+    bpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const float* depth /* W*H */, const float* normal_roughness /* W*H*4 */,
+    const float* in_half_res /* rw*rh*4 */, float* out_full_res /* W*H*4 */);
 
 /* ---------------------------------------------------------------------------------------
  * DDGI-style probe tracing through the same extend/shade kernels

@@ -93,6 +93,8 @@ BPT_API bpt_status obpt_precompute_sky_ibl(obpt_context* ctx, const bpt_sky_ibl_
 BPT_API bpt_status obpt_debug_read_sky_ibl(obpt_context* ctx, float* diffuse_rgba32f, float* specular_rgba32f, float* brdf_lut_rg32f);
 BPT_API bpt_status obpt_trace_reflection(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const bpt_reflection_settings* settings,
                                          const float* depth, const bpt_gbuffer_texel* gbuffer, float* out_reflection, float* out_hit_positions);
+BPT_API bpt_status obpt_upscale_half_res(obpt_context* ctx, const bpt_camera* camera, uint32_t frame_index, const float* depth, const float* normal_roughness,
+                                         const float* in_half_res, float* out_full_res);
 BPT_API bpt_status obpt_trace_probes(
     obpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2,
     uint32_t frame_index, uint32_t num_bounces, float* out_radiance_dist);

@@ -351,6 +351,19 @@ static inline f3 surface_eval(f3 N, f3 T, f3 B, f3 V, f3 L, const SurfaceData& s
     f3 specular = fr * ndf * vis * fmax_(ll.z, 0.0f);
     return diffuse + specular;
 }
+// exp(x) for x <= 0 in fixed order (shared definition with csrc/bpt_math.cuh: exp_neg): ln 2 range reduction + degree-6 polynomial
+static inline float exp_neg(float x) {
+    if (x < -87.0f) return 0.0f;
+    float n = floorf(x * 1.44269504f + 0.5f);
+    float r = (x - n * 0.693145752f) - n * 1.42860677e-6f;
+    float p = 0.00833333333f + r * 0.00138888889f;
+    p = 0.0416666667f + r * p;
+    p = 0.166666667f + r * p;
+    p = 0.5f + r * p;
+    p = 1.0f + r * p;
+    p = 1.0f + r * p;
+    return p * u2f((uint32_t)((int)n + 127) << 23);
+}
 // the specular term alone (the `bsdf_specular` out-parameter of surface_eval, material.hlsl:81-118 / lit.hlsl:5-35)
 static inline f3 surface_eval_specular(f3 N, f3 T, f3 B, f3 V, f3 L, const SurfaceData& s, uint32_t surface_model) {
     if (surface_model != 1u) return splat3(0.0f);

@@ -1158,6 +1158,48 @@ bpt_status obpt_trace_reflection(obpt_context* c, const bpt_camera* cam, uint32_
     return BPT_OK;
 }
 
+// "RTR Upscale Hit" / "RTR Upscale Color": simple_upscale_cs (shaders/renderer/simple_upscale.hlsl:47-97; reflection.cpp:452-530). The group-shared
+// tile of the shader is only a cache: tap (dx, dy) of pixel (x, y) is half-res texel clamp((x / 2 + dx, y / 2 + dy), 0, (tex_size + 1) / 2) (:25-35).
+bpt_status obpt_upscale_half_res(obpt_context* c, const bpt_camera* cam, uint32_t frame_index, const float* depth_img, const float* nr_img, const float* in_half, float* out) {
+    CHECK_CTX(c); if (!cam || !depth_img || !nr_img || !in_half || !out) return BPT_ERR_INVALID;
+    const int W = (int)c->width, H = (int)c->height, rw = (W + 1) / 2, rh = (H + 1) / 2;
+    const float a = cam->matrix_inv_proj[11], b = cam->matrix_inv_proj[15];                      // inv_proj[3].z / .w: HLSL M[3] is row 3 (depth.hlsl:31-35)
+    auto linear01 = [&](float d) { return ((1.0f - d) * b) / (a * d + b); };
+    auto depth_at = [&](int px, int py) { return (px < W && py < H) ? depth_img[(size_t)py * W + px] : 0.0f; };      // Texture.Load out of range = 0
+    auto normal_at = [&](int px, int py) {
+        f2 e = (px < W && py < H) ? f2{nr_img[4 * ((size_t)py * W + px)], nr_img[4 * ((size_t)py * W + px) + 1]} : f2{0.0f, 0.0f};
+        return oct_decode(e);
+    };
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const float center_depth = linear01(depth_at(x, y));
+            const f3 center_normal = normal_at(x, y);
+            const float cx = (x & 1) ? 0.75f : 0.25f, cy = (y & 1) ? 0.75f : 0.25f;             // :66-69
+            const float ix = (frame_index & 1u) ? 0.75f : 0.25f, iy = (frame_index & 2u) ? 0.75f : 0.25f;     // :70-73
+            const int sx = (int)(frame_index & 1u), sy = (int)((frame_index >> 1) & 1u);        // :32
+            float sum[4] = {0, 0, 0, 0}, sum_weight = 0.0f;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    float ox = ((float)dx + ix) - cx, oy = ((float)dy + iy) - cy;               // :79
+                    float r = sqrtf(sqrtf(ox * ox + oy * oy));                                  // :80 sqrt(length(offset))
+                    float temp = r / 0.2f;
+                    float w = exp_neg(-(temp * temp));                                          // gaussian(r, 0.2), :38-41
+                    int hx = std::min(std::max(x / 2 + dx, 0), rw), hy = std::min(std::max(y / 2 + dy, 0), rh);
+                    float v[4] = {0, 0, 0, 0};
+                    if (hx < rw && hy < rh) for (int k = 0; k < 4; k++) v[k] = in_half[4 * ((size_t)hy * rw + hx) + k];
+                    float tap_depth = linear01(depth_at(hx * 2 + sx, hy * 2 + sy));
+                    f3 tap_normal = normal_at(hx * 2 + sx, hy * 2 + sy);
+                    w = w * fmax_(dot(tap_normal, center_normal), 0.0f);                        // :87
+                    w = w * fmax_(0.0f, 1.0f - fabsf(tap_depth - center_depth));                // :89
+                    for (int k = 0; k < 4; k++) sum[k] = sum[k] + v[k] * w;
+                    sum_weight = sum_weight + w;
+                }
+            float* o = out + 4 * ((size_t)y * W + x);
+            for (int k = 0; k < 4; k++) o[k] = sum_weight == 0.0f ? 0.0f : sum[k] / sum_weight; // :96
+        }
+    return BPT_OK;
+}
+
 // DDGI-style probe tracing: ddgi/trace_gbuffer.hlsl:10-51 (probe centre, R2-table direction, TraceRay) +
 // ddgi/deferred_lighting.hlsl:12-118 (diffuse-only surface, V = normalize(probe - P)); further bounces continue
 // the path through the same trace/shade code (BASELINE configs[4]); previous-frame DDGI feedback is not modelled.

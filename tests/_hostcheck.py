@@ -67,6 +67,7 @@ def lib():
         _lib.hc_trace_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.hc_read_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_void_p]
         _lib.hc_precompute_sky_ibl.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(capi.SkyIblDesc), C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.hc_upscale_half_res.argtypes = [C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_post_process.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.PostSettings), C.c_void_p]
     return _lib
 
@@ -222,3 +223,11 @@ def precompute_sky_ibl(scene, desc):
         s_ = desc.specular_size >> l
         levels.append(spec[off:off + 6 * s_ * s_].reshape(6, s_, s_, 4)); off += 6 * s_ * s_
     return diffuse, levels, brdf
+
+
+def upscale_half_res(camera, width, height, frame_index, depth, normal_roughness, half):
+    d = np.ascontiguousarray(depth, np.float32); nr = np.ascontiguousarray(normal_roughness, np.float32); h = np.ascontiguousarray(half, np.float32)
+    out = np.zeros((height, width, 4), np.float32)
+    lib().hc_upscale_half_res(C.byref(camera), width, height, frame_index, d.ctypes.data_as(C.c_void_p), nr.ctypes.data_as(C.c_void_p),
+                              h.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out

@@ -519,3 +519,14 @@ int hc_precompute_sky_ibl(const float* sky_faces, uint32_t sky_size, const bpt_s
     g_ibl.enabled = true;
     return 0;
 }
+
+extern "C" __attribute__((visibility("default")))
+int hc_upscale_half_res(const bpt_camera* cam, uint32_t W, uint32_t H, uint32_t frame_index, const float* depth, const float* nr, const float* in_half, float* out) {
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) {
+            float4 v = upscale_pixel(*cam, x, y, W, H, frame_index, depth, reinterpret_cast<const float4*>(nr), reinterpret_cast<const float4*>(in_half));
+            float* o = out + 4 * ((size_t)y * W + x);
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        }
+    return 0;
+}

@@ -195,3 +195,67 @@ def test_gpu_sky_ibl_and_reflection_with_ibl(oracle):
     dd, ss, bb = gpu.precompute_sky_ibl(capi.SkyIblDesc())
     assert dd.shape == (6, 256, 256, 4) and len(ss) == 5 and bb.shape == (128, 128, 2) and np.isfinite(dd).all() and np.isfinite(ss[4]).all()
     gpu.close(); ctx.close()
+
+
+# ---- "RTR Upscale Hit / Color": simple_upscale.hlsl (reflection.cpp:452-530) ------------------------------------------------
+def _upscale_case(oracle, size=(W, H)):
+    w, h = size
+    scene = _glossy_scene()
+    ctx = oracle.OracleContext(w, h); ctx.upload_scene(scene, capi.ACCEL_MERGED)
+    cam = oracle.camera_matrices(scene.camera, w, h)
+    depth, g = ctx.render_primary(cam, 0, capi.Settings(max_bounces=4))
+    return ctx, cam, depth, g
+
+
+def test_upscale_half_res_bit_exact_on_host(oracle):
+    ctx, cam, depth, g = _upscale_case(oracle)
+    nr = g["normal_roughness"]
+    for frame in range(4):
+        refl, hit = ctx.trace_reflection(cam, frame, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.6, True))
+        for half in (refl, hit):
+            full = ctx.upscale_half_res(cam, frame, depth, nr, half)
+            hfull = HC.upscale_half_res(cam, W, H, frame, depth, nr, half)
+            np.testing.assert_array_equal(full.view(np.uint32), hfull.view(np.uint32))
+            assert full.shape == (H, W, 4) and np.isfinite(full).all()
+    # a constant input stays that constant wherever any tap has weight (the filter is a normalised average)
+    const = np.full((H // 2, W // 2, 4), 0.625, np.float32)
+    full = ctx.upscale_half_res(cam, 1, depth, nr, const)
+    inner = full[:-2, :-2]                                    # (the last row / column also average the out-of-range half-res texel, which Loads as 0)
+    nz = inner[..., 0] != 0
+    assert nz.mean() > 0.5
+    np.testing.assert_allclose(inner[nz], 0.625, rtol=1e-6)
+    # the pixel whose sub-pixel equals the traced one takes (almost) only its own half-res texel: gaussian(0) = 1, the others <= exp(-12.5)
+    refl, _ = ctx.trace_reflection(cam, 3, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.6, True))
+    full = ctx.upscale_half_res(cam, 3, depth, nr, refl)
+    own = full[1::2, 1::2]                                   # frame 3 traced sub-pixel (0.75, 0.75) = odd x, odd y
+    sel = (depth[1::2, 1::2] > 0) & (refl[..., :3].max(axis=2) > 0)
+    np.testing.assert_allclose(own[sel][:, :3], refl[sel][:, :3], rtol=2e-3, atol=1e-5)
+
+
+def test_fixed_order_exp(oracle):
+    """exp_neg of the numeric contract (oracle_math.hpp = csrc/bpt_math.cuh) against libm, through the upscale weights: a one-texel
+    impulse spreads to its neighbours with gaussian(sqrt(|offset|), 0.2) = exp(-25 |offset|)."""
+    ctx, cam, depth, g = _upscale_case(oracle)
+    nr = np.zeros((H, W, 4), np.float32)                      # oct (0, 0) -> normal (0, 0, 1) everywhere: normal weight 1
+    flat = np.full((H, W), 0.5, np.float32)                  # constant depth: depth weight 1
+    imp = np.zeros((H // 2, W // 2, 4), np.float32); imp[8, 10] = 1.0
+    full = ctx.upscale_half_res(cam, 0, flat, nr, imp)       # frame 0: traced sub-pixel (0.25, 0.25) = even x, even y
+    # full-res pixel (20, 16) has the impulse as its centre tap with offset 0; pixel (21, 16) sees it at offset (-0.5, 0)
+    offs = lambda x, y: [((dx + 0.25) - (0.75 if x & 1 else 0.25), (dy + 0.25) - (0.75 if y & 1 else 0.25)) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+    for (x, y) in ((20, 16), (21, 16), (21, 17)):
+        ws = np.array([np.exp(-25.0 * np.hypot(ox, oy)) for ox, oy in offs(x, y)])
+        want = ws[4] / ws.sum()                               # the impulse is the centre tap (x / 2, y / 2) = (10, 8)
+        np.testing.assert_allclose(full[y, x, 0], want, rtol=2e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_upscale_half_res_bit_exact(oracle):
+    ctx, cam, depth, g = _upscale_case(oracle)
+    gpu = capi.Context(pkg.load_library(), W, H)
+    nr = g["normal_roughness"]
+    for frame in (0, 3):
+        refl, hit = ctx.trace_reflection(cam, frame, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.6, True))
+        for half in (refl, hit):
+            np.testing.assert_array_equal(gpu.upscale_half_res(cam, frame, depth, nr, half).view(np.uint32),
+                                          ctx.upscale_half_res(cam, frame, depth, nr, half).view(np.uint32))
+    gpu.close(); ctx.close()
