@@ -22,4 +22,4 @@ from . import capi, scenes  # noqa: E402,F401
 
 def load_library():
     """Loads libbpt.so (the CUDA implementation). Raises if it has not been built."""
-    return capi.Library(LIBBPT_PATH, "bpt_", capi.BPT_ONLY_API)
+    return capi.Library(_os.environ.get("BPT_LIB") or LIBBPT_PATH, "bpt_", capi.BPT_ONLY_API)      # BPT_LIB: an experimental variant (tools/build_variant.sh)
