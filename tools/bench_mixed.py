@@ -14,4 +14,10 @@ ctx.render(cam, 1000, 2, st); ctx.sync(); ctx.reset_counters()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream); ctx.render(cam, 0, 16, st); e1.record(stream); torch.cuda.synchronize()
 c = ctx.counters(); ms = e0.elapsed_time(e1)
-print(json.dumps({"tag": os.environ.get("BPT_WIDE_CONNECT_FROM_BOUNCE", "default"), "ms_per_spp": ms / 16, "mrays_per_s": (c.extend_rays + c.shadow_rays) / ms / 1e3}))
+out = {"tag": os.environ.get("BPT_WIDE_CONNECT_FROM_BOUNCE", "default"), "ms_per_spp": ms / 16, "mrays_per_s": (c.extend_rays + c.shadow_rays) / ms / 1e3,
+       "extend_rays_per_spp": c.extend_rays / 16, "shadow_rays_per_spp": c.shadow_rays / 16}
+ctx.profile_enable(True); ctx.render(cam, 0, 16, st); kt = ctx.profile_read(); ctx.profile_enable(False)
+for f, _ in kt._fields_:
+    v = getattr(kt, f)
+    out[f] = (v / 16) if isinstance(v, float) else v
+print(json.dumps(out))
