@@ -82,7 +82,13 @@ BPT_HD float2 ltc_brdf_lerp(const DScene& sc, float4 u) {                      /
 }
 BPT_HD void rewind(float3* L) { float3 t0 = L[0], t1 = L[1]; L[0] = L[3]; L[1] = L[2]; L[2] = t1; L[3] = t0; }
 
-BPT_HD void ltc_matrix_and_brdf(const DScene& sc, float3 lv, float rx, float ry, float3* L, Mat3& M, float2& brdf) {   // lights.hlsl:203-273
+// What of rect_light_eval_ltc depends on the SURFACE only (view direction in the tangent frame, roughness): LUT coordinates, the
+// two LUT fetches + lerps, quadrant flips, the matrix inverse (lights.hlsl:203-273 + :494). It is computed once per path vertex and
+// shared by all rect lights (16 on BASELINE configs[2]); per light only the corner winding (`rewind`) and the two integrals remain.
+// Same operations in the same order as the per-light form, so the result is unchanged bit for bit.
+struct LtcSetup { Mat3 Minv; float2 brdf; bool wind, flip_roughness; };
+BPT_HD LtcSetup ltc_setup(const DScene& sc, float3 lv, float rx, float ry) {
+    LtcSetup ls;
     float theta_wi = acos_(lv.z);
     bool flip_roughness = ry > rx;
     float phi_wi = atan2_(lv.y, lv.x);
@@ -98,15 +104,16 @@ BPT_HD void ltc_matrix_and_brdf(const DScene& sc, float3 lv, float rx, float ry,
     else if (phi_wi < 1.5f * kPi) { u3 = (phi_wi - kPi) / (kPi * 0.5f); flip.r0 = v3(-1, 0, 0); flip.r1 = v3(0, -1, 0); }
     else { u3 = (2.0f * kPi - phi_wi) / (kPi * 0.5f); flip.r1 = v3(0, -1, 0); do_wind = true; }
     float4 u = make_float4(u3, u2, u1, u0);
-    if (do_wind) rewind(L);
-    M = ltc_matrix_lerp(sc, u);
+    Mat3 M = ltc_matrix_lerp(sc, u);
     if (do_flip) M = mul_mm(flip, M);
-    brdf = ltc_brdf_lerp(sc, u);
+    ls.brdf = ltc_brdf_lerp(sc, u);
     if (flip_roughness) {
         Mat3 sw; sw.r0 = v3(0, 1, 0); sw.r1 = v3(1, 0, 0); sw.r2 = v3(0, 0, 1);
-        rewind(L);
         M = mul_mm(sw, M);
     }
+    ls.Minv = mat3_inverse(M);
+    ls.wind = do_wind; ls.flip_roughness = flip_roughness;
+    return ls;
 }
 
 BPT_HD float3 clip_mix(float3 a, float3 b) { return -a.z * b + b.z * a; }      // -A.z * B + B.z * A
@@ -169,12 +176,9 @@ BPT_HD float ltc_integrate(float3 P, float3 N, float3 T, float3 B, const Mat3& M
     return integral;
 }
 
-// rect_light_eval_ltc (lights.hlsl:449-513) + surface_eval_lut
+// rect_light_eval_ltc (lights.hlsl:449-513) + surface_eval_lut. `setup` = ltc_setup of this vertex when lv.z > 0 (else unused).
 BPT_HD float3 eval_rect_light(const DScene& sc, const bpt_rect_light_data& light, float3 P, float3 N, float3 T, float3 B, float3 V,
-                              const Surface& s, uint32_t surface_model, float3* diff_mrp = nullptr) {
-    float rx, ry;
-    aniso_roughness(s.roughness, s.anisotropy, rx, ry);
-    float3 lv = v3(dot3(V, T), dot3(V, B), dot3(V, N));
+                              const Surface& s, uint32_t surface_model, float3 lv, const LtcSetup& setup, float3* diff_mrp = nullptr) {
     float3 spec = v3s(0.0f), diff = v3s(0.0f);
     float2 brdf = make_float2(0.0f, 0.0f);
     if (lv.z > 0.0f) {
@@ -183,10 +187,10 @@ BPT_HD float3 eval_rect_light(const DScene& sc, const bpt_rect_light_data& light
         float3 emission = v3(light.emission[0], light.emission[1], light.emission[2]);
         Mat3 I; I.r0 = v3(1, 0, 0); I.r1 = v3(0, 1, 0); I.r2 = v3(0, 0, 1);
         diff = emission * ltc_integrate(P, N, T, B, I, L, light.two_sided != 0, diff_mrp);
-        Mat3 M;
-        ltc_matrix_and_brdf(sc, lv, rx, ry, L, M, brdf);
-        Mat3 Minv = mat3_inverse(M);
-        spec = emission * ltc_integrate(P, N, T, B, Minv, L, light.two_sided != 0);
+        if (setup.wind) rewind(L);                                  // lights.hlsl:203-273: the quadrant's winding, then the roughness swap's
+        if (setup.flip_roughness) rewind(L);
+        brdf = setup.brdf;
+        spec = emission * ltc_integrate(P, N, T, B, setup.Minv, L, light.two_sided != 0);
     }
     return bsdf_eval_lut(N, V, s, diff, spec, brdf, surface_model);
 }

@@ -92,10 +92,18 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     }
     float3 V = normalize3(O - P);                                       // deferred_lighting_secondary.hlsl:45
 
+    LtcSetup ltc{};                                                     // the LUT side of the LTC evaluation: once per vertex, not per light
+    float3 ltc_lv = v3s(0.0f);
+    if (sc.num_rect) {
+        float rx, ry;
+        aniso_roughness(surf.roughness, surf.anisotropy, rx, ry);
+        ltc_lv = v3(dot3(V, T), dot3(V, B), dot3(V, N));
+        if (ltc_lv.z > 0.0f) ltc = ltc_setup(sc, ltc_lv, rx, ry);
+    }
     for (uint32_t l = 0; l < sc.num_rect; l++) {                        // :72-96 (unshadowed, as the reference, unless rect_shadow)
         const bpt_rect_light_data& rl = sc.rect_lights[l];
         float3 mrp = v3s(0.0f);
-        float3 c = eval_rect_light(sc, rl, P, N, T, B, V, surf, surface_model, sp.rect_shadow ? &mrp : nullptr) * Wl;
+        float3 c = eval_rect_light(sc, rl, P, N, T, B, V, surf, surface_model, ltc_lv, ltc, sp.rect_shadow ? &mrp : nullptr) * Wl;
         if (!sp.rect_shadow) { sink.add(c); continue; }
         if (!(max3c(c) > 0.0f)) continue;
         // distance to the light's plane along mrp (as rect_light_sample_texture, lights.hlsl:425-438)
