@@ -426,6 +426,8 @@ bpt_status bpt_clear_accum(bpt_context* c) {
 static bpt_status check_precision(bpt_context* c, const bpt_settings* st) {
     if (st->state_precision != BPT_STATE_FP32 && st->state_precision != BPT_STATE_REFERENCE_FP16)
         return fail(c, BPT_ERR_INVALID, "state_precision: unknown value");
+    if ((st->nee_mode != BPT_NEE_SHADOW_RAY && st->nee_mode != BPT_NEE_NONE) || st->rect_shadow > 1 || st->russian_roulette > 1 || st->pixel_jitter > 1)
+        return fail(c, BPT_ERR_INVALID, "settings: unknown value of a mode switch (nee_mode, rect_shadow, russian_roulette, pixel_jitter)");
     const bool fp16 = st->state_precision == BPT_STATE_REFERENCE_FP16;
     if (c->accum_used && fp16 != c->wf.accum_fp16)
         return fail(c, BPT_ERR_STATE, "state_precision changed without bpt_clear_accum");

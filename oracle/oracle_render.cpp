@@ -718,6 +718,8 @@ bpt_status obpt_render(obpt_context* c, const bpt_camera* cam, uint32_t first, u
     CHECK_CTX(c); if (!cam || !st) return BPT_ERR_INVALID;
     if (!c->scene.accel_built) return fail(c, BPT_ERR_STATE, "render before build_accel");
     if (st->state_precision != BPT_STATE_FP32 && st->state_precision != BPT_STATE_REFERENCE_FP16) return fail(c, BPT_ERR_INVALID, "state_precision: unknown value");
+    if ((st->nee_mode != BPT_NEE_SHADOW_RAY && st->nee_mode != BPT_NEE_NONE) || st->rect_shadow > 1 || st->russian_roulette > 1 || st->pixel_jitter > 1)
+        return fail(c, BPT_ERR_INVALID, "settings: unknown value of a mode switch (nee_mode, rect_shadow, russian_roulette, pixel_jitter)");
     const bool fp16 = st->state_precision == BPT_STATE_REFERENCE_FP16;
     if (c->accum_used && fp16 != c->accum_fp16) return fail(c, BPT_ERR_STATE, "state_precision changed without bpt_clear_accum");
     c->accum_used = true; c->accum_fp16 = fp16;

@@ -50,6 +50,75 @@ def test_bvh_bit_exact(lib, oracle, scene_fn, mode):
         assert_bvh_equal(gpu.read_bvh(capi.BVH_TLAS), ref.read_bvh(capi.BVH_TLAS))
 
 
+def _tiny_scene(num_tris, num_instances=1):
+    b = scenes.SceneBuilder(f"tiny_{num_tris}x{num_instances}")
+    m = b.add_material((0.8, 0.7, 0.6), roughness=0.4)
+    P = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.2], [2, 0, 0.1], [2, 1, 0.3]], np.float32)
+    N = np.tile(np.array([[0, 0, 1]], np.float32), (6, 1)); T = np.tile(np.array([[1, 0, 0, 1]], np.float32), (6, 1))
+    idx = np.array([[0, 1, 2], [1, 3, 2], [1, 4, 3], [4, 5, 3]], np.uint32)[:num_tris]
+    mesh = b.add_mesh((P, N, T, P[:, :2].copy(), idx))
+    for k in range(num_instances):
+        b.add_drawable(mesh, m, scenes.translate(0.0, 1.3 * k, -0.4 * k))
+    return b.finish(dir_lights=scenes.dir_light((0.2, 0.3, 1.0)), sky_faces=scenes.procedural_sky(8, (0.2, 0.3, 1.0)),
+                    camera=dict(position=(0.8, 0.9, 4), front_dir=(0, 0, -1), up_dir=(0, 1, 0), yfov=40, near_z=0.01, far_z=100),
+                    bounds=(np.array([-1.0, -1.0, -2.0]), np.array([3.0, 4.0, 1.0])))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("tris,insts", [(1, 1), (2, 1), (1, 2), (3, 1), (4, 3)])
+def test_tiny_scenes_and_edge_inputs(lib, oracle, mode, tris, insts):
+    """The degenerate ends of every structure: a BVH that is a single leaf (no node, no wide node), two leaves (one node), a TLAS of one
+    or two instances — through the single-block build, the wide collapse and both traversal kernels — and a 1 x 1 image."""
+    scene = _tiny_scene(tris, insts)
+    gpu, ref = make_pair(lib, oracle, scene, 24, 16, mode)
+    nb = len(scene.blas) if mode == capi.ACCEL_TWO_LEVEL else 1
+    for b in range(nb):
+        assert_bvh_equal(gpu.read_bvh(b), ref.read_bvh(b))
+    if mode == capi.ACCEL_TWO_LEVEL:
+        assert_bvh_equal(gpu.read_bvh(capi.BVH_TLAS), ref.read_bvh(capi.BVH_TLAS))
+    rays = random_rays(scene, 2000, 5)
+    rays["origin"][:500] = (0.4, 0.3, 2.0); rays["direction"][:500] = (0, 0, -1)
+    rays["origin"][:500, :2] += np.random.default_rng(1).uniform(-0.5, 2.0, (500, 2)).astype(np.float32)
+    a, b_ = gpu.trace_rays(rays, 3), ref.trace_rays(rays, 3)
+    for f in ("t", "u", "v", "instance", "primitive"):
+        np.testing.assert_array_equal(a[f], b_[f], err_msg=f)
+    assert (a["t"] >= 0).sum() > 20
+    np.testing.assert_array_equal(gpu.trace_shadow_rays(rays, 3), ref.trace_shadow_rays(rays, 3))
+    cam = engine.camera_matrices(scene.camera, 24, 16)
+    st = capi.Settings(max_bounces=4)
+    gpu.render(cam, 0, 3, st); ref.render(cam, 0, 3, st)
+    np.testing.assert_array_equal(gpu.resolve(3), ref.resolve(3))
+    assert gpu.counters().extend_rays == ref.counters().extend_rays and gpu.counters().shadow_rays == ref.counters().shadow_rays
+    gpu.close(); ref.close()
+    g1 = capi.Context(lib, 1, 1); r1 = oracle.OracleContext(1, 1)                   # a 1 x 1 image
+    g1.upload_scene(scene, mode); r1.upload_scene(scene, mode)
+    c1 = engine.camera_matrices(scene.camera, 1, 1)
+    g1.render(c1, 7, 2, st); r1.render(c1, 7, 2, st)
+    np.testing.assert_array_equal(g1.resolve(2), r1.resolve(2))
+    np.testing.assert_array_equal(g1.post_process(capi.PostSettings(True, 0.1, 0.5), 2), oracle.post_process_image(r1.resolve(2), capi.PostSettings(True, 0.1, 0.5)))
+    g1.close(); r1.close()
+
+
+def test_error_paths_on_the_device(lib):
+    ctx = capi.Context(lib, 8, 8)
+    with pytest.raises(capi.BptError):
+        ctx.build_accel(capi.ACCEL_MERGED)                                          # nothing uploaded
+    with pytest.raises(capi.BptError):
+        ctx.render(capi.Camera(), 0, 1, capi.Settings())                            # render before build
+    with pytest.raises(capi.BptError):
+        ctx.precompute_sky_ibl(capi.SkyIblDesc(specular_size=4, specular_levels=5))  # last mip would have no texel
+    scene = _tiny_scene(2)
+    ctx.upload_scene(scene, capi.ACCEL_TWO_LEVEL)
+    with pytest.raises(capi.BptError):
+        ctx.render(engine.camera_matrices(scene.camera, 8, 8), 0, 1, capi.Settings(nee_mode=7))     # unknown mode switch
+    with pytest.raises(capi.BptError):
+        ctx.post_process(capi.PostSettings(True, float("nan"), 0.5), 1)
+    ctx.render(engine.camera_matrices(scene.camera, 8, 8), 0, 1, capi.Settings(max_bounces=0))      # clamped to [2, 16] (path_tracing.cpp:290)
+    c = ctx.counters()
+    assert c.extend_rays_per_bounce[1] == 64 and c.extend_rays_per_bounce[2] == 0
+    ctx.close()
+
+
 def random_rays(scene, n, seed):
     rng = np.random.default_rng(seed)
     lo, hi = scene.bounds

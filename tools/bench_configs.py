@@ -39,6 +39,12 @@ def run(name, scene, W, H, bounces, spp, mode, ray_length=100.0):
     out = dict(config=name, width=W, height=H, spp=spp, max_bounces=bounces, accel="merged" if mode else "two_level", triangles=scene.num_triangles,
                ms_total=ms, ms_per_spp=ms / spp, mrays_per_s=(c.extend_rays + c.shadow_rays) / ms / 1e3, mpix_spp_per_s=W * H * spp / ms / 1e3,
                extend_rays=c.extend_rays, shadow_rays=c.shadow_rays, accel_build_ms=build_ms)
+    if "--classes" in sys.argv:          # per-class kernel milliseconds per sample (CUDA events inside the library; serialises nothing)
+        ctx.profile_enable(True); ctx.render(cam, 0, min(spp, 8), st); kt = ctx.profile_read(); ctx.profile_enable(False)
+        for f, _ in kt._fields_:
+            v = getattr(kt, f)
+            if isinstance(v, float):
+                out[f] = v / min(spp, 8)
     print(json.dumps(out), flush=True)
     ctx.close()
     return out
