@@ -130,6 +130,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     for (uint32_t l = 0; l < sc.num_point; l++) {                       // :61-70
         float3 L; float dist;
         float3 le = eval_point_light(sc.point_lights[l], P, L, dist);
+        if (le.x == 0.0f && le.y == 0.0f && le.z == 0.0f) continue;     // out of range / outside the cone: 0 * bsdf can only be 0 or NaN, neither emits a ray
         float3 c = (le * bsdf_eval(N, T, B, V, L, surf, surface_model)) * Wl;
         if (max3c(c) > 0.0f) sink.shadow(P, L, dist * 0.999f, c, sc.num_dir + l);
     }
