@@ -49,6 +49,11 @@ for sc in (scene, basic):
         # multi-kernel radix-sort build for the rest)
         ctx.trace_reflection(cam, 1, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.5, True))
         ctx.trace_reflection(cam, 2, depth, g, capi.ReflectionSettings(16.0, 1.0, 0.3, 0.1, False))
+        refl, hitp = ctx.trace_reflection(cam, 1, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.5, True))
+        ctx.upscale_half_res(cam, 1, depth, g["normal_roughness"], refl)
+        ctx.precompute_sky_ibl(capi.SkyIblDesc(4, 8, 4, 8))
+        ctx.trace_reflection(cam, 3, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.5, False, ibl=True))
+        ctx.trace_probes_range(vol, tab, 2, 2, 3, 4)
         ctx.render(cam, 0, 2, capi.Settings(max_bounces=3))
         assert np.isfinite(ctx.post_process(capi.PostSettings(True, 0.3, 0.5), 2)).all()
         ctx.post_process(capi.PostSettings(False), 2)
@@ -61,7 +66,9 @@ for sc in (scene, basic):
 r = engine.Renderer(W, H); r.set_scene(scene, capi.ACCEL_MERGED)
 for _ in range(3):
     n = r.frame(max_bounces=4)
-r.image(n); r.close()
+r.image(n); r.post_process(True, 0.3, 0.5); r.close()
+pc = capi.Context(lib, W, H); pc.upload_scene(scenes.small_test_scene(), capi.ACCEL_MERGED)
+engine.run_renderer(pc, scenes.small_test_scene(), W, H, 2, max_bounces=3, bloom=True, bloom_threshold=0.3); pc.close()
 # a tree above the single-block limit (4096 leaves) through the multi-kernel build, both modes, and an odd-sized post-process
 big = scenes.cornell_box(tess=40)
 for mode in (capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED):
