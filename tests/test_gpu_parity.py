@@ -4,6 +4,8 @@ Bars (BASELINE.json): integer work (Morton codes, sort permutation, BVH topology
 bit-exact; per-sample radiance within 1e-4 relative (the single-light scenes are in fact bit-equal
 because both sides follow one numeric contract — DESIGN.md "Numerics").
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -521,6 +523,34 @@ def test_project_loader_upload(lib, oracle, tmp_path):
         ca, cb = gpu.counters(), ref.counters()
         assert ca.extend_rays == cb.extend_rays and ca.shadow_rays == cb.shadow_rays and a[..., :3].mean() > 0.02
         gpu.close()
+    p.close()
+
+
+def test_native_host_renders_a_project(lib, oracle, tmp_path):
+    """The whole drop-in path in C++ only (host/render_project.cpp): project directory -> loader -> C ABI -> renderer selected by name ->
+    frames -> post-process -> PFM. The image equals the oracle's render + post-process of the same project."""
+    import subprocess
+    import _mini_project
+    _mini_project.write(str(tmp_path))
+    exe = os.path.join(pkg.PACKAGE_DIR, "host", "render_project")
+    assert os.path.exists(exe), "build it first: make -C bisemutum-engine_b200/host (there is no fallback)"
+    out = str(tmp_path / "out.pfm")
+    r = subprocess.run([exe, str(tmp_path), out, "3", "--merged", "--bloom", "0.4", "0.5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "CudaPathTracingRenderer: 3 frames" in r.stdout
+    with open(out, "rb") as f:
+        assert f.readline() == b"PF\n"
+        w, h = (int(v) for v in f.readline().split())
+        assert f.readline().strip() == b"-1.0"
+        img = np.frombuffer(f.read(), "<f4").reshape(h, w, 3)[::-1]
+    p = engine.Project(str(tmp_path))
+    assert (w, h) == (p.info.target_width, p.info.target_height)
+    ref = oracle.OracleContext(w, h); ref.upload_scene(p.scene_data(), capi.ACCEL_MERGED)
+    ref.render(engine.camera_matrices(p.camera(), w, h), 0, 3, capi.Settings(max_bounces=p.info.max_bounces, ray_length=p.info.ray_length))
+    want = oracle.post_process_image(ref.resolve(3), capi.PostSettings(True, 0.4, 0.5))[..., :3]
+    np.testing.assert_allclose(img, want, rtol=2e-3, atol=1e-5)     # two lights (unordered atomics) through the half stores of the bloom chain
+    bad = subprocess.run([exe, str(tmp_path), out, "1", "--renderer", "BasicRenderer"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "not registered" in bad.stderr
     p.close()
 
 
