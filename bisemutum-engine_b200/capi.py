@@ -474,6 +474,22 @@ class Context:
         self._call("trace_probes_range", C.byref(volume), _ptr(table), frame_index, num_bounces, first_probe, num_probes, _ptr(out))
         return out
 
+    def trace_probes_range_into(self, volume: ProbeVolume, sample_table: np.ndarray, frame_index: int, num_bounces: int, first_probe: int, num_probes: int,
+                                device_ptr: int):
+        """trace_probes_range into DEVICE memory (num_probes * rays_per_probe float4 at `device_ptr`): no host round trip."""
+        table = np.ascontiguousarray(sample_table, dtype=f32)
+        self._call("trace_probes_range", C.byref(volume), _ptr(table), frame_index, num_bounces, first_probe, num_probes, _VP(device_ptr))
+
+    def blend_probes_from_device(self, volume: ProbeVolume, sample_table, frame_index, rays_device_ptr: int, irradiance=None, visibility=None,
+                                 irradiance_size=6, visibility_size=14, alpha=0.97):
+        """blend_probes with the per-ray results read from DEVICE memory (e.g. the output of an NCCL all-gather)."""
+        nx, ny, nz = volume.probe_counts
+        bl = ProbeBlend(irradiance_size, visibility_size, alpha, 0 if irradiance is None else 1)
+        irr = np.zeros((nz * (irradiance_size + 2), nx * ny * (irradiance_size + 2), 4), f32) if irradiance is None else np.ascontiguousarray(irradiance, f32).copy()
+        vis = np.zeros((nz * (visibility_size + 2), nx * ny * (visibility_size + 2), 2), f32) if visibility is None else np.ascontiguousarray(visibility, f32).copy()
+        self._call("blend_probes", C.byref(volume), _ptr(np.ascontiguousarray(sample_table, f32)), frame_index, _VP(rays_device_ptr), C.byref(bl), _ptr(irr), _ptr(vis))
+        return irr, vis
+
     def set_ddgi_volume(self, volume: ProbeVolume | None, irradiance=None, visibility=None, irradiance_size=6, visibility_size=14):
         """Binds the atlases of the previous DDGI update (None unbinds): feedback for trace_probes, input of ddgi_lighting."""
         if volume is None:

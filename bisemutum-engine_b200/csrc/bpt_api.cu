@@ -34,7 +34,7 @@ bpt_status dev_reserve(bpt_context* ctx, DevBuf& b, size_t bytes) {
 bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes) {
     bpt_status s = dev_reserve(ctx, b, bytes);
     if (s) return s;
-    if (bytes && src) BPT_CUDA_TRY(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (bytes && src) BPT_CUDA_TRY(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyDefault, ctx->stream));    // (unified addressing: `src` may be a device pointer)
     return BPT_OK;
 }
 

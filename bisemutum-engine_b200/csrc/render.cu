@@ -1027,7 +1027,7 @@ bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol,
         if ((s = run_bounces(ctx, a, st, B, count, false))) { dev_free(table); return s; }
         k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), count);
         ctx->launches++;
-        e = cudaMemcpyAsync(h_out + 4 * base, wf.color.p, (size_t)count * 16, cudaMemcpyDeviceToHost, ctx->stream);
+        e = cudaMemcpyAsync(h_out + 4 * base, wf.color.p, (size_t)count * 16, cudaMemcpyDefault, ctx->stream);      // host or device destination
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { dev_free(table); ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
     }

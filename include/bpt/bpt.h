@@ -530,7 +530,9 @@ BPT_API bpt_status bpt_trace_probes(
 /* The same for the probes [first_probe, first_probe + num_probes) only (linear probe index = (iz * ny + iy) * nx + ix):
  * out_radiance_dist holds num_probes*rays_per_probe float4. Every random choice is keyed by the probe's GLOBAL index
  * (ddgi/trace_gbuffer.hlsl:25-29), so the rays of a range are bit-identical to the same rays of a full bpt_trace_probes — the unit
- * of the multi-GPU sharding of the DDGI update (shard by probe index, all-gather the per-ray results, sharding.py). */
+ * of the multi-GPU sharding of the DDGI update (shard by probe index, all-gather the per-ray results, sharding.py).
+ * out_radiance_dist of bpt_trace_probes[_range] and ray_radiance_dist of bpt_blend_probes may be HOST or DEVICE pointers (unified
+ * addressing): a sharded update keeps the per-ray results on the device between the trace, the NCCL all-gather and the blend. */
 BPT_API bpt_status bpt_trace_probes_range(
     bpt_context* ctx, const bpt_probe_volume* volume, const float* sample_table_r2 /* 8192 float2 */,
     uint32_t frame_index, uint32_t num_bounces, uint32_t first_probe, uint32_t num_probes, float* out_radiance_dist);

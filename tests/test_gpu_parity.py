@@ -375,6 +375,14 @@ def test_probe_range_is_the_sharding_unit(lib, oracle):
     np.testing.assert_array_equal(np.concatenate(parts).view(np.uint32), full.view(np.uint32))
     np.testing.assert_array_equal(parts[2], ref.trace_probes_range(vol, table, 3, 2, *sharding.probe_range(105, 2, 4)))
     assert gpu.trace_probes_range(vol, table, 3, 2, 10, 0).shape == (0, 4)
+    # device-resident results (what a sharded update keeps between trace, all-gather and blend): same bits, same atlases
+    import torch
+    dev = torch.empty((105 * 64, 4), dtype=torch.float32, device="cuda")
+    gpu.trace_probes_range_into(vol, table, 3, 2, 0, 105, dev.data_ptr())
+    np.testing.assert_array_equal(dev.cpu().numpy().view(np.uint32), full.view(np.uint32))
+    irr_d, vis_d = gpu.blend_probes_from_device(vol, table, 3, dev.data_ptr())
+    irr_h, vis_h = gpu.blend_probes(vol, table, 3, full)
+    np.testing.assert_array_equal(irr_d, irr_h); np.testing.assert_array_equal(vis_d, vis_h)
     with pytest.raises(capi.BptError):
         gpu.trace_probes_range(vol, table, 3, 2, 100, 6)
 

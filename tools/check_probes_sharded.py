@@ -27,24 +27,28 @@ counts, rays_per_probe = (32, 32, 16), 256                        # BASELINE con
 vol = scenes.probe_volume(scene, counts, rays_per_probe); tab = scenes.ddgi_sample_randoms()
 n = counts[0] * counts[1] * counts[2]
 first, count = sharding.probe_range(n, rank, world)
-warm = torch.from_numpy(ctx.trace_probes_range(vol, tab, 100, 2, first, count)).cuda()   # warm-up: kernels, pinned staging, NCCL communicator
-sharding.allgather_probe_rays(warm, n, rays_per_probe)
+# the per-ray results stay on the device: trace into a torch tensor, NCCL all-gather device to device, blend from the gathered tensor
+mine = torch.empty((count * rays_per_probe, 4), dtype=torch.float32, device="cuda")
+ctx.trace_probes_range_into(vol, tab, 100, 2, first, count, mine.data_ptr())        # warm-up: kernels, NCCL communicator
+sharding.allgather_probe_rays(mine, n, rays_per_probe)
 dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
-mine = torch.from_numpy(ctx.trace_probes_range(vol, tab, 0, 2, first, count)).cuda()
+ctx.trace_probes_range_into(vol, tab, 0, 2, first, count, mine.data_ptr())
 rays = sharding.allgather_probe_rays(mine, n, rays_per_probe)
 torch.cuda.synchronize(); dist.barrier()
 dt = time.perf_counter() - t0
-irr, vis = ctx.blend_probes(vol, tab, 0, rays.cpu().numpy())
+irr, vis = ctx.blend_probes_from_device(vol, tab, 0, rays.contiguous().data_ptr())
 ok = True
 if rank == 0:
+    one = torch.empty((n * rays_per_probe, 4), dtype=torch.float32, device="cuda")
     t1 = time.perf_counter()
-    full = ctx.trace_probes(vol, tab, 0, 2)
+    ctx.trace_probes_range_into(vol, tab, 0, 2, 0, n, one.data_ptr()); torch.cuda.synchronize()
     dt1 = time.perf_counter() - t1
+    full = one.cpu().numpy()
     firr, fvis = ctx.blend_probes(vol, tab, 0, full)
     same = np.array_equal(rays.cpu().numpy().view(np.uint32), full.view(np.uint32)) and np.array_equal(irr, firr) and np.array_equal(vis, fvis)
     print(f"DDGI update over {world} GPUs: rays + atlases bit-identical to one GPU: {same}; trace + gather {dt * 1e3:.1f} ms vs one GPU trace {dt1 * 1e3:.1f} ms "
-          f"({n * rays_per_probe} rays x 2 bounces, incl. host read-back)")
+          f"({n * rays_per_probe} rays x 2 bounces, results device-resident)")
     ok = same
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, src=0)
