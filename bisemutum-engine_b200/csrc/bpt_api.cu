@@ -583,7 +583,7 @@ bpt_status bpt_accum_device_ptr(bpt_context* c, float** out) { NEED(c); if (!out
 bpt_status bpt_upload_accum(bpt_context* c, const float* sums) {
     NEED(c);
     if (!sums) return BPT_ERR_INVALID;
-    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->wf.accum.p, sums, (size_t)c->width * c->height * 16, cudaMemcpyHostToDevice, c->stream));
+    BPT_CUDA_TRY(c, cudaMemcpyAsync(c->wf.accum.p, sums, (size_t)c->width * c->height * 16, cudaMemcpyDefault, c->stream));
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return BPT_OK;
 }

@@ -890,8 +890,8 @@ bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uin
         ctx->launches += 4;
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess && h_depth) e = cudaMemcpyAsync(h_depth, d_depth.p, (size_t)npx * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && h_gbuffer) e = cudaMemcpyAsync(h_gbuffer, d_g.p, (size_t)npx * sizeof(bpt_gbuffer_texel), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && h_depth) e = cudaMemcpyAsync(h_depth, d_depth.p, (size_t)npx * 4, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess && h_gbuffer) e = cudaMemcpyAsync(h_gbuffer, d_g.p, (size_t)npx * sizeof(bpt_gbuffer_texel), cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("render_primary: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -928,7 +928,7 @@ bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t 
         ctx->launches += 4;
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out.p, (size_t)n * 8, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("trace_ao: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -967,8 +967,8 @@ bpt_status wavefront_trace_reflection(bpt_context* ctx, const bpt_camera& cam, u
     k_tally<<<1, 64, 0, ctx->stream>>>(wf.qcount.as<uint32_t>(), wf.totals.as<uint64_t>(), 0u);
     ctx->launches += 2;
     e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_refl, d_refl.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hit, d_hit.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_refl, d_refl.p, (size_t)n * 16, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hit, d_hit.p, (size_t)n * 16, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("trace_reflection: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -986,7 +986,7 @@ bpt_status launch_upscale_half_res(bpt_context* ctx, const bpt_camera& cam, uint
                                                                                      d_in.as<float4>(), d_out.as<float4>());
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out.p, (size_t)W * H * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, d_out.p, (size_t)W * H * 16, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("upscale_half_res: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -1068,7 +1068,7 @@ bpt_status launch_trace_batch(bpt_context* ctx, const bpt_ray* h_rays, uint64_t 
         use_wide2(ctx) ? 1u : 0u);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hits ? (void*)h_hits : (void*)h_visible, out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hits ? (void*)h_hits : (void*)h_visible, out.p, out_bytes, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     dev_free(rays); dev_free(out);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -1085,7 +1085,7 @@ bpt_status launch_ddgi_lighting(bpt_context* ctx, uint64_t n, const float* h_pos
     k_ddgi_lighting<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->scene_view(), n, pos.as<float>(), nrm.as<float>(), view.as<float>(), out.as<float4>());
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, out.p, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, out.p, n * 16, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("ddgi_lighting: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }
@@ -1113,8 +1113,8 @@ bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, co
                                                                                     bl.alpha, bl.history_valid, vis.as<float>());
     ctx->launches += 2;
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_irr, irr.p, irr_bytes, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_vis, vis.p, vis_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_irr, irr.p, irr_bytes, cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_vis, vis.p, vis_bytes, cudaMemcpyDefault, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cleanup();
     if (e != cudaSuccess) { ctx->err = std::string("blend_probes: ") + cudaGetErrorString(e); return BPT_ERR_CUDA; }

@@ -51,6 +51,10 @@ typedef enum bpt_status {
 /* ---------------------------------------------------------------------------------------
  * Context
  * ------------------------------------------------------------------------------------- */
+/* Bulk data pointers (images, ray batches, per-ray results, atlases, G-buffers: every `const float*` / `float*` / texel-array
+ * parameter of the pass-level entry points below) may be HOST or DEVICE pointers: copies use unified addressing. A host that
+ * already holds its depth / G-buffer / results on the GPU (external memory, another CUDA library, an NCCL collective) therefore
+ * pays no PCIe round trip; scene-description uploads (geometry, materials, lights, instances) are host arrays. */
 typedef struct bpt_config {
     int32_t device;      /* CUDA ordinal */
     uint32_t width;      /* camera target extent; reference: path_tracing.cpp:228-229 */

@@ -259,3 +259,34 @@ def test_gpu_upscale_half_res_bit_exact(oracle):
             np.testing.assert_array_equal(gpu.upscale_half_res(cam, frame, depth, nr, half).view(np.uint32),
                                           ctx.upscale_half_res(cam, frame, depth, nr, half).view(np.uint32))
     gpu.close(); ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_bulk_pointers_may_be_device_pointers(oracle):
+    """include/bpt/bpt.h: images, G-buffers and results of the pass-level entry points may live on the device (no PCIe round trip):
+    reflection, upscale and RTAO with torch device tensors as inputs and outputs == the host-pointer calls, bit for bit."""
+    import ctypes as C
+    import torch
+    ctx, cam, depth, g = _inputs(oracle, _glossy_scene(), capi.ACCEL_MERGED)
+    ctx.close()
+    gpu = capi.Context(pkg.load_library(), W, H); gpu.upload_scene(_glossy_scene(), capi.ACCEL_MERGED)
+    rs = capi.ReflectionSettings(16.0, 1.0, 1.0, 0.6, True)
+    refl, hit = gpu.trace_reflection(cam, 2, depth, g, rs)
+    full = gpu.upscale_half_res(cam, 2, depth, g["normal_roughness"], refl)
+    ao = gpu.trace_ao(cam, 2, depth, g["normal_roughness"], 0.5, 0.5, True)
+    d_depth = torch.from_numpy(np.ascontiguousarray(depth)).cuda()
+    d_g = torch.from_numpy(np.ascontiguousarray(g).view(np.float32).reshape(H, W, 16).copy()).cuda()
+    d_nr = torch.from_numpy(np.ascontiguousarray(g["normal_roughness"])).cuda()
+    d_refl = torch.empty((H // 2, W // 2, 4), device="cuda"); d_hit = torch.empty_like(d_refl)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    gpu._call("trace_reflection", C.byref(cam), 2, C.byref(rs), vp(d_depth), vp(d_g), vp(d_refl), vp(d_hit))
+    np.testing.assert_array_equal(d_hit.cpu().numpy().view(np.uint32), hit.view(np.uint32))
+    assert np.abs(d_refl.cpu().numpy() - refl).max() <= 1e-4 * max(float(refl[..., :3].max()), 1e-6)
+    d_full = torch.empty((H, W, 4), device="cuda")
+    gpu._call("upscale_half_res", C.byref(cam), 2, vp(d_depth), vp(d_nr), vp(torch.from_numpy(refl).cuda()), vp(d_full))
+    np.testing.assert_array_equal(d_full.cpu().numpy().view(np.uint32), full.view(np.uint32))
+    d_ao = torch.empty((H // 2, W // 2, 2), device="cuda")
+    aos = capi.AoSettings(0.5, 0.5, 1)
+    gpu._call("trace_ao", C.byref(cam), 2, C.byref(aos), vp(d_depth), vp(d_nr), vp(d_ao))
+    np.testing.assert_array_equal(d_ao.cpu().numpy().view(np.uint32), ao.view(np.uint32))
+    gpu.close()
