@@ -318,8 +318,7 @@ bpt_status bpt_build_accel(bpt_context* c, uint32_t mode) {
     }
     if ((s = dev_reserve(c, c->d_blas_bounds, want_blas * 6 * sizeof(float)))) return s;
     if (mode == BPT_ACCEL_TWO_LEVEL) {
-        for (uint32_t b = 0; b < c->blas.size(); b++)
-            if ((s = build_blas_two_level(c, b))) return s;
+        if ((s = build_all_blas_two_level(c))) return s;
         if ((s = build_tlas(c))) return s;
     } else {
         if ((s = build_blas_merged(c))) return s;

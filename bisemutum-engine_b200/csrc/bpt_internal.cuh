@@ -84,6 +84,7 @@ struct bpt_context {
     // build scratch: grow-only chunks, bump-allocated with stack discipline (bvh_build.cu: Scratch), so a per-frame rebuild
     // (the reference rebuilds its TLAS every frame, accel.cpp:134-159) makes no cudaMalloc / cudaFree calls
     std::vector<DevBuf> arena_chunks; size_t arena_chunk = 0, arena_offset = 0;
+    bool arena_hold = false; size_t arena_held_bytes = 0;       // build_all_blas_two_level: scratch of concurrent builds is released together
 
     WavefrontState wf;
     DevBuf d_post;               // rgba16_sfloat targets of the bloom chain (post.cu)
@@ -118,6 +119,7 @@ bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes
 // Builds an LBVH over `n` primitives whose AABBs are in d_lo/d_hi (float4 each, device).
 bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d_lo, const float4* d_hi, float* d_bounds6);
 bpt_status build_blas_two_level(bpt_context* ctx, uint32_t blas_index);
+bpt_status build_all_blas_two_level(bpt_context* ctx);
 bpt_status build_blas_merged(bpt_context* ctx);
 bpt_status build_tlas(bpt_context* ctx);
 bpt_status upload_instance_table(bpt_context* ctx);

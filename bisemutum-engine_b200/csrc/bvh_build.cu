@@ -265,7 +265,7 @@ __global__ void k_refit(uint32_t n, const uint32_t* __restrict__ prims, const fl
 // composite (code, primitive index) — whose order is unique, i.e. the stable LSD sort's — in shared memory, then the Karras
 // and refit steps above separated by block barriers. One launch instead of 33: the reference rebuilds its TLAS every frame
 // (accel.cpp:134-159), and a 512-instance TLAS was 0.2 ms of launch latency.
-constexpr uint32_t kSmallMax = 4096;
+constexpr uint32_t kSmallMax = 8192;      // 96 KB of shared memory at the upper end
 constexpr int kSmallThreads = 1024;
 __global__ void __launch_bounds__(kSmallThreads) k_lbvh_small(const float4* __restrict__ lo, const float4* __restrict__ hi, uint32_t n, uint32_t np2,
                                                               float* __restrict__ bounds6, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ prims_out,
@@ -395,7 +395,7 @@ struct Scratch {
     bpt_context* ctx;
     size_t chunk0, offset0;
     explicit Scratch(bpt_context* c) : ctx(c), chunk0(c->arena_chunk), offset0(c->arena_offset) {}
-    ~Scratch() { ctx->arena_chunk = chunk0; ctx->arena_offset = offset0; }
+    ~Scratch() { if (!ctx->arena_hold) { ctx->arena_chunk = chunk0; ctx->arena_offset = offset0; } }
     bpt_status get(bpt_context*, DevBuf& out, size_t bytes) {
         bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
         auto& ch = ctx->arena_chunks;
@@ -406,6 +406,7 @@ struct Scratch {
         }
         out.p = (char*)ch[ctx->arena_chunk].p + ctx->arena_offset; out.bytes = bytes;
         ctx->arena_offset += bytes;
+        if (ctx->arena_hold) ctx->arena_held_bytes += bytes;
         return BPT_OK;
     }
 };
@@ -529,6 +530,51 @@ bpt_status build_blas_two_level(bpt_context* ctx, uint32_t bi) {
     if ((s = lbvh_build(ctx, ctx->blas[bi], n, lo.as<float4>(), hi.as<float4>(), ctx->d_blas_bounds.as<float>() + 6 * (size_t)bi))) return s;
     if ((s = emit_tris(ctx, ctx->blas[bi], raw.as<float4>()))) return s;
     return collapse_wide(ctx, ctx->blas[bi]);
+}
+
+// Every BLAS of the scene. The builds are independent, and a small one is a handful of launches that occupy one SM (k_lbvh_small), so they
+// are issued round-robin on a few streams and overlap; their scratch is held until all of them are done (the arena's stack discipline
+// assumes one stream) and released in one step, with a flush whenever more than 1 GB is held. The TLAS build that follows on the
+// context's stream waits for all of them through events.
+bpt_status build_all_blas_two_level(bpt_context* ctx) {
+    const uint32_t nb = (uint32_t)ctx->blas.size();
+    if (nb <= 2) {
+        for (uint32_t b = 0; b < nb; b++) if (bpt_status s = build_blas_two_level(ctx, b)) return s;
+        return BPT_OK;
+    }
+    constexpr int kStreams = 8;
+    cudaStream_t main_stream = ctx->stream, st[kStreams];
+    cudaEvent_t ready, done[kStreams];
+    BPT_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    BPT_CUDA_TRY(ctx, cudaEventRecord(ready, main_stream));                      // the instance table / earlier uploads on the context's stream
+    for (int k = 0; k < kStreams; k++) {
+        BPT_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+        BPT_CUDA_TRY(ctx, cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        BPT_CUDA_TRY(ctx, cudaStreamWaitEvent(st[k], ready, 0));
+    }
+    const size_t chunk0 = ctx->arena_chunk, offset0 = ctx->arena_offset;
+    ctx->arena_hold = true; ctx->arena_held_bytes = 0;
+    bpt_status s = BPT_OK;
+    auto flush = [&]() {                                                        // wait for every stream, then the held scratch is free again
+        for (int k = 0; k < kStreams; k++) cudaStreamSynchronize(st[k]);
+        ctx->arena_chunk = chunk0; ctx->arena_offset = offset0; ctx->arena_held_bytes = 0;
+    };
+    for (uint32_t b = 0; b < nb && s == BPT_OK; b++) {
+        if (ctx->arena_held_bytes > ((size_t)1 << 30)) flush();
+        ctx->stream = st[b % kStreams];
+        s = build_blas_two_level(ctx, b);
+    }
+    ctx->stream = main_stream;
+    ctx->arena_hold = false;
+    for (int k = 0; k < kStreams; k++) {                                        // what follows on the context's stream (TLAS build) is ordered after all builds
+        cudaEventRecord(done[k], st[k]);
+        cudaStreamWaitEvent(main_stream, done[k], 0);
+    }
+    if (s != BPT_OK) flush();                                                   // error path: nothing may still be using the scratch
+    ctx->arena_chunk = chunk0; ctx->arena_offset = offset0;                     // (success: re-use is ordered by the events above)
+    for (int k = 0; k < kStreams; k++) { cudaStreamDestroy(st[k]); cudaEventDestroy(done[k]); }
+    cudaEventDestroy(ready);
+    return s;
 }
 
 bpt_status build_blas_merged(bpt_context* ctx) {
