@@ -2,7 +2,7 @@
 probe range (bpt_trace_probes_range), one NCCL all-gather assembles the per-ray results (sharding.allgather_probe_rays), every rank
 blends; the atlases and rays must equal a single-GPU update bit for bit (all keys are global probe indices).
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/check_probes_sharded.py
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tests/check_probes_sharded_multigpu.py
 """
 import os
 import sys

@@ -2,7 +2,7 @@
 every rank renders its block of samples, bpt_reduce sums the FP32 buffers to rank 0 over NCCL, and rank 0's image must
 equal a single-GPU render of all samples to ~1e-6 (FP32 sum order differs) — and the oracle's image within 1e-4.
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/check_reduce.py
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/check_reduce_multigpu.py
 """
 import os
 import sys

@@ -564,7 +564,7 @@ def test_native_host_renders_a_project(lib, oracle, tmp_path):
 
 def test_library_reduce_single_rank(lib, oracle):
     """bpt_comm_unique_id / bpt_comm_init / bpt_reduce with a one-rank communicator: NCCL loads, the reduce is the identity, the
-    fp16 running average refuses it. (The N >= 2 check is tools/check_reduce.py under torchrun; the CPU suite covers the sharding
+    fp16 running average refuses it. (The N >= 2 check is tests/check_reduce_multigpu.py under torchrun; the CPU suite covers the sharding
     arithmetic with gloo.)"""
     scene = scenes.small_test_scene()
     W, H = 64, 48
