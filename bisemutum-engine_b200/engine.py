@@ -121,9 +121,10 @@ class Project:
                "indices": (4, np.uint32), "blas": (5, capi.BLAS_DESC), "drawables": (6, capi.DRAWABLE_SBT), "instances": (7, capi.INSTANCE_DESC),
                "materials": (8, capi.MATERIAL), "dir_lights": (9, capi.DIR_LIGHT), "point_lights": (10, capi.POINT_LIGHT), "rect_lights": (11, capi.RECT_LIGHT)}
 
-    def __init__(self, directory: str):
+    def __init__(self, directory: str, _loader: str = "bpt_host_project_load"):
         h = host_library()
         h.bpt_host_project_load.argtypes, h.bpt_host_project_load.restype = [C.c_char_p, C.c_char_p, C.c_uint64], C.c_void_p
+        h.bpt_host_project_import_gltf.argtypes, h.bpt_host_project_import_gltf.restype = [C.c_char_p, C.c_char_p, C.c_uint64], C.c_void_p
         h.bpt_host_project_free.argtypes = [C.c_void_p]
         h.bpt_host_project_get_info.argtypes = [C.c_void_p, C.POINTER(ProjectInfo)]
         h.bpt_host_project_array.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -131,11 +132,18 @@ class Project:
         h.bpt_host_project_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         h.bpt_host_project_error.argtypes, h.bpt_host_project_error.restype = [C.c_void_p], C.c_char_p
         err = C.create_string_buffer(512)
-        self._h = h.bpt_host_project_load(directory.encode(), err, 512)
+        self._h = getattr(h, _loader)(directory.encode(), err, 512)
         if not self._h:
             raise RuntimeError(f"project {directory}: {err.value.decode()}")
         self.info = ProjectInfo()
         h.bpt_host_project_get_info(self._h, C.byref(self.info))
+
+    @classmethod
+    def from_gltf(cls, path: str) -> "Project":
+        """A .gltf / .glb file through the C++ importer (host/gltf.cpp = the reference's `menu_action_import_model_gltf`,
+        import_model.cpp:27-430): meshes, MikkTSpace tangents, metallic-roughness materials, textures and the node hierarchy.
+        Camera and lights are not part of the import (the reference ignores glTF cameras / lights too)."""
+        return cls(path, _loader="bpt_host_project_import_gltf")
 
     def array(self, name: str) -> np.ndarray:
         which, dt = self._ARRAYS[name]
@@ -161,9 +169,12 @@ class Project:
         texs = []
         for k in range(self.info.num_textures):
             texels, fmt = self.texture(k)
+            smp = (C.c_uint32 * 4)()
+            host_library().bpt_host_project_texture_sampler(C.c_void_p(self._h), k, smp)
             texs.append({"texels": np.ascontiguousarray(texels), "width": texels.shape[1], "height": texels.shape[0],
                          "format": {43: capi.TEXTURE_RGBA8_SRGB, 109: capi.TEXTURE_RGBA32_FLOAT}.get(fmt, capi.TEXTURE_RGBA8_UNORM),
-                         "address_u": capi.ADDRESS_REPEAT, "address_v": capi.ADDRESS_REPEAT, "linear": 1})
+                         "address_u": capi.ADDRESS_REPEAT if smp[2] == 0 else capi.ADDRESS_CLAMP,
+                         "address_v": capi.ADDRESS_REPEAT if smp[3] == 0 else capi.ADDRESS_CLAMP, "linear": 1 if smp[0] == 1 else 0})   # as upload_project maps them
         nd = self.info.num_drawables
         va = np.full(nd, capi.VA_POSITION | capi.VA_NORMAL | capi.VA_TANGENT | capi.VA_TEXCOORD, np.uint32)
         return scenes.SceneData(name="project", positions=self.array("positions"), normals=self.array("normals"), tangents=self.array("tangents"),

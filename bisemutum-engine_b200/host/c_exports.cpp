@@ -2,6 +2,7 @@
 #include <cstring>
 #include "engine.hpp"
 #include "project.hpp"
+#include "gltf.hpp"
 
 using namespace bi;
 
@@ -128,6 +129,21 @@ HOST_API bpt_host_project* bpt_host_project_load(const char* dir, char* err, uin
     return h;
 }
 HOST_API void bpt_host_project_free(bpt_host_project* h) { delete h; }
+// glTF 2.0 import (host/gltf.hpp = menu_action_import_model_gltf, import_model.cpp:27-430): the model only; camera / lights come from the caller.
+HOST_API bpt_host_project* bpt_host_project_import_gltf(const char* path, char* err, uint64_t err_len) {
+    auto* h = new bpt_host_project();
+    if (!project::import_gltf(path, h->p, h->err)) {
+        if (err && err_len) { std::strncpy(err, h->err.c_str(), err_len - 1); err[err_len - 1] = 0; }
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+// StaticMesh::calculate_tspace for one submesh (static_mesh.cpp:93-152); arrays are indexed from vertex 0, tangents: 4 floats per vertex (out).
+HOST_API void bpt_host_mikk_tangents(const float* positions, const float* normals, const float* texcoords, float* tangents,
+                                     const uint32_t* indices, uint64_t num_indices, uint32_t base_vertex) {
+    project::mikk_tangents(positions, normals, texcoords, tangents, indices, (size_t)num_indices, base_vertex);
+}
 HOST_API void bpt_host_project_get_info(const bpt_host_project* h, bpt_host_project_info* o) {
     const project::Project& p = h->p;
     *o = bpt_host_project_info{};
@@ -170,6 +186,13 @@ HOST_API const void* bpt_host_project_array(const bpt_host_project* h, uint32_t 
     }
     *bytes = 0;
     return nullptr;
+}
+// sampler of texture k as rhi::SamplerDesc enum values (rhi/sampler.hpp:10-26): out = {mag_filter, min_filter, address_mode_u, address_mode_v}
+HOST_API int bpt_host_project_texture_sampler(const bpt_host_project* h, uint32_t k, uint32_t out[4]) {
+    if (k >= h->p.textures.size()) return -1;
+    auto& t = h->p.textures[k];
+    out[0] = t.mag_filter; out[1] = t.min_filter; out[2] = t.address_u; out[3] = t.address_v;
+    return 0;
 }
 // geometry + materials/textures + instances + lights + sky + acceleration structure into `ctx`. Returns bpt_status.
 HOST_API int bpt_host_project_upload(bpt_host_project* h, bpt_context* ctx, uint32_t accel_mode) {

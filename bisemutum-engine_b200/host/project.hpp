@@ -8,7 +8,7 @@
 //   scene.toml              [[objects]] with [[objects.components]]: Transform, CameraComponent, *LightComponent, StaticMeshComponent,
 //                           MeshRendererComponent, BasicRendererOverrideVolume (settings.path_tracing / ambient_occlusion)
 // Materials are HLSL snippets in the reference; the loader recognises the closed set of snippets the CUDA kernels restate
-// (include/bpt/bpt.h: BPT_MATERIAL_KIND_*) and fails loudly on anything else. glTF / assimp import (import_model.cpp) is not here.
+// (include/bpt/bpt.h: BPT_MATERIAL_KIND_*) and fails loudly on anything else. glTF import (import_model.cpp:27-430) is host/gltf.hpp; assimp import is not built.
 #pragma once
 #include <string>
 #include <utility>

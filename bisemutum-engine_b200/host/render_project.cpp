@@ -4,13 +4,17 @@
 // GraphicsManager::render_frame (graphics_manager.cpp:407-427): per frame prepare_renderer_per_frame_data, per camera
 // prepare_renderer_per_camera_data + render_camera, then RenderGraph::execute. Writes the back buffer as a little-endian PFM.
 //
-//   render_project <project dir> <out.pfm> [frames=16] [width height] [--merged] [--bloom threshold softness] [--renderer name]
+//   render_project <project dir | model.gltf | model.glb> <out.pfm> [frames=16] [width height] [--merged] [--bloom threshold softness] [--renderer name]
+//                  [--camera px py pz fx fy fz [yfov]] [--dir-light dx dy dz r g b strength] [--bounces n]
+// A .gltf / .glb argument goes through the glTF importer (host/gltf.hpp = the editor's "Import Model (glTF)" action); a glTF import carries no
+// camera or light (the reference ignores them too), so they come from the command line.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 #include "project.hpp"
+#include "gltf.hpp"
 
 using namespace bi;
 
@@ -23,11 +27,16 @@ int main(int argc, char** argv) {
     uint32_t frames = 16, width = 0, height = 0, accel = BPT_ACCEL_TWO_LEVEL;
     PostProcessVolume post;
     std::vector<std::string> pos;
+    std::vector<float> cam_arg, light_arg;
+    uint32_t bounces = 0;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--merged") accel = BPT_ACCEL_MERGED;
         else if (a == "--bloom" && i + 2 < argc) { post.bloom = true; post.bloom_threshold = (float)std::atof(argv[++i]); post.bloom_threshold_softness = (float)std::atof(argv[++i]); }
         else if (a == "--renderer" && i + 1 < argc) renderer_name = argv[++i];
+        else if (a == "--camera" && i + 6 < argc) { for (int k = 0; k < 6; k++) cam_arg.push_back((float)std::atof(argv[++i])); if (i + 1 < argc && argv[i + 1][0] != '-') cam_arg.push_back((float)std::atof(argv[++i])); }
+        else if (a == "--dir-light" && i + 7 < argc) { for (int k = 0; k < 7; k++) light_arg.push_back((float)std::atof(argv[++i])); }
+        else if (a == "--bounces" && i + 1 < argc) bounces = (uint32_t)std::atoi(argv[++i]);
         else pos.push_back(a);
     }
     if (pos.size() >= 1) frames = (uint32_t)std::atoi(pos[0].c_str());
@@ -35,7 +44,20 @@ int main(int argc, char** argv) {
 
     project::Project prj;
     std::string err;
-    if (!project::load_project(dir, prj, err)) { std::fprintf(stderr, "load_project: %s\n", err.c_str()); return 1; }
+    auto ends_with = [&](const char* e) { return dir.size() >= std::strlen(e) && dir.compare(dir.size() - std::strlen(e), std::string::npos, e) == 0; };
+    if (ends_with(".gltf") || ends_with(".glb")) {
+        if (!project::import_gltf(dir, prj, err)) { std::fprintf(stderr, "import_gltf: %s\n", err.c_str()); return 1; }
+    } else if (!project::load_project(dir, prj, err)) { std::fprintf(stderr, "load_project: %s\n", err.c_str()); return 1; }
+    if (cam_arg.size() >= 6) {
+        for (int k = 0; k < 3; k++) { prj.cam_position[k] = cam_arg[(size_t)k]; prj.cam_front[k] = cam_arg[(size_t)k + 3]; }
+        if (cam_arg.size() > 6) prj.yfov = cam_arg[6];
+    }
+    if (light_arg.size() == 7) {                                                       // the light's direction is its transform's +Y axis (lights.cpp:52-63)
+        DirectionalLightComponent l; l.color = {light_arg[3], light_arg[4], light_arg[5]}; l.strength = light_arg[6];
+        LightTransform lt; lt.rotation[1] = light_arg[0]; lt.rotation[4] = light_arg[1]; lt.rotation[7] = light_arg[2];
+        prj.lights.add(l, lt);
+    }
+    if (bounces) prj.path_tracing.max_bounces = bounces;
     if (!width || !height) { width = prj.target_width ? prj.target_width : 640; height = prj.target_height ? prj.target_height : 360; }
 
     bpt_config cfg{};
