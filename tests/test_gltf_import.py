@@ -286,3 +286,33 @@ def test_imported_gltf_uploads_and_renders_on_the_gpu(tmp_path, oracle):
         assert ca.extend_rays == cb.extend_rays and ca.shadow_rays == cb.shadow_rays and a[..., :3].mean() > 0.02
         gpu.close(); ref.close()
     p.close()
+
+
+# ---- committed fixture: tests/golden/cornell_box.glb (input) + cornell_box_gltf.npz (import result + oracle image), made by make_gltf_fixture.py
+def _fixture():
+    import importlib.util
+    import os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_gltf_fixture", os.path.join(d, "make_gltf_fixture.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m, np.load(m.NPZ)
+
+
+def test_committed_glb_imports_to_the_committed_arrays(oracle):
+    m, gold = _fixture()
+    arrays, sd = m.imported()
+    for k, v in arrays.items():
+        np.testing.assert_array_equal(v.view(np.uint8) if v.dtype.names else v, gold[k], err_msg=k)
+    np.testing.assert_array_equal(m.render(oracle.OracleContext, sd, capi.ACCEL_TWO_LEVEL), gold["image"])
+    # merged mode bakes the instance transforms into the vertices: same scene, hits differ in the last bits
+    np.testing.assert_allclose(m.render(oracle.OracleContext, sd, capi.ACCEL_MERGED), gold["image"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_committed_glb_renders_to_the_golden_image_on_the_gpu():
+    import bisemutum_engine_b200 as pkg
+    m, gold = _fixture()
+    _, sd = m.imported()
+    lib = pkg.load_library()
+    np.testing.assert_array_equal(m.render(lambda w, h: capi.Context(lib, w, h), sd, capi.ACCEL_TWO_LEVEL), gold["image"])   # one light: no summation-order freedom
+    np.testing.assert_allclose(m.render(lambda w, h: capi.Context(lib, w, h), sd, capi.ACCEL_MERGED), gold["image"], rtol=1e-4, atol=1e-5)
