@@ -358,7 +358,7 @@ def main():
             roofline = {"bound": "hbm", "kernel": "k_trace_spec<false,false> (extend)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
                         "algorithmic_gb_per_launch": per_ray * rays_per_launch / 1e9,
-                        "note": "the 29 MB scene+BVH is L2-resident (traffic << algorithmic bytes), so HBM does not bind this kernel: bounce 1 (binary tree) is issue-bound, later bounces (4-wide quantised tree) are L1/issue-bound; see profiles/r1_v8_kernels.md",
+                        "note": "the 29 MB scene+BVH is L2-resident (traffic << algorithmic bytes), so HBM does not bind this kernel: bounce 1 (binary tree) is issue-bound, later bounces (4-wide quantised tree) are L1/issue-bound; see profiles/r1_final_kernels.md (and r1_v8_kernels.md for the readings)",
                         "peak_source": peak_src, "bytes_per_ray": per_ray, "nodes_per_ray": nodes, "tris_per_ray": tris,
                         "wide_nodes_per_ray": ora["ext_wide_nodes"], "leaf_boxes_per_ray": ora["ext_leaf_boxes"], "wide_ray_share": ora["ext_wide_ray_share"],
                         "rays_per_launch": rays_per_launch, "avg_launch_ms": avg_s * 1e3,

@@ -358,8 +358,11 @@ struct KernelSink {
     }
 };
 
+#ifndef BPT_SHADE_MIN_BLOCKS
+#define BPT_SHADE_MIN_BLOCKS 8      // 64 registers; 6 (80) and 5 (96) measured: see DESIGN section 5
+#endif
 template <bool IBL>
-__global__ void __launch_bounds__(kBlock, 8) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+__global__ void __launch_bounds__(kBlock, BPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < a.qcount[QE + bounce];
     bool cont = false;
