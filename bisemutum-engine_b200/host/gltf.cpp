@@ -178,7 +178,9 @@ auto load_uri(std::string const& uri, std::string const& base_dir, std::string& 
 // ---------------------------------------------------------------------------------------------------------------------------------
 auto be32(const unsigned char* p) -> uint32_t { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
-auto decode_png(std::string const& file, uint32_t& w, uint32_t& h, std::vector<uint8_t>& rgba, std::string& err) -> bool {
+} // namespace
+
+auto decode_png(std::string const& file, uint32_t& w, uint32_t& h, uint32_t& channels, std::vector<uint8_t>& rgba, bool force_rgba, std::string& err) -> bool {
     static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     auto d = reinterpret_cast<const unsigned char*>(file.data());
     if (file.size() < 8 || std::memcmp(d, sig, 8)) { err = "image is not a PNG (only PNG images are decoded by the headless importer)"; return false; }
@@ -223,6 +225,18 @@ auto decode_png(std::string const& file, uint32_t& w, uint32_t& h, std::vector<u
             cur[x] = (uint8_t)(src[x] + pred);
         }
     }
+    if (!force_rgba) {                                                     // stb_image with req_comp = 0: the file's own channel count, palettes expanded
+        channels = ctype == 3 ? (trns.empty() ? 3u : 4u) : ch;
+        if (ctype != 3) { rgba = std::move(img); return true; }
+        rgba.resize((size_t)w * h * channels);
+        for (size_t i = 0; i < (size_t)w * h; i++) {
+            if ((size_t)img[i] * 3 + 2 >= palette.size()) { err = "PNG: palette index out of range"; return false; }
+            for (uint32_t c = 0; c < 3; c++) rgba[channels * i + c] = palette[img[i] * 3 + c];
+            if (channels == 4) rgba[4 * i + 3] = img[i] < trns.size() ? trns[img[i]] : 255;
+        }
+        return true;
+    }
+    channels = 4;
     rgba.resize((size_t)w * h * 4);
     for (size_t i = 0; i < (size_t)w * h; i++) {
         uint8_t* q = &rgba[4 * i]; const uint8_t* s = &img[(size_t)ch * i];
@@ -239,6 +253,8 @@ auto decode_png(std::string const& file, uint32_t& w, uint32_t& h, std::vector<u
     }
     return true;
 }
+
+namespace {
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // FP32 vector helpers in MikkTSpace's operation order
@@ -521,7 +537,7 @@ auto import_gltf(std::string const& path, Project& out, std::string& err) -> boo
                 if (buf < 0 || (size_t)buf >= model.buffers.size() || off + len > model.buffers[(size_t)buf].size()) { err = path + ": image " + std::to_string(src) + ": bad bufferView"; return false; }
                 bytes.assign(model.buffers[(size_t)buf], off, len);
             }
-            if (!decode_png(bytes, t.width, t.height, t.texels, e)) { err = path + ": image " + std::to_string(src) + ": " + e; return false; }
+            if (uint32_t ch = 0; !decode_png(bytes, t.width, t.height, ch, t.texels, true, e)) { err = path + ": image " + std::to_string(src) + ": " + e; return false; }
         } else { t.width = t.height = 1; t.texels = {255, 255, 255, 255}; } // the importer's 1x1 white default image (import_model.cpp:63-69)
         const int smp = gt.int_or("sampler", -1);
         if (smp >= 0 && (size_t)smp < samplers.size()) {                   // import_model.cpp:118-139

@@ -25,6 +25,11 @@ namespace bi::project {
 auto mikk_tangents(const float* positions, const float* normals, const float* texcoords, float* tangents,
                    const uint32_t* indices, size_t num_indices, uint32_t base_vertex) -> void;
 
+// PNG, 8 bits per channel, non-interlaced (the subset stb_image is asked for here). force_rgba = true: tinygltf's default `req_comp = 4`
+// (grey -> (g, g, g, 255), grey+alpha -> (g, g, g, a), RGB -> (r, g, b, 255)); false: stbi_load_from_memory(..., req_comp = 0), the
+// file's own channel count (palettes expanded to 3 or 4), as TextureAsset::load uses it for PNG-per-layer storage (texture.cpp:110-131).
+auto decode_png(std::string const& file, uint32_t& width, uint32_t& height, uint32_t& channels, std::vector<uint8_t>& pixels, bool force_rgba, std::string& err) -> bool;
+
 // Appends the model to `out` (geometry streams, BLAS descs, drawables + instances, materials, textures, object names).
 // Camera, lights and renderer settings are not part of a glTF import in the reference either (the importer ignores glTF cameras / lights).
 auto import_gltf(std::string const& path, Project& out, std::string& err) -> bool;

@@ -1,5 +1,6 @@
 // host/project.cpp — see project.hpp. File:line citations are relative to /root/reference/bisemutum/.
 #include "project.hpp"
+#include "gltf.hpp"
 
 #include <zlib.h>
 
@@ -307,8 +308,20 @@ auto load_texture(std::string const& path, TextureData& t, std::string& err) -> 
     t.format = desc[16]; t.dim = desc[17];
     if (version == 1) {                                                 // texture.cpp:105-132
         uint32_t storage = 0; r.pod(storage);
-        if (storage != 0) { err = path + ": PNG-per-layer storage (texture.cpp:110-131) is not supported"; return false; }
-        r.vec(t.texels);
+        if (storage == 1) {                                             // one PNG per layer, stbi's native channel count, bytes_per_layer copied
+            const uint32_t texel = (t.format >= 9 && t.format <= 15) ? 1u : (t.format >= 16 && t.format <= 22) ? 2u : (t.format >= 37 && t.format <= 57) ? 4u : 0u;   // rhi/defines.hpp:44-100
+            if (!texel) { err = path + ": PNG-per-layer storage with a format that is not 8 bits per channel"; return false; }
+            const size_t layer_bytes = (size_t)t.width * t.height * texel;
+            for (uint32_t layer = 0; layer < t.depth; layer++) {
+                std::vector<uint8_t> png, px; uint32_t w = 0, h = 0, ch = 0; std::string e;
+                r.vec(png);
+                if (!r.ok) { err = path + ": truncated PNG layer"; return false; }
+                if (!decode_png(std::string(png.begin(), png.end()), w, h, ch, px, false, e)) { err = path + ": layer " + std::to_string(layer) + ": " + e; return false; }
+                if (w != t.width || h != t.height || ch != texel) { err = path + ": layer " + std::to_string(layer) + ": the PNG does not match the texture description"; return false; }
+                t.texels.insert(t.texels.end(), px.begin(), px.begin() + (std::ptrdiff_t)layer_bytes);
+            }
+        } else if (storage != 0) { err = path + ": unknown storage type " + std::to_string(storage); return false; }
+        else r.vec(t.texels);
     } else {
         std::vector<uint8_t> raw;
         if (!r.compressed_part(raw)) { err = path + ": bad compressed part"; return false; }

@@ -30,13 +30,22 @@ def write_mesh(path, positions, normals, tangents, texcoords, indices, version=2
         f.write(_header("StaticMesh", version) + (_compressed(body) if version >= 2 else body))
 
 
-def write_texture(path, texels_rgba8, fmt=37):
+def write_texture(path, texels_rgba8, fmt=37, storage="v2"):
+    """storage: "v2" (zlib part), "v1_raw" (storage type 0) or "v1_png" (storage type 1: one PNG per layer, texture.cpp:110-131)."""
     h, w, _ = texels_rgba8.shape
     sampler = bytes([1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0]) + struct.pack("<ffff", 0.0, 0.0, 0.0, 1000.0)      # linear / linear / repeat
     desc = struct.pack("<IIII", w, h, 1, 1) + bytes([fmt, 1, 1, 0])
     raw = struct.pack("<Q", texels_rgba8.size) + np.ascontiguousarray(texels_rgba8, np.uint8).tobytes()
+    if storage == "v1_raw":
+        body, version = struct.pack("<I", 0) + raw, 1
+    elif storage == "v1_png":
+        import _gltf_writer
+        png = _gltf_writer.png_bytes(texels_rgba8)
+        body, version = struct.pack("<I", 1) + struct.pack("<Q", len(png)) + png, 1
+    else:
+        body, version = _compressed(raw), 2
     with open(path, "wb") as f:
-        f.write(_header("Texture", 2) + sampler + desc + _compressed(raw))
+        f.write(_header("Texture", version) + sampler + desc + body)
 
 
 def quad(size=4.0):

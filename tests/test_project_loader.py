@@ -135,6 +135,29 @@ def test_mini_project_round_trip(tmp_path, oracle):
     p.close()
 
 
+@pytest.mark.parametrize("storage", ["v1_raw", "v1_png"])
+def test_texture_storage_variants(tmp_path, storage):
+    """Texture v1 with raw texels and with one PNG per layer (TextureAsset::load, texture.cpp:105-132) load to the same texels as v2."""
+    import _mini_project
+    wrote = _mini_project.write(str(tmp_path))
+    _mini_project.write_texture(str(tmp_path / "textures" / "cage.texture.biasset"), wrote["texture"], storage=storage)
+    p = engine.Project(str(tmp_path))
+    tex, fmt = p.texture(0)
+    assert fmt == 37
+    np.testing.assert_array_equal(tex, wrote["texture"])
+    p.close()
+    if storage == "v1_png":                                                # a PNG whose channel count does not match the format fails loudly
+        import struct
+        import _gltf_writer
+        path = str(tmp_path / "textures" / "cage.texture.biasset")
+        png = _gltf_writer.png_bytes(wrote["texture"][..., :3])
+        head = open(path, "rb").read()
+        cut = head.index(b"\x89PNG") - 8
+        open(path, "wb").write(head[:cut] + struct.pack("<Q", len(png)) + png)
+        with pytest.raises(RuntimeError, match="does not match the texture description"):
+            engine.Project(str(tmp_path))
+
+
 def test_toml_subset_and_error_paths(tmp_path):
     with pytest.raises(RuntimeError):
         engine.Project(str(tmp_path))                                              # no project.toml
