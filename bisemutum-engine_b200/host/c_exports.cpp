@@ -3,17 +3,12 @@
 #include "engine.hpp"
 #include "project.hpp"
 #include "gltf.hpp"
+#include "../../include/bpt/bpt_host.h"     // the declarations: the compiler checks every definition below against them
 
 using namespace bi;
 
 extern "C" {
 #define HOST_API __attribute__((visibility("default")))
-
-struct bpt_host_camera_desc {
-    float position[3]; float front_dir[3]; float up_dir[3];
-    float yfov; float near_z; float far_z;
-    uint32_t width; uint32_t height; uint32_t orthographic;
-};
 
 static gfx::Camera make_camera(const bpt_host_camera_desc* d) {
     gfx::Camera c;
@@ -112,13 +107,6 @@ HOST_API int bpt_host_pass_read_primary(bpt_host_pass* p, float ray_length, uint
 }
 // ---- headless project loading (host/project.hpp): the reference's project directory -> the C ABI's arrays ------------------------
 struct bpt_host_project { project::Project p; std::string err; };
-struct bpt_host_project_info {
-    uint32_t num_drawables, num_blas, num_materials, num_textures, num_dir_lights, num_point_lights, num_rect_lights;
-    uint32_t target_width, target_height;
-    bpt_host_camera_desc camera;
-    float ray_length; uint32_t max_bounces; uint32_t accumulate;
-    bpt_ao_settings ambient_occlusion;
-};
 HOST_API bpt_host_project* bpt_host_project_load(const char* dir, char* err, uint64_t err_len) {
     auto* h = new bpt_host_project();
     if (!project::load_project(dir, h->p, h->err)) {

@@ -24,6 +24,20 @@ def test_libbpt_exports_every_declared_symbol():
     assert b"sm_100a" in lib.bpt_version()
 
 
+def test_libbpt_host_exports_every_declared_symbol():
+    """include/bpt/bpt_host.h is the C view of the host mirror; c_exports.cpp includes it, so the compiler has already checked the signatures."""
+    header = open(os.path.join(pkg.REPO_ROOT, "include", "bpt", "bpt_host.h")).read()
+    declared = sorted(set(re.findall(r"BPT_HOST_API\s+[\w\s\*]+?\b(bpt_host_\w+)\s*\(", header)))
+    assert len(declared) >= 25
+    lib = engine.host_library()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    defined = set(re.findall(r"^HOST_API\s+[\w\s\*]+?\b(bpt_host_\w+)\s*\(", open(os.path.join(pkg.PACKAGE_DIR, "host", "c_exports.cpp")).read(), re.M))
+    assert defined == set(declared)                      # nothing exported that the header does not declare
+    assert '#include "../../include/bpt/bpt_host.h"' in open(os.path.join(pkg.PACKAGE_DIR, "host", "c_exports.cpp")).read()
+    assert C.sizeof(engine.ProjectInfo) == 9 * 4 + C.sizeof(engine.HostCameraDesc) + 12 + C.sizeof(capi.AoSettings)
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device bpt_create must fail loudly (BPT_ERR_NO_DEVICE), never fall back."""
     import torch

@@ -316,3 +316,35 @@ def test_committed_glb_renders_to_the_golden_image_on_the_gpu():
     lib = pkg.load_library()
     np.testing.assert_array_equal(m.render(lambda w, h: capi.Context(lib, w, h), sd, capi.ACCEL_TWO_LEVEL), gold["image"])   # one light: no summation-order freedom
     np.testing.assert_allclose(m.render(lambda w, h: capi.Context(lib, w, h), sd, capi.ACCEL_MERGED), gold["image"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_native_host_renders_the_committed_glb(oracle, tmp_path):
+    """render_project model.glb (C++ only: glTF import -> C ABI -> CudaPathTracingRenderer -> PostProcessPass -> PFM) with camera and light
+    from the command line == the oracle's render + output pass of the imported scene."""
+    import os
+    import subprocess
+    import bisemutum_engine_b200 as pkg
+    m, _ = _fixture()
+    _, sd = m.imported()
+    exe = os.path.join(pkg.PACKAGE_DIR, "host", "render_project")
+    assert os.path.exists(exe), "build it first: make -C bisemutum-engine_b200/host (there is no fallback)"
+    out = str(tmp_path / "out.pfm")
+    cam, light = sd.camera, sd.dir_lights[0]
+    emission = np.float32(light["emission"])
+    args = [exe, m.GLB, out, "3", "80", "56", "--bounces", "5", "--camera", *(repr(float(v)) for v in (*cam["position"], *cam["front_dir"])),
+            "--dir-light", *(repr(float(np.float32(v))) for v in light["direction"]), *(repr(float(v)) for v in emission), "1"]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    with open(out, "rb") as f:
+        assert f.readline() == b"PF\n"
+        w, h = (int(v) for v in f.readline().split())
+        f.readline()
+        img = np.frombuffer(f.read(), "<f4").reshape(h, w, 3)[::-1]
+    assert (w, h) == (80, 56)
+    ref = oracle.OracleContext(w, h); ref.upload_scene(sd, capi.ACCEL_TWO_LEVEL)
+    ref.render(oracle.camera_matrices(cam, w, h), 0, 3, capi.Settings(max_bounces=5))
+    want = oracle.post_process_image(ref.resolve(3), capi.PostSettings(False, 1.5, 0.5))[..., :3]
+    np.testing.assert_allclose(img, want, rtol=1e-4, atol=1e-6)
+    assert img.mean() > 0.02
+    ref.close()
