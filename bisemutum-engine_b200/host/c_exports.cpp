@@ -1,5 +1,7 @@
 // host/c_exports.cpp — plain-C view of the host mirror for the Python harness (tests / bench).
 #include <cstring>
+#include <exception>
+#include <string>
 #include "engine.hpp"
 #include "project.hpp"
 #include "gltf.hpp"
@@ -109,7 +111,9 @@ HOST_API int bpt_host_pass_read_primary(bpt_host_pass* p, float ray_length, uint
 struct bpt_host_project { project::Project p; std::string err; };
 HOST_API bpt_host_project* bpt_host_project_load(const char* dir, char* err, uint64_t err_len) {
     auto* h = new bpt_host_project();
-    if (!project::load_project(dir, h->p, h->err)) {
+    bool ok = false;
+    try { ok = project::load_project(dir, h->p, h->err); } catch (std::exception const& e) { h->err = std::string("exception: ") + e.what(); }   // nothing may unwind through the C boundary
+    if (!ok) {
         if (err && err_len) { std::strncpy(err, h->err.c_str(), err_len - 1); err[err_len - 1] = 0; }
         delete h;
         return nullptr;
@@ -120,7 +124,9 @@ HOST_API void bpt_host_project_free(bpt_host_project* h) { delete h; }
 // glTF 2.0 import (host/gltf.hpp = menu_action_import_model_gltf, import_model.cpp:27-430): the model only; camera / lights come from the caller.
 HOST_API bpt_host_project* bpt_host_project_import_gltf(const char* path, char* err, uint64_t err_len) {
     auto* h = new bpt_host_project();
-    if (!project::import_gltf(path, h->p, h->err)) {
+    bool ok = false;
+    try { ok = project::import_gltf(path, h->p, h->err); } catch (std::exception const& e) { h->err = std::string("exception: ") + e.what(); }   // nothing may unwind through the C boundary
+    if (!ok) {
         if (err && err_len) { std::strncpy(err, h->err.c_str(), err_len - 1); err[err_len - 1] = 0; }
         delete h;
         return nullptr;

@@ -32,7 +32,10 @@ struct Json {
         return nullptr;
     }
     auto number_or(std::string_view key, double d) const -> double { auto v = get(key); return v && v->kind == Kind::number ? v->num : d; }
-    auto int_or(std::string_view key, int d) const -> int { auto v = get(key); return v && v->kind == Kind::number ? (int)v->num : d; }
+    auto int_or(std::string_view key, int d) const -> int { auto v = get(key); return v && v->kind == Kind::number && v->num > -2e9 && v->num < 2e9 ? (int)v->num : d; }
+    // byte offsets / counts / indices: a negative, fractional-huge or NaN number becomes a value every bounds check rejects
+    static auto to_size(double x) -> size_t { return x >= 0.0 && x < 9e15 ? (size_t)x : (size_t)-1 / 4; }
+    auto size_or(std::string_view key, size_t d) const -> size_t { auto v = get(key); return v && v->kind == Kind::number ? to_size(v->num) : d; }
     auto string_or(std::string_view key, std::string d) const -> std::string { auto v = get(key); return v && v->kind == Kind::string ? v->str : d; }
     auto bool_or(std::string_view key, bool d) const -> bool { auto v = get(key); return v && v->kind == Kind::boolean ? v->b : d; }
     auto array_of(std::string_view key) const -> std::vector<Json> const& {
@@ -205,6 +208,8 @@ auto decode_png(std::string const& file, uint32_t& w, uint32_t& h, uint32_t& cha
     unsigned ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!ch) { err = "PNG: bad colour type"; return false; }
     const size_t stride = (size_t)w * ch;
+    // a header that promises more than the IDAT stream can inflate to (deflate expands at most ~1032x) is rejected before anything is allocated
+    if (w > 65536 || h > 65536 || (stride + 1) * h > idat.size() * 1032 + 1024) { err = "PNG: image size does not match its data"; return false; }
     std::vector<uint8_t> raw((stride + 1) * h);
     uLongf dst = (uLongf)raw.size();
     if (uncompress(raw.data(), &dst, reinterpret_cast<const Bytef*>(idat.data()), (uLong)idat.size()) != Z_OK || dst != raw.size()) { err = "PNG: bad IDAT stream"; return false; }
@@ -462,13 +467,14 @@ struct Model {
         auto& bv = views[(size_t)view];
         const int buf = bv.int_or("buffer", -1);
         if (buf < 0 || (size_t)buf >= buffers.size()) { err = "bufferView.buffer out of range"; return false; }
-        const size_t off = (size_t)a.number_or("byteOffset", 0) + (size_t)bv.number_or("byteOffset", 0);
-        stride = (size_t)bv.number_or("byteStride", 0);
-        count = (size_t)a.number_or("count", 0);
+        const size_t off = a.size_or("byteOffset", 0) + bv.size_or("byteOffset", 0);
+        stride = bv.size_or("byteStride", 0);
+        count = a.size_or("count", 0);
         component_type = a.int_or("componentType", 0);
         type = a.string_or("type", "");
-        const size_t step = stride ? stride : elem_bytes_hint;
-        if (count && off + (count - 1) * step + elem_bytes_hint > buffers[(size_t)buf].size()) { err = "accessor reads past the end of its buffer"; return false; }
+        const size_t step = stride ? stride : elem_bytes_hint, have = buffers[(size_t)buf].size();
+        if (stride > 4096 || off > have || count > have) { err = "accessor reads past the end of its buffer"; return false; }      // keeps the products below from wrapping
+        if (count && off + (count - 1) * step + elem_bytes_hint > have) { err = "accessor reads past the end of its buffer"; return false; }
         data = reinterpret_cast<const unsigned char*>(buffers[(size_t)buf].data()) + off;
         return true;
     }
@@ -510,7 +516,7 @@ auto import_gltf(std::string const& path, Project& out, std::string& err) -> boo
         auto uri = b.get("uri");
         if (!uri) { if (is_glb && i == 0) model.buffers.back() = glb_bin; else { err = path + ": buffer " + std::to_string(i) + " has no uri"; return false; } }
         else if (std::string e; !load_uri(uri->str, model.base_dir, model.buffers.back(), e)) { err = path + ": buffer " + std::to_string(i) + ": " + e; return false; }
-        if (model.buffers.back().size() < (size_t)b.number_or("byteLength", 0)) { err = path + ": buffer " + std::to_string(i) + " is shorter than its byteLength"; return false; }
+        if (model.buffers.back().size() < b.size_or("byteLength", 0)) { err = path + ": buffer " + std::to_string(i) + " is shorter than its byteLength"; return false; }
         ++i;
     }
 
@@ -533,7 +539,7 @@ auto import_gltf(std::string const& path, Project& out, std::string& err) -> boo
                 if (view < 0 || (size_t)view >= views.size()) { err = path + ": image " + std::to_string(src) + " has neither uri nor bufferView"; return false; }
                 auto& bv = views[(size_t)view];
                 const int buf = bv.int_or("buffer", -1);
-                const size_t off = (size_t)bv.number_or("byteOffset", 0), len = (size_t)bv.number_or("byteLength", 0);
+                const size_t off = bv.size_or("byteOffset", 0), len = bv.size_or("byteLength", 0);
                 if (buf < 0 || (size_t)buf >= model.buffers.size() || off + len > model.buffers[(size_t)buf].size()) { err = path + ": image " + std::to_string(src) + ": bad bufferView"; return false; }
                 bytes.assign(model.buffers[(size_t)buf], off, len);
             }
@@ -672,7 +678,7 @@ auto import_gltf(std::string const& path, Project& out, std::string& err) -> boo
     bool ok = true;
     std::function<void(Xform const&, size_t, int)> process_node = [&](Xform const& parent_world, size_t ni, int depth) {
         if (!ok) return;
-        if (ni >= nodes.size() || depth > 256) { err = path + ": bad node hierarchy"; ok = false; return; }
+        if (ni >= nodes.size() || depth > 256 || num_nodes > (1u << 20)) { err = path + ": bad node hierarchy"; ok = false; return; }   // cycles / DAG blow-up
         const Json& node = nodes[ni];
         const std::string name = unique_name(node.string_or("name", ""), "node", num_nodes, used_names);
         ++num_nodes;
@@ -708,14 +714,14 @@ auto import_gltf(std::string const& path, Project& out, std::string& err) -> boo
                 out.object_names.push_back(name);
             }
         }
-        for (auto& ch : node.array_of("children")) if (ch.kind == Json::Kind::number) process_node(world, (size_t)ch.num, depth + 1);
+        for (auto& ch : node.array_of("children")) if (ch.kind == Json::Kind::number) process_node(world, Json::to_size(ch.num), depth + 1);
     };
     auto& scenes = root.array_of("scenes");
     if (scenes.empty()) { err = path + ": no scenes"; return false; }
     const size_t scene_index = (size_t)std::max(0, root.int_or("scene", -1));   // scenes[max(0, defaultScene)]
     if (scene_index >= scenes.size()) { err = path + ": default scene out of range"; return false; }
     const Xform base_world = from_matrix(mat_mul(matrix_of(Xform{}), matrix_of(Xform{})));
-    for (auto& n : scenes[scene_index].array_of("nodes")) if (n.kind == Json::Kind::number) process_node(base_world, (size_t)n.num, 0);
+    for (auto& n : scenes[scene_index].array_of("nodes")) if (n.kind == Json::Kind::number) process_node(base_world, Json::to_size(n.num), 0);
     if (!ok) return false;
     if (out.drawables.empty()) { err = path + ": no renderable primitive"; return false; }
     return true;

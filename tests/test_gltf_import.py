@@ -348,3 +348,40 @@ def test_native_host_renders_the_committed_glb(oracle, tmp_path):
     np.testing.assert_allclose(img, want, rtol=1e-4, atol=1e-6)
     assert img.mean() > 0.02
     ref.close()
+
+
+def test_mutated_files_never_crash_the_importer(tmp_path):
+    """Robustness: 400 seeded mutations of the committed .glb (byte flips in the JSON chunk, number replacements, truncations) either import or
+    raise — the importer runs in this process, so a wild read would take the test run down."""
+    import re
+    import struct
+    m, _ = _fixture()
+    blob = open(m.GLB, "rb").read()
+    jlen = struct.unpack_from("<I", blob, 12)[0]
+    js, rest = blob[20:20 + jlen], blob[20 + jlen:]
+    rng = np.random.default_rng(11)
+    numbers = [mm.span() for mm in re.finditer(rb"-?\d+(\.\d+)?", js)]
+    outcomes = {"ok": 0, "error": 0}
+    for k in range(400):
+        j = bytearray(js)
+        kind = k % 4
+        if kind == 0:                                                        # flip a few bytes
+            for pos in rng.integers(0, len(j), 3):
+                j[pos] = int(rng.integers(32, 127))
+        elif kind == 1:                                                      # replace one number by a hostile one
+            a, b_ = numbers[int(rng.integers(0, len(numbers)))]
+            j[a:b_] = [b"-1", b"4294967295", b"1e300", b"-1e300", b"0", b"99999999", b"2.5", b"18446744073709551615"][int(rng.integers(0, 8))]
+        elif kind == 2:                                                      # truncate the JSON
+            j = j[:int(rng.integers(1, len(j)))]
+        body = bytes(j) + b" " * (-len(j) % 4)
+        data = blob[:12] + struct.pack("<II", len(body), 0x4E4F534A) + body + rest
+        if kind == 3:                                                        # truncate the whole file (binary chunk included)
+            data = data[:int(rng.integers(12, len(data)))]
+        path = str(tmp_path / "mut.glb")
+        open(path, "wb").write(data)
+        try:
+            engine.Project.from_gltf(path).close()
+            outcomes["ok"] += 1
+        except RuntimeError:
+            outcomes["error"] += 1
+    assert outcomes["error"] > 100 and outcomes["ok"] + outcomes["error"] == 400
