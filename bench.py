@@ -383,4 +383,19 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line, the JSON: anything a library prints there while the bench runs (NCCL announces
+    # "NCCL version ..." on stdout at communicator creation) is sent to stderr; the real stdout comes back for the print()s.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):                                   # noqa: A001 — the module's own prints go to the real stdout
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        try:
+            _print(*a, **k)
+            sys.stdout.flush()
+        finally:
+            os.dup2(2, 1)
     main()

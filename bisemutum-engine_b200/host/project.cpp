@@ -238,20 +238,20 @@ namespace {
 struct ByteReader {                                                      // ReadByteStream, byte_stream.hpp:31-44 / byte_stream.cpp:20-45
     const uint8_t* p = nullptr; size_t n = 0, o = 0; bool ok = true;
     template <class T> auto pod(T& v) -> ByteReader& {
-        if (o + sizeof(T) > n) { ok = false; return *this; }
+        if (!ok || sizeof(T) > n - o) { ok = false; return *this; }
         std::memcpy(&v, p + o, sizeof(T)); o += sizeof(T);
         return *this;
     }
     auto str(std::string& s) -> ByteReader& {
         uint64_t len = 0; pod(len);
-        if (!ok || o + len > n) { ok = false; return *this; }
+        if (!ok || len > n - o) { ok = false; return *this; }                      // (compared without o + len: a hostile length must not wrap)
         s.assign(reinterpret_cast<const char*>(p + o), len); o += len;
         return *this;
     }
     template <class T> auto vec(std::vector<T>& v, size_t elems_per_item = 1) -> ByteReader& {      // u64 count of ITEMS, raw elements
         uint64_t cnt = 0; pod(cnt);
+        if (!ok || cnt > (n - o) / (elems_per_item * sizeof(T))) { ok = false; return *this; }
         size_t bytes = cnt * elems_per_item * sizeof(T);
-        if (!ok || o + bytes > n) { ok = false; return *this; }
         v.resize(cnt * elems_per_item);
         if (bytes) std::memcpy(v.data(), p + o, bytes);
         o += bytes;
@@ -259,7 +259,7 @@ struct ByteReader {                                                      // Read
     }
     auto compressed_part(std::vector<uint8_t>& raw) -> bool {                                        // byte_stream.cpp:28-45,77-97
         uint64_t ulen = 0, clen = 0; pod(ulen).pod(clen);
-        if (!ok || o + clen > n) return ok = false;
+        if (!ok || clen > n - o || ulen > clen * 1032 + 1024) return ok = false;                     // deflate expands at most ~1032x: nothing larger is allocated
         raw.resize(ulen);
         uLongf dst = (uLongf)ulen;
         if (uncompress(raw.data(), &dst, p + o, (uLong)clen) != Z_OK || dst != ulen) return ok = false;
