@@ -480,6 +480,11 @@ auto load_project(std::string const& dir, Project& out, std::string& err) -> boo
         for (auto& sub : sm.submeshes) {                                   // BLAS per (mesh, submesh): graphics_manager.cpp:616-654
             uint32_t avail = (uint32_t)sm.indices.size() - std::min<uint32_t>(sub.index_offset, (uint32_t)sm.indices.size());
             uint32_t num = std::min<uint32_t>(sub.num_indices, avail);     // num_indices = ~0u means "to the end" (mesh.hpp:16-22)
+            // a file is untrusted input: every index must address a vertex of this mesh (the kernels fetch positions / attributes unchecked)
+            if (sub.base_vertex > nv) { err = a->second.path + ": submesh base_vertex beyond the vertex count"; return false; }
+            const size_t first = std::min<size_t>(sub.index_offset, sm.indices.size());
+            for (size_t k = first; k < first + num / 3 * 3; k++)
+                if (sm.indices[k] >= nv - sub.base_vertex) { err = a->second.path + ": index " + std::to_string(sm.indices[k]) + " beyond the vertex count"; return false; }
             bpt_blas_desc bd{};
             bd.position_offset = (vbase + sub.base_vertex) * 3; bd.index_offset = ibase + sub.index_offset; bd.num_triangles = num / 3;
             per_sub.push_back((uint32_t)out.blas.size());

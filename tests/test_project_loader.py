@@ -158,6 +158,16 @@ def test_texture_storage_variants(tmp_path, storage):
             engine.Project(str(tmp_path))
 
 
+def test_mesh_with_out_of_range_indices_is_rejected(tmp_path):
+    import _mini_project
+    _mini_project.write(str(tmp_path))
+    q = _mini_project.quad()
+    bad = q[4].copy(); bad[-1] = len(q[0])                                  # one past the last vertex
+    _mini_project.write_mesh(str(tmp_path / "meshes" / "plane.static_mesh.biasset"), q[0], q[1], q[2], q[3], bad)
+    with pytest.raises(RuntimeError, match="beyond the vertex count"):
+        engine.Project(str(tmp_path))
+
+
 def test_toml_subset_and_error_paths(tmp_path):
     with pytest.raises(RuntimeError):
         engine.Project(str(tmp_path))                                              # no project.toml
