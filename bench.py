@@ -349,14 +349,17 @@ def main():
             avg_s = kt.extend_ms * 1e-3 / kt.extend_launches
             achieved = per_ray * rays_per_launch / avg_s / 1e9
             total_k = kt.raygen_ms + kt.extend_ms + kt.shade_ms + kt.connect_ms + kt.other_ms
-            traffic, traffic_src = None, None
+            traffic, traffic_src, traffic_detail = None, None, None
             tpath = os.path.join(ROOT, "profiles", "r1_extend_traffic.json")
             if os.path.exists(tpath) and (W, H, B, args.accel) == (WIDTH, HEIGHT, BOUNCES, "merged"):
                 with open(tpath) as f:
                     tj = json.load(f)
                 traffic, traffic_src = tj["traffic_bytes_per_launch"] / 1e9, tj["source"]     # GB per launch (dram read + write, ncu --set full)
+                traffic_detail = {k: tj[k] for k in ("avg_launch_ms_under_ncu", "dram_gb_per_s", "capture") if k in tj}
+                if "dram_gb_per_s" in traffic_detail:
+                    traffic_detail["dram_frac_of_peak"] = traffic_detail["dram_gb_per_s"] / peak
             roofline = {"bound": "hbm", "kernel": "k_trace_spec<false,false> (extend)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src,
+                        "traffic": traffic, "traffic_unit": "GB per launch", "traffic_source": traffic_src, "traffic_detail": traffic_detail,
                         "algorithmic_gb_per_launch": per_ray * rays_per_launch / 1e9,
                         "note": "the 29 MB scene+BVH is L2-resident (traffic << algorithmic bytes), so HBM does not bind this kernel: bounce 1 (binary tree) is issue-bound, later bounces (4-wide quantised tree) are L1/issue-bound; see profiles/r1_final_kernels.md (and r1_v8_kernels.md for the readings)",
                         "peak_source": peak_src, "bytes_per_ray": per_ray, "nodes_per_ray": nodes, "tris_per_ray": tris,
