@@ -220,6 +220,7 @@ BPT_ONLY_API = {
     "set_stream": [_VP, _VP],
     "sync": [_VP],
     "resolve_device": [_VP, _U32, _VP],
+    "resolve_device_rgba16f": [_VP, _U32, _VP],
     "accum_device_ptr": [_VP, C.POINTER(_VP)],
     "upload_accum": [_VP, _VP],
     "post_process": [_VP, C.POINTER(PostSettings), _U32, _VP],
@@ -381,6 +382,12 @@ class Context:
 
     def accumulate_ahead(self, count: int = 1):
         self._call("accumulate_ahead", count)
+
+    def pending_ahead(self):
+        """(samples traced ahead and not yet accumulated, frame_index of the next one) — bpt_pending_ahead."""
+        pending, nxt = C.c_uint32(0), C.c_uint32(0)
+        self._call("pending_ahead", C.byref(pending), C.byref(nxt))
+        return pending.value, nxt.value
 
     def resolve(self, total_samples: int) -> np.ndarray:
         out = np.empty((self.height, self.width, 4), dtype=f32)
@@ -546,6 +553,10 @@ class Context:
 
     def resolve_device(self, total_samples: int, device_ptr: int):
         self._call("resolve_device", total_samples, _VP(device_ptr))
+
+    def resolve_device_rgba16f(self, total_samples: int, device_ptr: int):
+        """The resolved image as rgba16_sfloat (the reference's OutputData.color format), 8 bytes per pixel, device memory."""
+        self._call("resolve_device_rgba16f", total_samples, _VP(device_ptr))
 
     def comm_init(self, unique_id: bytes, rank: int, world_size: int):
         """Joins the NCCL communicator identified by `unique_id` (128 bytes from Library.comm_unique_id() on rank 0)."""

@@ -67,6 +67,9 @@ DScene bpt_context::scene_view() const {
 }
 
 static bpt_status fail(bpt_context* c, bpt_status s, const char* msg) { c->err = msg; return s; }
+// Samples traced ahead (bpt_render_ahead) were shaded with the scene as it was: every entry point that changes what a sample would
+// see drops them, so bpt_pending_ahead reports 0 and the pass traces the frame again with the current scene.
+static void invalidate_ahead(bpt_context* c) { c->wf.ahead_slots = c->wf.ahead_cursor = 0; c->scene_generation++; }
 #define NEED(c) do { if (!(c)) return BPT_ERR_INVALID; cudaSetDevice((c)->device); } while (0)
 
 // ---- NCCL, loaded at run time so that libbpt.so has no link-time dependency on it (single-GPU hosts need none) -------------
@@ -155,6 +158,7 @@ bpt_status bpt_resize(bpt_context* c, uint32_t w, uint32_t h) {
     if (!w || !h) return BPT_ERR_INVALID;
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->width = w; c->height = h;
+    invalidate_ahead(c);
     return wavefront_alloc(c);
 }
 
@@ -162,6 +166,7 @@ bpt_status bpt_scene_upload_geometry(bpt_context* c, const bpt_geometry_streams*
                                      uint32_t nd, const bpt_blas_desc* blas, uint32_t nb) {
     NEED(c);
     if (!g || !dr || !blas || !nd || !nb || !g->positions || !g->indices) return fail(c, BPT_ERR_INVALID, "geometry: null stream or empty scene");
+    invalidate_ahead(c);
     bpt_status s;
     if ((s = dev_upload(c, c->d_positions, g->positions, g->num_position_floats * 4))) return s;
     if ((s = dev_upload(c, c->d_normals, g->normals, g->normals ? g->num_normal_floats * 4 : 0))) return s;
@@ -193,13 +198,14 @@ bpt_status bpt_scene_upload_geometry(bpt_context* c, const bpt_geometry_streams*
 bpt_status bpt_scene_upload_instances(bpt_context* c, const bpt_instance_desc* inst, uint32_t n) {
     NEED(c);
     if (!inst || !n) return fail(c, BPT_ERR_INVALID, "instances: empty");
-    c->h_instances.assign(inst, inst + n);
+    c->h_instances.assign(inst, inst + n);       // (takes effect with the next bpt_build_accel / bpt_update_tlas, which drop prefetched samples)
     return BPT_OK;
 }
 
 bpt_status bpt_scene_upload_materials(bpt_context* c, const bpt_material* m, uint32_t n, const bpt_texture_desc* t, uint32_t nt) {
     NEED(c);
     if (!m || !n) return fail(c, BPT_ERR_INVALID, "materials: empty");
+    invalidate_ahead(c);
     c->h_materials.assign(m, m + n);
     bpt_status s;
     if ((s = dev_upload(c, c->d_materials, m, (size_t)n * sizeof(bpt_material)))) return s;
@@ -235,6 +241,16 @@ bpt_status bpt_scene_upload_lights(bpt_context* c, const bpt_dir_light_data* d, 
     NEED(c);
     if ((nd && !d) || (np && !p) || (nr && !r)) return fail(c, BPT_ERR_INVALID, "lights: null array");
     bpt_status s;
+    // prefetched samples stay valid only if the lights are byte-for-byte what they were shaded with (the per-frame refresh of an
+    // unchanged LightsContext); the LTC tables are constants of the reference (a new set arrives with a count change only)
+    auto same = [](std::vector<uint8_t>& keep, const void* src, size_t bytes) {
+        bool eq = keep.size() == bytes && (bytes == 0 || memcmp(keep.data(), src, bytes) == 0);
+        if (!eq) keep.assign(static_cast<const uint8_t*>(src), static_cast<const uint8_t*>(src) + bytes);
+        return eq;
+    };
+    const bool eq_d = same(c->h_dir_bytes, d, (size_t)nd * sizeof(*d)), eq_p = same(c->h_point_bytes, p, (size_t)np * sizeof(*p)),
+               eq_r = same(c->h_rect_bytes, r, (size_t)nr * sizeof(*r));
+    if (!(eq_d && eq_p && eq_r)) invalidate_ahead(c);
     if (nd == c->num_dir && np == c->num_point && nr == c->num_rect && c->d_dir.p && (!nr || c->d_ltc[0].p)) {
         // per-frame refresh (PathTracingPass::update_params): same counts → overwrite in place, stream-ordered
         if (nd) BPT_CUDA_TRY(c, cudaMemcpyAsync(c->d_dir.p, d, (size_t)nd * sizeof(*d), cudaMemcpyHostToDevice, c->stream));
@@ -260,6 +276,7 @@ bpt_status bpt_scene_upload_lights(bpt_context* c, const bpt_dir_light_data* d, 
 bpt_status bpt_scene_upload_sky(bpt_context* c, const float* faces, uint32_t size, const float xf[9], const float col[3]) {
     NEED(c);
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    invalidate_ahead(c);
     c->ibl_valid = false;                                   // derived from the faces: bpt_precompute_sky_ibl again
     if (faces && size) {
         bpt_status s = dev_upload(c, c->d_sky, faces, (size_t)6 * size * size * 16);
@@ -274,6 +291,7 @@ bpt_status bpt_scene_upload_sky(bpt_context* c, const float* faces, uint32_t siz
 
 bpt_status bpt_scene_update_sky_params(bpt_context* c, const float xf[9], const float col[3]) {
     NEED(c);
+    if ((xf && memcmp(c->sky_transform, xf, sizeof(float) * 9) != 0) || (col && memcmp(c->sky_color, col, sizeof(float) * 3) != 0)) invalidate_ahead(c);
     if (xf) memcpy(c->sky_transform, xf, sizeof(float) * 9);
     if (col) memcpy(c->sky_color, col, sizeof(float) * 3);
     return BPT_OK;
@@ -307,6 +325,7 @@ bpt_status bpt_build_accel(bpt_context* c, uint32_t mode) {
     bpt_status s;
     if ((s = validate_scene(c))) return s;
     if (mode != BPT_ACCEL_TWO_LEVEL && mode != BPT_ACCEL_MERGED) return fail(c, BPT_ERR_INVALID, "unknown accel mode");
+    invalidate_ahead(c);
     c->accel_built = false;
     c->accel_mode = mode;
     if ((s = upload_instance_table(c))) return s;
@@ -335,6 +354,7 @@ bpt_status bpt_update_tlas(bpt_context* c) {
     if (!c->accel_built || c->accel_mode != BPT_ACCEL_TWO_LEVEL) return fail(c, BPT_ERR_STATE, "update_tlas needs a built two-level accel");
     bpt_status s;
     if ((s = validate_scene(c))) return s;
+    invalidate_ahead(c);
     if ((s = upload_instance_table(c))) return s;
     return build_tlas(c);
 }
@@ -486,6 +506,7 @@ bpt_status bpt_precompute_sky_ibl(bpt_context* c, const bpt_sky_ibl_desc* d) {
         (d->specular_size >> (d->specular_levels - 1)) == 0 || d->diffuse_size > 4096 || d->specular_size > 4096 || d->brdf_lut_size > 4096)
         return fail(c, BPT_ERR_INVALID, "sky ibl: sizes out of range (2 <= levels <= 12, last mip >= 1 texel)");
     c->ibl_valid = false;
+    invalidate_ahead(c);
     bpt_status s = launch_precompute_sky_ibl(c, *d);
     if (s) return s;
     c->ibl_desc = *d; c->ibl_valid = true;
@@ -516,6 +537,7 @@ bpt_status bpt_trace_reflection(bpt_context* c, const bpt_camera* cam, uint32_t 
 
 bpt_status bpt_set_ddgi_volume(bpt_context* c, const bpt_probe_volume* vol, const bpt_probe_blend* bl, const float* irr, const float* vis) {
     NEED(c);
+    invalidate_ahead(c);
     if (!vol || !bl || !irr || !vis) { c->ddgi_enabled = false; return BPT_OK; }        // unbind
     const uint64_t nx = vol->probe_counts[0], ny = vol->probe_counts[1], nz = vol->probe_counts[2];
     if (!nx || !ny || !nz || bl->irradiance_size < 2 || bl->visibility_size < 2 || bl->irradiance_size > 30 || bl->visibility_size > 30)
@@ -538,6 +560,12 @@ bpt_status bpt_resolve_device(bpt_context* c, uint32_t total, float* d_out) {
     NEED(c);
     if (!total || !d_out) return BPT_ERR_INVALID;
     return launch_resolve(c, total, d_out);
+}
+
+bpt_status bpt_resolve_device_rgba16f(bpt_context* c, uint32_t total, void* d_out) {
+    NEED(c);
+    if (!total || !d_out) return BPT_ERR_INVALID;
+    return launch_resolve_rgba16f(c, total, d_out);
 }
 
 bpt_status bpt_post_process_device(bpt_context* c, const bpt_post_settings* st, uint32_t total, float* d_out) {

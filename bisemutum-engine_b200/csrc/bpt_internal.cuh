@@ -58,6 +58,8 @@ struct bpt_context {
     std::vector<bpt_material> h_materials;
     uint64_t num_position_floats = 0, num_indices = 0;
     uint32_t num_dir = 0, num_point = 0, num_rect = 0;
+    std::vector<uint8_t> h_dir_bytes, h_point_bytes, h_rect_bytes;   // the light arrays as last uploaded (prefetch validity, bpt_scene_upload_lights)
+    uint64_t scene_generation = 0;                                    // bumped by every call that changes what a sample would see
     bool has_normals = false, has_tangents = false, has_texcoords = false;
 
     // device scene
@@ -75,6 +77,7 @@ struct bpt_context {
 
     // accel
     bool accel_built = false;
+    bool lbvh_small_attr_set = false;      // cudaFuncSetAttribute(k_lbvh_small, MaxDynamicSharedMemorySize) done on this context's device
     uint32_t accel_mode = 0;
     std::vector<DevBvh> blas;
     DevBvh tlas;
@@ -140,6 +143,7 @@ bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol,
 bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, const float* h_rays,
                                const bpt_probe_blend& bl, float* h_irr, float* h_vis);
 bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out);
+bpt_status launch_resolve_rgba16f(bpt_context* ctx, uint32_t total_samples, void* d_out);
 // ibl.cu
 bpt_status launch_precompute_sky_ibl(bpt_context* ctx, const bpt_sky_ibl_desc& desc);
 // post.cu

@@ -448,8 +448,8 @@ bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d
     if (n <= kSmallMax) {                        // TLAS / small BLAS: one block does everything
         uint32_t np2 = 2; while (np2 < n) np2 <<= 1;
         const size_t smem = (size_t)np2 * 12;
-        static bool attr_set = false;
-        if (!attr_set) { BPT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_lbvh_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallMax * 12))); attr_set = true; }
+        // the opt-in is per device (one process may hold contexts on several GPUs): remembered in the context, not in a process-wide flag
+        if (!ctx->lbvh_small_attr_set) { BPT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_lbvh_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmallMax * 12))); ctx->lbvh_small_attr_set = true; }
         k_lbvh_small<<<1, kSmallThreads, smem, ctx->stream>>>(d_lo, d_hi, n, np2, d_bounds6, out.morton.as<uint64_t>(), out.prims.as<uint32_t>(), c0.as<int32_t>(),
                                                               c1.as<int32_t>(), np.as<int32_t>(), lp.as<int32_t>(), nlo.as<float4>(), nhi.as<float4>(),
                                                               flags.as<uint32_t>(), out.nodes.as<float4>());

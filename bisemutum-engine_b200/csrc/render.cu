@@ -454,6 +454,17 @@ __global__ void k_resolve(const float4* __restrict__ accum, float4* __restrict__
     out[p] = make_float4(v.x * inv, v.y * inv, v.z * inv, 1.0f);
 }
 
+// OutputData.color in the reference's own texture format (rgba16_sfloat, path_tracing.cpp:248-252): four IEEE halves per pixel,
+// round-to-nearest-even of the FP32 mean (q_half's rounding), alpha 1.
+__global__ void k_resolve_rgba16f(const float4* __restrict__ accum, uint2* __restrict__ out, uint32_t npx, float inv) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    float4 v = accum[p];
+    const uint32_t r = __half_as_ushort(__float2half_rn(v.x * inv)), g = __half_as_ushort(__float2half_rn(v.y * inv)),
+                   b = __half_as_ushort(__float2half_rn(v.z * inv));
+    out[p] = make_uint2(r | (g << 16), b | (0x3c00u << 16));
+}
+
 // ---- arbitrary ray batches (bpt_trace_rays / bpt_trace_shadow_rays) ----------------------------
 __global__ void __launch_bounds__(kBlock) k_trace_batch(const __grid_constant__ DScene sc, const bpt_ray* __restrict__ rays, uint64_t n, uint32_t frame_index,
                                                         bpt_hit* __restrict__ hits, uint8_t* __restrict__ visible, const DInstance* __restrict__ inst,
@@ -679,6 +690,7 @@ bpt_status wavefront_alloc(bpt_context* ctx) {
         wf.capacity = paths;
         wf.slots = slots;
         wf.shadow_capacity = 0;
+        wf.ahead_slots = wf.ahead_cursor = 0;        // the per-sample colours of a prefetched wave went with the old buffer
     }
     if (!wf.qcount.p) {
         if ((s = dev_alloc(ctx, wf.qcount, QN * sizeof(uint32_t)))) return s;
@@ -1054,6 +1066,13 @@ bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out
     uint32_t npx = ctx->width * ctx->height;
     float inv = ctx->wf.accum_fp16 ? 1.0f : 1.0f / (float)total_samples;      // reference_fp16: the buffer already is the running average
     LAUNCH(ctx, k_resolve, (npx + 255) / 256, 256, ctx->wf.accum.as<float4>(), reinterpret_cast<float4*>(d_out), npx, inv);
+    return BPT_OK;
+}
+
+bpt_status launch_resolve_rgba16f(bpt_context* ctx, uint32_t total_samples, void* d_out) {
+    uint32_t npx = ctx->width * ctx->height;
+    float inv = ctx->wf.accum_fp16 ? 1.0f : 1.0f / (float)total_samples;
+    LAUNCH(ctx, k_resolve_rgba16f, (npx + 255) / 256, 256, ctx->wf.accum.as<float4>(), reinterpret_cast<uint2*>(d_out), npx, inv);
     return BPT_OK;
 }
 

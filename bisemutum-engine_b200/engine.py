@@ -45,6 +45,7 @@ def host_library():
         h.bpt_host_pass_set_camera.argtypes = [C.c_void_p, C.POINTER(HostCameraDesc)]
         h.bpt_host_pass_set_frame.argtypes = [C.c_void_p, C.c_uint64]
         h.bpt_host_pass_set_prefetch.argtypes = [C.c_void_p, C.c_uint32]
+        h.bpt_host_pass_reset_history.argtypes = [C.c_void_p]
         h.bpt_host_pass_read_primary.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p]
         h.bpt_host_pass_frame.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         h.bpt_host_pass_frame.restype = C.c_int
@@ -244,6 +245,10 @@ class Renderer:
     def set_prefetch(self, frames: int):
         """Samples traced ahead per wave while the history stays valid (PathTracingPass::set_prefetch_frames)."""
         host_library().bpt_host_pass_set_prefetch(self._pass, frames)
+
+    def reset_history(self):
+        """The next frame() starts a new accumulation: the image is cleared and samples traced ahead are dropped (PathTracingPass::reset_history)."""
+        host_library().bpt_host_pass_reset_history(self._pass)
 
     def set_frame(self, frame: int):
         host_library().bpt_host_pass_set_frame(self._pass, frame)

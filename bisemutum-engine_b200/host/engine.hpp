@@ -190,6 +190,9 @@ private:
 public:
     auto set_frame_count(uint64_t f) -> void { frame_counter_ = f; }
     auto set_prefetch_frames(uint32_t n) -> void { prefetch_frames_ = n ? n : 1; }
+    // Forgets every camera's history (what destroying and re-creating the reference's pass does): the next render() of any camera
+    // starts a new accumulation (frame_count = 1) and clears the image, which also drops samples traced ahead.
+    auto reset_history() -> void { camera_history_infos_.clear(); }
 };
 
 // ---- the step after it ------------------------------------------------------------------------------

@@ -621,9 +621,14 @@ auto import_gltf(std::string const& path, Project& out, std::string& err) -> boo
             const size_t isz = ctype == GLTF_U32 ? 4 : ctype == GLTF_U16 ? 2 : ctype == GLTF_U8 ? 1 : 0;
             if (!isz) { err = where + ": index component type " + std::to_string(ctype) + " is not an unsigned integer"; return false; }
             if (!model.accessor(iacc, data, stride, count, ctype, type, isz, e)) { err = where + ": indices: " + e; return false; }
-            for (size_t k = 0; k < count; k++) {                            // tightly packed (the reference memcpy's count elements)
+            // glTF 2.0 forbids byteStride on index bufferViews; the bounds check above used `stride` as the step, so the reads below use
+            // that same step (a hostile byteStride smaller than the element would otherwise pass the check and over-read the buffer)
+            if (stride != 0 && stride < isz) { err = where + ": indices: bufferView.byteStride smaller than the index size"; return false; }
+            const size_t istep = stride ? stride : isz;
+            for (size_t k = 0; k < count; k++) {
                 uint32_t v = 0;
-                if (isz == 4) std::memcpy(&v, data + 4 * k, 4); else if (isz == 2) { uint16_t h; std::memcpy(&h, data + 2 * k, 2); v = h; } else v = data[k];
+                const unsigned char* q = data + istep * k;
+                if (isz == 4) std::memcpy(&v, q, 4); else if (isz == 2) { uint16_t h; std::memcpy(&h, q, 2); v = h; } else v = q[0];
                 out.indices.push_back(v);
             }
             sub.num_indices = (uint32_t)count; num_indices += count;

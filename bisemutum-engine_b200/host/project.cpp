@@ -1,5 +1,6 @@
 // host/project.cpp — see project.hpp. File:line citations are relative to /root/reference/bisemutum/.
 #include "project.hpp"
+#include <cerrno>
 #include "gltf.hpp"
 
 #include <zlib.h>
@@ -32,6 +33,12 @@ auto Toml::at(std::string_view path) const -> Toml const* {
     return cur;
 }
 auto Toml::number_or(std::string_view path, double dflt) const -> double { auto v = at(path); return v && v->kind == Kind::number ? v->num : dflt; }
+auto Toml::id_or(std::string_view path, uint64_t dflt) const -> uint64_t {
+    auto v = at(path);
+    if (!v || v->kind != Kind::number) return dflt;
+    if (v->is_int) return v->u64;
+    return (v->num >= 0.0 && v->num < 18446744073709551616.0) ? (uint64_t)v->num : dflt;      // (no cast of a negative / out-of-range double: undefined)
+}
 auto Toml::string_or(std::string_view path, std::string dflt) const -> std::string { auto v = at(path); return v && v->kind == Kind::string ? v->str : dflt; }
 auto Toml::bool_or(std::string_view path, bool dflt) const -> bool { auto v = at(path); return v && v->kind == Kind::boolean ? v->b : dflt; }
 
@@ -104,7 +111,11 @@ struct TomlParser {
         i++;
         return true;
     }
+    int depth = 0;                                   // nesting of arrays / inline tables (a hostile file must not overflow the stack)
+    struct DepthGuard { int& d; explicit DepthGuard(int& x) : d(x) { ++d; } ~DepthGuard() { --d; } };
     auto parse_value(Toml& v) -> bool {
+        DepthGuard guard(depth);
+        if (depth > 256) return fail("arrays / inline tables nested deeper than 256");
         skip_ws(false);
         if (i >= s.size()) return fail("expected a value");
         char c = s[i];
@@ -156,6 +167,17 @@ struct TomlParser {
         double d = (tok == "inf" || tok == "+inf") ? INFINITY : (tok == "-inf" ? -INFINITY : std::strtod(tok.c_str(), &end));
         if (end && *end != 0) return fail("bad number '" + tok + "'");
         v.kind = Toml::Kind::number; v.num = d;
+        {   // integer token: keep the exact 64-bit value beside the double
+            size_t k = (tok[0] == '+' || tok[0] == '-') ? 1 : 0;
+            bool digits = k < tok.size();
+            for (size_t q = k; q < tok.size(); q++) digits = digits && std::isdigit((unsigned char)tok[q]);
+            if (digits) {
+                errno = 0;
+                char* e2 = nullptr;
+                if (tok[0] == '-') { long long sv = std::strtoll(tok.c_str(), &e2, 10); v.u64 = (uint64_t)sv; v.is_int = errno == 0 && sv >= 0; }
+                else { v.u64 = std::strtoull(tok.c_str() + (tok[0] == '+' ? 1 : 0), &e2, 10); v.is_int = errno == 0; }
+            }
+        }
         i = j;
         return true;
     }
@@ -330,6 +352,15 @@ auto load_texture(std::string const& path, TextureData& t, std::string& err) -> 
         r.ok = body.ok;
     }
     if (!r.ok) { err = path + ": truncated texel data"; return false; }
+    // untrusted header: level 0 of the payload must hold width x height texels of the declared format before anything reads it
+    // (upload_project hands texels.data() to bpt_scene_upload_materials, which copies / decodes width*height*bytes of it)
+    if (t.width == 0 || t.height == 0 || t.width > 65536 || t.height > 65536) { err = path + ": texture extent " + std::to_string(t.width) + " x " + std::to_string(t.height) + " out of range"; return false; }
+    const size_t texel_bytes = (t.format >= 9 && t.format <= 15) ? 1u : (t.format >= 16 && t.format <= 22) ? 2u : (t.format >= 37 && t.format <= 57) ? 4u
+                             : (t.format == 109 ? 16u : 0u);                                                                    // rhi/defines.hpp:44-100
+    if (texel_bytes && t.texels.size() < (size_t)t.width * t.height * texel_bytes) {
+        err = path + ": texel payload (" + std::to_string(t.texels.size()) + " bytes) is smaller than " + std::to_string(t.width) + " x " + std::to_string(t.height) + " texels of " + std::to_string(texel_bytes) + " bytes";
+        return false;
+    }
     return true;
 }
 
@@ -382,7 +413,7 @@ auto load_project(std::string const& dir, Project& out, std::string& err) -> boo
     struct AssetRef { std::string path, type; };
     std::map<uint64_t, AssetRef> assets;
     if (auto a = meta.find("assets"); a && a->kind == Toml::Kind::array)
-        for (auto& e : a->arr) assets[(uint64_t)e.number_or("id", -1)] = AssetRef{resolve(e.string_or("path", "")), e.string_or("type", "")};
+        for (auto& e : a->arr) assets[e.id_or("id", ~0ull)] = AssetRef{resolve(e.string_or("path", "")), e.string_or("type", "")};
 
     std::map<uint64_t, uint32_t> mesh_first_blas, texture_index, material_index;     // asset id -> index, loaded on first use
     std::vector<std::vector<uint32_t>> mesh_blas;                                    // per loaded mesh: BLAS index per submesh
@@ -416,7 +447,7 @@ auto load_project(std::string const& dir, Project& out, std::string& err) -> boo
         auto ptex = [&](const char* n, int& idx) -> bool {
             auto it = params.find(n);
             if (it == params.end() || !it->second || it->second->kind != Toml::Kind::table) { err = a->second.path + ": texture parameter '" + n + "' missing"; return false; }
-            return need_texture((uint64_t)it->second->number_or("asset_id", -1), idx);
+            return need_texture(it->second->id_or("asset_id", ~0ull), idx);
         };
         bpt_material m{};
         m.base_color[0] = m.base_color[1] = m.base_color[2] = 0.5f; m.base_color[3] = 1.0f;
@@ -556,14 +587,14 @@ auto load_project(std::string const& dir, Project& out, std::string& err) -> boo
         if (!mesh_c || !renderer_c) continue;
         // one drawable per submesh from submesh_start_index on, material k for submesh start + k (static_mesh_render_system.cpp)
         uint32_t mesh = 0;
-        if (!need_mesh((uint64_t)mesh_c->number_or("static_mesh.asset_id", -1), mesh)) return false;
+        if (!need_mesh(mesh_c->id_or("static_mesh.asset_id", ~0ull), mesh)) return false;
         auto mats = renderer_c->find("materials");
         const uint32_t start = (uint32_t)renderer_c->number_or("submesh_start_index", 0);
         for (size_t k = 0; mats && mats->kind == Toml::Kind::array && k < mats->arr.size(); k++) {
             const uint32_t sub = start + (uint32_t)k;
             if (sub >= mesh_blas[mesh].size()) break;
             uint32_t mat = 0;
-            if (!need_material((uint64_t)mats->arr[k].number_or("asset_id", -1), mat)) return false;
+            if (!need_material(mats->arr[k].id_or("asset_id", ~0ull), mat)) return false;
             const uint32_t vb = mesh_vbase[mesh] + mesh_submeshes[mesh][sub].base_vertex, io = mesh_ibase[mesh] + mesh_submeshes[mesh][sub].index_offset;
             const uint32_t index = (uint32_t)out.drawables.size();
             bpt_drawable_sbt_data dr{};                                    // drawable_stb_data.hpp:7-17, written at graphics_manager.cpp:1318-1329

@@ -22,6 +22,7 @@ struct Toml {
     enum class Kind { nil, boolean, number, string, array, table } kind = Kind::nil;
     bool b = false;
     double num = 0.0;
+    bool is_int = false; uint64_t u64 = 0;               // an integer token keeps all 64 bits (asset ids are 2^62 + k: a double cannot hold them)
     std::string str;
     std::vector<Toml> arr;
     std::vector<std::pair<std::string, Toml>> tab;
@@ -29,6 +30,7 @@ struct Toml {
     auto find(std::string_view key) const -> Toml const*;
     auto at(std::string_view dotted_path) const -> Toml const*;       // "a.b.c" through tables
     auto number_or(std::string_view path, double dflt) const -> double;
+    auto id_or(std::string_view path, uint64_t dflt) const -> uint64_t;   // exact for integer tokens; a non-negative whole double otherwise
     auto string_or(std::string_view path, std::string dflt) const -> std::string;
     auto bool_or(std::string_view path, bool dflt) const -> bool;
 };

@@ -333,6 +333,9 @@ BPT_API bpt_status bpt_pending_ahead(bpt_context* ctx, uint32_t* out_pending, ui
 BPT_API bpt_status bpt_resolve(bpt_context* ctx, uint32_t total_samples, float* out_rgba32f);
 /* Same, written to device memory (no synchronisation). */
 BPT_API bpt_status bpt_resolve_device(bpt_context* ctx, uint32_t total_samples, float* out_rgba32f_device);
+/* Same image in the format of the reference's OutputData.color (rgba16_sfloat, bisemutum/src/renderer/pass/path_tracing.cpp:248-252):
+ * W*H x 4 IEEE halves (8 bytes per pixel), round-to-nearest-even of the FP32 mean, alpha = 1; device memory, no synchronisation. */
+BPT_API bpt_status bpt_resolve_device_rgba16f(bpt_context* ctx, uint32_t total_samples, void* out_rgba16f_device);
 /* Raw FP32 sum buffer (device pointer, W*H float4) for the multi-GPU reduce. */
 BPT_API bpt_status bpt_accum_device_ptr(bpt_context* ctx, float** out_device_ptr);
 /* Replaces the sum buffer contents from the host (checkpoint/resume of the history). */

@@ -226,6 +226,37 @@ def test_import_fails_loudly(tmp_path):
         engine.Project.from_gltf(str(tmp_path / "short.gltf"))
 
 
+def test_index_accessor_with_a_hostile_byte_stride(tmp_path):
+    """the bounds check of an accessor steps by bufferView.byteStride, so the index loop must read with that same step.
+    byteStride = 1 on a u32 index view placed LAST in the buffer passes the check with count + 3 bytes; reading it as tightly packed
+    would run 4 * count bytes past it. The importer must refuse (or read inside the checked range) — never over-read."""
+    p_, n_, t_, uv_, i_ = scenes.grid_patch(8, 8, lambda u, v: np.stack([u, v, 0 * u], -1))
+    b = gw.GltfBuilder()
+    mat = b.material()
+    attrs = {"POSITION": b.accessor(np.float32(p_).reshape(-1, 3), "VEC3"), "NORMAL": b.accessor(np.float32(n_).reshape(-1, 3), "VEC3"),
+             "TEXCOORD_0": b.accessor(np.float32(uv_).reshape(-1, 2), "VEC2")}
+    count = len(i_)
+    view = b._view(bytes(count + 3), stride=1)                                # the LAST bytes of the buffer: count + 3 of them
+    b.doc["accessors"].append({"bufferView": view, "componentType": 5125, "count": count, "type": "SCALAR"})
+    b.node(mesh=b.mesh([{"attributes": attrs, "indices": len(b.doc["accessors"]) - 1, "material": mat}]))
+    path = str(tmp_path / "stride.gltf")
+    b.write(path, "gltf+data")
+    with pytest.raises(RuntimeError, match="byteStride smaller than the index size"):
+        engine.Project.from_gltf(path)
+    # a legal (if unusual) stride >= the element size is read with that stride
+    b2 = gw.GltfBuilder()
+    mat = b2.material()
+    attrs = {"POSITION": b2.accessor(np.float32(p_).reshape(-1, 3), "VEC3"), "NORMAL": b2.accessor(np.float32(n_).reshape(-1, 3), "VEC3"),
+             "TEXCOORD_0": b2.accessor(np.float32(uv_).reshape(-1, 2), "VEC2")}
+    idx = b2.accessor(np.uint32(i_).reshape(-1), "SCALAR", interleave_pad=4)  # u32 index, 4 junk bytes, ...
+    b2.node(mesh=b2.mesh([{"attributes": attrs, "indices": idx, "material": mat}]))
+    path2 = str(tmp_path / "stride8.gltf")
+    b2.write(path2, "gltf+data")
+    pr = engine.Project.from_gltf(path2)
+    np.testing.assert_array_equal(pr.array("indices"), np.uint32(i_).reshape(-1))
+    pr.close()
+
+
 def test_imported_cornell_box_renders_through_the_oracle(tmp_path, oracle):
     """The imported model carries everything the renderer needs: with the source scene's camera and light it renders through the oracle, and the
     image agrees with the hand-assembled scene wherever tangents do not matter (primary visibility + direct light of rough dielectrics: the

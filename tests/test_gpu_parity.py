@@ -251,6 +251,51 @@ def test_host_pass_accumulates_like_reference(lib, oracle):
     r.close()
 
 
+def test_scene_change_invalidates_prefetched_samples(lib, oracle):
+    """the pass traces a wave of samples ahead while the camera stands still. A light, sky or instance change between two
+    frames must show in the very next frame, as in the reference (which shades every frame with the current parameters): the samples
+    traced ahead are dropped and re-traced. An unchanged per-frame light upload (PathTracingPass::update_params) keeps them."""
+    import copy
+    scene = scenes.small_test_scene()
+    W, H = 64, 48
+    st = capi.Settings(max_bounces=4)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    r = engine.Renderer(W, H)
+    r.set_scene(scene, capi.ACCEL_MERGED)
+    r.set_prefetch(8)
+    ref = oracle.OracleContext(W, H)
+    ref.upload_scene(scene, capi.ACCEL_MERGED)
+    for f in range(2):
+        r.ctx.upload_lights(scene)                           # same bytes every frame: nothing is dropped
+        r.frame(max_bounces=4)
+    assert r.ctx.pending_ahead()[0] == 6
+    ref.render(cam, 0, 2, st)
+    dimmed = copy.copy(scene)
+    dimmed.dir_lights = scene.dir_lights.copy()
+    dimmed.dir_lights["emission"] *= 0.25
+    r.ctx.upload_lights(dimmed)                              # frame 2 onwards sees the dimmed light
+    assert r.ctx.pending_ahead()[0] == 0
+    ref.upload_lights(dimmed)
+    for f in range(2):
+        r.frame(max_bounces=4)
+    ref.render(cam, 2, 2, st)
+    np.testing.assert_array_equal(r.image(4), ref.resolve(4))
+    r.ctx.update_sky_params(scene.sky_transform, np.float32(scene.sky_color) * 0.5)
+    assert r.ctx.pending_ahead()[0] == 0
+    ref.update_sky_params(scene.sky_transform, np.float32(scene.sky_color) * 0.5)
+    r.frame(max_bounces=4); ref.render(cam, 4, 1, st)
+    np.testing.assert_array_equal(r.image(5), ref.resolve(5))
+    # a light-count change re-sizes the wave buffers: whatever was traced ahead is gone, never summed from a fresh allocation
+    more = copy.copy(dimmed)
+    more.dir_lights = np.concatenate([dimmed.dir_lights, scene.dir_lights])
+    r.ctx.upload_lights(more); ref.upload_lights(more)
+    assert r.ctx.pending_ahead()[0] == 0
+    r.frame(max_bounces=4); ref.render(cam, 5, 1, st)
+    a, b = r.image(6), ref.resolve(6)
+    np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-6)   # two shadow rays per vertex: unordered atomics
+    r.close(); ref.close()
+
+
 def test_renderer_plugin_runs_pt_and_post_process(lib, oracle):
     """The plugin level: an IRenderer registered by name and selected like `renderer = "..."` in project.toml runs
     BasicRenderer's path-tracing pipeline — update_params per frame, PathTracingPass::render + PostProcessPass::render per camera

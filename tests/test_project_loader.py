@@ -179,3 +179,53 @@ def test_toml_subset_and_error_paths(tmp_path):
     (tmp_path / "s.toml").write_text("[[objects]\nname = 'broken'\n")
     with pytest.raises(RuntimeError, match="toml line 1"):
         engine.Project(str(tmp_path))
+
+
+def test_truncated_texture_payload_is_rejected(tmp_path):
+    """width / height / format come from the asset header; a payload that holds fewer texels than they describe (truncated
+    or hostile asset) must fail at load, before upload_project hands the short buffer to bpt_scene_upload_materials."""
+    import _mini_project
+    wrote = _mini_project.write(str(tmp_path))
+    tex = wrote["texture"]
+    for storage in ("v2", "v1_raw"):
+        _mini_project.write_texture(str(tmp_path / "textures" / "cage.texture.biasset"), tex[: tex.shape[0] // 2], storage=storage)   # half the rows ...
+        path = str(tmp_path / "textures" / "cage.texture.biasset")
+        blob = bytearray(open(path, "rb").read())
+        import struct
+        at = blob.index(struct.pack("<IIII", tex.shape[1], tex.shape[0] // 2, 1, 1))
+        blob[at + 4: at + 8] = struct.pack("<I", tex.shape[0])                                                                             # ... under the full height
+        open(path, "wb").write(bytes(blob))
+        with pytest.raises(RuntimeError, match="texel payload"):
+            engine.Project(str(tmp_path))
+    _mini_project.write_texture(str(tmp_path / "textures" / "cage.texture.biasset"), tex[:0], storage="v2")                              # height 0
+    with pytest.raises(RuntimeError, match="extent"):
+        engine.Project(str(tmp_path))
+
+
+def test_toml_keeps_64_bit_asset_ids_and_bounds_nesting(tmp_path):
+    """the engine's built-in assets have ids 2^62 + k (bisemutum/assets/asset_metadata.toml); as doubles they all collide.
+    Two assets whose ids differ only below 2^53's resolution must stay distinct; nesting is bounded so a hostile file cannot overflow the stack."""
+    import _mini_project
+    _mini_project.write(str(tmp_path))
+    meta = (tmp_path / "asset_metadata.toml").read_text()
+    scene = (tmp_path / "scene.toml").read_text()
+    import re
+    ids = sorted({int(x) for x in re.findall(r"^id = (\d+)", meta, flags=re.M)})
+    assert len(ids) >= 4
+    big = {i: (1 << 62) + k for k, i in enumerate(ids)}                       # consecutive integers above 2^62: identical as doubles
+    assert len({float(v) for v in big.values()}) == 1
+
+    def remap(text, key):
+        return re.sub(rf"({key} = )(\d+)", lambda m: m.group(1) + str(big.get(int(m.group(2)), int(m.group(2)))), text)
+    (tmp_path / "asset_metadata.toml").write_text(remap(meta, "id"))
+    (tmp_path / "scene.toml").write_text(remap(scene, "asset_id"))
+    for f in (tmp_path / "materials").glob("*.toml"):
+        f.write_text(remap(f.read_text(), "asset_id"))
+    p = engine.Project(str(tmp_path))
+    assert (p.info.num_drawables, p.info.num_blas, p.info.num_materials, p.info.num_textures) == (3, 2, 3, 1)
+    kinds = [(int(f) >> 8) & 0xff for f in p.array("materials")["flags"]]
+    assert kinds == [capi.MATERIAL_KIND_CHECKERBOARD, capi.MATERIAL_KIND_CONSTANT_COLOR, capi.MATERIAL_KIND_CAGE]   # each drawable found ITS material
+    p.close()
+    (tmp_path / "scene.toml").write_text("x = " + "[" * 5000 + "]" * 5000 + "\n")
+    with pytest.raises(RuntimeError, match="nested deeper"):
+        engine.Project(str(tmp_path))

@@ -4,6 +4,9 @@
   python tools/summarize_ncu.py full gpurun_out/X.ncu-rep [traffic.json]     -> markdown tables of every captured launch
                                                                                 (+ DRAM traffic per extend launch as JSON)
   python tools/summarize_ncu.py source gpurun_out/X.ncu-rep                  -> per-source-line / per-phase instruction shares
+  python tools/summarize_ncu.py counters raw.csv device_only.json out.json   -> per-RAY hardware counters of the extend kernel (warp
+                                                                                instructions, active threads, DRAM bytes): what bench.py's
+                                                                                roofline scales by its own live launch times
 """
 import csv
 import io
@@ -106,6 +109,39 @@ def full(rep, traffic_out=None):
                   open(traffic_out, "w"), indent=1)
 
 
+def counters(rep, device_only_json, out_path):
+    """Sums over the extend launches of ONE wave (ncu capture of `bench.py --device-only --steps S`), divided by the extend rays of that wave
+    (the counters the same command prints): per-ray figures that do not depend on the wave size."""
+    rows, units = raw_rows(rep)
+    dev = json.load(open(device_only_json))
+    sc = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tsc = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6}
+
+    def f(d, k, scale=1.0):
+        return float(d[k].replace(",", "")) * scale
+    ext = [d for d in rows if short(d["Kernel Name"]) == "k_trace_spec (extend)"]
+    per_bounce = [r for r in dev["extend_rays_per_bounce"] if r]
+    waves = dev["steps"] and max(1, len(ext) // max(1, len(per_bounce)))
+    rays = sum(per_bounce)                     # all extend rays the command traced in its timed region ...
+    # ... the capture may hold the warm-up waves too: keep the LAST len(per_bounce) extend launches (the timed wave)
+    ext = ext[-len(per_bounce):]
+    inst = sum(f(d, "smsp__inst_executed.sum") for d in ext)
+    thr = sum(f(d, "smsp__inst_executed.sum") * f(d, "smsp__thread_inst_executed_per_inst_executed.ratio") for d in ext)
+    dram = sum(f(d, "dram__bytes_read.sum", sc.get(units["dram__bytes_read.sum"], 1.0)) + f(d, "dram__bytes_write.sum", sc.get(units["dram__bytes_write.sum"], 1.0)) for d in ext)
+    ms = sum(f(d, "gpu__time_duration.sum", tsc.get(units["gpu__time_duration.sum"], 1.0)) for d in ext)
+    out = {"kernel": "k_trace_spec<ANY=false> (extend: every instantiation the wave launches)", "launches": len(ext), "rays": rays,
+           "warp_inst_per_ray": inst / rays, "active_threads_per_warp": thr / inst, "dram_bytes_per_ray": dram / rays,
+           "warp_inst_sum": inst, "dram_bytes_sum": dram, "ms_sum_under_ncu": ms,
+           "per_launch": [{"bounce": i + 1, "rays": per_bounce[i], "ms": f(d, "gpu__time_duration.sum", tsc.get(units["gpu__time_duration.sum"], 1.0)),
+                           "warp_inst": f(d, "smsp__inst_executed.sum"), "active_threads_per_warp": f(d, "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                           "issue_active_pct": f(d, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                           "dram_bytes": f(d, "dram__bytes_read.sum", sc.get(units["dram__bytes_read.sum"], 1.0)) + f(d, "dram__bytes_write.sum", sc.get(units["dram__bytes_write.sum"], 1.0))}
+                          for i, d in enumerate(ext)],
+           "source": f"ncu --set full --clock-control none of `bench.py --device-only --steps {dev['steps']}` ({rep}): the {len(ext)} extend launches of the timed wave; rays from the same command's counters"}
+    json.dump(out, open(out_path, "w"), indent=1)
+    print(json.dumps({k: v for k, v in out.items() if k != "per_launch"}, indent=1))
+
+
 def source(rep):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     cur = fn = hdr = None
@@ -135,4 +171,4 @@ def source(rep):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "source": source}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "full": full, "source": source, "counters": counters}[sys.argv[1]](*sys.argv[2:])
