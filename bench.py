@@ -392,8 +392,7 @@ def main():
     # on rank 0 only when N > 1: the other ranks' partial sums are not a result; the job's result is the ONE reduce at the end,
     # read back in FP32 on rank 0. Everything the timed frames consume is traced inside the timed region: the history is reset after
     # the warm-up frames (which drops their prefetched samples) and the step count is a whole number of waves.
-    e2e = None
-    if not args.no_e2e:
+    def run_e2e(n_steps):
         r = engine.Renderer(W, H, device=local_rank)
         r.ctx.set_stream(stream.cuda_stream)
         r.set_scene(scene, mode)
@@ -401,8 +400,8 @@ def main():
             sharding.comm_init(r.ctx, torch.device("cuda", local_rank))
             r.ctx.reduce(0); r.ctx.sync()
         wave = max(1, min(32, (1 << 26) // npx))        # what the library traces per wave at this resolution (render.cu: wave_slots)
-        prefetch = min(wave, my_steps)
-        e2e_steps = (my_steps // prefetch) * prefetch   # whole waves, so traced samples == consumed frames
+        prefetch = min(wave, n_steps)
+        e2e_steps = (n_steps // prefetch) * prefetch   # whole waves, so traced samples == consumed frames
         r.set_prefetch(prefetch)
         job_steps = torch.tensor([float(e2e_steps)], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -478,6 +477,16 @@ def main():
                "d2h_note": "rank 0's bytes; the other ranks copy nothing to the host" if world > 1 else "every frame's image"}
         assert e2e["value"] > 0.0
         r.close()
+        return e2e
+
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(my_steps)
+        # the same measurement over 128 frames per rank when the job is shorter: a K-frame job ends with the read-back of its last wave
+        # (samples_per_wave frames x the PCIe time of one image), which a long-running pass amortises
+        if my_steps < 128 and args.scaling == "weak":
+            e2e["steady_state_128_steps"] = {k: v for k, v in run_e2e(128).items() if k in ("value", "ms_per_step", "steps", "samples_per_wave", "mpix_spp_per_s")}
 
     if rank != 0:
         if world > 1:
