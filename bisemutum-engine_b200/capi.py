@@ -90,6 +90,12 @@ class TextureDesc(C.Structure):
                 ("address_mode_u", C.c_uint32), ("address_mode_v", C.c_uint32), ("filter_linear", C.c_uint32)]
 
 
+class LightTextureDesc(C.Structure):
+    """bpt_light_texture_desc: a rect-light texture (RectLightComponent::texture) and how its sampler filters it."""
+    _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("levels", C.c_uint32),
+                ("address_mode_u", C.c_uint32), ("address_mode_v", C.c_uint32), ("filter_linear", C.c_uint32), ("mip_linear", C.c_uint32)]
+
+
 class LtcLuts(C.Structure):
     _fields_ = [("matrix_lut0", C.c_void_p), ("matrix_lut1", C.c_void_p), ("matrix_lut2", C.c_void_p), ("norm_lut", C.c_void_p)]
 
@@ -189,6 +195,8 @@ COMMON_API = {
     "scene_upload_materials": [_VP, _VP, _U32, C.POINTER(TextureDesc), _U32],
     "scene_upload_lights": [_VP, _VP, _U32, _VP, _U32, _VP, _U32, C.POINTER(LtcLuts)],
     "scene_upload_sky": [_VP, _VP, _U32, _VP, _VP],
+    "scene_upload_light_textures": [_VP, C.POINTER(LightTextureDesc), _U32],
+    "debug_read_light_texture": [_VP, _U32, _VP, _U64, _PU64],
     "scene_update_sky_params": [_VP, _VP, _VP],
     "build_accel": [_VP, _U32],
     "update_tlas": [_VP],
@@ -322,6 +330,7 @@ class Context:
         self._call("scene_upload_materials", _ptr(scene.materials), len(scene.materials), texs, len(scene.textures))
         self.upload_instances(scene.instances)
         self.upload_lights(scene)
+        self.upload_light_textures(getattr(scene, "light_textures", []))
         self.upload_sky(scene)
         self._call("build_accel", accel_mode)
 
@@ -334,6 +343,26 @@ class Context:
             luts.matrix_lut0, luts.matrix_lut1, luts.matrix_lut2, luts.norm_lut = (_ptr(a) for a in scene.ltc_luts)
         self._call("scene_upload_lights", _ptr(scene.dir_lights), len(scene.dir_lights), _ptr(scene.point_lights),
                    len(scene.point_lights), _ptr(scene.rect_lights), len(scene.rect_lights), C.byref(luts))
+
+    def upload_light_textures(self, textures):
+        """`textures`: list of dicts {texels (H, W, 4) uint8 or float32, format, levels, address_u, address_v, linear, mip_linear};
+        entry k is what bpt_rect_light_data.texture_index == k samples."""
+        descs = (LightTextureDesc * max(1, len(textures)))()
+        keep = []
+        for i, t in enumerate(textures):
+            tex = np.ascontiguousarray(t["texels"]); keep.append(tex)
+            descs[i] = LightTextureDesc(texels=_ptr(tex), width=tex.shape[1], height=tex.shape[0], format=t["format"], levels=t.get("levels", 1),
+                                        address_mode_u=t.get("address_u", ADDRESS_CLAMP), address_mode_v=t.get("address_v", ADDRESS_CLAMP),
+                                        filter_linear=t.get("linear", 1), mip_linear=t.get("mip_linear", 0))
+        self._call("scene_upload_light_textures", descs, len(textures))
+
+    def read_light_texture(self, index: int):
+        """The generated mip chain of light texture `index`: list of (h, w, 4) float32 arrays, level 0 first."""
+        n = C.c_uint64(0)
+        self._call("debug_read_light_texture", index, None, 0, C.byref(n))
+        flat = np.zeros((n.value, 4), f32)
+        self._call("debug_read_light_texture", index, _ptr(flat), n.value, C.byref(n))
+        return flat
 
     def upload_sky(self, scene):
         xf = np.ascontiguousarray(scene.sky_transform, dtype=f32)

@@ -57,6 +57,7 @@ DScene bpt_context::scene_view() const {
     s.dir_lights = d_dir.as<bpt_dir_light_data>(); s.num_dir = num_dir;
     s.point_lights = d_point.as<bpt_point_light_data>(); s.num_point = num_point;
     s.rect_lights = d_rect.as<bpt_rect_light_data>(); s.num_rect = num_rect;
+    s.light_textures = d_light_textures.as<DLightTexture>(); s.num_light_textures = (uint32_t)h_light_textures.size();
     s.ltc_m0 = d_ltc[0].as<float>(); s.ltc_m1 = d_ltc[1].as<float>(); s.ltc_m2 = d_ltc[2].as<float>(); s.ltc_norm = d_ltc[3].as<float>();
     s.sky_faces = d_sky.as<float4>(); s.sky_size = sky_size;
     memcpy(s.sky_transform, sky_transform, sizeof(sky_transform));
@@ -131,12 +132,13 @@ bpt_status bpt_destroy(bpt_context* c) {
     if (c->nccl_comm && c->nccl_owned) nccl().CommDestroy(c->nccl_comm);
     DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
-                      &c->d_ltc[2], &c->d_ltc[3], &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->d_post, &c->d_post_out, &c->d_ibl_diffuse, &c->d_ibl_specular, &c->d_ibl_brdf, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
+                      &c->d_ltc[2], &c->d_ltc[3], &c->d_light_textures, &c->d_srgb_tables, &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->d_post, &c->d_post_out, &c->d_ibl_diffuse, &c->d_ibl_specular, &c->d_ibl_brdf, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
                       &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims,
                       &c->tlas.wide, &c->tlas.leafbox};
     for (DevBuf* b : bufs) dev_free(*b);
     for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
     for (auto& t : c->d_texels) dev_free(t);
+    for (auto& t : c->d_light_texels) dev_free(t);
     for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
     for (auto& a : c->arena_chunks) dev_free(a);
     delete c;
@@ -271,6 +273,18 @@ bpt_status bpt_scene_upload_lights(bpt_context* c, const bpt_dir_light_data* d, 
     c->num_dir = nd; c->num_point = np; c->num_rect = nr;
     BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return wavefront_alloc(c);
+}
+
+bpt_status bpt_scene_upload_light_textures(bpt_context* c, const bpt_light_texture_desc* t, uint32_t nt) {
+    NEED(c);
+    if ((nt && !t) || nt > BPT_MAX_RECT_LIGHT_TEXTURES) return fail(c, BPT_ERR_INVALID, "light textures: null array or more than 16");
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    invalidate_ahead(c);
+    return upload_light_textures(c, t, nt);
+}
+bpt_status bpt_debug_read_light_texture(bpt_context* c, uint32_t index, float* out, uint64_t cap, uint64_t* out_texels) {
+    NEED(c);
+    return read_light_texture(c, index, out, cap, out_texels);
 }
 
 bpt_status bpt_scene_upload_sky(bpt_context* c, const float* faces, uint32_t size, const float xf[9], const float col[3]) {

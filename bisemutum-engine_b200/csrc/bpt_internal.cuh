@@ -1,5 +1,7 @@
 // bpt_internal.cuh — host-side context of libbpt.so (not part of the ABI).
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cuda_runtime.h>
 #include <string>
 #include <vector>
@@ -67,6 +69,8 @@ struct bpt_context {
     DevBuf d_textures; std::vector<DevBuf> d_texels;
     DevBuf d_instances;          // DInstance[]
     DevBuf d_dir, d_point, d_rect, d_ltc[4];
+    std::vector<DevBuf> d_light_texels; DevBuf d_light_textures, d_srgb_tables;     // rect-light textures (lighttex.cu)
+    std::vector<bptd::DLightTexture> h_light_textures;
     DevBuf d_sky; uint32_t sky_size = 0;
     DevBuf d_ibl_diffuse, d_ibl_specular, d_ibl_brdf;      // bpt_precompute_sky_ibl (ibl.cu)
     bool ibl_valid = false; bpt_sky_ibl_desc ibl_desc{};
@@ -144,6 +148,9 @@ bpt_status launch_blend_probes(bpt_context* ctx, const bpt_probe_volume& vol, co
                                const bpt_probe_blend& bl, float* h_irr, float* h_vis);
 bpt_status launch_resolve(bpt_context* ctx, uint32_t total_samples, float* d_out);
 bpt_status launch_resolve_rgba16f(bpt_context* ctx, uint32_t total_samples, void* d_out);
+// lighttex.cu
+bpt_status upload_light_textures(bpt_context* ctx, const bpt_light_texture_desc* textures, uint32_t num_textures);
+bpt_status read_light_texture(bpt_context* ctx, uint32_t index, float* out, uint64_t capacity_texels, uint64_t* out_texels);
 // ibl.cu
 bpt_status launch_precompute_sky_ibl(bpt_context* ctx, const bpt_sky_ibl_desc& desc);
 // post.cu

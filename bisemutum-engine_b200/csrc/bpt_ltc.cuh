@@ -3,7 +3,7 @@
 // winding, horizon clipping, edge integrals) and the caller in
 // shaders/renderer/raytracing/deferred_lighting_secondary.hlsl:72-96. The 8x8x64 LUTs are read
 // with explicit FP32 trilinear interpolation from plain global memory (no texture unit: its 8-bit
-// filter weights would exceed the 1e-4 parity budget). Light textures are not supported.
+// filter weights would exceed the 1e-4 parity budget). Light textures (lights.hlsl:425-447,495-511): bpt_scene.cuh: light_texture_sample.
 #pragma once
 #include "bpt_scene.cuh"
 
@@ -86,7 +86,7 @@ BPT_HD void rewind(float3* L) { float3 t0 = L[0], t1 = L[1]; L[0] = L[3]; L[1] =
 // two LUT fetches + lerps, quadrant flips, the matrix inverse (lights.hlsl:203-273 + :494). It is computed once per path vertex and
 // shared by all rect lights (16 on BASELINE configs[2]); per light only the corner winding (`rewind`) and the two integrals remain.
 // Same operations in the same order as the per-light form, so the result is unchanged bit for bit.
-struct LtcSetup { Mat3 Minv; float2 brdf; bool wind, flip_roughness; };
+struct LtcSetup { Mat3 Minv; Mat3 M; float2 brdf; bool wind, flip_roughness; };
 BPT_HD LtcSetup ltc_setup(const DScene& sc, float3 lv, float rx, float ry) {
     LtcSetup ls;
     float theta_wi = acos_(lv.z);
@@ -112,6 +112,7 @@ BPT_HD LtcSetup ltc_setup(const DScene& sc, float3 lv, float rx, float ry) {
         M = mul_mm(sw, M);
     }
     ls.Minv = mat3_inverse(M);
+    ls.M = M;
     ls.wind = do_wind; ls.flip_roughness = flip_roughness;
     return ls;
 }
@@ -153,7 +154,8 @@ BPT_HD float4 ltc_edge(float3 v1, float3 v2) {                                  
     float3 c = cross3(v1, v2);
     return make_float4(c.x * k, c.y * k, c.z * k, c.z * k);
 }
-BPT_HD float ltc_integrate(float3 P, float3 N, float3 T, float3 B, const Mat3& Minv, const float3* L, bool two_sided, float3* mrp = nullptr) {   // lights.hlsl:383-423
+// `M` = the lobe's matrix for the most representative point (nullptr: identity, the diffuse lobe)
+BPT_HD float ltc_integrate(float3 P, float3 N, float3 T, float3 B, const Mat3& Minv, const float3* L, bool two_sided, float3* mrp = nullptr, const Mat3* M = nullptr) {   // lights.hlsl:383-423
     Mat3 TBN; TBN.r0 = T; TBN.r1 = B; TBN.r2 = N;
     float3 LP[5];
 #pragma unroll
@@ -171,9 +173,31 @@ BPT_HD float ltc_integrate(float3 P, float3 N, float3 T, float3 B, const Mat3& M
     if (n == 5) { e = ltc_edge(LP[4], LP[0]); sum.x += e.x; sum.y += e.y; sum.z += e.z; sum.w += e.w; }
     float integral = two_sided ? fabsf(sum.w) : tmax_(0.0f, sum.w);
     if (!is_finite1(integral)) integral = 0.0f;
-    // most representative point direction, lights.hlsl:420 with the identity matrix: mul(sum.xyz, TBN) = x*T + y*B + z*N
-    if (mrp) *mrp = normalize3((sum.x * T + sum.y * B) + sum.z * N);
+    // most representative point direction, lights.hlsl:420: mul(mul(ltc_matrix, sum.xyz), TBN) = x*T + y*B + z*N of the lobe-space vector
+    if (mrp) {
+        float3 sv = v3(sum.x, sum.y, sum.z);
+        if (M) sv = mul_mv(*M, sv);
+        *mrp = normalize3((sv.x * T + sv.y * B) + sv.z * N);
+    }
     return integral;
+}
+
+// rect_light_sample_texture (lights.hlsl:425-447): where the direction `dir` from P meets the light's plane, in the rectangle's (u, v),
+// at the level whose texels are as large as the footprint (distance x roughness x texels per metre).
+BPT_HD float3 rect_light_texture(const DLightTexture& tex, const bpt_rect_light_data& light, float3 dir, float3 P, float roughness) {
+    const float3 ln = v3(light.normal[0], light.normal[1], light.normal[2]);
+    const float3 p1 = v3(light.position1[0], light.position1[1], light.position1[2]), p2 = v3(light.position2[0], light.position2[1], light.position2[2]),
+                 p3 = v3(light.position3[0], light.position3[1], light.position3[2]);
+    float step = fabsf(dot3(dir, ln));
+    if (step < 0.0001f) return v3s(0.0f);
+    float dist = fabsf(dot3(P - p2, ln));
+    float t = dist / step;
+    float3 rect_pos = (P + dir * t) - p2;
+    float u = sat(dot3(rect_pos, p3 - p2) * light.inv_width_sqr);
+    float v = sat(dot3(rect_pos, p1 - p2) * light.inv_height_sqr);
+    float num_texels = (t * roughness) * light.inv_texel_size;
+    float level = log2_(tmax_(1.0f, num_texels));
+    return light_texture_sample(tex, u, v, level);
 }
 
 // rect_light_eval_ltc (lights.hlsl:449-513) + surface_eval_lut. `setup` = ltc_setup of this vertex when lv.z > 0 (else unused).
@@ -186,11 +210,23 @@ BPT_HD float3 eval_rect_light(const DScene& sc, const bpt_rect_light_data& light
                        v3(light.position1[0], light.position1[1], light.position1[2]), v3(light.position0[0], light.position0[1], light.position0[2])};
         float3 emission = v3(light.emission[0], light.emission[1], light.emission[2]);
         Mat3 I; I.r0 = v3(1, 0, 0); I.r1 = v3(0, 1, 0); I.r2 = v3(0, 0, 1);
-        diff = emission * ltc_integrate(P, N, T, B, I, L, light.two_sided != 0, diff_mrp);
+        const bool textured = light.texture_index >= 0 && (uint32_t)light.texture_index < sc.num_light_textures;
+        float3 dmrp = v3s(0.0f), smrp = v3s(0.0f);
+        const float i_diff = ltc_integrate(P, N, T, B, I, L, light.two_sided != 0, (diff_mrp || textured) ? &dmrp : nullptr);
+        if (diff_mrp) *diff_mrp = dmrp;
+        diff = emission * i_diff;
         if (setup.wind) rewind(L);                                  // lights.hlsl:203-273: the quadrant's winding, then the roughness swap's
         if (setup.flip_roughness) rewind(L);
         brdf = setup.brdf;
-        spec = emission * ltc_integrate(P, N, T, B, setup.Minv, L, light.two_sided != 0);
+        const float i_spec = ltc_integrate(P, N, T, B, setup.Minv, L, light.two_sided != 0, textured ? &smrp : nullptr, &setup.M);
+        spec = emission * i_spec;
+        if (textured) {                                             // lights.hlsl:495-511 (a zero integral leaves `mrp` unwritten there: the product stays 0 here)
+            const DLightTexture& tex = sc.light_textures[light.texture_index];
+            float rx, ry;
+            aniso_roughness(s.roughness, s.anisotropy, rx, ry);
+            diff = i_diff != 0.0f ? diff * rect_light_texture(tex, light, dmrp, P, 1.0f) : v3s(0.0f);
+            spec = i_spec != 0.0f ? spec * rect_light_texture(tex, light, smrp, P, sqrtf(rx * ry)) : v3s(0.0f);
+        }
     }
     return bsdf_eval_lut(N, V, s, diff, spec, brdf, surface_model);
 }

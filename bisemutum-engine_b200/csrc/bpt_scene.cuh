@@ -31,6 +31,12 @@ struct DTexture {
     uint32_t w, h, format, addr_u, addr_v, linear;
 };
 
+// A rect-light texture: the whole mip chain as FP32 texels, level after level (level l is max(w >> l, 1) x max(h >> l, 1)).
+struct DLightTexture {
+    const float4* texels;
+    uint32_t w, h, levels, addr_u, addr_v, linear, mip_linear;
+};
+
 struct DInstance {           // 128 B
     float o2w[12];
     float w2o[12];
@@ -57,6 +63,7 @@ struct DScene {
     const bpt_point_light_data* point_lights; uint32_t num_point;
     const bpt_rect_light_data* rect_lights; uint32_t num_rect;
     const float* ltc_m0; const float* ltc_m1; const float* ltc_m2; const float* ltc_norm;
+    const DLightTexture* light_textures; uint32_t num_light_textures;
     // sky
     const float4* sky_faces; uint32_t sky_size;
     float sky_transform[9]; float sky_color[3];
@@ -136,26 +143,106 @@ BPT_HD float4 sample_or(const DScene& sc, int32_t tex, float2 uv, float4 dflt) {
 
 // ---- sky (deferred_lighting_secondary.hlsl:24-29; Vulkan cube face rule = inverse of
 //      core/utils/cubemap.hlsl:3-21; bilinear inside the face, clamp to edge) --------------------
-BPT_HD float3 sample_cube(const float4* faces, uint32_t size, float3 d) {
-    if (size == 0) return v3s(0.0f);
+// ---- rect-light textures: Texture2D.SampleLevel(sampler, uv, level) on the generated chain (lights.hlsl:446) ----
+BPT_HD float4 light_texel(const float4* base, int w, int x, int y) { return BPT_LDG(base + (size_t)y * w + x); }
+BPT_HD float4 light_level_sample(const DLightTexture& t, uint32_t level, float u, float v) {
+    size_t off = 0;
+    for (uint32_t l = 0; l < level; l++) off += (size_t)((t.w >> l) ? (t.w >> l) : 1u) * ((t.h >> l) ? (t.h >> l) : 1u);
+    const int w = (int)((t.w >> level) ? (t.w >> level) : 1u), h = (int)((t.h >> level) ? (t.h >> level) : 1u);
+    const float4* base = t.texels + off;
+    if (!t.linear) return light_texel(base, w, wrap_tc((int)floorf(u * (float)w), w, t.addr_u), wrap_tc((int)floorf(v * (float)h), h, t.addr_v));
+    float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = wrap_tc((int)x0f, w, t.addr_u), x1 = wrap_tc((int)x0f + 1, w, t.addr_u);
+    int y0 = wrap_tc((int)y0f, h, t.addr_v), y1 = wrap_tc((int)y0f + 1, h, t.addr_v);
+    float4 top = mix4(light_texel(base, w, x0, y0), light_texel(base, w, x1, y0), fx);
+    float4 bot = mix4(light_texel(base, w, x0, y1), light_texel(base, w, x1, y1), fx);
+    return mix4(top, bot, fy);
+}
+BPT_HD float3 light_texture_sample(const DLightTexture& t, float u, float v, float level) {
+    const float top = (float)(t.levels - 1u);
+    level = level < 0.0f ? 0.0f : (level > top ? top : level);
+    if (!t.mip_linear) {
+        int l = (int)ceilf(level + 0.5f) - 1;
+        l = l < 0 ? 0 : (l > (int)t.levels - 1 ? (int)t.levels - 1 : l);
+        float4 c = light_level_sample(t, (uint32_t)l, u, v);
+        return v3(c.x, c.y, c.z);
+    }
+    const float lf = floorf(level);
+    const uint32_t l0 = (uint32_t)lf, l1 = l0 + 1u < t.levels ? l0 + 1u : l0;
+    float4 a = light_level_sample(t, l0, u, v);
+    if (l1 == l0) return v3(a.x, a.y, a.z);
+    float4 b = light_level_sample(t, l1, u, v);
+    return mix3(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), level - lf);
+}
+
+// Major-axis face selection of a direction (the Vulkan / D3D cube rule, the inverse of core/utils/cubemap.hlsl:3-21):
+// face, and (s, t) in [-1, 1] on it.
+BPT_HD bool cube_face_st(float3 d, int& face, float& s, float& t) {
     float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    int face; float s_, t_, ma;
+    float s_, t_, ma;
     if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; ma = ax; s_ = d.x >= 0.0f ? -d.z : d.z; t_ = -d.y; }
     else if (ay >= az) { face = d.y >= 0.0f ? 2 : 3; ma = ay; s_ = d.x; t_ = d.y >= 0.0f ? d.z : -d.z; }
     else { face = d.z >= 0.0f ? 4 : 5; ma = az; s_ = d.z >= 0.0f ? d.x : -d.x; t_ = -d.y; }
-    if (!(ma > 0.0f)) return v3s(0.0f);
-    float u = 0.5f * (s_ / ma + 1.0f), v = 0.5f * (t_ / ma + 1.0f);
+    if (!(ma > 0.0f)) return false;
+    s = s_ / ma; t = t_ / ma;
+    return true;
+}
+// cubemap_direction_from_layered_uv (core/utils/cubemap.hlsl:3-21) without the normalisation; (s, t) may lie outside [-1, 1]
+BPT_HD float3 cube_dir_of(int face, float s, float t) {
+    switch (face) {
+        case 0: return v3(1.0f, -t, -s);
+        case 1: return v3(-1.0f, -t, s);
+        case 2: return v3(s, 1.0f, t);
+        case 3: return v3(s, -1.0f, -t);
+        case 4: return v3(s, -t, 1.0f);
+        default: return v3(-s, -t, -1.0f);
+    }
+}
+// One tap of a seamless bilinear footprint: texel (x, y) of `face`, where ONE of the coordinates may be -1 or n. Such a texel lies
+// across an edge of the cube: its centre on the extended face plane is re-projected onto the cube and the nearest texel of the
+// adjacent face is taken — the texel that touches the edge at the same position along it ((j + 1) n / (n + 1) floors to j).
+BPT_HD float3 cube_tap(const float4* faces, int n, int face, int x, int y) {
+    if (x < 0 || x >= n || y < 0 || y >= n) {
+        const float inv = 1.0f / (float)n;
+        float3 d = cube_dir_of(face, (2.0f * (float)x + 1.0f) * inv - 1.0f, (2.0f * (float)y + 1.0f) * inv - 1.0f);
+        float s, t;
+        cube_face_st(d, face, s, t);
+        x = (int)floorf(0.5f * (s + 1.0f) * (float)n); y = (int)floorf(0.5f * (t + 1.0f) * (float)n);
+        x = x < 0 ? 0 : (x >= n ? n - 1 : x); y = y < 0 ? 0 : (y >= n ? n - 1 : y);
+    }
+    float4 v = BPT_LDG(faces + ((size_t)face * n + y) * n + x);
+    return v3(v.x, v.y, v.z);
+}
+// TextureCube.SampleLevel with a linear sampler (deferred_lighting_secondary.hlsl:26, skybox_precompute_*.hlsl): bilinear with
+// SEAMLESS edges, as Vulkan / D3D12 filter cube maps — a footprint that crosses an edge takes the outside texels from the adjacent
+// face; at a cube corner only three texels exist and the fourth is their average.
+BPT_HD float3 sample_cube(const float4* faces, uint32_t size, float3 d) {
+    if (size == 0) return v3s(0.0f);
+    int face; float s_, t_;
+    if (!cube_face_st(d, face, s_, t_)) return v3s(0.0f);
+    float u = 0.5f * (s_ + 1.0f), v = 0.5f * (t_ + 1.0f);
     int n = (int)size;
     float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
     float x0f = floorf(x), y0f = floorf(y);
     float fx = x - x0f, fy = y - y0f;
-    int x0 = wrap_tc((int)x0f, n, BPT_ADDRESS_CLAMP), x1 = wrap_tc((int)x0f + 1, n, BPT_ADDRESS_CLAMP);
-    int y0 = wrap_tc((int)y0f, n, BPT_ADDRESS_CLAMP), y1 = wrap_tc((int)y0f + 1, n, BPT_ADDRESS_CLAMP);
-    const float4* base = faces + (size_t)face * n * n;
-    float4 a = BPT_LDG(base + (size_t)y0 * n + x0), b = BPT_LDG(base + (size_t)y0 * n + x1);
-    float4 c = BPT_LDG(base + (size_t)y1 * n + x0), e = BPT_LDG(base + (size_t)y1 * n + x1);
-    float3 top = mix3(v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), fx);
-    float3 bot = mix3(v3(c.x, c.y, c.z), v3(e.x, e.y, e.z), fx);
+    int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+    const bool ox0 = x0 < 0, ox1 = x1 >= n, oy0 = y0 < 0, oy1 = y1 >= n;
+    float3 a, b, c, e;
+    if ((ox0 || ox1) && (oy0 || oy1)) {                     // cube corner: the tap outside in both directions does not exist
+        const int xi = ox0 ? x1 : x0, yi = oy0 ? y1 : y0;   // the in-face column / row
+        const int xo = ox0 ? x0 : x1, yo = oy0 ? y0 : y1;   // the outside column / row
+        float3 in_ = cube_tap(faces, n, face, xi, yi), ex = cube_tap(faces, n, face, xo, yi), ey = cube_tap(faces, n, face, xi, yo);
+        float3 avg = ((in_ + ex) + ey) * (1.0f / 3.0f);
+        auto pick = [&](int xx, int yy) { return xx == xi ? (yy == yi ? in_ : ey) : (yy == yi ? ex : avg); };
+        a = pick(x0, y0); b = pick(x1, y0); c = pick(x0, y1); e = pick(x1, y1);
+    } else {
+        a = cube_tap(faces, n, face, x0, y0); b = cube_tap(faces, n, face, x1, y0);
+        c = cube_tap(faces, n, face, x0, y1); e = cube_tap(faces, n, face, x1, y1);
+    }
+    float3 top = mix3(a, b, fx);
+    float3 bot = mix3(c, e, fx);
     return mix3(top, bot, fy);
 }
 BPT_HD float3 sample_sky(const DScene& sc, float3 d) { return sample_cube(sc.sky_faces, sc.sky_size, d); }

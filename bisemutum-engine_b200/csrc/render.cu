@@ -9,6 +9,8 @@
 // Queue compaction: warp ballot + popc, one atomicAdd per warp. Queue ORDER is
 // therefore not deterministic, queue CONTENT is (every entry is keyed by its pixel index).
 #include <algorithm>
+#include <cstdio>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: a no-op unless a profiler injects itself
 #include "bpt_internal.cuh"
 #include "bpt_shade.cuh"
 #include "bpt_ddgi.cuh"
@@ -37,6 +39,13 @@ constexpr int QN = 128;
 #ifndef BPT_REFILL
 #define BPT_REFILL 12
 #endif
+#ifndef BPT_SMEM_STACK
+#define BPT_SMEM_STACK 0
+#endif
+#ifndef BPT_SORT_OCTANT
+#define BPT_SORT_OCTANT 0
+#endif
+constexpr int kSmemStack = BPT_SMEM_STACK;             // stack entries per lane kept in shared memory (0: the whole stack in local memory)
 constexpr int kMinNodeLanes = BPT_MIN_NODE_LANES;       // node phase ends when fewer lanes than this still have an internal node
 constexpr int kRefillThreshold = BPT_REFILL;            // refill a warp's finished lanes when fewer rays than this are still in flight
 
@@ -158,7 +167,14 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_
     const float4* __restrict__ tris = TWO_LEVEL ? nullptr : a.m_tris;
     const float4* __restrict__ leafbox = nullptr;       // TWO_LEVEL && WIDE: exact leaf boxes of the BLAS being traversed (nullptr: single-leaf BLAS)
     const uint32_t lane = threadIdx.x & 31;
-    int32_t stack[(TWO_LEVEL && WIDE) ? 2 * kStackSize : kStackSize];     // two wide trees deep
+    // Short stack in shared memory (north star): the BOTTOM kSmemStack entries of every lane's stack live in shared memory as
+    // [entry][thread] (one bank per lane: conflict-free whatever the lanes' depths are), deeper entries in local memory. A push or pop
+    // at depth d touches exactly one of the two, so the local-memory traffic that is left is the accesses at depth >= kSmemStack.
+    constexpr int S = kSmemStack;
+    __shared__ int32_t s_stack[S > 0 ? S : 1][kBlock];
+    int32_t stack[((TWO_LEVEL && WIDE) ? 2 * kStackSize : kStackSize) - S];     // two wide trees deep
+    auto st_put = [&](int i, int32_t v) { if (S > 0 && i < S) s_stack[i][threadIdx.x] = v; else stack[i - S] = v; };
+    auto st_get = [&](int i) -> int32_t { return (S > 0 && i < S) ? s_stack[i][threadIdx.x] : stack[i - S]; };
     RayState rs;
     RaySpace sp_;
     rs.found = false; rs.tbest = 0.0f; rs.tcull = 0.0f; rs.tmin = 0.001f; rs.cull_non_opaque = ANY && a.cull_non_opaque != 0;
@@ -168,8 +184,8 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_
     int32_t tos = kEmpty;
     int sp = 0;
     // (the wide kernels push up to three nodes per step with predicated stores and keep a plain stack)
-    auto push = [&](int32_t v) { if (WIDE) { stack[sp++] = v; } else { stack[sp++] = tos; tos = v; } };
-    auto pop = [&]() { if (WIDE) return sp ? stack[--sp] : kEmpty; int32_t v = tos; tos = sp ? stack[--sp] : kEmpty; return v; };
+    auto push = [&](int32_t v) { if (WIDE) { st_put(sp++, v); } else { st_put(sp++, tos); tos = v; } };
+    auto pop = [&]() { if (WIDE) return sp ? st_get(--sp) : kEmpty; int32_t v = tos; tos = sp ? st_get(--sp) : kEmpty; return v; };
     uint32_t ray = 0xffffffffu, path = 0;
     uint32_t slot = 0xffffffffu, inst_anyhit = 0;     // TWO_LEVEL: the instance being traversed
     bool in_blas = !TWO_LEVEL;
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_
                         node_test4q(nodes, node, sp_, rs.tmin, rs.tcull, ch, hitmask, best);
 #pragma unroll
                         for (int k = 0; k < 4; k++) {                       // store above the top unconditionally, keep it only if wanted
-                            stack[sp] = ch[k];
+                            st_put(sp, ch[k]);
                             sp += (((hitmask >> k) & 1u) && k != best) ? 1 : 0;
                         }
                         next = best < 0 ? BPT_POP : (best == 0 ? ch[0] : (best == 1 ? ch[1] : (best == 2 ? ch[2] : ch[3])));
@@ -379,8 +395,31 @@ __global__ void __launch_bounds__(kBlock, BPT_SHADE_MIN_BLOCKS) k_shade(const __
         cont = shade_vertex<KernelSink, IBL>(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
     }
     // next-ray queue: ballot per warp, ONE atomicAdd per block (all threads of the block reach this point)
-    __shared__ uint32_t s_warp_cnt[kBlock / 32], s_warp_base[kBlock / 32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if BPT_SORT_OCTANT
+    // The block's surviving rays are written grouped by direction octant (a counting sort over 8 keys inside the block): the warps of
+    // the next extend launch then hold rays that agree on the near / far order of every node, which is what keeps their lanes together.
+    // Queue CONTENT is unchanged (a set), only the order inside the block's slot range differs.
+    __shared__ uint32_t s_cnt[kBlock / 32][8], s_off[kBlock / 32][8];
+    if (threadIdx.x < (kBlock / 32) * 8) (&s_cnt[0][0])[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t key = cont ? ((nD.x < 0.0f ? 1u : 0u) | (nD.y < 0.0f ? 2u : 0u) | (nD.z < 0.0f ? 4u : 0u)) : 8u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (cont && rank == 0) s_cnt[warp][key] = __popc(peers);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int k = 0; k < 8; k++)
+            for (int w = 0; w < kBlock / 32; w++) { s_off[w][k] = total; total += s_cnt[w][k]; }
+        uint32_t base = total ? atomicAdd(&a.qcount[QE + bounce + 1], total) : 0u;
+        for (int k = 0; k < 8; k++)
+            for (int w = 0; w < kBlock / 32; w++) s_off[w][k] += base;
+    }
+    __syncthreads();
+    uint32_t slot = cont ? s_off[warp][key] + rank : 0u;
+#else
+    __shared__ uint32_t s_warp_cnt[kBlock / 32], s_warp_base[kBlock / 32];
     const uint32_t ballot = __ballot_sync(0xffffffffu, cont);
     if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
     __syncthreads();
@@ -394,6 +433,7 @@ __global__ void __launch_bounds__(kBlock, BPT_SHADE_MIN_BLOCKS) k_shade(const __
     }
     __syncthreads();
     uint32_t slot = s_warp_base[warp] + __popc(ballot & ((1u << lane) - 1u));
+#endif
     if (cont) {
         a.ray_o_out[slot] = make_float4(nO.x, nO.y, nO.z, __uint_as_float(path));
         a.ray_d_out[slot] = make_float4(nD.x, nD.y, nD.z, 0.0f);
@@ -622,6 +662,18 @@ __global__ void k_probe_blend(const __grid_constant__ bpt_probe_volume vol, cons
 
 } // namespace
 
+// NVTX ranges carry the labels the reference gives its render-graph passes (path_tracing.cpp:293,313,347,385,429,442,465): a timeline
+// of this library reads like a RenderDoc / Nsight capture of the engine. The fused kernels map as: k_raygen = "PT Generate Camera Ray",
+// extend = "PT Trace GBuffer #i", k_shade = "PT Lighting #i" + "PT Sample Ray #i+1" (one kernel), connect = the shadow-map lookups of
+// "PT Lighting #i" as rays, k_accumulate = "PT Blit Color" + "PT Accumulate".
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    NvtxRange(const char* fmt, unsigned i) { char b[64]; snprintf(b, sizeof(b), fmt, i); nvtxRangePushA(b); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 #define LAUNCH(ctx, kernel, grid, block, ...)                                   \
     do {                                                                        \
         kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);             \
@@ -826,10 +878,17 @@ static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_setting
     for (uint32_t i = 1; i < B; i++) {
         a.ray_o_in = wf.ray_o[cur].as<float4>(); a.ray_d_in = wf.ray_d[cur].as<float4>(); a.ray_w_in = wf.ray_w[cur].as<float4>();
         a.ray_o_out = wf.ray_o[cur ^ 1].as<float4>(); a.ray_d_out = wf.ray_d[cur ^ 1].as<float4>(); a.ray_w_out = wf.ray_w[cur ^ 1].as<float4>();
-        if ((s = launch_extend(ctx, a, i))) return s;
-        if (a.sp.ibl) LAUNCH_T(ctx, 2, k_shade<true>, grid_paths, kBlock, a, i);      // ray-traced reflections with settings.ibl
-        else LAUNCH_T(ctx, 2, k_shade<false>, grid_paths, kBlock, a, i);
+        {
+            NvtxRange r("PT Trace GBuffer #%u", i);
+            if ((s = launch_extend(ctx, a, i))) return s;
+        }
+        {
+            NvtxRange r("PT Lighting + Sample Ray #%u", i);
+            if (a.sp.ibl) LAUNCH_T(ctx, 2, k_shade<true>, grid_paths, kBlock, a, i);      // ray-traced reflections with settings.ibl
+            else LAUNCH_T(ctx, 2, k_shade<false>, grid_paths, kBlock, a, i);
+        }
         if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point + (st.rect_shadow ? ctx->num_rect : 0)) > 0) {
+            NvtxRange r("PT Lighting #%u (shadow rays)", i);
             if ((s = launch_connect(ctx, a, i))) return s;
         }
         if (st.state_precision == BPT_STATE_REFERENCE_FP16) LAUNCH_T(ctx, 4, k_commit_bounce, grid_paths, kBlock, a, i);
@@ -865,10 +924,12 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
         BPT_CUDA_TRY(ctx, cudaMemsetAsync(wf.qcount.p, 0, QN * sizeof(uint32_t), ctx->stream));
         a.ray_o_out = wf.ray_o[0].as<float4>(); a.ray_d_out = wf.ray_d[0].as<float4>(); a.ray_w_out = wf.ray_w[0].as<float4>();
         {
+            NvtxRange r("PT Generate Camera Ray");
             const uint64_t gen_threads = (uint64_t)((ctx->width + 7) / 8) * ((ctx->height + 3) / 4) * 32 * slots;
             LAUNCH_T(ctx, 0, k_raygen, (unsigned)((gen_threads + kBlock - 1) / kBlock), kBlock, a);
         }
         if ((s = run_bounces(ctx, a, st, B, paths, capture))) return s;
+        NvtxRange racc("PT Accumulate");
         if (keep_ahead) { wf.ahead_slots = slots; wf.ahead_cursor = 0; wf.ahead_frame_first = frame_first; }
         else if (st.state_precision == BPT_STATE_REFERENCE_FP16) {
             LAUNCH_T(ctx, 4, k_accumulate_fp16, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, 0u, slots, wf.accum_count);
@@ -882,6 +943,7 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
 
 // OutputData{depth, gbuffer} of PathTracingPass::render: camera rays of one frame, their closest hits, packed like the trace pass packs them.
 bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_settings& st, float* h_depth, bpt_gbuffer_texel* h_gbuffer) {
+    NvtxRange r("PT Trace GBuffer #1 + PT Depth");
     bpt_status s;
     if ((s = wavefront_alloc(ctx))) return s;
     WavefrontState& wf = ctx->wf;
@@ -916,6 +978,7 @@ bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uin
 // AmbientOcclusionPass::render_raytraced (ambient_occlusion.cpp:217-262): depth + normal G-buffer in, rg16_sfloat (ao, valid) out.
 bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_ao_settings& ao, const float* h_depth,
                               const float* h_normal_roughness, float* h_out) {
+    NvtxRange r("RTAO");                                                       // ambient_occlusion.cpp:217-262
     bpt_status s;
     if ((s = wavefront_alloc(ctx))) return s;
     WavefrontState& wf = ctx->wf;
@@ -953,6 +1016,7 @@ bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t 
 // Ray-traced reflections: one wave of (specular sample -> extend -> shade -> connect) over the reflection image.
 bpt_status wavefront_trace_reflection(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_reflection_settings& rs, const float* h_depth,
                                       const bpt_gbuffer_texel* h_gbuffer, float* h_refl, float* h_hit) {
+    NvtxRange r("RTR Trace + Lighting");                                       // reflection.cpp:317-450
     bpt_status s;
     if ((s = wavefront_alloc(ctx))) return s;
     WavefrontState& wf = ctx->wf;
@@ -1011,6 +1075,7 @@ bpt_status launch_upscale_half_res(bpt_context* ctx, const bpt_camera& cam, uint
 // DDGI-style probe tracing through the same extend / shade / connect kernels (BASELINE configs[4]).
 bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol, const float* h_table, uint32_t frame_index, uint32_t num_bounces, float* h_out,
                                   uint32_t first_probe, uint32_t num_probes) {
+    NvtxRange r("DDGI Trace GBuffer + Lighting");                              // ddgi.cpp probe update
     bpt_status s;
     if ((s = wavefront_alloc(ctx))) return s;
     WavefrontState& wf = ctx->wf;
@@ -1051,6 +1116,7 @@ bpt_status wavefront_trace_probes(bpt_context* ctx, const bpt_probe_volume& vol,
 }
 
 bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count) {
+    NvtxRange r("PT Accumulate");
     WavefrontState& wf = ctx->wf;
     if (count == 0 || wf.ahead_cursor + count > wf.ahead_slots) { ctx->err = "accumulate_ahead: not enough prefetched samples"; return BPT_ERR_STATE; }
     const uint32_t npx = ctx->width * ctx->height;

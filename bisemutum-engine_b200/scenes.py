@@ -39,6 +39,7 @@ class SceneData:
     point_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.POINT_LIGHT))
     rect_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.RECT_LIGHT))
     ltc_luts: tuple | None = None
+    light_textures: list = field(default_factory=list)   # rect-light textures: dicts for capi.Context.upload_light_textures
     sky_faces: np.ndarray | None = None
     sky_transform: np.ndarray = field(default_factory=lambda: np.eye(3, dtype=f32).reshape(9))
     sky_color: np.ndarray = field(default_factory=lambda: np.ones(3, f32))
@@ -483,6 +484,36 @@ def add_mixed_lights(scene: SceneData, n_point: int, n_rect: int, ltc_luts, seed
         scene.dir_lights = np.zeros(0, capi.DIR_LIGHT)
     scene.ltc_luts = tuple(np.ascontiguousarray(a, f32) for a in ltc_luts) if n_rect else None
     scene.name += f"+{n_point}point+{n_rect}rect"
+    return scene
+
+
+def light_texture(width: int, height: int, fmt: int = None, levels: int = 16, seed: int = 5, mip_linear: int = 1, linear: int = 1) -> dict:
+    """A procedural rect-light texture (colour bars over a soft gradient, a dark frame): enough structure that a wrong (u, v), mip level or
+    filter shows up. 8-bit formats as uint8 (H, W, 4), RGBA32F as float32."""
+    fmt = capi.TEXTURE_RGBA8_SRGB if fmt is None else fmt
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width]
+    u, v = (x + 0.5) / width, (y + 0.5) / height
+    bars = rng.uniform(0.1, 1.0, (7, 3))[(u * 7).astype(int) % 7]
+    img = bars * (0.35 + 0.65 * v[..., None]) * (0.6 + 0.4 * np.sin(9.0 * u + 4.0 * v)[..., None] ** 2)
+    frame = (np.minimum(np.minimum(u, 1 - u), np.minimum(v, 1 - v)) < 0.06)[..., None]
+    img = np.where(frame, 0.03, img)
+    rgba = np.concatenate([img, np.ones((height, width, 1))], -1)
+    texels = rgba.astype(f32) * 2.0 if fmt == capi.TEXTURE_RGBA32_FLOAT else np.clip(np.rint(rgba * 255.0), 0, 255).astype(np.uint8)
+    return {"texels": np.ascontiguousarray(texels), "format": fmt, "levels": levels, "address_u": capi.ADDRESS_CLAMP, "address_v": capi.ADDRESS_CLAMP,
+            "linear": linear, "mip_linear": mip_linear}
+
+
+def texture_rect_lights(scene: SceneData, textures: list, light_width: float = 1.0, light_height: float = 1.0) -> SceneData:
+    """Gives rect light i the texture i % len(textures), with inv_texel_size as LightsContext::collect_all_lights computes it
+    (lights.cpp:233-237: max(texture width / light width, texture height / light height))."""
+    scene.light_textures = list(textures)
+    for i in range(len(scene.rect_lights)):
+        k = i % len(textures)
+        t = textures[k]["texels"]
+        scene.rect_lights[i]["texture_index"] = k
+        scene.rect_lights[i]["inv_texel_size"] = max(f32(t.shape[1]) / f32(light_width), f32(t.shape[0]) / f32(light_height))
+    scene.name += "+lighttex"
     return scene
 
 

@@ -231,6 +231,28 @@ typedef struct bpt_ltc_luts {
     const float* norm_lut;                                                          /* 8*8*64*2 floats */
 } bpt_ltc_luts;
 
+/* Rect-light textures (RectLightComponent::texture, bisemutum/src/renderer/context/lights.cpp:229-239; sampled by
+ * rect_light_sample_texture, shaders/renderer/lights.hlsl:425-447, at the two call sites :495-511). Texture k is the one
+ * bpt_rect_light_data::texture_index == k refers to (the reference binds up to 16, lights.hpp:65); a light whose index has no
+ * texture here is evaluated untextured. `texels` is level 0; with levels > 1 the chain is generated as the engine generates it
+ * when a TextureAsset is uploaded (scene_basic/texture.cpp:176 -> GraphicsManager::generate_mipmaps_2d ->
+ * shaders/core/mipmap.hlsl, MIPMAP_MODE_AVG, each level stored in the texture's own format). SampleLevel(level) filters inside a level
+ * as `filter_linear` says and between levels as `mip_linear` says (rhi::SamplerDesc::mipmap_mode; nearest = the Vulkan rule
+ * ceil(level + 0.5) - 1), all in explicit FP32 arithmetic. Call before or after bpt_scene_upload_lights; 0 textures clears them. */
+typedef struct bpt_light_texture_desc {
+    const void* texels;
+    uint32_t width, height;
+    uint32_t format;        /* BPT_TEXTURE_* */
+    uint32_t levels;        /* >= 1; clamped to floor(log2(max(width, height))) + 1 as generate_mipmaps_2d does */
+    uint32_t address_mode_u, address_mode_v;
+    uint32_t filter_linear; /* 0 = nearest, 1 = bilinear inside a level */
+    uint32_t mip_linear;    /* 0 = nearest level, 1 = linear between levels */
+} bpt_light_texture_desc;
+#define BPT_MAX_RECT_LIGHT_TEXTURES 16u
+BPT_API bpt_status bpt_scene_upload_light_textures(bpt_context* ctx, const bpt_light_texture_desc* textures, uint32_t num_textures);
+/* Debug: the generated chain of light texture `index` as RGBA32F texels, level after level (W*H + (W/2)*(H/2) + ... float4). */
+BPT_API bpt_status bpt_debug_read_light_texture(bpt_context* ctx, uint32_t index, float* out_rgba32f, uint64_t capacity_texels, uint64_t* out_texels);
+
 BPT_API bpt_status bpt_scene_upload_lights(
     bpt_context* ctx,
     const bpt_dir_light_data* dir_lights, uint32_t num_dir_lights,

@@ -77,6 +77,8 @@ BPT_API bpt_status obpt_debug_read_queue(
 BPT_API bpt_status obpt_set_wide_from_bounce(obpt_context* ctx, uint32_t bounce);
 /* The 4-wide quantised tree of merged mode (oracle_wide.cpp = the definition csrc/bpt_wide.cuh must reproduce) and work
  * statistics of wide traversals on a ray batch: counts = {rays, wide nodes, triangles, child boxes, exact leaf boxes}. */
+BPT_API bpt_status obpt_scene_upload_light_textures(obpt_context* ctx, const bpt_light_texture_desc* textures, uint32_t num_textures);
+BPT_API bpt_status obpt_debug_read_light_texture(obpt_context* ctx, uint32_t index, float* out_rgba32f, uint64_t capacity_texels, uint64_t* out_texels);
 BPT_API bpt_status obpt_debug_read_wide(obpt_context* ctx, float* wide_nodes, float* leaf_boxes, uint32_t capacity_leaves);
 BPT_API bpt_status obpt_wide_stats(obpt_context* ctx, uint32_t width, uint32_t quantised, uint32_t order, const bpt_ray* rays, uint64_t n,
                                    float* t_out, uint32_t* prim_out, uint64_t counts[5]);
@@ -158,6 +160,16 @@ BPT_API void obpt_surface_eval_lit(const float N[3], const float T[3], const flo
                                    float roughness, float anisotropy, float out_rgb[3]);
 /* state_precision = reference_fp16: one value through an rgba16_sfloat store; (N, T, surface) through the four G-buffer
  * textures (gbuffer.hlsl:18-45). in12 = base[3] f0[3] f90[3] roughness anisotropy ior; out18 = N T base f0 f90 roughness anisotropy ior. */
+/* Unit entry points for the independent float64 pins (tests/test_oracle.py): one reference function each. */
+BPT_API void obpt_unit_ltc_integrate(const float P[3], const float N[3], const float T[3], const float B[3], const float* Minv9_or_null, const float L[12],
+                                     uint32_t two_sided, float* integral, float mrp[3]);
+BPT_API void obpt_unit_rect_light(obpt_context* ctx, const bpt_rect_light_data* light, const float P[3], const float N[3], const float T[3], const float B[3],
+                                  const float V[3], const float base[3], const float f0[3], const float f90[3], float roughness, float anisotropy,
+                                  float out_rgb[3], float diff_mrp_or_null[3]);
+BPT_API void obpt_unit_point_light(const bpt_point_light_data* light, const float P[3], float radiance[3], float dir[3], float* dist);
+BPT_API void obpt_unit_sample_sky(obpt_context* ctx, const float dir[3], float out_rgb[3]);
+BPT_API bpt_status obpt_unit_hit_vertex(obpt_context* ctx, uint32_t instance_slot, uint32_t prim, float u, float v, float out14[14]);
+BPT_API float obpt_unit_log2(float x);
 BPT_API float obpt_store_half(float f);
 BPT_API void obpt_gbuffer_roundtrip(const float N[3], const float T[3], const float in12[12], uint32_t model, float out18[18], uint32_t* model_out);
 BPT_API uint64_t obpt_morton63(const float c[3], const float lo[3], const float hi[3]);

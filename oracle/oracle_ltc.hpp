@@ -1,7 +1,7 @@
 // oracle_ltc.hpp — TEST INFRASTRUCTURE ONLY (CPU oracle).
 // LTC rect lights: restatement of shaders/renderer/lights.hlsl:164-513 and the caller loop
-// shaders/renderer/raytracing/deferred_lighting_secondary.hlsl:72-96. Rect-light textures
-// (lights.hlsl:425-447) are not supported: texture_index is treated as -1.
+// shaders/renderer/raytracing/deferred_lighting_secondary.hlsl:72-96, including rect-light textures
+// (lights.hlsl:425-447,495-511) on the mip chain of shaders/core/mipmap.hlsl (built in oracle_render.cpp).
 #pragma once
 #include "oracle_scene.hpp"
 
@@ -154,8 +154,8 @@ static inline f4 ltc_integrate_edge(f3 v1, f3 v2) {
     f3 c = cross(v1, v2);
     return f4{c.x * tdst, c.y * tdst, c.z * tdst, c.z * tdst};
 }
-// lights.hlsl:383-423 (mrp is only consumed by the unsupported light-texture lookup)
-static inline float ltc_integrate(f3 P, f3 N, f3 T, f3 B, const m33& ltc_matrix_inv, const f3 L[4], bool two_sided, f3* mrp = nullptr) {
+// lights.hlsl:383-423; `ltc_matrix` (nullptr = identity) only enters the most representative point
+static inline float ltc_integrate(f3 P, f3 N, f3 T, f3 B, const m33& ltc_matrix_inv, const f3 L[4], bool two_sided, f3* mrp = nullptr, const m33* ltc_matrix = nullptr) {
     m33 TBN{T, B, N};
     f3 LP[5];
     for (int k = 0; k < 4; k++) LP[k] = mul(ltc_matrix_inv, mul(TBN, L[k] - P));
@@ -172,9 +172,56 @@ static inline float ltc_integrate(f3 P, f3 N, f3 T, f3 B, const m33& ltc_matrix_
     if (n == 5) acc(ltc_integrate_edge(LP[4], LP[0]));
     float integral = two_sided ? fabsf(sum.w) : fmax_(0.0f, sum.w);
     if (!std::isfinite(integral)) integral = 0.0f;
-    // lights.hlsl:420 with the identity matrix (the diffuse lobe): mrp = normalize(mul(sum.xyz, TBN)) = x*T + y*B + z*N
-    if (mrp) *mrp = normalize((sum.x * T + sum.y * B) + sum.z * N);
+    // lights.hlsl:420: mrp = normalize(mul(mul(ltc_matrix, sum.xyz), TBN)); a row vector times TBN is x*T + y*B + z*N
+    if (mrp) {
+        f3 v = mk3(sum.x, sum.y, sum.z);
+        if (ltc_matrix) v = mul(*ltc_matrix, v);
+        *mrp = normalize((v.x * T + v.y * B) + v.z * N);
+    }
     return integral;
+}
+
+// Texture2D.SampleLevel on the chain: bilinear (or nearest) inside a level, linear or nearest between levels (rhi::SamplerDesc).
+static inline f3 light_texture_fetch(const LightTexture& t, int level, float u, float v) {
+    const int w = (int)std::max(t.w >> level, 1u), h = (int)std::max(t.h >> level, 1u);
+    const float* img = t.level[(size_t)level].data();
+    auto wrap = [](int c, int n, uint32_t mode) { if (mode == BPT_ADDRESS_REPEAT) { int m = c % n; return m < 0 ? m + n : m; } return c < 0 ? 0 : (c >= n ? n - 1 : c); };
+    auto px = [&](int x, int y) { const float* p = img + ((size_t)y * w + x) * 4; return mk3(p[0], p[1], p[2]); };
+    if (!t.linear) return px(wrap((int)floorf(u * (float)w), w, t.addr_u), wrap((int)floorf(v * (float)h), h, t.addr_v));
+    float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    float x0f = floorf(x), y0f = floorf(y);
+    float fx = x - x0f, fy = y - y0f;
+    int x0 = wrap((int)x0f, w, t.addr_u), x1 = wrap((int)x0f + 1, w, t.addr_u), y0 = wrap((int)y0f, h, t.addr_v), y1 = wrap((int)y0f + 1, h, t.addr_v);
+    return lerp3(lerp3(px(x0, y0), px(x1, y0), fx), lerp3(px(x0, y1), px(x1, y1), fx), fy);
+}
+static inline f3 light_texture_sample_level(const LightTexture& t, float u, float v, float level) {
+    const int last = (int)t.level.size() - 1;
+    level = fmin_(fmax_(level, 0.0f), (float)last);
+    if (!t.mip_linear) {
+        int l = (int)ceilf(level + 0.5f) - 1;                     // Vulkan: nearest level
+        return light_texture_fetch(t, std::min(std::max(l, 0), last), u, v);
+    }
+    const float base = floorf(level);
+    const int l0 = (int)base, l1 = std::min(l0 + 1, last);
+    f3 a = light_texture_fetch(t, l0, u, v);
+    if (l1 == l0) return a;
+    return lerp3(a, light_texture_fetch(t, l1, u, v), level - base);
+}
+// lights.hlsl:425-447
+static inline f3 rect_light_sample_texture(const LightTexture& tex, const bpt_rect_light_data& light, f3 direction, f3 P, float roughness) {
+    const f3 n = mk3(light.normal[0], light.normal[1], light.normal[2]);
+    const f3 p1 = mk3(light.position1[0], light.position1[1], light.position1[2]), p2 = mk3(light.position2[0], light.position2[1], light.position2[2]),
+             p3 = mk3(light.position3[0], light.position3[1], light.position3[2]);
+    float step = fabsf(dot(direction, n));
+    if (step < 0.0001f) return splat3(0.0f);
+    float dist = fabsf(dot(P - p2, n));
+    float t = dist / step;
+    f3 rect_pos = (P + direction * t) - p2;
+    float u = saturate(dot(rect_pos, p3 - p2) * light.inv_width_sqr);
+    float v = saturate(dot(rect_pos, p1 - p2) * light.inv_height_sqr);
+    float num_texels = (t * roughness) * light.inv_texel_size;
+    float level = log2_(fmax_(1.0f, num_texels));
+    return light_texture_sample_level(tex, u, v, level);
 }
 
 // rect_light_eval_ltc (lights.hlsl:449-513) + surface_eval_lut (deferred_lighting_secondary.hlsl:80-96)
@@ -190,13 +237,21 @@ static inline f3 ltc_rect_light(const Scene& sc, const bpt_rect_light_data& ligh
                    mk3(light.position1[0], light.position1[1], light.position1[2]), mk3(light.position0[0], light.position0[1], light.position0[2])};
         f3 emission = mk3(light.emission[0], light.emission[1], light.emission[2]);
         m33 identity{mk3(1, 0, 0), mk3(0, 1, 0), mk3(0, 0, 1)};
-        float integral_diff = ltc_integrate(P, N, T, B, identity, L, light.two_sided != 0, diff_mrp);
+        f3 mrp_d = splat3(0.0f), mrp_s = splat3(0.0f);
+        float integral_diff = ltc_integrate(P, N, T, B, identity, L, light.two_sided != 0, &mrp_d);
+        if (diff_mrp) *diff_mrp = mrp_d;
         ltc_diff = emission * integral_diff;
         m33 ltc_matrix;
         get_ltc_matrix_and_brdf(sc, local_v, rx, ry, L, ltc_matrix, ltc_brdf);
         m33 ltc_matrix_inv = inverse(ltc_matrix);
-        float integral_spec = ltc_integrate(P, N, T, B, ltc_matrix_inv, L, light.two_sided != 0);
+        float integral_spec = ltc_integrate(P, N, T, B, ltc_matrix_inv, L, light.two_sided != 0, &mrp_s, &ltc_matrix);
         ltc_spec = emission * integral_spec;
+        if (light.texture_index >= 0 && (size_t)light.texture_index < sc.light_textures.size()) {       // lights.hlsl:495-511
+            // (with a zero integral the reference leaves `mrp` unwritten and multiplies 0 by whatever the lookup returns; the term stays 0 here)
+            const LightTexture& tex = sc.light_textures[(size_t)light.texture_index];
+            ltc_diff = integral_diff != 0.0f ? ltc_diff * rect_light_sample_texture(tex, light, mrp_d, P, 1.0f) : splat3(0.0f);
+            ltc_spec = integral_spec != 0.0f ? ltc_spec * rect_light_sample_texture(tex, light, mrp_s, P, sqrtf(rx * ry)) : splat3(0.0f);
+        }
     }
     return surface_eval_lut(N, V, surf, ltc_diff, ltc_spec, ltc_brdf, surface_model);
 }

@@ -133,6 +133,23 @@ static inline float acos_(float x) {
     return 2.0f * atan2_(sqrtf(1.0f - x), sqrtf(1.0f + x));
 }
 
+// log2(x), x >= 1 finite, fixed operation order (lights.hlsl:445 needs a log2 that two compilers agree on bit for bit):
+// x = m * 2^e, m in [sqrt(1/2), sqrt(2)); log2(m) = 2/ln2 * atanh(s) with s = (m - 1)/(m + 1), series through s^9.
+static inline float log2_(float x) {
+    uint32_t bits; std::memcpy(&bits, &x, 4);
+    int e = (int)((bits >> 23) & 0xffu) - 127;
+    uint32_t mb = (bits & 0x007fffffu) | 0x3f800000u;
+    float m; std::memcpy(&m, &mb, 4);
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    const float s = (m - 1.0f) / (m + 1.0f), s2 = s * s;
+    float p = 1.0f / 9.0f;
+    p = p * s2 + 1.0f / 7.0f;
+    p = p * s2 + 1.0f / 5.0f;
+    p = p * s2 + 1.0f / 3.0f;
+    p = p * s2 + 1.0f;
+    return (float)e + (2.88539008f * s) * p;
+}
+
 // ---- frames: core/utils/frame.hlsl:9-34 --------------------------------------------------
 struct Frame { f3 x, y, z; };
 static inline Frame create_frame(f3 n) {             // frame.hlsl:9-18

@@ -61,27 +61,60 @@ static inline f4 sample_or_default(const Scene& sc, int32_t tex, f2 uv, f4 dflt)
     return sample_texture(sc.textures[tex], uv.x, uv.y);
 }
 
-// ---- sky: deferred_lighting_secondary.hlsl:24-29; face/uv selection is the Vulkan cube rule,
-//      the inverse of core/utils/cubemap.hlsl:3-21; bilinear inside the face, clamp to edge. ----
+// ---- sky: deferred_lighting_secondary.hlsl:24-29. TextureCube.SampleLevel with the linear skybox sampler: face / (s, t) selection
+//      is the Vulkan cube rule (the inverse of core/utils/cubemap.hlsl:3-21); bilinear, SEAMLESS across edges as Vulkan and D3D12
+//      filter cube maps: taps beyond an edge come from the adjacent face, the missing fourth tap at a corner is the mean of the three.
+struct CubeCoord { int face; float s, t; bool ok; };
+static inline CubeCoord cube_coord(f3 d) {
+    CubeCoord c{0, 0.0f, 0.0f, false};
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z), sc_, tc, ma;
+    if (ax >= ay && ax >= az) { c.face = d.x >= 0.0f ? 0 : 1; ma = ax; sc_ = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; }
+    else if (ay >= az) { c.face = d.y >= 0.0f ? 2 : 3; ma = ay; sc_ = d.x; tc = d.y >= 0.0f ? d.z : -d.z; }
+    else { c.face = d.z >= 0.0f ? 4 : 5; ma = az; sc_ = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; }
+    if (!(ma > 0.0f)) return c;
+    c.s = sc_ / ma; c.t = tc / ma; c.ok = true;
+    return c;
+}
+static inline f3 cube_point(int face, float s, float t) {           // cubemap.hlsl:3-21 before the normalize; (s, t) may leave [-1, 1]
+    static const float sx[6][3] = {{0, 0, -1}, {0, 0, 1}, {1, 0, 0}, {1, 0, 0}, {1, 0, 0}, {-1, 0, 0}};     // d = major + s * sx + t * tx
+    static const float tx[6][3] = {{0, -1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {0, -1, 0}, {0, -1, 0}};
+    static const float mj[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    // one non-zero term per component: no rounding is involved, the sums below are exact selections
+    return mk3(mj[face][0] + (sx[face][0] * s + tx[face][0] * t), mj[face][1] + (sx[face][1] * s + tx[face][1] * t), mj[face][2] + (sx[face][2] * s + tx[face][2] * t));
+}
+static inline f3 cube_texel(const float* faces, int n, int face, int x, int y) {
+    if (x < 0 || x >= n || y < 0 || y >= n) {                        // across an edge: centre of the virtual texel, re-projected
+        const float inv = 1.0f / (float)n;
+        CubeCoord c = cube_coord(cube_point(face, (2.0f * (float)x + 1.0f) * inv - 1.0f, (2.0f * (float)y + 1.0f) * inv - 1.0f));
+        face = c.face;
+        x = (int)floorf(0.5f * (c.s + 1.0f) * (float)n); y = (int)floorf(0.5f * (c.t + 1.0f) * (float)n);
+        x = std::min(std::max(x, 0), n - 1); y = std::min(std::max(y, 0), n - 1);
+    }
+    const float* p = faces + (((size_t)face * n + y) * n + x) * 4;
+    return mk3(p[0], p[1], p[2]);
+}
 static inline f3 sample_cube(const float* faces, uint32_t size, f3 d) {
     if (size == 0) return splat3(0.0f);
-    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    int face; float sc_, tc, ma;
-    if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; ma = ax; sc_ = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; }
-    else if (ay >= az) { face = d.y >= 0.0f ? 2 : 3; ma = ay; sc_ = d.x; tc = d.y >= 0.0f ? d.z : -d.z; }
-    else { face = d.z >= 0.0f ? 4 : 5; ma = az; sc_ = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; }
-    if (!(ma > 0.0f)) return splat3(0.0f);
-    float u = 0.5f * (sc_ / ma + 1.0f), v = 0.5f * (tc / ma + 1.0f);
+    CubeCoord cc = cube_coord(d);
+    if (!cc.ok) return splat3(0.0f);
+    float u = 0.5f * (cc.s + 1.0f), v = 0.5f * (cc.t + 1.0f);
     int n = (int)size;
     float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
     float x0f = floorf(x), y0f = floorf(y);
     float fx = x - x0f, fy = y - y0f;
-    int x0 = wrap_coord((int)x0f, n, BPT_ADDRESS_CLAMP), x1 = wrap_coord((int)x0f + 1, n, BPT_ADDRESS_CLAMP);
-    int y0 = wrap_coord((int)y0f, n, BPT_ADDRESS_CLAMP), y1 = wrap_coord((int)y0f + 1, n, BPT_ADDRESS_CLAMP);
-    const float* base = faces + (size_t)face * n * n * 4;
-    auto tx = [&](int xx, int yy) { const float* p = base + ((size_t)yy * n + xx) * 4; return mk3(p[0], p[1], p[2]); };
-    f3 top = lerp3(tx(x0, y0), tx(x1, y0), fx);
-    f3 bot = lerp3(tx(x0, y1), tx(x1, y1), fx);
+    int xs[2] = {(int)x0f, (int)x0f + 1}, ys[2] = {(int)y0f, (int)y0f + 1};
+    f3 tap[2][2];                                                    // [row][column]
+    int bad_r = -1, bad_c = -1;
+    for (int r = 0; r < 2; r++)
+        for (int c = 0; c < 2; c++) {
+            bool out_x = xs[c] < 0 || xs[c] >= n, out_y = ys[r] < 0 || ys[r] >= n;
+            if (out_x && out_y) { bad_r = r; bad_c = c; continue; }  // beyond a cube corner: no such texel
+            tap[r][c] = cube_texel(faces, n, cc.face, xs[c], ys[r]);
+        }
+    if (bad_r >= 0)                                                  // mean of the three that exist: (in-face + across x) + across y
+        tap[bad_r][bad_c] = ((tap[1 - bad_r][1 - bad_c] + tap[1 - bad_r][bad_c]) + tap[bad_r][1 - bad_c]) * (1.0f / 3.0f);
+    f3 top = lerp3(tap[0][0], tap[0][1], fx);
+    f3 bot = lerp3(tap[1][0], tap[1][1], fx);
     return lerp3(top, bot, fy);
 }
 static inline f3 sample_sky(const Scene& sc, f3 d) { return sample_cube(sc.sky_faces.data(), sc.sky_size, d); }
@@ -658,6 +691,78 @@ bpt_status obpt_scene_upload_lights(obpt_context* c, const bpt_dir_light_data* d
     }
     return BPT_OK;
 }
+// Rect-light textures. Level 0 is decoded to what a sampler returns; the chain follows shaders/core/mipmap.hlsl:46-93 as
+// CommandHelpers::generate_mipmaps_2d dispatches it (command_helpers.cpp:66-215: tex_size = the DESTINATION extent, so the "odd" taps are
+// taken when the destination is odd; reads past the source level return 0), every level stored in the texture's format.
+namespace {
+double srgb_to_linear(double v) { return v <= 0.04045 ? v / 12.92 : std::pow((v + 0.055) / 1.055, 2.4); }
+float store_in_format(float x, uint32_t format, int channel) {
+    if (format == BPT_TEXTURE_RGBA32_FLOAT) return x;
+    if (format == BPT_TEXTURE_RGBA8_UNORM || channel == 3) return store_unorm(x, 8);
+    if (!(x > 0.0f)) return 0.0f;
+    // nearest 8-bit sRGB code in the encoded domain = the code c with EOTF((c - 0.5)/255) <= x < EOTF((c + 0.5)/255); then decoded again
+    int code = 0;
+    for (int c = 1; c < 256; c++) if ((float)srgb_to_linear((c - 0.5) / 255.0) <= x) code = c; else break;
+    return (float)srgb_to_linear(code / 255.0);
+}
+}
+bpt_status obpt_scene_upload_light_textures(obpt_context* c, const bpt_light_texture_desc* t, uint32_t nt) {
+    CHECK_CTX(c);
+    if ((nt && !t) || nt > BPT_MAX_RECT_LIGHT_TEXTURES) return fail(c, BPT_ERR_INVALID, "light textures: null array or more than 16");
+    std::vector<LightTexture> out(nt);
+    for (uint32_t i = 0; i < nt; i++) {
+        const bpt_light_texture_desc& d = t[i];
+        if (!d.texels || !d.width || !d.height || d.width > 16384 || d.height > 16384 || d.format > BPT_TEXTURE_RGBA8_SRGB || d.levels == 0 ||
+            d.address_mode_u > BPT_ADDRESS_CLAMP || d.address_mode_v > BPT_ADDRESS_CLAMP) return fail(c, BPT_ERR_INVALID, "bad light texture desc");
+        LightTexture& lt = out[i];
+        lt.w = d.width; lt.h = d.height; lt.addr_u = d.address_mode_u; lt.addr_v = d.address_mode_v; lt.linear = d.filter_linear != 0; lt.mip_linear = d.mip_linear != 0;
+        uint32_t levels = 1;
+        while ((std::max(d.width, d.height) >> levels) != 0) levels++;
+        levels = std::min(levels, d.levels);
+        lt.level.resize(levels);
+        std::vector<float>& l0 = lt.level[0];
+        l0.resize((size_t)d.width * d.height * 4);
+        if (d.format == BPT_TEXTURE_RGBA32_FLOAT) std::memcpy(l0.data(), d.texels, l0.size() * 4);
+        else {
+            const uint8_t* src = static_cast<const uint8_t*>(d.texels);
+            for (size_t k = 0; k < l0.size(); k++)
+                l0[k] = (d.format == BPT_TEXTURE_RGBA8_SRGB && (k & 3) != 3) ? (float)srgb_to_linear(src[k] / 255.0) : (float)src[k] / 255.0f;
+        }
+        for (uint32_t l = 1; l < levels; l++) {
+            const uint32_t sw = std::max(d.width >> (l - 1), 1u), sh = std::max(d.height >> (l - 1), 1u), dw = std::max(sw / 2, 1u), dh = std::max(sh / 2, 1u);
+            const std::vector<float>& src = lt.level[l - 1];
+            std::vector<float>& dst = lt.level[l];
+            dst.resize((size_t)dw * dh * 4);
+            const bool odd_x = (dw & 1u) != 0, odd_y = (dh & 1u) != 0;
+            for (uint32_t y = 0; y < dh; y++)
+                for (uint32_t x = 0; x < dw; x++)
+                    for (int ch = 0; ch < 4; ch++) {
+                        auto at = [&](uint32_t xx, uint32_t yy) { return (xx < sw && yy < sh) ? src[((size_t)yy * sw + xx) * 4 + ch] : 0.0f; };
+                        const uint32_t sx = 2 * x, sy = 2 * y;
+                        float r = (at(sx, sy) + at(sx, sy + 1)) + (at(sx + 1, sy) + at(sx + 1, sy + 1));
+                        uint32_t num = 4;
+                        if (odd_x) { r = r + (at(sx + 2, sy) + at(sx + 2, sy + 1)); num += 2; }
+                        if (odd_y) { r = r + (at(sx, sy + 2) + at(sx + 1, sy + 2)); num += 2; }
+                        if (odd_x && odd_y) { r = r + at(sx + 2, sy + 2); num += 1; }
+                        dst[((size_t)y * dw + x) * 4 + ch] = store_in_format(r / (float)num, d.format, ch);
+                    }
+        }
+    }
+    c->scene.light_textures = std::move(out);
+    return BPT_OK;
+}
+bpt_status obpt_debug_read_light_texture(obpt_context* c, uint32_t index, float* out, uint64_t cap, uint64_t* out_texels) {
+    CHECK_CTX(c);
+    if (index >= c->scene.light_textures.size()) return fail(c, BPT_ERR_INVALID, "light texture index out of range");
+    uint64_t total = 0;
+    for (auto& l : c->scene.light_textures[index].level) total += l.size() / 4;
+    if (out_texels) *out_texels = total;
+    if (!out) return BPT_OK;
+    if (cap < total) return fail(c, BPT_ERR_INVALID, "capacity too small");
+    for (auto& l : c->scene.light_textures[index].level) { std::memcpy(out, l.data(), l.size() * 4); out += l.size(); }
+    return BPT_OK;
+}
+
 bpt_status obpt_scene_upload_sky(obpt_context* c, const float* faces, uint32_t size, const float xf[9], const float col[3]) {
     CHECK_CTX(c);
     Scene& sc = c->scene;
@@ -1386,6 +1491,48 @@ void obpt_surface_eval_lit(const float N[3], const float T[3], const float V[3],
     f3 r = surface_eval(n, t, cross(n, t), mk3(V[0], V[1], V[2]), mk3(L[0], L[1], L[2]), s, 1u);
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
+// ---- unit entry points for the independent float64 pins of tests/test_oracle.py (test hooks, not part of the boundary) ----
+// ltc_integrate (lights.hlsl:383-423) of the quad L[4] (row k = L[k]) seen from P in the frame (T, B, N); Minv = nullptr: identity
+void obpt_unit_ltc_integrate(const float P[3], const float N[3], const float T[3], const float B[3], const float* Minv, const float L[12], uint32_t two_sided,
+                             float* integral, float mrp[3]) {
+    m33 I{mk3(1, 0, 0), mk3(0, 1, 0), mk3(0, 0, 1)};
+    m33 mi = Minv ? m33{mk3(Minv[0], Minv[1], Minv[2]), mk3(Minv[3], Minv[4], Minv[5]), mk3(Minv[6], Minv[7], Minv[8])} : I;
+    f3 Lq[4] = {mk3(L[0], L[1], L[2]), mk3(L[3], L[4], L[5]), mk3(L[6], L[7], L[8]), mk3(L[9], L[10], L[11])};
+    f3 m = splat3(0.0f);
+    *integral = ltc_integrate(mk3(P[0], P[1], P[2]), mk3(N[0], N[1], N[2]), mk3(T[0], T[1], T[2]), mk3(B[0], B[1], B[2]), mi, Lq, two_sided != 0, &m);
+    mrp[0] = m.x; mrp[1] = m.y; mrp[2] = m.z;
+}
+// rect_light_eval_ltc + surface_eval_lut for one light with the context's LUTs and light textures (deferred_lighting_secondary.hlsl:80-96)
+void obpt_unit_rect_light(obpt_context* c, const bpt_rect_light_data* light, const float P[3], const float N[3], const float T[3], const float B[3], const float V[3],
+                          const float base[3], const float f0[3], const float f90[3], float roughness, float anisotropy, float out[3], float diff_mrp[3]) {
+    SurfaceData s = surface_data_default();
+    s.base_color = mk3(base[0], base[1], base[2]); s.f0_color = mk3(f0[0], f0[1], f0[2]); s.f90_color = mk3(f90[0], f90[1], f90[2]);
+    s.roughness = roughness; s.anisotropy = anisotropy;
+    f3 m = splat3(0.0f);
+    f3 r = ltc_rect_light(c->scene, *light, mk3(P[0], P[1], P[2]), mk3(N[0], N[1], N[2]), mk3(T[0], T[1], T[2]), mk3(B[0], B[1], B[2]), mk3(V[0], V[1], V[2]), s, 1u, &m);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+    if (diff_mrp) { diff_mrp[0] = m.x; diff_mrp[1] = m.y; diff_mrp[2] = m.z; }
+}
+void obpt_unit_point_light(const bpt_point_light_data* l, const float P[3], float radiance[3], float dir[3], float* dist) {     // lights.hlsl:14-25
+    f3 d; float t;
+    f3 e = point_light_eval(*l, mk3(P[0], P[1], P[2]), d, t);
+    radiance[0] = e.x; radiance[1] = e.y; radiance[2] = e.z; dir[0] = d.x; dir[1] = d.y; dir[2] = d.z; *dist = t;
+}
+void obpt_unit_sample_sky(obpt_context* c, const float d[3], float out[3]) {                // skybox.SampleLevel(sampler, dir, 0)
+    f3 r = sample_sky(c->scene, mk3(d[0], d[1], d[2]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+// fetch_vertex_attributes (core/raytracing/hit.hlsl:27-164) for a hit on instance slot `slot`: normal, tangent, bitangent, position, texcoord
+bpt_status obpt_unit_hit_vertex(obpt_context* c, uint32_t slot, uint32_t prim, float u, float v, float out[14]) {
+    CHECK_CTX(c);
+    if (!c->scene.accel_built || slot >= c->scene.xf.size()) return fail(c, BPT_ERR_INVALID, "unit_hit_vertex: bad slot or no accel");
+    Vertex vt = fetch_vertex_attributes(c->scene, c->scene.xf[slot], prim, u, v);
+    const f3 a[4] = {vt.normal_world, vt.tangent_world, vt.bitangent_world, vt.position_world};
+    for (int k = 0; k < 4; k++) { out[3 * k] = a[k].x; out[3 * k + 1] = a[k].y; out[3 * k + 2] = a[k].z; }
+    out[12] = vt.texcoord.x; out[13] = vt.texcoord.y;
+    return BPT_OK;
+}
+float obpt_unit_log2(float x) { return log2_(x); }
 float obpt_store_half(float f) { return store_half(f); }
 void obpt_gbuffer_roundtrip(const float N[3], const float T[3], const float in[12], uint32_t model, float out[18], uint32_t* model_out) {
     SurfaceData s = surface_data_default();

@@ -47,6 +47,13 @@ struct TraceStats {
     void add(const TraceStats& o) { rays += o.rays; nodes += o.nodes; tris += o.tris; instances += o.instances; wide_nodes += o.wide_nodes; leaf_boxes += o.leaf_boxes; }
 };
 
+// Rect-light texture with its generated mip chain: one RGBA32F image per level (what the sampler returns after format decoding).
+struct LightTexture {
+    uint32_t w = 0, h = 0, addr_u = 0, addr_v = 0;
+    bool linear = true, mip_linear = false;
+    std::vector<std::vector<float>> level;          // level[l]: max(w >> l, 1) * max(h >> l, 1) * 4 floats
+};
+
 struct Scene {
     std::vector<float> positions, normals, tangents, colors, texcoords, texcoords2;
     std::vector<uint32_t> indices;
@@ -60,6 +67,7 @@ struct Scene {
     std::vector<bpt_point_light_data> point_lights;
     std::vector<bpt_rect_light_data> rect_lights;
     std::vector<float> ltc_m0, ltc_m1, ltc_m2, ltc_norm;
+    std::vector<LightTexture> light_textures;
     std::vector<float> sky_faces;     // 6 * size * size * 4
     uint32_t sky_size = 0;
     float sky_transform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};

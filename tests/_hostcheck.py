@@ -17,6 +17,10 @@ class HcBvh(C.Structure):
     _fields_ = [("n", C.c_uint32), ("root", C.c_int32), ("nodes", C.c_void_p), ("prims", C.c_void_p)]
 
 
+class HcLightTex(C.Structure):
+    _fields_ = [("chain", C.c_void_p)] + [(n, C.c_uint32) for n in ("w", "h", "levels", "addr_u", "addr_v", "linear", "mip_linear")]
+
+
 class HcScene(C.Structure):
     _fields_ = [("positions", C.c_void_p), ("normals", C.c_void_p), ("tangents", C.c_void_p), ("texcoords", C.c_void_p),
                 ("indices", C.c_void_p),
@@ -31,7 +35,8 @@ class HcScene(C.Structure):
                 ("sky_faces", C.c_void_p), ("sky_size", C.c_uint32), ("sky_transform", C.c_float * 9), ("sky_color", C.c_float * 3),
                 ("accel_mode", C.c_uint32),
                 ("blas_bvh", C.POINTER(HcBvh)), ("tlas", HcBvh),
-                ("textures", C.POINTER(capi.TextureDesc)), ("num_textures", C.c_uint32)]
+                ("textures", C.POINTER(capi.TextureDesc)), ("num_textures", C.c_uint32),
+                ("light_textures", C.POINTER(HcLightTex)), ("num_light_textures", C.c_uint32)]
 
 
 _lib = None
@@ -116,6 +121,19 @@ class HostScene:
                                        address_mode_u=t.get("address_u", 0), address_mode_v=t.get("address_v", 0), filter_linear=t.get("linear", 1))
         h.textures, h.num_textures = texs, len(scene.textures)
         self.keep.append(texs)
+        lts = getattr(scene, "light_textures", [])
+        ltex = (HcLightTex * max(1, len(lts)))()
+        for i, t in enumerate(lts):
+            chain = oracle_ctx.read_light_texture(i)                       # the oracle's generated chain (the generator is checked on the GPU)
+            self.keep.append(chain)
+            hh, ww = t["texels"].shape[:2]
+            levels, n = 0, 0
+            while n < len(chain):
+                n += max(ww >> levels, 1) * max(hh >> levels, 1); levels += 1
+            ltex[i] = HcLightTex(_p(chain), ww, hh, levels, t.get("address_u", capi.ADDRESS_CLAMP), t.get("address_v", capi.ADDRESS_CLAMP),
+                                 t.get("linear", 1), t.get("mip_linear", 0))
+        h.light_textures, h.num_light_textures = ltex, len(lts)
+        self.keep.append(ltex)
         self.scene = scene
         self.h = h
 

@@ -38,6 +38,10 @@ struct hc_scene {
     const hc_bvh* blas_bvh;        // num_blas entries (two-level) or 1 (merged)
     hc_bvh tlas;
     const bpt_texture_desc* textures; uint32_t num_textures;
+    // rect-light textures: the generated chain as RGBA32F (read back from the oracle: the generator itself is a GPU kernel, checked on the GPU),
+    // so that the SAMPLING and LTC arithmetic of the device headers runs on the host
+    struct light_tex { const float* chain; uint32_t w, h, levels, addr_u, addr_v, linear, mip_linear; };
+    const light_tex* light_textures; uint32_t num_light_textures;
 };
 
 namespace {
@@ -51,6 +55,7 @@ struct Built {
     std::vector<DBlas> blas;
     std::vector<std::vector<float4>> wide, leafbox;   // two-level mode: 4-wide form of every BLAS ([0..nb)) and of the TLAS ([nb])
     std::vector<DTexture> textures;
+    std::vector<DLightTexture> light_textures;
     std::vector<std::vector<float>> decoded;     // sRGB textures decoded to linear FP32 (as bpt_scene_upload_materials does)
     DScene sc{};
 };
@@ -140,6 +145,12 @@ void build(const hc_scene& h, Built& b) {
         b.textures[i] = DTexture{texels, t.width, t.height, fmt, t.address_mode_u, t.address_mode_v, t.filter_linear};
     }
     s.textures = b.textures.data(); s.num_textures = h.num_textures;
+    b.light_textures.resize(h.num_light_textures);
+    for (uint32_t i = 0; i < h.num_light_textures; i++) {
+        const hc_scene::light_tex& t = h.light_textures[i];
+        b.light_textures[i] = DLightTexture{reinterpret_cast<const float4*>(t.chain), t.w, t.h, t.levels, t.addr_u, t.addr_v, t.linear, t.mip_linear};
+    }
+    s.light_textures = b.light_textures.data(); s.num_light_textures = h.num_light_textures;
     s.instances = b.inst.data(); s.num_instances = h.num_instances;
     s.accel_mode = h.accel_mode;
     s.tlas_nodes = reinterpret_cast<const float4*>(h.tlas.nodes); s.tlas_prims = h.tlas.prims; s.tlas_root = h.tlas.root; s.tlas_n = h.tlas.n;

@@ -218,6 +218,68 @@ def test_atrium_full_size_bvh_and_render(lib, oracle):
     assert all(c.extend_rays_per_bounce[i] >= c.extend_rays_per_bounce[i + 1] for i in range(1, 8))
 
 
+def _tile_mask(W, H, stride, offset=0, tile=16):
+    """Pixels the oracle renders under obpt_set_tile_sample(stride, offset): every stride-th 16x16 tile in row-major tile order."""
+    tx = (W + tile - 1) // tile
+    ys, xs = np.mgrid[0:H, 0:W]
+    return ((ys // tile) * tx + xs // tile) % stride == offset
+
+
+def test_config2_full_resolution_radiance(lib, oracle):
+    """BASELINE configs[1] AT ITS OWN SIZE: the atrium at 1920x1080, depth 8, one sample of the full frame — every pixel of the CUDA
+    image equals the oracle's (one shadow ray per vertex: the FP32 sums are bit-identical), and so do the ray counts per bounce."""
+    scene = scenes.atrium()
+    W, H = 1920, 1080
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_MERGED)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=8)
+    gpu.render(cam, 7, 1, st); ref.render(cam, 7, 1, st)
+    a, b = gpu.resolve(1), ref.resolve(1)
+    assert np.isfinite(b).all() and b[..., :3].mean() > 0.01
+    np.testing.assert_array_equal(a, b)
+    ca, cb = gpu.counters(), ref.counters()
+    assert list(ca.extend_rays_per_bounce) == list(cb.extend_rays_per_bounce) and list(ca.shadow_rays_per_bounce) == list(cb.shadow_rays_per_bounce)
+    assert ca.extend_rays_per_bounce[1] == W * H
+    gpu.close(); ref.close()
+
+
+def test_config3_full_resolution_radiance_on_sampled_tiles(lib, oracle):
+    """BASELINE configs[2] at 1920x1080: 64 point/spot + 16 LTC rect lights, depth 3. The oracle renders every 8th 16x16 tile (the full
+    frame is ~50 M shadow rays per sample); on those tiles the CUDA image of the FULL frame agrees to 1e-4 (up to 80 unordered
+    shadow-ray atomics per pixel)."""
+    luts = scenes.load_ltc_luts(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ltc_luts.npz"))
+    scene = scenes.mixed_lights(luts)
+    W, H = 1920, 1080
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_MERGED)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=3)
+    ref.set_tile_sample(8, 3)
+    gpu.render(cam, 2, 1, st); ref.render(cam, 2, 1, st)
+    a, b = gpu.resolve(1), ref.resolve(1)
+    m = _tile_mask(W, H, 8, 3)
+    assert m.mean() > 0.1 and (b[m][:, :3].max(axis=1) > 0).mean() > 0.5 and not b[~m][:, :3].any()
+    err = np.abs(a[m] - b[m]) / np.maximum(np.abs(b[m]), 1e-3)
+    assert err.max() <= 1e-4, err.max()
+    gpu.close(); ref.close()
+
+
+def test_config4_full_resolution_radiance_on_sampled_tiles(lib, oracle):
+    """BASELINE configs[3] at 3840x2160: 2 M-triangle mesh x 512 instances, two-level BVH, depth 8. Every 64th tile through the oracle;
+    bit-identical radiance there (one directional light: one shadow ray per vertex)."""
+    scene = scenes.instanced()
+    W, H = 3840, 2160
+    gpu, ref = make_pair(lib, oracle, scene, W, H, capi.ACCEL_TWO_LEVEL)
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=8, ray_length=1000.0)
+    ref.set_tile_sample(64, 5)
+    gpu.render(cam, 1, 1, st); ref.render(cam, 1, 1, st)
+    a, b = gpu.resolve(1), ref.resolve(1)
+    m = _tile_mask(W, H, 64, 5)
+    assert (b[m][:, :3].max(axis=1) > 0).mean() > 0.5
+    np.testing.assert_array_equal(a[m], b[m])
+    gpu.close(); ref.close()
+
+
 def test_host_pass_accumulates_like_reference(lib, oracle):
     """PathTracingPass::render history rule (path_tracing.cpp:231-246): consecutive frames with an
     unchanged camera accumulate; a camera move resets. Image == oracle's mean of the same frames."""
@@ -311,6 +373,45 @@ def test_renderer_plugin_runs_pt_and_post_process(lib, oracle):
     with pytest.raises(KeyError):
         engine.run_renderer(gpu, scene, W, H, 1, renderer="BasicRenderer")        # only what was registered can be selected
     gpu.close(); ref.close()
+
+
+# ---- rect-light textures (lights.hlsl:425-447,495-511; mip chain: shaders/core/mipmap.hlsl) --------------------------
+@pytest.mark.parametrize("fmt", [capi.TEXTURE_RGBA8_UNORM, capi.TEXTURE_RGBA8_SRGB, capi.TEXTURE_RGBA32_FLOAT])
+def test_light_texture_mip_chain_bit_exact(lib, oracle, fmt):
+    """k_light_tex_level0 + k_mip_downsample == the oracle's chain, texel for texel (odd sizes, 1-texel-wide levels, every format)."""
+    gpu, ref = capi.Context(lib, 16, 16), oracle.OracleContext(16, 16)
+    texs = [scenes.light_texture(w, h, fmt, levels=16, seed=w) for (w, h) in ((37, 22), (64, 64), (9, 5), (1, 7), (130, 3))]
+    gpu.upload_light_textures(texs); ref.upload_light_textures(texs)
+    for k in range(len(texs)):
+        np.testing.assert_array_equal(gpu.read_light_texture(k), ref.read_light_texture(k))
+    gpu.upload_light_textures([]); ref.upload_light_textures([])            # clearing is allowed
+    gpu.close(); ref.close()
+
+
+def test_textured_rect_lights_parity(lib, oracle):
+    """Rect lights with textures (three formats, linear and nearest mip filters, two-sided and one-sided), through the whole pass."""
+    luts = scenes.load_ltc_luts(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ltc_luts.npz"))
+    scene = scenes.add_mixed_lights(scenes.small_test_scene(), 2, 4, luts, keep_dir_lights=True, light_range=12.0)
+    scene.rect_lights["two_sided"][::2] = 1
+    texs = [scenes.light_texture(37, 22, capi.TEXTURE_RGBA8_SRGB, mip_linear=1), scenes.light_texture(16, 16, capi.TEXTURE_RGBA8_UNORM, mip_linear=0, seed=8),
+            scenes.light_texture(9, 5, capi.TEXTURE_RGBA32_FLOAT, levels=3, mip_linear=1, linear=0, seed=9)]
+    plain = scenes.add_mixed_lights(scenes.small_test_scene(), 2, 4, luts, keep_dir_lights=True, light_range=12.0)
+    plain.rect_lights["two_sided"][::2] = 1
+    scenes.texture_rect_lights(scene, texs)
+    W, H = 96, 64
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=4)
+    for mode in (capi.ACCEL_MERGED, capi.ACCEL_TWO_LEVEL):
+        gpu, ref = make_pair(lib, oracle, scene, W, H, mode)
+        gpu.render(cam, 0, 2, st); ref.render(cam, 0, 2, st)
+        a, b = gpu.resolve(2), ref.resolve(2)
+        assert (np.abs(a - b) / np.maximum(np.abs(b), 1e-3)).max() <= 1e-4          # several lights per vertex: unordered shadow-ray atomics
+        gpu.close(); ref.close()
+    # the textures matter: the same lights untextured give a different image
+    gpu2 = capi.Context(lib, W, H); gpu2.upload_scene(plain, capi.ACCEL_MERGED)
+    gpu2.render(cam, 0, 2, st)
+    assert np.abs(gpu2.resolve(2) - a).max() > 0.02
+    gpu2.close()
 
 
 # ---- BASELINE configs[2]: mixed lights (64 point/spot + 16 LTC rect) ---------------------------------

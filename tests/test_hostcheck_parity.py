@@ -51,11 +51,18 @@ def _scene(name):
     if name == "mixed":
         luts = scenes.load_ltc_luts(os.path.join(GOLDEN, "ltc_luts.npz"))
         return scenes.add_mixed_lights(scenes.small_test_scene(), 5, 3, luts, keep_dir_lights=True, light_range=12.0)
+    if name == "lighttex":                       # rect lights with textures: sRGB / unorm / float chains, linear and nearest mip filters
+        luts = scenes.load_ltc_luts(os.path.join(GOLDEN, "ltc_luts.npz"))
+        sc = scenes.add_mixed_lights(scenes.small_test_scene(), 2, 4, luts, keep_dir_lights=True, light_range=12.0)
+        sc.rect_lights["two_sided"][::2] = 1
+        texs = [scenes.light_texture(37, 22, capi.TEXTURE_RGBA8_SRGB, mip_linear=1), scenes.light_texture(16, 16, capi.TEXTURE_RGBA8_UNORM, mip_linear=0, seed=8),
+                scenes.light_texture(9, 5, capi.TEXTURE_RGBA32_FLOAT, levels=3, mip_linear=1, linear=0, seed=9)]
+        return scenes.texture_rect_lights(sc, texs)
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("name,bounces", [("cornell", 5), ("small", 6), ("mixed", 3)])
+@pytest.mark.parametrize("name,bounces", [("cornell", 5), ("small", 6), ("mixed", 3), ("lighttex", 3)])
 def test_render_bit_exact(oracle, name, bounces, mode):
     scene = _scene(name)
     W, H = 40, 28
