@@ -90,6 +90,19 @@ class TextureDesc(C.Structure):
                 ("address_mode_u", C.c_uint32), ("address_mode_v", C.c_uint32), ("filter_linear", C.c_uint32)]
 
 
+class ReblurSettings(C.Structure):
+    """bpt_reblur_settings, defaults = the constants of ReblurPass::render (reblur.cpp:318-319,383)."""
+    _fields_ = [("virtual_history", C.c_uint32), ("blur_radius", C.c_float), ("anti_flickering_strength", C.c_float), ("_pad", C.c_uint32)]
+
+    def __init__(self, virtual_history=1, blur_radius=0.9, anti_flickering_strength=3.5):
+        super().__init__(virtual_history, blur_radius, anti_flickering_strength, 0)
+
+
+class ReblurInputs(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("noised", C.c_void_p), ("hit_positions", C.c_void_p), ("depth", C.c_void_p),
+                ("normal_roughness", C.c_void_p), ("velocity", C.c_void_p), ("history_validation", C.c_void_p)]
+
+
 class LightTextureDesc(C.Structure):
     """bpt_light_texture_desc: a rect-light texture (RectLightComponent::texture) and how its sampler filters it."""
     _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("levels", C.c_uint32),
@@ -196,6 +209,9 @@ COMMON_API = {
     "scene_upload_lights": [_VP, _VP, _U32, _VP, _U32, _VP, _U32, C.POINTER(LtcLuts)],
     "scene_upload_sky": [_VP, _VP, _U32, _VP, _VP],
     "scene_upload_light_textures": [_VP, C.POINTER(LightTextureDesc), _U32],
+    "denoise_reblur": [_VP, C.POINTER(Camera), _U64, C.POINTER(ReblurSettings), C.POINTER(ReblurInputs), _VP],
+    "reblur_reset": [_VP],
+    "debug_read_reblur": [_VP, _U32, _VP, _U64],
     "debug_read_light_texture": [_VP, _U32, _VP, _U64, _PU64],
     "scene_update_sky_params": [_VP, _VP, _VP],
     "build_accel": [_VP, _U32],
@@ -343,6 +359,33 @@ class Context:
             luts.matrix_lut0, luts.matrix_lut1, luts.matrix_lut2, luts.norm_lut = (_ptr(a) for a in scene.ltc_luts)
         self._call("scene_upload_lights", _ptr(scene.dir_lights), len(scene.dir_lights), _ptr(scene.point_lights),
                    len(scene.point_lights), _ptr(scene.rect_lights), len(scene.rect_lights), C.byref(luts))
+
+    def denoise_reblur(self, camera: Camera, frame_count: int, noised, hit_positions, depth, normal_roughness, velocity=None, history_validation=None,
+                       settings: "ReblurSettings | None" = None) -> np.ndarray:
+        """ReblurPass::render on one frame (bpt_denoise_reblur). noised / hit_positions: (h, w, 4) float32 at the context's extent or half of it;
+        depth (H, W), normal_roughness (H, W, 4), velocity (H, W, 2) or None, history_validation (h, w) uint8 or None. Returns (h, w, 4)."""
+        noised = np.ascontiguousarray(noised, f32); hit_positions = np.ascontiguousarray(hit_positions, f32)
+        depth = np.ascontiguousarray(depth, f32); normal_roughness = np.ascontiguousarray(normal_roughness, f32)
+        velocity = None if velocity is None else np.ascontiguousarray(velocity, f32)
+        history_validation = None if history_validation is None else np.ascontiguousarray(history_validation, np.uint8)
+        h, w = noised.shape[:2]
+        assert depth.shape == (self.height, self.width) and normal_roughness.shape == (self.height, self.width, 4) and hit_positions.shape == noised.shape
+        ins = ReblurInputs(w, h, _ptr(noised), _ptr(hit_positions), _ptr(depth), _ptr(normal_roughness), _ptr(velocity), _ptr(history_validation))
+        st = settings or ReblurSettings()
+        out = np.zeros((h, w, 4), f32)
+        self._call("denoise_reblur", C.byref(camera), frame_count, C.byref(st), C.byref(ins), _ptr(out))
+        return out
+
+    def reblur_reset(self):
+        self._call("reblur_reset")
+
+    def read_reblur(self, which: int, w: int, h: int) -> np.ndarray:
+        """Working textures of the last denoise_reblur (bpt_debug_read_reblur): 0 lighting_dist_0 + mips, 1 lighting_dist_1, 2 accumulation, 3 linear depth + mips."""
+        chain = sum((w >> l) * (h >> l) for l in range(4))
+        n = {0: chain * 4, 1: w * h * 4, 2: w * h, 3: chain}[which]
+        out = np.zeros(n, f32)
+        self._call("debug_read_reblur", which, _ptr(out), n)
+        return out
 
     def upload_light_textures(self, textures):
         """`textures`: list of dicts {texels (H, W, 4) uint8 or float32, format, levels, address_u, address_v, linear, mip_linear};

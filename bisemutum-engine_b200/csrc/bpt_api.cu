@@ -139,6 +139,12 @@ bpt_status bpt_destroy(bpt_context* c) {
     for (int k = 0; k < 2; k++) { dev_free(c->wf.ray_o[k]); dev_free(c->wf.ray_d[k]); dev_free(c->wf.ray_w[k]); }
     for (auto& t : c->d_texels) dev_free(t);
     for (auto& t : c->d_light_texels) dev_free(t);
+    {
+        ReblurState& r = c->reblur;
+        DevBuf* rb[] = {&r.ld0, &r.ld1, &r.accum, &r.lin_depth, &r.denoised, &r.hist_ld0, &r.hist_ld1, &r.hist_accum, &r.depth[0], &r.depth[1], &r.nr[0], &r.nr[1],
+                        &r.velocity, &r.validation, &r.noised, &r.hit};
+        for (DevBuf* b : rb) dev_free(*b);
+    }
     for (auto& b : c->blas) { dev_free(b.nodes); dev_free(b.tris); dev_free(b.morton); dev_free(b.prims); dev_free(b.wide); dev_free(b.leafbox); }
     for (auto& a : c->arena_chunks) dev_free(a);
     delete c;
@@ -581,6 +587,14 @@ bpt_status bpt_resolve_device_rgba16f(bpt_context* c, uint32_t total, void* d_ou
     if (!total || !d_out) return BPT_ERR_INVALID;
     return launch_resolve_rgba16f(c, total, d_out);
 }
+
+bpt_status bpt_denoise_reblur(bpt_context* c, const bpt_camera* cam, uint64_t frame_count, const bpt_reblur_settings* st, const bpt_reblur_inputs* in, float* out) {
+    NEED(c);
+    if (!cam || !st || !in || !out) return BPT_ERR_INVALID;
+    return launch_reblur(c, *cam, frame_count, *st, *in, out);
+}
+bpt_status bpt_reblur_reset(bpt_context* c) { NEED(c); return reblur_reset(c); }
+bpt_status bpt_debug_read_reblur(bpt_context* c, uint32_t which, float* out, uint64_t cap) { NEED(c); if (!out) return BPT_ERR_INVALID; return reblur_debug_read(c, which, out, cap); }
 
 bpt_status bpt_post_process_device(bpt_context* c, const bpt_post_settings* st, uint32_t total, float* d_out) {
     NEED(c);

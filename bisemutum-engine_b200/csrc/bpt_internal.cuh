@@ -44,6 +44,13 @@ struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through 
     DevBuf totals;          // uint64[40]: extend per bounce [0..15], shadow per bounce [16..31], samples [32]
 };
 
+// ReBLUR (reblur.cu): working textures, and the history the reference keeps on the camera between frames
+struct ReblurState {
+    uint32_t w = 0, h = 0, gw = 0, gh = 0;
+    bool has_history = false; uint64_t last_frame = 0; bpt_camera last_cam{}; int cur = 0;
+    DevBuf ld0, ld1, accum, lin_depth, denoised, hist_ld0, hist_ld1, hist_accum, depth[2], nr[2], velocity, validation, noised, hit;
+};
+
 struct bpt_context {
     int device = 0;
     uint32_t width = 0, height = 0;
@@ -94,6 +101,7 @@ struct bpt_context {
     bool arena_hold = false; size_t arena_held_bytes = 0;       // build_all_blas_two_level: scratch of concurrent builds is released together
 
     WavefrontState wf;
+    ReblurState reblur;
     DevBuf d_post;               // rgba16_sfloat targets of the bloom chain (post.cu)
     DevBuf d_post_out;           // staging of bpt_post_process's host read-back
     bool profile = false;
@@ -151,6 +159,10 @@ bpt_status launch_resolve_rgba16f(bpt_context* ctx, uint32_t total_samples, void
 // lighttex.cu
 bpt_status upload_light_textures(bpt_context* ctx, const bpt_light_texture_desc* textures, uint32_t num_textures);
 bpt_status read_light_texture(bpt_context* ctx, uint32_t index, float* out, uint64_t capacity_texels, uint64_t* out_texels);
+// reblur.cu
+bpt_status launch_reblur(bpt_context* ctx, const bpt_camera& cam, uint64_t frame_count, const bpt_reblur_settings& st, const bpt_reblur_inputs& in, float* h_out);
+bpt_status reblur_reset(bpt_context* ctx);
+bpt_status reblur_debug_read(bpt_context* ctx, uint32_t which, float* out, uint64_t capacity_floats);
 // ibl.cu
 bpt_status launch_precompute_sky_ibl(bpt_context* ctx, const bpt_sky_ibl_desc& desc);
 // post.cu

@@ -230,7 +230,11 @@ BPT_HD float3 sample_cube(const float4* faces, uint32_t size, float3 d) {
     int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
     const bool ox0 = x0 < 0, ox1 = x1 >= n, oy0 = y0 < 0, oy1 = y1 >= n;
     float3 a, b, c, e;
-    if ((ox0 || ox1) && (oy0 || oy1)) {                     // cube corner: the tap outside in both directions does not exist
+    if (!(ox0 || ox1 || oy0 || oy1)) {                      // the whole footprint inside the face (all but a 1-texel rim): four plain loads
+        const float4* row0 = faces + ((size_t)face * n + y0) * n + x0;
+        float4 va = BPT_LDG(row0), vb = BPT_LDG(row0 + 1), vc = BPT_LDG(row0 + n), ve = BPT_LDG(row0 + n + 1);
+        a = v3(va.x, va.y, va.z); b = v3(vb.x, vb.y, vb.z); c = v3(vc.x, vc.y, vc.z); e = v3(ve.x, ve.y, ve.z);
+    } else if ((ox0 || ox1) && (oy0 || oy1)) {                     // cube corner: the tap outside in both directions does not exist
         const int xi = ox0 ? x1 : x0, yi = oy0 ? y1 : y0;   // the in-face column / row
         const int xo = ox0 ? x0 : x1, yo = oy0 ? y0 : y1;   // the outside column / row
         float3 in_ = cube_tap(faces, n, face, xi, yi), ex = cube_tap(faces, n, face, xo, yi), ey = cube_tap(faces, n, face, xi, yo);

@@ -364,6 +364,40 @@ BPT_API bpt_status bpt_accum_device_ptr(bpt_context* ctx, float** out_device_ptr
 BPT_API bpt_status bpt_upload_accum(bpt_context* ctx, const float* sum_rgba32f);
 
 /* ---------------------------------------------------------------------------------------
+ * ReBLUR, the denoiser of the ray-traced reflections: ReblurPass::render
+ * (bisemutum/src/renderer/pass/reblur.cpp:273-588, shaders/renderer/reblur/\*.hlsl), called by ReflectionPass::render with the
+ * output of the reflection trace (reflection.cpp:529). Eight passes: pre blur, temporal accumulate (surface + virtual-position
+ * history), fetch linear depth, gen depth mip, fix history, blur, temporal stabilize, post blur. `noised` / `hit_positions` are what
+ * bpt_trace_reflection returns (camera extent, or half of it: the denoiser then runs at half resolution like the reference,
+ * reblur.cpp:280); depth (d32: 0 = background), normal_roughness (the G-buffer texture: xy = octahedral normal, w = roughness) and
+ * velocity (uv units, NULL = static) have the context's extent; history_validation (denoiser extent, NULL = all valid) is the mask of
+ * validate_history.hlsl. The history the reference keeps on the camera (last frame's depth / normal_roughness, the blurred and the
+ * stabilised image, the accumulation speed) and last frame's camera matrices are kept by the context; it is used when `frame_count`
+ * is last call's + 1 (reblur.cpp:282-285). Every texture the reference stores as rgba16_sfloat / r16_sfloat is rounded to half at
+ * the same points. out_rgba32f: the denoised image, denoiser extent. */
+typedef struct bpt_reblur_settings {
+    uint32_t virtual_history;          /* reblur.cpp:383: 1 */
+    float blur_radius;                 /* reblur.cpp:318: 0.9 */
+    float anti_flickering_strength;    /* reblur.cpp:319: 3.5 */
+    uint32_t _pad;
+} bpt_reblur_settings;
+typedef struct bpt_reblur_inputs {
+    uint32_t width, height;            /* of noised / hit_positions / history_validation / the result */
+    const float* noised;               /* rgba32f */
+    const float* hit_positions;        /* rgba32f: w = hit distance, -1 = miss / no ray */
+    const float* depth;                /* r32f, context extent */
+    const float* normal_roughness;     /* rgba32f, context extent */
+    const float* velocity;             /* rg32f, context extent, or NULL */
+    const uint8_t* history_validation; /* r8_uint, or NULL */
+} bpt_reblur_inputs;
+BPT_API bpt_status bpt_denoise_reblur(bpt_context* ctx, const bpt_camera* camera, uint64_t frame_count, const bpt_reblur_settings* settings,
+                                      const bpt_reblur_inputs* inputs, float* out_rgba32f);
+BPT_API bpt_status bpt_reblur_reset(bpt_context* ctx);      /* forgets the history (a new camera, reblur.cpp:283) */
+/* Debug: 0 = lighting_dist_0 with its 4 mip levels (level 0 = the blurred image), 1 = lighting_dist_1 (the stabilised image),
+ * 2 = accumulation, 3 = linear depth with its 4 mip levels; as float32, after the last bpt_denoise_reblur. */
+BPT_API bpt_status bpt_debug_read_reblur(bpt_context* ctx, uint32_t which, float* out, uint64_t capacity_floats);
+
+/* ---------------------------------------------------------------------------------------
  * The step after the path: PostProcessPass::render, called with the path tracer's colour
  * (bisemutum/src/renderer/basic.cpp:228-231; bisemutum/src/renderer/pass/post_process.cpp:92-273) — bloom
  * (bloom_pre.hlsl, 3 iterations of bloom_filter.hlsl at W>>1, W>>2, W>>3, bloom_combine.hlsl chain) and the output pass

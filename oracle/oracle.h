@@ -77,6 +77,10 @@ BPT_API bpt_status obpt_debug_read_queue(
 BPT_API bpt_status obpt_set_wide_from_bounce(obpt_context* ctx, uint32_t bounce);
 /* The 4-wide quantised tree of merged mode (oracle_wide.cpp = the definition csrc/bpt_wide.cuh must reproduce) and work
  * statistics of wide traversals on a ray batch: counts = {rays, wide nodes, triangles, child boxes, exact leaf boxes}. */
+BPT_API bpt_status obpt_denoise_reblur(obpt_context* ctx, const bpt_camera* camera, uint64_t frame_count, const bpt_reblur_settings* settings,
+                                       const bpt_reblur_inputs* inputs, float* out_rgba32f);
+BPT_API bpt_status obpt_reblur_reset(obpt_context* ctx);
+BPT_API bpt_status obpt_debug_read_reblur(obpt_context* ctx, uint32_t which, float* out, uint64_t capacity_floats);
 BPT_API bpt_status obpt_scene_upload_light_textures(obpt_context* ctx, const bpt_light_texture_desc* textures, uint32_t num_textures);
 BPT_API bpt_status obpt_debug_read_light_texture(obpt_context* ctx, uint32_t index, float* out_rgba32f, uint64_t capacity_texels, uint64_t* out_texels);
 BPT_API bpt_status obpt_debug_read_wide(obpt_context* ctx, float* wide_nodes, float* leaf_boxes, uint32_t capacity_leaves);
@@ -170,6 +174,7 @@ BPT_API void obpt_unit_point_light(const bpt_point_light_data* light, const floa
 BPT_API void obpt_unit_sample_sky(obpt_context* ctx, const float dir[3], float out_rgb[3]);
 BPT_API bpt_status obpt_unit_hit_vertex(obpt_context* ctx, uint32_t instance_slot, uint32_t prim, float u, float v, float out14[14]);
 BPT_API float obpt_unit_log2(float x);
+BPT_API void obpt_unit_reblur_scalars(float ndotv, float roughness, float parallax, float out6[6]);
 BPT_API float obpt_store_half(float f);
 BPT_API void obpt_gbuffer_roundtrip(const float N[3], const float T[3], const float in12[12], uint32_t model, float out18[18], uint32_t* model_out);
 BPT_API uint64_t obpt_morton63(const float c[3], const float lo[3], const float hi[3]);

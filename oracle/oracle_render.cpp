@@ -616,7 +616,7 @@ bpt_status obpt_create(const bpt_config* cfg, obpt_context** out) {
     *out = c;
     return BPT_OK;
 }
-bpt_status obpt_destroy(obpt_context* c) { delete c; return BPT_OK; }
+bpt_status obpt_destroy(obpt_context* c) { if (c) obpt_reblur_free(c); delete c; return BPT_OK; }
 const char* obpt_last_error(const obpt_context* c) { return c ? c->err.c_str() : "null context"; }
 bpt_status obpt_set_threads(obpt_context* c, uint32_t n) { CHECK_CTX(c); c->threads = n; return BPT_OK; }
 uint32_t obpt_get_threads(const obpt_context* c) { return c->threads ? c->threads : std::max(1u, std::thread::hardware_concurrency()); }

@@ -120,8 +120,12 @@ float eval_opacity(const Scene& sc, uint32_t instance_id, uint32_t prim, float u
 
 } // namespace orc
 
+struct obpt_reblur_state;            // oracle_reblur.cpp: the denoiser's per-camera history
+void obpt_reblur_free(struct obpt_context* c);
+
 struct obpt_context {
     orc::Scene scene;
+    obpt_reblur_state* reblur = nullptr;
     uint32_t width = 0, height = 0;
     uint32_t threads = 0;
     uint32_t tile_stride = 1, tile_offset = 0;

@@ -73,6 +73,8 @@ def lib():
         _lib.hc_read_wide.argtypes = [C.POINTER(HcScene), C.c_void_p, C.c_void_p]
         _lib.hc_precompute_sky_ibl.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(capi.SkyIblDesc), C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.hc_upscale_half_res.argtypes = [C.POINTER(capi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.hc_reblur.argtypes = [C.POINTER(capi.Camera), C.c_uint64, C.POINTER(capi.ReblurSettings), C.POINTER(capi.ReblurInputs), C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.hc_reblur_read.argtypes = [C.c_uint32, C.c_void_p]
         _lib.hc_post_process.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.PostSettings), C.c_void_p]
     return _lib
 
@@ -249,3 +251,35 @@ def upscale_half_res(camera, width, height, frame_index, depth, normal_roughness
     lib().hc_upscale_half_res(C.byref(camera), width, height, frame_index, d.ctypes.data_as(C.c_void_p), nr.ctypes.data_as(C.c_void_p),
                               h.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+class HostReblur:
+    """bpt_reblur.cuh's per-pixel passes on the host (hc_reblur), with the same call shape as capi.Context.denoise_reblur."""
+
+    def __init__(self, width, height):
+        self.width, self.height = width, height
+        lib().hc_reblur_reset()
+
+    def denoise_reblur(self, camera, frame_count, noised, hit_positions, depth, normal_roughness, velocity=None, history_validation=None, settings=None):
+        f32 = np.float32
+        noised = np.ascontiguousarray(noised, f32); hit_positions = np.ascontiguousarray(hit_positions, f32)
+        depth = np.ascontiguousarray(depth, f32); normal_roughness = np.ascontiguousarray(normal_roughness, f32)
+        velocity = None if velocity is None else np.ascontiguousarray(velocity, f32)
+        history_validation = None if history_validation is None else np.ascontiguousarray(history_validation, np.uint8)
+        h, w = noised.shape[:2]
+        ins = capi.ReblurInputs(w, h, _p(noised), _p(hit_positions), _p(depth), _p(normal_roughness), _p(velocity), _p(history_validation))
+        st = settings or capi.ReblurSettings()
+        out = np.zeros((h, w, 4), f32)
+        lib().hc_reblur(C.byref(camera), frame_count, C.byref(st), C.byref(ins), self.width, self.height, out.ctypes.data_as(C.c_void_p))
+        self._wh = (w, h)
+        return out
+
+    def reblur_reset(self):
+        lib().hc_reblur_reset()
+
+    def read_reblur(self, which, w, h):
+        chain = sum((w >> l) * (h >> l) for l in range(4))
+        n = {0: chain * 4, 1: w * h * 4, 2: w * h, 3: chain}[which]
+        out = np.zeros(n, np.float32)
+        lib().hc_reblur_read(which, out.ctypes.data_as(C.c_void_p))
+        return out

@@ -14,6 +14,8 @@
 #include "../../bisemutum-engine_b200/csrc/bpt_aov.cuh"
 #include "../../bisemutum-engine_b200/csrc/bpt_wide.cuh"
 #include "../../bisemutum-engine_b200/csrc/bpt_post.cuh"
+#include "../../bisemutum-engine_b200/csrc/bpt_reblur.cuh"
+#include <cmath>
 
 using namespace bptd;
 
@@ -539,5 +541,98 @@ int hc_upscale_half_res(const bpt_camera* cam, uint32_t W, uint32_t H, uint32_t 
             float* o = out + 4 * ((size_t)y * W + x);
             o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
         }
+    return 0;
+}
+
+
+// ---- ReBLUR: the per-pixel pass functions of bpt_reblur.cuh run on the host in the order launch_reblur (reblur.cu) launches them ----
+namespace {
+struct HcReblur {
+    bool has_history = false; uint64_t last_frame = 0; bpt_camera last_cam{}; uint32_t w = 0, h = 0, gw = 0, gh = 0;
+    std::vector<float4> ld0, ld1, denoised, hist_ld0, hist_ld1, nr[2], noised, hit;
+    std::vector<float> accum, lin_depth, hist_accum, depth[2];
+    std::vector<float2> velocity; std::vector<uint8_t> validation;
+    int cur = 0;
+} g_rb;
+const float kHcPre[32] = {0.840188f, 0.394383f, 0.783099f, 0.79844f, 0.911647f, 0.197551f, 0.335223f, 0.76823f, 0.277775f, 0.55397f, 0.477397f, 0.628871f, 0.364784f, 0.513401f,
+                          0.95223f, 0.916195f, 0.635712f, 0.717297f, 0.141603f, 0.606969f, 0.0163006f, 0.242887f, 0.137232f, 0.804177f, 0.156679f, 0.400944f, 0.12979f, 0.108809f,
+                          0.998924f, 0.218257f, 0.512932f, 0.839112f};
+const float kHcBlur[32] = {0.61264f, 0.296032f, 0.637552f, 0.524287f, 0.493583f, 0.972775f, 0.292517f, 0.771358f, 0.526745f, 0.769914f, 0.400229f, 0.891529f, 0.283315f, 0.352458f,
+                           0.807725f, 0.919026f, 0.0697553f, 0.949327f, 0.525995f, 0.0860558f, 0.192214f, 0.663227f, 0.890233f, 0.348893f, 0.0641713f, 0.020023f, 0.457702f,
+                           0.0630958f, 0.23828f, 0.970634f, 0.902208f, 0.85092f};
+const float kHcPost[32] = {0.266666f, 0.53976f, 0.375207f, 0.760249f, 0.512535f, 0.667724f, 0.531606f, 0.0392803f, 0.437638f, 0.931835f, 0.93081f, 0.720952f, 0.284293f, 0.738534f,
+                           0.639979f, 0.354049f, 0.687861f, 0.165974f, 0.440105f, 0.880075f, 0.829201f, 0.330337f, 0.228968f, 0.893372f, 0.35036f, 0.68667f, 0.956468f, 0.58864f,
+                           0.657304f, 0.858676f, 0.43956f, 0.92397f};
+float4 hc_rotator(float a) { float ca = std::cos(a), sa = std::sin(a); return make_float4(ca, sa, -sa, ca); }
+} // namespace
+
+extern "C" __attribute__((visibility("default"))) void hc_reblur_reset() { g_rb.has_history = false; }
+
+extern "C" __attribute__((visibility("default")))
+int hc_reblur(const bpt_camera* cam, uint64_t frame_count, const bpt_reblur_settings* st, const bpt_reblur_inputs* in, uint32_t gw, uint32_t gh, float* out) {
+    HcReblur& r = g_rb;
+    const uint32_t w = in->width, h = in->height;
+    const size_t n = (size_t)w * h, gn = (size_t)gw * gh, chain = reblur_mip_offset(w, h, 4);
+    if (r.w != w || r.h != h || r.gw != gw || r.gh != gh) { r.has_history = false; r.w = w; r.h = h; r.gw = gw; r.gh = gh; }
+    r.ld0.resize(chain); r.ld1.resize(n); r.denoised.resize(n); r.hist_ld0.resize(n); r.hist_ld1.resize(n); r.accum.resize(n); r.lin_depth.resize(chain); r.hist_accum.resize(n);
+    for (int k = 0; k < 2; k++) { r.depth[k].resize(gn); r.nr[k].resize(gn); }
+    const bool has_history = r.has_history && r.last_frame + 1 == frame_count;
+    const int cur = r.cur ^ 1;
+    memcpy(r.depth[cur].data(), in->depth, gn * 4); memcpy(r.nr[cur].data(), in->normal_roughness, gn * 16);
+    r.noised.assign(reinterpret_cast<const float4*>(in->noised), reinterpret_cast<const float4*>(in->noised) + n);
+    r.hit.assign(reinterpret_cast<const float4*>(in->hit_positions), reinterpret_cast<const float4*>(in->hit_positions) + n);
+    if (in->velocity) r.velocity.assign(reinterpret_cast<const float2*>(in->velocity), reinterpret_cast<const float2*>(in->velocity) + gn);
+    if (in->history_validation) r.validation.assign(in->history_validation, in->history_validation + n);
+    ReblurView rv{};
+    rv.w = w; rv.h = h; rv.gw = gw; rv.gh = gh; rv.half_res = w != gw ? 1u : 0u; rv.frame_index = (uint32_t)frame_count;
+    rv.has_history = has_history ? 1u : 0u; rv.virtual_history = st->virtual_history; rv.blur_radius = st->blur_radius; rv.anti_flicker = st->anti_flickering_strength;
+    rv.cam = *cam; rv.hist_cam = has_history ? r.last_cam : *cam;
+    const uint32_t ri = (uint32_t)(frame_count % 32);
+    rv.rot_pre = hc_rotator(kHcPre[ri]); rv.rot_blur = hc_rotator(kHcBlur[ri]); rv.rot_post = hc_rotator(kHcPost[ri]);
+    rv.depth = r.depth[cur].data(); rv.normal_roughness = r.nr[cur].data();
+    rv.velocity = in->velocity ? r.velocity.data() : nullptr; rv.validation = in->history_validation ? r.validation.data() : nullptr;
+    rv.hit_positions = r.hit.data(); rv.noised = r.noised.data();
+    rv.hist_depth = r.depth[cur ^ 1].data(); rv.hist_normal_roughness = r.nr[cur ^ 1].data();
+    rv.hist_ld0 = r.hist_ld0.data(); rv.hist_ld1 = r.hist_ld1.data(); rv.hist_accum = r.hist_accum.data();
+    rv.ld0 = r.ld0.data(); rv.ld1 = r.ld1.data(); rv.accum = r.accum.data(); rv.lin_depth = r.lin_depth.data(); rv.denoised = r.denoised.data();
+    auto each = [&](auto fn) { for (int y = 0; y < (int)h; y++) for (int x = 0; x < (int)w; x++) fn(rv, x, y); };
+    each(reblur_pre_blur);
+    each(reblur_temporal_accumulate);
+    each(reblur_fetch_linear_depth);
+    for (int ty = 0; ty < (int)((h + 15) / 16); ty++)                       // k_reblur_gen_depth_mip: one 64-thread group per tile
+        for (int tx = 0; tx < (int)((w + 15) / 16); tx++) {
+            float4 sv[64]; float sd[64]; int px[64], py[64];
+            for (uint32_t l = 0; l < 64; l++) { rb_mip_level1(rv, tx, ty, l, sv[l], sd[l], px[l], py[l]); rb_mip_store(rv, 1, px[l] >> 1, py[l] >> 1, sv[l], sd[l]); }
+            for (uint32_t l = 0; l < 64; l += 4) {
+                float4 vv[4] = {sv[l], sv[l + 1], sv[l + 2], sv[l + 3]}; float dd[4] = {sd[l], sd[l + 1], sd[l + 2], sd[l + 3]};
+                rb_mip_reduce(vv, dd, sv[l], sd[l]);
+                rb_mip_store(rv, 2, px[l] >> 2, py[l] >> 2, sv[l], sd[l]);
+            }
+            for (uint32_t l = 0; l < 64; l += 16) {
+                float4 vv[4] = {sv[l], sv[l + 4], sv[l + 8], sv[l + 12]}; float dd[4] = {sd[l], sd[l + 4], sd[l + 8], sd[l + 12]};
+                float4 v; float d;
+                rb_mip_reduce(vv, dd, v, d);
+                rb_mip_store(rv, 3, px[l] >> 3, py[l] >> 3, v, d);
+            }
+        }
+    each(reblur_fix_history);
+    each(reblur_blur);
+    memcpy(r.hist_ld0.data(), r.ld0.data(), n * 16); r.hist_accum = r.accum;
+    each(reblur_temporal_stabilize);
+    r.hist_ld1 = r.ld1;
+    each(reblur_post_blur);
+    memcpy(out, r.denoised.data(), n * 16);
+    r.has_history = true; r.last_frame = frame_count; r.last_cam = *cam; r.cur = cur;
+    return 0;
+}
+extern "C" __attribute__((visibility("default")))
+int hc_reblur_read(uint32_t which, float* out) {
+    HcReblur& r = g_rb;
+    const size_t n = (size_t)r.w * r.h;
+    if (which == 0) memcpy(out, r.ld0.data(), r.ld0.size() * 16);
+    else if (which == 1) memcpy(out, r.ld1.data(), n * 16);
+    else if (which == 2) memcpy(out, r.accum.data(), n * 4);
+    else if (which == 3) memcpy(out, r.lin_depth.data(), r.lin_depth.size() * 4);
+    else return -1;
     return 0;
 }
