@@ -230,6 +230,27 @@ auto PostProcessPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, In
         });
 }
 
+// reblur.cpp:273-588. The history rule (consecutive frame counts per camera, :282-285) and the history textures the reference parks
+// on the camera live inside the library's context; blur_radius / anti_flickering_strength / virtual_history are the constants of :318-319,383.
+auto ReblurPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, InputData const& input) -> gfx::TextureHandle {
+    auto denoised = rg.add_texture(textures_.width, textures_.height, 8);                  // rgba16_sfloat (:287-291)
+    struct PassData { gfx::TextureHandle noised; gfx::TextureHandle denoised; };
+    auto [builder, pass_data] = rg.add_compute_pass<PassData>("ReBLUR CUDA");
+    pass_data->noised = builder.read(input.noised_tex);
+    pass_data->denoised = builder.write(denoised);
+    builder.set_execution_function<PassData>(
+        [this, &camera](CRef<PassData>, gfx::ComputePassContext const&) {
+            bpt_camera cam;
+            std::memcpy(cam.matrix_inv_view, camera.matrix_inv_view().data(), 64);
+            std::memcpy(cam.matrix_inv_proj, camera.matrix_inv_proj().data(), 64);
+            std::memcpy(cam.matrix_proj_view, camera.matrix_proj_view().data(), 64);
+            bpt_reblur_settings st{};
+            st.virtual_history = 1; st.blur_radius = 0.9f; st.anti_flickering_strength = 3.5f;
+            status_ = out_ ? bpt_denoise_reblur(ctx_, &cam, frame_counter_, &st, &textures_, out_) : BPT_ERR_INVALID;
+        });
+    return denoised;
+}
+
 // ---- renderer level ------------------------------------------------------------------------------------------------
 auto CudaPathTracingRenderer::prepare_renderer_per_frame_data() -> void {                 // basic.cpp:31-48
     path_tracing_pass.update_params(lights_ctx, skybox_ctx, settings.path_tracing);

@@ -221,6 +221,35 @@ private:
     bpt_status status_ = BPT_OK;
 };
 
+// Drop-in for bi::ReblurPass (src/renderer/pass/reblur.hpp:9-47; render: reblur.cpp:273-588), the denoiser ReflectionPass::render calls
+// on the ray-traced reflection (reflection.cpp:529): the same InputData and render() signature; records ONE render-graph pass whose
+// lambda calls bpt_denoise_reblur (the reference records eight). The textures the handles name are the host arrays given to
+// bind_textures() — the engine-side binding hands over its own depth / G-buffer / velocity / validation / reflection images there.
+struct ReblurPass final {
+    struct InputData final {
+        gfx::TextureHandle velocity;
+        gfx::TextureHandle depth;
+        PathTracingPass::GBufferTextures gbuffer;
+        gfx::TextureHandle history_validation;
+        gfx::TextureHandle hit_positions_tex;
+        gfx::TextureHandle noised_tex;
+    };
+    explicit ReblurPass(bpt_context* ctx) : ctx_(ctx) {}
+    auto render(gfx::Camera const& camera, gfx::RenderGraph& rg, InputData const& input) -> gfx::TextureHandle;
+
+    // host images behind the handles of InputData (`width` x `height` = extent of noised_tex: the camera's, or half of it) and the result
+    auto bind_textures(bpt_reblur_inputs const& textures, float* denoised_rgba32f) -> void { textures_ = textures; out_ = denoised_rgba32f; }
+    auto set_frame_count(uint64_t f) -> void { frame_counter_ = f; }      // stands in for g_engine->window()->frame_count()
+    auto last_status() const -> bpt_status { return status_; }
+
+private:
+    bpt_context* ctx_;
+    bpt_reblur_inputs textures_{};
+    float* out_ = nullptr;
+    uint64_t frame_counter_ = 0;
+    bpt_status status_ = BPT_OK;
+};
+
 // ---- renderer level: the plugin the engine selects with `renderer = "..."` in project.toml -----------------------------
 // An IRenderer (include/bisemutum/graphics/renderer.hpp:10-23) that runs BasicRenderer's path-tracing pipeline
 // (src/renderer/basic.cpp:31-48 per frame; :157-166 and :228-231 per camera) through the two CUDA passes above. Registered and
