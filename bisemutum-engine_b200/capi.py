@@ -53,6 +53,7 @@ VA_POSITION, VA_NORMAL, VA_TANGENT, VA_COLOR, VA_TEXCOORD, VA_TEXCOORD2 = 1, 2, 
 INSTANCE_FORCE_OPAQUE, INSTANCE_FORCE_NON_OPAQUE = 4, 8
 MATERIAL_KIND_GLTF_PBR, MATERIAL_KIND_ASSIMP_DIFFUSE, MATERIAL_KIND_DEFAULT = 0, 1, 2
 MATERIAL_KIND_CONSTANT_COLOR, MATERIAL_KIND_CHECKERBOARD, MATERIAL_KIND_TEXTURED, MATERIAL_KIND_TRANSPARENT, MATERIAL_KIND_CAGE = 3, 4, 5, 6, 7
+MATERIAL_KIND_VERTEX_COLOR = 8
 SURFACE_MODEL_UNLIT, SURFACE_MODEL_LIT = 0, 1
 BLEND_OPAQUE, BLEND_ALPHA_TEST, BLEND_TRANSLUCENT = 0, 1, 2
 MATERIAL_FLAG_TWO_SIDED = 1
@@ -330,7 +331,7 @@ class Context:
         """`scene` is a scenes.SceneData. Uploads everything and builds the acceleration structure."""
         g = GeometryStreams()
         for name, arr in (("positions", scene.positions), ("normals", scene.normals), ("tangents", scene.tangents),
-                          ("colors", None), ("texcoords", scene.texcoords), ("texcoords2", None)):
+                          ("colors", getattr(scene, "colors", None)), ("texcoords", scene.texcoords), ("texcoords2", None)):
             setattr(g, name, _ptr(arr))
             field = {"positions": "num_position_floats", "normals": "num_normal_floats", "tangents": "num_tangent_floats",
                      "colors": "num_color_floats", "texcoords": "num_texcoord_floats", "texcoords2": "num_texcoord2_floats"}[name]

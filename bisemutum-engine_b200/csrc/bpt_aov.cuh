@@ -22,8 +22,8 @@ BPT_HD void primary_outputs(const DScene& sc, const bpt_camera& cam, float3 O, f
     const bpt_material& mat = sc.materials[dr.material_offset / (uint32_t)sizeof(bpt_material)];
     uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
     float3 P = O + D * hit.t;                                           // rt_gbuffer.hlsl:32
-    HitVertex hv = fetch_hit_vertex(sc, in, hit.prim, hit.u, hit.v, material_needs_position(mat));
-    Surface surf = eval_material(sc, mat, hv.texcoord, hv.position_world);
+    HitVertex hv = fetch_hit_vertex(sc, in, hit.prim, hit.u, hit.v, material_needs_position(mat), material_needs_color(mat));
+    Surface surf = eval_material(sc, mat, hv.texcoord, hv.position_world, hv.color);
     float3 nts = surf.normal_map_value * 2.0f - v3s(1.0f);              // rt_gbuffer_hit.hlsl:10-14
     float3 N = normalize3((nts.x * hv.tangent_world + nts.y * hv.bitangent_world) + nts.z * hv.normal_world);
     if (surf.two_sided && dot3(D, N) > 0.0f) N = -N;

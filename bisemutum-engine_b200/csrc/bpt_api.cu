@@ -41,7 +41,7 @@ bpt_status dev_upload(bpt_context* ctx, DevBuf& b, const void* src, size_t bytes
 DScene bpt_context::scene_view() const {
     DScene s{};
     s.positions = d_positions.as<float>(); s.normals = d_normals.as<float>(); s.tangents = d_tangents.as<float>();
-    s.texcoords = d_texcoords.as<float>(); s.indices = d_indices.as<uint32_t>();
+    s.texcoords = d_texcoords.as<float>(); s.colors = d_colors.as<float>(); s.indices = d_indices.as<uint32_t>();
     s.drawables = d_drawables.as<bpt_drawable_sbt_data>(); s.drawable_va = d_drawable_va.as<uint32_t>();
     s.materials = d_materials.as<bpt_material>();
     s.textures = d_textures.as<DTexture>(); s.num_textures = (uint32_t)d_texels.size();
@@ -130,7 +130,7 @@ bpt_status bpt_destroy(bpt_context* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     if (c->nccl_comm && c->nccl_owned) nccl().CommDestroy(c->nccl_comm);
-    DevBuf* bufs[] = {&c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
+    DevBuf* bufs[] = {&c->d_colors, &c->d_positions, &c->d_normals, &c->d_tangents, &c->d_texcoords, &c->d_indices, &c->d_drawables, &c->d_drawable_va,
                       &c->d_materials, &c->d_textures, &c->d_instances, &c->d_dir, &c->d_point, &c->d_rect, &c->d_ltc[0], &c->d_ltc[1],
                       &c->d_ltc[2], &c->d_ltc[3], &c->d_light_textures, &c->d_srgb_tables, &c->d_sky, &c->d_ddgi_irr, &c->d_ddgi_vis, &c->d_blas_table, &c->d_inst_aabb, &c->d_blas_bounds, &c->d_post, &c->d_post_out, &c->d_ibl_diffuse, &c->d_ibl_specular, &c->d_ibl_brdf, &c->wf.hit, &c->wf.hit_slot, &c->wf.sh_o,
                       &c->wf.sh_d, &c->wf.sh_c, &c->wf.accum, &c->wf.color, &c->wf.bcol, &c->wf.qcount, &c->wf.totals, &c->tlas.nodes, &c->tlas.tris, &c->tlas.morton, &c->tlas.prims,
@@ -180,13 +180,16 @@ bpt_status bpt_scene_upload_geometry(bpt_context* c, const bpt_geometry_streams*
     if ((s = dev_upload(c, c->d_normals, g->normals, g->normals ? g->num_normal_floats * 4 : 0))) return s;
     if ((s = dev_upload(c, c->d_tangents, g->tangents, g->tangents ? g->num_tangent_floats * 4 : 0))) return s;
     if ((s = dev_upload(c, c->d_texcoords, g->texcoords, g->texcoords ? g->num_texcoord_floats * 4 : 0))) return s;
+    if ((s = dev_upload(c, c->d_colors, g->colors, g->colors ? g->num_color_floats * 4 : 0))) return s;
     if ((s = dev_upload(c, c->d_indices, g->indices, g->num_indices * 4))) return s;
     c->has_normals = g->normals != nullptr; c->has_tangents = g->tangents != nullptr; c->has_texcoords = g->texcoords != nullptr;
+    c->has_colors = g->colors != nullptr;
     c->num_position_floats = g->num_position_floats; c->num_indices = g->num_indices;
     c->h_drawables.assign(dr, dr + nd);
     std::vector<uint32_t> vam(nd);
     for (uint32_t i = 0; i < nd; i++) {
-        uint32_t m = va ? va[i] : (BPT_VA_POSITION | BPT_VA_NORMAL | BPT_VA_TANGENT | BPT_VA_TEXCOORD);
+        uint32_t m = va ? va[i] : (BPT_VA_POSITION | BPT_VA_NORMAL | BPT_VA_TANGENT | BPT_VA_TEXCOORD | (g->colors ? (uint32_t)BPT_VA_COLOR : 0u));
+        if (!c->has_colors) m &= ~BPT_VA_COLOR;
         if (!c->has_normals) m &= ~BPT_VA_NORMAL;
         if (!c->has_tangents) m &= ~BPT_VA_TANGENT;
         if (!c->has_texcoords) m &= ~BPT_VA_TEXCOORD;

@@ -69,9 +69,10 @@ struct bpt_context {
     uint32_t num_dir = 0, num_point = 0, num_rect = 0;
     std::vector<uint8_t> h_dir_bytes, h_point_bytes, h_rect_bytes;   // the light arrays as last uploaded (prefetch validity, bpt_scene_upload_lights)
     uint64_t scene_generation = 0;                                    // bumped by every call that changes what a sample would see
-    bool has_normals = false, has_tangents = false, has_texcoords = false;
+    bool has_normals = false, has_tangents = false, has_texcoords = false, has_colors = false;
 
     // device scene
+    DevBuf d_colors;
     DevBuf d_positions, d_normals, d_tangents, d_texcoords, d_indices, d_drawables, d_drawable_va, d_materials;
     DevBuf d_textures; std::vector<DevBuf> d_texels;
     DevBuf d_instances;          // DInstance[]

@@ -46,7 +46,7 @@ struct DInstance {           // 128 B
 };
 
 struct DScene {
-    const float* positions; const float* normals; const float* tangents; const float* texcoords;
+    const float* positions; const float* normals; const float* tangents; const float* texcoords; const float* colors;
     const uint32_t* indices;
     const bpt_drawable_sbt_data* drawables;
     const uint32_t* drawable_va;
@@ -252,7 +252,7 @@ BPT_HD float3 sample_cube(const float4* faces, uint32_t size, float3 d) {
 BPT_HD float3 sample_sky(const DScene& sc, float3 d) { return sample_cube(sc.sky_faces, sc.sky_size, d); }
 
 // ---- vertex fetch (core/raytracing/hit.hlsl:27-164) ---------------------------------------------
-struct HitVertex { float3 normal_world, tangent_world, bitangent_world, position_world; float2 texcoord; };
+struct HitVertex { float3 normal_world, tangent_world, bitangent_world, position_world, color; float2 texcoord; };
 
 BPT_HD void load_tri_indices(const DScene& sc, const bpt_drawable_sbt_data& dr, uint32_t prim, uint32_t idx[3]) {
     const uint32_t* p = sc.indices + (size_t)dr.index_offset + 3ull * prim;
@@ -268,7 +268,7 @@ BPT_HD float2 load_texcoord(const DScene& sc, const bpt_drawable_sbt_data& dr, u
     return make_float2(bary_mix(t0.x, t1.x, t2.x, bu, bv), bary_mix(t0.y, t1.y, t2.y, bu, bv));
 }
 BPT_HD float3 load3(const float* p) { return v3(BPT_LDG(p), BPT_LDG(p + 1), BPT_LDG(p + 2)); }
-BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_t prim, float bu, float bv, bool need_position) {
+BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_t prim, float bu, float bv, bool need_position, bool need_color = false) {
     const bpt_drawable_sbt_data& dr = sc.drawables[in.instance_id];
     uint32_t va = BPT_LDG(sc.drawable_va + in.instance_id);
     uint32_t idx[3];
@@ -293,6 +293,12 @@ BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_
     hv.tangent_world = normalize3(xf_vector(in.o2w, tangent));                       // hit.hlsl:158
     hv.bitangent_world = normalize3(cross3(hv.normal_world, hv.tangent_world)) * tangent_w;   // hit.hlsl:159
     hv.texcoord = load_texcoord(sc, dr, va, idx, bu, bv);
+    hv.color = v3s(0.0f);
+    if (need_color && (va & BPT_VA_COLOR)) {                                         // hit.hlsl:97-113: color2 is read at index.x (as upstream)
+        const float* b = sc.colors + dr.color_offset;
+        float3 c0 = load3(b + 3ull * idx[0]), c1 = load3(b + 3ull * idx[1]), c2 = load3(b + 3ull * idx[0]);
+        hv.color = v3(bary_mix(c0.x, c1.x, c2.x, bu, bv), bary_mix(c0.y, c1.y, c2.y, bu, bv), bary_mix(c0.z, c1.z, c2.z, bu, bv));
+    }
     hv.position_world = v3s(0.0f);
     if (need_position) {                                                             // hit.hlsl:34-52,152
         const float* b = sc.positions + dr.position_offset;
@@ -305,7 +311,8 @@ BPT_HD HitVertex fetch_hit_vertex(const DScene& sc, const DInstance& in, uint32_
 
 // ---- material_function: closed set of the reference's HLSL snippets -----------------------------
 BPT_HD bool material_needs_position(const bpt_material& m) { return ((m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu) == BPT_MATERIAL_KIND_CHECKERBOARD; }
-BPT_HD Surface eval_material(const DScene& sc, const bpt_material& m, float2 uv, float3 position_world) {
+BPT_HD bool material_needs_color(const bpt_material& m) { return ((m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu) == BPT_MATERIAL_KIND_VERTEX_COLOR; }
+BPT_HD Surface eval_material(const DScene& sc, const bpt_material& m, float2 uv, float3 position_world, float3 vertex_color = v3s(0.0f)) {
     Surface s = surface_default();
     uint32_t kind = (m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu;
     if (kind == BPT_MATERIAL_KIND_GLTF_PBR) {                                        // import_model.cpp:208-230
@@ -344,6 +351,9 @@ BPT_HD Surface eval_material(const DScene& sc, const bpt_material& m, float2 uv,
         s.base_color = v3(m.base_color[0], m.base_color[1], m.base_color[2]);
         s.opacity = m.base_color[3];
         s.two_sided = true;
+    } else if (kind == BPT_MATERIAL_KIND_VERTEX_COLOR) {                             // surface.base_color = vertex.color
+        s.base_color = vertex_color;
+        s.roughness = m.roughness;
     } else if (kind == BPT_MATERIAL_KIND_CAGE) {                                     // .../cage.toml
         float4 v = sample_or(sc, m.base_color_tex, uv, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
         s.base_color = v3(v.x, v.y, v.z);

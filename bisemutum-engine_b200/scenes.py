@@ -35,6 +35,7 @@ class SceneData:
     instances: np.ndarray
     materials: np.ndarray
     textures: list = field(default_factory=list)
+    colors: np.ndarray | None = None      # vertex colours, 3 floats per vertex (drawable color_offset), optional
     dir_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.DIR_LIGHT))
     point_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.POINT_LIGHT))
     rect_lights: np.ndarray = field(default_factory=lambda: np.zeros(0, capi.RECT_LIGHT))

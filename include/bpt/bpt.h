@@ -153,7 +153,10 @@ enum {
                                               base_color.a = roughness_0, emission.rgb = base_color_1, roughness = roughness_1 */
     BPT_MATERIAL_KIND_TEXTURED = 5,        /* textured.toml: base_color_tex, normal_map_tex (raw texel), roughness */
     BPT_MATERIAL_KIND_TRANSPARENT = 6,     /* transparent.toml: base_color.rgb, opacity = base_color.a, two-sided */
-    BPT_MATERIAL_KIND_CAGE = 7             /* cage.toml: base = f0 = tex.rgb, opacity = tex.a < 0.5 ? 0 : 1, two-sided */
+    BPT_MATERIAL_KIND_CAGE = 7,            /* cage.toml: base = f0 = tex.rgb, opacity = tex.a < 0.5 ? 0 : 1, two-sided */
+    /* `surface.base_color = vertex.color;` — the one consumer of the vertex-colour stream (VA_TYPE_COLOR, core/raytracing/hit.hlsl:97-113).
+     * The hit shader interpolates it with its THIRD corner read at index.x instead of index.z (:108-112); reproduced. roughness = material's. */
+    BPT_MATERIAL_KIND_VERTEX_COLOR = 8
 };
 enum { BPT_SURFACE_MODEL_UNLIT = 0, BPT_SURFACE_MODEL_LIT = 1 };         /* material.hlsl:3-5 */
 enum { BPT_BLEND_OPAQUE = 0, BPT_BLEND_ALPHA_TEST = 1, BPT_BLEND_TRANSLUCENT = 2 };

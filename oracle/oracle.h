@@ -172,7 +172,7 @@ BPT_API void obpt_unit_rect_light(obpt_context* ctx, const bpt_rect_light_data* 
                                   float out_rgb[3], float diff_mrp_or_null[3]);
 BPT_API void obpt_unit_point_light(const bpt_point_light_data* light, const float P[3], float radiance[3], float dir[3], float* dist);
 BPT_API void obpt_unit_sample_sky(obpt_context* ctx, const float dir[3], float out_rgb[3]);
-BPT_API bpt_status obpt_unit_hit_vertex(obpt_context* ctx, uint32_t instance_slot, uint32_t prim, float u, float v, float out14[14]);
+BPT_API bpt_status obpt_unit_hit_vertex(obpt_context* ctx, uint32_t instance_slot, uint32_t prim, float u, float v, float out17[17]);
 BPT_API float obpt_unit_log2(float x);
 BPT_API void obpt_unit_reblur_scalars(float ndotv, float roughness, float parallax, float out6[6]);
 BPT_API float obpt_store_half(float f);

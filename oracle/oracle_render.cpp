@@ -149,7 +149,7 @@ static inline f3 ibl_lighting(const Scene& sc, f3 N, f3 V, const SurfaceData& su
 }
 
 // ---- vertex fetch: core/raytracing/hit.hlsl:27-164 ---------------------------------------------
-struct Vertex { f3 normal_world, tangent_world, bitangent_world, position_world; f2 texcoord; };
+struct Vertex { f3 normal_world, tangent_world, bitangent_world, position_world, color; f2 texcoord; };
 
 static inline void fetch_indices(const Scene& sc, const bpt_drawable_sbt_data& dr, uint32_t prim, uint32_t idx[3]) {
     for (int c = 0; c < 3; c++) idx[c] = sc.indices[(size_t)dr.index_offset + 3ull * prim + c];   // hit.hlsl:28-32
@@ -188,6 +188,13 @@ static Vertex fetch_vertex_attributes(const Scene& sc, const InstanceXf& x, uint
     vt.tangent_world = normalize(xf_vector(x.o2w, tangent));                                       // hit.hlsl:158
     vt.bitangent_world = normalize(cross(vt.normal_world, vt.tangent_world)) * tangent_w;          // hit.hlsl:159
     vt.texcoord = fetch_texcoord(sc, dr, va, idx, bu, bv);
+    vt.color = splat3(0.0f);                                                                        // hit.hlsl:96-113
+    if ((va & BPT_VA_COLOR) && !sc.colors.empty()) {
+        const float* base = &sc.colors[dr.color_offset];
+        // upstream reads the third corner's colour at index.x (hit.hlsl:108-112 repeats `index.x`), so a triangle's colour varies along one
+        // edge only; kept as is
+        vt.color = interp3(base + 3ull * idx[0], base + 3ull * idx[1], base + 3ull * idx[0], bu, bv);
+    }
     {                                                                                               // hit.hlsl:34-52,152
         const float* b = &sc.positions[dr.position_offset];
         f3 p = interp3(b + 3ull * idx[0], b + 3ull * idx[1], b + 3ull * idx[2], bu, bv);
@@ -197,7 +204,7 @@ static Vertex fetch_vertex_attributes(const Scene& sc, const InstanceXf& x, uint
 }
 
 // ---- material_function: the closed set of snippets (hit.hlsl:166-173) --------------------------
-static SurfaceData material_function(const Scene& sc, const bpt_material& m, f2 uv, f3 position_world) {
+static SurfaceData material_function(const Scene& sc, const bpt_material& m, f2 uv, f3 position_world, f3 vertex_color = f3{0.0f, 0.0f, 0.0f}) {
     SurfaceData s = surface_data_default();
     uint32_t kind = (m.flags >> BPT_MATERIAL_KIND_SHIFT) & 0xffu;
     if (kind == BPT_MATERIAL_KIND_GLTF_PBR) {                    // import_model.cpp:208-230
@@ -238,6 +245,9 @@ static SurfaceData material_function(const Scene& sc, const bpt_material& m, f2 
         s.base_color = mk3(m.base_color[0], m.base_color[1], m.base_color[2]);
         s.opacity = m.base_color[3];
         s.two_sided = true;
+    } else if (kind == BPT_MATERIAL_KIND_VERTEX_COLOR) {         // `surface.base_color = vertex.color;`
+        s.base_color = vertex_color;
+        s.roughness = m.roughness;
     } else if (kind == BPT_MATERIAL_KIND_CAGE) {                 // examples/scene_basic/materials/cage.toml
         f4 v = sample_or_default(sc, m.base_color_tex, uv, f4{1, 1, 1, 1});
         s.base_color = mk3(v.x, v.y, v.z);
@@ -429,7 +439,7 @@ static void trace_path(const obpt_context& ctx, const bpt_settings& st, bool dif
         uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
         f3 P = O + D * h.t;                                                                 // rt_gbuffer.hlsl:32
         Vertex vt = fetch_vertex_attributes(sc, x, h.prim, h.u, h.v);
-        SurfaceData surf = material_function(sc, mat, vt.texcoord, vt.position_world);
+        SurfaceData surf = material_function(sc, mat, vt.texcoord, vt.position_world, vt.color);
         f3 nts = surf.normal_map_value * 2.0f - splat3(1.0f);                               // rt_gbuffer_hit.hlsl:10-14
         f3 N = normalize((nts.x * vt.tangent_world + nts.y * vt.bitangent_world) + nts.z * vt.normal_world);
         if (surf.two_sided && dot(D, N) > 0.0f) N = -N;
@@ -640,7 +650,8 @@ bpt_status obpt_scene_upload_geometry(obpt_context* c, const bpt_geometry_stream
     sc.drawables.assign(dr, dr + nd);
     sc.drawable_va.resize(nd);
     for (uint32_t i = 0; i < nd; i++) {
-        uint32_t m = va ? va[i] : (BPT_VA_POSITION | BPT_VA_NORMAL | BPT_VA_TANGENT | BPT_VA_TEXCOORD);
+        uint32_t m = va ? va[i] : (BPT_VA_POSITION | BPT_VA_NORMAL | BPT_VA_TANGENT | BPT_VA_TEXCOORD | (s->colors ? (uint32_t)BPT_VA_COLOR : 0u));
+        if (!s->colors) m &= ~BPT_VA_COLOR;
         if (!s->normals) m &= ~BPT_VA_NORMAL;
         if (!s->tangents) m &= ~BPT_VA_TANGENT;
         if (!s->texcoords) m &= ~BPT_VA_TEXCOORD;
@@ -961,7 +972,7 @@ bpt_status obpt_render_primary(obpt_context* c, const bpt_camera* cam, uint32_t 
                 uint32_t surface_model = (mat.flags >> BPT_MATERIAL_MODEL_SHIFT) & 0xffu;
                 f3 P = O + D * h.t;
                 Vertex vt = fetch_vertex_attributes(sc, x, h.prim, h.u, h.v);
-                SurfaceData surf = material_function(sc, mat, vt.texcoord, vt.position_world);
+                SurfaceData surf = material_function(sc, mat, vt.texcoord, vt.position_world, vt.color);
                 f3 nts = surf.normal_map_value * 2.0f - splat3(1.0f);
                 f3 N = normalize((nts.x * vt.tangent_world + nts.y * vt.bitangent_world) + nts.z * vt.normal_world);
                 if (surf.two_sided && dot(D, N) > 0.0f) N = -N;
@@ -1523,13 +1534,14 @@ void obpt_unit_sample_sky(obpt_context* c, const float d[3], float out[3]) {    
     out[0] = r.x; out[1] = r.y; out[2] = r.z;
 }
 // fetch_vertex_attributes (core/raytracing/hit.hlsl:27-164) for a hit on instance slot `slot`: normal, tangent, bitangent, position, texcoord
-bpt_status obpt_unit_hit_vertex(obpt_context* c, uint32_t slot, uint32_t prim, float u, float v, float out[14]) {
+bpt_status obpt_unit_hit_vertex(obpt_context* c, uint32_t slot, uint32_t prim, float u, float v, float out[17]) {
     CHECK_CTX(c);
     if (!c->scene.accel_built || slot >= c->scene.xf.size()) return fail(c, BPT_ERR_INVALID, "unit_hit_vertex: bad slot or no accel");
     Vertex vt = fetch_vertex_attributes(c->scene, c->scene.xf[slot], prim, u, v);
     const f3 a[4] = {vt.normal_world, vt.tangent_world, vt.bitangent_world, vt.position_world};
     for (int k = 0; k < 4; k++) { out[3 * k] = a[k].x; out[3 * k + 1] = a[k].y; out[3 * k + 2] = a[k].z; }
     out[12] = vt.texcoord.x; out[13] = vt.texcoord.y;
+    out[14] = vt.color.x; out[15] = vt.color.y; out[16] = vt.color.z;
     return BPT_OK;
 }
 float obpt_unit_log2(float x) { return log2_(x); }

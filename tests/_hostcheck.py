@@ -36,7 +36,7 @@ class HcScene(C.Structure):
                 ("accel_mode", C.c_uint32),
                 ("blas_bvh", C.POINTER(HcBvh)), ("tlas", HcBvh),
                 ("textures", C.POINTER(capi.TextureDesc)), ("num_textures", C.c_uint32),
-                ("light_textures", C.POINTER(HcLightTex)), ("num_light_textures", C.c_uint32)]
+                ("light_textures", C.POINTER(HcLightTex)), ("num_light_textures", C.c_uint32), ("colors", C.c_void_p)]
 
 
 _lib = None
@@ -135,6 +135,7 @@ class HostScene:
             ltex[i] = HcLightTex(_p(chain), ww, hh, levels, t.get("address_u", capi.ADDRESS_CLAMP), t.get("address_v", capi.ADDRESS_CLAMP),
                                  t.get("linear", 1), t.get("mip_linear", 0))
         h.light_textures, h.num_light_textures = ltex, len(lts)
+        h.colors = _p(getattr(scene, "colors", None))
         self.keep.append(ltex)
         self.scene = scene
         self.h = h

@@ -44,6 +44,7 @@ struct hc_scene {
     // so that the SAMPLING and LTC arithmetic of the device headers runs on the host
     struct light_tex { const float* chain; uint32_t w, h, levels, addr_u, addr_v, linear, mip_linear; };
     const light_tex* light_textures; uint32_t num_light_textures;
+    const float* colors;           // vertex colours (may be null)
 };
 
 namespace {
@@ -153,6 +154,7 @@ void build(const hc_scene& h, Built& b) {
         b.light_textures[i] = DLightTexture{reinterpret_cast<const float4*>(t.chain), t.w, t.h, t.levels, t.addr_u, t.addr_v, t.linear, t.mip_linear};
     }
     s.light_textures = b.light_textures.data(); s.num_light_textures = h.num_light_textures;
+    s.colors = h.colors;
     s.instances = b.inst.data(); s.num_instances = h.num_instances;
     s.accel_mode = h.accel_mode;
     s.tlas_nodes = reinterpret_cast<const float4*>(h.tlas.nodes); s.tlas_prims = h.tlas.prims; s.tlas_root = h.tlas.root; s.tlas_n = h.tlas.n;

@@ -58,11 +58,21 @@ def _scene(name):
         texs = [scenes.light_texture(37, 22, capi.TEXTURE_RGBA8_SRGB, mip_linear=1), scenes.light_texture(16, 16, capi.TEXTURE_RGBA8_UNORM, mip_linear=0, seed=8),
                 scenes.light_texture(9, 5, capi.TEXTURE_RGBA32_FLOAT, levels=3, mip_linear=1, linear=0, seed=9)]
         return scenes.texture_rect_lights(sc, texs)
+    if name == "vcolor":                         # the vertex-colour stream (VA_TYPE_COLOR) through a `base_color = vertex.color` material
+        sc = scenes.small_test_scene()
+        rng = np.random.default_rng(3)
+        sc.colors = rng.uniform(0.05, 1.0, sc.positions.size).astype(np.float32)
+        sc.drawables["color_offset"] = sc.drawables["position_offset"]
+        sc.drawable_va = sc.drawable_va | capi.VA_COLOR
+        kinds = (sc.materials["flags"] >> 8) & 0xff
+        pick = np.nonzero(kinds != capi.MATERIAL_KIND_TRANSPARENT)[0][:2]
+        sc.materials["flags"][pick] = (sc.materials["flags"][pick] & ~np.uint32(0xff00)) | np.uint32(capi.MATERIAL_KIND_VERTEX_COLOR << 8)
+        return sc
     raise KeyError(name)
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("name,bounces", [("cornell", 5), ("small", 6), ("mixed", 3), ("lighttex", 3)])
+@pytest.mark.parametrize("name,bounces", [("cornell", 5), ("small", 6), ("mixed", 3), ("lighttex", 3), ("vcolor", 4)])
 def test_render_bit_exact(oracle, name, bounces, mode):
     scene = _scene(name)
     W, H = 40, 28

@@ -645,10 +645,13 @@ def test_hit_vertex_normal_is_the_inverse_transpose(oracle):
     assert abs(np.linalg.det(M)) > 0.05
     slot = 1
     sc.instances["transform"][slot][:, :3] = M.astype(np.float32); sc.instances["transform"][slot][:, 3] = (0.3, -0.2, 0.9)
+    sc.colors = rng.uniform(0, 1, sc.positions.size).astype(np.float32)          # one colour per vertex, same offsets as the positions
+    sc.drawables["color_offset"] = sc.drawables["position_offset"]
+    sc.drawable_va = sc.drawable_va | capi.VA_COLOR
     ctx = oracle.OracleContext(8, 8); ctx.upload_scene(sc, capi.ACCEL_TWO_LEVEL)
     inst = sc.instances[slot]; dr = sc.drawables[int(inst["instance_id_and_mask"]) & 0xffffff]
     M32 = inst["transform"].astype(np.float64)
-    out = np.zeros(14, np.float32)
+    out = np.zeros(17, np.float32)
     ntri = int(sc.blas[int(inst["blas"])]["num_triangles"])
     for _ in range(60):
         prim = int(rng.integers(0, ntri)); u = float(rng.uniform(0, 1)); v = float(rng.uniform(0, 1 - u))
@@ -666,6 +669,10 @@ def test_hit_vertex_normal_is_the_inverse_transpose(oracle):
         np.testing.assert_allclose(out[0:3], Nw, atol=3e-5); np.testing.assert_allclose(out[3:6], Tw, atol=3e-5)
         np.testing.assert_allclose(out[6:9], Bw, atol=3e-5); np.testing.assert_allclose(out[9:12], A @ pos + M32[:, 3], atol=3e-5)
         np.testing.assert_allclose(out[12:14], uv, atol=1e-5)
+        # vertex colour with the upstream quirk (hit.hlsl:108-112 reads the third corner at index.x): c0 + (c1 - c0) u + (c0 - c0) v
+        col = sc.colors[int(dr["color_offset"]):].reshape(-1, 3)[idx].astype(np.float64)
+        np.testing.assert_allclose(out[14:17], col[0] + (col[1] - col[0]) * u, atol=1e-6)
+        assert np.abs(out[14:17] - (col * bary[:, None]).sum(0)).max() > 1e-4 or v < 0.02          # NOT the true barycentric colour
     ctx.close()
 
 
