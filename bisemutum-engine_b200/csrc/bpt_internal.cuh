@@ -88,6 +88,7 @@ struct bpt_context {
     float sky_color[3] = {1, 1, 1};
 
     // accel
+    bool scene_has_anyhit = true;          // some instance needs the any-hit opacity rule (upload_instance_table); false selects the kernels without it
     bool accel_built = false;
     bool lbvh_small_attr_set = false;      // cudaFuncSetAttribute(k_lbvh_small, MaxDynamicSharedMemorySize) done on this context's device
     uint32_t accel_mode = 0;

@@ -110,11 +110,33 @@ BPT_HD int wrap_tc(int c, int n, uint32_t mode) {
     if (mode == BPT_ADDRESS_REPEAT) { int m = c % n; return m < 0 ? m + n : m; }
     return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
+// wrap_tc(c) and wrap_tc(c + 1) with ONE modulo (an integer % by a run-time n is ~20 instructions; a bilinear fetch needed four of them),
+// none at all for power-of-two sizes. Integer arithmetic: the same indices as two wrap_tc calls.
+BPT_HD void wrap_tc2(int c, int n, uint32_t mode, int& a, int& b) {
+    if (mode == BPT_ADDRESS_REPEAT) {
+        int m;
+        if ((n & (n - 1)) == 0) m = c & (n - 1);
+        else { m = c % n; m = m < 0 ? m + n : m; }
+        a = m; b = m + 1 == n ? 0 : m + 1;
+    } else {
+        a = c < 0 ? 0 : (c >= n ? n - 1 : c);
+        const int d = c + 1;
+        b = d < 0 ? 0 : (d >= n ? n - 1 : d);
+    }
+}
+// k / 255 for k in 0..255, correctly rounded, without an IEEE division (16 of them per bilinear RGBA8 fetch were ~160 instructions):
+// q = k * r, one Newton residual step with r = fl(1 / 255). Equal to (float)k / 255.0f for all 256 inputs (tests/test_hostcheck_parity.py
+// checks every one; the oracle keeps the division).
+BPT_HD float unorm8_to_float(uint32_t k) {
+    const float r = 1.0f / 255.0f, kf = (float)k;
+    const float q = kf * r;
+    return fmaf(fmaf(-q, 255.0f, kf), r, q);
+}
 BPT_HD float4 texel_at(const DTexture& t, int x, int y) {
     size_t i = (size_t)y * t.w + x;
     if (t.format == BPT_TEXTURE_RGBA8_UNORM) {
         uchar4 p = BPT_LDG(reinterpret_cast<const uchar4*>(t.texels) + i);
-        return make_float4((float)p.x / 255.0f, (float)p.y / 255.0f, (float)p.z / 255.0f, (float)p.w / 255.0f);
+        return make_float4(unorm8_to_float(p.x), unorm8_to_float(p.y), unorm8_to_float(p.z), unorm8_to_float(p.w));
     }
     return BPT_LDG(reinterpret_cast<const float4*>(t.texels) + i);
 }
@@ -130,8 +152,9 @@ BPT_HD float4 sample_tex(const DTexture& t, float u, float v) {
     float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
     float x0f = floorf(x), y0f = floorf(y);
     float fx = x - x0f, fy = y - y0f;
-    int x0 = wrap_tc((int)x0f, (int)t.w, t.addr_u), x1 = wrap_tc((int)x0f + 1, (int)t.w, t.addr_u);
-    int y0 = wrap_tc((int)y0f, (int)t.h, t.addr_v), y1 = wrap_tc((int)y0f + 1, (int)t.h, t.addr_v);
+    int x0, x1, y0, y1;
+    wrap_tc2((int)x0f, (int)t.w, t.addr_u, x0, x1);
+    wrap_tc2((int)y0f, (int)t.h, t.addr_v, y0, y1);
     float4 top = mix4(texel_at(t, x0, y0), texel_at(t, x1, y0), fx);
     float4 bot = mix4(texel_at(t, x0, y1), texel_at(t, x1, y1), fx);
     return mix4(top, bot, fy);

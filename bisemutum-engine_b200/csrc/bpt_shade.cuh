@@ -51,10 +51,12 @@ BPT_HD float3 accumulate_fp16(float3 image, float3 C, uint32_t n) {
 // Returns true when the path continues; (nO, nD, nW) is then the next extend ray.
 // IBL (compile time): the reflection pass's kernel evaluates the IBL block; the path tracer's kernel is compiled without it, like
 // the reference compiles its shader with DEFERRED_LIGHTING_NO_IBL (path_tracing.cpp:152).
-template <class Sink, bool IBL = false>
+// RECT / GENERAL (compile time): the path tracer's common case — no rect lights; FP32 state, no probe mode, no Russian roulette — gets a
+// kernel without the LTC evaluation and without the branches of those modes (fewer live registers: 722 -> ~130 bytes of spills at 64).
+template <class Sink, bool IBL = false, bool RECT = true, bool GENERAL = true>
 BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame_index, uint32_t bounce, uint32_t pixel,
                          float3 O, float3 D, float3 Wt, const TraceResult& hit, Sink& sink, float3& nO, float3& nD, float3& nW) {
-    const bool fp16 = sp.state_precision == BPT_STATE_REFERENCE_FP16;
+    const bool fp16 = GENERAL && sp.state_precision == BPT_STATE_REFERENCE_FP16;
     const float3 Wl = fp16 ? v3s(1.0f) : Wt;                            // weight of the light terms handed to the sink
     if (!hit.hit) {                                                     // deferred_lighting_secondary.hlsl:24-29
         const float* m = sc.sky_transform;
@@ -84,7 +86,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     }
     float3 B = cross3(N, T);
     surf.opacity = 1.0f;                                                // gbuffer.hlsl:44
-    if (sp.diffuse_only) {                                              // ddgi/deferred_lighting.hlsl:44-45
+    if (GENERAL && sp.diffuse_only) {                                   // ddgi/deferred_lighting.hlsl:44-45
         Surface d = surface_default();
         d.base_color = surf.base_color;
         surf = d;
@@ -94,13 +96,13 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
 
     LtcSetup ltc{};                                                     // the LUT side of the LTC evaluation: once per vertex, not per light
     float3 ltc_lv = v3s(0.0f);
-    if (sc.num_rect) {
+    if (RECT && sc.num_rect) {
         float rx, ry;
         aniso_roughness(surf.roughness, surf.anisotropy, rx, ry);
         ltc_lv = v3(dot3(V, T), dot3(V, B), dot3(V, N));
         if (ltc_lv.z > 0.0f) ltc = ltc_setup(sc, ltc_lv, rx, ry);
     }
-    for (uint32_t l = 0; l < sc.num_rect; l++) {                        // :72-96 (unshadowed, as the reference, unless rect_shadow)
+    for (uint32_t l = 0; RECT && l < sc.num_rect; l++) {                // :72-96 (unshadowed, as the reference, unless rect_shadow)
         const bpt_rect_light_data& rl = sc.rect_lights[l];
         float3 mrp = v3s(0.0f);
         float3 c = eval_rect_light(sc, rl, P, N, T, B, V, surf, surface_model, ltc_lv, ltc, sp.rect_shadow ? &mrp : nullptr) * Wl;
@@ -117,7 +119,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     // Probe paths only: the previous DDGI update lights the path's last vertex (ddgi/deferred_lighting.hlsl:102-115:
     // color += ddgi.xyz / ddgi.a * base_color / pi). The reference traces one bounce, so every probe-ray hit gets it; with
     // more bounces (BASELINE configs[4]) it closes the path instead of being added at every vertex.
-    if (sp.diffuse_only && sc.ddgi_enabled && bounce + 1 >= sp.max_bounces) {
+    if (GENERAL && sp.diffuse_only && sc.ddgi_enabled && bounce + 1 >= sp.max_bounces) {
         float4 g = ddgi_volume_lighting(sc.ddgi_volume, sc.ddgi_irr_size, sc.ddgi_vis_size, sc.ddgi_irradiance, sc.ddgi_visibility, P, N, V);
         if (g.w > 0.0f) sink.add(((v3(g.x / g.w, g.y / g.w, g.z / g.w) * surf.base_color) * kInvPi) * Wl);
     }
@@ -157,7 +159,7 @@ BPT_HD bool shade_vertex(const DScene& sc, const ShadeParams& sp, uint32_t frame
     if (fp16) { w2 = q_half3(w2); out_dir = q_half3(out_dir); }         // ray_weights / ray_directions are rgba16_sfloat (:66-68)
     // a zero-weight path can never contribute again (deferred_lighting_secondary.hlsl:17-21): drop it
     if (w2.x == 0.0f && w2.y == 0.0f && w2.z == 0.0f) return false;
-    if (sp.russian_roulette && bounce >= 2) {                           // third draw of this bounce's stream
+    if (GENERAL && sp.russian_roulette && bounce >= 2) {                           // third draw of this bounce's stream
         float q = clampf_(max3c(w2), 0.05f, 1.0f);
         float u3 = rng_next(seed);
         if (!(u3 < q)) return false;

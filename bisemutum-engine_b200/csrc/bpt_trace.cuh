@@ -62,7 +62,9 @@ BPT_HD bool anyhit_keep(const DScene& sc, RayState& rs, uint32_t slot, uint32_t 
 }
 
 // Möller–Trumbore on the (v0, e1, e2) record; unfused arithmetic (see bpt_math.cuh header).
-template <bool ANY>
+// AH = false: the scene has no instance that needs the any-hit rule (every material opaque or every instance force-opaque), so the
+// per-triangle flag is not even looked at and the opacity evaluation (material + texture fetches) is not compiled into the kernel.
+template <bool ANY, bool AH = true>
 BPT_HD bool test_triangle_rec(const DScene& sc, RayState& rs, float4 a, float4 b, float4 c, float3 O, float3 D, uint32_t slot_or_none, uint32_t instance_anyhit);
 template <bool ANY>
 BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, float3 O, float3 D, uint32_t slot_or_none, uint32_t instance_anyhit) {
@@ -70,7 +72,7 @@ BPT_HD bool test_triangle(const DScene& sc, RayState& rs, const float4* tri, flo
     return test_triangle_rec<ANY>(sc, rs, a, b, c, O, D, slot_or_none, instance_anyhit);
 }
 // the same test on an already fetched (v0 | prim), (e1 | slot), (e2 | any-hit flag) record
-template <bool ANY>
+template <bool ANY, bool AH>
 BPT_HD bool test_triangle_rec(const DScene& sc, RayState& rs, float4 a, float4 b, float4 c, float3 O, float3 D, uint32_t slot_or_none, uint32_t instance_anyhit) {
     float3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
     float3 pvec = cross3(D, e2);
@@ -90,8 +92,10 @@ BPT_HD bool test_triangle_rec(const DScene& sc, RayState& rs, float4 a, float4 b
     bool better = t < rs.tbest || (t == rs.tbest && (!rs.found || slot < rs.best_slot || (slot == rs.best_slot && prim < rs.best_prim)));
     if (!better) return false;
     // any-hit flag: per triangle (merged: e2.w) or per entered instance (two-level)
-    uint32_t need_anyhit = slot_or_none == 0xffffffffu ? f2u(c.w) : instance_anyhit;
-    if (need_anyhit && (rs.cull_non_opaque || !anyhit_keep(sc, rs, slot, prim, u, v))) return false;
+    if (AH) {
+        uint32_t need_anyhit = slot_or_none == 0xffffffffu ? f2u(c.w) : instance_anyhit;
+        if (need_anyhit && (rs.cull_non_opaque || !anyhit_keep(sc, rs, slot, prim, u, v))) return false;
+    }
     rs.tbest = t; rs.tcull = t * 1.00001f; rs.bu = u; rs.bv = v; rs.best_slot = slot; rs.best_prim = prim; rs.found = true;
     return true;
 }

@@ -490,6 +490,13 @@ bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d
 
 bpt_status upload_instance_table(bpt_context* ctx) {
     uint32_t n = (uint32_t)ctx->h_instances.size();
+    // the rule of k_make_instances, on the host copies (validated by bpt_build_accel): does ANY instance need the any-hit opacity rule?
+    ctx->scene_has_anyhit = false;
+    for (const bpt_instance_desc& in : ctx->h_instances) {
+        const uint32_t flags = in.sbt_offset_and_flags >> 24, id = in.instance_id_and_mask & 0xffffffu;
+        const uint32_t blend = (ctx->h_materials[ctx->h_drawables[id].material_offset / (uint32_t)sizeof(bpt_material)].flags >> BPT_MATERIAL_BLEND_SHIFT) & 0xffu;
+        if ((flags & BPT_INSTANCE_FORCE_NON_OPAQUE) && blend != BPT_BLEND_OPAQUE) { ctx->scene_has_anyhit = true; break; }
+    }
     Scratch sc(ctx);
     DevBuf desc;
     bpt_status s;

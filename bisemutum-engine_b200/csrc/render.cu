@@ -156,7 +156,8 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 // WIDE: the node phase steps through the 4-wide quantised trees (merged: a.m_wide; two-level: the TLAS's and every BLAS's own) instead
 // of the binary ones, and a proposed leaf — a triangle, or an instance of the TLAS — is taken only if the ray passes that leaf's exact
 // box (bpt_wide.cuh: same hits, about half the node fetches).
-template <bool ANY, bool TWO_LEVEL, bool WIDE = false>
+// AH = false: no instance of the scene needs the any-hit opacity rule (bpt_trace.cuh) — the usual case; the kernel then carries no material code.
+template <bool ANY, bool TWO_LEVEL, bool WIDE = false, bool AH = true>
 __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : BPT_TRACE_MIN_BLOCKS)) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
     uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_
                     float4 blo = ta, bhi = ta;
                     if (leafbox) { blo = BPT_LDG(leafbox + 2 * (size_t)j); bhi = BPT_LDG(leafbox + 2 * (size_t)j + 1); }
                     accepted = (!leafbox || leaf_box_hit_rec(blo, bhi, sp_, rs.tmin, rs.tcull)) &&
-                               test_triangle_rec<ANY>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, slot, inst_anyhit);
+                               test_triangle_rec<ANY, AH>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, slot, inst_anyhit);
                 } else if (WIDE) {                                           // leaf box and triangle fetched together: one latency, not two
                     const uint32_t j = (uint32_t)~leaf;
                     const float4* tp = tris + 3 * (size_t)j;
@@ -326,9 +327,11 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_
                     float4 blo = ta, bhi = ta;
                     if (a.m_n != 1) { blo = BPT_LDG(bp); bhi = BPT_LDG(bp + 1); }
                     accepted = (a.m_n == 1 || leaf_box_hit_rec(blo, bhi, sp_, rs.tmin, rs.tcull)) &&
-                               test_triangle_rec<ANY>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, 0xffffffffu, 0u);
+                               test_triangle_rec<ANY, AH>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, 0xffffffffu, 0u);
                 } else {
-                    accepted = test_triangle<ANY>(a.sc, rs, tris + 3 * (size_t)(uint32_t)~leaf, sp_.O, sp_.D, TWO_LEVEL ? slot : 0xffffffffu, inst_anyhit);
+                    const float4* tp = tris + 3 * (size_t)(uint32_t)~leaf;
+                    float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
+                    accepted = test_triangle_rec<ANY, AH>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, TWO_LEVEL ? slot : 0xffffffffu, inst_anyhit);
                 }
                 leaf = leaf2; leaf2 = 0;
                 if (ANY && accepted) { node = kEmpty; sp = 0; tos = kEmpty; leaf = 0; break; }
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_
     }
 }
 
-// the four instantiations (macro arguments cannot carry the template commas)
+// the instantiations (macro arguments cannot carry the template commas); *_o: scenes without any-hit instances
 static const auto k_extend_merged = k_trace_spec<false, false>;
 static const auto k_connect_merged = k_trace_spec<true, false>;
 static const auto k_extend_wide = k_trace_spec<false, false, true>;
@@ -353,6 +356,14 @@ static const auto k_extend_two_level = k_trace_spec<false, true>;
 static const auto k_connect_two_level = k_trace_spec<true, true>;
 static const auto k_extend_two_level_wide = k_trace_spec<false, true, true>;
 static const auto k_connect_two_level_wide = k_trace_spec<true, true, true>;
+static const auto k_extend_merged_o = k_trace_spec<false, false, false, false>;
+static const auto k_connect_merged_o = k_trace_spec<true, false, false, false>;
+static const auto k_extend_wide_o = k_trace_spec<false, false, true, false>;
+static const auto k_connect_wide_o = k_trace_spec<true, false, true, false>;
+static const auto k_extend_two_level_o = k_trace_spec<false, true, false, false>;
+static const auto k_connect_two_level_o = k_trace_spec<true, true, false, false>;
+static const auto k_extend_two_level_wide_o = k_trace_spec<false, true, true, false>;
+static const auto k_connect_two_level_wide_o = k_trace_spec<true, true, true, false>;
 
 // ---- shade: material + lighting + next direction, emits shadow rays and the next extend ray ---
 struct KernelSink {
@@ -377,7 +388,8 @@ struct KernelSink {
 #ifndef BPT_SHADE_MIN_BLOCKS
 #define BPT_SHADE_MIN_BLOCKS 8      // 64 registers; 6 (80) and 5 (96) measured: see DESIGN section 5
 #endif
-template <bool IBL>
+// RECT = false: the scene has no rect lights — the LTC evaluation (LUT fetches, clipping, edge integrals, light textures) is compiled out
+template <bool IBL, bool RECT = true, bool GENERAL = true>
 __global__ void __launch_bounds__(kBlock, BPT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < a.qcount[QE + bounce];
@@ -390,9 +402,9 @@ __global__ void __launch_bounds__(kBlock, BPT_SHADE_MIN_BLOCKS) k_shade(const __
         uint32_t pixel = path % a.npx + a.pixel_base, frame = a.frame_base + path / a.npx;
         TraceResult r;
         r.t = h.x; r.u = h.y; r.v = h.z; r.prim = __float_as_uint(h.w); r.slot = a.hit_slot[i]; r.hit = h.x >= 0.0f;
-        if (a.probe_mode && bounce == 1) a.color[path].w = r.t;          // hit distance of the probe ray (or -1)
+        if (GENERAL && a.probe_mode && bounce == 1) a.color[path].w = r.t;          // hit distance of the probe ray (or -1)
         KernelSink sink{a, bounce, path};
-        cont = shade_vertex<KernelSink, IBL>(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
+        cont = shade_vertex<KernelSink, IBL, RECT, GENERAL>(a.sc, a.sp, frame, bounce, pixel, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), v3(w.x, w.y, w.z), r, sink, nO, nD, nW);
     }
     // next-ray queue: ballot per warp, ONE atomicAdd per block (all threads of the block reach this point)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -440,6 +452,11 @@ __global__ void __launch_bounds__(kBlock, BPT_SHADE_MIN_BLOCKS) k_shade(const __
         a.ray_w_out[slot] = make_float4(nW.x, nW.y, nW.z, 0.0f);
     }
 }
+
+static const auto k_shade_ibl = k_shade<true, true>;
+static const auto k_shade_rect = k_shade<false, true>;
+static const auto k_shade_norect = k_shade<false, false>;
+static const auto k_shade_plain = k_shade<false, false, false>;
 
 // ---- reference_fp16 only: end of a bounce. colour = half(bounce sum * throughput), written (bounce 1) or added with a
 //      half result (deferred_lighting_secondary.hlsl:110 + the additive blit, path_tracing.cpp:441-459) --------------
@@ -852,20 +869,24 @@ static bool use_wide2(const bpt_context* ctx, uint32_t bounce = 99, bool connect
     if (!enabled || bounce < (connect ? connect_from : from_bounce) || ctx->accel_mode != BPT_ACCEL_TWO_LEVEL) return false;
     return ctx->tlas.n <= 1 || ctx->tlas.wide.p != nullptr;      // (every BLAS with two or more triangles has its wide form, bvh_build.cu)
 }
+// BPT_SPECIALISE=0 launches the general kernels everywhere (A/B measurements)
+static bool specialise_opaque() { static const bool on = [] { const char* e = getenv("BPT_SPECIALISE"); return !e || atoi(e) != 0; }(); return on; }
 static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     WavefrontState& wf = ctx->wf;
-    if (use_wide2(ctx, i)) LAUNCH_T(ctx, 1, k_extend_two_level_wide, wf.grid_extend_w2, kBlock, a, i);
-    else if (use_wide(ctx, i)) LAUNCH_T(ctx, 1, k_extend_wide, wf.grid_extend_w, kBlock, a, i);
-    else if (ctx->accel_mode == BPT_ACCEL_MERGED) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i);
-    else LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i);
+    const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
+    if (use_wide2(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_two_level_wide, wf.grid_extend_w2, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_two_level_wide_o, wf.grid_extend_w2, kBlock, a, i); }
+    else if (use_wide(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_wide, wf.grid_extend_w, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_wide_o, wf.grid_extend_w, kBlock, a, i); }
+    else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_merged_o, wf.grid_extend_m, kBlock, a, i); }
+    else { if (ah) LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_two_level_o, wf.grid_extend, kBlock, a, i); }
     return BPT_OK;
 }
 static bpt_status launch_connect(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     WavefrontState& wf = ctx->wf;
-    if (use_wide2(ctx, i, true)) LAUNCH_T(ctx, 3, k_connect_two_level_wide, wf.grid_connect_w2, kBlock, a, i);
-    else if (use_wide(ctx, i, true)) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i);
-    else if (ctx->accel_mode == BPT_ACCEL_MERGED) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i);
-    else LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i);
+    const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
+    if (use_wide2(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_two_level_wide, wf.grid_connect_w2, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_two_level_wide_o, wf.grid_connect_w2, kBlock, a, i); }
+    else if (use_wide(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_wide_o, wf.grid_connect_w, kBlock, a, i); }
+    else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_merged_o, wf.grid_connect_m, kBlock, a, i); }
+    else { if (ah) LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_two_level_o, wf.grid_connect, kBlock, a, i); }
     return BPT_OK;
 }
 
@@ -884,8 +905,10 @@ static bpt_status run_bounces(bpt_context* ctx, RenderArgs& a, const bpt_setting
         }
         {
             NvtxRange r("PT Lighting + Sample Ray #%u", i);
-            if (a.sp.ibl) LAUNCH_T(ctx, 2, k_shade<true>, grid_paths, kBlock, a, i);      // ray-traced reflections with settings.ibl
-            else LAUNCH_T(ctx, 2, k_shade<false>, grid_paths, kBlock, a, i);
+            if (a.sp.ibl) LAUNCH_T(ctx, 2, k_shade_ibl, grid_paths, kBlock, a, i);      // ray-traced reflections with settings.ibl
+            else if (ctx->num_rect || !specialise_opaque()) LAUNCH_T(ctx, 2, k_shade_rect, grid_paths, kBlock, a, i);
+            else if (a.probe_mode || a.sp.diffuse_only || a.sp.russian_roulette || a.sp.state_precision != BPT_STATE_FP32) LAUNCH_T(ctx, 2, k_shade_norect, grid_paths, kBlock, a, i);
+            else LAUNCH_T(ctx, 2, k_shade_plain, grid_paths, kBlock, a, i);
         }
         if (st.nee_mode == BPT_NEE_SHADOW_RAY && (ctx->num_dir + ctx->num_point + (st.rect_shadow ? ctx->num_rect : 0)) > 0) {
             NvtxRange r("PT Lighting #%u (shadow rays)", i);

@@ -638,3 +638,8 @@ int hc_reblur_read(uint32_t which, float* out) {
     else return -1;
     return 0;
 }
+
+// exhaustive check hooks for the exact-arithmetic shortcuts of bpt_scene.cuh
+extern "C" __attribute__((visibility("default"))) float hc_unorm8_to_float(uint32_t k) { return unorm8_to_float(k); }
+extern "C" __attribute__((visibility("default"))) void hc_wrap_tc2(int c, int n, uint32_t mode, int* a, int* b) { wrap_tc2(c, n, mode, *a, *b); }
+extern "C" __attribute__((visibility("default"))) int hc_wrap_tc(int c, int n, uint32_t mode) { return wrap_tc(c, n, mode); }

@@ -448,3 +448,21 @@ def test_reference_example_scene_bit_exact(oracle, mode):
     ref = ctx.resolve(1)
     np.testing.assert_array_equal(HC.HostScene(scene, ctx, mode).render(cam, W, H, 0, 2, st)[..., :3], ref[..., :3])
     assert ref[..., :3].mean() > 0.05
+
+
+def test_exact_shortcuts_of_the_texture_fetch():
+    """csrc/bpt_scene.cuh: unorm8_to_float(k) == (float)k / 255 for every k (two FMAs instead of an IEEE division); wrap_tc2 == two wrap_tc
+    calls for every address mode, size (power of two or not) and coordinate, including far negative ones."""
+    import ctypes as C
+    H = HC.lib()
+    H.hc_unorm8_to_float.argtypes, H.hc_unorm8_to_float.restype = [C.c_uint32], C.c_float
+    H.hc_wrap_tc.argtypes, H.hc_wrap_tc.restype = [C.c_int, C.c_int, C.c_uint32], C.c_int
+    H.hc_wrap_tc2.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for k in range(256):
+        assert np.float32(H.hc_unorm8_to_float(k)) == np.float32(k) / np.float32(255.0), k
+    a, b = C.c_int(), C.c_int()
+    for mode in (capi.ADDRESS_REPEAT, capi.ADDRESS_CLAMP):
+        for n in (1, 2, 3, 5, 8, 16, 37, 64, 100, 256):
+            for c in list(range(-3 * n - 2, 3 * n + 3)) + [-100000, 99999, -(1 << 30), (1 << 30) - 1]:
+                H.hc_wrap_tc2(c, n, mode, C.byref(a), C.byref(b))
+                assert (a.value, b.value) == (H.hc_wrap_tc(c, n, mode), H.hc_wrap_tc(c + 1, n, mode)), (mode, n, c)
