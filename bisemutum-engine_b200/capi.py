@@ -243,6 +243,7 @@ COMMON_API = {
 # Exported by the CUDA library only.
 BPT_ONLY_API = {
     "set_stream": [_VP, _VP],
+    "set_wave_budget": [_VP, _U64],
     "sync": [_VP],
     "resolve_device": [_VP, _U32, _VP],
     "resolve_device_rgba16f": [_VP, _U32, _VP],
@@ -626,6 +627,10 @@ class Context:
 
     def resolve_device(self, total_samples: int, device_ptr: int):
         self._call("resolve_device", total_samples, _VP(device_ptr))
+
+    def set_wave_budget(self, max_paths_in_flight: int):
+        """Caps the wavefront footprint: paths in flight per wave (bpt_set_wave_budget; 0 = default 2^26)."""
+        self._call("set_wave_budget", max_paths_in_flight)
 
     def resolve_device_rgba16f(self, total_samples: int, device_ptr: int):
         """The resolved image as rgba16_sfloat (the reference's OutputData.color format), 8 bytes per pixel, device memory."""

@@ -170,6 +170,14 @@ bpt_status bpt_resize(bpt_context* c, uint32_t w, uint32_t h) {
     return wavefront_alloc(c);
 }
 
+bpt_status bpt_set_wave_budget(bpt_context* c, uint64_t max_paths) {
+    NEED(c);
+    BPT_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->wave_paths_budget = max_paths;
+    invalidate_ahead(c);
+    return wavefront_alloc(c);
+}
+
 bpt_status bpt_scene_upload_geometry(bpt_context* c, const bpt_geometry_streams* g, const bpt_drawable_sbt_data* dr, const uint32_t* va,
                                      uint32_t nd, const bpt_blas_desc* blas, uint32_t nb) {
     NEED(c);

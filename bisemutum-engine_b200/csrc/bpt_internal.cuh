@@ -58,6 +58,7 @@ struct bpt_context {
     std::string err;
     uint64_t launches = 0;
     void* nccl_comm = nullptr; bool nccl_owned = false;   // bpt_comm_init / bpt_comm_attach (NCCL is dlopen'ed, see bpt_api.cu)
+    uint64_t wave_paths_budget = 0;   // bpt_set_wave_budget: paths in flight per wave (0 = default 2^26)
     bool accum_used = false;    // a render has added to wf.accum since the last bpt_clear_accum
 
     // host copies needed for validation / rebuilds

@@ -126,7 +126,7 @@ BPT_HD void wrap_tc2(int c, int n, uint32_t mode, int& a, int& b) {
 }
 // k / 255 for k in 0..255, correctly rounded, without an IEEE division (16 of them per bilinear RGBA8 fetch were ~160 instructions):
 // q = k * r, one Newton residual step with r = fl(1 / 255). Equal to (float)k / 255.0f for all 256 inputs (tests/test_hostcheck_parity.py
-// checks every one; the oracle keeps the division).
+// checks every one against the division).
 BPT_HD float unorm8_to_float(uint32_t k) {
     const float r = 1.0f / 255.0f, kf = (float)k;
     const float q = kf * r;

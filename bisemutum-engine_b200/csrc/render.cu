@@ -726,7 +726,8 @@ static uint32_t wave_slots(const bpt_context* ctx) {
     // per sample: every late, nearly empty bounce has a ~150 us latency floor that more samples per wave amortise);
     // BPT_WAVE_PATHS_LOG2 overrides for tuning
     static const int log2_paths = [] { const char* e = getenv("BPT_WAVE_PATHS_LOG2"); int v = e ? atoi(e) : 26; return v < 16 ? 16 : (v > 30 ? 30 : v); }();
-    uint64_t by_paths = std::max<uint64_t>(1, (1ull << log2_paths) / npx);
+    const uint64_t budget = ctx->wave_paths_budget ? ctx->wave_paths_budget : (1ull << log2_paths);     // bpt_set_wave_budget: the host's cap on the footprint
+    uint64_t by_paths = std::max<uint64_t>(1, budget / npx);
     uint64_t by_shadow = std::max<uint64_t>(1, (8ull << 30) / (npx * nl * 48));    // <= 8 GiB of shadow-ray records
     return (uint32_t)std::min<uint64_t>(std::min(by_paths, by_shadow), 64);
 }

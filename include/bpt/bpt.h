@@ -64,6 +64,11 @@ typedef struct bpt_config {
 
 BPT_API bpt_status bpt_create(const bpt_config* cfg, bpt_context** out_ctx);
 BPT_API bpt_status bpt_destroy(bpt_context* ctx);
+/* Footprint control for a pass that shares the GPU with an engine. A render call keeps `samples per wave` = min(64, max_paths / pixels,
+ * 8 GiB / (pixels * lights * 48 B)) samples of every pixel in flight; the wavefront state is ~132 B per path plus 48 B per path and light
+ * for the shadow-ray queue (default max_paths = 2^26: 32 samples and ~9 GB at 1080p; 2^23 = 4 samples, ~1.1 GB, about 15 % slower —
+ * DESIGN.md section 5). 0 restores the default. Re-allocates the wave buffers and drops samples traced ahead. */
+BPT_API bpt_status bpt_set_wave_budget(bpt_context* ctx, uint64_t max_paths_in_flight);
 BPT_API const char* bpt_last_error(const bpt_context* ctx);
 BPT_API const char* bpt_version(void);
 /* All later work is enqueued on `cuda_stream` (a cudaStream_t; NULL = legacy default stream). */

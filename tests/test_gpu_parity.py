@@ -358,6 +358,24 @@ def test_scene_change_invalidates_prefetched_samples(lib, oracle):
     r.close(); ref.close()
 
 
+def test_wave_budget_changes_the_footprint_not_the_image(lib, oracle):
+    """bpt_set_wave_budget: fewer samples in flight per wave (a smaller footprint for a pass that shares the GPU) — the accumulated image is
+    the same bit for bit, because samples are folded into the sum in frame order whatever the wave size."""
+    scene = scenes.small_test_scene()
+    W, H = 64, 48
+    cam = engine.camera_matrices(scene.camera, W, H)
+    st = capi.Settings(max_bounces=4)
+    imgs = []
+    for budget in (0, W * H * 3, 1):                       # default (64 samples per wave here), 3 samples per wave, 1 sample per wave
+        gpu = capi.Context(lib, W, H); gpu.upload_scene(scene, capi.ACCEL_MERGED)
+        gpu.set_wave_budget(budget)
+        gpu.render(cam, 0, 7, st)
+        imgs.append(gpu.resolve(7)); gpu.close()
+    np.testing.assert_array_equal(imgs[0], imgs[1]); np.testing.assert_array_equal(imgs[0], imgs[2])
+    ref = oracle.OracleContext(W, H); ref.upload_scene(scene, capi.ACCEL_MERGED); ref.render(cam, 0, 7, st)
+    np.testing.assert_array_equal(imgs[0], ref.resolve(7)); ref.close()
+
+
 def test_renderer_plugin_runs_pt_and_post_process(lib, oracle):
     """The plugin level: an IRenderer registered by name and selected like `renderer = "..."` in project.toml runs
     BasicRenderer's path-tracing pipeline — update_params per frame, PathTracingPass::render + PostProcessPass::render per camera
