@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cuda_runtime.h>
 #include <string>
+#include <utility>
 #include <vector>
 #include "bpt_scene.cuh"
 
@@ -30,7 +31,7 @@ struct WavefrontState {     // per-path SoA, two ray buffers (ping-pong through 
     uint32_t npx = 0, slots = 1;
     DevBuf color;           // float4 per path: per-sample colour C_s
     uint32_t ahead_slots = 0, ahead_cursor = 0, ahead_frame_first = 0;   // prefetched samples still in `color`
-    unsigned grid_extend = 0, grid_connect = 0, grid_extend_m = 0, grid_connect_m = 0, grid_extend_w = 0, grid_connect_w = 0, grid_extend_w2 = 0, grid_connect_w2 = 0;   // resident grid sizes of the persistent traversal kernels
+    std::vector<std::pair<const void*, unsigned>> grids;   // resident grid size per persistent traversal kernel (render.cu: resident_grid)
     DevBuf ray_o[2], ray_d[2], ray_w[2];   // float4 each: (O|pixel), (D|-), (W|-)
     DevBuf hit;             // float4 (t,u,v,prim)
     DevBuf hit_slot;        // uint32

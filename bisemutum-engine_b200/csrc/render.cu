@@ -46,8 +46,17 @@ constexpr int QN = 128;
 #define BPT_SORT_OCTANT 0
 #endif
 constexpr int kSmemStack = BPT_SMEM_STACK;             // stack entries per lane kept in shared memory (0: the whole stack in local memory)
-constexpr int kMinNodeLanes = BPT_MIN_NODE_LANES;       // node phase ends when fewer lanes than this still have an internal node
-constexpr int kRefillThreshold = BPT_REFILL;            // refill a warp's finished lanes when fewer rays than this are still in flight
+// Two-level mode has its own pair (instanced 2 M x 512 scene, ms per 4K sample: (4, 12) 43.7, (8, 12) 40.2, (12, 16) 38.9, (16, 20) 37.9 ...:
+// leaving the node phase earlier keeps more lanes together through the instance entries)
+#ifndef BPT_MIN_NODE_LANES_2L
+#define BPT_MIN_NODE_LANES_2L 16
+#endif
+#ifndef BPT_REFILL_2L
+#define BPT_REFILL_2L 20
+#endif
+constexpr int kMinNodeLanes1 = BPT_MIN_NODE_LANES;      // node phase ends when fewer lanes than this still have an internal node
+constexpr int kRefillThreshold1 = BPT_REFILL;           // refill a warp's finished lanes when fewer rays than this are still in flight
+constexpr int kMinNodeLanes2 = BPT_MIN_NODE_LANES_2L, kRefillThreshold2 = BPT_REFILL_2L;
 
 struct RenderArgs {
     DScene sc;
@@ -150,6 +159,9 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 #ifndef BPT_TRACE_MIN_BLOCKS
 #define BPT_TRACE_MIN_BLOCKS 10
 #endif
+#ifndef BPT_TRACE_MIN_BLOCKS_2L
+#define BPT_TRACE_MIN_BLOCKS_2L 8       // two-level kernels of scenes without any-hit instances (the general ones stay at 8: see above)
+#endif
 #ifndef BPT_TRACE_MIN_BLOCKS_WIDE
 #define BPT_TRACE_MIN_BLOCKS_WIDE 10
 #endif
@@ -158,7 +170,7 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 // box (bpt_wide.cuh: same hits, about half the node fetches).
 // AH = false: no instance of the scene needs the any-hit opacity rule (bpt_trace.cuh) — the usual case; the kernel then carries no material code.
 template <bool ANY, bool TWO_LEVEL, bool WIDE = false, bool AH = true>
-__global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : BPT_TRACE_MIN_BLOCKS)) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+__global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BLOCKS_2L) : (WIDE ? BPT_TRACE_MIN_BLOCKS_WIDE : BPT_TRACE_MIN_BLOCKS)) k_trace_spec(const __grid_constant__ RenderArgs a, uint32_t bounce) {
     const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
     uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
     const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
@@ -168,6 +180,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? 8 : (WIDE ? BPT_TRACE_MIN_
     const float4* __restrict__ tris = TWO_LEVEL ? nullptr : a.m_tris;
     const float4* __restrict__ leafbox = nullptr;       // TWO_LEVEL && WIDE: exact leaf boxes of the BLAS being traversed (nullptr: single-leaf BLAS)
     const uint32_t lane = threadIdx.x & 31;
+    constexpr int kMinNodeLanes = TWO_LEVEL ? kMinNodeLanes2 : kMinNodeLanes1, kRefillThreshold = TWO_LEVEL ? kRefillThreshold2 : kRefillThreshold1;
     // Short stack in shared memory (north star): the BOTTOM kSmemStack entries of every lane's stack live in shared memory as
     // [entry][thread] (one bank per lane: conflict-free whatever the lanes' depths are), deeper entries in local memory. A push or pop
     // at depth d touches exactly one of the two, so the local-memory traffic that is left is the accesses at depth >= kSmemStack.
@@ -827,23 +840,6 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
     a.contrib = st.state_precision == BPT_STATE_REFERENCE_FP16 ? wf.bcol.as<float4>() : a.color;
     a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
     a.pixel_base = 0; a.probe_mode = 0; a.cull_non_opaque = 0;
-    if (!wf.grid_extend) {      // resident grids of the persistent traversal kernels: SMs x blocks that fit per SM
-        int dev = 0, sms = 0, be = 0, ba = 0;
-        BPT_CUDA_TRY(ctx, cudaGetDevice(&dev));
-        BPT_CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, true>, kBlock, 0));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, true>, kBlock, 0));
-        wf.grid_extend = (unsigned)(sms * std::max(be, 1)); wf.grid_connect = (unsigned)(sms * std::max(ba, 1));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, false>, kBlock, 0));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, false>, kBlock, 0));
-        wf.grid_extend_m = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_m = (unsigned)(sms * std::max(ba, 1));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, false, true>, kBlock, 0));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, false, true>, kBlock, 0));
-        wf.grid_extend_w = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_w = (unsigned)(sms * std::max(ba, 1));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&be, k_trace_spec<false, true, true>, kBlock, 0));
-        BPT_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ba, k_trace_spec<true, true, true>, kBlock, 0));
-        wf.grid_extend_w2 = (unsigned)(sms * std::max(be, 1)); wf.grid_connect_w2 = (unsigned)(sms * std::max(ba, 1));
-    }
     if (ctx->accel_mode == BPT_ACCEL_MERGED) {
         a.m_nodes = ctx->blas[0].nodes.as<float4>(); a.m_tris = ctx->blas[0].tris.as<float4>(); a.m_root = ctx->blas[0].root; a.m_n = ctx->blas[0].n;
         a.m_wide = ctx->blas[0].wide.as<float4>(); a.m_leafbox = ctx->blas[0].leafbox.as<float4>();
@@ -870,24 +866,35 @@ static bool use_wide2(const bpt_context* ctx, uint32_t bounce = 99, bool connect
     if (!enabled || bounce < (connect ? connect_from : from_bounce) || ctx->accel_mode != BPT_ACCEL_TWO_LEVEL) return false;
     return ctx->tlas.n <= 1 || ctx->tlas.wide.p != nullptr;      // (every BLAS with two or more triangles has its wide form, bvh_build.cu)
 }
+// Resident grid of a persistent traversal kernel: SMs x the blocks of that very instantiation that fit on one (queried once per kernel).
+template <class K>
+static unsigned resident_grid(bpt_context* ctx, K kernel) {
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (auto& e : ctx->wf.grids) if (e.first == key) return e.second;
+    int dev = 0, sms = 148, blocks = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kBlock, 0) != cudaSuccess) { blocks = 8; (void)cudaGetLastError(); }
+    const unsigned g = (unsigned)(sms * std::max(blocks, 1));
+    ctx->wf.grids.emplace_back(key, g);
+    return g;
+}
 // BPT_SPECIALISE=0 launches the general kernels everywhere (A/B measurements)
 static bool specialise_opaque() { static const bool on = [] { const char* e = getenv("BPT_SPECIALISE"); return !e || atoi(e) != 0; }(); return on; }
 static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
-    WavefrontState& wf = ctx->wf;
     const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
-    if (use_wide2(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_two_level_wide, wf.grid_extend_w2, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_two_level_wide_o, wf.grid_extend_w2, kBlock, a, i); }
-    else if (use_wide(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_wide, wf.grid_extend_w, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_wide_o, wf.grid_extend_w, kBlock, a, i); }
-    else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 1, k_extend_merged, wf.grid_extend_m, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_merged_o, wf.grid_extend_m, kBlock, a, i); }
-    else { if (ah) LAUNCH_T(ctx, 1, k_extend_two_level, wf.grid_extend, kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_two_level_o, wf.grid_extend, kBlock, a, i); }
+    if (use_wide2(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_two_level_wide, resident_grid(ctx, k_extend_two_level_wide), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_two_level_wide_o, resident_grid(ctx, k_extend_two_level_wide_o), kBlock, a, i); }
+    else if (use_wide(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_wide, resident_grid(ctx, k_extend_wide), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_wide_o, resident_grid(ctx, k_extend_wide_o), kBlock, a, i); }
+    else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 1, k_extend_merged, resident_grid(ctx, k_extend_merged), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_merged_o, resident_grid(ctx, k_extend_merged_o), kBlock, a, i); }
+    else { if (ah) LAUNCH_T(ctx, 1, k_extend_two_level, resident_grid(ctx, k_extend_two_level), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_two_level_o, resident_grid(ctx, k_extend_two_level_o), kBlock, a, i); }
     return BPT_OK;
 }
 static bpt_status launch_connect(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
-    WavefrontState& wf = ctx->wf;
     const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
-    if (use_wide2(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_two_level_wide, wf.grid_connect_w2, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_two_level_wide_o, wf.grid_connect_w2, kBlock, a, i); }
-    else if (use_wide(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_wide, wf.grid_connect_w, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_wide_o, wf.grid_connect_w, kBlock, a, i); }
-    else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 3, k_connect_merged, wf.grid_connect_m, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_merged_o, wf.grid_connect_m, kBlock, a, i); }
-    else { if (ah) LAUNCH_T(ctx, 3, k_connect_two_level, wf.grid_connect, kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_two_level_o, wf.grid_connect, kBlock, a, i); }
+    if (use_wide2(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_two_level_wide, resident_grid(ctx, k_connect_two_level_wide), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_two_level_wide_o, resident_grid(ctx, k_connect_two_level_wide_o), kBlock, a, i); }
+    else if (use_wide(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_wide, resident_grid(ctx, k_connect_wide), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_wide_o, resident_grid(ctx, k_connect_wide_o), kBlock, a, i); }
+    else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 3, k_connect_merged, resident_grid(ctx, k_connect_merged), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_merged_o, resident_grid(ctx, k_connect_merged_o), kBlock, a, i); }
+    else { if (ah) LAUNCH_T(ctx, 3, k_connect_two_level, resident_grid(ctx, k_connect_two_level), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_two_level_o, resident_grid(ctx, k_connect_two_level_o), kBlock, a, i); }
     return BPT_OK;
 }
 

@@ -16,19 +16,28 @@ ap.add_argument("--spp", type=int, default=64)
 ap.add_argument("--accel", default="merged")
 ap.add_argument("--tag", default="")
 ap.add_argument("--lib", default="", help="experimental libbpt variant (tools/build_variant.sh)")
+ap.add_argument("--config", default="atrium", choices=["atrium", "instanced", "mixed"])
 args = ap.parse_args()
 
 lib = capi.Library(os.path.abspath(args.lib), "bpt_", capi.BPT_ONLY_API) if args.lib else pkg.load_library()
 W, H, B = 1920, 1080, 8
-scene = scenes.atrium()
+RAY_LENGTH = 100.0
+if args.config == "instanced":
+    W, H, RAY_LENGTH = 3840, 2160, 1000.0
+    scene = scenes.instanced(); args.accel = "two_level"
+elif args.config == "mixed":
+    B = 3
+    scene = scenes.mixed_lights(scenes.load_ltc_luts(os.path.join(pkg.REPO_ROOT, "tests", "golden", "ltc_luts.npz")))
+else:
+    scene = scenes.atrium()
 mode = capi.ACCEL_MERGED if args.accel == "merged" else capi.ACCEL_TWO_LEVEL
 ctx = capi.Context(lib, W, H)
 stream = torch.cuda.current_stream()
 ctx.set_stream(stream.cuda_stream)
 ctx.upload_scene(scene, mode)
 cam = engine.camera_matrices(scene.camera, W, H)
-st = capi.Settings(ray_length=100.0, max_bounces=B)
-ctx.render(cam, 10_000, 16, st); ctx.sync(); ctx.reset_counters()
+st = capi.Settings(ray_length=RAY_LENGTH, max_bounces=B)
+ctx.render(cam, 10_000, 16 if args.config == "atrium" else 8, st); ctx.sync(); ctx.reset_counters()
 best = 1e30
 for rep in range(3):
     ctx.reset_counters()
@@ -36,12 +45,13 @@ for rep in range(3):
     e0.record(stream); ctx.render(cam, 0, args.spp, st); e1.record(stream); torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 c = ctx.counters()
+PS = 16 if args.config == "atrium" else 8
 ctx.profile_enable(True)
-ctx.render(cam, 0, 16, st)
+ctx.render(cam, 0, PS, st)
 kt = ctx.profile_read()
 ctx.profile_enable(False)
-out = {"tag": args.tag, "ms_per_spp": best / args.spp, "mrays_per_s": (c.extend_rays + c.shadow_rays) / best / 1e3}
+out = {"tag": args.tag, "config": args.config, "ms_per_spp": best / args.spp, "mrays_per_s": (c.extend_rays + c.shadow_rays) / best / 1e3}
 for f, _ in kt._fields_:
     v = getattr(kt, f)
-    out[f] = (v / 16) if isinstance(v, float) else v
+    out[f] = (v / PS) if isinstance(v, float) else v
 print(json.dumps(out))
