@@ -78,4 +78,38 @@ for mode in (capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED):
     ctx.render(cam, 0, 2, capi.Settings(max_bounces=3))
     assert np.isfinite(ctx.post_process(capi.PostSettings(True, 0.2, 1.0), 2)).all()
     ctx.close()
+# round 2: textured rect lights (level-0 decode + mip kernels, three formats), the specialised kernels' counterparts (a scene with and one without
+# any-hit instances / rect lights ran above), vertex colours, the rgba16f resolve, a small wave budget, ReBLUR at full and half resolution
+import torch
+tl = scenes.add_mixed_lights(scenes.small_test_scene(), 1, 3, luts, keep_dir_lights=True, light_range=12.0)
+scenes.texture_rect_lights(tl, [scenes.light_texture(37, 22, capi.TEXTURE_RGBA8_SRGB), scenes.light_texture(16, 16, capi.TEXTURE_RGBA8_UNORM, mip_linear=0),
+                                scenes.light_texture(9, 5, capi.TEXTURE_RGBA32_FLOAT, levels=3, linear=0)])
+tl.colors = np.random.default_rng(1).uniform(0, 1, tl.positions.size).astype(np.float32)
+tl.drawables["color_offset"] = tl.drawables["position_offset"]; tl.drawable_va = tl.drawable_va | capi.VA_COLOR
+tl.materials["flags"][0] = (tl.materials["flags"][0] & ~np.uint32(0xff00)) | np.uint32(capi.MATERIAL_KIND_VERTEX_COLOR << 8)
+for mode in (capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED):
+    ctx = capi.Context(lib, W, H); ctx.upload_scene(tl, mode)
+    ctx.set_wave_budget(W * H * 2)
+    cam = engine.camera_matrices(tl.camera, W, H)
+    ctx.render(cam, 0, 5, capi.Settings(max_bounces=4))
+    half = torch.empty(H, W, 4, dtype=torch.float16, device="cuda")
+    ctx.resolve_device_rgba16f(5, half.data_ptr()); ctx.sync()
+    assert torch.isfinite(half).all()
+    for k in range(3):
+        ctx.read_light_texture(k)
+    ctx.upload_light_textures([])
+    ctx.close()
+sb = scenes.scene_basic(os.path.join(pkg.REPO_ROOT, "tests", "golden", "scene_basic.npz"))
+ctx = capi.Context(lib, W, H); ctx.upload_scene(sb, capi.ACCEL_MERGED)
+cam = engine.camera_matrices(sb.camera, W, H)
+for half_res in (False, True):
+    ctx.reblur_reset()
+    for k in range(3):
+        depth, g = ctx.render_primary(cam, k, capi.Settings(max_bounces=4))
+        refl, hitp = ctx.trace_reflection(cam, k, depth, g, capi.ReflectionSettings(16.0, 1.0, 1.0, 0.6, half_res))
+        vel = np.full((H, W, 2), 0.003, np.float32) if k == 2 else None
+        mask = (np.random.default_rng(k).uniform(size=refl.shape[:2]) < 0.1).astype(np.uint8) if k == 2 else None
+        out = ctx.denoise_reblur(cam, k, refl, hitp, depth, np.ascontiguousarray(g["normal_roughness"]), vel, mask)
+        assert np.isfinite(out).all()
+ctx.close()
 print("sanitize smoke ok")
