@@ -42,6 +42,11 @@ constexpr int QN = 128;
 #ifndef BPT_SMEM_STACK
 #define BPT_SMEM_STACK 0
 #endif
+// Two-level mode: 1 = a lane that reaches a TLAS leaf PARKS there until the node phase ends; all parked lanes then enter their instances together
+// (instance record fetch, ray transform, three IEEE divisions of make_space: ~100 instructions that otherwise ran at ~2 active lanes)
+#ifndef BPT_PARK_INSTANCES
+#define BPT_PARK_INSTANCES 1
+#endif
 #ifndef BPT_SORT_OCTANT
 #define BPT_SORT_OCTANT 0
 #endif
@@ -205,32 +210,42 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
     bool in_blas = !TWO_LEVEL;
     bool exhausted = false;
 
-    // Brings `node` into a state the node phase understands: enters instances, leaves them when allowed.
+    constexpr bool PARK = TWO_LEVEL && (BPT_PARK_INSTANCES != 0);
+    float3 widir = v3s(0.0f);                           // 1 / D of the world-space ray (PARK: leaving an instance restores the ray space without dividing again)
+    // a TLAS leaf the lane stands on (two-level mode): an instance to enter
+    auto at_instance = [&]() { return TWO_LEVEL && node < 0 && node != kSentinel && !in_blas; };
+    // node is a triangle leaf of the tree being traversed
+    auto at_triangle = [&]() { return node < 0 && node != kSentinel && (!TWO_LEVEL || in_blas); };
+    // Enters the instance of the TLAS leaf `node` (or skips it when only a quantised box proposed it): the object-space ray, a sentinel on the stack.
+    auto enter_instance = [&]() {
+        if (WIDE && a.sc.tlas_n != 1 && !leaf_box_hit(a.sc.tlas_leafbox, (uint32_t)~node, sp_, rs.tmin, rs.tcull)) {
+            node = pop();                              // the binary TLAS would not have reached it
+            return;
+        }
+        slot = __ldg(a.sc.tlas_prims + (uint32_t)~node);
+        const DInstance& in = a.sc.instances[slot];
+        const DBlas bl = a.sc.blas[in.blas];
+        inst_anyhit = in.anyhit;
+        sp_ = make_space(xf_point(in.w2o, rs.O), xf_vector(in.w2o, rs.D));
+        nodes = WIDE ? bl.wide : bl.nodes; tris = bl.tris; in_blas = true;
+        if (WIDE) leafbox = bl.leafbox;
+        push(kSentinel);
+        node = bl.root;
+    };
+    // Brings `node` into a state the node phase understands: leaves instances when allowed; enters them at once (PARK = false) or leaves the
+    // lane parked on the TLAS leaf for the entry phase (PARK = true).
     auto settle = [&]() {
         if (!TWO_LEVEL) return;
         for (;;) {
             if (node == kSentinel) {
                 if (leaf != 0) return;                 // postponed triangles of this instance first
-                sp_ = make_space(rs.O, rs.D); nodes = tlas_nodes; tris = nullptr; in_blas = false;
+                if (PARK) { sp_.O = rs.O; sp_.D = rs.D; sp_.idir = widir; sp_.ood = rs.O * widir; }      // = make_space(rs.O, rs.D), bit for bit
+                else sp_ = make_space(rs.O, rs.D);
+                nodes = tlas_nodes; tris = nullptr; in_blas = false;
                 node = pop();
                 continue;
             }
-            if (node < 0 && !in_blas) {                // TLAS leaf: enter the instance
-                if (WIDE && a.sc.tlas_n != 1 && !leaf_box_hit(a.sc.tlas_leafbox, (uint32_t)~node, sp_, rs.tmin, rs.tcull)) {
-                    node = pop();                      // only proposed by a quantised box: the binary TLAS would not have reached it
-                    continue;
-                }
-                slot = __ldg(a.sc.tlas_prims + (uint32_t)~node);
-                const DInstance& in = a.sc.instances[slot];
-                const DBlas bl = a.sc.blas[in.blas];
-                inst_anyhit = in.anyhit;
-                sp_ = make_space(xf_point(in.w2o, rs.O), xf_vector(in.w2o, rs.D));
-                nodes = WIDE ? bl.wide : bl.nodes; tris = bl.tris; in_blas = true;
-                if (WIDE) leafbox = bl.leafbox;
-                push(kSentinel);
-                node = bl.root;
-                continue;
-            }
+            if (!PARK && at_instance()) { enter_instance(); continue; }
             return;
         }
     };
@@ -267,6 +282,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                         rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu; rs.bu = 0.0f; rs.bv = 0.0f;
                         rs.frame_index = a.frame_base + path / a.npx; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
                         sp_ = make_space(rs.O, rs.D);
+                        widir = sp_.idir;
                         sp = 0; tos = kEmpty; leaf = 0; leaf2 = 0;
                         if (TWO_LEVEL) {
                             nodes = tlas_nodes; tris = nullptr; in_blas = false; slot = 0xffffffffu;
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                         } else {
                             node = a.m_n == 0 ? kEmpty : a.m_root;
                         }
-                        if (node < 0 && node != kSentinel) { leaf = node; node = pop(); settle(); }   // root is a leaf
+                        if (at_triangle()) { leaf = node; node = pop(); settle(); }   // root is a leaf
                     }
                 }
                 if (base + (uint32_t)__popc(mask) >= n) exhausted = true;  // warp-uniform
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     if (next == BPT_POP) next = pop();
                     node = next;
                     settle();
-                    if (node < 0 && node != kSentinel && leaf2 == 0) {    // a triangle: postpone, keep descending
+                    if (at_triangle() && leaf2 == 0) {                    // a triangle: postpone, keep descending
                         if (leaf == 0) leaf = node; else leaf2 = node;
 #ifdef BPT_PREFETCH_TRI
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(tris + 3 * (size_t)(uint32_t)~node));
@@ -320,6 +336,22 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                 // leave the node phase when nobody is still looking for a first leaf, or when too few lanes have node
                 // work left (the others idle with postponed leaves or finished rays): test triangles / refill instead
                 if (searching == 0 || __popc(can_work) < kMinNodeLanes) break;
+            }
+            // ---- instance-entry phase (two-level, PARK): every lane parked on a TLAS leaf enters its instance now, together ----
+            if (PARK) {
+                const bool parked = at_instance();
+                if (__ballot_sync(0xffffffffu, parked) != 0u) {
+                    if (parked) {
+                        enter_instance();
+                        settle();                                        // (a skipped instance may have popped a sentinel)
+                        if (at_triangle() && leaf2 == 0) {               // a single-triangle BLAS, or a triangle popped after a skip
+                            if (leaf == 0) leaf = node; else leaf2 = node;
+                            node = pop();
+                            settle();
+                        }
+                    }
+                    continue;                                            // back to the node phase: the entered lanes are searching again
+                }
             }
             // ---- triangle phase ----
             while (leaf != 0) {
@@ -350,7 +382,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                 if (ANY && accepted) { node = kEmpty; sp = 0; tos = kEmpty; leaf = 0; break; }
                 if (leaf == 0) {
                     settle();                                            // a sentinel that was waiting for the triangles
-                    if (node < 0 && node != kSentinel) { leaf = node; node = pop(); settle(); }
+                    if (at_triangle()) { leaf = node; node = pop(); settle(); }
                 }
             }
             uint32_t alive = __ballot_sync(0xffffffffu, node != kEmpty);

@@ -5,6 +5,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
+import torch   # first: its bundled NCCL must be the one in the process before libbpt dlopen()s "libnccl.so.2" (bpt_comm_init below)
 
 import bisemutum_engine_b200 as pkg
 from bisemutum_engine_b200 import capi, engine, scenes
@@ -80,7 +81,6 @@ for mode in (capi.ACCEL_TWO_LEVEL, capi.ACCEL_MERGED):
     ctx.close()
 # round 2: textured rect lights (level-0 decode + mip kernels, three formats), the specialised kernels' counterparts (a scene with and one without
 # any-hit instances / rect lights ran above), vertex colours, the rgba16f resolve, a small wave budget, ReBLUR at full and half resolution
-import torch
 tl = scenes.add_mixed_lights(scenes.small_test_scene(), 1, 3, luts, keep_dir_lights=True, light_range=12.0)
 scenes.texture_rect_lights(tl, [scenes.light_texture(37, 22, capi.TEXTURE_RGBA8_SRGB), scenes.light_texture(16, 16, capi.TEXTURE_RGBA8_UNORM, mip_linear=0),
                                 scenes.light_texture(9, 5, capi.TEXTURE_RGBA32_FLOAT, levels=3, linear=0)])
