@@ -284,10 +284,8 @@ def main():
     lib = pkg.load_library()
     # frames per rank: weak = K each; strong = the K-frame job split (the first K % N ranks take one more)
     if args.scaling == "strong":
-        base, extra = divmod(args.steps, world)
-        my_steps = base + (1 if rank < extra else 0)
-        my_first = rank * base + min(rank, extra)
-        if base == 0:
+        my_first, my_steps = sharding.split_frames(args.steps, rank, world)
+        if args.steps < world:
             raise SystemExit("bench.py: --scaling strong needs --steps >= --gpus")
     else:
         my_steps, my_first = args.steps, sharding.first_frame(args.steps, rank, world)

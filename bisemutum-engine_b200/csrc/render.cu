@@ -52,12 +52,13 @@ constexpr int QN = 128;
 #endif
 constexpr int kSmemStack = BPT_SMEM_STACK;             // stack entries per lane kept in shared memory (0: the whole stack in local memory)
 // Two-level mode has its own pair (instanced 2 M x 512 scene, ms per 4K sample: (4, 12) 43.7, (8, 12) 40.2, (12, 16) 38.9, (16, 20) 37.9 ...:
-// leaving the node phase earlier keeps more lanes together through the instance entries)
+// leaving the node phase earlier keeps more lanes together through the instance entries; with the parked instance entries (BPT_PARK_INSTANCES):
+// (8, 12) 38.6, (12, 16) 36.5, (16, 20) 35.3, (16, 24) 35.0, (20, 24) 35.0, (24, 28) 35.5)
 #ifndef BPT_MIN_NODE_LANES_2L
 #define BPT_MIN_NODE_LANES_2L 16
 #endif
 #ifndef BPT_REFILL_2L
-#define BPT_REFILL_2L 20
+#define BPT_REFILL_2L 24
 #endif
 constexpr int kMinNodeLanes1 = BPT_MIN_NODE_LANES;      // node phase ends when fewer lanes than this still have an internal node
 constexpr int kRefillThreshold1 = BPT_REFILL;           // refill a warp's finished lanes when fewer rays than this are still in flight

@@ -16,6 +16,14 @@ def first_frame(steps: int, rank: int, world: int, first: int = 0) -> int:
     return first + rank * steps
 
 
+def split_frames(total_frames: int, rank: int, world: int, first: int = 0) -> tuple[int, int]:
+    """Strong scaling: ONE job of `total_frames` samples split over the ranks in contiguous blocks — (first frame, count) of `rank`; the
+    first `total_frames % world` ranks take one frame more. The blocks tile [first, first + total_frames) exactly, so the reduced sum
+    buffer is the single-GPU buffer of the same job (up to FP32 association across ranks)."""
+    base, extra = divmod(total_frames, world)
+    return first + rank * base + min(rank, extra), base + (1 if rank < extra else 0)
+
+
 def frame_index(step: int, steps: int, rank: int, world: int, first: int = 0) -> int:
     """frame_index of the `step`-th frame this rank renders."""
     return first_frame(steps, rank, world, first) + step

@@ -51,6 +51,17 @@ def test_two_rank_sharding_equals_single_process(oracle, tmp_path):
     np.testing.assert_allclose(img, ref, rtol=1e-5, atol=1e-7)
 
 
+def test_strong_scaling_split_tiles_the_job():
+    """sharding.split_frames (bench.py --scaling strong; BASELINE configs[3]: 64 spp split across 8 GPUs): contiguous blocks that tile the job."""
+    from bisemutum_engine_b200 import sharding
+    for total in (8, 20, 64, 67, 256):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [sharding.split_frames(total, r, world, first=5) for r in range(world)]
+            frames = [f for first, n in blocks for f in range(first, first + n)]
+            assert frames == list(range(5, 5 + total))
+            assert max(n for _, n in blocks) - min(n for _, n in blocks) <= 1
+
+
 # ---- DDGI update sharded by probe index + all-gather of the per-ray results (SURVEY §8e) -------------------------------------
 PROBES, RAYS = (3, 2, 3), 16
 
