@@ -320,19 +320,27 @@ def main():
     sampler.start()
     ev0.record(stream)
     ctx.render(cam, my_first, my_steps, st)         # the rank's frames of 1 spp each
+    ev_mid = torch.cuda.Event(enable_timing=True)
+    ev_mid.record(stream)
     if world > 1:   # the one exchange step: FP32 sum buffers → rank 0 (one NCCL reduce per batch of frames, issued by the library)
         ctx.reduce(0)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    render_ms, exchange_ms = ev0.elapsed_time(ev_mid), ev_mid.elapsed_time(ev1)      # this rank's own split of the timed region
     c = ctx.counters()
     launches = c.kernel_launches
-    stats = torch.tensor([ms, float(c.extend_rays), float(c.shadow_rays), float(c.samples)], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([ms, float(c.extend_rays), float(c.shadow_rays), float(c.samples), render_ms, exchange_ms], dtype=torch.float64, device="cuda")
+    timed_split = None
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mn = stats.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms = float(mx[0]); ext, shd, samples = float(sm[1]), float(sm[2]), float(sm[3])
+        # where the timed region went: the slowest and fastest rank's render time, and the exchange as each rank saw it (a rank that finishes
+        # rendering early waits inside the reduce for the slowest one, so max exchange = skew + the collective itself)
+        timed_split = {"render_ms_max": float(mx[4]), "render_ms_min": float(mn[4]), "exchange_ms_max": float(mx[5]), "exchange_ms_min": float(mn[5])}
     else:
         ext, shd, samples = float(c.extend_rays), float(c.shadow_rays), float(c.samples)
     assert samples == float(total_steps) * npx, (samples, total_steps, npx)          # every counted sample was traced inside the timed region
@@ -567,6 +575,8 @@ def main():
     }
     if reduce_check is not None:
         out["reduce_check"] = reduce_check
+    if timed_split is not None:
+        out["timed_region_split"] = timed_split
     if e2e is not None and args.scaling == "weak":
         # an end-to-end step contains the device step: it cannot be faster (2 % allowance for run-to-run noise); reported, not asserted,
         # so that a noisy box still yields a line
