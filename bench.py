@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--accel", default="", choices=["", "merged", "two_level"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-waves", default="", help="e2e arm: explicit wave schedule, e.g. 14,6 (must add up to the steps of a rank); default: tapered")
     ap.add_argument("--device-only", action="store_true", help="only the device-resident timed loop (for ncu captures)")
     ap.add_argument("--cpu-tile-stride", type=int, default=0, help="oracle sample: every n-th 16x16 tile (0 = auto)")
     a = ap.parse_args()
@@ -397,7 +398,7 @@ def main():
     # format of the reference's OutputData.color (rgba16_sfloat, path_tracing.cpp:248-252) and read back to pinned host memory —
     # on rank 0 only when N > 1: the other ranks' partial sums are not a result; the job's result is the ONE reduce at the end,
     # read back in FP32 on rank 0. Everything the timed frames consume is traced inside the timed region: the history is reset after
-    # the warm-up frames (which drops their prefetched samples) and the step count is a whole number of waves.
+    # the warm-up frames (which drops their prefetched samples) and the waves of the timed frames add up to the step count exactly.
     def run_e2e(n_steps):
         r = engine.Renderer(W, H, device=local_rank)
         r.ctx.set_stream(stream.cuda_stream)
@@ -406,9 +407,20 @@ def main():
             sharding.comm_init(r.ctx, torch.device("cuda", local_rank))
             r.ctx.reduce(0); r.ctx.sync()
         wave = max(1, min(32, (1 << 26) // npx))        # what the library traces per wave at this resolution (render.cu: wave_slots)
-        prefetch = min(wave, n_steps)
-        e2e_steps = (n_steps // prefetch) * prefetch   # whole waves, so traced samples == consumed frames
-        r.set_prefetch(prefetch)
+        # Wave schedule of a FINITE job. The frames of a wave become available together when its last bounce ends, and their images then
+        # leave over PCIe one after the other (0.30 ms each at 1080p) while the NEXT wave is traced; only the last wave's read-back has
+        # nothing to hide behind. So the application (which knows the job's length; the pass does not) asks for waves that shrink towards
+        # the end — each 4/5 of what is left, at most the library's wave — instead of one full wave whose read-back is all tail.
+        # Every sample is still traced inside the timed region and consumed by exactly one frame (asserted below).
+        schedule, left = [], n_steps
+        while left > 0:
+            schedule.append(min(wave, max(1, -(-4 * left // 5))))
+            left -= schedule[-1]
+        if args.e2e_waves and sum(int(x) for x in args.e2e_waves.split(",")) == n_steps:
+            schedule = [int(x) for x in args.e2e_waves.split(",")]
+        e2e_steps = n_steps
+        prefetch = max(schedule)
+        r.set_prefetch(schedule[0])
         job_steps = torch.tensor([float(e2e_steps)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(job_steps, op=dist.ReduceOp.SUM)
@@ -431,34 +443,76 @@ def main():
         final_dev = torch.empty(H, W, 4, dtype=torch.float32, device="cuda") if reads else None
         copy_stream = torch.cuda.Stream()
         done = [None] * ring
+        if reads and os.environ.get("BENCH_E2E_PRETOUCH", "1") == "1":
+            # an application reuses its result buffers from job to job: map them for DMA once, outside the timed region (the first copy
+            # into a freshly pinned 33 MB buffer was measured at 8-30 GB/s instead of 55)
+            final_host.copy_(final_dev, non_blocking=True)
+            for hb, db in zip(host_imgs, dev_imgs):
+                hb.copy_(db, non_blocking=True)
+            torch.cuda.synchronize()
+        trace = os.environ.get("BENCH_E2E_TRACE") == "1" and reads     # diagnostic: where the timed region goes (GPU events + host clock per frame)
+        tr_ready, tr_done, tr_host = [], [], []
         barrier()
         t0 = time.perf_counter()
+        if trace:
+            tr_start = torch.cuda.Event(enable_timing=True); tr_start.record(stream)
         n = 0
+        wave_i, wave_left = 0, 0
         for i in range(e2e_steps):
+            if wave_left == 0:                              # this frame finds no sample traced ahead: the pass traces the next wave now
+                r.set_prefetch(schedule[wave_i])
+                wave_left = schedule[wave_i]; wave_i += 1
+            wave_left -= 1
             r.ctx.upload_lights(lights)                     # PathTracingPass::update_params: per-frame H2D of the light arrays
-            n = r.frame(args.ray_length, B, True)           # Camera::update_shader_params + PathTracingPass::render + RenderGraph::execute
             if reads:
                 b = i % ring
                 if done[b] is not None:
                     done[b].synchronize()                   # the host buffer of frame i - ring has landed
-                r.ctx.resolve_device_rgba16f(n, dev_imgs[b].data_ptr())     # OutputData.color of this frame ...
-                ready = torch.cuda.Event(); ready.record(stream)
+                r.set_color_target(dev_imgs[b].data_ptr())  # the device memory behind this frame's OutputData.color
+            n = r.frame(args.ray_length, B, True)           # Camera::update_shader_params + PathTracingPass::render + RenderGraph::execute
+            if reads:                                       # OutputData.color of this frame (written by the pass) ...
+                ready = torch.cuda.Event(enable_timing=trace); ready.record(stream)
                 with torch.cuda.stream(copy_stream):        # ... read back to pinned host memory while the next frames render
                     copy_stream.wait_event(ready)
                     host_imgs[b].copy_(dev_imgs[b], non_blocking=True)
-                    done[b] = torch.cuda.Event(); done[b].record(copy_stream)
+                    done[b] = torch.cuda.Event(enable_timing=trace); done[b].record(copy_stream)
+                if trace:
+                    tr_ready.append(ready); tr_done.append(done[b]); tr_host.append((time.perf_counter() - t0) * 1e3)
         assert n == e2e_steps, (n, e2e_steps)
         if world > 1:
             r.ctx.reduce(0)                                 # the job's one exchange: every rank's sums -> rank 0
         if reads:
             r.ctx.resolve_device(job_steps, final_dev.data_ptr())
-            final_host.copy_(final_dev, non_blocking=True)  # the job's result, FP32, on the host
+            if trace:
+                tr_res = torch.cuda.Event(enable_timing=True); tr_res.record(stream)
+            if os.environ.get("BENCH_E2E_FINAL_ON_COPY_STREAM") == "1":
+                fin = torch.cuda.Event(); fin.record(stream)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(fin)
+                    final_host.copy_(final_dev, non_blocking=True)
+                    fdone = torch.cuda.Event(); fdone.record(copy_stream)
+                stream.wait_event(fdone)
+            else:
+                final_host.copy_(final_dev, non_blocking=True)  # the job's result, FP32, on the host
+        if trace:
+            tr_end = torch.cuda.Event(enable_timing=True); tr_end.record(stream); th0 = (time.perf_counter() - t0) * 1e3
         for ev in done:
             if ev is not None:
                 ev.synchronize()
+        if trace:
+            th1 = (time.perf_counter() - t0) * 1e3
         stream.synchronize()
+        if trace:
+            th2 = (time.perf_counter() - t0) * 1e3
         barrier()
         dt = time.perf_counter() - t0
+        if trace:
+            sys.stderr.write("e2e tail: host after issue %.3f, after copy events %.3f, after stream sync %.3f, after barrier %.3f; GPU end of the FP32 resolve %.3f, of the FP32 copy %.3f\n"
+                             % (th0, th1, th2, dt * 1e3, tr_start.elapsed_time(tr_res), tr_start.elapsed_time(tr_end)))
+        if trace:
+            sys.stderr.write("e2e trace (ms since start): total %.3f\n" % (dt * 1e3))
+            for i in range(len(tr_ready)):
+                sys.stderr.write("  frame %3d host-issued %.3f resolved %.3f copied %.3f\n" % (i, tr_host[i], tr_start.elapsed_time(tr_ready[i]), tr_start.elapsed_time(tr_done[i])))
         ec = r.ctx.counters()
         assert ec.samples == e2e_steps * npx, (ec.samples, e2e_steps, npx)       # traced inside the timed region == consumed
         erays = torch.tensor([float(ec.extend_rays + ec.shadow_rays), dt, float(ec.samples)], dtype=torch.float64, device="cuda")
@@ -477,7 +531,7 @@ def main():
         h2d = lights_bytes + 3 * 64 + 32                    # light arrays (pinned) + camera matrices + settings (kernel parameters)
         d2h = npx * 8 + npx * 16 / e2e_steps                # per frame rgba16f + the FP32 result once per job
         e2e = {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e2e_steps, "job_steps": job_steps, "ms_per_step": e_dt / e2e_steps * 1e3, "mpix_spp_per_s": e_samples / e_dt / 1e6, "samples_per_wave": prefetch,
+               "steps": e2e_steps, "job_steps": job_steps, "ms_per_step": e_dt / e2e_steps * 1e3, "mpix_spp_per_s": e_samples / e_dt / 1e6, "samples_per_wave": prefetch, "wave_schedule": schedule,
                "result_format": "per frame: rgba16_sfloat (the reference's OutputData.color) read back on rank 0; once per job: the FP32 image"
                                 + (" after the NCCL reduce" if world > 1 else ""),
                "d2h_note": "rank 0's bytes; the other ranks copy nothing to the host" if world > 1 else "every frame's image"}
@@ -492,7 +546,7 @@ def main():
         # the same measurement over 128 frames per rank when the job is shorter: a K-frame job ends with the read-back of its last wave
         # (samples_per_wave frames x the PCIe time of one image), which a long-running pass amortises
         if my_steps < 128 and args.scaling == "weak":
-            e2e["steady_state_128_steps"] = {k: v for k, v in run_e2e(128).items() if k in ("value", "ms_per_step", "steps", "samples_per_wave", "mpix_spp_per_s")}
+            e2e["steady_state_128_steps"] = {k: v for k, v in run_e2e(128).items() if k in ("value", "ms_per_step", "steps", "samples_per_wave", "wave_schedule", "mpix_spp_per_s")}
 
     if rank != 0:
         if world > 1:

@@ -247,6 +247,7 @@ BPT_ONLY_API = {
     "sync": [_VP],
     "resolve_device": [_VP, _U32, _VP],
     "resolve_device_rgba16f": [_VP, _U32, _VP],
+    "accumulate_ahead_rgba16f": [_VP, _U32, _VP],
     "accum_device_ptr": [_VP, C.POINTER(_VP)],
     "upload_accum": [_VP, _VP],
     "post_process": [_VP, C.POINTER(PostSettings), _U32, _VP],
@@ -456,6 +457,10 @@ class Context:
 
     def accumulate_ahead(self, count: int = 1):
         self._call("accumulate_ahead", count)
+
+    def accumulate_ahead_rgba16f(self, total_samples: int, device_ptr: int):
+        """accumulate_ahead(1) + resolve_device_rgba16f(total_samples, device_ptr) in one launch."""
+        self._call("accumulate_ahead_rgba16f", total_samples, _VP(device_ptr))
 
     def pending_ahead(self):
         """(samples traced ahead and not yet accumulated, frame_index of the next one) — bpt_pending_ahead."""

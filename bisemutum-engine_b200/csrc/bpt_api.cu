@@ -503,6 +503,11 @@ bpt_status bpt_render_ahead(bpt_context* c, const bpt_camera* cam, uint32_t firs
     return s;
 }
 bpt_status bpt_accumulate_ahead(bpt_context* c, uint32_t count) { NEED(c); return wavefront_accumulate_ahead(c, count); }
+bpt_status bpt_accumulate_ahead_rgba16f(bpt_context* c, uint32_t total_samples, void* d_out) {
+    NEED(c);
+    if (!total_samples || !d_out) return BPT_ERR_INVALID;
+    return wavefront_accumulate_ahead_rgba16f(c, total_samples, d_out);
+}
 bpt_status bpt_pending_ahead(bpt_context* c, uint32_t* pending, uint32_t* next_frame) {
     NEED(c);
     if (pending) *pending = c->wf.ahead_slots - c->wf.ahead_cursor;

@@ -147,6 +147,7 @@ bpt_status upload_instance_table(bpt_context* ctx);
 bpt_status wavefront_alloc(bpt_context* ctx);
 bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_first, uint32_t nsamples, const bpt_settings& st, bool keep_ahead = false);
 bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count);
+bpt_status wavefront_accumulate_ahead_rgba16f(bpt_context* ctx, uint32_t total_samples, void* d_out);
 bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_settings& st, float* h_depth, bpt_gbuffer_texel* h_gbuffer);
 bpt_status wavefront_trace_ao(bpt_context* ctx, const bpt_camera& cam, uint32_t frame_index, const bpt_ao_settings& ao, const float* h_depth,
                               const float* h_normal_roughness, float* h_out);

@@ -37,7 +37,7 @@ constexpr int QN = 128;
 #define BPT_MIN_NODE_LANES 8
 #endif
 #ifndef BPT_REFILL
-#define BPT_REFILL 12
+#define BPT_REFILL 8
 #endif
 #ifndef BPT_SMEM_STACK
 #define BPT_SMEM_STACK 0
@@ -62,6 +62,29 @@ constexpr int kSmemStack = BPT_SMEM_STACK;             // stack entries per lane
 #endif
 constexpr int kMinNodeLanes1 = BPT_MIN_NODE_LANES;      // node phase ends when fewer lanes than this still have an internal node
 constexpr int kRefillThreshold1 = BPT_REFILL;           // refill a warp's finished lanes when fewer rays than this are still in flight
+// The merged-mode kernels that walk the 4-wide tree (the incoherent bounces) have their own pair. Round 2, whole frame on configs[1]
+// (profiles/r2p..r2r_variants.jsonl; binary pair (8, 12)): wide (6, 12) 1.587, (8, 8) 1.580, (8, 12) 1.568, (8, 16) 1.569, (10, 20) 1.559,
+// (12, 16) 1.562, (12, 20) 1.552, (12, 24) 1.552, (16, 20) 1.549, (16, 24) 1.548, (20, 24) 1.556 ms; then the binary pair under wide (16, 24):
+// (8, 10) 1.545, (8, 8) 1.543, (6, 8) 1.541, (8, 6) 1.540 (all within the noise of each other): incoherent rays want to leave the node
+// phase early and refill early, like the two-level kernels.
+#ifndef BPT_MIN_NODE_LANES_W
+#define BPT_MIN_NODE_LANES_W 16
+#endif
+#ifndef BPT_REFILL_W
+#define BPT_REFILL_W 24
+#endif
+constexpr int kMinNodeLanesW = BPT_MIN_NODE_LANES_W, kRefillThresholdW = BPT_REFILL_W;
+// Triangle phase: 0 = a lane whose postponed leaves are done keeps testing the triangles it pops one after the other (a run of leaf
+// children of a wide node) while the other lanes wait; 1 = it only postpones the next (up to two) and goes back to the node phase with the warp.
+// Measured (profiles/r2p_variants.jsonl): 1 is 4.5 % slower on the whole frame (1.640 vs 1.569 ms), a third postponed leaf (BPT_LEAF3) 1.4 %
+// slower (1.591), both together 6.6 % (1.673): the short triangle runs are cheaper than another trip through the node phase.
+#ifndef BPT_TRI_LOOP
+#define BPT_TRI_LOOP 0
+#endif
+// Postponed leaves per lane: 2 (leaf, leaf2) or 3 (A/B builds)
+#ifndef BPT_LEAF3
+#define BPT_LEAF3 0
+#endif
 constexpr int kMinNodeLanes2 = BPT_MIN_NODE_LANES_2L, kRefillThreshold2 = BPT_REFILL_2L;
 
 struct RenderArgs {
@@ -186,7 +209,8 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
     const float4* __restrict__ tris = TWO_LEVEL ? nullptr : a.m_tris;
     const float4* __restrict__ leafbox = nullptr;       // TWO_LEVEL && WIDE: exact leaf boxes of the BLAS being traversed (nullptr: single-leaf BLAS)
     const uint32_t lane = threadIdx.x & 31;
-    constexpr int kMinNodeLanes = TWO_LEVEL ? kMinNodeLanes2 : kMinNodeLanes1, kRefillThreshold = TWO_LEVEL ? kRefillThreshold2 : kRefillThreshold1;
+    constexpr int kMinNodeLanes = TWO_LEVEL ? kMinNodeLanes2 : (WIDE ? kMinNodeLanesW : kMinNodeLanes1);
+    constexpr int kRefillThreshold = TWO_LEVEL ? kRefillThreshold2 : (WIDE ? kRefillThresholdW : kRefillThreshold1);
     // Short stack in shared memory (north star): the BOTTOM kSmemStack entries of every lane's stack live in shared memory as
     // [entry][thread] (one bank per lane: conflict-free whatever the lanes' depths are), deeper entries in local memory. A push or pop
     // at depth d touches exactly one of the two, so the local-memory traffic that is left is the accesses at depth >= kSmemStack.
@@ -198,7 +222,10 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
     RayState rs;
     RaySpace sp_;
     rs.found = false; rs.tbest = 0.0f; rs.tcull = 0.0f; rs.tmin = 0.001f; rs.cull_non_opaque = ANY && a.cull_non_opaque != 0;
-    int32_t node = kEmpty, leaf = 0, leaf2 = 0;
+    int32_t node = kEmpty, leaf = 0, leaf2 = 0, leaf3 = 0;
+    constexpr bool kLeaf3 = BPT_LEAF3 != 0;
+    auto leaf_room = [&]() { return kLeaf3 ? leaf3 == 0 : leaf2 == 0; };
+    auto leaf_put = [&](int32_t v) { if (leaf == 0) leaf = v; else if (!kLeaf3 || leaf2 == 0) leaf2 = v; else leaf3 = v; };
     // The top of the stack lives in a register (`tos`, kEmpty = nothing left): a pop hands out `tos` at once and the load of
     // the entry below it overlaps the node fetch instead of preceding it (ncu: 9 % of the stall samples sat behind that load).
     int32_t tos = kEmpty;
@@ -284,7 +311,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                         rs.frame_index = a.frame_base + path / a.npx; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
                         sp_ = make_space(rs.O, rs.D);
                         widir = sp_.idir;
-                        sp = 0; tos = kEmpty; leaf = 0; leaf2 = 0;
+                        sp = 0; tos = kEmpty; leaf = 0; leaf2 = 0; leaf3 = 0;
                         if (TWO_LEVEL) {
                             nodes = tlas_nodes; tris = nullptr; in_blas = false; slot = 0xffffffffu;
                             node = a.sc.tlas_n == 0 ? kEmpty : a.sc.tlas_root;
@@ -322,8 +349,8 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     if (next == BPT_POP) next = pop();
                     node = next;
                     settle();
-                    if (at_triangle() && leaf2 == 0) {                    // a triangle: postpone, keep descending
-                        if (leaf == 0) leaf = node; else leaf2 = node;
+                    if (at_triangle() && leaf_room()) {                   // a triangle: postpone, keep descending
+                        leaf_put(node);
 #ifdef BPT_PREFETCH_TRI
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(tris + 3 * (size_t)(uint32_t)~node));
 #endif
@@ -345,8 +372,8 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     if (parked) {
                         enter_instance();
                         settle();                                        // (a skipped instance may have popped a sentinel)
-                        if (at_triangle() && leaf2 == 0) {               // a single-triangle BLAS, or a triangle popped after a skip
-                            if (leaf == 0) leaf = node; else leaf2 = node;
+                        if (at_triangle() && leaf_room()) {              // a single-triangle BLAS, or a triangle popped after a skip
+                            leaf_put(node);
                             node = pop();
                             settle();
                         }
@@ -379,11 +406,17 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
                     accepted = test_triangle_rec<ANY, AH>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, TWO_LEVEL ? slot : 0xffffffffu, inst_anyhit);
                 }
-                leaf = leaf2; leaf2 = 0;
-                if (ANY && accepted) { node = kEmpty; sp = 0; tos = kEmpty; leaf = 0; break; }
+                leaf = leaf2; leaf2 = kLeaf3 ? leaf3 : 0; leaf3 = 0;
+                if (ANY && accepted) { node = kEmpty; sp = 0; tos = kEmpty; leaf = 0; leaf2 = 0; break; }
                 if (leaf == 0) {
                     settle();                                            // a sentinel that was waiting for the triangles
-                    if (at_triangle()) { leaf = node; node = pop(); settle(); }
+                    if (at_triangle()) {
+                        leaf = node; node = pop(); settle();
+#if BPT_TRI_LOOP == 1
+                        if (at_triangle()) { leaf2 = node; node = pop(); settle(); }
+                        break;
+#endif
+                    }
                 }
             }
             uint32_t alive = __ballot_sync(0xffffffffu, node != kEmpty);
@@ -535,6 +568,20 @@ __global__ void k_accumulate(const float4* __restrict__ color, float4* __restric
         v.x += c.x; v.y += c.y; v.z += c.z;
     }
     accum[p] = v;
+}
+
+// One engine frame of a frame-at-a-time pass: fold sample slot `slot` into the sum AND write OutputData.color (rgba16_sfloat, as
+// k_resolve_rgba16f) in the same pass over the pixels — 116 instead of 150 bytes per pixel and one launch instead of two per frame.
+__global__ void k_accumulate_resolve_rgba16f(const float4* __restrict__ color, float4* __restrict__ accum, uint2* __restrict__ out, uint32_t npx, uint32_t slot, float inv) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npx) return;
+    float4 v = accum[p];
+    float4 c = color[(size_t)slot * npx + p];
+    v.x += c.x; v.y += c.y; v.z += c.z;
+    accum[p] = v;
+    const uint32_t r = __half_as_ushort(__float2half_rn(v.x * inv)), g = __half_as_ushort(__float2half_rn(v.y * inv)),
+                   b = __half_as_ushort(__float2half_rn(v.z * inv));
+    out[p] = make_uint2(r | (g << 16), b | (0x3c00u << 16));
 }
 
 // reference_fp16: the running fp16 lerp of pt_accumulate.hlsl, samples in ascending frame order; `count` = samples already in the image
@@ -1189,6 +1236,23 @@ bpt_status wavefront_accumulate_ahead(bpt_context* ctx, uint32_t count) {
         wf.accum_count += count;
     } else LAUNCH_T(ctx, 4, k_accumulate, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), npx, wf.ahead_cursor, wf.ahead_cursor + count);
     wf.ahead_cursor += count;
+    return BPT_OK;
+}
+
+// bpt_accumulate_ahead(ctx, 1) + bpt_resolve_device_rgba16f(ctx, total_samples, d_out) in one launch (FP32 state; the literal fp16 state
+// keeps its two kernels: its sum buffer already is the running average)
+bpt_status wavefront_accumulate_ahead_rgba16f(bpt_context* ctx, uint32_t total_samples, void* d_out) {
+    WavefrontState& wf = ctx->wf;
+    if (wf.accum_fp16) {
+        bpt_status s = wavefront_accumulate_ahead(ctx, 1);
+        return s ? s : launch_resolve_rgba16f(ctx, total_samples, d_out);
+    }
+    NvtxRange r("PT Accumulate");
+    if (wf.ahead_cursor + 1 > wf.ahead_slots) { ctx->err = "accumulate_ahead: not enough prefetched samples"; return BPT_ERR_STATE; }
+    const uint32_t npx = ctx->width * ctx->height;
+    LAUNCH_T(ctx, 4, k_accumulate_resolve_rgba16f, (npx + 255) / 256, 256, wf.color.as<float4>(), wf.accum.as<float4>(), reinterpret_cast<uint2*>(d_out), npx,
+             wf.ahead_cursor, 1.0f / (float)total_samples);
+    wf.ahead_cursor += 1;
     return BPT_OK;
 }
 

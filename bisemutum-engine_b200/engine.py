@@ -45,6 +45,7 @@ def host_library():
         h.bpt_host_pass_set_camera.argtypes = [C.c_void_p, C.POINTER(HostCameraDesc)]
         h.bpt_host_pass_set_frame.argtypes = [C.c_void_p, C.c_uint64]
         h.bpt_host_pass_set_prefetch.argtypes = [C.c_void_p, C.c_uint32]
+        h.bpt_host_pass_set_color_target.argtypes = [C.c_void_p, C.c_void_p]
         h.bpt_host_pass_reset_history.argtypes = [C.c_void_p]
         h.bpt_host_pass_read_primary.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p]
         h.bpt_host_pass_frame.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
@@ -249,6 +250,10 @@ class Renderer:
     def reset_history(self):
         """The next frame() starts a new accumulation: the image is cleared and samples traced ahead are dropped (PathTracingPass::reset_history)."""
         host_library().bpt_host_pass_reset_history(self._pass)
+
+    def set_color_target(self, device_ptr: int):
+        """Binds the device memory behind OutputData.color (rgba16_sfloat): every frame() then writes its accumulated colour there (0: unbound)."""
+        host_library().bpt_host_pass_set_color_target(self._pass, C.c_void_p(device_ptr) if device_ptr else None)
 
     def set_frame(self, frame: int):
         host_library().bpt_host_pass_set_frame(self._pass, frame)

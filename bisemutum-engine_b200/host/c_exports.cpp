@@ -196,6 +196,7 @@ HOST_API const char* bpt_host_project_error(const bpt_host_project* h) { return 
 
 // Samples traced ahead per wave while the history stays valid (throughput vs latency of the first frame; default 8).
 HOST_API void bpt_host_pass_set_prefetch(bpt_host_pass* p, uint32_t frames) { p->pass->set_prefetch_frames(frames); }
+HOST_API void bpt_host_pass_set_color_target(bpt_host_pass* p, void* device_rgba16f) { p->pass->set_color_target(device_rgba16f); }
 HOST_API void bpt_host_pass_reset_history(bpt_host_pass* p) { p->pass->reset_history(); }
 // One engine frame: camera.update_shader_params → pass.render (records) → rg.execute. Returns bpt_status.
 HOST_API int bpt_host_pass_frame(bpt_host_pass* p, float ray_length, uint32_t max_bounces, int accumulate, uint64_t* accumulated_frames) {

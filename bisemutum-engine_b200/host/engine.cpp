@@ -166,7 +166,7 @@ auto PathTracingPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, In
     auto [builder, pass_data] = rg.add_compute_pass<PassData>("PT CUDA wavefront");
     pass_data->color = builder.write(out.color);
     builder.set_execution_function<PassData>(
-        [this, &camera, settings, reset](CRef<PassData>, gfx::ComputePassContext const&) {
+        [this, &camera, settings, reset, frames = hist_camera_it->second.frame_count](CRef<PassData>, gfx::ComputePassContext const&) {
             bpt_camera cam;
             std::memcpy(cam.matrix_inv_view, camera.matrix_inv_view().data(), 64);
             std::memcpy(cam.matrix_inv_proj, camera.matrix_inv_proj().data(), 64);
@@ -188,7 +188,10 @@ auto PathTracingPass::render(gfx::Camera const& camera, gfx::RenderGraph& rg, In
                 status_ = bpt_render_ahead(ctx_, &cam, camera.frame_index(), depth, &st, nullptr);
                 ahead_settings_ = st;
             }
-            if (status_ == BPT_OK) status_ = bpt_accumulate_ahead(ctx_, 1);
+            if (status_ != BPT_OK) return;
+            // "PT Accumulate" (path_tracing.cpp:461-480): the frame's sample joins the history; with a colour target bound the
+            // accumulated colour is written in the same launch
+            status_ = color_target_ ? bpt_accumulate_ahead_rgba16f(ctx_, (uint32_t)frames, color_target_) : bpt_accumulate_ahead(ctx_, 1);
         });
     return out;
 }

@@ -187,9 +187,14 @@ private:
     uint64_t frame_counter_ = 0;      // stands in for g_engine->window()->frame_count()
     uint32_t prefetch_frames_ = 8;    // samples traced per wave when the history is valid (clamped by the library)
     bpt_settings ahead_settings_{};
+    void* color_target_ = nullptr;
 public:
     auto set_frame_count(uint64_t f) -> void { frame_counter_ = f; }
     auto set_prefetch_frames(uint32_t n) -> void { prefetch_frames_ = n ? n : 1; }
+    // The device memory behind OutputData.color (rgba16_sfloat, W x H x 8 bytes) — in the real engine the CUDA mapping of the render-graph
+    // texture. When set, render() writes the frame's accumulated colour there in the same launch that folds the
+    // frame's sample into the history; nullptr: the caller resolves separately (bpt_resolve_device*).
+    auto set_color_target(void* device_rgba16f) -> void { color_target_ = device_rgba16f; }
     // Forgets every camera's history (what destroying and re-creating the reference's pass does): the next render() of any camera
     // starts a new accumulation (frame_count = 1) and clears the image, which also drops samples traced ahead.
     auto reset_history() -> void { camera_history_infos_.clear(); }

@@ -359,6 +359,10 @@ BPT_API bpt_status bpt_render_ahead(
     const bpt_settings* settings, uint32_t* out_samples);
 BPT_API bpt_status bpt_accumulate_ahead(bpt_context* ctx, uint32_t count);
 BPT_API bpt_status bpt_pending_ahead(bpt_context* ctx, uint32_t* out_pending, uint32_t* out_next_frame_index);
+/* One engine frame in one launch: bpt_accumulate_ahead(ctx, 1) followed by bpt_resolve_device_rgba16f(ctx, total_samples, out) — the next
+ * prefetched sample joins the sum and OutputData.color (rgba16_sfloat, path_tracing.cpp:248-252,461-480 "PT Accumulate") is written from it.
+ * `total_samples` = frames in the history including this one. Same bits as the two calls. */
+BPT_API bpt_status bpt_accumulate_ahead_rgba16f(bpt_context* ctx, uint32_t total_samples, void* out_rgba16f_device);
 /* out[p] = (sum[p].rgb * (1/total_samples), 1). Host destination (synchronises). */
 BPT_API bpt_status bpt_resolve(bpt_context* ctx, uint32_t total_samples, float* out_rgba32f);
 /* Same, written to device memory (no synchronisation). */

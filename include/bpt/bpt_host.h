@@ -53,6 +53,8 @@ BPT_HOST_API void bpt_host_pass_destroy(bpt_host_pass* p);
 BPT_HOST_API void bpt_host_pass_set_camera(bpt_host_pass* p, const bpt_host_camera_desc* cam);
 BPT_HOST_API void bpt_host_pass_set_frame(bpt_host_pass* p, uint64_t frame);
 BPT_HOST_API void bpt_host_pass_set_prefetch(bpt_host_pass* p, uint32_t frames);   /* samples traced ahead while the history stays valid */
+/* device memory behind OutputData.color (rgba16_sfloat, W*H*8 bytes): every frame writes its accumulated colour there (NULL: unbound) */
+BPT_HOST_API void bpt_host_pass_set_color_target(bpt_host_pass* p, void* device_rgba16f);
 BPT_HOST_API void bpt_host_pass_reset_history(bpt_host_pass* p);                   /* every camera starts a new accumulation at its next frame (drops samples traced ahead) */
 /* one engine frame: camera.update_shader_params -> pass.render (records) -> RenderGraph::execute; returns bpt_status */
 BPT_HOST_API int bpt_host_pass_frame(bpt_host_pass* p, float ray_length, uint32_t max_bounces, int accumulate, uint64_t* accumulated_frames);

@@ -313,6 +313,39 @@ def test_host_pass_accumulates_like_reference(lib, oracle):
     r.close()
 
 
+def test_pass_writes_output_color_in_place(lib):
+    """With a colour target bound (the device memory behind OutputData.color), the pass folds the frame's sample into the history and writes
+    the rgba16_sfloat colour in ONE launch (bpt_accumulate_ahead_rgba16f): same bits as accumulate + bpt_resolve_device_rgba16f, frame by
+    frame, and the FP32 history is the same too."""
+    import torch
+    scene = scenes.small_test_scene()
+    W, H = 72, 40
+    outs = []
+    for fused in (False, True):
+        r = engine.Renderer(W, H)
+        r.set_scene(scene, capi.ACCEL_MERGED)
+        r.set_prefetch(3)
+        target = torch.zeros(H, W, 4, dtype=torch.float16, device="cuda")
+        frames = []
+        for f in range(5):                                   # two waves (3 + 2 of the next)
+            if fused:
+                r.set_color_target(target.data_ptr())
+            n = r.frame(max_bounces=4)
+            assert n == f + 1
+            if not fused:
+                r.ctx.resolve_device_rgba16f(n, target.data_ptr())
+            r.ctx.sync()
+            frames.append(target.cpu().numpy().view(np.uint16).copy())
+        outs.append((frames, r.image(5)))
+        r.set_color_target(0)
+        assert r.frame(max_bounces=4) == 6                   # unbound again: plain accumulate
+        r.close()
+    for a, b in zip(outs[0][0], outs[1][0]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    assert outs[1][0][-1][..., 3].min() == 0x3c00 and outs[1][0][-1][..., :3].any()
+
+
 def test_scene_change_invalidates_prefetched_samples(lib, oracle):
     """the pass traces a wave of samples ahead while the camera stands still. A light, sky or instance change between two
     frames must show in the very next frame, as in the reference (which shades every frame with the current parameters): the samples
