@@ -92,6 +92,7 @@ struct bpt_context {
     // accel
     bool scene_has_anyhit = true;          // some instance needs the any-hit opacity rule (upload_instance_table); false selects the kernels without it
     bool accel_built = false;
+    bool bloom_attr_set = false;           // the same opt-in for the bloom level kernels (post.cu)
     bool lbvh_small_attr_set = false;      // cudaFuncSetAttribute(k_lbvh_small, MaxDynamicSharedMemorySize) done on this context's device
     uint32_t accel_mode = 0;
     std::vector<DevBvh> blas;

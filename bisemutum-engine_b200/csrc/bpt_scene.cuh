@@ -14,6 +14,15 @@
 #else
 #define BPT_LDG(p) (*(p))
 #endif
+// 256-bit read-only loads (sm_100: LDG.E.256): a 64-B BVH node is two load instructions instead of four, an exact leaf box one instead of
+// two. The traversal kernels of the incoherent bounces run the L1 at 75-88 % of its throughput with every lane fetching its own node, and
+// the L1 handles one request per instruction per distinct line — fewer, wider instructions are fewer requests. `p` must be 32-byte aligned
+// (nodes: 64-B records, leaf boxes: 32-B records, both in 256-B aligned allocations). BPT_LDG256=0: four / two 128-bit loads (A/B builds).
+// Measured (profiles/r2y_variants.jsonl): configs[1] 1.525 -> 1.498 ms per sample (extend 0.924 -> 0.905, connect 0.215 -> 0.211); the
+// two-level kernels keep the 128-bit loads (W256 = false): atrium two-level +0.8 %, but the DRAM-sized instanced scene -2 %.
+#ifndef BPT_LDG256
+#define BPT_LDG256 1
+#endif
 
 namespace bptd {
 
@@ -76,6 +85,20 @@ struct DScene {
     const float4* ddgi_irradiance; const float2* ddgi_visibility;
     bpt_probe_volume ddgi_volume;
 };
+
+template <bool W256 = true>
+BPT_HD void ldg_32B(const float4* p, float4& a, float4& b) {
+#if defined(__CUDA_ARCH__) && BPT_LDG256
+    if (W256) {
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+        return;
+    }
+#endif
+    a = BPT_LDG(p); b = BPT_LDG(p + 1);
+}
+template <bool W256 = true>
+BPT_HD void ldg_64B(const float4* p, float4& a, float4& b, float4& c, float4& d) { ldg_32B<W256>(p, a, b); ldg_32B<W256>(p + 2, c, d); }
 
 BPT_HD float3 xf_point(const float* m, float3 p) {
     return v3(((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7],

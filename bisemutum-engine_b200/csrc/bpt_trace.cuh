@@ -114,9 +114,11 @@ BPT_HD RaySpace make_space(float3 O, float3 D) {
 // One node step: returns the next node to visit (or BPT_POP) and, when both children are hit, the farther one in `far`
 // (BPT_POP otherwise) for the caller to push.
 #define BPT_POP ((int32_t)0x80000001)
+template <bool W256 = true>
 BPT_HD int32_t node_step2(const float4* nodes, int32_t cur, const RaySpace& r, float tmin, float tcull, int32_t& far) {
     const float4* n = nodes + 4 * (size_t)cur;
-    float4 n0 = BPT_LDG(n), n1 = BPT_LDG(n + 1), n2 = BPT_LDG(n + 2), n3 = BPT_LDG(n + 3);
+    float4 n0, n1, n2, n3;
+    ldg_64B<W256>(n, n0, n1, n2, n3);
     float c0lox = fmaf(n0.x, r.idir.x, -r.ood.x), c0hix = fmaf(n0.y, r.idir.x, -r.ood.x);
     float c0loy = fmaf(n0.z, r.idir.y, -r.ood.y), c0hiy = fmaf(n0.w, r.idir.y, -r.ood.y);
     float c1lox = fmaf(n1.x, r.idir.x, -r.ood.x), c1hix = fmaf(n1.y, r.idir.x, -r.ood.x);

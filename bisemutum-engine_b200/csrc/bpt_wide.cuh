@@ -112,7 +112,8 @@ BPT_HD void leaf_boxes_of_node(const float4* nodes2, int32_t i, float4* leafbox)
 }
 BPT_HD bool leaf_box_hit_rec(float4 lo, float4 hi, const RaySpace& r, float tmin, float tcull);
 BPT_HD bool leaf_box_hit(const float4* leafbox, uint32_t j, const RaySpace& r, float tmin, float tcull) {
-    float4 lo = BPT_LDG(leafbox + 2 * (size_t)j), hi = BPT_LDG(leafbox + 2 * (size_t)j + 1);
+    float4 lo, hi;
+    ldg_32B(leafbox + 2 * (size_t)j, lo, hi);
     return leaf_box_hit_rec(lo, hi, r, tmin, tcull);
 }
 BPT_HD bool leaf_box_hit_rec(float4 lo, float4 hi, const RaySpace& r, float tmin, float tcull) {
@@ -131,9 +132,11 @@ BPT_HD float byte_to_float(uint32_t w) { return (float)((w >> (8 * K)) & 0xffu);
 
 // One wide step: the four child references, a bit mask of the children whose decoded box the ray enters, and the slot
 // of the nearest of them (ties: lowest slot; -1 when none is hit).
+template <bool W256 = true>
 BPT_HD void node_test4q(const float4* wide, int32_t cur, const RaySpace& r, float tmin, float tcull, int32_t ch[4], uint32_t& hitmask, int& best) {
     const float4* n = wide + 4 * (size_t)cur;
-    float4 q0 = BPT_LDG(n), q1 = BPT_LDG(n + 1), q2 = BPT_LDG(n + 2), q3 = BPT_LDG(n + 3);
+    float4 q0, q1, q2, q3;
+    ldg_64B<W256>(n, q0, q1, q2, q3);
     const uint32_t eb = f2u(q0.w);
     const float sx = u2f((eb & 0xffu) << 23), sy = u2f(((eb >> 8) & 0xffu) << 23), sz = u2f(((eb >> 16) & 0xffu) << 23);
     const uint32_t lox = f2u(q2.x), loy = f2u(q2.y), loz = f2u(q2.z), hix = f2u(q2.w), hiy = f2u(q3.x), hiz = f2u(q3.y);

@@ -159,11 +159,10 @@ bpt_status launch_post_process(bpt_context* ctx, const bpt_post_settings& st, ui
         for (int i = 0; i < 5; i++) t[i] = reinterpret_cast<uint2*>(static_cast<char*>(ctx->d_post.p) + off[i]);
         auto gridt = [&](int w, int h) { return dim3((unsigned)((w + kTX - 1) / kTX), (unsigned)((h + kTY - 1) / kTY)); };
         const BloomWeights bw = bloom_weights(st.bloom_threshold, st.bloom_threshold_softness);
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx->bloom_attr_set) {      // per context (= per device): the opt-in is a property of the function on that device
             BPT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bloom_level<TexPre>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLevelSmem));
             BPT_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bloom_level<TexHalf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLevelSmem));
-            attr_set = true;
+            ctx->bloom_attr_set = true;
         }
         LAUNCH2(ctx, k_bloom_level<TexPre>, gridt(lw[0], lh[0]), kPostThreads, kLevelSmem, TexPre{accum, W, inv, bw}, W, H, t[0], lw[0], lh[0]);
         LAUNCH2(ctx, k_bloom_level<TexHalf>, gridt(lw[1], lh[1]), kPostThreads, kLevelSmem, TexHalf{t[0], lw[0]}, lw[0], lh[0], t[1], lw[1], lh[1]);

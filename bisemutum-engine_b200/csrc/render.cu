@@ -85,6 +85,13 @@ constexpr int kMinNodeLanesW = BPT_MIN_NODE_LANES_W, kRefillThresholdW = BPT_REF
 #ifndef BPT_LEAF3
 #define BPT_LEAF3 0
 #endif
+// Wide step, pushing the hit children that are not visited next: 1 = predicated stores (only the kept children, ~0.9 per step, cost an L1
+// request), 0 = four unconditional stores above the top of which the kept ones stay (same instruction count). The wide kernels run the L1 at
+// 77-88 % of its throughput (profiles/r2w_kernels.md), so requests matter: 1 is 1.3 % faster on configs[1], 3 % on the two-level scenes
+// (profiles/r2x_variants.jsonl).
+#ifndef BPT_WIDE_PUSH_PRED
+#define BPT_WIDE_PUSH_PRED 1
+#endif
 constexpr int kMinNodeLanes2 = BPT_MIN_NODE_LANES_2L, kRefillThreshold2 = BPT_REFILL_2L;
 
 struct RenderArgs {
@@ -334,16 +341,21 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     int32_t next;
                     if (WIDE) {
                         int32_t ch[4]; uint32_t hitmask; int best;
-                        node_test4q(nodes, node, sp_, rs.tmin, rs.tcull, ch, hitmask, best);
+                        node_test4q<!TWO_LEVEL>(nodes, node, sp_, rs.tmin, rs.tcull, ch, hitmask, best);
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {                       // store above the top unconditionally, keep it only if wanted
-                            st_put(sp, ch[k]);
-                            sp += (((hitmask >> k) & 1u) && k != best) ? 1 : 0;
+                        for (int k = 0; k < 4; k++) {
+                            const bool keep = ((hitmask >> k) & 1u) && k != best;
+#if BPT_WIDE_PUSH_PRED
+                            if (keep) st_put(sp, ch[k]);                    // predicated store: only the kept children cost an L1 transaction
+#else
+                            st_put(sp, ch[k]);                              // store above the top unconditionally, keep it only if wanted
+#endif
+                            sp += keep ? 1 : 0;
                         }
                         next = best < 0 ? BPT_POP : (best == 0 ? ch[0] : (best == 1 ? ch[1] : (best == 2 ? ch[2] : ch[3])));
                     } else {
                         int32_t far;
-                        next = node_step2(nodes, node, sp_, rs.tmin, rs.tcull, far);
+                        next = node_step2<!TWO_LEVEL>(nodes, node, sp_, rs.tmin, rs.tcull, far);
                         if (far != BPT_POP) push(far);
                     }
                     if (next == BPT_POP) next = pop();
@@ -389,7 +401,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     const float4* tp = tris + 3 * (size_t)j;
                     float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
                     float4 blo = ta, bhi = ta;
-                    if (leafbox) { blo = BPT_LDG(leafbox + 2 * (size_t)j); bhi = BPT_LDG(leafbox + 2 * (size_t)j + 1); }
+                    if (leafbox) ldg_32B<false>(leafbox + 2 * (size_t)j, blo, bhi);
                     accepted = (!leafbox || leaf_box_hit_rec(blo, bhi, sp_, rs.tmin, rs.tcull)) &&
                                test_triangle_rec<ANY, AH>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, slot, inst_anyhit);
                 } else if (WIDE) {                                           // leaf box and triangle fetched together: one latency, not two
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     const float4* bp = a.m_leafbox + 2 * (size_t)(a.m_n == 1 ? 0u : j);
                     float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
                     float4 blo = ta, bhi = ta;
-                    if (a.m_n != 1) { blo = BPT_LDG(bp); bhi = BPT_LDG(bp + 1); }
+                    if (a.m_n != 1) ldg_32B(bp, blo, bhi);
                     accepted = (a.m_n == 1 || leaf_box_hit_rec(blo, bhi, sp_, rs.tmin, rs.tcull)) &&
                                test_triangle_rec<ANY, AH>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, 0xffffffffu, 0u);
                 } else {
