@@ -92,6 +92,11 @@ constexpr int kMinNodeLanesW = BPT_MIN_NODE_LANES_W, kRefillThresholdW = BPT_REF
 #ifndef BPT_WIDE_PUSH_PRED
 #define BPT_WIDE_PUSH_PRED 1
 #endif
+// Ray loads / hit stores of the traversal kernels with the streaming (evict-first) policy: each is touched once, the L1 / L2 lines are
+// worth more to the BVH (+0.4 % on configs[1], profiles/r2ab_variants.jsonl)
+#ifndef BPT_STREAM_RAYS
+#define BPT_STREAM_RAYS 1
+#endif
 constexpr int kMinNodeLanes2 = BPT_MIN_NODE_LANES_2L, kRefillThreshold2 = BPT_REFILL_2L;
 
 struct RenderArgs {
@@ -238,6 +243,8 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
     int32_t tos = kEmpty;
     int sp = 0;
     // (the wide kernels push up to three nodes per step with predicated stores and keep a plain stack)
+    // (A lazily spilled register top for the wide kernels — the last push stays in a register until another push follows — was measured:
+    // fewer L1 requests, but 3-5 % slower, profiles/r2ab_variants.jsonl: the extra predicated moves cost more than the requests saved.)
     auto push = [&](int32_t v) { if (WIDE) { st_put(sp++, v); } else { st_put(sp++, tos); tos = v; } };
     auto pop = [&]() { if (WIDE) return sp ? st_get(--sp) : kEmpty; int32_t v = tos; tos = sp ? st_get(--sp) : kEmpty; return v; };
     uint32_t ray = 0xffffffffu, path = 0;
@@ -294,8 +301,13 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                     atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
                 }
             } else {
+#if BPT_STREAM_RAYS
+                __stcs(a.hit + ray, make_float4(rs.found ? rs.tbest : -1.0f, rs.bu, rs.bv, __uint_as_float(rs.best_prim)));
+                __stcs(a.hit_slot + ray, rs.best_slot);
+#else
                 a.hit[ray] = make_float4(rs.found ? rs.tbest : -1.0f, rs.bu, rs.bv, __uint_as_float(rs.best_prim));
                 a.hit_slot[ray] = rs.best_slot;
+#endif
             }
             ray = 0xffffffffu;
         }
@@ -309,7 +321,11 @@ __global__ void __launch_bounds__(kBlock, TWO_LEVEL ? (AH ? 8 : BPT_TRACE_MIN_BL
                 if (want) {
                     uint32_t idx = base + __popc(mask & ((1u << lane) - 1u));
                     if (idx < n) {
+#if BPT_STREAM_RAYS
+                        float4 o = __ldcs(qo + idx), d = __ldcs(qd + idx);      // read once: do not displace BVH lines
+#else
                         float4 o = qo[idx], d = qd[idx];
+#endif
                         ray = idx;
                         path = __float_as_uint(o.w);
                         rs.O = v3(o.x, o.y, o.z); rs.D = v3(d.x, d.y, d.z);
