@@ -67,6 +67,11 @@ for sc in (scene, basic):
 r = engine.Renderer(W, H); r.set_scene(scene, capi.ACCEL_MERGED)
 for _ in range(3):
     n = r.frame(max_bounces=4)
+target = torch.zeros(H, W, 4, dtype=torch.float16, device="cuda")      # OutputData.color written by the pass (bpt_accumulate_ahead_rgba16f)
+r.set_color_target(target.data_ptr())
+for _ in range(2):
+    n = r.frame(max_bounces=4)
+r.ctx.sync(); assert torch.isfinite(target).all()
 r.image(n); r.post_process(True, 0.3, 0.5); r.close()
 pc = capi.Context(lib, W, H); pc.upload_scene(scenes.small_test_scene(), capi.ACCEL_MERGED)
 engine.run_renderer(pc, scenes.small_test_scene(), W, H, 2, max_bounces=3, bloom=True, bloom_threshold=0.3); pc.close()
