@@ -10,6 +10,7 @@
 // therefore not deterministic, queue CONTENT is (every entry is keyed by its pixel index).
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 #include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: a no-op unless a profiler injects itself
 #include "bpt_internal.cuh"
 #include "bpt_shade.cuh"
@@ -94,6 +95,10 @@ constexpr int kMinNodeLanesW = BPT_MIN_NODE_LANES_W, kRefillThresholdW = BPT_REF
 #endif
 // Ray loads / hit stores of the traversal kernels with the streaming (evict-first) policy: each is touched once, the L1 / L2 lines are
 // worth more to the BVH (+0.4 % on configs[1], profiles/r2ab_variants.jsonl)
+// Packet traversal (k_trace_packet): resident blocks per SM
+#ifndef BPT_PACKET_MIN_BLOCKS
+#define BPT_PACKET_MIN_BLOCKS 10
+#endif
 #ifndef BPT_STREAM_RAYS
 #define BPT_STREAM_RAYS 1
 #endif
@@ -120,6 +125,7 @@ struct RenderArgs {
     uint32_t pixel_jitter;
     uint32_t probe_mode;      // 1: paths start at probes; colour.w receives the first hit distance
     uint32_t cull_non_opaque; // connect kernel only: RAY_FLAG_CULL_NON_OPAQUE (the RTAO rays)
+    uint32_t camera_paths;    // 1: the queue of bounce 1 was written by k_raygen (32 consecutive entries = the camera rays of one 8x4 pixel tile)
 };
 
 // warp-aggregated append: returns the slot for this lane (valid only if `emit`)
@@ -471,6 +477,165 @@ static const auto k_extend_two_level_o = k_trace_spec<false, true, false, false>
 static const auto k_connect_two_level_o = k_trace_spec<true, true, false, false>;
 static const auto k_extend_two_level_wide_o = k_trace_spec<false, true, true, false>;
 static const auto k_connect_two_level_wide_o = k_trace_spec<true, true, true, false>;
+
+// ---- packet traversal of coherent rays (merged mode, binary tree): camera rays, and the shadow rays of the camera rays' hit points ----------
+// The persistent kernel above gives every lane its own traversal; for the camera rays of an 8x4 pixel tile that is 32 walks through nearly
+// the same nodes: measured on configs[1] (oracle BVH, 300 tiles), a ray visits 37.9 nodes and 2.3 leaves, the UNION over the tile is 44.6
+// nodes and 5.5 leaves. Here one warp walks that union ONCE: 32 consecutive queue entries are a packet, the warp keeps one stack of
+// (node, lane mask) in shared memory, every lane tests both child boxes of the same node (one broadcast fetch instead of 32), a ballot
+// gives the lanes that enter each child, the child more lanes prefer is visited first and the other pushed with its mask; at a leaf
+// the lanes of its mask test the triangle. A lane tests a triangle iff its own ray passed every ancestor's box with its own current
+// cull distance — the candidates of its own traversal in another order, and results do not depend on the order (bpt_trace.cuh header):
+// hits are bit-identical to k_trace_spec's. Correct for ANY 32 rays; fast when they are coherent, so it is launched for bounce 1 of
+// camera paths only (RenderArgs::camera_paths). Measured on configs[1] (profiles/r2ad_variants.jsonl, r2ae_packet_source.md): the camera
+// rays' extend launch 5.24 -> 4.54 ms per 16-sample wave (3.9 G instead of 4.9 G warp instructions at 29.8 instead of 24 lanes); what
+// binds it now is the L1 data path (every lane still receives every 64-B node: 76 %) together with the ALU pipe (min / max: 74 %).
+// The shadow rays of the camera rays' hit points as packets: slower (connect 0.209 -> 0.227 ms; mixed lights 9.3 -> 10.8), off.
+// A FRUSTUM walk instead of per-lane box tests (twelve lanes test the twelve (child, plane) pairs of a node against the packet's four
+// side planes and depth range, every lane runs the exact leaf-box + triangle test at the leaves — valid because a ray passes a leaf's
+// exact box only if it passes every ancestor's) was built and is bit-exact too, but visits 3x the nodes (336 instead of 107 stack
+// accesses per packet: its depth pruning is the packet's WORST cull distance) and is slower than k_trace_spec:
+// profiles/r2ag_frustum_kernel.patch, r2ag_frustum_source.md, r2af_variants.jsonl.
+constexpr int kPacketStack = 100;      // one entry per tree level at most (Karras depth bound 95, bpt_trace.cuh)
+template <bool ANY, bool AH>
+__global__ void __launch_bounds__(kBlock, BPT_PACKET_MIN_BLOCKS) k_trace_packet(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    const uint32_t n = ANY ? (uint32_t)min((uint64_t)a.qcount[QS + bounce], a.shadow_capacity) : a.qcount[QE + bounce];
+    uint32_t* cursor = &a.qcount[(ANY ? QWS : QWE) + bounce];
+    const float4* __restrict__ qo = ANY ? a.sh_o : a.ray_o_in;
+    const float4* __restrict__ qd = ANY ? a.sh_d : a.ray_d_in;
+    const float4* __restrict__ nodes = a.m_nodes;
+    const float4* __restrict__ tris = a.m_tris;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int32_t s_node_all[kBlock / 32][kPacketStack];
+    __shared__ uint32_t s_mask_all[kBlock / 32][kPacketStack];
+    int32_t* const s_node = s_node_all[warp];
+    uint32_t* const s_mask = s_mask_all[warp];
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t idx = base + lane;
+        const bool valid = idx < n;
+        RayState rs;
+        RaySpace sp_;
+        uint32_t path = 0;
+        {
+            float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+            if (valid) { o = __ldcs(qo + idx); d = __ldcs(qd + idx); }
+            path = __float_as_uint(o.w);
+            rs.O = v3(o.x, o.y, o.z); rs.D = v3(d.x, d.y, d.z);
+            rs.tmin = 0.001f; rs.tbest = ANY ? d.w : a.sp.ray_length; rs.tcull = rs.tbest * 1.00001f;
+            rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu; rs.bu = 0.0f; rs.bv = 0.0f;
+            rs.frame_index = a.frame_base + path / a.npx; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
+            rs.cull_non_opaque = ANY && a.cull_non_opaque != 0;
+            sp_ = make_space(rs.O, rs.D);
+        }
+        bool alive = valid;                                  // ANY: cleared by the first accepted hit
+        int sp = 0;
+        int32_t node = a.m_n == 0 ? kEmpty : a.m_root;
+        uint32_t mask = __ballot_sync(0xffffffffu, alive);
+        auto walk = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+        while (node != kEmpty) {
+            if (node >= 0) {
+                const float4* np = nodes + 4 * (size_t)node;
+                float4 n0, n1, n2, n3;
+                ldg_64B(np, n0, n1, n2, n3);
+                const RaySpace& r = sp_;
+                float t0n, t0f, t1n, t1f;
+                if (MODE == 8) {                                     // lanes disagree on a direction sign: node_step2's own expressions
+                    float c0lox = fmaf(n0.x, r.idir.x, -r.ood.x), c0hix = fmaf(n0.y, r.idir.x, -r.ood.x);
+                    float c0loy = fmaf(n0.z, r.idir.y, -r.ood.y), c0hiy = fmaf(n0.w, r.idir.y, -r.ood.y);
+                    float c1lox = fmaf(n1.x, r.idir.x, -r.ood.x), c1hix = fmaf(n1.y, r.idir.x, -r.ood.x);
+                    float c1loy = fmaf(n1.z, r.idir.y, -r.ood.y), c1hiy = fmaf(n1.w, r.idir.y, -r.ood.y);
+                    float c0loz = fmaf(n2.x, r.idir.z, -r.ood.z), c0hiz = fmaf(n2.y, r.idir.z, -r.ood.z);
+                    float c1loz = fmaf(n2.z, r.idir.z, -r.ood.z), c1hiz = fmaf(n2.w, r.idir.z, -r.ood.z);
+                    t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), rs.tmin));
+                    t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), rs.tcull));
+                    t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), rs.tmin));
+                    t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), rs.tcull));
+                } else {
+                    // The whole packet looks into ONE octant (camera rays of a tile nearly always do): the near plane of every slab is known
+                    // at compile time, and for a valid box (lo <= hi) the slab value of the near plane IS min(t(lo), t(hi)) bit for bit (fmaf is
+                    // monotone in the plane) — the twelve per-axis min / max of a node step disappear.
+                    constexpr bool SX = (MODE & 1) != 0, SY = (MODE & 2) != 0, SZ = (MODE & 4) != 0;
+                    const float a0nx = fmaf(SX ? n0.y : n0.x, r.idir.x, -r.ood.x), a0fx = fmaf(SX ? n0.x : n0.y, r.idir.x, -r.ood.x);
+                    const float a0ny = fmaf(SY ? n0.w : n0.z, r.idir.y, -r.ood.y), a0fy = fmaf(SY ? n0.z : n0.w, r.idir.y, -r.ood.y);
+                    const float a0nz = fmaf(SZ ? n2.y : n2.x, r.idir.z, -r.ood.z), a0fz = fmaf(SZ ? n2.x : n2.y, r.idir.z, -r.ood.z);
+                    const float a1nx = fmaf(SX ? n1.y : n1.x, r.idir.x, -r.ood.x), a1fx = fmaf(SX ? n1.x : n1.y, r.idir.x, -r.ood.x);
+                    const float a1ny = fmaf(SY ? n1.w : n1.z, r.idir.y, -r.ood.y), a1fy = fmaf(SY ? n1.z : n1.w, r.idir.y, -r.ood.y);
+                    const float a1nz = fmaf(SZ ? n2.w : n2.z, r.idir.z, -r.ood.z), a1fz = fmaf(SZ ? n2.z : n2.w, r.idir.z, -r.ood.z);
+                    t0n = fmaxf(fmaxf(a0nx, a0ny), fmaxf(a0nz, rs.tmin)); t0f = fminf(fminf(a0fx, a0fy), fminf(a0fz, rs.tcull));
+                    t1n = fmaxf(fmaxf(a1nx, a1ny), fmaxf(a1nz, rs.tmin)); t1f = fminf(fminf(a1fx, a1fy), fminf(a1fz, rs.tcull));
+                }
+                const bool mine = alive && ((mask >> lane) & 1u);
+                const bool h0 = mine && t0n <= t0f, h1 = mine && t1n <= t1f;
+                const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                const int32_t ch0 = (int32_t)f2u(n3.x), ch1 = (int32_t)f2u(n3.y);
+                if ((m0 | m1) == 0u) {
+                    if (sp == 0) { node = kEmpty; continue; }
+                    --sp; node = s_node[sp]; mask = s_mask[sp];
+                } else if (m0 != 0u && m1 != 0u) {
+                    // visit first the child more lanes reach first (a lane that enters one child only votes for that one)
+                    const uint32_t pref0 = __ballot_sync(0xffffffffu, h0 && (!h1 || t0n <= t1n));
+                    const bool first0 = 2 * __popc(pref0) >= __popc(m0 | m1);
+                    s_node[sp] = first0 ? ch1 : ch0; s_mask[sp] = first0 ? m1 : m0; ++sp;
+                    node = first0 ? ch0 : ch1; mask = first0 ? m0 : m1;
+                } else {
+                    node = m0 != 0u ? ch0 : ch1; mask = m0 | m1;
+                }
+            } else {
+                if (alive && ((mask >> lane) & 1u)) {
+                    const float4* tp = tris + 3 * (size_t)(uint32_t)~node;
+                    float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
+                    const bool accepted = test_triangle_rec<ANY, AH>(a.sc, rs, ta, tb, tc, sp_.O, sp_.D, 0xffffffffu, 0u);
+                    if (ANY && accepted) alive = false;
+                }
+                if (ANY && __ballot_sync(0xffffffffu, alive) == 0u) { node = kEmpty; continue; }
+                if (sp == 0) { node = kEmpty; continue; }
+                --sp; node = s_node[sp]; mask = s_mask[sp];
+            }
+        }
+        };
+        {
+            // direction octant of the packet, if its lanes agree on it
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            const uint32_t bx = __ballot_sync(0xffffffffu, valid && sp_.idir.x < 0.0f), by = __ballot_sync(0xffffffffu, valid && sp_.idir.y < 0.0f),
+                           bz = __ballot_sync(0xffffffffu, valid && sp_.idir.z < 0.0f);
+            const bool uniform = (bx == 0u || bx == vm) && (by == 0u || by == vm) && (bz == 0u || bz == vm);
+            const int mode = uniform ? ((bx ? 1 : 0) | (by ? 2 : 0) | (bz ? 4 : 0)) : 8;
+            switch (mode) {
+                case 0: walk(std::integral_constant<int, 0>{}); break;
+                case 1: walk(std::integral_constant<int, 1>{}); break;
+                case 2: walk(std::integral_constant<int, 2>{}); break;
+                case 3: walk(std::integral_constant<int, 3>{}); break;
+                case 4: walk(std::integral_constant<int, 4>{}); break;
+                case 5: walk(std::integral_constant<int, 5>{}); break;
+                case 6: walk(std::integral_constant<int, 6>{}); break;
+                case 7: walk(std::integral_constant<int, 7>{}); break;
+                default: walk(std::integral_constant<int, 8>{}); break;
+            }
+        }
+        if (valid) {
+            if (ANY) {
+                if (!rs.found) {
+                    float4 c = a.sh_c[idx];
+                    float* px = reinterpret_cast<float*>(a.contrib + path);
+                    atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+                }
+            } else {
+                __stcs(a.hit + idx, make_float4(rs.found ? rs.tbest : -1.0f, rs.bu, rs.bv, __uint_as_float(rs.best_prim)));
+                __stcs(a.hit_slot + idx, rs.best_slot);
+            }
+        }
+    }
+}
+
+static const auto k_extend_packet = k_trace_packet<false, true>;
+static const auto k_extend_packet_o = k_trace_packet<false, false>;
+static const auto k_connect_packet = k_trace_packet<true, true>;
+static const auto k_connect_packet_o = k_trace_packet<true, false>;
 
 // ---- shade: material + lighting + next direction, emits shadow rays and the next extend ray ---
 struct KernelSink {
@@ -947,7 +1112,7 @@ static bpt_status prepare_args(bpt_context* ctx, RenderArgs& a, const bpt_settin
     a.accum = wf.accum.as<float4>(); a.color = wf.color.as<float4>();
     a.contrib = st.state_precision == BPT_STATE_REFERENCE_FP16 ? wf.bcol.as<float4>() : a.color;
     a.qcount = wf.qcount.as<uint32_t>(); a.shadow_capacity = wf.shadow_capacity;
-    a.pixel_base = 0; a.probe_mode = 0; a.cull_non_opaque = 0;
+    a.pixel_base = 0; a.probe_mode = 0; a.cull_non_opaque = 0; a.camera_paths = 0;
     if (ctx->accel_mode == BPT_ACCEL_MERGED) {
         a.m_nodes = ctx->blas[0].nodes.as<float4>(); a.m_tris = ctx->blas[0].tris.as<float4>(); a.m_root = ctx->blas[0].root; a.m_n = ctx->blas[0].n;
         a.m_wide = ctx->blas[0].wide.as<float4>(); a.m_leafbox = ctx->blas[0].leafbox.as<float4>();
@@ -989,8 +1154,15 @@ static unsigned resident_grid(bpt_context* ctx, K kernel) {
 }
 // BPT_SPECIALISE=0 launches the general kernels everywhere (A/B measurements)
 static bool specialise_opaque() { static const bool on = [] { const char* e = getenv("BPT_SPECIALISE"); return !e || atoi(e) != 0; }(); return on; }
+// BPT_PACKET (default 1): bit 0 = the camera rays walk the tree as packets (k_trace_packet), bit 1 = so do the shadow rays of their hit points
+// (measured: slower, off); 0 = everything through k_trace_spec (merged mode only)
+static uint32_t packet_mode() { static const uint32_t m = [] { const char* e = getenv("BPT_PACKET"); return e ? (uint32_t)atoi(e) : 1u; }(); return m; }
 static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
+    if (i == 1 && a.camera_paths && (packet_mode() & 1u) && ctx->accel_mode == BPT_ACCEL_MERGED) {
+        if (ah) LAUNCH_T(ctx, 1, k_extend_packet, resident_grid(ctx, k_extend_packet), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_packet_o, resident_grid(ctx, k_extend_packet_o), kBlock, a, i);
+        return BPT_OK;
+    }
     if (use_wide2(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_two_level_wide, resident_grid(ctx, k_extend_two_level_wide), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_two_level_wide_o, resident_grid(ctx, k_extend_two_level_wide_o), kBlock, a, i); }
     else if (use_wide(ctx, i)) { if (ah) LAUNCH_T(ctx, 1, k_extend_wide, resident_grid(ctx, k_extend_wide), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_wide_o, resident_grid(ctx, k_extend_wide_o), kBlock, a, i); }
     else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 1, k_extend_merged, resident_grid(ctx, k_extend_merged), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_merged_o, resident_grid(ctx, k_extend_merged_o), kBlock, a, i); }
@@ -999,6 +1171,10 @@ static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t 
 }
 static bpt_status launch_connect(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
+    if (i == 1 && a.camera_paths && (packet_mode() & 2u) && ctx->accel_mode == BPT_ACCEL_MERGED) {
+        if (ah) LAUNCH_T(ctx, 3, k_connect_packet, resident_grid(ctx, k_connect_packet), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_packet_o, resident_grid(ctx, k_connect_packet_o), kBlock, a, i);
+        return BPT_OK;
+    }
     if (use_wide2(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_two_level_wide, resident_grid(ctx, k_connect_two_level_wide), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_two_level_wide_o, resident_grid(ctx, k_connect_two_level_wide_o), kBlock, a, i); }
     else if (use_wide(ctx, i, true)) { if (ah) LAUNCH_T(ctx, 3, k_connect_wide, resident_grid(ctx, k_connect_wide), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_wide_o, resident_grid(ctx, k_connect_wide_o), kBlock, a, i); }
     else if (ctx->accel_mode == BPT_ACCEL_MERGED) { if (ah) LAUNCH_T(ctx, 3, k_connect_merged, resident_grid(ctx, k_connect_merged), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_merged_o, resident_grid(ctx, k_connect_merged_o), kBlock, a, i); }
@@ -1049,6 +1225,7 @@ bpt_status wavefront_render(bpt_context* ctx, const bpt_camera& cam, uint32_t fr
     if ((s = prepare_args(ctx, a, st, B))) return s;
     a.cam = cam;
     a.npx = npx;
+    a.camera_paths = 1;
     const bool capture = ctx->capture && nsamples == 1;
     if (capture) {
         ctx->cap_bounces = B;
@@ -1090,7 +1267,7 @@ bpt_status wavefront_render_primary(bpt_context* ctx, const bpt_camera& cam, uin
     const uint32_t npx = ctx->width * ctx->height;
     RenderArgs a;
     if ((s = prepare_args(ctx, a, st, 2))) return s;
-    a.cam = cam; a.npx = npx; a.nslots = 1; a.frame_base = frame_index;
+    a.cam = cam; a.npx = npx; a.nslots = 1; a.frame_base = frame_index; a.camera_paths = 1;
     DevBuf d_depth, d_g;
     auto cleanup = [&]() { dev_free(d_depth); dev_free(d_g); };
     if ((s = dev_alloc(ctx, d_depth, (size_t)npx * 4)) || (s = dev_alloc(ctx, d_g, (size_t)npx * sizeof(bpt_gbuffer_texel)))) { cleanup(); return s; }

@@ -6,9 +6,9 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r2f_gpu_tests.log; cat gpurun_out/r2f_gpu_tests.log
 python bench.py --steps 16 --warmup 16 --device-only > gpurun_out/r2f_device_only_s16.json 2> gpurun_out/r2f_device_only.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 16 --warmup 16 --device-only > gpurun_out/ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_trace_spec|k_shade" -s 21 -c 21 -o /tmp/r2f_kernels python bench.py --steps 16 --warmup 16 --device-only > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_trace_spec|k_trace_packet|k_shade" -s 21 -c 21 -o /tmp/r2f_kernels python bench.py --steps 16 --warmup 16 --device-only > gpurun_out/ncu_full.log 2>&1
 ncu -i /tmp/r2f_kernels.ncu-rep --page raw --csv > gpurun_out/r2f_raw.csv 2> gpurun_out/ncu_export.err
-ncu --set full --clock-control none --import-source on -k regex:"k_trace_spec" -s 14 -c 3 -o /tmp/r2f_trace python bench.py --steps 16 --warmup 16 --device-only >> gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_trace_spec|k_trace_packet" -s 14 -c 3 -o /tmp/r2f_trace python bench.py --steps 16 --warmup 16 --device-only >> gpurun_out/ncu_full.log 2>&1
 python tools/summarize_ncu.py source /tmp/r2f_trace.ncu-rep > gpurun_out/r2f_trace_source.md 2>&1
 python bench.py --config instanced --steps 8 --warmup 8 --device-only > gpurun_out/r2f_inst_device_only_s8.json 2> gpurun_out/r2f_inst_device_only.err
 ncu --set full --clock-control none -k regex:"k_trace_spec" -s 14 -c 14 -o /tmp/r2f_inst python bench.py --config instanced --steps 8 --warmup 8 --device-only > gpurun_out/ncu_inst.log 2>&1

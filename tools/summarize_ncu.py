@@ -29,9 +29,9 @@ RAW = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_s
 
 
 def short(name):
-    for k in ("k_trace_spec", "k_shade", "k_raygen", "k_accumulate", "k_tally", "k_commit_bounce"):
+    for k in ("k_trace_spec", "k_trace_packet", "k_shade", "k_raygen", "k_accumulate", "k_tally", "k_commit_bounce"):
         if k in name:
-            if k == "k_trace_spec":
+            if k in ("k_trace_spec", "k_trace_packet"):      # first template argument: ANY (shadow rays); the packet kernel counts as a traversal launch of its class
                 any_ = "(bool)1, " in name or "<1, " in name
                 return "k_trace_spec (connect)" if any_ else "k_trace_spec (extend)"
             return k
