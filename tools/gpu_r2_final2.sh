@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, capture F (FINAL kernels of the round: + predicated wide pushes, 256-bit node loads, streaming ray accesses):
+# round 2, capture F (FINAL kernels of the round: + predicated wide pushes, 256-bit node loads, streaming ray accesses, packet traversal of the camera rays):
 # GPU tests, ncu launch list + --set full of one wave on configs[1], --set full of the traversal launches on configs[3] (instanced),
 # per-ray counters for bench.py's roofline, then the bench lines (driver command, 128 steps, instanced, reference arm)
 mkdir -p gpurun_out
