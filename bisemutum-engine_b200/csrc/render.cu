@@ -480,7 +480,7 @@ static const auto k_connect_two_level_wide_o = k_trace_spec<true, true, true, fa
 
 // ---- packet traversal of coherent rays (merged mode, binary tree): camera rays, and the shadow rays of the camera rays' hit points ----------
 // The persistent kernel above gives every lane its own traversal; for the camera rays of an 8x4 pixel tile that is 32 walks through nearly
-// the same nodes: measured on configs[1] (oracle BVH, 300 tiles), a ray visits 37.9 nodes and 2.3 leaves, the UNION over the tile is 44.6
+// the same nodes: measured on the binary BVH of configs[1] over 300 tiles, a ray visits 37.9 nodes and 2.3 leaves, the UNION over the tile is 44.6
 // nodes and 5.5 leaves. Here one warp walks that union ONCE: 32 consecutive queue entries are a packet, the warp keeps one stack of
 // (node, lane mask) in shared memory, every lane tests both child boxes of the same node (one broadcast fetch instead of 32), a ballot
 // gives the lanes that enter each child, the child more lanes prefer is visited first and the other pushed with its mask; at a leaf
