@@ -1,6 +1,10 @@
-"""How many nodes does a PACKET of 32 camera rays (one 8x4 pixel tile) visit, against the sum of its rays own traversals? Walks the binary BVH the\nCPU checker builds for configs[1] (test infrastructure: this script is an analysis tool, not product code) with exact per-ray box tests and each\nray final hit distance as its cull bound. Result quoted in DESIGN.md section 5: 37.9 nodes / 2.3 leaves per ray, 44.6 / 5.5 per tile."""
+"""Analysis script (not a test; lives under tests/ because it uses the CPU checker): how many nodes does a PACKET of 32 camera rays
+(one 8x4 pixel tile) visit, against the sum of its rays' own traversals? Walks the binary BVH the checker builds for configs[1] with exact
+per-ray box tests and each ray's final hit distance as its cull bound. Result quoted in DESIGN.md section 5: 37.9 nodes / 2.3 leaves per
+ray, 44.6 / 5.5 per tile — the measurement behind k_trace_packet.   python tests/analysis_packet_union.py"""
 import sys, os, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import numpy as np
 import bisemutum_engine_b200 as pkg
 from bisemutum_engine_b200 import capi, engine, scenes
