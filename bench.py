@@ -412,10 +412,7 @@ def main():
         # nothing to hide behind. So the application (which knows the job's length; the pass does not) asks for waves that shrink towards
         # the end — each 4/5 of what is left, at most the library's wave — instead of one full wave whose read-back is all tail.
         # Every sample is still traced inside the timed region and consumed by exactly one frame (asserted below).
-        schedule, left = [], n_steps
-        while left > 0:
-            schedule.append(min(wave, max(1, -(-4 * left // 5))))
-            left -= schedule[-1]
+        schedule = sharding.wave_schedule(n_steps, wave)
         if args.e2e_waves and sum(int(x) for x in args.e2e_waves.split(",")) == n_steps:
             schedule = [int(x) for x in args.e2e_waves.split(",")]
         e2e_steps = n_steps

@@ -24,6 +24,18 @@ def split_frames(total_frames: int, rank: int, world: int, first: int = 0) -> tu
     return first + rank * base + min(rank, extra), base + (1 if rank < extra else 0)
 
 
+def wave_schedule(frames: int, max_wave: int) -> list[int]:
+    """Sample waves of a FINITE frame-at-a-time job (PathTracingPass with prefetch): the frames of a wave become available together when
+    its last bounce ends, and their images then leave over PCIe while the next wave is traced — only the LAST wave's read-back is exposed.
+    So the waves shrink towards the end: each is 4/5 of what is left (at most `max_wave`, the library's wave size at this resolution).
+    Every frame belongs to exactly one wave; a one-frame job is one wave of one."""
+    out, left = [], int(frames)
+    while left > 0:
+        out.append(min(int(max_wave), max(1, -(-4 * left // 5))))
+        left -= out[-1]
+    return out
+
+
 def frame_index(step: int, steps: int, rank: int, world: int, first: int = 0) -> int:
     """frame_index of the `step`-th frame this rank renders."""
     return first_frame(steps, rank, world, first) + step

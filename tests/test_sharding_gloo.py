@@ -51,6 +51,20 @@ def test_two_rank_sharding_equals_single_process(oracle, tmp_path):
     np.testing.assert_allclose(img, ref, rtol=1e-5, atol=1e-7)
 
 
+def test_wave_schedule_of_a_finite_job():
+    """bench.py's e2e arm: shrinking waves that add up to the job exactly; no wave larger than the library's; the last one is short."""
+    sys.path.insert(0, ROOT)
+    from bisemutum_engine_b200 import sharding
+    assert sharding.wave_schedule(20, 32) == [16, 4]
+    assert sharding.wave_schedule(128, 32) == [32, 32, 32, 26, 5, 1]
+    assert sharding.wave_schedule(1, 32) == [1] and sharding.wave_schedule(0, 32) == []
+    for frames in range(1, 300):
+        for wave in (1, 2, 8, 32):
+            sched = sharding.wave_schedule(frames, wave)
+            assert sum(sched) == frames and all(1 <= w <= wave for w in sched)
+            assert sched == sorted(sched, reverse=True)
+
+
 def test_strong_scaling_split_tiles_the_job():
     """sharding.split_frames (bench.py --scaling strong; BASELINE configs[3]: 64 spp split across 8 GPUs): contiguous blocks that tile the job."""
     from bisemutum_engine_b200 import sharding
