@@ -207,7 +207,8 @@ constexpr int32_t kEmpty = 0x7fffffff;      // no internal node left for this la
 #define BPT_TRACE_MIN_BLOCKS 10
 #endif
 #ifndef BPT_TRACE_MIN_BLOCKS_2L
-#define BPT_TRACE_MIN_BLOCKS_2L 8       // two-level kernels of scenes without any-hit instances (the general ones stay at 8: see above)
+#define BPT_TRACE_MIN_BLOCKS_2L 8       // two-level kernels of scenes without any-hit instances (the general ones stay at 8: see above); final kernels on the
+                                        // instanced scene: 7 blocks (72 registers) 876, 8 (64) 920, 9 (56, 64 B more spills) 867 Mrays/s (profiles/r2am_variants.jsonl)
 #endif
 #ifndef BPT_TRACE_MIN_BLOCKS_WIDE
 #define BPT_TRACE_MIN_BLOCKS_WIDE 10
