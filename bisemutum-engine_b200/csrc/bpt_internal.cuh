@@ -90,6 +90,7 @@ struct bpt_context {
     float sky_color[3] = {1, 1, 1};
 
     // accel
+    uint64_t instanced_triangles = 0;      // sum over the instances of their BLAS's triangles (upload_instance_table): what a camera ray can see
     bool scene_has_anyhit = true;          // some instance needs the any-hit opacity rule (upload_instance_table); false selects the kernels without it
     bool accel_built = false;
     bool bloom_attr_set = false;           // the same opt-in for the bloom level kernels (post.cu)

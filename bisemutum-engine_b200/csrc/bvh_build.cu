@@ -491,6 +491,9 @@ bpt_status lbvh_build(bpt_context* ctx, DevBvh& out, uint32_t n, const float4* d
 bpt_status upload_instance_table(bpt_context* ctx) {
     uint32_t n = (uint32_t)ctx->h_instances.size();
     // the rule of k_make_instances, on the host copies (validated by bpt_build_accel): does ANY instance need the any-hit opacity rule?
+    ctx->instanced_triangles = 0;
+    for (const bpt_instance_desc& in : ctx->h_instances)
+        if (in.blas < ctx->h_blas_desc.size()) ctx->instanced_triangles += ctx->h_blas_desc[in.blas].num_triangles;
     ctx->scene_has_anyhit = false;
     for (const bpt_instance_desc& in : ctx->h_instances) {
         const uint32_t flags = in.sbt_offset_and_flags >> 24, id = in.instance_id_and_mask & 0xffffffu;

@@ -633,6 +633,115 @@ __global__ void __launch_bounds__(kBlock, BPT_PACKET_MIN_BLOCKS) k_trace_packet(
     }
 }
 
+// ---- the same for two-level mode: the packet walks the TLAS with the world-space rays; at an instance the lanes of its mask move their
+//      ray into object space TOGETHER (one instance record for the warp, the three IEEE divisions of make_space at full width instead of
+//      the ~2 lanes an instance entry has in k_trace_spec) and the packet walks that BLAS; a sentinel on the stack brings everybody back
+//      to world space. Binary trees, general box tests (the octant changes with every instance). Candidates per lane = those of its own
+//      binary two-level traversal (= the wide one's, bpt_wide.cuh), hence the same hits. ---------------------------------------------------
+template <bool AH>
+__global__ void __launch_bounds__(kBlock, 8) k_extend_packet_2l(const __grid_constant__ RenderArgs a, uint32_t bounce) {
+    const uint32_t n = a.qcount[QE + bounce];
+    uint32_t* cursor = &a.qcount[QWE + bounce];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kDepth = 2 * kPacketStack;
+    __shared__ int32_t s_node_all[kBlock / 32][kDepth];
+    __shared__ uint32_t s_mask_all[kBlock / 32][kDepth];
+    int32_t* const s_node = s_node_all[warp];
+    uint32_t* const s_mask = s_mask_all[warp];
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t idx = base + lane;
+        const bool valid = idx < n;
+        RayState rs;
+        RaySpace cur;
+        float3 widir, wood;                                   // the world-space ray's 1 / D and O / D (restored when the packet leaves an instance)
+        {
+            float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+            if (valid) { o = __ldcs(a.ray_o_in + idx); d = __ldcs(a.ray_d_in + idx); }
+            const uint32_t path = __float_as_uint(o.w);
+            rs.O = v3(o.x, o.y, o.z); rs.D = v3(d.x, d.y, d.z);
+            rs.tmin = 0.001f; rs.tbest = a.sp.ray_length; rs.tcull = rs.tbest * 1.00001f;
+            rs.best_slot = 0xffffffffu; rs.best_prim = 0xffffffffu; rs.bu = 0.0f; rs.bv = 0.0f;
+            rs.frame_index = a.frame_base + path / a.npx; rs.opacity_u = 0.0f; rs.have_u = false; rs.found = false;
+            rs.cull_non_opaque = false;
+            cur = make_space(rs.O, rs.D);
+            widir = cur.idir; wood = cur.ood;
+        }
+        const float4* nodes = a.sc.tlas_nodes;
+        const float4* tris = nullptr;
+        bool in_blas = false;                                  // warp-uniform
+        uint32_t slot = 0xffffffffu, inst_anyhit = 0u;         // warp-uniform: the instance the packet is inside
+        int sp = 0;
+        int32_t node = a.sc.tlas_n == 0 ? kEmpty : a.sc.tlas_root;
+        uint32_t mask = __ballot_sync(0xffffffffu, valid);
+        auto pop = [&]() {
+            if (sp == 0) { node = kEmpty; return; }
+            --sp; node = s_node[sp]; mask = s_mask[sp];
+        };
+        while (node != kEmpty) {
+            if (node == kSentinel) {                           // the BLAS is done: back to the world-space rays and the TLAS
+                cur.O = rs.O; cur.D = rs.D; cur.idir = widir; cur.ood = wood;
+                nodes = a.sc.tlas_nodes; tris = nullptr; in_blas = false; slot = 0xffffffffu;
+                pop();
+            } else if (node >= 0) {
+                const float4* np = nodes + 4 * (size_t)node;
+                float4 n0, n1, n2, n3;
+                ldg_64B<false>(np, n0, n1, n2, n3);
+                const RaySpace& r = cur;
+                float c0lox = fmaf(n0.x, r.idir.x, -r.ood.x), c0hix = fmaf(n0.y, r.idir.x, -r.ood.x);
+                float c0loy = fmaf(n0.z, r.idir.y, -r.ood.y), c0hiy = fmaf(n0.w, r.idir.y, -r.ood.y);
+                float c1lox = fmaf(n1.x, r.idir.x, -r.ood.x), c1hix = fmaf(n1.y, r.idir.x, -r.ood.x);
+                float c1loy = fmaf(n1.z, r.idir.y, -r.ood.y), c1hiy = fmaf(n1.w, r.idir.y, -r.ood.y);
+                float c0loz = fmaf(n2.x, r.idir.z, -r.ood.z), c0hiz = fmaf(n2.y, r.idir.z, -r.ood.z);
+                float c1loz = fmaf(n2.z, r.idir.z, -r.ood.z), c1hiz = fmaf(n2.w, r.idir.z, -r.ood.z);
+                float t0n = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), rs.tmin));
+                float t0f = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), rs.tcull));
+                float t1n = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), rs.tmin));
+                float t1f = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), rs.tcull));
+                const bool mine = (mask >> lane) & 1u;
+                const bool h0 = mine && t0n <= t0f, h1 = mine && t1n <= t1f;
+                const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+                const int32_t ch0 = (int32_t)f2u(n3.x), ch1 = (int32_t)f2u(n3.y);
+                if ((m0 | m1) == 0u) {
+                    pop();
+                } else if (m0 != 0u && m1 != 0u) {
+                    const uint32_t pref0 = __ballot_sync(0xffffffffu, h0 && (!h1 || t0n <= t1n));
+                    const bool first0 = 2 * __popc(pref0) >= __popc(m0 | m1);
+                    s_node[sp] = first0 ? ch1 : ch0; s_mask[sp] = first0 ? m1 : m0; ++sp;
+                    node = first0 ? ch0 : ch1; mask = first0 ? m0 : m1;
+                } else {
+                    node = m0 != 0u ? ch0 : ch1; mask = m0 | m1;
+                }
+            } else if (!in_blas) {                             // a TLAS leaf: the lanes of `mask` enter the instance
+                slot = __ldg(a.sc.tlas_prims + (uint32_t)~node);
+                const DInstance& in = a.sc.instances[slot];
+                const DBlas bl = a.sc.blas[in.blas];
+                inst_anyhit = in.anyhit;
+                if ((mask >> lane) & 1u) cur = make_space(xf_point(in.w2o, rs.O), xf_vector(in.w2o, rs.D));
+                s_node[sp] = kSentinel; s_mask[sp] = 0u; ++sp;
+                nodes = bl.nodes; tris = bl.tris; in_blas = true;
+                node = bl.n == 0 ? kSentinel : bl.root;        // (an empty BLAS: straight back out)
+                if (bl.n == 0) --sp;
+            } else {                                           // a triangle of the instance
+                if ((mask >> lane) & 1u) {
+                    const float4* tp = tris + 3 * (size_t)(uint32_t)~node;
+                    float4 ta = BPT_LDG(tp), tb = BPT_LDG(tp + 1), tc = BPT_LDG(tp + 2);
+                    test_triangle_rec<false, AH>(a.sc, rs, ta, tb, tc, cur.O, cur.D, slot, inst_anyhit);
+                }
+                pop();
+            }
+        }
+        if (valid) {
+            __stcs(a.hit + idx, make_float4(rs.found ? rs.tbest : -1.0f, rs.bu, rs.bv, __uint_as_float(rs.best_prim)));
+            __stcs(a.hit_slot + idx, rs.best_slot);
+        }
+    }
+}
+static const auto k_extend_packet_2l_a = k_extend_packet_2l<true>;
+static const auto k_extend_packet_2l_o = k_extend_packet_2l<false>;
 static const auto k_extend_packet = k_trace_packet<false, true>;
 static const auto k_extend_packet_o = k_trace_packet<false, false>;
 static const auto k_connect_packet = k_trace_packet<true, true>;
@@ -1155,12 +1264,24 @@ static unsigned resident_grid(bpt_context* ctx, K kernel) {
 }
 // BPT_SPECIALISE=0 launches the general kernels everywhere (A/B measurements)
 static bool specialise_opaque() { static const bool on = [] { const char* e = getenv("BPT_SPECIALISE"); return !e || atoi(e) != 0; }(); return on; }
-// BPT_PACKET (default 1): bit 0 = the camera rays walk the tree as packets (k_trace_packet), bit 1 = so do the shadow rays of their hit points
-// (measured: slower, off); 0 = everything through k_trace_spec (merged mode only)
-static uint32_t packet_mode() { static const uint32_t m = [] { const char* e = getenv("BPT_PACKET"); return e ? (uint32_t)atoi(e) : 1u; }(); return m; }
+// Camera rays as packets (k_trace_packet in merged mode, k_extend_packet_2l in two-level mode) pay when a pixel tile's rays really share
+// their nodes, i.e. when triangles are not much smaller than pixels: configs[1] (262 k triangles at 1080p: 0.13 per pixel) +6 %, the same
+// atrium in two-level mode 1 816 -> 2 011 Mrays/s, but configs[3] (2 M x 512 instanced triangles at 4K: 129 per pixel) 924 -> 782
+// (profiles/r2an_variants.jsonl). Default: packets iff the instanced triangle count is at most twice the pixel count.
+// BPT_PACKET overrides (A/B runs): bit 0 = merged-mode camera rays, bit 1 = the shadow rays of their hit points (measured: slower),
+// bit 4 = two-level camera rays; 0 = everything through k_trace_spec.
+static uint32_t packet_mode(const bpt_context* ctx) {
+    static const int forced = [] { const char* e = getenv("BPT_PACKET"); return e ? atoi(e) : -1; }();
+    if (forced >= 0) return (uint32_t)forced;
+    return ctx->instanced_triangles <= 2ull * ctx->width * ctx->height ? 17u : 0u;
+}
 static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
-    if (i == 1 && a.camera_paths && (packet_mode() & 1u) && ctx->accel_mode == BPT_ACCEL_MERGED) {
+    if (i == 1 && a.camera_paths && (packet_mode(ctx) & 16u) && ctx->accel_mode == BPT_ACCEL_TWO_LEVEL) {
+        if (ah) LAUNCH_T(ctx, 1, k_extend_packet_2l_a, resident_grid(ctx, k_extend_packet_2l_a), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_packet_2l_o, resident_grid(ctx, k_extend_packet_2l_o), kBlock, a, i);
+        return BPT_OK;
+    }
+    if (i == 1 && a.camera_paths && (packet_mode(ctx) & 1u) && ctx->accel_mode == BPT_ACCEL_MERGED) {
         if (ah) LAUNCH_T(ctx, 1, k_extend_packet, resident_grid(ctx, k_extend_packet), kBlock, a, i); else LAUNCH_T(ctx, 1, k_extend_packet_o, resident_grid(ctx, k_extend_packet_o), kBlock, a, i);
         return BPT_OK;
     }
@@ -1172,7 +1293,7 @@ static bpt_status launch_extend(bpt_context* ctx, const RenderArgs& a, uint32_t 
 }
 static bpt_status launch_connect(bpt_context* ctx, const RenderArgs& a, uint32_t i) {
     const bool ah = ctx->scene_has_anyhit || !specialise_opaque();
-    if (i == 1 && a.camera_paths && (packet_mode() & 2u) && ctx->accel_mode == BPT_ACCEL_MERGED) {
+    if (i == 1 && a.camera_paths && (packet_mode(ctx) & 2u) && ctx->accel_mode == BPT_ACCEL_MERGED) {
         if (ah) LAUNCH_T(ctx, 3, k_connect_packet, resident_grid(ctx, k_connect_packet), kBlock, a, i); else LAUNCH_T(ctx, 3, k_connect_packet_o, resident_grid(ctx, k_connect_packet_o), kBlock, a, i);
         return BPT_OK;
     }
